@@ -1,0 +1,244 @@
+/*
+ * smenv.h -- C ABI of the B200-native SafeMotions environment step ("libsmenv.so").
+ *
+ * This is the drop-in boundary of the hot path.  Every entry point replaces a piece of the
+ * reference's gym.Env surface for N independent environments at once:
+ *
+ *   smenv_create / smenv_destroy   <- SafeMotionsBase.__init__ / close()          (safe_motions_base.py:85, :1487)
+ *   smenv_set_state                <- the injected start state of reset()          (safe_motions_base.py:913-1022,
+ *                                     collision_torque_limit_prevention.py:1461-1656, parity protocol SURVEY 8c)
+ *   smenv_fill_pools               <- get_starting_point_joint_pos_vel_acc + Planet.reset + _add_moving_object
+ *                                     (ctlp.py:1461-1656, :4470-4501, :1723-1931) as device-side rejection sampling
+ *   smenv_reset                    <- SafeObservation.reset()                       (observations.py:144-187)
+ *   smenv_step                     <- SafeMotionsBase.step()                        (safe_motions_base.py:1043-1227)
+ *   smenv_safe_range               <- _calculate_safe_acc_range()                   (actions.py:206-211)
+ *   smenv_distances                <- get_minimum_distance(+_to_moving_obstacles)   (ctlp.py:3217-3374)
+ *
+ * Conventions: plain pointers and sizes only, no torch types.  All device pointers are caller-owned (the Python host
+ * allocates them as torch CUDA tensors); the library owns only the read-only scene constants it uploads in
+ * smenv_create.  Every call is stream-ordered on the caller's cudaStream_t and returns 0 on success or a negative
+ * SmStatus; smenv_last_error() gives the message.  Nothing in this library has a CPU fallback.
+ */
+#ifndef SMENV_H
+#define SMENV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SM_MAX_JOINTS 8
+#define SM_MAX_SHAPES 96
+#define SM_MAX_OBSTACLES 2
+#define SM_MAX_PAIRS 48
+#define SM_MAX_MOV_ROBOT 24
+#define SM_MAX_OBS 64
+#define SM_KIN_STRIDE 32  /* doubles per env in the kinematic record: q[8] v[8] a[8] q_act[8] */
+#define SM_OBST_STRIDE 16 /* doubles per env in the obstacle record */
+#define SM_INFO_STRIDE 16 /* floats per env in the step-info record */
+
+enum SmStatus { SM_OK = 0, SM_ERR_ARG = -1, SM_ERR_CUDA = -2, SM_ERR_SCENE = -3, SM_ERR_STATE = -4 };
+enum SmObstacleKind { SM_OBST_NONE = 0, SM_OBST_PLANET = 1, SM_OBST_BALL = 2 };
+
+/* Termination reasons: SafeMotionsBase.TERMINATION_* (safe_motions_base.py:64-70). */
+enum SmTermination {
+    SM_TERM_UNSET = -1,
+    SM_TERM_JOINT_LIMITS = 1,
+    SM_TERM_TRAJECTORY_LENGTH = 2,
+    SM_TERM_SELF_COLLISION = 3,
+    SM_TERM_STATIC_COLLISION = 4,
+    SM_TERM_MOVING_COLLISION = 5
+};
+
+/* Slots of the per-env float info record written by smenv_step (SM_INFO_STRIDE floats per env). */
+enum SmInfoSlot {
+    SM_INFO_D_STATIC = 0,       /* min distance to static obstacles after the <1 mm clamp (rewards.py:115-117) */
+    SM_INFO_D_SELF = 1,         /* idem self collision (rewards.py:119-121) */
+    SM_INFO_D_MOVING = 2,       /* idem moving obstacles (rewards.py:153-155) */
+    SM_INFO_COLL_STATIC = 3,    /* collision_rate_static_obstacles (safe_motions_base.py:1350-1355) */
+    SM_INFO_COLL_SELF = 4,
+    SM_INFO_COLL_MOVING = 5,
+    SM_INFO_ACTION_PUNISH = 6,  /* rewards.py:164-169 */
+    SM_INFO_R_STATIC = 7,       /* static_obstacles_collision_reward (rewards.py:128-131) */
+    SM_INFO_R_SELF = 8,
+    SM_INFO_R_MOVING = 9,
+    SM_INFO_EPISODE_LENGTH = 10,
+    SM_INFO_EPISODE_RETURN = 11,
+    SM_INFO_RANGE_CODE = 12,    /* OR of the per-joint violation codes of the range used for this step */
+    SM_INFO_CONTACT_LATCH = 13, /* 1 if a sub-step contact with a moving obstacle was latched (ctlp.py:2631-2637) */
+    SM_INFO_MAX_JERK_REL = 14,  /* max_j |jerk_j| / jerk_max_j of the step (rewards.py:181-203) */
+    SM_INFO_RESERVED = 15
+};
+
+/* Slots of the per-env obstacle record (SM_OBST_STRIDE doubles per env; integers are stored exactly as doubles). */
+enum SmObstSlot {
+    SM_OB_INDEX = 0,        /* planets: current_time_step_index of planet one (planet two is phase-coupled,
+                               ctlp.py:4470-4531); ball: position_update_step_counter (ctlp.py:4103-4105) */
+    SM_OB_LATCH = 1,        /* latched contact: Planet._collision_detected / Ball final state HIT_ROBOT */
+    SM_OB_BALL_P0 = 2,      /* release point xyz (ctlp.py:1933-1954) */
+    SM_OB_BALL_V0 = 5,      /* initial speed vector xyz (ctlp.py:1792-1809) */
+    SM_OB_BALL_EULER0 = 8,  /* initial orientation as euler xyz (ctlp.py:4029-4034) */
+    SM_OB_BALL_OMEGA = 11,  /* angular velocity of euler-y in rad/s (ctlp.py:4056-4057) */
+    SM_OB_BALL_T = 12,      /* accumulated flight time self._t (ctlp.py:4105) */
+    SM_OB_BALL_ACTIVE = 13, /* moving_object_active_list[0] (ctlp.py:2836-2861) */
+    SM_OB_BALL_NMAX = 14,   /* max_time_update_step_counter (ctlp.py:4101) */
+    SM_OB_BALL_NHIT = 15    /* obstacle_hit_time (ctlp.py:1889-1917) */
+};
+
+typedef struct SmShape {
+    int32_t frame;    /* 0 = world, 1..n_joints = robot link frame of joint (frame-1), 100+k = obstacle k */
+    int32_t vert_off; /* first vertex in SmScene.verts */
+    int32_t vert_cnt;
+    int32_t link;     /* URDF link index of the robot link carrying the shape, -1 for obstacles */
+    double margin;    /* Bullet collision margin subtracted from the core distance (1 mm for URDF shapes) */
+    double center[3]; /* bounding sphere of the core vertices, in frame coordinates */
+    double radius;
+} SmShape;
+
+/*
+ * Scene constants for one env configuration.  Built on the host by safemotionsrisk_b200/scene.py from the compiled
+ * URDF/mesh assets and the reference's env_config keys; uploaded once per smenv_create.
+ */
+typedef struct SmScene {
+    /* --- kinematics: frame f = 1+j is the URDF child link of revolute joint j */
+    int32_t n_joints;
+    int32_t joint_parent[SM_MAX_JOINTS]; /* parent frame (0 = world) */
+    double joint_R[SM_MAX_JOINTS][9];    /* fixed rotation parent frame -> joint frame (row major) */
+    double joint_t[SM_MAX_JOINTS][3];
+    double joint_axis[SM_MAX_JOINTS][3];
+    /* --- limits (robot_scene_base.py:20-22, :347-371, :441-455) */
+    double pos_lo[SM_MAX_JOINTS], pos_hi[SM_MAX_JOINTS];
+    double vel_max[SM_MAX_JOINTS], acc_max[SM_MAX_JOINTS], jerk_max[SM_MAX_JOINTS];
+    double ts;            /* trajectory_time_step */
+    int32_t substeps;     /* obstacle_client_update_steps_per_action = round(ts / (1/240)) */
+    int32_t limit_velocity, limit_position; /* actions.py:31-32 */
+    double action_mapping_factor;           /* actions.py:35, :271-276 */
+    /* --- motor tracking model of the simulation client (robot_scene_base.py:789-805) */
+    double track_kp;      /* 0.1: PyBullet default positionGain */
+    double track_vel;     /* 0.87 with use_controller_target_velocities, else 0 */
+    int32_t contact_stride; /* test contacts every contact_stride sub-steps (1 = every 1/240 s as the reference) */
+    int32_t reserved0;
+    /* --- collision geometry */
+    int32_t n_shapes;
+    int32_t n_verts;
+    SmShape shapes[SM_MAX_SHAPES];
+    const double* verts; /* n_verts x 3, host pointer */
+    int32_t n_static_pairs;
+    int32_t static_pairs[SM_MAX_PAIRS][2]; /* (robot shape, static obstacle shape) */
+    int32_t n_self_pairs;
+    int32_t self_pairs[SM_MAX_PAIRS][2];
+    int32_t n_mov_reward;                    /* robot shapes observed for the moving-obstacle distance */
+    int32_t mov_reward[SM_MAX_MOV_ROBOT];
+    int32_t n_mov_contact;                   /* robot shapes that can make contact in the simulation client */
+    int32_t mov_contact[SM_MAX_MOV_ROBOT];
+    /* --- moving obstacles */
+    int32_t n_obstacles;
+    int32_t obst_kind[SM_MAX_OBSTACLES];
+    int32_t obst_shape_off[SM_MAX_OBSTACLES], obst_shape_cnt[SM_MAX_OBSTACLES];
+    double obst_center[SM_MAX_OBSTACLES][3]; /* bounding sphere of the whole obstacle body (incl. margins) */
+    double obst_radius[SM_MAX_OBSTACLES];
+    double contact_thresh[SM_MAX_OBSTACLES][SM_MAX_MOV_ROBOT]; /* manifold contact-breaking threshold per link */
+    /* planets */
+    int32_t planet_steps;                         /* table length (1200) */
+    int32_t planet_shift;                         /* time_step_index_shift of planet two (ctlp.py:4435-4437) */
+    const double* planet_pos[SM_MAX_OBSTACLES];   /* planet_steps x 3 */
+    const double* planet_quat[SM_MAX_OBSTACLES];  /* planet_steps x 4 (xyzw) */
+    const double* planet_local_xy;                /* planet_steps x 2, planet one, for the observation */
+    double planet_obs_half[2];                    /* 1.05 * radius_xy (observations.py:280-288) */
+    int32_t obs_planet_size;                      /* obs_planet_size_per_planet: 1 or 2 */
+    int32_t reserved1;
+    /* ball */
+    double ball_obs_pos_min[3], ball_obs_pos_max[3]; /* ctlp.py:303-333 */
+    double ball_obs_vel_min[3], ball_obs_vel_max[3]; /* ctlp.py:335-348 */
+    double ball_active_xy;                           /* 1.25 m (ctlp.py:2830) */
+    /* --- distances / reward (rewards.py:95-169, :432-502) */
+    double static_cap;       /* closest_point_maximum_relevant_distance (ctlp.py:354-366) */
+    double moving_query;     /* query distance for moving obstacles (rewards.py:142-151) */
+    double collision_dist;   /* 0.001 */
+    double w_self, w_static, w_moving;
+    double d_self, d_static, d_moving;
+    double w_low_acc, thr_low_acc, w_low_vel, thr_low_vel;
+    int32_t punish_action;
+    int32_t terminate_self, terminate_static, terminate_moving;
+    double action_thresh, action_max_punishment;
+    double termination_bonus, early_termination_punishment;
+    int32_t episode_steps;   /* round(trajectory_duration / ts) (trajectory_manager.py:87, :187-192) */
+    int32_t obs_size;
+    /* --- start-state sampling (ctlp.py:171-183, :1461-1656) */
+    double start_box_min[3], start_box_max[3];
+    double target_offset[3];   /* target_link_offset in the frame of the last joint (after the fixed EE transform) */
+    double target_R[9], target_t[3]; /* fixed transform last joint frame -> target link frame */
+    double kinematic_sampling_probability, stay_in_state_probability;
+    double min_start_distance;  /* 0.001 in collision-avoidance mode */
+    /* ball launch (ctlp.py:1723-1954) */
+    double ball_sphere_center[3], ball_sphere_radius, ball_height_min, ball_height_max, ball_angle_min, ball_angle_max;
+    double ball_speed, ball_radius, ball_high_angle_probability;
+    double ball_target_box_min[3], ball_target_box_max[3];   /* target_point_cartesian_range */
+    double ball_invalid_min[3], ball_invalid_max[3];         /* invalid target link point area */
+    double ball_final_min[3], ball_final_max[3];             /* final_ball_position_min_max */
+    double plane_z;                                          /* plane_z_offset */
+    int32_t ball_check_invalid, ball_random_initial;
+} SmScene;
+
+/* Device buffers of one call (all caller-owned, N = num_envs). */
+typedef struct SmBuffers {
+    double* kin;          /* [N][SM_KIN_STRIDE]  q, v, a, q_act */
+    double* obst;         /* [N][SM_OBST_STRIDE] */
+    int32_t* episode;     /* [N][4]  episode_length, reset_count, reserved, reserved */
+    double* ep_return;    /* [N] running episode return */
+    const float* actions; /* [N][n_joints] in [-1, 1] */
+    float* obs;           /* [N][obs_size] */
+    float* reward;        /* [N] */
+    uint8_t* done;        /* [N] */
+    int32_t* term_reason; /* [N] */
+    float* info;          /* [N][SM_INFO_STRIDE] */
+    double* stats;        /* [32] episode statistics accumulated with atomics (train.py:59-117); may be NULL */
+} SmBuffers;
+
+typedef struct SmCounters {
+    unsigned long long gjk_calls, gjk_iters, support_dots, culled_pairs, env_steps, contact_tests;
+} SmCounters;
+
+typedef struct SmEnv SmEnv;
+typedef void* SmStream; /* cudaStream_t */
+
+const char* smenv_last_error(void);
+int smenv_abi_version(void);
+int smenv_sizeof_scene(void);
+int smenv_sizeof_shape(void);
+
+int smenv_create(const SmScene* scene, int num_envs, int device, uint64_t seed, SmEnv** out);
+int smenv_destroy(SmEnv* env);
+
+/* Start-state / ball pools, sampled on the device (rejection sampling with Philox). */
+int smenv_pool_sizes(SmEnv* env, int* start_pool, int* ball_pool);
+int smenv_fill_pools(SmEnv* env, uint64_t seed, SmStream stream);
+int smenv_pool_ptrs(SmEnv* env, double** start_pool, double** ball_pool);
+
+/* Injects a start state (parity protocol).  Host or device pointers are both accepted; mask==NULL means all envs. */
+int smenv_set_state(SmEnv* env, const SmBuffers* buf, const double* q, const double* v, const double* a,
+                    const double* obst, const uint8_t* mask, SmStream stream);
+/* Resets the masked envs (NULL = all) from the pools and writes their first observation. */
+int smenv_reset(SmEnv* env, const SmBuffers* buf, const uint8_t* mask, SmStream stream);
+/* One env step for all N envs.  auto_reset != 0 re-initialises finished envs from the pools inside the same launch
+ * (obs is then the first observation of the new episode; done/reward/info describe the finished step). */
+int smenv_step(SmEnv* env, const SmBuffers* buf, int auto_reset, SmStream stream);
+/* Same launch with device-generated U(-1,1) actions (get_random_action, safe_motions_base.py:1327-1328). */
+int smenv_step_random(SmEnv* env, const SmBuffers* buf, int auto_reset, SmStream stream);
+
+/* Pieces of the step exposed for parity tests. */
+int smenv_safe_range(SmEnv* env, const double* kin, double* range_lo, double* range_hi, int32_t* code, int n,
+                     SmStream stream);
+int smenv_distances(SmEnv* env, const double* kin, const double* obst, float* d_static, float* d_self,
+                    float* d_moving, int n, SmStream stream);
+int smenv_observation(SmEnv* env, const SmBuffers* buf, SmStream stream);
+
+int smenv_counters(SmEnv* env, SmCounters* out, int reset);
+int smenv_enable_counters(SmEnv* env, int enable);
+int smenv_launch_count(SmEnv* env, unsigned long long* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMENV_H */

@@ -1,0 +1,126 @@
+"""ctypes mirror of ``include/smenv.h`` (the C ABI of libsmenv.so).
+
+The field order and sizes must match the header exactly; ``tests/test_abi.py`` checks ``ctypes.sizeof`` against
+``smenv_sizeof_scene()`` / ``smenv_sizeof_shape()`` and that every symbol the header declares is exported.
+"""
+import ctypes as C
+
+SM_MAX_JOINTS = 8
+SM_MAX_SHAPES = 96
+SM_MAX_OBSTACLES = 2
+SM_MAX_PAIRS = 48
+SM_MAX_MOV_ROBOT = 24
+SM_KIN_STRIDE = 32
+SM_OBST_STRIDE = 16
+SM_INFO_STRIDE = 16
+
+SM_OBST_NONE, SM_OBST_PLANET, SM_OBST_BALL = 0, 1, 2
+
+# termination reasons (safe_motions_base.py:64-70)
+TERMINATION_UNSET = -1
+TERMINATION_SUCCESS = 0
+TERMINATION_JOINT_LIMITS = 1
+TERMINATION_TRAJECTORY_LENGTH = 2
+TERMINATION_SELF_COLLISION = 3
+TERMINATION_COLLISION_WITH_STATIC_OBSTACLE = 4
+TERMINATION_COLLISION_WITH_MOVING_OBSTACLE = 5
+
+INFO_SLOTS = ["d_static", "d_self", "d_moving", "coll_static", "coll_self", "coll_moving", "action_punishment",
+              "r_static", "r_self", "r_moving", "episode_length", "episode_return", "range_code", "contact_latch",
+              "max_jerk_rel", "reserved"]
+INFO = {name: i for i, name in enumerate(INFO_SLOTS)}
+
+OB_INDEX, OB_LATCH, OB_BALL_P0, OB_BALL_V0, OB_BALL_EULER0, OB_BALL_OMEGA, OB_BALL_T, OB_BALL_ACTIVE, \
+    OB_BALL_NMAX, OB_BALL_NHIT = 0, 1, 2, 5, 8, 11, 12, 13, 14, 15
+
+d, i32 = C.c_double, C.c_int32
+dp = C.POINTER(C.c_double)
+
+
+class SmShape(C.Structure):
+    _fields_ = [("frame", i32), ("vert_off", i32), ("vert_cnt", i32), ("link", i32), ("margin", d),
+                ("center", d * 3), ("radius", d)]
+
+
+class SmScene(C.Structure):
+    _fields_ = [
+        ("n_joints", i32),
+        ("joint_parent", i32 * SM_MAX_JOINTS),
+        ("joint_R", (d * 9) * SM_MAX_JOINTS),
+        ("joint_t", (d * 3) * SM_MAX_JOINTS),
+        ("joint_axis", (d * 3) * SM_MAX_JOINTS),
+        ("pos_lo", d * SM_MAX_JOINTS), ("pos_hi", d * SM_MAX_JOINTS),
+        ("vel_max", d * SM_MAX_JOINTS), ("acc_max", d * SM_MAX_JOINTS), ("jerk_max", d * SM_MAX_JOINTS),
+        ("ts", d),
+        ("substeps", i32),
+        ("limit_velocity", i32), ("limit_position", i32),
+        ("action_mapping_factor", d),
+        ("track_kp", d), ("track_vel", d),
+        ("contact_stride", i32), ("reserved0", i32),
+        ("n_shapes", i32), ("n_verts", i32),
+        ("shapes", SmShape * SM_MAX_SHAPES),
+        ("verts", dp),
+        ("n_static_pairs", i32), ("static_pairs", (i32 * 2) * SM_MAX_PAIRS),
+        ("n_self_pairs", i32), ("self_pairs", (i32 * 2) * SM_MAX_PAIRS),
+        ("n_mov_reward", i32), ("mov_reward", i32 * SM_MAX_MOV_ROBOT),
+        ("n_mov_contact", i32), ("mov_contact", i32 * SM_MAX_MOV_ROBOT),
+        ("n_obstacles", i32),
+        ("obst_kind", i32 * SM_MAX_OBSTACLES),
+        ("obst_shape_off", i32 * SM_MAX_OBSTACLES), ("obst_shape_cnt", i32 * SM_MAX_OBSTACLES),
+        ("obst_center", (d * 3) * SM_MAX_OBSTACLES),
+        ("obst_radius", d * SM_MAX_OBSTACLES),
+        ("contact_thresh", (d * SM_MAX_MOV_ROBOT) * SM_MAX_OBSTACLES),
+        ("planet_steps", i32), ("planet_shift", i32),
+        ("planet_pos", dp * SM_MAX_OBSTACLES),
+        ("planet_quat", dp * SM_MAX_OBSTACLES),
+        ("planet_local_xy", dp),
+        ("planet_obs_half", d * 2),
+        ("obs_planet_size", i32), ("reserved1", i32),
+        ("ball_obs_pos_min", d * 3), ("ball_obs_pos_max", d * 3),
+        ("ball_obs_vel_min", d * 3), ("ball_obs_vel_max", d * 3),
+        ("ball_active_xy", d),
+        ("static_cap", d), ("moving_query", d), ("collision_dist", d),
+        ("w_self", d), ("w_static", d), ("w_moving", d),
+        ("d_self", d), ("d_static", d), ("d_moving", d),
+        ("w_low_acc", d), ("thr_low_acc", d), ("w_low_vel", d), ("thr_low_vel", d),
+        ("punish_action", i32),
+        ("terminate_self", i32), ("terminate_static", i32), ("terminate_moving", i32),
+        ("action_thresh", d), ("action_max_punishment", d),
+        ("termination_bonus", d), ("early_termination_punishment", d),
+        ("episode_steps", i32), ("obs_size", i32),
+        ("start_box_min", d * 3), ("start_box_max", d * 3),
+        ("target_offset", d * 3),
+        ("target_R", d * 9), ("target_t", d * 3),
+        ("kinematic_sampling_probability", d), ("stay_in_state_probability", d),
+        ("min_start_distance", d),
+        ("ball_sphere_center", d * 3), ("ball_sphere_radius", d),
+        ("ball_height_min", d), ("ball_height_max", d), ("ball_angle_min", d), ("ball_angle_max", d),
+        ("ball_speed", d), ("ball_radius", d), ("ball_high_angle_probability", d),
+        ("ball_target_box_min", d * 3), ("ball_target_box_max", d * 3),
+        ("ball_invalid_min", d * 3), ("ball_invalid_max", d * 3),
+        ("ball_final_min", d * 3), ("ball_final_max", d * 3),
+        ("plane_z", d),
+        ("ball_check_invalid", i32), ("ball_random_initial", i32),
+    ]
+
+
+class SmBuffers(C.Structure):
+    _fields_ = [
+        ("kin", C.c_void_p), ("obst", C.c_void_p), ("episode", C.c_void_p), ("ep_return", C.c_void_p),
+        ("actions", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p),
+        ("term_reason", C.c_void_p), ("info", C.c_void_p), ("stats", C.c_void_p),
+    ]
+
+
+class SmCounters(C.Structure):
+    _fields_ = [("gjk_calls", C.c_ulonglong), ("gjk_iters", C.c_ulonglong), ("support_dots", C.c_ulonglong),
+                ("culled_pairs", C.c_ulonglong), ("env_steps", C.c_ulonglong), ("contact_tests", C.c_ulonglong)]
+
+
+# every extern "C" symbol include/smenv.h declares
+EXPORTED_SYMBOLS = [
+    "smenv_last_error", "smenv_abi_version", "smenv_sizeof_scene", "smenv_sizeof_shape", "smenv_create",
+    "smenv_destroy", "smenv_pool_sizes", "smenv_fill_pools", "smenv_pool_ptrs", "smenv_set_state", "smenv_reset",
+    "smenv_step", "smenv_step_random", "smenv_safe_range", "smenv_distances", "smenv_observation",
+    "smenv_counters", "smenv_enable_counters", "smenv_launch_count",
+]

@@ -1,0 +1,146 @@
+"""Environment configuration: the reference's ``env_config`` keyword surface.
+
+Mirrors the constructor keywords of the reference env stack (``SafeMotionsBase.__init__`` safe_motions_base.py:85-207,
+``AccelerationPredictionBoundedJerkAccVelPos.__init__`` actions.py:29-44, ``RewardBase`` / ``CollisionAvoidanceReward``
+rewards.py:40-54, :409-417, ``SafeObservation`` observations.py:46-49) with the same names and defaults, so a
+``params.json`` of a reference checkpoint can be passed unchanged.  Unknown keys are swallowed exactly like the
+reference's ``**kwargs`` (safe_motions_base.py:207).  Keys that select parts of the reference
+this package does not implement raise ``NotImplementedError`` instead of being silently ignored.
+"""
+import json
+
+# name -> default, taken from the reference signatures cited above
+_DEFAULTS = dict(
+    experiment_name="smenv",
+    # limits / timing
+    pos_limit_factor=1.0, vel_limit_factor=1.0, acc_limit_factor=1.0, jerk_limit_factor=1.0, torque_limit_factor=1.0,
+    acceleration_after_max_vel_limit_factor=0.01,
+    trajectory_duration=8.0, trajectory_time_step=0.1,
+    limit_velocity=True, limit_position=True, set_velocity_after_max_pos_to_zero=True,
+    action_preprocessing_function=None, action_mapping_factor=1.0,
+    # scene
+    robot_scene=0, obstacle_scene=0, ball_machine_mode=False, use_controller_target_velocities=False,
+    collision_check_time=None, closest_point_safety_distance=0.1, starting_point_cartesian_range_scene=0,
+    target_link_name=None, target_link_offset=None, no_self_collision=False,
+    # planets
+    planet_mode=False, planet_one_center=None, planet_one_radius_xy=None, planet_one_euler_angles=None,
+    planet_one_period=None, planet_two_center=None, planet_two_radius_xy=None, planet_two_euler_angles=None,
+    planet_two_period=None, planet_two_time_shift=None, obs_planet_size_per_planet=1,
+    # balls
+    use_moving_objects=False, moving_object_sequence=0, moving_object_area_center=None,
+    moving_object_area_width_height=None, moving_object_sphere_center=None, moving_object_sphere_radius=None,
+    moving_object_sphere_height_min_max=None, moving_object_sphere_angle_min_max=None,
+    moving_object_speed_meter_per_second=1.0, moving_object_aim_at_current_robot_position=False,
+    moving_object_check_invalid_target_link_point_positions=False, moving_object_active_number_single=1,
+    moving_object_random_initial_position=False, moving_object_high_launch_angle_probability=1.0,
+    target_point_cartesian_range_scene=0,
+    # human
+    human_network_checkpoint=None,
+    # termination / collision avoidance mode
+    terminate_on_self_collision=False, terminate_on_collision_with_static_obstacle=False,
+    terminate_on_collision_with_moving_obstacle=False,
+    collision_avoidance_mode=False, collision_avoidance_kinematic_state_sampling_mode=False,
+    collision_avoidance_kinematic_state_sampling_probability=1.0, collision_avoidance_stay_in_state_probability=0.3,
+    # rewards
+    punish_action=False, action_punishment_min_threshold=0.9, action_max_punishment=1.0,
+    collision_avoidance_self_collision_max_reward=0.0, collision_avoidance_self_collision_max_reward_distance=0.05,
+    collision_avoidance_static_obstacles_max_reward=0.0,
+    collision_avoidance_static_obstacles_max_reward_distance=0.1,
+    collision_avoidance_moving_obstacles_max_reward=0.0,
+    collision_avoidance_moving_obstacles_max_reward_distance=0.30,
+    collision_avoidance_low_acceleration_max_reward=1.0, collision_avoidance_low_acceleration_threshold=0.1,
+    collision_avoidance_low_velocity_max_reward=1.0, collision_avoidance_low_velocity_threshold=0.1,
+    collision_avoidance_episode_termination_bonus=0.0, collision_avoidance_episode_early_termination_punishment=-0.0,
+    normalize_reward_to_frequency=False,
+    # braking-trajectory method and target points: not part of the hot path this package implements
+    check_braking_trajectory_collisions=False, check_braking_trajectory_torque_limits=False,
+    use_target_points=False, risk_config_dir=None, risk_config=None, risk_threshold=None,
+    # misc accepted-and-ignored (rendering, logging, real robot)
+    use_gui=False, render_video=False, use_real_robot=False, seed=None, random_agent=False, logging_level="WARNING",
+    solver_iterations=None, episodes_per_simulation_reset=None, log_obstacle_data=False,
+    # extension of this package: test contacts every n-th 1/240 s sub-step (1 = reference behaviour)
+    contact_check_stride=1,
+)
+
+_UNSUPPORTED_TRUE = ["check_braking_trajectory_collisions", "check_braking_trajectory_torque_limits",
+                     "use_real_robot", "moving_object_aim_at_current_robot_position"]
+
+
+class EnvConfig(dict):
+    """Dict of the recognised env_config keys with reference defaults filled in (attribute access allowed)."""
+
+    def __init__(self, **kwargs):
+        super().__init__(_DEFAULTS)
+        self.ignored = {}
+        for key, value in kwargs.items():
+            if key in _DEFAULTS:
+                self[key] = value
+            else:
+                self.ignored[key] = value  # swallowed like the reference's **kwargs
+        for key in _UNSUPPORTED_TRUE:
+            if self[key]:
+                raise NotImplementedError("env_config key '{}' selects a part of the reference outside the hot path "
+                                          "implemented here (see DESIGN.md, out of scope)".format(key))
+        if self["robot_scene"] != 0:
+            raise NotImplementedError("only robot_scene=0 (one iiwa7) is implemented; the reference itself defines "
+                                      "only robot_scene 0 and 9 (robot_scene_base.py:169-183)")
+        if self["moving_object_sequence"] != 0 and self["use_moving_objects"]:
+            raise NotImplementedError("moving_object_sequence != 0 is not implemented")
+        if self["trajectory_time_step"] <= 0:
+            raise ValueError("trajectory_time_step must be positive")
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name)
+
+    @classmethod
+    def from_params_json(cls, path, **overrides):
+        """Loads the ``env_config`` of a reference checkpoint's params.json (evaluate.py:452-639)."""
+        with open(path) as f:
+            params = json.load(f)
+        cfg = dict(params.get("env_config", params))
+        cfg.update(overrides)
+        return cls(**cfg)
+
+
+# README.md:74 / :81 training commands and trained_networks/backup_networks/*/params.json
+_BACKUP_COMMON = dict(
+    acc_limit_factor=1.0, action_max_punishment=0.4, action_punishment_min_threshold=0.95,
+    closest_point_safety_distance=0.01, collision_avoidance_episode_early_termination_punishment=-15.0,
+    collision_avoidance_episode_termination_bonus=15.0, collision_avoidance_kinematic_state_sampling_mode=True,
+    collision_avoidance_kinematic_state_sampling_probability=0.7,
+    collision_avoidance_low_acceleration_max_reward=0.0, collision_avoidance_low_acceleration_threshold=1.0,
+    collision_avoidance_low_velocity_max_reward=0.0, collision_avoidance_low_velocity_threshold=1.0,
+    collision_avoidance_mode=True, collision_avoidance_moving_obstacles_max_reward_distance=0.6,
+    collision_avoidance_moving_obstacles_max_reward=3.0, collision_avoidance_self_collision_max_reward_distance=0.05,
+    collision_avoidance_self_collision_max_reward=1.0, collision_avoidance_static_obstacles_max_reward_distance=0.1,
+    collision_avoidance_static_obstacles_max_reward=1.0, collision_avoidance_stay_in_state_probability=0.3,
+    collision_check_time=0.033, jerk_limit_factor=1.0, obstacle_scene=5, pos_limit_factor=1.0, punish_action=True,
+    robot_scene=0, solver_iterations=50, starting_point_cartesian_range_scene=1,
+    terminate_on_collision_with_moving_obstacle=True, terminate_on_collision_with_static_obstacle=True,
+    terminate_on_self_collision=True, trajectory_duration=2.0, trajectory_time_step=0.1,
+    use_controller_target_velocities=True, vel_limit_factor=1.0,
+)
+
+
+def space_backup_config(**overrides):
+    """The Space backup-policy env of README.md:74 (BASELINE.json configs[0])."""
+    cfg = dict(_BACKUP_COMMON, experiment_name="backup_space", obs_planet_size_per_planet=2, planet_mode=True,
+               planet_one_center=[-0.1, 0.0, 0.8], planet_one_euler_angles=[0.35, 0, 0], planet_one_period=5.0,
+               planet_one_radius_xy=[0.65, 0.8], planet_two_center=[-0.1, 0, 0.8],
+               planet_two_euler_angles=[-0.35, 0, 0], planet_two_radius_xy=[0.75, 0.8], planet_two_time_shift=-2.0)
+    cfg.update(overrides)
+    return EnvConfig(**cfg)
+
+
+def ball_backup_config(**overrides):
+    """The Ball backup-policy env of README.md:81 (BASELINE.json configs[1])."""
+    cfg = dict(_BACKUP_COMMON, experiment_name="backup_ball", moving_object_sphere_center=[0, 0, 0.5],
+               moving_object_sphere_radius=2.5, moving_object_sphere_height_min_max=[-0.5, 0.5],
+               moving_object_sphere_angle_min_max=[0, 6.2831], moving_object_speed_meter_per_second=6.0,
+               moving_object_check_invalid_target_link_point_positions=True,
+               moving_object_random_initial_position=True, use_moving_objects=True)
+    cfg.update(overrides)
+    return EnvConfig(**cfg)
