@@ -179,6 +179,11 @@ typedef struct SmScene {
     double ball_final_min[3], ball_final_max[3];             /* final_ball_position_min_max */
     double plane_z;                                          /* plane_z_offset */
     int32_t ball_check_invalid, ball_random_initial;
+    double min_start_self;         /* self-collision clearance of a start pose (ctlp.py:1468-1477) */
+    double ball_target_min_static; /* clearances of the random pose a ball is aimed at (ctlp.py:1725-1728) */
+    double ball_target_min_self;
+    int32_t has_table;             /* obstacle_scene != 0 (ctlp.py:1890) */
+    int32_t reserved2;
 } SmScene;
 
 /* Device buffers of one call (all caller-owned, N = num_envs). */

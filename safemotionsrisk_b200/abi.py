@@ -101,6 +101,8 @@ class SmScene(C.Structure):
         ("ball_final_min", d * 3), ("ball_final_max", d * 3),
         ("plane_z", d),
         ("ball_check_invalid", i32), ("ball_random_initial", i32),
+        ("min_start_self", d), ("ball_target_min_static", d), ("ball_target_min_self", d),
+        ("has_table", i32), ("reserved2", i32),
     ]
 
 

@@ -1,0 +1,438 @@
+// smenv.cu -- C ABI of libsmenv.so (include/smenv.h): scene upload, pools, reset, step.  sm_100a only, no CPU path.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "smenv_pools.cuh"
+#include "smenv_step.cuh"
+
+static thread_local std::string g_error;
+static int fail(int code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+#define CU(call)                                                                                            \
+    do {                                                                                                    \
+        cudaError_t e_ = (call);                                                                            \
+        if (e_ != cudaSuccess)                                                                              \
+            return fail(SM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                   \
+    } while (0)
+
+struct SmEnv {
+    int n = 0, device = 0;
+    uint64_t seed = 0;
+    DevScene host_scene;  // device pointers inside
+    float4* d_verts = nullptr;
+    float4* d_ppos[SM_MAX_OBSTACLES] = {nullptr, nullptr};
+    float4* d_pquat[SM_MAX_OBSTACLES] = {nullptr, nullptr};
+    double* d_plocal = nullptr;
+    double* d_start_pool = nullptr;
+    double* d_ball_pool = nullptr;
+    int start_pool_n = 0, ball_pool_n = 0;
+    bool pools_filled = false;
+    unsigned long long* d_counters = nullptr;
+    bool count = false;
+    size_t smem_bytes = 0;
+    int grid = 0;
+    uint32_t step_counter = 0;
+    unsigned long long launches = 0;
+};
+
+static SmEnv* g_active = nullptr;  // whose scene currently sits in constant memory
+
+static int activate(SmEnv* env, cudaStream_t stream) {
+    CU(cudaSetDevice(env->device));
+    if (g_active != env) {
+        CU(cudaMemcpyToSymbolAsync(c_sc, &env->host_scene, sizeof(DevScene), 0, cudaMemcpyHostToDevice, stream));
+        g_active = env;
+    }
+    return SM_OK;
+}
+
+extern "C" const char* smenv_last_error(void) { return g_error.c_str(); }
+extern "C" int smenv_abi_version(void) { return 1; }
+extern "C" int smenv_sizeof_scene(void) { return (int)sizeof(SmScene); }
+extern "C" int smenv_sizeof_shape(void) { return (int)sizeof(SmShape); }
+
+template <typename T>
+static int upload(T** dst, const std::vector<T>& src) {
+    CU(cudaMalloc((void**)dst, src.size() * sizeof(T)));
+    CU(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return SM_OK;
+}
+
+extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_t seed, SmEnv** out) {
+    if (!sc || !out || num_envs <= 0) return fail(SM_ERR_ARG, "smenv_create: bad argument");
+    if (sc->n_joints <= 0 || sc->n_joints > 7) return fail(SM_ERR_SCENE, "n_joints must be in 1..7");
+    if (sc->substeps < 1 || sc->substeps > SM_MAX_SUB) return fail(SM_ERR_SCENE, "substeps must be in 1..32");
+    if (sc->n_shapes > SM_MAX_SHAPES || sc->n_verts <= 0) return fail(SM_ERR_SCENE, "bad shape table");
+    if (sc->obs_size > SM_MAX_OBS) return fail(SM_ERR_SCENE, "obs_size too large");
+    for (int j = 0; j < sc->n_joints; ++j)
+        if (sc->joint_parent[j] != j) return fail(SM_ERR_SCENE, "only serial kinematic chains are supported");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(SM_ERR_ARG, "smenv_create: no such CUDA device");
+    CU(cudaSetDevice(device));
+    SmEnv* env = new SmEnv();
+    env->n = num_envs;
+    env->device = device;
+    env->seed = seed;
+    DevScene& d = env->host_scene;
+    memset(&d, 0, sizeof(d));
+    d.n_joints = sc->n_joints; d.substeps = sc->substeps; d.contact_stride = sc->contact_stride;
+    d.limit_velocity = sc->limit_velocity; d.limit_position = sc->limit_position;
+    for (int j = 0; j < SM_MAX_JOINTS; ++j) {
+        d.joint_parent[j] = sc->joint_parent[j];
+        for (int i = 0; i < 9; ++i) d.jR[j][i] = (float)sc->joint_R[j][i];
+        for (int i = 0; i < 3; ++i) { d.jt[j][i] = (float)sc->joint_t[j][i]; d.jaxis[j][i] = (float)sc->joint_axis[j][i]; }
+        d.pos_lo[j] = sc->pos_lo[j]; d.pos_hi[j] = sc->pos_hi[j]; d.vel_max[j] = sc->vel_max[j];
+        d.acc_max[j] = sc->acc_max[j]; d.jerk_max[j] = sc->jerk_max[j];
+    }
+    d.ts = sc->ts; d.action_mapping_factor = sc->action_mapping_factor; d.track_kp = sc->track_kp;
+    d.track_vel = sc->track_vel;
+    d.n_shapes = sc->n_shapes; d.n_verts = sc->n_verts;
+    std::vector<float4> verts(sc->n_verts);
+    for (int i = 0; i < sc->n_verts; ++i)
+        verts[i] = make_float4((float)sc->verts[3 * i], (float)sc->verts[3 * i + 1], (float)sc->verts[3 * i + 2], 0.f);
+    for (int s = 0; s < sc->n_shapes; ++s) {
+        const SmShape& h = sc->shapes[s];
+        DevShape& g = d.shapes[s];
+        g.frame = h.frame; g.off = h.vert_off; g.cnt = h.vert_cnt; g.link = h.link;
+        g.margin = (float)h.margin; g.cx = (float)h.center[0]; g.cy = (float)h.center[1]; g.cz = (float)h.center[2];
+        // bounding sphere recomputed on the float32 vertices so that it certainly contains them
+        float r = 0.f;
+        for (int k = 0; k < 3; ++k) { g.bmin[k] = FLT_MAX; g.bmax[k] = -FLT_MAX; }
+        for (int i = h.vert_off; i < h.vert_off + h.vert_cnt; ++i) {
+            float dx = verts[i].x - g.cx, dy = verts[i].y - g.cy, dz = verts[i].z - g.cz;
+            r = fmaxf(r, sqrtf(dx * dx + dy * dy + dz * dz));
+            g.bmin[0] = fminf(g.bmin[0], verts[i].x); g.bmax[0] = fmaxf(g.bmax[0], verts[i].x);
+            g.bmin[1] = fminf(g.bmin[1], verts[i].y); g.bmax[1] = fmaxf(g.bmax[1], verts[i].y);
+            g.bmin[2] = fminf(g.bmin[2], verts[i].z); g.bmax[2] = fmaxf(g.bmax[2], verts[i].z);
+        }
+        g.radius = r * (1.0f + 1e-6f) + 1e-7f;
+    }
+    d.n_static_pairs = sc->n_static_pairs; d.n_self_pairs = sc->n_self_pairs;
+    d.n_mov_reward = sc->n_mov_reward; d.n_mov_contact = sc->n_mov_contact;
+    for (int i = 0; i < SM_MAX_PAIRS; ++i)
+        for (int k = 0; k < 2; ++k) {
+            d.static_pairs[i][k] = (short)sc->static_pairs[i][k];
+            d.self_pairs[i][k] = (short)sc->self_pairs[i][k];
+        }
+    for (int i = 0; i < SM_MAX_MOV_ROBOT; ++i) { d.mov_reward[i] = (short)sc->mov_reward[i]; d.mov_contact[i] = (short)sc->mov_contact[i]; }
+    {  // contact slots must be sorted by frame for the per-lane broad phase
+        int f = 0;
+        d.contact_frame_start[0] = 0;
+        for (int slot = 0; slot < sc->n_mov_contact; ++slot) {
+            int fr = sc->shapes[sc->mov_contact[slot]].frame;
+            if (fr < f || fr > sc->n_joints) { delete env; return fail(SM_ERR_SCENE, "mov_contact must be sorted by frame"); }
+            while (f < fr) d.contact_frame_start[++f] = slot;
+        }
+        while (f <= sc->n_joints) d.contact_frame_start[++f] = sc->n_mov_contact;
+    }
+    d.n_obstacles = sc->n_obstacles;
+    for (int o = 0; o < SM_MAX_OBSTACLES; ++o) {
+        d.obst_kind[o] = sc->obst_kind[o]; d.obst_shape_off[o] = sc->obst_shape_off[o];
+        d.obst_shape_cnt[o] = sc->obst_shape_cnt[o];
+        for (int i = 0; i < 3; ++i) d.obst_center[o][i] = (float)sc->obst_center[o][i];
+        d.obst_radius[o] = (float)sc->obst_radius[o] * (1.0f + 1e-6f) + 1e-6f;
+        float mx = 0.f;
+        for (int i = 0; i < SM_MAX_MOV_ROBOT; ++i) { d.contact_thresh[o][i] = (float)sc->contact_thresh[o][i]; mx = fmaxf(mx, d.contact_thresh[o][i]); }
+        d.contact_thresh_max[o] = mx;
+    }
+    d.planet_steps = sc->planet_steps; d.planet_shift = sc->planet_shift; d.obs_planet_size = sc->obs_planet_size;
+    d.planet_obs_half[0] = sc->planet_obs_half[0]; d.planet_obs_half[1] = sc->planet_obs_half[1];
+    for (int i = 0; i < 3; ++i) {
+        d.ball_obs_pos_min[i] = sc->ball_obs_pos_min[i]; d.ball_obs_pos_max[i] = sc->ball_obs_pos_max[i];
+        d.ball_obs_vel_min[i] = sc->ball_obs_vel_min[i]; d.ball_obs_vel_max[i] = sc->ball_obs_vel_max[i];
+        d.start_box_min[i] = sc->start_box_min[i]; d.start_box_max[i] = sc->start_box_max[i];
+        d.target_offset[i] = (float)sc->target_offset[i]; d.target_t[i] = (float)sc->target_t[i];
+        d.ball_sphere_center[i] = sc->ball_sphere_center[i];
+        d.ball_target_box_min[i] = sc->ball_target_box_min[i]; d.ball_target_box_max[i] = sc->ball_target_box_max[i];
+        d.ball_invalid_min[i] = sc->ball_invalid_min[i]; d.ball_invalid_max[i] = sc->ball_invalid_max[i];
+        d.ball_final_min[i] = sc->ball_final_min[i]; d.ball_final_max[i] = sc->ball_final_max[i];
+    }
+    for (int i = 0; i < 9; ++i) d.target_R[i] = (float)sc->target_R[i];
+    d.ball_active_xy = sc->ball_active_xy;
+    d.static_cap = sc->static_cap; d.moving_query = sc->moving_query; d.collision_dist = sc->collision_dist;
+    d.w_self = sc->w_self; d.w_static = sc->w_static; d.w_moving = sc->w_moving;
+    d.d_self = sc->d_self; d.d_static = sc->d_static; d.d_moving = sc->d_moving;
+    d.w_low_acc = sc->w_low_acc; d.thr_low_acc = sc->thr_low_acc; d.w_low_vel = sc->w_low_vel; d.thr_low_vel = sc->thr_low_vel;
+    d.punish_action = sc->punish_action; d.terminate_self = sc->terminate_self;
+    d.terminate_static = sc->terminate_static; d.terminate_moving = sc->terminate_moving;
+    d.action_thresh = sc->action_thresh; d.action_max_punishment = sc->action_max_punishment;
+    d.termination_bonus = sc->termination_bonus; d.early_termination_punishment = sc->early_termination_punishment;
+    d.episode_steps = sc->episode_steps; d.obs_size = sc->obs_size;
+    d.kinematic_sampling_probability = sc->kinematic_sampling_probability;
+    d.stay_in_state_probability = sc->stay_in_state_probability;
+    d.min_start_distance = sc->min_start_distance; d.min_start_self = sc->min_start_self;
+    d.ball_target_min_static = sc->ball_target_min_static; d.ball_target_min_self = sc->ball_target_min_self;
+    d.ball_sphere_radius = sc->ball_sphere_radius; d.ball_height_min = sc->ball_height_min;
+    d.ball_height_max = sc->ball_height_max; d.ball_angle_min = sc->ball_angle_min; d.ball_angle_max = sc->ball_angle_max;
+    d.ball_speed = sc->ball_speed; d.ball_radius = sc->ball_radius;
+    d.ball_high_angle_probability = sc->ball_high_angle_probability; d.plane_z = sc->plane_z;
+    d.ball_check_invalid = sc->ball_check_invalid; d.ball_random_initial = sc->ball_random_initial;
+    d.has_table = sc->has_table;
+
+    int rc = upload(&env->d_verts, verts);
+    if (rc) { delete env; return rc; }
+    d.verts = env->d_verts;
+    for (int o = 0; o < sc->n_obstacles; ++o) {
+        if (sc->obst_kind[o] != SM_OBST_PLANET) continue;
+        std::vector<float4> pp(sc->planet_steps), pq(sc->planet_steps);
+        for (int i = 0; i < sc->planet_steps; ++i) {
+            pp[i] = make_float4((float)sc->planet_pos[o][3 * i], (float)sc->planet_pos[o][3 * i + 1],
+                                (float)sc->planet_pos[o][3 * i + 2], 0.f);
+            pq[i] = make_float4((float)sc->planet_quat[o][4 * i], (float)sc->planet_quat[o][4 * i + 1],
+                                (float)sc->planet_quat[o][4 * i + 2], (float)sc->planet_quat[o][4 * i + 3]);
+        }
+        if ((rc = upload(&env->d_ppos[o], pp)) || (rc = upload(&env->d_pquat[o], pq))) { delete env; return rc; }
+        d.planet_pos[o] = env->d_ppos[o];
+        d.planet_quat[o] = env->d_pquat[o];
+    }
+    if (sc->n_obstacles > 0 && sc->obst_kind[0] == SM_OBST_PLANET) {
+        std::vector<double> pl(sc->planet_local_xy, sc->planet_local_xy + 2 * sc->planet_steps);
+        if ((rc = upload(&env->d_plocal, pl))) { delete env; return rc; }
+        d.planet_local_xy = env->d_plocal;
+    }
+    // pools: one start state per env is plenty of variety up to 65536; balls are consumed faster
+    env->start_pool_n = num_envs < 65536 ? (num_envs < 1024 ? 1024 : num_envs) : 65536;
+    env->ball_pool_n = (sc->n_obstacles > 0 && sc->obst_kind[0] == SM_OBST_BALL) ? 4 * env->start_pool_n : 0;
+    CU(cudaMalloc((void**)&env->d_start_pool, (size_t)env->start_pool_n * SM_POOL_STRIDE * sizeof(double)));
+    CU(cudaMemset(env->d_start_pool, 0, (size_t)env->start_pool_n * SM_POOL_STRIDE * sizeof(double)));
+    if (env->ball_pool_n) CU(cudaMalloc((void**)&env->d_ball_pool, (size_t)env->ball_pool_n * SM_BALL_STRIDE * sizeof(double)));
+    CU(cudaMalloc((void**)&env->d_counters, 8 * sizeof(unsigned long long)));
+    CU(cudaMemset(env->d_counters, 0, 8 * sizeof(unsigned long long)));
+
+    env->smem_bytes = (((size_t)sc->n_verts * sizeof(float4) + 15) & ~(size_t)15) +
+                      SM_WARPS_PER_BLOCK * sizeof(WarpScratch) + sizeof(BlockShared);
+    CU(cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
+    CU(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
+    CU(cudaFuncSetAttribute(fill_ball_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
+    CU(cudaFuncSetAttribute(fill_start_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
+    CU(cudaFuncSetAttribute(distances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
+    // persistent grid: as many CTAs as fit on the device at once (a multiple of the SM count), each looping over envs
+    int sms = 0, per_sm = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<false>, SM_WARPS_PER_BLOCK * 32, env->smem_bytes));
+    if (per_sm < 1) { delete env; return fail(SM_ERR_CUDA, "step kernel does not fit on an SM"); }
+    env->grid = sms * per_sm;
+    *out = env;
+    return SM_OK;
+}
+
+extern "C" int smenv_destroy(SmEnv* env) {
+    if (!env) return SM_OK;
+    cudaSetDevice(env->device);
+    if (g_active == env) g_active = nullptr;
+    cudaFree(env->d_verts); cudaFree(env->d_plocal); cudaFree(env->d_start_pool); cudaFree(env->d_ball_pool);
+    cudaFree(env->d_counters);
+    for (int o = 0; o < SM_MAX_OBSTACLES; ++o) { cudaFree(env->d_ppos[o]); cudaFree(env->d_pquat[o]); }
+    delete env;
+    return SM_OK;
+}
+
+static int grid_for(const SmEnv* env, int items) {
+    int blocks = (items + SM_WARPS_PER_BLOCK - 1) / SM_WARPS_PER_BLOCK;
+    return blocks < env->grid ? blocks : env->grid;
+}
+
+extern "C" int smenv_pool_sizes(SmEnv* env, int* start_pool, int* ball_pool) {
+    if (!env) return fail(SM_ERR_ARG, "null env");
+    if (start_pool) *start_pool = env->start_pool_n;
+    if (ball_pool) *ball_pool = env->ball_pool_n;
+    return SM_OK;
+}
+extern "C" int smenv_pool_ptrs(SmEnv* env, double** start_pool, double** ball_pool) {
+    if (!env) return fail(SM_ERR_ARG, "null env");
+    if (start_pool) *start_pool = env->d_start_pool;
+    if (ball_pool) *ball_pool = env->d_ball_pool;
+    return SM_OK;
+}
+
+extern "C" int smenv_fill_pools(SmEnv* env, uint64_t seed, SmStream s) {
+    if (!env) return fail(SM_ERR_ARG, "null env");
+    cudaStream_t stream = (cudaStream_t)s;
+    int rc = activate(env, stream);
+    if (rc) return rc;
+    PoolArgs A{env->d_start_pool, env->start_pool_n, env->d_ball_pool, env->ball_pool_n, (uint32_t)seed, (uint32_t)(seed >> 32)};
+    if (env->ball_pool_n) {
+        fill_ball_pool_kernel<<<grid_for(env, env->ball_pool_n), SM_WARPS_PER_BLOCK * 32, env->smem_bytes, stream>>>(A);
+        env->launches++;
+    }
+    fill_start_pool_kernel<<<grid_for(env, env->start_pool_n), SM_WARPS_PER_BLOCK * 32, env->smem_bytes, stream>>>(A);
+    env->launches++;
+    CU(cudaGetLastError());
+    env->pools_filled = true;
+    return SM_OK;
+}
+
+// helper: is the pointer device memory?
+static bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+__global__ void set_state_kernel(SmBuffers buf, int n, int nj, const double* q, const double* v, const double* a,
+                                 const double* obst, const uint8_t* mask, double tvdt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int env = i >> 5, lane = i & 31;
+    if (env >= n || (mask && !mask[env])) return;
+    int grp = lane >> 3, j = lane & 7;
+    double val = 0.0;
+    if (j < nj) {
+        double qq = q[(size_t)env * nj + j], vv = v[(size_t)env * nj + j];
+        // the reset poses the robot and runs one stepSimulation with the start state as motor target
+        // (safe_motions_base.py:959-978): the tracked pose leaves the start position by track_vel * dt * v0
+        val = grp == 0 ? qq : grp == 1 ? vv : grp == 2 ? a[(size_t)env * nj + j] : __dadd_rn(qq, __dmul_rn(tvdt, vv));
+    }
+    buf.kin[(size_t)env * SM_KIN_STRIDE + lane] = val;
+    if (obst && lane < SM_OBST_STRIDE) buf.obst[(size_t)env * SM_OBST_STRIDE + lane] = obst[(size_t)env * SM_OBST_STRIDE + lane];
+    if (lane == 0) {
+        int* ep = buf.episode + 4 * (size_t)env;
+        ep[0] = 0;
+        buf.ep_return[env] = 0.0;
+    }
+}
+
+extern "C" int smenv_set_state(SmEnv* env, const SmBuffers* buf, const double* q, const double* v, const double* a,
+                               const double* obst, const uint8_t* mask, SmStream s) {
+    if (!env || !buf || !q || !v || !a) return fail(SM_ERR_ARG, "smenv_set_state: null argument");
+    cudaStream_t stream = (cudaStream_t)s;
+    int rc = activate(env, stream);
+    if (rc) return rc;
+    const int n = env->n, nj = env->host_scene.n_joints;
+    // host pointers are staged through temporary device buffers
+    std::vector<void*> tmp;
+    auto stage = [&](const void* p, size_t bytes, const void** out) -> int {
+        if (!p || is_device_ptr(p)) { *out = p; return SM_OK; }
+        void* dptr = nullptr;
+        CU(cudaMalloc(&dptr, bytes));
+        tmp.push_back(dptr);
+        CU(cudaMemcpyAsync(dptr, p, bytes, cudaMemcpyHostToDevice, stream));
+        *out = dptr;
+        return SM_OK;
+    };
+    const void *dq, *dv, *da, *dob, *dm;
+    if ((rc = stage(q, (size_t)n * nj * 8, &dq)) || (rc = stage(v, (size_t)n * nj * 8, &dv)) ||
+        (rc = stage(a, (size_t)n * nj * 8, &da)) || (rc = stage(obst, (size_t)n * SM_OBST_STRIDE * 8, &dob)) ||
+        (rc = stage(mask, (size_t)n, &dm)))
+        return rc;
+    double dt = env->host_scene.ts / (double)env->host_scene.substeps;
+    double tvdt = env->host_scene.track_vel * dt;
+    set_state_kernel<<<(n * 32 + 255) / 256, 256, 0, stream>>>(*buf, n, nj, (const double*)dq, (const double*)dv,
+                                                               (const double*)da, (const double*)dob,
+                                                               (const uint8_t*)dm, tvdt);
+    env->launches++;
+    CU(cudaGetLastError());
+    if (buf->obs) {
+        observation_kernel<<<(n * 32 + 255) / 256, 256, 0, stream>>>(*buf, n);
+        env->launches++;
+        CU(cudaGetLastError());
+    }
+    if (!tmp.empty()) {
+        CU(cudaStreamSynchronize(stream));
+        for (void* p : tmp) cudaFree(p);
+    }
+    return SM_OK;
+}
+
+extern "C" int smenv_observation(SmEnv* env, const SmBuffers* buf, SmStream s) {
+    if (!env || !buf || !buf->obs) return fail(SM_ERR_ARG, "smenv_observation: null argument");
+    cudaStream_t stream = (cudaStream_t)s;
+    int rc = activate(env, stream);
+    if (rc) return rc;
+    observation_kernel<<<(env->n * 32 + 255) / 256, 256, 0, stream>>>(*buf, env->n);
+    env->launches++;
+    CU(cudaGetLastError());
+    return SM_OK;
+}
+
+extern "C" int smenv_reset(SmEnv* env, const SmBuffers* buf, const uint8_t* mask, SmStream s) {
+    if (!env || !buf) return fail(SM_ERR_ARG, "smenv_reset: null argument");
+    if (!env->pools_filled) return fail(SM_ERR_STATE, "smenv_reset: call smenv_fill_pools first");
+    if (mask && !is_device_ptr(mask)) return fail(SM_ERR_ARG, "smenv_reset: mask must be a device pointer");
+    cudaStream_t stream = (cudaStream_t)s;
+    int rc = activate(env, stream);
+    if (rc) return rc;
+    ResetArgs A{*buf, env->n, mask, env->d_start_pool, env->start_pool_n, (uint32_t)env->seed, (uint32_t)(env->seed >> 32)};
+    reset_kernel<<<(env->n * 32 + 255) / 256, 256, 0, stream>>>(A);
+    env->launches++;
+    CU(cudaGetLastError());
+    return SM_OK;
+}
+
+static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int random_actions, SmStream s) {
+    if (!env || !buf) return fail(SM_ERR_ARG, "smenv_step: null argument");
+    if (!random_actions && !buf->actions) return fail(SM_ERR_ARG, "smenv_step: actions missing");
+    if (auto_reset && !env->pools_filled) return fail(SM_ERR_STATE, "smenv_step: auto_reset needs smenv_fill_pools");
+    cudaStream_t stream = (cudaStream_t)s;
+    int rc = activate(env, stream);
+    if (rc) return rc;
+    StepArgs A;
+    A.buf = *buf; A.n = env->n; A.auto_reset = auto_reset; A.random_actions = random_actions;
+    A.k0 = (uint32_t)env->seed; A.k1 = (uint32_t)(env->seed >> 32);
+    A.step_counter = env->step_counter++;
+    A.start_pool = env->pools_filled ? env->d_start_pool : nullptr;
+    A.start_pool_n = env->pools_filled ? env->start_pool_n : 0;
+    A.ball_pool = env->pools_filled ? env->d_ball_pool : nullptr;
+    A.ball_pool_n = env->pools_filled ? env->ball_pool_n : 0;
+    A.counters = env->d_counters;
+    int grid = grid_for(env, env->n);
+    if (env->count) step_kernel<true><<<grid, SM_WARPS_PER_BLOCK * 32, env->smem_bytes, stream>>>(A);
+    else step_kernel<false><<<grid, SM_WARPS_PER_BLOCK * 32, env->smem_bytes, stream>>>(A);
+    env->launches++;
+    CU(cudaGetLastError());
+    return SM_OK;
+}
+extern "C" int smenv_step(SmEnv* env, const SmBuffers* buf, int auto_reset, SmStream s) {
+    return step_impl(env, buf, auto_reset, 0, s);
+}
+extern "C" int smenv_step_random(SmEnv* env, const SmBuffers* buf, int auto_reset, SmStream s) {
+    return step_impl(env, buf, auto_reset, 1, s);
+}
+
+extern "C" int smenv_safe_range(SmEnv* env, const double* kin, double* lo, double* hi, int32_t* code, int n, SmStream s) {
+    if (!env || !kin || !lo || !hi || !code) return fail(SM_ERR_ARG, "smenv_safe_range: null argument");
+    cudaStream_t stream = (cudaStream_t)s;
+    int rc = activate(env, stream);
+    if (rc) return rc;
+    safe_range_kernel<<<(n * 8 + 127) / 128, 128, 0, stream>>>(kin, lo, hi, code, n);
+    env->launches++;
+    CU(cudaGetLastError());
+    return SM_OK;
+}
+
+extern "C" int smenv_distances(SmEnv* env, const double* kin, const double* obst, float* d_static, float* d_self,
+                               float* d_moving, int n, SmStream s) {
+    if (!env || !kin || !obst || !d_static || !d_self || !d_moving) return fail(SM_ERR_ARG, "smenv_distances: null argument");
+    cudaStream_t stream = (cudaStream_t)s;
+    int rc = activate(env, stream);
+    if (rc) return rc;
+    distances_kernel<<<grid_for(env, n), SM_WARPS_PER_BLOCK * 32, env->smem_bytes, stream>>>(kin, obst, d_static, d_self, d_moving, n);
+    env->launches++;
+    CU(cudaGetLastError());
+    return SM_OK;
+}
+
+extern "C" int smenv_enable_counters(SmEnv* env, int enable) {
+    if (!env) return fail(SM_ERR_ARG, "null env");
+    env->count = enable != 0;
+    return SM_OK;
+}
+extern "C" int smenv_counters(SmEnv* env, SmCounters* out, int reset) {
+    if (!env || !out) return fail(SM_ERR_ARG, "null argument");
+    CU(cudaSetDevice(env->device));
+    unsigned long long h[8];
+    CU(cudaMemcpy(h, env->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+    out->gjk_calls = h[0]; out->gjk_iters = h[1]; out->support_dots = h[2]; out->culled_pairs = h[3];
+    out->env_steps = h[4]; out->contact_tests = h[5];
+    if (reset) CU(cudaMemset(env->d_counters, 0, sizeof(h)));
+    return SM_OK;
+}
+extern "C" int smenv_launch_count(SmEnv* env, unsigned long long* out) {
+    if (!env || !out) return fail(SM_ERR_ARG, "null argument");
+    *out = env->launches;
+    return SM_OK;
+}

@@ -415,6 +415,10 @@ class Scene:
             if cfg.collision_avoidance_kinematic_state_sampling_mode else 0.0
         sc.stay_in_state_probability = cfg.collision_avoidance_stay_in_state_probability
         sc.min_start_distance = 0.001 if cfg.collision_avoidance_mode else cfg.closest_point_safety_distance + 0.09
+        sc.min_start_self = 0.001 if cfg.collision_avoidance_mode else cfg.closest_point_safety_distance + 0.04
+        sc.ball_target_min_static = cfg.closest_point_safety_distance + 0.09   # ctlp.py:1725-1726
+        sc.ball_target_min_self = cfg.closest_point_safety_distance            # ctlp.py:2357-2358
+        sc.has_table = int(cfg.obstacle_scene != 0)
         sc.plane_z = -0.94   # robot_scene_base.py:172
 
     # ------------------------------------------------------------------------------------------------------

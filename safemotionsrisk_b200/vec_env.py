@@ -1,0 +1,338 @@
+"""Batched, GPU-resident mirror of the reference env API.
+
+``SafeMotionsVecEnv(num_envs, device, **env_config)`` keeps the surface RLlib and the reference's scripts use on
+``SafeMotionsEnvCollisionAvoidance`` (safe_motions_env.py:38-45):
+
+    reset() -> obs                         observations.py:144-187, safe_motions_base.py:913-1022
+    step(action) -> obs, reward, done, info   safe_motions_base.py:1043-1227
+    observation_space / action_space       Box(-1, 1, (n,), float32)  actions.py:50-51, observations.py:116-117
+    set_seed, close, TERMINATION_* constants, termination_reason, episode_counter, trajectory_time_step, pid
+
+for N independent environments at once.  With ``num_envs == 1`` and ``squeeze=True`` the scalar gym API is reproduced
+(NumPy in / NumPy out, python float reward, bool done, info dict).  Otherwise observations, rewards and dones are
+torch tensors that view the pre-allocated device buffers of the env (valid until the next ``step``).
+
+All numerics run in libsmenv.so (hand-written sm_100a CUDA, include/smenv.h).  PyTorch only provides device memory
+and streams.  There is no CPU path: constructing the env without a CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import abi, cabi
+from .config import EnvConfig
+from .scene import Scene
+
+
+class Box:
+    """Minimal stand-in for gym.spaces.Box (gym is not a dependency of this package)."""
+
+    def __init__(self, low, high, shape, dtype=np.float32):
+        self.low = np.full(shape, low, dtype=dtype)
+        self.high = np.full(shape, high, dtype=dtype)
+        self.shape = tuple(shape)
+        self.dtype = np.dtype(dtype)
+
+    def sample(self):
+        return np.random.uniform(self.low, self.high).astype(self.dtype)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
+
+    def __repr__(self):
+        return "Box({}, {}, {}, {})".format(self.low.min(), self.high.max(), self.shape, self.dtype)
+
+
+class SafeMotionsVecEnv:
+    # safe_motions_base.py:64-70
+    TERMINATION_UNSET = abi.TERMINATION_UNSET
+    TERMINATION_SUCCESS = abi.TERMINATION_SUCCESS
+    TERMINATION_JOINT_LIMITS = abi.TERMINATION_JOINT_LIMITS
+    TERMINATION_TRAJECTORY_LENGTH = abi.TERMINATION_TRAJECTORY_LENGTH
+    TERMINATION_SELF_COLLISION = abi.TERMINATION_SELF_COLLISION
+    TERMINATION_COLLISION_WITH_STATIC_OBSTACLE = abi.TERMINATION_COLLISION_WITH_STATIC_OBSTACLE
+    TERMINATION_COLLISION_WITH_MOVING_OBSTACLE = abi.TERMINATION_COLLISION_WITH_MOVING_OBSTACLE
+
+    def __init__(self, num_envs=1, device=None, seed=None, auto_reset=True, squeeze=False, fill_pools=True,
+                 config=None, **env_config):
+        if not torch.cuda.is_available():
+            raise cabi.SmEnvError("SafeMotionsVecEnv needs a CUDA device (sm_100a); there is no CPU fallback")
+        self._lib = cabi.load()
+        self.config = config if isinstance(config, EnvConfig) else EnvConfig(seed=seed, **env_config)
+        if device is None:
+            device = "cuda:{}".format(int(os.environ.get("LOCAL_RANK", 0)))
+        self.device = torch.device(device)
+        self.num_envs = int(num_envs)
+        self.auto_reset = bool(auto_reset)
+        self._squeeze = bool(squeeze) and self.num_envs == 1
+        self.scene = Scene(self.config)
+        self._seed = int(seed if seed is not None else (self.config.seed if self.config.seed is not None else 0))
+        self._handle = C.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        torch.cuda.set_device(dev_index)
+        cabi.check(self._lib.smenv_create(self.scene.pointer(), self.num_envs, dev_index, self._seed,
+                                          C.byref(self._handle)), "smenv_create")
+        n, nj, d = self.num_envs, self.scene.n_joints, self.scene.obs_size
+        dev = self.device
+        # device-resident env state (SoA of per-env records, see include/smenv.h)
+        self.kin = torch.zeros((n, abi.SM_KIN_STRIDE), dtype=torch.float64, device=dev)
+        self.obst = torch.zeros((n, abi.SM_OBST_STRIDE), dtype=torch.float64, device=dev)
+        self.episode = torch.zeros((n, 4), dtype=torch.int32, device=dev)
+        self.ep_return = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.actions = torch.zeros((n, nj), dtype=torch.float32, device=dev)
+        self.obs = torch.zeros((n, d), dtype=torch.float32, device=dev)
+        self.reward = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.term_reason = torch.full((n,), -1, dtype=torch.int32, device=dev)
+        self.info = torch.zeros((n, abi.SM_INFO_STRIDE), dtype=torch.float32, device=dev)
+        self.stats = torch.zeros(32, dtype=torch.float64, device=dev)
+        self._buf = abi.SmBuffers(
+            kin=self.kin.data_ptr(), obst=self.obst.data_ptr(), episode=self.episode.data_ptr(),
+            ep_return=self.ep_return.data_ptr(), actions=self.actions.data_ptr(), obs=self.obs.data_ptr(),
+            reward=self.reward.data_ptr(), done=self.done.data_ptr(), term_reason=self.term_reason.data_ptr(),
+            info=self.info.data_ptr(), stats=self.stats.data_ptr())
+        # pinned host staging for the host-buffer API (step_host)
+        self._h_actions = torch.zeros((n, nj), dtype=torch.float32).pin_memory()
+        self._h_obs = torch.zeros((n, d), dtype=torch.float32).pin_memory()
+        self._h_reward = torch.zeros(n, dtype=torch.float32).pin_memory()
+        self._h_done = torch.zeros(n, dtype=torch.uint8).pin_memory()
+        self.observation_space = Box(-1.0, 1.0, (d,), np.float32)
+        self.action_space = Box(-1.0, 1.0, (nj,), np.float32)
+        self.episode_counter = 0
+        self.pid = os.getpid()
+        self._pools_filled = False
+        if fill_pools:
+            self.fill_pools(self._seed)
+
+    # ------------------------------------------------------------------ reference helper surface
+    @property
+    def trajectory_time_step(self):
+        return self.config.trajectory_time_step
+
+    @property
+    def use_real_robot(self):
+        return False
+
+    @property
+    def max_resampling_attempts(self):
+        return 0
+
+    @property
+    def termination_reason(self):
+        r = self.term_reason
+        return int(r[0].item()) if self._squeeze else r
+
+    @property
+    def observation_size(self):
+        return self.scene.obs_size
+
+    def set_seed(self, seed=None):
+        """safe_motions_base.py:1704-1710: re-seeds the sampling streams (pools are re-drawn)."""
+        if seed is not None:
+            self._seed = int(seed)
+            self.fill_pools(self._seed)
+        return [seed]
+
+    def close(self):
+        if self._handle:
+            self._lib.smenv_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def fill_pools(self, seed=0):
+        cabi.check(self._lib.smenv_fill_pools(self._handle, int(seed), self._stream()), "smenv_fill_pools")
+        self._pools_filled = True
+
+    def pools(self):
+        """(start_pool [P, 48], ball_pool [B, 12] or None) copied to the host, for inspection and tests."""
+        ps, pb = C.c_int(), C.c_int()
+        cabi.check(self._lib.smenv_pool_sizes(self._handle, C.byref(ps), C.byref(pb)), "smenv_pool_sizes")
+        sp, bp = C.c_void_p(), C.c_void_p()
+        cabi.check(self._lib.smenv_pool_ptrs(self._handle, C.byref(sp), C.byref(bp)), "smenv_pool_ptrs")
+        torch.cuda.synchronize(self.device)
+
+        def fetch(ptr, rows, cols):
+            out = torch.empty((rows, cols), dtype=torch.float64)
+            rc = torch.cuda.cudart().cudaMemcpy(out.data_ptr(), ptr, rows * cols * 8, 2)
+            if int(rc) != 0:
+                raise cabi.SmEnvError("cudaMemcpy of a pool failed: {}".format(rc))
+            return out.numpy()
+        start = fetch(sp.value, ps.value, 48)
+        ball = fetch(bp.value, pb.value, 12) if pb.value else None
+        return start, ball
+
+    # ------------------------------------------------------------------ reset / step
+    def reset(self, mask=None):
+        """Resets all (or the masked) envs from the device-resident start pool; returns the first observations."""
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask, dtype=torch.uint8, device=self.device).contiguous()
+        cabi.check(self._lib.smenv_reset(self._handle, C.byref(self._buf), C.c_void_p(m.data_ptr()) if m is not None
+                                         else None, self._stream()), "smenv_reset")
+        self.episode_counter += self.num_envs if m is None else int(m.sum().item())
+        if self._squeeze:
+            return self.obs[0].cpu().numpy()
+        return self.obs
+
+    def set_state(self, q, v, a, obst=None, mask=None):
+        """Injects start states (parity protocol): q, v, a [N, n_joints] float64, obst [N, 16] or None."""
+        def prep(x, cols):
+            if x is None:
+                return None
+            t = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x, dtype=torch.float64)
+            return t.reshape(self.num_envs, cols).to(self.device).contiguous()
+        nj = self.scene.n_joints
+        tq, tv, ta, tob = prep(q, nj), prep(v, nj), prep(a, nj), prep(obst, abi.SM_OBST_STRIDE)
+        tm = None if mask is None else torch.as_tensor(mask, dtype=torch.uint8, device=self.device).contiguous()
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        cabi.check(self._lib.smenv_set_state(self._handle, C.byref(self._buf), ptr(tq), ptr(tv), ptr(ta), ptr(tob),
+                                             ptr(tm), self._stream()), "smenv_set_state")
+        self.done.zero_()
+        return self.obs
+
+    def step(self, actions):
+        """One env step for all envs.  actions: [N, n_joints] in [-1, 1] (torch on the env's device, or array-like)."""
+        if torch.is_tensor(actions) and actions.device == self.device:
+            self.actions.copy_(actions.reshape(self.num_envs, -1), non_blocking=True)
+        else:
+            arr = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, -1)
+            self.actions.copy_(torch.from_numpy(arr), non_blocking=False)
+        cabi.check(self._lib.smenv_step(self._handle, C.byref(self._buf), int(self.auto_reset), self._stream()),
+                   "smenv_step")
+        return self._outputs()
+
+    def step_random(self):
+        """Step with device-generated U(-1, 1) actions (``random_agent``, safe_motions_base.py:1047-1048)."""
+        cabi.check(self._lib.smenv_step_random(self._handle, C.byref(self._buf), int(self.auto_reset),
+                                               self._stream()), "smenv_step_random")
+        return self._outputs()
+
+    def step_host(self, actions_np):
+        """Host-buffer API: NumPy actions in, NumPy (obs, reward, done) out through pinned staging buffers."""
+        self._h_actions.numpy()[...] = np.asarray(actions_np, dtype=np.float32).reshape(self.num_envs, -1)
+        self.actions.copy_(self._h_actions, non_blocking=True)
+        cabi.check(self._lib.smenv_step(self._handle, C.byref(self._buf), int(self.auto_reset), self._stream()),
+                   "smenv_step")
+        self._h_obs.copy_(self.obs, non_blocking=True)
+        self._h_reward.copy_(self.reward, non_blocking=True)
+        self._h_done.copy_(self.done, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._h_obs.numpy(), self._h_reward.numpy(), self._h_done.numpy()
+
+    def _outputs(self):
+        if self._squeeze:
+            done = bool(self.done[0].item())
+            return self.obs[0].cpu().numpy(), float(self.reward[0].item()), done, self.infos()[0]
+        return self.obs, self.reward, self.done, self.info
+
+    # ------------------------------------------------------------------ info dicts (materialised on demand)
+    def infos(self, only_done=False):
+        """Per-env info dicts with the reference's key names (safe_motions_base.py:1350-1396, rewards.py:490-498)."""
+        info = self.info.cpu().numpy()
+        done = self.done.cpu().numpy()
+        reason = self.term_reason.cpu().numpy()
+        out = []
+        for e in range(self.num_envs):
+            if only_done and not done[e]:
+                out.append({})
+                continue
+            row = info[e]
+            step = dict(collision_rate_self=float(row[abi.INFO["coll_self"]]),
+                        collision_rate_static_obstacles=float(row[abi.INFO["coll_static"]]),
+                        collision_rate_moving_obstacles=float(row[abi.INFO["coll_moving"]]),
+                        action_punishment=float(row[abi.INFO["action_punishment"]]),
+                        self_collision_reward=float(row[abi.INFO["r_self"]]),
+                        static_obstacles_collision_reward=float(row[abi.INFO["r_static"]]),
+                        moving_obstacles_collision_reward=float(row[abi.INFO["r_moving"]]),
+                        joint_jerk_violation=float(row[abi.INFO["max_jerk_rel"]] > 1.002))
+            d = {"average": dict(step), "max": dict(step), "min": {}}
+            if done[e]:
+                d["episode_length"] = int(row[abi.INFO["episode_length"]])
+                d["trajectory_length"] = self.scene.struct.episode_steps + 1
+                d["termination_reason"] = int(reason[e])
+                d["trajectory_successful"] = 1.0
+                d["episode_return"] = float(row[abi.INFO["episode_return"]])
+            out.append(d)
+        return out
+
+    def episode_statistics(self, reset=False):
+        """Accumulated episode statistics of this shard (the quantities train.py:59-117 turns into custom_metrics):
+        [episodes, sum return, sum length, count by termination reason ...]; all-reduced over ranks by the caller."""
+        s = self.stats.clone()
+        if reset:
+            self.stats.zero_()
+        return s
+
+    # ------------------------------------------------------------------ RLlib VectorEnv duck-typing
+    def vector_reset(self):
+        return list(self.reset().cpu().numpy())
+
+    def reset_at(self, index):
+        mask = np.zeros(self.num_envs, dtype=np.uint8)
+        mask[index] = 1
+        self.reset(mask)
+        return self.obs[index].cpu().numpy()
+
+    def vector_step(self, actions):
+        obs, rew, done, _ = self.step(np.asarray(actions, dtype=np.float32))
+        if self._squeeze:
+            return [obs], [rew], [done], [self.infos()[0]]
+        return list(obs.cpu().numpy()), list(rew.cpu().numpy()), [bool(x) for x in done.cpu().numpy()], \
+            self.infos(only_done=True)
+
+    def get_unwrapped(self):
+        return [self]
+
+    # ------------------------------------------------------------------ parity / measurement hooks
+    def safe_range(self, kin=None):
+        kin = self.kin if kin is None else torch.as_tensor(kin, dtype=torch.float64, device=self.device).contiguous()
+        n = kin.shape[0]
+        lo = torch.zeros((n, abi.SM_MAX_JOINTS), dtype=torch.float64, device=self.device)
+        hi = torch.zeros_like(lo)
+        code = torch.zeros((n, abi.SM_MAX_JOINTS), dtype=torch.int32, device=self.device)
+        cabi.check(self._lib.smenv_safe_range(self._handle, kin.data_ptr(), lo.data_ptr(), hi.data_ptr(),
+                                              code.data_ptr(), n, self._stream()), "smenv_safe_range")
+        nj = self.scene.n_joints
+        return lo[:, :nj], hi[:, :nj], code[:, :nj]
+
+    def distances(self, kin=None, obst=None):
+        kin = self.kin if kin is None else torch.as_tensor(kin, dtype=torch.float64, device=self.device).contiguous()
+        obst = self.obst if obst is None else torch.as_tensor(obst, dtype=torch.float64,
+                                                              device=self.device).contiguous()
+        n = kin.shape[0]
+        out = [torch.zeros(n, dtype=torch.float32, device=self.device) for _ in range(3)]
+        cabi.check(self._lib.smenv_distances(self._handle, kin.data_ptr(), obst.data_ptr(), out[0].data_ptr(),
+                                             out[1].data_ptr(), out[2].data_ptr(), n, self._stream()),
+                   "smenv_distances")
+        return out
+
+    def enable_counters(self, enable=True):
+        cabi.check(self._lib.smenv_enable_counters(self._handle, int(enable)), "smenv_enable_counters")
+
+    def counters(self, reset=False):
+        c = abi.SmCounters()
+        torch.cuda.synchronize(self.device)
+        cabi.check(self._lib.smenv_counters(self._handle, C.byref(c), int(reset)), "smenv_counters")
+        return {k: int(getattr(c, k)) for k, _ in abi.SmCounters._fields_}
+
+    def launch_count(self):
+        n = C.c_ulonglong()
+        cabi.check(self._lib.smenv_launch_count(self._handle, C.byref(n)), "smenv_launch_count")
+        return int(n.value)
+
+
+def make_env(env_config, num_envs=1, **kwargs):
+    """``tune.register_env(name, lambda cfg: make_env(cfg))`` style factory (train.py:620, evaluate.py:748)."""
+    return SafeMotionsVecEnv(num_envs=num_envs, **kwargs, **dict(env_config))
