@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Benchmark of the env-step hot path (BASELINE.json: env-steps/sec, whole box, device-timed).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--scene ball|space] [--envs 65536] [--impl reference]
+
+Own arm (default): one process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE), each rank steps its own shard of
+`--envs` environments with device-generated random actions (get_random_action, safe_motions_base.py:1327-1328) and
+auto-reset; no collective on the step path.  K steps are timed with CUDA events on the launching stream, the L2 is
+flushed between timed steps, the max over ranks is taken and rank 0 prints ONE JSON line.
+`e2e` is the same metric through the public host-buffer API (SafeMotionsVecEnv.step_host): pinned host actions in,
+observations / rewards / dones out, copies inside the timed region.
+`--impl reference` times the CPU restatement of the reference path (oracle/, all host threads) on the same workload;
+the real PyBullet/klimits env cannot be installed in this image (no network).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/sec (whole box, device-timed)"
+UNIT = "env-steps/s"
+F_FIXED = 3300.0  # safe range + FK + interpolation + reward flops per env step
+
+
+def scene_config(name):
+    from safemotionsrisk_b200 import ball_backup_config, space_backup_config
+    if name == "ball":
+        return ball_backup_config()
+    if name == "space":
+        return space_backup_config()
+    if name == "space_bm":
+        return space_backup_config(ball_machine_mode=True)
+    if name == "ball_bm":
+        return ball_backup_config(ball_machine_mode=True)
+    raise SystemExit("unknown scene " + name)
+
+
+WORKLOAD = {"ball": "Ball env (moving ball obstacles) batched random-action rollout, 65,536 envs per B200 "
+                    "(BASELINE.json configs[1])",
+            "space": "Space env (planet_mode, obstacle_scene=5) batched random-action rollout",
+            "space_bm": "Space env, ball_machine_mode (shipped checkpoints' robot)",
+            "ball_bm": "Ball env, ball_machine_mode (shipped checkpoints' robot)"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                clk, mx = float(parts[0]), float(parts[1])
+            except ValueError:
+                continue
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(clk)
+                for name, val in zip(names, parts[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_run(scene_name, envs_per_thread, steps, warmup, threads):
+    """Times the CPU oracle on `threads` host threads (ctypes releases the GIL); returns env-steps/s and a note."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle
+    from safemotionsrisk_b200.scene import Scene
+    scene = Scene(scene_config(scene_name))
+    rng = np.random.default_rng(0)
+    lo, hi = np.array(scene.pos_lo), np.array(scene.pos_hi)
+    shards = []
+    for t in range(threads):
+        env = oracle.OracleEnvs(scene, envs_per_thread)
+        q = rng.uniform(0.5 * lo, 0.5 * hi, (envs_per_thread, scene.n_joints))
+        ob = np.zeros((envs_per_thread, 16))
+        if scene.struct.n_obstacles and scene.struct.obst_kind[0] == 1:
+            ob[:, 0] = rng.integers(0, scene.struct.planet_steps, envs_per_thread)
+        elif scene.struct.n_obstacles:
+            ob[:, 2:5], ob[:, 5:8] = [2.4, 0.3, 1.0], [-5.5, -0.6, 1.5]
+            ob[:, 13], ob[:, 14], ob[:, 15] = 1, 200, 150
+        env.set_state(q, np.zeros_like(q), np.zeros_like(q), ob)
+        env._q0, env._ob0 = q, ob
+        shards.append(env)
+    acts = rng.uniform(-1, 1, (envs_per_thread, scene.n_joints)).astype(np.float32)
+    nb = np.tile(np.array([2.4, 0.3, 1.0, -5.5, -0.6, 1.5, 0.3, 0.1, 0.0, 1.0, 200, 150.0]), (envs_per_thread, 1))
+
+    def one_step(env):
+        _, _, done, _, _ = env.step(acts, nb)
+        if done.any():  # episodes restart from the same pool of start states
+            env.set_state(env._q0, np.zeros_like(env._q0), np.zeros_like(env._q0), env._ob0)
+    with ThreadPoolExecutor(threads) as pool:
+        for _ in range(warmup):
+            list(pool.map(one_step, shards))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            list(pool.map(one_step, shards))
+        dt = time.perf_counter() - t0
+    total = threads * envs_per_thread * steps
+    return total / dt, dt, total
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--scene", default="ball")
+    ap.add_argument("--envs", type=int, default=65536, help="environments per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    threads = os.cpu_count() or 1
+    config = {"workload": WORKLOAD[args.scene], "scene": args.scene, "envs_per_gpu": args.envs,
+              "actions": "device Philox U(-1,1)", "auto_reset": True, "parallelism": "env-shards x{}".format(world),
+              "l2": "flushed between timed steps (256 MiB write)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        # bounded sample: small shards so that `steps` finish within minutes on the host cores
+        per_thread = 64 if args.scene.startswith("ball") else 2
+        steps = max(1, min(args.steps, 40))
+        val, dt, total = cpu_reference_run(args.scene, per_thread, steps, min(args.warmup, 2), threads)
+        sample = "{} host threads x {} envs x {} steps of the same scene ({} env-steps in {:.1f} s)".format(
+            threads, per_thread, steps, total, dt)
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                             "note": "oracle restatement -- NOT the PyBullet reference (pybullet/klimits cannot be "
+                                     "installed in this image)"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from safemotionsrisk_b200.vec_env import SafeMotionsVecEnv
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    cfg = scene_config(args.scene)
+    env = SafeMotionsVecEnv(num_envs=args.envs, device=dev, seed=1000 * rank, auto_reset=True, config=cfg)
+    env.reset()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    for _ in range(max(3, args.warmup)):
+        env.step_random()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    launches0 = env.launch_count()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_wall0 = time.time()
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)  # evict the env state from L2 (outside the timed region of the step)
+        starts[i].record()
+        env.step_random()
+        ends[i].record()
+    torch.cuda.synchronize(dev)
+    t_wall1 = time.time()
+    launches = env.launch_count() - launches0
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = float(sum(step_ms))
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tmax_ms = float(t.item())
+    value = world * args.envs * args.steps / (tmax_ms * 1e-3)
+
+    # end-of-iteration episode statistics: the only collective of the design (train.py:59-117 custom_metrics)
+    stats = env.episode_statistics()
+    t0 = time.perf_counter()
+    if world > 1:
+        dist.all_reduce(stats)
+        torch.cuda.synchronize(dev)
+    stats_ms = 1e3 * (time.perf_counter() - t0)
+    stats = stats.cpu().numpy()
+
+    # ---------------- roofline of the dominant kernel (step_kernel): algorithmic flops from device counters
+    env.enable_counters(True)
+    env.counters(reset=True)
+    for _ in range(3):
+        env.step_random()
+    c = env.counters()
+    env.enable_counters(False)
+    steps_counted = max(1, c["env_steps"])
+    n_dot, n_iter = c["support_dots"] / steps_counted, c["gjk_iters"] / steps_counted
+    f_step = F_FIXED + 5.0 * n_dot + 100.0 * n_iter
+    kernel_ms = statistics.mean(step_ms)
+    per_gpu_steps_s = args.envs / (kernel_ms * 1e-3)
+    achieved_tflops = per_gpu_steps_s * f_step / 1e12
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    peak_tflops = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12  # FP32 pipe at the SM clock seen under load
+    sc = env.scene.struct
+    bytes_step = 2 * (8 * 32 + 8 * 16 + 16 + 8) + 4 * sc.obs_size + 4 + 1 + 4 + 4 * 16
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    roofline = {"bound": "fp32", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
+                "frac": achieved_tflops / peak_tflops, "traffic": None,
+                "peak_source": "148 SMs x 128 FP32 lanes x 2 x median SM clock under load ({} MHz)".format(sm_mhz),
+                "flops_per_env_step": f_step, "support_dots_per_env_step": n_dot, "gjk_iters_per_env_step": n_iter,
+                "gjk_calls_per_env_step": c["gjk_calls"] / steps_counted, "kernel": "step_kernel<false>",
+                "kernel_ms": kernel_ms,
+                "hbm": {"achieved": per_gpu_steps_s * bytes_step / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": per_gpu_steps_s * bytes_step / 1e9 / hbm_peak, "bytes_per_env_step": bytes_step,
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+
+    # ---------------- end to end through the host-buffer API
+    e2e = None
+    if not args.no_e2e:
+        rng = np.random.default_rng(rank)
+        acts = rng.uniform(-1, 1, (args.envs, sc.n_joints)).astype(np.float32)
+        for _ in range(3):
+            env.step_host(acts)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        k_e2e = min(args.steps, 100)
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            env.step_host(acts)
+        torch.cuda.synchronize(dev)
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * args.envs * k_e2e / float(te.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(acts.nbytes), "d2h_bytes_per_step": int(args.envs * (4 * sc.obs_size + 4 + 1)),
+               "steps": k_e2e, "api": "SafeMotionsVecEnv.step_host (pinned host buffers)"}
+
+    # ---------------- CPU baseline beside it (rank 0, N = 1 only, bounded sample)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        per_thread = 64 if args.scene.startswith("ball") else 2
+        val, dt, total = cpu_reference_run(args.scene, per_thread, 20, 1, threads)
+        cpu = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "{} host threads x {} envs x 20 steps of the same scene ({} env-steps in {:.1f} s)".format(
+                   threads, per_thread, total, dt),
+               "note": "oracle restatement -- NOT the PyBullet reference (not installable here)"}
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": max(3, args.warmup), "ms_per_step": tmax_ms / args.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64 joint space / f32 geometry",
+               "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+               "roofline": roofline, "cpu_baseline": cpu,
+               "episode_stats": {"episodes": float(stats[0]), "mean_return": float(stats[1] / max(stats[0], 1)),
+                                 "mean_length": float(stats[2] / max(stats[0], 1)),
+                                 "by_termination_reason": {str(r): float(stats[3 + r]) for r in range(1, 6)},
+                                 "allreduce_ms": stats_ms}}
+        print(json.dumps(out))
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -220,6 +220,8 @@ int smenv_destroy(SmEnv* env);
 int smenv_pool_sizes(SmEnv* env, int* start_pool, int* ball_pool);
 int smenv_fill_pools(SmEnv* env, uint64_t seed, SmStream stream);
 int smenv_pool_ptrs(SmEnv* env, double** start_pool, double** ball_pool);
+/* Copies the pools to host arrays of pool_size x 48 / x 12 doubles (either may be NULL); synchronises the device. */
+int smenv_copy_pools(SmEnv* env, double* host_start, double* host_ball);
 
 /* Injects a start state (parity protocol).  Host or device pointers are both accepted; mask==NULL means all envs. */
 int smenv_set_state(SmEnv* env, const SmBuffers* buf, const double* q, const double* v, const double* a,

@@ -37,8 +37,7 @@ def build(force=False):
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB_PATH):
-            build()
+        build()  # no-op when the library is newer than its sources
         _lib = C.CDLL(_LIB_PATH)
         _lib.smo_gjk_flat.restype = C.c_double
         assert _lib.smo_sizeof_scene() == C.sizeof(abi.SmScene), "SmScene layout mismatch"

@@ -26,6 +26,7 @@ def load():
     lib.smenv_destroy.argtypes = [vp]
     lib.smenv_pool_sizes.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
     lib.smenv_pool_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    lib.smenv_copy_pools.argtypes = [vp, vp, vp]
     lib.smenv_fill_pools.argtypes = [vp, u64, vp]
     lib.smenv_set_state.argtypes = [vp, C.POINTER(abi.SmBuffers), vp, vp, vp, vp, vp, vp]
     lib.smenv_reset.argtypes = [vp, C.POINTER(abi.SmBuffers), vp, vp]

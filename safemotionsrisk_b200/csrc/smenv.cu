@@ -250,6 +250,19 @@ extern "C" int smenv_pool_ptrs(SmEnv* env, double** start_pool, double** ball_po
     return SM_OK;
 }
 
+extern "C" int smenv_copy_pools(SmEnv* env, double* host_start, double* host_ball) {
+    if (!env) return fail(SM_ERR_ARG, "null env");
+    CU(cudaSetDevice(env->device));
+    CU(cudaDeviceSynchronize());
+    if (host_start)
+        CU(cudaMemcpy(host_start, env->d_start_pool, (size_t)env->start_pool_n * SM_POOL_STRIDE * sizeof(double),
+                      cudaMemcpyDeviceToHost));
+    if (host_ball && env->ball_pool_n)
+        CU(cudaMemcpy(host_ball, env->d_ball_pool, (size_t)env->ball_pool_n * SM_BALL_STRIDE * sizeof(double),
+                      cudaMemcpyDeviceToHost));
+    return SM_OK;
+}
+
 extern "C" int smenv_fill_pools(SmEnv* env, uint64_t seed, SmStream s) {
     if (!env) return fail(SM_ERR_ARG, "null env");
     cudaStream_t stream = (cudaStream_t)s;

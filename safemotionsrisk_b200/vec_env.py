@@ -159,18 +159,10 @@ class SafeMotionsVecEnv:
         """(start_pool [P, 48], ball_pool [B, 12] or None) copied to the host, for inspection and tests."""
         ps, pb = C.c_int(), C.c_int()
         cabi.check(self._lib.smenv_pool_sizes(self._handle, C.byref(ps), C.byref(pb)), "smenv_pool_sizes")
-        sp, bp = C.c_void_p(), C.c_void_p()
-        cabi.check(self._lib.smenv_pool_ptrs(self._handle, C.byref(sp), C.byref(bp)), "smenv_pool_ptrs")
-        torch.cuda.synchronize(self.device)
-
-        def fetch(ptr, rows, cols):
-            out = torch.empty((rows, cols), dtype=torch.float64)
-            rc = torch.cuda.cudart().cudaMemcpy(out.data_ptr(), ptr, rows * cols * 8, 2)
-            if int(rc) != 0:
-                raise cabi.SmEnvError("cudaMemcpy of a pool failed: {}".format(rc))
-            return out.numpy()
-        start = fetch(sp.value, ps.value, 48)
-        ball = fetch(bp.value, pb.value, 12) if pb.value else None
+        start = np.zeros((ps.value, 48))
+        ball = np.zeros((pb.value, 12)) if pb.value else None
+        cabi.check(self._lib.smenv_copy_pools(self._handle, start.ctypes.data,
+                                              ball.ctypes.data if ball is not None else None), "smenv_copy_pools")
         return start, ball
 
     # ------------------------------------------------------------------ reset / step

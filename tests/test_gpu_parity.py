@@ -1,0 +1,336 @@
+"""Parity of the CUDA path (through the C ABI, libsmenv.so) against the CPU oracle and the golden vectors.
+
+Tolerances are the north star's (BASELINE.json): safe-action clipping / joint trajectory bit-exact in float64,
+termination and collision flags exact except for contacts within 1e-5 m of a threshold, distances within 1e-4 m,
+rewards within 1e-4 relative.
+"""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle  # noqa: E402
+from safemotionsrisk_b200 import abi, ball_backup_config, space_backup_config  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CONFIGS = {"space": lambda **k: space_backup_config(**k), "ball": lambda **k: ball_backup_config(**k),
+           "space_bm": lambda **k: space_backup_config(ball_machine_mode=True, **k),
+           "ball_bm": lambda **k: ball_backup_config(ball_machine_mode=True, **k)}
+I = abi.INFO
+THRESH = 1e-3   # collision threshold of the reward (rewards.py:115-155)
+
+
+def make_env(name, n, **kw):
+    from safemotionsrisk_b200.vec_env import SafeMotionsVecEnv
+    opts = dict(seed=3, auto_reset=False)
+    opts.update(kw)
+    cfg_kw = opts.pop("cfg", {})
+    return SafeMotionsVecEnv(num_envs=n, config=CONFIGS[name](**cfg_kw), **opts)
+
+
+def knife_edge(d_raw_oracle, caps):
+    """True where an oracle distance sits within 1e-5 m of a decision threshold (flags may legitimately differ)."""
+    edge = np.zeros(d_raw_oracle.shape[0], dtype=bool)
+    for col in range(3):
+        for th in (THRESH, caps[col]):
+            edge |= np.abs(d_raw_oracle[:, col] - th) < 1e-5
+    return edge
+
+
+def test_extension_is_loaded_and_counts_launches():
+    env = make_env("ball", 32, fill_pools=False)
+    n0 = env.launch_count()
+    q = np.zeros((32, 7))
+    env.set_state(q, q, q, np.zeros((32, 16)))
+    env.step(np.zeros((32, 7), dtype=np.float32))
+    torch.cuda.synchronize()
+    assert env.launch_count() - n0 == 3          # set_state + observation + step kernels
+    env.close()
+
+
+def test_safe_range_bit_exact():
+    env = make_env("space", 8, fill_pools=False)
+    sc = env.scene
+    rng = np.random.default_rng(0)
+    n = 20000
+    lo_p, hi_p, V, A = (np.array(x) for x in (sc.pos_lo, sc.pos_hi, sc.vel_max, sc.acc_max))
+    q = rng.uniform(lo_p, hi_p, (n, 7))
+    v = rng.uniform(-1, 1, (n, 7)) * V
+    a = rng.uniform(-1, 1, (n, 7)) * A
+    # a quarter of the states hug a position limit, a quarter a velocity limit
+    q[: n // 4] = hi_p - rng.uniform(0, 0.05, (n // 4, 7)) ** 2
+    v[n // 4: n // 2] = V * (1 - rng.uniform(0, 0.05, (n // 4, 7)) ** 2)
+    kin = np.zeros((n, 32))
+    kin[:, 0:7], kin[:, 8:15], kin[:, 16:23] = q, v, a
+    lo, hi, code = env.safe_range(kin)
+    o_lo, o_hi, o_code = oracle.safe_range(sc, q, v, a)
+    assert np.array_equal(lo.cpu().numpy(), o_lo)
+    assert np.array_equal(hi.cpu().numpy(), o_hi)
+    assert np.array_equal(code.cpu().numpy(), o_code)
+    env.close()
+
+
+@pytest.mark.parametrize("name", ["space", "ball", "space_bm", "ball_bm"])
+def test_distances_match_oracle(name):
+    n = 192
+    env = make_env(name, n, fill_pools=False)
+    sc = env.scene
+    rng = np.random.default_rng(1)
+    q = rng.uniform(sc.pos_lo, sc.pos_hi, (n, 7))
+    ob = np.zeros((n, 16))
+    if name.startswith("space"):
+        ob[:, 0] = rng.integers(0, 1200, n)
+    else:
+        # balls placed near the arm so that many distances are below the 0.6 m query
+        ob[:, 2:5] = rng.uniform([-0.8, -0.8, 0.1], [0.6, 0.8, 1.3], (n, 3))
+        ob[:, 8:11] = rng.uniform(-1, 1, (n, 3))
+        ob[:, 13] = 1
+    kin = np.zeros((n, 32))
+    kin[:, 0:7] = q
+    ds, dse, dm = (x.cpu().numpy() for x in env.distances(kin, ob))
+    ref = np.array([oracle.distances(sc, q[e], ob[e]) for e in range(n)])
+    clamp = lambda d: np.where(d < THRESH, 0.0, d)    # below 1 mm everything counts as collision (rewards.py:115)
+    for dev, col in ((ds, 0), (dse, 1), (dm, 2)):
+        assert np.abs(clamp(dev) - clamp(ref[:, col])).max() < 1e-4, (name, col)
+    assert (ref[:, 2] < 0.6).sum() > 10 and (ref[:, 0] < 0.102).sum() > 5
+    env.close()
+
+
+@pytest.mark.parametrize("name", ["space", "ball", "space_bm", "ball_bm"])
+def test_golden_rollout(name):
+    """Committed oracle vectors: same start states and actions through the CUDA step."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    n = g["q"].shape[0]
+    env = make_env(name, n, fill_pools=False)
+    caps = (env.scene.struct.static_cap, env.scene.struct.static_cap, env.scene.struct.moving_query)
+    env.set_state(g["q"], g["v"], g["a"], g["obst"])
+    torch.cuda.synchronize()
+    assert np.array_equal(env.kin.cpu().numpy(), g["kin0"])
+    assert np.array_equal(env.obs.cpu().numpy(), g["obs0"])
+    alive = np.ones(n, dtype=bool)
+    for s in range(g["actions"].shape[0]):
+        if "balls" in g:   # the oracle takes the replacement launch as an input: inject the same one on the device
+            ob = env.obst.cpu().numpy()
+        obs, rew, done, info = env.step(g["actions"][s])
+        torch.cuda.synchronize()
+        kin, obst = env.kin.cpu().numpy(), env.obst.cpu().numpy()
+        if "balls" in g:
+            repl = obst[:, 13] == 0        # no device pool in this test: inactive balls are replaced by hand
+            if repl.any():
+                obst[repl, 2:12], obst[repl, 14:16] = g["balls"][s][repl, :10], g["balls"][s][repl, 10:12]
+                obst[repl, 0], obst[repl, 12], obst[repl, 13], obst[repl, 1] = 0, 0, 1, 0
+                env.obst.copy_(torch.from_numpy(obst))
+                env._lib.smenv_observation(env._handle, __import__("ctypes").byref(env._buf), env._stream())
+                torch.cuda.synchronize()
+        o_info = g["out_info"][s]
+        ok = alive.copy()
+        assert np.array_equal(kin[ok], g["out_kin"][s][ok]), "joint trajectory must be bit-exact"
+        d_dev, d_ref = info.cpu().numpy()[:, :3], o_info[:, :3]
+        assert np.abs(d_dev - d_ref)[ok].max() < 1e-4
+        flags_equal = (info.cpu().numpy()[:, 3:6] == o_info[:, 3:6]).all(1) & (done.cpu().numpy() == g["out_done"][s])
+        edge = knife_edge(d_ref, caps) | (np.abs(d_dev - d_ref).max(1) > 0)  # flag flips need a distance on an edge
+        assert (flags_equal | ~ok | edge).all()
+        ok &= flags_equal
+        assert np.allclose(rew.cpu().numpy()[ok], g["out_reward"][s][ok], rtol=1e-4, atol=1e-4)
+        assert np.array_equal(env.term_reason.cpu().numpy()[ok], g["out_term"][s][ok])
+        assert np.array_equal(obst[ok], g["out_obst"][s][ok])
+        assert np.array_equal(env.obs.cpu().numpy()[ok], g["out_obs"][s][ok])
+        alive &= ok & (g["out_done"][s] == 0)
+    env.close()
+
+
+@pytest.mark.parametrize("name", ["space", "ball"])
+def test_rollout_from_device_pools_matches_oracle(name):
+    """Start states sampled on the device, full 20-step episodes against the live oracle."""
+    n = 128
+    env = make_env(name, n, seed=11)
+    start, ball = env.pools()
+    q, v, a, ob = start[:n, 0:7], start[:n, 8:15], start[:n, 16:23], start[:n, 32:48]
+    env.set_state(q, v, a, ob)
+    orc = oracle.OracleEnvs(env.scene, n)
+    orc.set_state(q, v, a, ob)
+    rng = np.random.default_rng(5)
+    alive = np.ones(n, dtype=bool)
+    mism = 0
+    for s in range(20):
+        act = rng.uniform(-1, 1, (n, 7)).astype(np.float32)
+        obs, rew, done, info = env.step(act)
+        torch.cuda.synchronize()
+        dev_ob = env.obst.cpu().numpy()
+        nb = np.concatenate([dev_ob[:, 2:12], dev_ob[:, 14:16]], axis=1)   # the launch the device drew from its pool
+        o_obs, o_rew, o_done, o_term, o_info = orc.step(act, nb)
+        assert np.array_equal(env.kin.cpu().numpy()[alive], orc.kin[alive])
+        assert np.abs(info.cpu().numpy()[:, :3] - o_info[:, :3])[alive].max() < 1e-4
+        same = (done.cpu().numpy() == o_done) & (info.cpu().numpy()[:, 3:6] == o_info[:, 3:6]).all(1)
+        mism += int((~same & alive).sum())
+        alive &= same
+        assert np.allclose(rew.cpu().numpy()[alive], o_rew[alive], rtol=1e-4, atol=1e-4)
+        assert np.array_equal(obs.cpu().numpy()[alive], o_obs[alive])
+        assert np.array_equal(dev_ob[alive], orc.obst[alive])
+        alive &= o_done == 0
+    assert mism <= 1      # knife-edge contacts only
+    env.close()
+
+
+@pytest.mark.parametrize("name", ["space", "ball", "space_bm"])
+def test_pools_hold_valid_start_states(name):
+    """Device-side rejection sampling (ctlp.py:1461-1656, :4470-4501, :1723-1931) checked with the oracle."""
+    env = make_env(name, 256, seed=5)
+    sc = env.scene
+    start, ball = env.pools()
+    assert start.shape[0] >= 1024 and np.isfinite(start).all()
+    q, v, a = start[:, 0:7], start[:, 8:15], start[:, 16:23]
+    assert (q >= np.array(sc.pos_lo) - 1e-12).all() and (q <= np.array(sc.pos_hi) + 1e-12).all()
+    _, _, code = oracle.safe_range(sc, q[:512], v[:512], a[:512])
+    assert (code == 0).all()                                   # ctlp.py:1513-1523
+    assert (np.abs(v).sum(1) > 0).mean() > 0.5                 # kinematic-state sampling is used (p = 0.7)
+    # q_act = q + 0.87 dt v  (reset stepSimulation, safe_motions_base.py:973-978)
+    assert np.allclose(start[:, 24:31], q + 0.87 * (0.1 / 24) * v, rtol=0, atol=1e-15)
+    box_min, box_max = np.array(sc.struct.start_box_min[:]), np.array(sc.struct.start_box_max[:])
+    for e in range(64):
+        fr = oracle.fk(sc, q[e])
+        r = fr[7][:9].reshape(3, 3)
+        tgt = fr[7][9:] + r @ (np.array(sc.struct.target_t[:]) +
+                               np.array(sc.struct.target_R[:]).reshape(3, 3) @ np.array(sc.struct.target_offset[:]))
+        assert (tgt >= box_min - 1e-5).all() and (tgt <= box_max + 1e-5).all()
+        ds, dse, dm = oracle.distances(sc, q[e], start[e, 32:48])
+        assert ds >= 1e-3 - 1e-5 and dse >= 1e-3 - 1e-5        # collision-free start (ctlp.py:1468-1472)
+        assert dm > 0                                           # obstacle phase without contact
+    if name.startswith("space"):
+        idx = start[:, 32]
+        assert (idx == np.round(idx)).all() and idx.min() >= 0 and idx.max() < 1200 and len(np.unique(idx)) > 200
+    if ball is not None:
+        assert np.isfinite(ball).all()
+        speed = np.linalg.norm(ball[:, 3:6], axis=1)
+        assert np.allclose(speed, 6.0, atol=1e-9)              # moving_object_speed_meter_per_second
+        rel = ball[:, 0:3] - np.array([0, 0, 0.5])
+        assert np.allclose(np.linalg.norm(rel, axis=1), 2.5, atol=1e-9)   # release sphere (README.md:81)
+        assert (ball[:, 10] > 0).all() and (ball[:, 11] > 0).all()
+    env.close()
+
+
+def test_auto_reset_loads_the_philox_indexed_pool_entry():
+    n = 512
+    env = make_env("space", n, seed=9, auto_reset=True)
+    start, _ = env.pools()
+    env.reset()
+    torch.cuda.synchronize()
+    first = env.kin.cpu().numpy().copy()
+    key0, key1 = 9, 0
+    for e in range(0, n, 37):      # reset #0 of env e picks entry philox(e, 0, 0x5E7, 1) % pool
+        idx = oracle.philox(e, 0, 0x5E7, 1, key0, key1)[0] % start.shape[0]
+        assert np.array_equal(first[e], start[idx, :32])
+    # run until every env finished at least once; afterwards every env sits on some pool entry's trajectory
+    finished = np.zeros(n, dtype=bool)
+    lengths = []
+    for s in range(21):
+        obs, rew, done, info = env.step_random()
+        torch.cuda.synchronize()
+        d = done.cpu().numpy() > 0
+        lengths.append(info.cpu().numpy()[d, I["episode_length"]])
+        ep = env.episode.cpu().numpy()
+        assert (ep[d, 0] == 0).all()                       # finished envs restart at episode_length 0
+        finished |= d
+    assert finished.all()
+    lengths = np.concatenate(lengths)
+    assert lengths.max() <= 20 and lengths.min() >= 1
+    stats = env.episode_statistics().cpu().numpy()
+    assert stats[0] == len(lengths) and abs(stats[2] - lengths.sum()) < 1e-9
+    env.close()
+
+
+def test_device_random_actions_are_uniform_and_deterministic():
+    a = make_env("ball", 4096, seed=21, auto_reset=True)
+    b = make_env("ball", 4096, seed=21, auto_reset=True)
+    a.reset(); b.reset()
+    for _ in range(5):
+        a.step_random(); b.step_random()
+    torch.cuda.synchronize()
+    assert torch.equal(a.kin, b.kin) and torch.equal(a.obs, b.obs) and torch.equal(a.reward, b.reward)
+    a.close(); b.close()
+
+
+def test_envs_are_independent_of_batch_composition():
+    """Multi-GPU sharding rests on this: an env's trajectory does not depend on which other envs share the launch."""
+    n = 64
+    env = make_env("space", n, seed=4)
+    start, _ = env.pools()
+    q, v, a, ob = start[:n, 0:7], start[:n, 8:15], start[:n, 16:23], start[:n, 32:48]
+    rng = np.random.default_rng(2)
+    acts = rng.uniform(-1, 1, (5, n, 7)).astype(np.float32)
+    env.set_state(q, v, a, ob)
+    for s in range(5):
+        env.step(acts[s])
+    torch.cuda.synchronize()
+    full_kin, full_rew = env.kin.cpu().numpy().copy(), env.reward.cpu().numpy().copy()
+    env.close()
+    half = make_env("space", n // 2, seed=4, fill_pools=False)
+    sel = np.arange(n // 2) * 2 + 1
+    half.set_state(q[sel], v[sel], a[sel], ob[sel])
+    for s in range(5):
+        half.step(acts[s][sel])
+    torch.cuda.synchronize()
+    assert np.array_equal(half.kin.cpu().numpy(), full_kin[sel])
+    assert np.array_equal(half.reward.cpu().numpy(), full_rew[sel])
+    half.close()
+
+
+@pytest.mark.parametrize("name", ["space", "ball"])
+def test_full_size_invariants(name):
+    """BASELINE.json size (65,536 envs): size-independent properties over several auto-reset steps."""
+    n = 65536
+    env = make_env(name, n, seed=1, auto_reset=True)
+    sc = env.scene
+    env.reset()
+    lo_p, hi_p, V, A = (torch.tensor(x, device=env.device) for x in (sc.pos_lo, sc.pos_hi, sc.vel_max, sc.acc_max))
+    total_done = 0
+    for s in range(25):
+        obs, rew, done, info = env.step_random()
+        q, v, a = env.kin[:, 0:7], env.kin[:, 8:15], env.kin[:, 16:23]
+        assert bool(((q >= lo_p - 1e-6) & (q <= hi_p + 1e-6)).all())
+        assert bool((v.abs() <= V * (1 + 1e-9)).all()) and bool((a.abs() <= A * (1 + 1e-12)).all())
+        assert bool((obs.abs() <= 1).all()) and bool(torch.isfinite(rew).all())
+        assert float(info[:, I["max_jerk_rel"]].max()) <= 1.0 + 1e-6
+        assert bool((info[:, I["episode_length"]] <= 20).all())
+        d = done > 0
+        total_done += int(d.sum())
+        reasons = env.term_reason[d]
+        assert bool(((reasons >= 2) & (reasons <= 5)).all())
+        # reward algebra holds for every env (rewards.py:481-488)
+        pun = info[:, I["action_punishment"]]
+        base = 0.4 * (1 - pun) + info[:, I["r_self"]] + info[:, I["r_static"]] + 3 * info[:, I["r_moving"]]
+        coll = (info[:, I["coll_static"]] + info[:, I["coll_self"]] + info[:, I["coll_moving"]]) > 0
+        bonus = torch.where(coll, torch.full_like(base, -15.0),
+                            torch.where(info[:, I["episode_length"]] >= 20, torch.full_like(base, 15.0),
+                                        torch.zeros_like(base)))
+        assert float((rew - base - bonus).abs().max()) < 1e-4
+    assert total_done > n        # every env finished at least once on average
+    stats = env.episode_statistics().cpu().numpy()
+    assert stats[0] == total_done
+    env.close()
+
+
+def test_squeeze_mode_reproduces_the_scalar_gym_api():
+    from safemotionsrisk_b200.vec_env import SafeMotionsVecEnv
+    env = SafeMotionsVecEnv(num_envs=1, squeeze=True, seed=2, auto_reset=False, config=space_backup_config())
+    obs = env.reset()
+    assert isinstance(obs, np.ndarray) and obs.shape == (23,) and obs.dtype == np.float32
+    assert env.observation_space.shape == (23,) and env.action_space.shape == (7,)
+    done, steps = False, 0
+    while not done:
+        obs, rew, done, info = env.step(env.action_space.sample())
+        steps += 1
+        assert isinstance(rew, float) and isinstance(done, bool) and "average" in info
+    assert steps <= 20 and info["termination_reason"] in (2, 4, 5) and info["episode_length"] == steps
+    env.close()
+
+
+def test_bad_arguments_raise():
+    from safemotionsrisk_b200 import cabi
+    env = make_env("space", 8, fill_pools=False)
+    with pytest.raises(cabi.SmEnvError):
+        env.reset()                      # pools not filled
+    env.close()
