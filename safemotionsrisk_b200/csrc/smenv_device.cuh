@@ -374,7 +374,18 @@ __device__ __forceinline__ int warp_support(const float4* __restrict__ v, int n,
     return __shfl_sync(FULL, bi, __ffs(bal) - 1);
 }
 
-// closest point to the origin on triangle abc (Ericson, Real-Time Collision Detection 5.1.5); mask = kept vertices
+// closest point to the origin on segment ab; mask bit 0 = a kept, bit 1 = b kept
+__device__ __forceinline__ V3 closest_segment(V3 a, V3 b, int& mask) {
+    V3 ab = b - a;
+    float t = -dot(a, ab), den = dot(ab, ab);
+    if (t <= 0.0f || !(den > 0.0f)) { mask = 1; return a; }
+    if (t >= den) { mask = 2; return b; }
+    mask = 3;
+    return a + (t / den) * ab;
+}
+
+// closest point to the origin on triangle abc (Ericson, Real-Time Collision Detection 5.1.5); mask = kept vertices.
+// Degenerate (collinear) triangles fall back to the closest of the three edges instead of dividing by ~0.
 __device__ __forceinline__ V3 closest_triangle(V3 a, V3 b, V3 c, int& mask) {
     V3 ab = b - a, ac = c - a;
     float d1 = -dot(ab, a), d2 = -dot(ac, a);
@@ -382,19 +393,29 @@ __device__ __forceinline__ V3 closest_triangle(V3 a, V3 b, V3 c, int& mask) {
     float d3 = -dot(ab, b), d4 = -dot(ac, b);
     if (d3 >= 0.0f && d4 <= d3) { mask = 2; return b; }
     float vc = d1 * d4 - d3 * d2;
-    if (vc <= 0.0f && d1 >= 0.0f && d3 <= 0.0f) { mask = 3; return a + (d1 / (d1 - d3)) * ab; }
+    if (vc <= 0.0f && d1 >= 0.0f && d3 <= 0.0f && d1 - d3 > 0.0f) { mask = 3; return a + (d1 / (d1 - d3)) * ab; }
     float d5 = -dot(ab, c), d6 = -dot(ac, c);
     if (d6 >= 0.0f && d5 <= d6) { mask = 4; return c; }
     float vb = d5 * d2 - d1 * d6;
-    if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f) { mask = 5; return a + (d2 / (d2 - d6)) * ac; }
+    if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f && d2 - d6 > 0.0f) { mask = 5; return a + (d2 / (d2 - d6)) * ac; }
     float va = d3 * d6 - d5 * d4;
-    if (va <= 0.0f && (d4 - d3) >= 0.0f && (d5 - d6) >= 0.0f) {
-        mask = 6;
-        return b + ((d4 - d3) / ((d4 - d3) + (d5 - d6))) * (c - b);
+    float e1 = d4 - d3, e2 = d5 - d6;
+    if (va <= 0.0f && e1 >= 0.0f && e2 >= 0.0f && e1 + e2 > 0.0f) { mask = 6; return b + (e1 / (e1 + e2)) * (c - b); }
+    float sum = va + vb + vc;
+    V3 nrm = cross(ab, ac);
+    // interior only if the triangle has a usable area: |n|^2 against the squared edge lengths
+    if (sum > 0.0f && dot(nrm, nrm) > 1e-10f * dot(ab, ab) * dot(ac, ac)) {
+        float denom = 1.0f / sum;
+        mask = 7;
+        return a + (vb * denom) * ab + (vc * denom) * ac;
     }
-    float denom = 1.0f / (va + vb + vc);
-    mask = 7;
-    return a + (vb * denom) * ab + (vc * denom) * ac;
+    int m1, m2, m3;
+    V3 p1 = closest_segment(a, b, m1), p2 = closest_segment(a, c, m2), p3 = closest_segment(b, c, m3);
+    float q1 = dot(p1, p1), q2 = dot(p2, p2), q3 = dot(p3, p3);
+    if (q1 <= q2 && q1 <= q3) { mask = m1; return p1; }                                   // a=1, b=2
+    if (q2 <= q3) { mask = (m2 & 1) | ((m2 & 2) << 1); return p2; }                       // a=1, c=4
+    mask = m3 << 1;                                                                       // b=2, c=4
+    return p3;
 }
 
 struct Simplex {
@@ -431,31 +452,36 @@ __device__ __forceinline__ bool simplex_solve(Simplex& S, V3& v) {
         simplex_keep3(S, S.p0, S.p1, S.p2, S.i0, S.i1, S.i2, mask);
         return false;
     }
-    // tetrahedron: faces (012|3) (013|2) (023|1) (123|0)
+    // tetrahedron: faces (012|3) (013|2) (023|1) (123|0).  The closest boundary point is taken over all four faces;
+    // the origin counts as enclosed only if every face test says "inside" AND the tetrahedron is not flat -- in
+    // float32 a sliver of four nearly coplanar support points must never certify a penetration.
     V3 A = S.p0, B = S.p1, Cc = S.p2, D = S.p3;
     int ia = S.i0, ib = S.i1, ic = S.i2, id = S.i3;
     float best = FLT_MAX;
     V3 bv = mk(0.f, 0.f, 0.f);
-    int bmask = 0, bf = -1;
-    bool outside_any = false;
+    int bmask = 0, bf = 0;
+    bool inside_all = true;
 #define SM_FACE(F, a, b, c, d)                                                  \
     {                                                                           \
         V3 nrm = cross(b - a, c - a);                                           \
         float sd = dot(d - a, nrm), so = -dot(a, nrm);                          \
-        if (sd == 0.0f || so * sd < 0.0f) {                                     \
-            outside_any = true;                                                 \
-            int m;                                                              \
-            V3 p = closest_triangle(a, b, c, m);                                \
-            float dd = dot(p, p);                                               \
-            if (dd < best) { best = dd; bv = p; bmask = m; bf = F; }            \
-        }                                                                       \
+        if (!(so * sd > 0.0f)) inside_all = false;                              \
+        int m;                                                                  \
+        V3 p = closest_triangle(a, b, c, m);                                    \
+        float dd = dot(p, p);                                                   \
+        if (dd < best) { best = dd; bv = p; bmask = m; bf = F; }                \
     }
     SM_FACE(0, A, B, Cc, D)
     SM_FACE(1, A, B, D, Cc)
     SM_FACE(2, A, Cc, D, B)
     SM_FACE(3, B, Cc, D, A)
 #undef SM_FACE
-    if (!outside_any || bf < 0) return true;
+    if (inside_all) {
+        V3 e1 = B - A, e2 = Cc - A, e3 = D - A;
+        float det = dot(e3, cross(e1, e2));
+        float scale2 = dot(e1, e1) * dot(e2, e2) * dot(e3, e3);
+        if (det * det > 1e-8f * scale2) return true;   // normalised volume above 1e-4: a genuine enclosure
+    }
     if (bf == 0) simplex_keep3(S, A, B, Cc, ia, ib, ic, bmask);
     else if (bf == 1) simplex_keep3(S, A, B, D, ia, ib, id, bmask);
     else if (bf == 2) simplex_keep3(S, A, Cc, D, ia, ic, id, bmask);
@@ -511,7 +537,7 @@ __device__ float gjk_warp(const float4* __restrict__ vA, int nA, const Xf& TA, c
         if (S.n < 3) S.i2 = -1;
         if (S.n < 2) S.i1 = -1;
         float nd = dot(nvv, nvv);
-        if (nd >= vv) break;  // numerical floor
+        if (!(nd < vv)) break;  // no progress (numerical floor) or a NaN from a degenerate simplex
         v = nvv; vv = nd;
         if (vv <= 1e-20f) return 0.0f;
         if (touch >= 0.0f && vv <= touch * touch) break;

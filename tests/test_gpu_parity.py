@@ -75,7 +75,7 @@ def test_safe_range_bit_exact():
 
 @pytest.mark.parametrize("name", ["space", "ball", "space_bm", "ball_bm"])
 def test_distances_match_oracle(name):
-    n = 192
+    n = 1024 if name.startswith("ball") else 256
     env = make_env(name, n, fill_pools=False)
     sc = env.scene
     rng = np.random.default_rng(1)
