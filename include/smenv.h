@@ -244,6 +244,10 @@ int smenv_observation(SmEnv* env, const SmBuffers* buf, SmStream stream);
 int smenv_counters(SmEnv* env, SmCounters* out, int reset);
 int smenv_enable_counters(SmEnv* env, int enable);
 int smenv_launch_count(SmEnv* env, unsigned long long* out);
+/* Debug: trace of one GJK call between shapes ia and ib for one env state given on the host (trace: 32 x 8 floats per
+ * iteration = simplex size, |v|^2, v.w, support ids, v; result: distance, iterations, then the 9 robot frames). */
+int smenv_debug_gjk(SmEnv* env, const double* kin_host, const double* obst_host, int ia, int ib, float upper,
+                    float* trace_host, float* result_host);
 
 #ifdef __cplusplus
 }

@@ -124,5 +124,5 @@ EXPORTED_SYMBOLS = [
     "smenv_last_error", "smenv_abi_version", "smenv_sizeof_scene", "smenv_sizeof_shape", "smenv_create",
     "smenv_destroy", "smenv_pool_sizes", "smenv_fill_pools", "smenv_pool_ptrs", "smenv_copy_pools", "smenv_set_state", "smenv_reset",
     "smenv_step", "smenv_step_random", "smenv_safe_range", "smenv_distances", "smenv_observation",
-    "smenv_counters", "smenv_enable_counters", "smenv_launch_count",
+    "smenv_counters", "smenv_enable_counters", "smenv_launch_count", "smenv_debug_gjk",
 ]

@@ -32,6 +32,7 @@ struct SmEnv {
     int start_pool_n = 0, ball_pool_n = 0;
     bool pools_filled = false;
     unsigned long long* d_counters = nullptr;
+    float* d_scratch = nullptr;  // per-env hand-over from joint_kernel to step_kernel
     bool count = false;
     size_t smem_bytes = 0;
     int grid = 0;
@@ -91,6 +92,15 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     }
     d.ts = sc->ts; d.action_mapping_factor = sc->action_mapping_factor; d.track_kp = sc->track_kp;
     d.track_vel = sc->track_vel;
+    {  // sub-step times exactly as np.linspace(ts / S, ts, S) produces them (actions.py:420-421)
+        const int S = sc->substeps;
+        volatile double start = sc->ts / (double)S;
+        volatile double step = S > 1 ? (sc->ts - start) / (double)(S - 1) : 0.0;
+        for (int k = 1; k <= S; ++k) {
+            volatile double prod = (double)(k - 1) * step;
+            d.sub_t[k] = (S <= 1 || k == S) ? sc->ts : start + prod;
+        }
+    }
     d.n_shapes = sc->n_shapes; d.n_verts = sc->n_verts;
     std::vector<float4> verts(sc->n_verts);
     for (int i = 0; i < sc->n_verts; ++i)
@@ -201,11 +211,12 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     CU(cudaMalloc((void**)&env->d_start_pool, (size_t)env->start_pool_n * SM_POOL_STRIDE * sizeof(double)));
     CU(cudaMemset(env->d_start_pool, 0, (size_t)env->start_pool_n * SM_POOL_STRIDE * sizeof(double)));
     if (env->ball_pool_n) CU(cudaMalloc((void**)&env->d_ball_pool, (size_t)env->ball_pool_n * SM_BALL_STRIDE * sizeof(double)));
+    CU(cudaMalloc((void**)&env->d_scratch, (size_t)num_envs * SM_SCRATCH_FLOATS * sizeof(float)));
+    CU(cudaMemset(env->d_scratch, 0, (size_t)num_envs * SM_SCRATCH_FLOATS * sizeof(float)));
     CU(cudaMalloc((void**)&env->d_counters, 8 * sizeof(unsigned long long)));
     CU(cudaMemset(env->d_counters, 0, 8 * sizeof(unsigned long long)));
 
-    env->smem_bytes = (((size_t)sc->n_verts * sizeof(float4) + 15) & ~(size_t)15) +
-                      SM_WARPS_PER_BLOCK * sizeof(WarpScratch) + sizeof(BlockShared);
+    env->smem_bytes = smem_bytes_for(sc->n_verts, SM_WARPS_PER_BLOCK);
     CU(cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
     CU(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
     CU(cudaFuncSetAttribute(fill_ball_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
@@ -226,7 +237,7 @@ extern "C" int smenv_destroy(SmEnv* env) {
     cudaSetDevice(env->device);
     if (g_active == env) g_active = nullptr;
     cudaFree(env->d_verts); cudaFree(env->d_plocal); cudaFree(env->d_start_pool); cudaFree(env->d_ball_pool);
-    cudaFree(env->d_counters);
+    cudaFree(env->d_counters); cudaFree(env->d_scratch);
     for (int o = 0; o < SM_MAX_OBSTACLES; ++o) { cudaFree(env->d_ppos[o]); cudaFree(env->d_pquat[o]); }
     delete env;
     return SM_OK;
@@ -383,10 +394,17 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
     cudaStream_t stream = (cudaStream_t)s;
     int rc = activate(env, stream);
     if (rc) return rc;
+    JointArgs JA;
+    JA.buf = *buf; JA.n = env->n; JA.random_actions = random_actions;
+    JA.k0 = (uint32_t)env->seed; JA.k1 = (uint32_t)(env->seed >> 32);
+    JA.step_counter = env->step_counter++;
+    JA.scratch = env->d_scratch;
+    joint_kernel<<<(env->n * 8 + 255) / 256, 256, 0, stream>>>(JA);
+    env->launches++;
     StepArgs A;
-    A.buf = *buf; A.n = env->n; A.auto_reset = auto_reset; A.random_actions = random_actions;
+    A.buf = *buf; A.n = env->n; A.auto_reset = auto_reset;
     A.k0 = (uint32_t)env->seed; A.k1 = (uint32_t)(env->seed >> 32);
-    A.step_counter = env->step_counter++;
+    A.scratch = env->d_scratch;
     A.start_pool = env->pools_filled ? env->d_start_pool : nullptr;
     A.start_pool_n = env->pools_filled ? env->start_pool_n : 0;
     A.ball_pool = env->pools_filled ? env->d_ball_pool : nullptr;
@@ -447,5 +465,24 @@ extern "C" int smenv_counters(SmEnv* env, SmCounters* out, int reset) {
 extern "C" int smenv_launch_count(SmEnv* env, unsigned long long* out) {
     if (!env || !out) return fail(SM_ERR_ARG, "null argument");
     *out = env->launches;
+    return SM_OK;
+}
+
+// debug: trace one GJK call on the device (not part of the product path; used by tools/ and tests to explain parity)
+extern "C" int smenv_debug_gjk(SmEnv* env, const double* kin_host, const double* obst_host, int ia, int ib, float upper,
+                               float* trace_host /* 32 x 8 */, float* result_host /* 4 + 12 * 9 */) {
+    if (!env || !kin_host || !obst_host || !trace_host || !result_host) return fail(SM_ERR_ARG, "null argument");
+    int rc = activate(env, 0);
+    if (rc) return rc;
+    double *dk, *dob; float *dt, *dr;
+    CU(cudaMalloc((void**)&dk, 32 * 8)); CU(cudaMalloc((void**)&dob, 16 * 8));
+    CU(cudaMalloc((void**)&dt, 256 * 4)); CU(cudaMalloc((void**)&dr, 128 * 4));
+    CU(cudaMemcpy(dk, kin_host, 32 * 8, cudaMemcpyHostToDevice)); CU(cudaMemcpy(dob, obst_host, 16 * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemset(dt, 0, 256 * 4)); CU(cudaMemset(dr, 0, 128 * 4));
+    CU(cudaFuncSetAttribute(debug_gjk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
+    debug_gjk_kernel<<<1, 32, env->smem_bytes, 0>>>(dk, dob, ia, ib, upper, dt, dr);
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(trace_host, dt, 256 * 4, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(result_host, dr, 128 * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dk); cudaFree(dob); cudaFree(dt); cudaFree(dr);
     return SM_OK;
 }

@@ -1,0 +1,82 @@
+// smenv_joint.cuh -- joint-space half of the env step: one THREAD per (env, joint), float64, strict IEEE.
+//
+//   safe acceleration range  -> action mapping -> 24 interpolated setpoints + motor-tracked pose -> new knot
+//   (actions.py:206-211, :268-280, :412-443; safe_motions_base.py:1179-1185, :1233-1277)
+//
+// Eight lanes serve one env (lane 7 idles for the 7-joint iiwa), so a warp advances four envs and ~88 % of the FP64
+// lanes do useful work; the geometry kernel (smenv_step.cuh, one warp per env) then consumes the per-env scratch
+// record written here.  Splitting the step keeps each kernel's code inside the instruction cache: the fused version
+// stalled ~48 cycles per issue on instruction fetch (profiles/r01_fused_step_ball.txt).
+#pragma once
+#include "smenv_kernels.cuh"
+
+#define SM_SCRATCH_FLOATS (SM_MAX_SUB * SM_MAX_JOINTS + 8) /* qsub[32][8] + misc[8] */
+#define SM_MISC_RCODE 0
+#define SM_MISC_JERK 1
+#define SM_MISC_UMAX 2
+
+struct JointArgs {
+    SmBuffers buf;
+    int n;
+    int random_actions;
+    uint32_t k0, k1, step_counter;
+    float* scratch;  // [n][SM_SCRATCH_FLOATS]
+};
+
+__global__ void __launch_bounds__(256) joint_kernel(JointArgs A) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int env = t >> 3, j = t & 7;
+    const int nj = c_sc.n_joints, S = c_sc.substeps;
+    const bool valid = env < A.n;
+    const bool jl = valid && j < nj;
+    const size_t e = valid ? (size_t)env : 0;
+    double* kin = A.buf.kin + e * SM_KIN_STRIDE;
+    float* scr = A.scratch + e * SM_SCRATCH_FLOATS;
+    double q = 0.0, v = 0.0, a = 0.0, qa = 0.0;
+    float uf = 0.0f;
+    if (jl) {
+        q = kin[j]; v = kin[8 + j]; a = kin[16 + j]; qa = kin[24 + j];
+        if (A.random_actions) {  // get_random_action (safe_motions_base.py:1327-1328)
+            uint4 r = philox((uint32_t)env, A.step_counter, (uint32_t)j, 0xAC71u, A.k0, A.k1);
+            uf = 2.0f * u01f(r.x) - 1.0f;
+        } else {
+            uf = A.buf.actions[e * nj + j];
+        }
+    }
+    double lo = 0.0, hi = 0.0, a1 = 0.0, q1 = q, v1 = v;
+    int code = 0;
+    float jerk_rel = 0.0f;
+    if (jl) {
+        safe_range_joint(j, q, v, a, lo, hi, code);
+        a1 = map_action((double)uf, lo, hi);
+        const double dt = xdiv(c_sc.ts, (double)S);
+        const double tvdt = xmul(c_sc.track_vel, dt);
+        const double jerk = xdiv(xsub(a1, a), c_sc.ts);      // actions.py:468-487, hoisted out of the sub-step loop
+        const double hj = xmul(0.5, jerk), ha = xmul(0.5, a), sj = xmul(1.0 / 6.0, jerk);
+        for (int k = 1; k <= S; ++k) {
+            const double tk = c_sc.sub_t[k];
+            double vs = xadd(xadd(v, xmul(a, tk)), xmul(xmul(hj, tk), tk));
+            double qs = xadd(xadd(xadd(q, xmul(v, tk)), xmul(xmul(ha, tk), tk)), xmul(xmul(xmul(sj, tk), tk), tk));
+            scr[(k - 1) * SM_MAX_JOINTS + j] = (float)qa;    // pose seen by the collision detection of sub-step k
+            qa = xadd(xadd(qa, xmul(c_sc.track_kp, xsub(qs, qa))), xmul(tvdt, vs));
+            q1 = qs; v1 = vs;                                // k == S: the new knot
+        }
+        jerk_rel = (float)(fabs(jerk) / c_sc.jerk_max[j]);   // rewards.py:181-186
+        kin[j] = q1; kin[8 + j] = v1; kin[16 + j] = a1; kin[24 + j] = qa;
+    } else if (valid) {
+        for (int k = 0; k < S; ++k) scr[k * SM_MAX_JOINTS + j] = 0.0f;
+    }
+    // per-env reductions over the eight lanes of the env (xor 1, 2, 4 stay inside the group)
+    unsigned rc = (unsigned)code;
+    float um = fabsf(uf);
+#pragma unroll
+    for (int m = 1; m < 8; m <<= 1) {
+        rc |= __shfl_xor_sync(FULL, rc, m);
+        jerk_rel = fmaxf(jerk_rel, __shfl_xor_sync(FULL, jerk_rel, m));
+        um = fmaxf(um, __shfl_xor_sync(FULL, um, m));
+    }
+    if (valid && j < 4) {
+        float val = j == SM_MISC_RCODE ? (float)rc : j == SM_MISC_JERK ? jerk_rel : j == SM_MISC_UMAX ? um : 0.0f;
+        scr[SM_MAX_SUB * SM_MAX_JOINTS + j] = val;
+    }
+}

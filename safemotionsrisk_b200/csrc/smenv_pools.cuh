@@ -1,4 +1,5 @@
-// smenv_pools.cuh -- device-side rejection sampling of start states and ball launches (one warp per pool entry).
+// smenv_pools.cuh -- device-side rejection sampling of start states and ball launches (one warp per pool entry),
+// reset, and the parity hooks.
 //
 // Restates, with Philox streams instead of the global np.random stream (safe_motions_base.py:1704-1710):
 //   * get_starting_point_joint_pos_vel_acc / _get_collision_free_robot_position   ctlp.py:1461-1656, :1980-2138
@@ -22,19 +23,22 @@ __device__ __forceinline__ uint64_t key64(uint32_t k0, uint32_t k1) { return ((u
 
 // static / self clearance of the pose whose frames are in W.fr (ctlp.py:2140-2208): query distance thr + 0.005,
 // violated if d < thr
-__device__ bool pose_is_free(const float4* verts, WarpScratch& W, float thr_static, float thr_self, int lane) {
-    float d = min_pair_list(verts, c_sc.static_pairs, c_sc.n_static_pairs, thr_static + 0.005f, W.fr, W.ob, lane, nullptr,
-                            nullptr);
+__device__ __noinline__ bool pose_is_free(const float4* verts, const SceneSmem& sm, WarpScratch& W, float thr_static,
+                                          float thr_self, int lane) {
+    float cap = thr_static + 0.005f;
+    float d = min_pairs(verts, sm, 0, sm.static_pairs, nullptr, c_sc.n_static_pairs, 1, 0, cap, cap, W.fr, W.obx, lane,
+                        nullptr);
     if (d < thr_static) return false;
-    d = min_pair_list(verts, c_sc.self_pairs, c_sc.n_self_pairs, thr_self + 0.005f, W.fr, W.ob, lane, nullptr, nullptr);
+    cap = thr_self + 0.005f;
+    d = min_pairs(verts, sm, 0, sm.self_pairs, nullptr, c_sc.n_self_pairs, 1, 0, cap, cap, W.fr, W.obx, lane, nullptr);
     return !(d < thr_self);
 }
 
 // Random joint vector with the target point inside the box and the static / self distances above the thresholds
 // (_get_collision_free_robot_position, ctlp.py:1980-2138).  Lane j gets q_j; frames are left in W.fr.
-__device__ int sample_free_pose(Rng& rng, const float4* verts, WarpScratch& W, const double* box_min,
-                                const double* box_max, float thr_static, float thr_self, double& q_out, V3& target,
-                                int lane) {
+__device__ __noinline__ double sample_free_pose(Rng& rng, const float4* verts, const SceneSmem& sm, WarpScratch& W,
+                                                const double* box_min, const double* box_max, float thr_static,
+                                                float thr_self, V3& target, int lane) {
     const int nj = c_sc.n_joints, j = lane & 7;
     const float ox = c_sc.target_t[0] + c_sc.target_R[0] * c_sc.target_offset[0] +
                      c_sc.target_R[1] * c_sc.target_offset[1] + c_sc.target_R[2] * c_sc.target_offset[2];
@@ -44,27 +48,27 @@ __device__ int sample_free_pose(Rng& rng, const float4* verts, WarpScratch& W, c
                      c_sc.target_R[7] * c_sc.target_offset[1] + c_sc.target_R[8] * c_sc.target_offset[2];
     int attempts = 0;
     double ql = 0.0;
+#pragma unroll 1
     while (true) {
         ++attempts;
+#pragma unroll 1
         for (int jj = 0; jj < nj; ++jj) {  // np.random.uniform(lower, upper) (ctlp.py:2035-2037)
             double r = rng.uniform(c_sc.pos_lo[jj], c_sc.pos_hi[jj]);
             if (j == jj) ql = r;
         }
-        frames_from_q64(ql, W.fr, lane);
-        __syncwarp();
+        frames_from_q64(sm, ql, W.fr, lane);
         target = xf_apply(W.fr[nj], ox, oy, oz);
         bool ok = target.x >= box_min[0] && target.x <= box_max[0] && target.y >= box_min[1] &&
                   target.y <= box_max[1] && target.z >= box_min[2] && target.z <= box_max[2];  // ctlp.py:2054-2061
-        if (ok) ok = pose_is_free(verts, W, thr_static, thr_self, lane);
+        if (ok) ok = pose_is_free(verts, sm, W, thr_static, thr_self, lane);
         __syncwarp();
         if (ok || attempts >= 100000) break;
     }
-    q_out = ql;
-    return attempts;
+    return ql;
 }
 
 // Ball.get_target_height_time (ctlp.py:4346-4361); NaN if the height is never reached
-__device__ __forceinline__ double target_height_time(double h0, double vz, double h) {
+__device__ __noinline__ double target_height_time(double h0, double vz, double h) {
     const double g = 9.81;
     double sq = vz * vz + 2.0 * g * (h0 - h);
     if (sq >= 0.0) {
@@ -76,18 +80,18 @@ __device__ __forceinline__ double target_height_time(double h0, double vz, doubl
 
 __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) fill_ball_pool_kernel(PoolArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* verts = reinterpret_cast<float4*>(smem_raw);
-    size_t off = ((size_t)c_sc.n_verts * sizeof(float4) + 15) & ~(size_t)15;
-    WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smem_raw + off);
+    SmemLayout L = block_prologue(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < c_sc.n_verts; i += blockDim.x) verts[i] = __ldg(c_sc.verts + i);
-    __syncthreads();
-    WarpScratch& W = scratch[warp];
+    WarpScratch& W = L.scratch[warp];
+    const SceneSmem& sm = L.bs->scene;
+    const float4* verts = L.verts;
     const double g = 9.81, spd = c_sc.ball_speed, rad = c_sc.ball_radius;
     const double upd = c_sc.ts / (double)c_sc.substeps;
+#pragma unroll 1
     for (int e = blockIdx.x * SM_WARPS_PER_BLOCK + warp; e < A.ball_pool_n; e += gridDim.x * SM_WARPS_PER_BLOCK) {
         Rng rng(key64(A.k0, A.k1), (uint32_t)e, 0xBA11u);
-        double rel[3] = {0, 0, 0}, vel[3] = {0, 0, 0}, nmax = 0.0, nhit = 0.0;
+        double rel[3] = {0, 0, 0}, vel[3] = {0, 0, 1}, nmax = 0.0, nhit = 0.0;
+#pragma unroll 1
         for (int attempt = 0; attempt < 25000; ++attempt) {
             // release point on the sphere segment (ctlp.py:1943-1952)
             double h = rng.uniform(c_sc.ball_height_min, c_sc.ball_height_max);
@@ -97,10 +101,9 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) fill_ball_pool_kernel
             rel[1] = c_sc.ball_sphere_center[1] + rr * sin(ang);
             rel[2] = c_sc.ball_sphere_center[2] + h;
             // aim at the target point of a random collision-free robot pose (ctlp.py:1782-1790)
-            double qd;
             V3 tgt;
-            sample_free_pose(rng, verts, W, c_sc.ball_target_box_min, c_sc.ball_target_box_max,
-                             (float)c_sc.ball_target_min_static, (float)c_sc.ball_target_min_self, qd, tgt, lane);
+            sample_free_pose(rng, verts, sm, W, c_sc.ball_target_box_min, c_sc.ball_target_box_max,
+                             (float)c_sc.ball_target_min_static, (float)c_sc.ball_target_min_self, tgt, lane);
             double dx = (double)tgt.x - rel[0], dy = (double)tgt.y - rel[1], dh = (double)tgt.z - rel[2];
             double dxy = sqrt(dx * dx + dy * dy);
             double num = spd * spd * spd * spd - g * (g * dxy * dxy + 2.0 * dh * spd * spd);  // ctlp.py:1797
@@ -125,9 +128,11 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) fill_ball_pool_kernel
             }
             double final_t = nan("");
             if (valid) {  // Ball.get_final_ball_position (ctlp.py:4304-4344): straight-line exit of the box, or floor
+#pragma unroll 1
                 for (int i = 0; i < 2; ++i) {
                     int ia = (i + 1) % 3, ib = (i + 2) % 3;
                     if (vel[i] != 0.0) {
+#pragma unroll 1
                         for (int mm = 0; mm < 2; ++mm) {
                             double bound = mm == 0 ? c_sc.ball_final_min[i] : c_sc.ball_final_max[i];
                             double t = (bound - rel[i]) / vel[i];
@@ -179,33 +184,35 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) fill_ball_pool_kernel
 
 __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) fill_start_pool_kernel(PoolArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* verts = reinterpret_cast<float4*>(smem_raw);
-    size_t off = ((size_t)c_sc.n_verts * sizeof(float4) + 15) & ~(size_t)15;
-    WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smem_raw + off);
+    SmemLayout L = block_prologue(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < c_sc.n_verts; i += blockDim.x) verts[i] = __ldg(c_sc.verts + i);
-    __syncthreads();
-    WarpScratch& W = scratch[warp];
+    WarpScratch& W = L.scratch[warp];
+    const SceneSmem& sm = L.bs->scene;
+    const float4* verts = L.verts;
     const int nj = c_sc.n_joints, j = lane & 7, S = c_sc.substeps;
     const bool jl = lane < nj;
     const float thr_s = (float)c_sc.min_start_distance, thr_self = (float)c_sc.min_start_self;
     const double dt = xdiv(c_sc.ts, (double)S), tvdt = xmul(c_sc.track_vel, dt);
     const int kind = c_sc.n_obstacles > 0 ? c_sc.obst_kind[0] : SM_OBST_NONE;
+#pragma unroll 1
     for (int e = blockIdx.x * SM_WARPS_PER_BLOCK + warp; e < A.start_pool_n; e += gridDim.x * SM_WARPS_PER_BLOCK) {
         Rng rng(key64(A.k0, A.k1), (uint32_t)e, 0x51A7u);
         double q = 0.0, v = 0.0, a = 0.0;
         uint32_t lane_ctr = 0;
+#pragma unroll 1
         for (int outer = 0; outer < 1000; ++outer) {
             V3 tgt;
-            sample_free_pose(rng, verts, W, c_sc.start_box_min, c_sc.start_box_max, thr_s, thr_self, q, tgt, lane);
+            q = sample_free_pose(rng, verts, sm, W, c_sc.start_box_min, c_sc.start_box_max, thr_s, thr_self, tgt, lane);
             v = 0.0; a = 0.0;
             if (rng.uniform() < c_sc.kinematic_sampling_probability) {
                 // per joint: up to 5 velocities x 10 accelerations with violation code 0 (ctlp.py:1503-1525)
                 bool found = false;
                 if (jl) {
+#pragma unroll 1
                     for (int iv = 0; iv < 5 && !found; ++iv) {
                         uint4 r = philox((uint32_t)e, 0x7000u + lane_ctr++, (uint32_t)lane, 0x51A8u, A.k0, A.k1);
                         double vj = c_sc.vel_max[j] * (2.0 * u01d(r.x, r.y) - 1.0);
+#pragma unroll 1
                         for (int ia = 0; ia < 10 && !found; ++ia) {
                             uint4 r2 = philox((uint32_t)e, 0x7000u + lane_ctr++, (uint32_t)lane, 0x51A9u, A.k0, A.k1);
                             double aj = c_sc.acc_max[j] * (2.0 * u01d(r2.x, r2.y) - 1.0);
@@ -219,52 +226,55 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) fill_start_pool_kerne
                 if (__all_sync(FULL, !jl || found)) break;
                 continue;  // some joint found no feasible (v, a): new pose (ctlp.py:1547-1556)
             }
-            // random walk from rest with random actions (ctlp.py:1558-1654)
-            double hq[3] = {q, q, q}, hv[3] = {0, 0, 0}, ha[3] = {0, 0, 0};  // last three states, [2] = newest
+            // random walk from rest with random actions (ctlp.py:1558-1654); h0 = oldest ... h2 = newest state
+            double hq0 = q, hq1 = q, hq2 = q, hv0 = 0, hv1 = 0, hv2 = 0, ha0 = 0, ha1 = 0, ha2 = 0;
             int len = 1;
+#pragma unroll 1
             while (true) {
-                if (rng.uniform() < c_sc.stay_in_state_probability) { q = hq[2]; v = hv[2]; a = ha[2]; break; }
-                double lo = 0.0, hi = 0.0, qe = hq[2], ve = hv[2], ae = ha[2];
+                if (rng.uniform() < c_sc.stay_in_state_probability) { q = hq2; v = hv2; a = ha2; break; }
+                double lo = 0.0, hi = 0.0, qe = hq2, ve = hv2, ae = ha2;
                 int code;
                 uint4 r = philox((uint32_t)e, 0x7000u + lane_ctr++, (uint32_t)lane, 0x51AAu, A.k0, A.k1);
                 if (jl) {
-                    safe_range_joint(j, hq[2], hv[2], ha[2], lo, hi, code);
+                    safe_range_joint(j, hq2, hv2, ha2, lo, hi, code);
                     double un = 2.0 * u01d(r.x, r.y) - 1.0;
                     double a1 = lo + 0.5 * (un + 1.0) * (hi - lo);  // denormalize (ctlp.py:1577-1578)
                     double as_;
-                    interpolate(hq[2], hv[2], ha[2], a1, c_sc.ts, qe, ve, as_);
+                    interpolate(hq2, hv2, ha2, a1, c_sc.ts, qe, ve, as_);
                     ae = a1;
                 }
-                frames_from_q64(qe, W.fr, lane);
-                __syncwarp();
-                bool free_pose = pose_is_free(verts, W, thr_s, thr_self, lane);
+                frames_from_q64(sm, qe, W.fr, lane);
+                bool free_pose = pose_is_free(verts, sm, W, thr_s, thr_self, lane);
                 __syncwarp();
                 if (free_pose) {
-                    hq[0] = hq[1]; hv[0] = hv[1]; ha[0] = ha[1];
-                    hq[1] = hq[2]; hv[1] = hv[2]; ha[1] = ha[2];
-                    hq[2] = qe; hv[2] = ve; ha[2] = ae;
+                    hq0 = hq1; hv0 = hv1; ha0 = ha1;
+                    hq1 = hq2; hv1 = hv2; ha1 = ha2;
+                    hq2 = qe; hv2 = ve; ha2 = ae;
                     ++len;
                 } else {  // collision: one of the three latest states (ctlp.py:1638-1648)
                     int m = len < 3 ? len : 3;
                     int sel = 1 + (int)(rng.next4().x % (uint32_t)m);
-                    q = hq[3 - sel]; v = hv[3 - sel]; a = ha[3 - sel];
+                    q = sel == 1 ? hq2 : sel == 2 ? hq1 : hq0;
+                    v = sel == 1 ? hv2 : sel == 2 ? hv1 : hv0;
+                    a = sel == 1 ? ha2 : sel == 2 ? ha1 : ha0;
                     break;
                 }
             }
             break;
         }
         // ---------------- obstacles at reset
-        frames_from_q64(q, W.fr, lane);
-        __syncwarp();
+        frames_from_q64(sm, q, W.fr, lane);
         double ob = 0.0;
         if (kind == SM_OBST_PLANET) {  // Planet.reset: random phase without contact (ctlp.py:4470-4501)
             int idx = 0;
+#pragma unroll 1
             for (int t = 0; t < 1000; ++t) {
                 idx = (int)(rng.next4().x % (uint32_t)c_sc.planet_steps);
-                if (lane < c_sc.n_obstacles) planet_pose(lane, idx, W.ob2[lane]);
+                if (lane < c_sc.n_obstacles) planet_pose(lane, idx, W.obx2[lane]);
                 __syncwarp();
                 bool hit = false;
-                for (int o = 0; o < c_sc.n_obstacles && !hit; ++o) hit = contact_exists(verts, o, W.fr, W.ob2, lane, nullptr);
+                for (int o = 0; o < c_sc.n_obstacles && !hit; ++o)
+                    hit = contact_exists(verts, sm, o, W.fr, W.obx2, lane, nullptr);
                 __syncwarp();
                 if (!hit) break;
             }
@@ -272,18 +282,20 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) fill_start_pool_kerne
             if (lane == SM_OB_INDEX) ob = (double)((idx + 1) % c_sc.planet_steps);
         } else if (kind == SM_OBST_BALL && A.ball_pool_n > 0) {
             const double* b = A.ball_pool + (size_t)(rng.next4().x % (uint32_t)A.ball_pool_n) * SM_BALL_STRIDE;
-            double bp0[3] = {b[0], b[1], b[2]}, bv0[3] = {b[3], b[4], b[5]}, be0[3] = {b[6], b[7], b[8]};
+            if (lane < 10) W.ob[SM_OB_BALL_P0 + lane] = b[lane];
+            __syncwarp();
             double nmax = b[10], nhit = b[11];
             double n0 = 0.0;
             if (c_sc.ball_random_initial) {  // ctlp.py:1090-1111
                 double mc = nhit < nmax ? nhit : nmax;
                 int max_ts = (int)floor(mc / (double)S);
                 if (max_ts < 0) max_ts = 0;
+#pragma unroll 1
                 for (int t = 0; t < 1000; ++t) {
                     n0 = (double)((int)(rng.next4().x % (uint32_t)(max_ts + 1)) * S);
-                    if (lane == 0) ball_pose(bp0, bv0, be0, b[9], n0 * dt, W.ob2[0]);
+                    if (lane == 0) ball_pose(W.ob, n0 * dt, W.obx2[0]);
                     __syncwarp();
-                    bool hit = contact_exists(verts, 0, W.fr, W.ob2, lane, nullptr);
+                    bool hit = contact_exists(verts, sm, 0, W.fr, W.obx2, lane, nullptr);
                     __syncwarp();
                     if (!hit) break;
                 }
@@ -302,6 +314,7 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) fill_start_pool_kerne
         double* o = A.start_pool + (size_t)e * SM_POOL_STRIDE;
         o[lane] = j < nj ? (grp == 0 ? qq : grp == 1 ? vv : grp == 2 ? aa : tt) : 0.0;
         if (lane < SM_OBST_STRIDE) o[SM_KIN_STRIDE + lane] = ob;
+        __syncwarp();
     }
 }
 
@@ -322,18 +335,14 @@ __global__ void __launch_bounds__(256) reset_kernel(ResetArgs A) {
     int4 ep = *reinterpret_cast<const int4*>(A.buf.episode + 4 * (size_t)env);
     uint4 r = philox((uint32_t)env, (uint32_t)ep.y, 0x5E7u, 1u, A.k0, A.k1);
     const double* e = A.start_pool + (size_t)(r.x % (uint32_t)A.start_pool_n) * SM_POOL_STRIDE;
-    double kv = e[lane];
-    double ob = lane < SM_OBST_STRIDE ? e[SM_KIN_STRIDE + lane] : 0.0;
-    A.buf.kin[(size_t)env * SM_KIN_STRIDE + lane] = kv;
-    if (lane < SM_OBST_STRIDE) A.buf.obst[(size_t)env * SM_OBST_STRIDE + lane] = ob;
+    A.buf.kin[(size_t)env * SM_KIN_STRIDE + lane] = e[lane];
+    if (lane < SM_OBST_STRIDE) A.buf.obst[(size_t)env * SM_OBST_STRIDE + lane] = e[SM_KIN_STRIDE + lane];
     if (lane == 0) {
         *reinterpret_cast<int4*>(A.buf.episode + 4 * (size_t)env) = make_int4(0, ep.y + 1, ep.z, ep.w);
         A.buf.ep_return[env] = 0.0;
         if (A.buf.done) A.buf.done[env] = 0;
     }
-    const int j = lane & 7;
-    write_observation(A.buf.obs + (size_t)env * c_sc.obs_size, shfl_d(kv, j), shfl_d(kv, 8 + j), shfl_d(kv, 16 + j), ob,
-                      lane);
+    write_observation(A.buf.obs + (size_t)env * c_sc.obs_size, e, e + SM_KIN_STRIDE, lane);
 }
 
 // observation only (after smenv_set_state)
@@ -341,10 +350,8 @@ __global__ void __launch_bounds__(256) observation_kernel(SmBuffers buf, int n) 
     const int lane = threadIdx.x & 31;
     const int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (env >= n) return;
-    double kv = buf.kin[(size_t)env * SM_KIN_STRIDE + lane];
-    double ob = lane < SM_OBST_STRIDE ? buf.obst[(size_t)env * SM_OBST_STRIDE + lane] : 0.0;
-    const int j = lane & 7;
-    write_observation(buf.obs + (size_t)env * c_sc.obs_size, shfl_d(kv, j), shfl_d(kv, 8 + j), shfl_d(kv, 16 + j), ob, lane);
+    write_observation(buf.obs + (size_t)env * c_sc.obs_size, buf.kin + (size_t)env * SM_KIN_STRIDE,
+                      buf.obst + (size_t)env * SM_OBST_STRIDE, lane);
 }
 
 // ---------------- parity hooks: pieces of the step on caller-supplied states
@@ -364,42 +371,44 @@ __global__ void safe_range_kernel(const double* kin, double* lo, double* hi, int
 __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32)
 distances_kernel(const double* kin, const double* obst, float* d_static, float* d_self, float* d_moving, int n) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* verts = reinterpret_cast<float4*>(smem_raw);
-    size_t off = ((size_t)c_sc.n_verts * sizeof(float4) + 15) & ~(size_t)15;
-    WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smem_raw + off);
+    SmemLayout L = block_prologue(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < c_sc.n_verts; i += blockDim.x) verts[i] = __ldg(c_sc.verts + i);
-    __syncthreads();
-    WarpScratch& W = scratch[warp];
+    WarpScratch& W = L.scratch[warp];
+    const SceneSmem& sm = L.bs->scene;
     const int kind = c_sc.n_obstacles > 0 ? c_sc.obst_kind[0] : SM_OBST_NONE;
+#pragma unroll 1
     for (int env = blockIdx.x * SM_WARPS_PER_BLOCK + warp; env < n; env += gridDim.x * SM_WARPS_PER_BLOCK) {
-        double kv = kin[(size_t)env * SM_KIN_STRIDE + lane];
-        double ob = lane < SM_OBST_STRIDE ? obst[(size_t)env * SM_OBST_STRIDE + lane] : 0.0;
-        double q = shfl_d(kv, lane & 7);
-        frames_from_q64(q, W.fr, lane);
-        int idx = (int)shfl_d(ob, SM_OB_INDEX);
-        double latch = shfl_d(ob, SM_OB_LATCH), active = shfl_d(ob, SM_OB_BALL_ACTIVE), t = shfl_d(ob, SM_OB_BALL_T);
-        double bp0[3] = {shfl_d(ob, SM_OB_BALL_P0), shfl_d(ob, SM_OB_BALL_P0 + 1), shfl_d(ob, SM_OB_BALL_P0 + 2)};
-        double bv0[3] = {shfl_d(ob, SM_OB_BALL_V0), shfl_d(ob, SM_OB_BALL_V0 + 1), shfl_d(ob, SM_OB_BALL_V0 + 2)};
-        double be0[3] = {shfl_d(ob, SM_OB_BALL_EULER0), shfl_d(ob, SM_OB_BALL_EULER0 + 1),
-                         shfl_d(ob, SM_OB_BALL_EULER0 + 2)};
-        double bom = shfl_d(ob, SM_OB_BALL_OMEGA);
-        if (kind == SM_OBST_PLANET && lane < c_sc.n_obstacles) planet_pose(lane, idx, W.ob[lane]);
-        if (kind == SM_OBST_BALL && lane == 0) ball_pose(bp0, bv0, be0, bom, t, W.ob[0]);
+        if (lane < SM_OBST_STRIDE) W.ob[lane] = obst[(size_t)env * SM_OBST_STRIDE + lane];
         __syncwarp();
-        const float cap = (float)c_sc.static_cap, query = (float)c_sc.moving_query;
-        float ds = min_pair_list(verts, c_sc.static_pairs, c_sc.n_static_pairs, cap, W.fr, W.ob, lane, nullptr, nullptr);
-        float dse = min_pair_list(verts, c_sc.self_pairs, c_sc.n_self_pairs, cap, W.fr, W.ob, lane, nullptr, nullptr);
-        float dm = query + 0.002f;
-        if (latch != 0.0) dm = 0.0f;
-        else if (c_sc.n_mov_reward > 0)
-            for (int o = 0; o < c_sc.n_obstacles; ++o) {
-                if (kind == SM_OBST_BALL && active == 0.0) continue;
-                dm = min_moving(verts, c_sc.mov_reward, c_sc.n_mov_reward, o, query, dm, W.fr, W.ob, lane, nullptr,
-                                nullptr);
-                if (dm <= 0.0f) break;
-            }
+        frames_from_q64(sm, kin[(size_t)env * SM_KIN_STRIDE + (lane & 7)], W.fr, lane);
+        if (kind == SM_OBST_PLANET && lane < c_sc.n_obstacles) planet_pose(lane, (int)W.ob[SM_OB_INDEX], W.obx[lane]);
+        if (kind == SM_OBST_BALL && lane == 0) ball_pose(W.ob, W.ob[SM_OB_BALL_T], W.obx[0]);
+        __syncwarp();
+        float ds, dse, dm;
+        all_distances(L.verts, sm, W.fr, W.obx, W.ob[SM_OB_LATCH] != 0.0,
+                      kind == SM_OBST_BALL && W.ob[SM_OB_BALL_ACTIVE] == 0.0, ds, dse, dm, lane, nullptr);
         __syncwarp();
         if (lane == 0) { d_static[env] = ds; d_self[env] = dse; d_moving[env] = dm; }
     }
+}
+
+// debug hook: trace of one GJK call (8 floats per iteration: simplex size, |v|^2, v.w, support ids, v)
+__global__ void __launch_bounds__(32) debug_gjk_kernel(const double* kin, const double* obst, int ia, int ib, float upper,
+                                                       float* trace, float* result) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemLayout L = block_prologue(smem_raw);
+    const int lane = threadIdx.x & 31;
+    WarpScratch& W = L.scratch[0];
+    const SceneSmem& sm = L.bs->scene;
+    const int kind = c_sc.n_obstacles > 0 ? c_sc.obst_kind[0] : SM_OBST_NONE;
+    if (lane < SM_OBST_STRIDE) W.ob[lane] = obst[lane];
+    __syncwarp();
+    frames_from_q64(sm, kin[lane & 7], W.fr, lane);
+    if (kind == SM_OBST_PLANET && lane < c_sc.n_obstacles) planet_pose(lane, (int)W.ob[SM_OB_INDEX], W.obx[lane]);
+    if (kind == SM_OBST_BALL && lane == 0) ball_pose(W.ob, W.ob[SM_OB_BALL_T], W.obx[0]);
+    __syncwarp();
+    GjkCounters cnt = {0u, 0u, 0u, trace};
+    float d = pair_distance(L.verts, sm, ia, ib, W.fr, W.obx, upper, -1.f, lane, &cnt);
+    if (lane == 0) { result[0] = d; result[1] = (float)cnt.iters; }
+    if (lane <= c_sc.n_joints) for (int i = 0; i < 12; ++i) result[4 + 12 * lane + i] = i < 9 ? W.fr[lane].r[i] : W.fr[lane].t[i - 9];
 }

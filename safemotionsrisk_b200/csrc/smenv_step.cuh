@@ -1,14 +1,15 @@
-// smenv_step.cuh -- one env step per warp (SafeMotionsBase.step, safe_motions_base.py:1043-1227).
+// smenv_step.cuh -- geometry half of the env step, one WARP per env (SafeMotionsBase.step, safe_motions_base.py:
+// 1043-1227): sub-step contacts, distances at the new knot, reward, termination, observation, auto-reset.
+// The joint-space half (safe range, action mapping, setpoints) ran before in joint_kernel (smenv_joint.cuh).
 #pragma once
-#include "smenv_kernels.cuh"
+#include "smenv_joint.cuh"
 
 struct StepArgs {
     SmBuffers buf;
     int n;
     int auto_reset;
-    int random_actions;
     uint32_t k0, k1;        // Philox key (seed)
-    uint32_t step_counter;  // launches so far: decorrelates the random actions of successive steps
+    const float* scratch;   // [n][SM_SCRATCH_FLOATS] written by joint_kernel
     const double* start_pool;
     int start_pool_n;
     const double* ball_pool;
@@ -16,109 +17,86 @@ struct StepArgs {
     unsigned long long* counters;  // device SmCounters, or NULL
 };
 
-// Broad phase of the sub-step contact test: lane k checks sub-step k+1.  Returns, per obstacle, whether some robot
-// bounding sphere comes within the contact threshold of the obstacle's bounding sphere at the poses that Bullet's
-// collision detection of that sub-step sees (tracked robot pose before integration, obstacle pose of the previous
-// update).
-__device__ __forceinline__ void substep_broad_phase(const WarpScratch& W, int k, V3 oc0, V3 oc1, bool use0, bool use1,
-                                                    bool& f0, bool& f1) {
-    f0 = f1 = false;
-    const float* qrow = W.qsub[k];
+// Broad phase of the sub-step contact test: lane k checks sub-step k+1.  Returns a 2-bit mask (bit o = obstacle o)
+// telling whether some robot bounding sphere comes within the contact threshold of the obstacle's bounding sphere at
+// the poses Bullet's collision detection of that sub-step sees (tracked robot pose before integration, obstacle pose
+// of the previous update).  Each lane runs its own serial FK chain.
+__device__ __noinline__ int substep_broad_phase(const SceneSmem& sm, const float* qrow, V3 oc0, V3 oc1, int use_mask) {
+    int hit = 0;
     Xf F;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) F.r[i] = (i % 4 == 0) ? 1.0f : 0.0f;
-    F.t[0] = F.t[1] = F.t[2] = 0.0f;
+    xf_identity(F);
+#pragma unroll 1
     for (int f = 0; f <= c_sc.n_joints; ++f) {
         if (f > 0) {  // serial chain: frame f hangs off frame f-1 (checked on the host)
-            int j = f - 1;
-            float s, c, R1[9], Rj[9];
+            const int j = f - 1;
+            float s, c;
             sincosf(qrow[j], &s, &c);
-            mat_mul(F.r, c_sc.jR[j], R1);
-            V3 tp = xf_apply(F, c_sc.jt[j][0], c_sc.jt[j][1], c_sc.jt[j][2]);
-            axis_angle(c_sc.jaxis[j], c, s, Rj);
-            mat_mul(R1, Rj, F.r);
-            F.t[0] = tp.x; F.t[1] = tp.y; F.t[2] = tp.z;
+            Xf L, C;
+            float Rj[9];
+            axis_angle(sm.jaxis[j][0], sm.jaxis[j][1], sm.jaxis[j][2], c, s, Rj);
+            const float* A = sm.jR[j];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    L.r[3 * i + k] = fmaf(A[3 * i], Rj[k], fmaf(A[3 * i + 1], Rj[3 + k], A[3 * i + 2] * Rj[6 + k]));
+            L.t[0] = sm.jt[j][0]; L.t[1] = sm.jt[j][1]; L.t[2] = sm.jt[j][2];
+            xf_compose(F, L, C);
+            F = C;
         }
+#pragma unroll 1
         for (int slot = c_sc.contact_frame_start[f]; slot < c_sc.contact_frame_start[f + 1]; ++slot) {
-            const DevShape& sh = c_sc.shapes[c_sc.mov_contact[slot]];
+            const DevShape& sh = sm.shapes[sm.mov_contact[slot]];
             V3 c = xf_apply(F, sh.cx, sh.cy, sh.cz);
             float rr = sh.radius + sh.margin;
-            if (use0) {
+            if (use_mask & 1) {
                 V3 d = c - oc0;
-                float lim = rr + c_sc.obst_radius[0] + c_sc.contact_thresh[0][slot];
-                f0 = f0 || dot(d, d) <= lim * lim;
+                float lim = rr + c_sc.obst_radius[0] + sm.contact_thresh[0][slot];
+                if (dot(d, d) <= lim * lim) hit |= 1;
             }
-            if (use1) {
+            if (use_mask & 2) {
                 V3 d = c - oc1;
-                float lim = rr + c_sc.obst_radius[1] + c_sc.contact_thresh[1][slot];
-                f1 = f1 || dot(d, d) <= lim * lim;
+                float lim = rr + c_sc.obst_radius[1] + sm.contact_thresh[1][slot];
+                if (dot(d, d) <= lim * lim) hit |= 2;
             }
         }
     }
+    return hit;
 }
 
 template <bool COUNT>
 __device__ void step_env(const StepArgs& A, int env, const float4* __restrict__ verts, WarpScratch& W, BlockShared& bs,
                          int lane) {
+    const SceneSmem& sm = bs.scene;
     const int nj = c_sc.n_joints, S = c_sc.substeps;
-    const int j = lane & 7;
-    const bool jl = lane < nj;
-    GjkCounters cnt = {0u, 0u, 0u};
+    GjkCounters cnt = {0u, 0u, 0u, nullptr};
     GjkCounters* pc = COUNT ? &cnt : nullptr;
 
-    // ---------------- load the env records (coalesced: one 256-byte and one 128-byte row per env)
-    double kv = A.buf.kin[(size_t)env * SM_KIN_STRIDE + lane];
-    double q = shfl_d(kv, j), v = shfl_d(kv, 8 + j), a = shfl_d(kv, 16 + j), qa = shfl_d(kv, 24 + j);
-    double ob = lane < SM_OBST_STRIDE ? A.buf.obst[(size_t)env * SM_OBST_STRIDE + lane] : 0.0;
-    int4 ep = *reinterpret_cast<const int4*>(A.buf.episode + 4 * (size_t)env);
+    // ---------------- load the env records; the kinematic record already holds the new knot (joint_kernel)
+    const double* kin = A.buf.kin + (size_t)env * SM_KIN_STRIDE;
+    const float* scr = A.scratch + (size_t)env * SM_SCRATCH_FLOATS;
+    const double q1 = kin[lane & 7];                                  // joint angle of the new knot
+    if (lane < SM_OBST_STRIDE) W.ob[lane] = A.buf.obst[(size_t)env * SM_OBST_STRIDE + lane];
+    for (int i = lane; i < S * SM_MAX_JOINTS; i += 32) (&W.qsub[0][0])[i] = scr[i];
+    const int4 ep = *reinterpret_cast<const int4*>(A.buf.episode + 4 * (size_t)env);
     const int ep_len = ep.x + 1;  // safe_motions_base.py:1044
-
-    float uf = 0.0f;
-    if (A.random_actions) {  // get_random_action (safe_motions_base.py:1327-1328), U(-1, 1) per joint
-        uint4 r = philox((uint32_t)env, A.step_counter, (uint32_t)j, 0xAC71u, A.k0, A.k1);
-        uf = 2.0f * u01f(r.x) - 1.0f;
-    } else if (jl) {
-        uf = A.buf.actions[(size_t)env * nj + j];
-    }
-    const double u = (double)uf;
-
-    // ---------------- safe range, action mapping (lanes 0..nj-1, float64)
-    double lo = 0.0, hi = 0.0, a1 = 0.0;
-    int code = 0;
-    if (jl) {
-        safe_range_joint(j, q, v, a, lo, hi, code);
-        a1 = map_action(u, lo, hi);
-    }
-    const int rcode = __reduce_or_sync(FULL, (unsigned)(jl ? code : 0));
-
-    // ---------------- sub-steps: setpoints and the motor-tracked pose (safe_motions_base.py:1233-1277)
+    const float rcode = scr[SM_MAX_SUB * SM_MAX_JOINTS + SM_MISC_RCODE];
+    const float jerk_rel = scr[SM_MAX_SUB * SM_MAX_JOINTS + SM_MISC_JERK];
+    const float umax = scr[SM_MAX_SUB * SM_MAX_JOINTS + SM_MISC_UMAX];
     const double dt = xdiv(c_sc.ts, (double)S);
-    const double tvdt = xmul(c_sc.track_vel, dt);
-    double q1 = q, v1 = v;
-    if (jl) {
-        for (int k = 1; k <= S; ++k) {
-            double qs, vs, as;
-            interpolate(q, v, a, a1, substep_time(k), qs, vs, as);
-            W.qsub[k - 1][j] = (float)qa;  // pose seen by the collision detection of sub-step k
-            qa = xadd(xadd(qa, xmul(c_sc.track_kp, xsub(qs, qa))), xmul(tvdt, vs));
-            q1 = qs; v1 = vs;              // k == S leaves the new knot (safe_motions_base.py:1179-1181)
-        }
-    }
-    float jerk_rel = jl ? (float)(fabs((a1 - a) / c_sc.ts) / c_sc.jerk_max[j]) : 0.0f;
-    jerk_rel = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(jerk_rel)));  // non-negative floats
     __syncwarp();
 
     // ---------------- sub-step contacts with the moving obstacles (ctlp.py:2590-2862)
-    double latch = shfl_d(ob, SM_OB_LATCH);
-    const int idx0 = (int)shfl_d(ob, SM_OB_INDEX);
+    double latch = W.ob[SM_OB_LATCH];
+    const int idx0 = (int)W.ob[SM_OB_INDEX];
     const int kind = c_sc.n_obstacles > 0 ? c_sc.obst_kind[0] : SM_OBST_NONE;
     const int stride = c_sc.contact_stride;
     int idx_new = idx0;
-    double ball_t = shfl_d(ob, SM_OB_BALL_T), ball_active = shfl_d(ob, SM_OB_BALL_ACTIVE);
+    double ball_t = W.ob[SM_OB_BALL_T], ball_active = W.ob[SM_OB_BALL_ACTIVE];
 
     if (kind == SM_OBST_PLANET) {
         if (stride > 0 && latch == 0.0 && c_sc.terminate_moving) {
-            bool f0 = false, f1 = false;
+            int f = 0;
             if (lane < S && ((lane + 1) % stride == 0)) {
                 Xf T;
                 planet_pose(0, (idx0 + lane) % c_sc.planet_steps, T);
@@ -128,31 +106,28 @@ __device__ void step_env(const StepArgs& A, int env, const float4* __restrict__ 
                     planet_pose(1, (idx0 + lane) % c_sc.planet_steps, T);
                     oc1 = xf_apply(T, c_sc.obst_center[1][0], c_sc.obst_center[1][1], c_sc.obst_center[1][2]);
                 }
-                substep_broad_phase(W, lane, oc0, oc1, true, c_sc.n_obstacles > 1, f0, f1);
+                f = substep_broad_phase(sm, W.qsub[lane], oc0, oc1, c_sc.n_obstacles > 1 ? 3 : 1);
             }
-            unsigned m0 = __ballot_sync(FULL, f0), m1 = __ballot_sync(FULL, f1);
+            unsigned m0 = __ballot_sync(FULL, f & 1), m1 = __ballot_sync(FULL, f & 2);
             unsigned m = m0 | m1;
             bool hit = false;
+#pragma unroll 1
             while (m && !hit) {
                 int k = __ffs(m) - 1;
                 m &= m - 1;
-                frames_from_q32(W.qsub[k], W.fr2, lane);
-                if (lane < c_sc.n_obstacles) planet_pose(lane, (idx0 + k) % c_sc.planet_steps, W.ob2[lane]);
+                frames_from_q32(sm, W.qsub[k], W.fr2, lane);
+                if (lane < c_sc.n_obstacles) planet_pose(lane, (idx0 + k) % c_sc.planet_steps, W.obx2[lane]);
                 __syncwarp();
-                if ((m0 >> k) & 1u) hit = contact_exists(verts, 0, W.fr2, W.ob2, lane, pc);
-                if (!hit && ((m1 >> k) & 1u)) hit = contact_exists(verts, 1, W.fr2, W.ob2, lane, pc);
+                if ((m0 >> k) & 1u) hit = contact_exists(verts, sm, 0, W.fr2, W.obx2, lane, pc);
+                if (!hit && ((m1 >> k) & 1u)) hit = contact_exists(verts, sm, 1, W.fr2, W.obx2, lane, pc);
                 __syncwarp();
             }
             if (hit) latch = 1.0;  // ctlp.py:2631-2637
         }
         idx_new = (idx0 + S) % c_sc.planet_steps;  // 24 x Planet.update (ctlp.py:4503-4505)
+        if (lane < c_sc.n_obstacles) planet_pose(lane, idx_new, W.obx[lane]);
     } else if (kind == SM_OBST_BALL) {
-        const double nmax = shfl_d(ob, SM_OB_BALL_NMAX), nhit = shfl_d(ob, SM_OB_BALL_NHIT);
-        double bp0[3] = {shfl_d(ob, SM_OB_BALL_P0), shfl_d(ob, SM_OB_BALL_P0 + 1), shfl_d(ob, SM_OB_BALL_P0 + 2)};
-        double bv0[3] = {shfl_d(ob, SM_OB_BALL_V0), shfl_d(ob, SM_OB_BALL_V0 + 1), shfl_d(ob, SM_OB_BALL_V0 + 2)};
-        double be0[3] = {shfl_d(ob, SM_OB_BALL_EULER0), shfl_d(ob, SM_OB_BALL_EULER0 + 1),
-                         shfl_d(ob, SM_OB_BALL_EULER0 + 2)};
-        double bom = shfl_d(ob, SM_OB_BALL_OMEGA);
+        const double nmax = W.ob[SM_OB_BALL_NMAX], nhit = W.ob[SM_OB_BALL_NHIT];
         if (ball_active != 0.0) {
             // first sub-step (1-based) at which the ball leaves by the counters (ctlp.py:2840-2848, :4196-4211)
             int k1 = (int)nmax - idx0 + 1, k2 = (int)nhit - idx0;
@@ -161,28 +136,30 @@ __device__ void step_env(const StepArgs& A, int env, const float4* __restrict__ 
             int last_k = k_end - 1 < S ? k_end - 1 : S;  // sub-steps that still test contacts
             int kc = 0;                                   // sub-step of the first contact, 0 = none
             if (stride > 0 && latch == 0.0) {
-                bool f0 = false, f1 = false;
+                int f = 0;
                 int sub = lane + 1;
                 if (sub <= last_k && (sub % stride == 0)) {
-                    // the test of sub-step `sub` happens after the ball moved to counter idx0+sub: active area uses
-                    // the new position (ctlp.py:2851-2854), the manifold the previous one
+                    // the test of sub-step `sub` happens after the ball moved to counter idx0+sub: the active area
+                    // uses the new position (ctlp.py:2851-2854), the manifold the previous one
                     double tn = ball_t + (double)sub * dt;
-                    double px = bp0[0] + bv0[0] * tn, py = bp0[1] + bv0[1] * tn;
+                    double px = W.ob[SM_OB_BALL_P0] + W.ob[SM_OB_BALL_V0] * tn;
+                    double py = W.ob[SM_OB_BALL_P0 + 1] + W.ob[SM_OB_BALL_V0 + 1] * tn;
                     if (sqrt(px * px + py * py) < c_sc.ball_active_xy) {
                         Xf T;
-                        ball_pose(bp0, bv0, be0, bom, ball_t + (double)lane * dt, T);
+                        ball_pose(W.ob, ball_t + (double)lane * dt, T);
                         V3 oc0 = xf_apply(T, c_sc.obst_center[0][0], c_sc.obst_center[0][1], c_sc.obst_center[0][2]);
-                        substep_broad_phase(W, lane, oc0, oc0, true, false, f0, f1);
+                        f = substep_broad_phase(sm, W.qsub[lane], oc0, oc0, 1);
                     }
                 }
-                unsigned m = __ballot_sync(FULL, f0);
+                unsigned m = __ballot_sync(FULL, f & 1);
+#pragma unroll 1
                 while (m && kc == 0) {
                     int k = __ffs(m) - 1;
                     m &= m - 1;
-                    frames_from_q32(W.qsub[k], W.fr2, lane);
-                    if (lane == 0) ball_pose(bp0, bv0, be0, bom, ball_t + (double)k * dt, W.ob2[0]);
+                    frames_from_q32(sm, W.qsub[k], W.fr2, lane);
+                    if (lane == 0) ball_pose(W.ob, ball_t + (double)k * dt, W.obx2[0]);
                     __syncwarp();
-                    if (contact_exists(verts, 0, W.fr2, W.ob2, lane, pc)) kc = k + 1;
+                    if (contact_exists(verts, sm, 0, W.fr2, W.obx2, lane, pc)) kc = k + 1;
                     __syncwarp();
                 }
             }
@@ -190,31 +167,18 @@ __device__ void step_env(const StepArgs& A, int env, const float4* __restrict__ 
             if (kc > 0) { adv = kc; ball_active = 0.0; latch = 1.0; }       // hit robot (ctlp.py:2858-2861)
             else if (k_end <= S) { adv = k_end; ball_active = 0.0; }        // missed robot / hit obstacle
             idx_new = idx0 + adv;
+#pragma unroll 1
             for (int i = 0; i < adv; ++i) ball_t = xadd(ball_t, dt);        // self._t += update_time_step
         }
-        // ---------------- final obstacle pose for the reward distance
-        if (lane == 0) ball_pose(bp0, bv0, be0, bom, ball_t, W.ob[0]);
+        if (lane == 0) ball_pose(W.ob, ball_t, W.obx[0]);  // final obstacle pose for the reward distance
     }
-    if (kind == SM_OBST_PLANET && lane < c_sc.n_obstacles) planet_pose(lane, idx_new, W.ob[lane]);
 
     // ---------------- distances at the new knot (rewards.py:95-162; ctlp.py:3217-3374)
-    frames_from_q64(q1, W.fr, lane);
+    frames_from_q64(sm, q1, W.fr, lane);
     __syncwarp();
-    const float cap = (float)c_sc.static_cap;
-    float d_static = min_pair_list(verts, c_sc.static_pairs, c_sc.n_static_pairs, cap, W.fr, W.ob, lane, pc, nullptr);
-    float d_self = min_pair_list(verts, c_sc.self_pairs, c_sc.n_self_pairs, cap, W.fr, W.ob, lane, pc, nullptr);
-    const float query = (float)c_sc.moving_query;
-    float d_moving = query + 0.002f;
-    if (latch != 0.0) {
-        d_moving = 0.0f;  // ctlp.py:3224-3234
-    } else if (c_sc.n_mov_reward > 0) {
-        for (int o = 0; o < c_sc.n_obstacles; ++o) {
-            if (kind == SM_OBST_BALL && ball_active == 0.0) continue;
-            d_moving = min_moving(verts, c_sc.mov_reward, c_sc.n_mov_reward, o, query, d_moving, W.fr, W.ob, lane, pc,
-                                  nullptr);
-            if (d_moving <= 0.0f) break;
-        }
-    }
+    float d_static, d_self, d_moving;
+    all_distances(verts, sm, W.fr, W.obx, latch != 0.0, kind == SM_OBST_BALL && ball_active == 0.0, d_static, d_self,
+                  d_moving, lane, pc);
 
     // ---------------- reward, termination (rewards.py:432-502; safe_motions_base.py:1775-1799): uniform float64
     double ds = (double)d_static, dse = (double)d_self, dm = (double)d_moving;
@@ -228,15 +192,15 @@ __device__ void step_env(const StepArgs& A, int env, const float4* __restrict__ 
     { double r = fmin(1.0, dm / c_sc.d_moving); r_moving = r * r; }
     double action_punishment = 1.0;
     if (c_sc.punish_action) {
-        float mu = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(jl ? fabsf(uf) : 0.0f)));
-        double pu = ((double)mu - c_sc.action_thresh) / (1.0 - c_sc.action_thresh);  // rewards.py:18-21
+        double pu = ((double)umax - c_sc.action_thresh) / (1.0 - c_sc.action_thresh);  // rewards.py:18-21
         pu = fmax(0.0, fmin(1.0, pu));
         action_punishment = pu * pu;
     }
     double low_acc = 0.0, low_vel = 0.0;
     if (c_sc.w_low_acc != 0.0 || c_sc.w_low_vel != 0.0) {  // rewards.py:448-460
-        float ra = jl ? (float)fabs(a1 / c_sc.acc_max[j]) : 0.0f;
-        float rv = jl ? (float)fabs(v1 / c_sc.vel_max[j]) : 0.0f;
+        const int j = lane & 7;
+        float ra = lane < nj ? (float)fabs(kin[16 + j] / c_sc.acc_max[j]) : 0.0f;
+        float rv = lane < nj ? (float)fabs(kin[8 + j] / c_sc.vel_max[j]) : 0.0f;
         ra = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(ra)));
         rv = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(rv)));
         double da = fmin(1.0, (double)ra / c_sc.thr_low_acc), dv = fmin(1.0, (double)rv / c_sc.thr_low_vel);
@@ -279,7 +243,7 @@ __device__ void step_env(const StepArgs& A, int env, const float4* __restrict__ 
             case SM_INFO_R_MOVING: val = (float)r_moving; break;
             case SM_INFO_EPISODE_LENGTH: val = (float)ep_len; break;
             case SM_INFO_EPISODE_RETURN: val = (float)ep_return; break;
-            case SM_INFO_RANGE_CODE: val = (float)rcode; break;
+            case SM_INFO_RANGE_CODE: val = rcode; break;
             case SM_INFO_CONTACT_LATCH: val = latch != 0.0 ? 1.0f : 0.0f; break;
             case SM_INFO_MAX_JERK_REL: val = jerk_rel; break;
             default: break;
@@ -296,7 +260,8 @@ __device__ void step_env(const StepArgs& A, int env, const float4* __restrict__ 
     // ---------------- new obstacle record; a ball that reached a final state is replaced when the observation is
     // taken (ctlp.py:2354-2360, :2893-2895).  The launch comes from the device-resident ball pool.
     int ball_draws = ep.z;
-    double ob_new = ob;
+    __syncwarp();
+    double ob_new = lane < SM_OBST_STRIDE ? W.ob[lane] : 0.0;
     if (lane == SM_OB_INDEX) ob_new = (double)idx_new;
     if (lane == SM_OB_LATCH) ob_new = latch;
     if (lane == SM_OB_BALL_T) ob_new = ball_t;
@@ -312,31 +277,32 @@ __device__ void step_env(const StepArgs& A, int env, const float4* __restrict__ 
         if (lane == SM_OB_BALL_NHIT) ob_new = e[11];
     }
 
-    // ---------------- new kinematic record (lane L: group L>>3 = q, v, a, q_act; joint L&7)
-    double qq = shfl_d(q1, j), vv = shfl_d(v1, j), aa = shfl_d(a1, j), tt = shfl_d(qa, j);
-    int grp = lane >> 3;
-    double kin_new = j < nj ? (grp == 0 ? qq : grp == 1 ? vv : grp == 2 ? aa : tt) : 0.0;
+    // ---------------- the kinematic record already holds the new knot; only an auto reset rewrites it
     int ep_len_new = ep_len, resets = ep.y;
     double ret_new = ep_return;
-
+    const double* kin_obs = kin;
     if (done && A.auto_reset && A.start_pool_n > 0) {  // vector-env auto reset from the device-resident start pool
         uint4 r = philox((uint32_t)env, (uint32_t)resets, 0x5E7u, 1u, A.k0, A.k1);
         const double* e = A.start_pool + (size_t)(r.x % (uint32_t)A.start_pool_n) * SM_POOL_STRIDE;
-        kin_new = e[lane];
+        A.buf.kin[(size_t)env * SM_KIN_STRIDE + lane] = e[lane];
         if (lane < SM_OBST_STRIDE) ob_new = e[SM_KIN_STRIDE + lane];
+        kin_obs = e;
         ep_len_new = 0;
         resets++;
         ret_new = 0.0;
     }
-    A.buf.kin[(size_t)env * SM_KIN_STRIDE + lane] = kin_new;
-    if (lane < SM_OBST_STRIDE) A.buf.obst[(size_t)env * SM_OBST_STRIDE + lane] = ob_new;
+    if (lane < SM_OBST_STRIDE) {
+        A.buf.obst[(size_t)env * SM_OBST_STRIDE + lane] = ob_new;
+        W.ob[lane] = ob_new;
+    }
     if (lane == 0) {
         *reinterpret_cast<int4*>(A.buf.episode + 4 * (size_t)env) = make_int4(ep_len_new, resets, ball_draws, ep.w);
         A.buf.ep_return[env] = ret_new;
     }
+    __syncwarp();
     // ---------------- observation of the state the next action acts on (observations.py:313-351)
-    write_observation(A.buf.obs + (size_t)env * c_sc.obs_size, shfl_d(kin_new, j), shfl_d(kin_new, 8 + j),
-                      shfl_d(kin_new, 16 + j), ob_new, lane);
+    write_observation(A.buf.obs + (size_t)env * c_sc.obs_size, kin_obs, W.ob, lane);
+    __syncwarp();
 
     if (COUNT && lane == 0) {
         atomicAdd(&bs.counters[0], (unsigned long long)cnt.calls);
@@ -349,18 +315,11 @@ __device__ void step_env(const StepArgs& A, int env, const float4* __restrict__ 
 template <bool COUNT>
 __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) step_kernel(StepArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* verts = reinterpret_cast<float4*>(smem_raw);
-    size_t off = ((size_t)c_sc.n_verts * sizeof(float4) + 15) & ~(size_t)15;
-    WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smem_raw + off);
-    BlockShared* bs = reinterpret_cast<BlockShared*>(smem_raw + off + SM_WARPS_PER_BLOCK * sizeof(WarpScratch));
+    SmemLayout L = block_prologue(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < c_sc.n_verts; i += blockDim.x) verts[i] = __ldg(c_sc.verts + i);  // hulls -> shared memory
-    if (tid < 16) bs->stats[tid] = 0.0;
-    if (tid < 6) bs->counters[tid] = 0ull;
-    __syncthreads();
     for (int env = blockIdx.x * SM_WARPS_PER_BLOCK + warp; env < A.n; env += gridDim.x * SM_WARPS_PER_BLOCK)
-        step_env<COUNT>(A, env, verts, scratch[warp], *bs, lane);
+        step_env<COUNT>(A, env, L.verts, L.scratch[warp], *L.bs, lane);
     __syncthreads();
-    if (A.buf.stats && tid < 16 && bs->stats[tid] != 0.0) atomicAdd(&A.buf.stats[tid], bs->stats[tid]);
-    if (COUNT && A.counters && tid < 6 && bs->counters[tid] != 0ull) atomicAdd(&A.counters[tid], bs->counters[tid]);
+    if (A.buf.stats && tid < 16 && L.bs->stats[tid] != 0.0) atomicAdd(&A.buf.stats[tid], L.bs->stats[tid]);
+    if (COUNT && A.counters && tid < 6 && L.bs->counters[tid] != 0ull) atomicAdd(&A.counters[tid], L.bs->counters[tid]);
 }
