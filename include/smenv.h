@@ -203,6 +203,11 @@ typedef struct SmBuffers {
 
 typedef struct SmCounters {
     unsigned long long gjk_calls, gjk_iters, support_dots, culled_pairs, env_steps, contact_tests;
+    unsigned long long flagged_substeps, reserved;
+    /* SM clock cycles summed over warps, per phase of the geometry kernel (counting build only):
+     * 0 load, 1 contact broad phase, 2 contact narrow phase, 3 end-pose FK, 4 static+self distance,
+     * 5 moving distance, 6 reward/outputs, 7 observation/auto-reset */
+    unsigned long long phase_cycles[8];
 } SmCounters;
 
 typedef struct SmEnv SmEnv;

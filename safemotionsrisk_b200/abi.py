@@ -116,7 +116,8 @@ class SmBuffers(C.Structure):
 
 class SmCounters(C.Structure):
     _fields_ = [("gjk_calls", C.c_ulonglong), ("gjk_iters", C.c_ulonglong), ("support_dots", C.c_ulonglong),
-                ("culled_pairs", C.c_ulonglong), ("env_steps", C.c_ulonglong), ("contact_tests", C.c_ulonglong)]
+                ("culled_pairs", C.c_ulonglong), ("env_steps", C.c_ulonglong), ("contact_tests", C.c_ulonglong),
+                ("flagged_substeps", C.c_ulonglong), ("reserved", C.c_ulonglong), ("phase_cycles", C.c_ulonglong * 8)]
 
 
 # every extern "C" symbol include/smenv.h declares

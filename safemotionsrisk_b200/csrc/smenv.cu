@@ -213,8 +213,8 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     if (env->ball_pool_n) CU(cudaMalloc((void**)&env->d_ball_pool, (size_t)env->ball_pool_n * SM_BALL_STRIDE * sizeof(double)));
     CU(cudaMalloc((void**)&env->d_scratch, (size_t)num_envs * SM_SCRATCH_FLOATS * sizeof(float)));
     CU(cudaMemset(env->d_scratch, 0, (size_t)num_envs * SM_SCRATCH_FLOATS * sizeof(float)));
-    CU(cudaMalloc((void**)&env->d_counters, 8 * sizeof(unsigned long long)));
-    CU(cudaMemset(env->d_counters, 0, 8 * sizeof(unsigned long long)));
+    CU(cudaMalloc((void**)&env->d_counters, 16 * sizeof(unsigned long long)));
+    CU(cudaMemset(env->d_counters, 0, 16 * sizeof(unsigned long long)));
 
     env->smem_bytes = smem_bytes_for(sc->n_verts, SM_WARPS_PER_BLOCK);
     CU(cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
@@ -455,10 +455,11 @@ extern "C" int smenv_enable_counters(SmEnv* env, int enable) {
 extern "C" int smenv_counters(SmEnv* env, SmCounters* out, int reset) {
     if (!env || !out) return fail(SM_ERR_ARG, "null argument");
     CU(cudaSetDevice(env->device));
-    unsigned long long h[8];
+    unsigned long long h[16];
     CU(cudaMemcpy(h, env->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
     out->gjk_calls = h[0]; out->gjk_iters = h[1]; out->support_dots = h[2]; out->culled_pairs = h[3];
-    out->env_steps = h[4]; out->contact_tests = h[5];
+    out->env_steps = h[4]; out->contact_tests = h[5]; out->flagged_substeps = h[6]; out->reserved = h[7];
+    for (int i = 0; i < 8; ++i) out->phase_cycles[i] = h[8 + i];
     if (reset) CU(cudaMemset(env->d_counters, 0, sizeof(h)));
     return SM_OK;
 }

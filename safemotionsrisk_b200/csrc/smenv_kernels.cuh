@@ -20,7 +20,7 @@ struct WarpScratch {
 struct BlockShared {
     SceneSmem scene;
     double stats[16];
-    unsigned long long counters[6];
+    unsigned long long counters[16];
 };
 
 // dynamic shared memory layout of the geometry kernels: hull vertices | BlockShared | WarpScratch[warps]
@@ -50,7 +50,7 @@ __device__ __forceinline__ SmemLayout block_prologue(unsigned char* raw) {
     for (int i = tid; i < c_sc.n_verts; i += blockDim.x) L.verts[i] = __ldg(c_sc.verts + i);
     stage_scene(L.bs->scene, tid, blockDim.x);
     if (tid < 16) L.bs->stats[tid] = 0.0;
-    if (tid < 6) L.bs->counters[tid] = 0ull;
+    if (tid < 16) L.bs->counters[tid] = 0ull;
     __syncthreads();
     return L;
 }
@@ -154,12 +154,19 @@ __device__ __noinline__ bool contact_exists(const float4* verts, const SceneSmem
 
 // static, self and moving-obstacle distances of the pose whose frames are in `robot` / `obst`
 // (get_minimum_distance ctlp.py:3282-3374, get_minimum_distance_to_moving_obstacles :3217-3256)
+template <bool COUNT>
 __device__ __forceinline__ void all_distances(const float4* verts, const SceneSmem& sm, const Xf* robot, const Xf* obst,
                                               bool latched, bool ball_inactive, float& d_static, float& d_self,
-                                              float& d_moving, int lane, GjkCounters* cnt) {
+                                              float& d_moving, int lane, GjkCounters* cnt,
+                                              unsigned long long* phase_counters, long long& tph) {
     const float cap = (float)c_sc.static_cap, query = (float)c_sc.moving_query;
     d_static = min_pairs(verts, sm, 0, sm.static_pairs, nullptr, c_sc.n_static_pairs, 1, 0, cap, cap, robot, obst, lane, cnt);
     d_self = min_pairs(verts, sm, 0, sm.self_pairs, nullptr, c_sc.n_self_pairs, 1, 0, cap, cap, robot, obst, lane, cnt);
+    if (COUNT) {
+        long long now_ = clock64();
+        if (lane == 0) atomicAdd(&phase_counters[8 + 4], (unsigned long long)(now_ - tph));
+        tph = now_;
+    }
     d_moving = query + 0.002f;  // ctlp.py:3259-3261
     if (latched) {
         d_moving = 0.0f;  // ctlp.py:3224-3234
@@ -170,6 +177,11 @@ __device__ __forceinline__ void all_distances(const float4* verts, const SceneSm
                                  c_sc.obst_shape_cnt[o], c_sc.obst_shape_off[o], query, d_moving, robot, obst, lane, cnt);
             if (d_moving <= 0.0f) break;
         }
+    }
+    if (COUNT) {
+        long long now_ = clock64();
+        if (lane == 0) atomicAdd(&phase_counters[8 + 5], (unsigned long long)(now_ - tph));
+        tph = now_;
     }
 }
 

@@ -385,8 +385,9 @@ distances_kernel(const double* kin, const double* obst, float* d_static, float* 
         if (kind == SM_OBST_BALL && lane == 0) ball_pose(W.ob, W.ob[SM_OB_BALL_T], W.obx[0]);
         __syncwarp();
         float ds, dse, dm;
-        all_distances(L.verts, sm, W.fr, W.obx, W.ob[SM_OB_LATCH] != 0.0,
-                      kind == SM_OBST_BALL && W.ob[SM_OB_BALL_ACTIVE] == 0.0, ds, dse, dm, lane, nullptr);
+        long long tph = 0;
+        all_distances<false>(L.verts, sm, W.fr, W.obx, W.ob[SM_OB_LATCH] != 0.0,
+                             kind == SM_OBST_BALL && W.ob[SM_OB_BALL_ACTIVE] == 0.0, ds, dse, dm, lane, nullptr, nullptr, tph);
         __syncwarp();
         if (lane == 0) { d_static[env] = ds; d_self[env] = dse; d_moving[env] = dm; }
     }

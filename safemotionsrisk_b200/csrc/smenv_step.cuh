@@ -71,6 +71,14 @@ __device__ void step_env(const StepArgs& A, int env, const float4* __restrict__ 
     const int nj = c_sc.n_joints, S = c_sc.substeps;
     GjkCounters cnt = {0u, 0u, 0u, nullptr};
     GjkCounters* pc = COUNT ? &cnt : nullptr;
+    long long tph = COUNT ? clock64() : 0;
+    unsigned n_flagged = 0, n_contact_tests = 0;
+#define SM_PHASE(i)                                                                          \
+    if (COUNT) {                                                                             \
+        long long now_ = clock64();                                                          \
+        if (lane == 0) atomicAdd(&bs.counters[8 + (i)], (unsigned long long)(now_ - tph));   \
+        tph = now_;                                                                          \
+    }
 
     // ---------------- load the env records; the kinematic record already holds the new knot (joint_kernel)
     const double* kin = A.buf.kin + (size_t)env * SM_KIN_STRIDE;
@@ -85,6 +93,7 @@ __device__ void step_env(const StepArgs& A, int env, const float4* __restrict__ 
     const float umax = scr[SM_MAX_SUB * SM_MAX_JOINTS + SM_MISC_UMAX];
     const double dt = xdiv(c_sc.ts, (double)S);
     __syncwarp();
+    SM_PHASE(0)
 
     // ---------------- sub-step contacts with the moving obstacles (ctlp.py:2590-2862)
     double latch = W.ob[SM_OB_LATCH];
@@ -111,6 +120,8 @@ __device__ void step_env(const StepArgs& A, int env, const float4* __restrict__ 
             unsigned m0 = __ballot_sync(FULL, f & 1), m1 = __ballot_sync(FULL, f & 2);
             unsigned m = m0 | m1;
             bool hit = false;
+            n_flagged += __popc(m);
+            SM_PHASE(1)
 #pragma unroll 1
             while (m && !hit) {
                 int k = __ffs(m) - 1;
@@ -152,6 +163,8 @@ __device__ void step_env(const StepArgs& A, int env, const float4* __restrict__ 
                     }
                 }
                 unsigned m = __ballot_sync(FULL, f & 1);
+                n_flagged += __popc(m);
+                SM_PHASE(1)
 #pragma unroll 1
                 while (m && kc == 0) {
                     int k = __ffs(m) - 1;
@@ -173,12 +186,14 @@ __device__ void step_env(const StepArgs& A, int env, const float4* __restrict__ 
         if (lane == 0) ball_pose(W.ob, ball_t, W.obx[0]);  // final obstacle pose for the reward distance
     }
 
+    SM_PHASE(2)
     // ---------------- distances at the new knot (rewards.py:95-162; ctlp.py:3217-3374)
     frames_from_q64(sm, q1, W.fr, lane);
     __syncwarp();
+    SM_PHASE(3)
     float d_static, d_self, d_moving;
-    all_distances(verts, sm, W.fr, W.obx, latch != 0.0, kind == SM_OBST_BALL && ball_active == 0.0, d_static, d_self,
-                  d_moving, lane, pc);
+    all_distances<COUNT>(verts, sm, W.fr, W.obx, latch != 0.0, kind == SM_OBST_BALL && ball_active == 0.0, d_static,
+                         d_self, d_moving, lane, pc, bs.counters, tph);
 
     // ---------------- reward, termination (rewards.py:432-502; safe_motions_base.py:1775-1799): uniform float64
     double ds = (double)d_static, dse = (double)d_self, dm = (double)d_moving;
@@ -257,6 +272,7 @@ __device__ void step_env(const StepArgs& A, int env, const float4* __restrict__ 
         atomicAdd(&bs.stats[3 + reason], 1.0);
     }
 
+    SM_PHASE(6)
     // ---------------- new obstacle record; a ball that reached a final state is replaced when the observation is
     // taken (ctlp.py:2354-2360, :2893-2895).  The launch comes from the device-resident ball pool.
     int ball_draws = ep.z;
@@ -304,7 +320,10 @@ __device__ void step_env(const StepArgs& A, int env, const float4* __restrict__ 
     write_observation(A.buf.obs + (size_t)env * c_sc.obs_size, kin_obs, W.ob, lane);
     __syncwarp();
 
+    SM_PHASE(7)
+    (void)n_contact_tests;
     if (COUNT && lane == 0) {
+        atomicAdd(&bs.counters[6], (unsigned long long)n_flagged);
         atomicAdd(&bs.counters[0], (unsigned long long)cnt.calls);
         atomicAdd(&bs.counters[1], (unsigned long long)cnt.iters);
         atomicAdd(&bs.counters[2], (unsigned long long)cnt.dots);
@@ -321,5 +340,5 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) step_kernel(StepArgs 
         step_env<COUNT>(A, env, L.verts, L.scratch[warp], *L.bs, lane);
     __syncthreads();
     if (A.buf.stats && tid < 16 && L.bs->stats[tid] != 0.0) atomicAdd(&A.buf.stats[tid], L.bs->stats[tid]);
-    if (COUNT && A.counters && tid < 6 && L.bs->counters[tid] != 0ull) atomicAdd(&A.counters[tid], L.bs->counters[tid]);
+    if (COUNT && A.counters && tid < 16 && L.bs->counters[tid] != 0ull) atomicAdd(&A.counters[tid], L.bs->counters[tid]);
 }

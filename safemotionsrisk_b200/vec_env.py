@@ -317,7 +317,9 @@ class SafeMotionsVecEnv:
         c = abi.SmCounters()
         torch.cuda.synchronize(self.device)
         cabi.check(self._lib.smenv_counters(self._handle, C.byref(c), int(reset)), "smenv_counters")
-        return {k: int(getattr(c, k)) for k, _ in abi.SmCounters._fields_}
+        out = {k: int(getattr(c, k)) for k, _ in abi.SmCounters._fields_ if k != "phase_cycles"}
+        out["phase_cycles"] = [int(x) for x in c.phase_cycles]
+        return out
 
     def launch_count(self):
         n = C.c_ulonglong()
