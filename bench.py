@@ -249,7 +249,7 @@ def main():
                 "frac": achieved_tflops / peak_tflops, "traffic": None,
                 "peak_source": "148 SMs x 128 FP32 lanes x 2 x median SM clock under load ({} MHz)".format(sm_mhz),
                 "flops_per_env_step": f_step, "support_dots_per_env_step": n_dot, "gjk_iters_per_env_step": n_iter,
-                "gjk_calls_per_env_step": c["gjk_calls"] / steps_counted, "kernel": "step_kernel<false>",
+                "gjk_calls_per_env_step": c["gjk_calls"] / steps_counted, "kernel": "distance_kernel<false>",
                 "kernel_ms": kernel_ms,
                 "hbm": {"achieved": per_gpu_steps_s * bytes_step / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": per_gpu_steps_s * bytes_step / 1e9 / hbm_peak, "bytes_per_env_step": bytes_step,

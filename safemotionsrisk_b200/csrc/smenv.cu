@@ -32,10 +32,12 @@ struct SmEnv {
     int start_pool_n = 0, ball_pool_n = 0;
     bool pools_filled = false;
     unsigned long long* d_counters = nullptr;
-    float* d_scratch = nullptr;  // per-env hand-over from joint_kernel to step_kernel
+    float* d_scratch = nullptr;  // per-env hand-over between the phase kernels of a step
+    int* d_worklist = nullptr;   // [0] = count, [1..n] = envs flagged by the contact broad phase
     bool count = false;
-    size_t smem_bytes = 0;
-    int grid = 0;
+    size_t smem_bytes = 0;        // kernels that stage the hull vertices
+    size_t smem_bytes_broad = 0;  // contact_broad_kernel: scene tables only
+    int grid = 0, grid_broad = 0;
     uint32_t step_counter = 0;
     unsigned long long launches = 0;
 };
@@ -213,21 +215,29 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     if (env->ball_pool_n) CU(cudaMalloc((void**)&env->d_ball_pool, (size_t)env->ball_pool_n * SM_BALL_STRIDE * sizeof(double)));
     CU(cudaMalloc((void**)&env->d_scratch, (size_t)num_envs * SM_SCRATCH_FLOATS * sizeof(float)));
     CU(cudaMemset(env->d_scratch, 0, (size_t)num_envs * SM_SCRATCH_FLOATS * sizeof(float)));
+    CU(cudaMalloc((void**)&env->d_worklist, ((size_t)num_envs + 1) * sizeof(int)));
+    CU(cudaMemset(env->d_worklist, 0, ((size_t)num_envs + 1) * sizeof(int)));
     CU(cudaMalloc((void**)&env->d_counters, 16 * sizeof(unsigned long long)));
     CU(cudaMemset(env->d_counters, 0, 16 * sizeof(unsigned long long)));
 
     env->smem_bytes = smem_bytes_for(sc->n_verts, SM_WARPS_PER_BLOCK);
-    CU(cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
-    CU(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
+    env->smem_bytes_broad = smem_bytes_for(0, SM_WARPS_PER_BLOCK);
+    CU(cudaFuncSetAttribute(contact_narrow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
+    CU(cudaFuncSetAttribute(contact_narrow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
+    CU(cudaFuncSetAttribute(distance_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
+    CU(cudaFuncSetAttribute(distance_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
     CU(cudaFuncSetAttribute(fill_ball_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
     CU(cudaFuncSetAttribute(fill_start_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
     CU(cudaFuncSetAttribute(distances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
     // persistent grid: as many CTAs as fit on the device at once (a multiple of the SM count), each looping over envs
     int sms = 0, per_sm = 0;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<false>, SM_WARPS_PER_BLOCK * 32, env->smem_bytes));
-    if (per_sm < 1) { delete env; return fail(SM_ERR_CUDA, "step kernel does not fit on an SM"); }
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, distance_kernel<false>, SM_WARPS_PER_BLOCK * 32, env->smem_bytes));
+    if (per_sm < 1) { delete env; return fail(SM_ERR_CUDA, "distance kernel does not fit on an SM"); }
     env->grid = sms * per_sm;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, contact_broad_kernel<false>, SM_WARPS_PER_BLOCK * 32, env->smem_bytes_broad));
+    if (per_sm < 1) { delete env; return fail(SM_ERR_CUDA, "contact broad kernel does not fit on an SM"); }
+    env->grid_broad = sms * per_sm;
     *out = env;
     return SM_OK;
 }
@@ -237,7 +247,7 @@ extern "C" int smenv_destroy(SmEnv* env) {
     cudaSetDevice(env->device);
     if (g_active == env) g_active = nullptr;
     cudaFree(env->d_verts); cudaFree(env->d_plocal); cudaFree(env->d_start_pool); cudaFree(env->d_ball_pool);
-    cudaFree(env->d_counters); cudaFree(env->d_scratch);
+    cudaFree(env->d_counters); cudaFree(env->d_scratch); cudaFree(env->d_worklist);
     for (int o = 0; o < SM_MAX_OBSTACLES; ++o) { cudaFree(env->d_ppos[o]); cudaFree(env->d_pquat[o]); }
     delete env;
     return SM_OK;
@@ -399,21 +409,41 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
     JA.k0 = (uint32_t)env->seed; JA.k1 = (uint32_t)(env->seed >> 32);
     JA.step_counter = env->step_counter++;
     JA.scratch = env->d_scratch;
+    JA.worklist = env->d_worklist;
     joint_kernel<<<(env->n * 8 + 255) / 256, 256, 0, stream>>>(JA);
     env->launches++;
     StepArgs A;
     A.buf = *buf; A.n = env->n; A.auto_reset = auto_reset;
     A.k0 = (uint32_t)env->seed; A.k1 = (uint32_t)(env->seed >> 32);
     A.scratch = env->d_scratch;
+    A.worklist = env->d_worklist;
     A.start_pool = env->pools_filled ? env->d_start_pool : nullptr;
     A.start_pool_n = env->pools_filled ? env->start_pool_n : 0;
     A.ball_pool = env->pools_filled ? env->d_ball_pool : nullptr;
     A.ball_pool_n = env->pools_filled ? env->ball_pool_n : 0;
     A.counters = env->d_counters;
-    int grid = grid_for(env, env->n);
-    if (env->count) step_kernel<true><<<grid, SM_WARPS_PER_BLOCK * 32, env->smem_bytes, stream>>>(A);
-    else step_kernel<false><<<grid, SM_WARPS_PER_BLOCK * 32, env->smem_bytes, stream>>>(A);
-    env->launches++;
+    const int T = SM_WARPS_PER_BLOCK * 32;
+    const int blocks = (env->n + SM_WARPS_PER_BLOCK - 1) / SM_WARPS_PER_BLOCK;
+    const int grid = blocks < env->grid ? blocks : env->grid;
+    const int grid_b = blocks < env->grid_broad ? blocks : env->grid_broad;
+    const int grid_f = (env->n + 7) / 8;
+    const bool contacts = env->host_scene.contact_stride > 0 && env->host_scene.n_obstacles > 0;
+    if (env->count) {
+        if (contacts) {
+            contact_broad_kernel<true><<<grid_b, T, env->smem_bytes_broad, stream>>>(A);
+            contact_narrow_kernel<true><<<grid, T, env->smem_bytes, stream>>>(A);
+        }
+        distance_kernel<true><<<grid, T, env->smem_bytes, stream>>>(A);
+        finish_kernel<true><<<grid_f, 256, 0, stream>>>(A);
+    } else {
+        if (contacts) {
+            contact_broad_kernel<false><<<grid_b, T, env->smem_bytes_broad, stream>>>(A);
+            contact_narrow_kernel<false><<<grid, T, env->smem_bytes, stream>>>(A);
+        }
+        distance_kernel<false><<<grid, T, env->smem_bytes, stream>>>(A);
+        finish_kernel<false><<<grid_f, 256, 0, stream>>>(A);
+    }
+    env->launches += contacts ? 4 : 2;
     CU(cudaGetLastError());
     return SM_OK;
 }

@@ -10,10 +10,17 @@
 #pragma once
 #include "smenv_kernels.cuh"
 
-#define SM_SCRATCH_FLOATS (SM_MAX_SUB * SM_MAX_JOINTS + 8) /* qsub[32][8] + misc[8] */
-#define SM_MISC_RCODE 0
-#define SM_MISC_JERK 1
-#define SM_MISC_UMAX 2
+#define SM_SCRATCH_FLOATS (SM_MAX_SUB * SM_MAX_JOINTS + 16) /* qsub[32][8] + misc[16] */
+#define SM_MISC_OFF (SM_MAX_SUB * SM_MAX_JOINTS)
+#define SM_MISC_RCODE 0     /* joint_kernel: OR of the violation codes */
+#define SM_MISC_JERK 1      /* joint_kernel: max relative jerk */
+#define SM_MISC_UMAX 2      /* joint_kernel: max |action| */
+#define SM_MISC_MASK0 4     /* contact_broad_kernel: bit k = sub-step k+1 needs a narrow-phase test, obstacle 0 */
+#define SM_MISC_MASK1 5     /* idem obstacle 1 */
+#define SM_MISC_HIT 6       /* contact_narrow_kernel: 1-based sub-step of the first contact, 0 = none */
+#define SM_MISC_DSTATIC 8   /* distance_kernel */
+#define SM_MISC_DSELF 9
+#define SM_MISC_DMOVING 10
 
 struct JointArgs {
     SmBuffers buf;
@@ -21,6 +28,7 @@ struct JointArgs {
     int random_actions;
     uint32_t k0, k1, step_counter;
     float* scratch;  // [n][SM_SCRATCH_FLOATS]
+    int* worklist;   // [0] = number of envs flagged for the narrow phase (reset here), [1..] = their indices
 };
 
 __global__ void __launch_bounds__(256) joint_kernel(JointArgs A) {
@@ -75,8 +83,9 @@ __global__ void __launch_bounds__(256) joint_kernel(JointArgs A) {
         jerk_rel = fmaxf(jerk_rel, __shfl_xor_sync(FULL, jerk_rel, m));
         um = fmaxf(um, __shfl_xor_sync(FULL, um, m));
     }
-    if (valid && j < 4) {
+    if (valid) {  // misc[0..7]: codes / jerk / max action; contact masks and hit cleared for the geometry kernels
         float val = j == SM_MISC_RCODE ? (float)rc : j == SM_MISC_JERK ? jerk_rel : j == SM_MISC_UMAX ? um : 0.0f;
-        scr[SM_MAX_SUB * SM_MAX_JOINTS + j] = val;
+        scr[SM_MISC_OFF + j] = val;
     }
+    if (t == 0 && A.worklist) A.worklist[0] = 0;
 }

@@ -9,7 +9,6 @@
 
 // per-warp scratch in shared memory
 struct WarpScratch {
-    float qsub[SM_MAX_SUB][SM_MAX_JOINTS];  // tracked joint pose seen by the contact test of each sub-step
     double ob[SM_OBST_STRIDE];              // the env's obstacle record (broadcast reads instead of shuffles)
     Xf fr[1 + SM_MAX_JOINTS];               // robot frames at the end-of-step setpoint pose
     Xf fr2[1 + SM_MAX_JOINTS];              // robot frames of one sub-step (narrow phase)
@@ -29,10 +28,10 @@ struct SmemLayout {
     BlockShared* bs;
     WarpScratch* scratch;
 };
-__device__ __forceinline__ SmemLayout carve_smem(unsigned char* raw) {
+__device__ __forceinline__ SmemLayout carve_smem(unsigned char* raw, bool with_verts) {
     SmemLayout L;
     L.verts = reinterpret_cast<float4*>(raw);
-    size_t off = ((size_t)c_sc.n_verts * sizeof(float4) + 15) & ~(size_t)15;
+    size_t off = with_verts ? ((size_t)c_sc.n_verts * sizeof(float4) + 15) & ~(size_t)15 : 0;
     L.bs = reinterpret_cast<BlockShared*>(raw + off);
     off += (sizeof(BlockShared) + 15) & ~(size_t)15;
     L.scratch = reinterpret_cast<WarpScratch*>(raw + off);
@@ -43,11 +42,12 @@ static size_t smem_bytes_for(int n_verts, int warps) {
     off += (sizeof(BlockShared) + 15) & ~(size_t)15;
     return off + (size_t)warps * sizeof(WarpScratch);
 }
-// block prologue: hulls and scene tables -> shared memory
-__device__ __forceinline__ SmemLayout block_prologue(unsigned char* raw) {
-    SmemLayout L = carve_smem(raw);
+// block prologue: hulls (only for kernels that run GJK) and scene tables -> shared memory
+__device__ __forceinline__ SmemLayout block_prologue(unsigned char* raw, bool with_verts) {
+    SmemLayout L = carve_smem(raw, with_verts);
     const int tid = threadIdx.x;
-    for (int i = tid; i < c_sc.n_verts; i += blockDim.x) L.verts[i] = __ldg(c_sc.verts + i);
+    if (with_verts)
+        for (int i = tid; i < c_sc.n_verts; i += blockDim.x) L.verts[i] = __ldg(c_sc.verts + i);
     stage_scene(L.bs->scene, tid, blockDim.x);
     if (tid < 16) L.bs->stats[tid] = 0.0;
     if (tid < 16) L.bs->counters[tid] = 0ull;
@@ -154,19 +154,12 @@ __device__ __noinline__ bool contact_exists(const float4* verts, const SceneSmem
 
 // static, self and moving-obstacle distances of the pose whose frames are in `robot` / `obst`
 // (get_minimum_distance ctlp.py:3282-3374, get_minimum_distance_to_moving_obstacles :3217-3256)
-template <bool COUNT>
 __device__ __forceinline__ void all_distances(const float4* verts, const SceneSmem& sm, const Xf* robot, const Xf* obst,
                                               bool latched, bool ball_inactive, float& d_static, float& d_self,
-                                              float& d_moving, int lane, GjkCounters* cnt,
-                                              unsigned long long* phase_counters, long long& tph) {
+                                              float& d_moving, int lane, GjkCounters* cnt) {
     const float cap = (float)c_sc.static_cap, query = (float)c_sc.moving_query;
     d_static = min_pairs(verts, sm, 0, sm.static_pairs, nullptr, c_sc.n_static_pairs, 1, 0, cap, cap, robot, obst, lane, cnt);
     d_self = min_pairs(verts, sm, 0, sm.self_pairs, nullptr, c_sc.n_self_pairs, 1, 0, cap, cap, robot, obst, lane, cnt);
-    if (COUNT) {
-        long long now_ = clock64();
-        if (lane == 0) atomicAdd(&phase_counters[8 + 4], (unsigned long long)(now_ - tph));
-        tph = now_;
-    }
     d_moving = query + 0.002f;  // ctlp.py:3259-3261
     if (latched) {
         d_moving = 0.0f;  // ctlp.py:3224-3234
@@ -177,11 +170,6 @@ __device__ __forceinline__ void all_distances(const float4* verts, const SceneSm
                                  c_sc.obst_shape_cnt[o], c_sc.obst_shape_off[o], query, d_moving, robot, obst, lane, cnt);
             if (d_moving <= 0.0f) break;
         }
-    }
-    if (COUNT) {
-        long long now_ = clock64();
-        if (lane == 0) atomicAdd(&phase_counters[8 + 5], (unsigned long long)(now_ - tph));
-        tph = now_;
     }
 }
 

@@ -80,7 +80,7 @@ __device__ __noinline__ double target_height_time(double h0, double vz, double h
 
 __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) fill_ball_pool_kernel(PoolArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SmemLayout L = block_prologue(smem_raw);
+    SmemLayout L = block_prologue(smem_raw, true);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     WarpScratch& W = L.scratch[warp];
     const SceneSmem& sm = L.bs->scene;
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) fill_ball_pool_kernel
 
 __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) fill_start_pool_kernel(PoolArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SmemLayout L = block_prologue(smem_raw);
+    SmemLayout L = block_prologue(smem_raw, true);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     WarpScratch& W = L.scratch[warp];
     const SceneSmem& sm = L.bs->scene;
@@ -371,7 +371,7 @@ __global__ void safe_range_kernel(const double* kin, double* lo, double* hi, int
 __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32)
 distances_kernel(const double* kin, const double* obst, float* d_static, float* d_self, float* d_moving, int n) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SmemLayout L = block_prologue(smem_raw);
+    SmemLayout L = block_prologue(smem_raw, true);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     WarpScratch& W = L.scratch[warp];
     const SceneSmem& sm = L.bs->scene;
@@ -385,9 +385,8 @@ distances_kernel(const double* kin, const double* obst, float* d_static, float* 
         if (kind == SM_OBST_BALL && lane == 0) ball_pose(W.ob, W.ob[SM_OB_BALL_T], W.obx[0]);
         __syncwarp();
         float ds, dse, dm;
-        long long tph = 0;
-        all_distances<false>(L.verts, sm, W.fr, W.obx, W.ob[SM_OB_LATCH] != 0.0,
-                             kind == SM_OBST_BALL && W.ob[SM_OB_BALL_ACTIVE] == 0.0, ds, dse, dm, lane, nullptr, nullptr, tph);
+        all_distances(L.verts, sm, W.fr, W.obx, W.ob[SM_OB_LATCH] != 0.0,
+                      kind == SM_OBST_BALL && W.ob[SM_OB_BALL_ACTIVE] == 0.0, ds, dse, dm, lane, nullptr);
         __syncwarp();
         if (lane == 0) { d_static[env] = ds; d_self[env] = dse; d_moving[env] = dm; }
     }
@@ -397,7 +396,7 @@ distances_kernel(const double* kin, const double* obst, float* d_static, float* 
 __global__ void __launch_bounds__(32) debug_gjk_kernel(const double* kin, const double* obst, int ia, int ib, float upper,
                                                        float* trace, float* result) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SmemLayout L = block_prologue(smem_raw);
+    SmemLayout L = block_prologue(smem_raw, true);
     const int lane = threadIdx.x & 31;
     WarpScratch& W = L.scratch[0];
     const SceneSmem& sm = L.bs->scene;

@@ -5,14 +5,14 @@ The reference cannot run in this image (pybullet / klimits / gym absent, SURVEY.
 so these fixtures pin the ORACLE (regression vectors), not the reference: inputs (start states, actions, ball
 launches) and the oracle's outputs per step.  `tests/test_needs_pybullet.py` documents how to re-record them from the
 real env on a box that has pybullet + klimits.
-Usage: python tools/make_golden.py
+Usage: python tests/golden/make_golden.py
 """
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import oracle  # noqa: E402
 from safemotionsrisk_b200 import ball_backup_config, space_backup_config  # noqa: E402

@@ -1,4 +1,6 @@
 """First GPU sanity script: parity of the CUDA step vs the oracle on a few envs + quick timing."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import sys, time
 import numpy as np, torch
 from safemotionsrisk_b200 import space_backup_config, ball_backup_config

@@ -1,4 +1,6 @@
 import numpy as np, torch, sys, ctypes as C
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from safemotionsrisk_b200 import space_backup_config, cabi
 from safemotionsrisk_b200.vec_env import SafeMotionsVecEnv
 from oracle import oracle

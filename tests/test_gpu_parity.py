@@ -47,7 +47,8 @@ def test_extension_is_loaded_and_counts_launches():
     env.set_state(q, q, q, np.zeros((32, 16)))
     env.step(np.zeros((32, 7), dtype=np.float32))
     torch.cuda.synchronize()
-    assert env.launch_count() - n0 == 4          # set_state + observation + joint + step kernels
+    # set_state + observation, then the step: joint + contact broad + contact narrow + distance + finish kernels
+    assert env.launch_count() - n0 == 7
     env.close()
 
 
