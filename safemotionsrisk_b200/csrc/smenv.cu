@@ -34,10 +34,11 @@ struct SmEnv {
     unsigned long long* d_counters = nullptr;
     float* d_scratch = nullptr;  // per-env hand-over between the phase kernels of a step
     int* d_worklist = nullptr;   // [0] = count, [1..n] = envs flagged by the contact broad phase
+    int* d_heavy = nullptr;      // [0] = count, [1..8n] = (env, joint) instances deferred to joint_heavy_kernel
     bool count = false;
     size_t smem_bytes = 0;        // kernels that stage the hull vertices
     size_t smem_bytes_broad = 0;  // contact_broad_kernel: scene tables only
-    int grid = 0, grid_broad = 0;
+    int grid = 0, grid_broad = 0, sms = 0;
     uint32_t step_counter = 0;
     unsigned long long launches = 0;
 };
@@ -217,6 +218,8 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     CU(cudaMemset(env->d_scratch, 0, (size_t)num_envs * SM_SCRATCH_FLOATS * sizeof(float)));
     CU(cudaMalloc((void**)&env->d_worklist, ((size_t)num_envs + 1) * sizeof(int)));
     CU(cudaMemset(env->d_worklist, 0, ((size_t)num_envs + 1) * sizeof(int)));
+    CU(cudaMalloc((void**)&env->d_heavy, ((size_t)num_envs * 8 + 1) * sizeof(int)));
+    CU(cudaMemset(env->d_heavy, 0, ((size_t)num_envs * 8 + 1) * sizeof(int)));
     CU(cudaMalloc((void**)&env->d_counters, 16 * sizeof(unsigned long long)));
     CU(cudaMemset(env->d_counters, 0, 16 * sizeof(unsigned long long)));
 
@@ -235,6 +238,7 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, distance_kernel<false>, SM_WARPS_PER_BLOCK * 32, env->smem_bytes));
     if (per_sm < 1) { delete env; return fail(SM_ERR_CUDA, "distance kernel does not fit on an SM"); }
     env->grid = sms * per_sm;
+    env->sms = sms;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, contact_broad_kernel<false>, SM_WARPS_PER_BLOCK * 32, env->smem_bytes_broad));
     if (per_sm < 1) { delete env; return fail(SM_ERR_CUDA, "contact broad kernel does not fit on an SM"); }
     env->grid_broad = sms * per_sm;
@@ -247,7 +251,7 @@ extern "C" int smenv_destroy(SmEnv* env) {
     cudaSetDevice(env->device);
     if (g_active == env) g_active = nullptr;
     cudaFree(env->d_verts); cudaFree(env->d_plocal); cudaFree(env->d_start_pool); cudaFree(env->d_ball_pool);
-    cudaFree(env->d_counters); cudaFree(env->d_scratch); cudaFree(env->d_worklist);
+    cudaFree(env->d_counters); cudaFree(env->d_scratch); cudaFree(env->d_worklist); cudaFree(env->d_heavy);
     for (int o = 0; o < SM_MAX_OBSTACLES; ++o) { cudaFree(env->d_ppos[o]); cudaFree(env->d_pquat[o]); }
     delete env;
     return SM_OK;
@@ -410,13 +414,20 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
     JA.step_counter = env->step_counter++;
     JA.scratch = env->d_scratch;
     JA.worklist = env->d_worklist;
+    JA.heavy = env->d_heavy;
     joint_kernel<<<(env->n * 8 + 255) / 256, 256, 0, stream>>>(JA);
-    env->launches++;
+    {   // the heavy list is at most 8 n long; blocks beyond its length exit at once
+        int hb = (env->n * 8 + 127) / 128;
+        if (hb > 8 * env->sms) hb = 8 * env->sms;
+        joint_heavy_kernel<<<hb, 128, 0, stream>>>(JA);
+    }
+    env->launches += 2;
     StepArgs A;
     A.buf = *buf; A.n = env->n; A.auto_reset = auto_reset;
     A.k0 = (uint32_t)env->seed; A.k1 = (uint32_t)(env->seed >> 32);
     A.scratch = env->d_scratch;
     A.worklist = env->d_worklist;
+    A.heavy = env->d_heavy;
     A.start_pool = env->pools_filled ? env->d_start_pool : nullptr;
     A.start_pool_n = env->pools_filled ? env->start_pool_n : 0;
     A.ball_pool = env->pools_filled ? env->d_ball_pool : nullptr;

@@ -191,6 +191,52 @@ __device__ __forceinline__ void clamp_range(double& lo, double& hi, double blo, 
     lo = nlo; hi = nhi;
 }
 
+// Conservative test "the position bound of pos_upper is inactive": true only if pos_peak(p, v, a, a1 = hi) is
+// certainly below pmax, in which case pos_upper returns SM_BIG after its first evaluation and the whole iterative
+// solve can be skipped without changing a bit of the result.  Bound on the braking trajectory pos_peak simulates:
+//   interval 1:  p(t) <= p + v+ ts + m0 ts^2 / 2,  v1 <= v + m0 ts            (m0 = max(a, a1, 0))
+//   ramp to -A:  n = ceil((a1+ + A) / (J ts)) + 1 intervals with acceleration <= a1+
+//   velocity along the profile <= vp = min(v1 + a1+ n ts, 1.001 V + 1e-6)     (the velocity clamp already applied
+//                                                                              to hi guarantees the second term)
+//   then constant -A: stopping distance <= vp^2 / (2A)
+// Everything is rounded up by a 1e-6 rad slack; plain double arithmetic (this is a filter, not part of the result).
+__device__ __forceinline__ bool pos_bound_inactive(double p, double v, double a, double a1, double pmax, double J,
+                                                   double A, double V, double ts, bool vel_guaranteed) {
+    const double m0 = fmax(fmax(a, a1), 0.0), a1p = fmax(a1, 0.0), vp0 = fmax(v, 0.0);
+    const double n = ceil((a1p + A) / (J * ts)) + 1.0;
+    double w = fmax(v + m0 * ts, 0.0) + a1p * n * ts;
+    if (vel_guaranteed) w = fmin(w, 1.001 * V + 1e-6);
+    w = fmax(w, vp0);
+    const double bound = p + vp0 * ts + 0.5 * m0 * ts * ts + w * n * ts + w * w / (2.0 * A);
+    return bound + 1e-6 < pmax;
+}
+
+// Cheap part of the range: jerk, acceleration and velocity bounds.  Returns through need_pos whether one of the two
+// position bounds may be active (then safe_range_joint has to run the iterative solve).
+__device__ __forceinline__ void safe_range_light(int j, double p, double v, double a, double& lo, double& hi, int& code,
+                                                 bool& need_pos) {
+    double ts = c_sc.ts, J = c_sc.jerk_max[j], A = c_sc.acc_max[j], V = c_sc.vel_max[j];
+    code = 0;
+    lo = xsub(a, xmul(J, ts)); hi = xadd(a, xmul(J, ts));
+    if (lo < -A) lo = -A;
+    if (hi > A) hi = A;
+    if (lo > hi) {
+        code |= CODE_ACC;
+        if (a > 0.0) lo = hi; else hi = lo;
+    }
+    if (c_sc.limit_velocity) {
+        double bhi = vel_upper(v, a, V, J, A, ts);
+        double blo = -vel_upper(-v, -a, V, J, A, ts);
+        clamp_range(lo, hi, blo, bhi, CODE_VEL_HI, CODE_VEL_LO, code);
+    }
+    need_pos = false;
+    if (c_sc.limit_position) {
+        const bool vg = c_sc.limit_velocity && code == 0 && fabs(v) <= V;
+        need_pos = !(pos_bound_inactive(p, v, a, hi, c_sc.pos_hi[j], J, A, V, ts, vg) &&
+                     pos_bound_inactive(-p, -v, -a, -lo, -c_sc.pos_lo[j], J, A, V, ts, vg));
+    }
+}
+
 __device__ void safe_range_joint(int j, double p, double v, double a, double& out_lo, double& out_hi, int& out_code) {
     double ts = c_sc.ts, J = c_sc.jerk_max[j], A = c_sc.acc_max[j], V = c_sc.vel_max[j];
     int code = 0;

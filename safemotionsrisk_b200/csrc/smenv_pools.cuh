@@ -362,7 +362,11 @@ __global__ void safe_range_kernel(const double* kin, double* lo, double* hi, int
     const double* k = kin + (size_t)env * SM_KIN_STRIDE;
     double l, h;
     int c;
-    safe_range_joint(j, k[j], k[8 + j], k[16 + j], l, h, c);
+    // same two-path evaluation as the step: the light path with the conservative position filter, the full
+    // iterative solve only where the filter cannot rule the position bounds out
+    bool need_pos;
+    safe_range_light(j, k[j], k[8 + j], k[16 + j], l, h, c, need_pos);
+    if (need_pos) safe_range_joint(j, k[j], k[8 + j], k[16 + j], l, h, c);
     lo[env * SM_MAX_JOINTS + j] = l;
     hi[env * SM_MAX_JOINTS + j] = h;
     code[env * SM_MAX_JOINTS + j] = c;

@@ -24,6 +24,7 @@ struct StepArgs {
     uint32_t k0, k1;   // Philox key (seed)
     float* scratch;    // [n][SM_SCRATCH_FLOATS]
     int* worklist;     // [0] = count, [1..] = env indices flagged by the broad phase
+    int* heavy;        // joint_heavy_kernel's list; its counter is cleared by finish_kernel for the next step
     const double* start_pool;
     int start_pool_n;
     const double* ball_pool;
@@ -280,6 +281,7 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
     __shared__ double s_ob[8][SM_OBST_STRIDE];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 16) s_stats[tid] = 0.0;
+    if (blockIdx.x == 0 && tid == 0 && A.heavy) A.heavy[0] = 0;
     __syncthreads();
     const int env = blockIdx.x * 8 + warp;
     const int nj = c_sc.n_joints;
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
         if (lane < SM_OBST_STRIDE) ob[lane] = A.buf.obst[(size_t)env * SM_OBST_STRIDE + lane];
         const int4 ep = *reinterpret_cast<const int4*>(A.buf.episode + 4 * (size_t)env);
         const int ep_len = ep.x + 1;  // safe_motions_base.py:1044
-        const float rcode = scr[SM_MISC_RCODE], jerk_rel = scr[SM_MISC_JERK], umax = scr[SM_MISC_UMAX];
+        const float rcode = (float)__float_as_int(scr[SM_MISC_RCODE]), jerk_rel = scr[SM_MISC_JERK], umax = scr[SM_MISC_UMAX];
         __syncwarp();
         const double latch = ob[SM_OB_LATCH], ball_active = ob[SM_OB_BALL_ACTIVE];
 

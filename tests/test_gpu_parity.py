@@ -47,8 +47,9 @@ def test_extension_is_loaded_and_counts_launches():
     env.set_state(q, q, q, np.zeros((32, 16)))
     env.step(np.zeros((32, 7), dtype=np.float32))
     torch.cuda.synchronize()
-    # set_state + observation, then the step: joint + contact broad + contact narrow + distance + finish kernels
-    assert env.launch_count() - n0 == 7
+    # set_state + observation, then the step: joint + joint heavy + contact broad + contact narrow + distance +
+    # finish kernels
+    assert env.launch_count() - n0 == 8
     env.close()
 
 
@@ -56,7 +57,7 @@ def test_safe_range_bit_exact():
     env = make_env("space", 8, fill_pools=False)
     sc = env.scene
     rng = np.random.default_rng(0)
-    n = 20000
+    n = 200000
     lo_p, hi_p, V, A = (np.array(x) for x in (sc.pos_lo, sc.pos_hi, sc.vel_max, sc.acc_max))
     q = rng.uniform(lo_p, hi_p, (n, 7))
     v = rng.uniform(-1, 1, (n, 7)) * V
@@ -64,6 +65,12 @@ def test_safe_range_bit_exact():
     # a quarter of the states hug a position limit, a quarter a velocity limit
     q[: n // 4] = hi_p - rng.uniform(0, 0.05, (n // 4, 7)) ** 2
     v[n // 4: n // 2] = V * (1 - rng.uniform(0, 0.05, (n // 4, 7)) ** 2)
+    # an eighth sits in the band where the conservative position filter of the light path switches (0 - 1.5 rad
+    # below the limit, moving towards it), an eighth mirrors that at the lower limit
+    q[n // 2: 5 * n // 8] = hi_p - rng.uniform(0, 1.5, (n // 8, 7))
+    v[n // 2: 5 * n // 8] = np.abs(v[n // 2: 5 * n // 8])
+    q[5 * n // 8: 3 * n // 4] = lo_p + rng.uniform(0, 1.5, (n // 8, 7))
+    v[5 * n // 8: 3 * n // 4] = -np.abs(v[5 * n // 8: 3 * n // 4])
     kin = np.zeros((n, 32))
     kin[:, 0:7], kin[:, 8:15], kin[:, 16:23] = q, v, a
     lo, hi, code = env.safe_range(kin)
