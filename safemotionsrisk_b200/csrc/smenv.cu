@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "smenv_pools.cuh"
@@ -19,11 +20,72 @@ static int fail(int code, const std::string& msg) {
             return fail(SM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                   \
     } while (0)
 
+// ------------------------------------------------------------------------------------------------------------------
+// Support-direction table of one hull (layout: smenv_device.cuh).  A vertex is listed for a cell if, for some sample
+// direction of the cell (a (SUB x SUB) grid that includes the cell border), its support value is within
+// diam * (distance to the nearest sample) of the maximum -- then it is listed for every direction of the cell it
+// could win.  Float rounding of lut_cell on the device at a cell border is covered by the same slack.
+// ------------------------------------------------------------------------------------------------------------------
+static void build_lut(const float4* v, int n, std::vector<uint32_t>& out) {
+    const int R = SM_LUT_RES, SUB = 33, cells = 6 * R * R;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int i = 0; i < n; ++i) {
+        const float p[3] = {v[i].x, v[i].y, v[i].z};
+        for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], p[k]); hi[k] = fmaxf(hi[k], p[k]); }
+    }
+    const double diam = sqrt((double)(hi[0] - lo[0]) * (hi[0] - lo[0]) + (double)(hi[1] - lo[1]) * (hi[1] - lo[1]) +
+                             (double)(hi[2] - lo[2]) * (hi[2] - lo[2]));
+    const double spacing = 2.0 / R / (SUB - 1);            // on the cube face; the chord on the sphere is shorter
+    const double slack = diam * spacing * 0.7072 * 1.05 + 1e-7;
+    std::vector<std::vector<unsigned char>> lists(cells);
+    std::vector<double> dots(n);
+    std::vector<char> take(n);
+    for (int face = 0; face < 6; ++face) {
+        const int ax = face / 2, a = (ax + 1) % 3, b = (ax + 2) % 3;
+        const double sgn = (face % 2 == 0) ? 1.0 : -1.0;
+        for (int iu = 0; iu < R; ++iu)
+            for (int iw = 0; iw < R; ++iw) {
+                std::fill(take.begin(), take.end(), 0);
+                for (int su = 0; su < SUB; ++su)
+                    for (int sw = 0; sw < SUB; ++sw) {
+                        double d[3];
+                        d[ax] = sgn;
+                        d[a] = -1.0 + 2.0 * (iu + (double)su / (SUB - 1)) / R;
+                        d[b] = -1.0 + 2.0 * (iw + (double)sw / (SUB - 1)) / R;
+                        const double nrm = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                        double mx = -1e300;
+                        for (int i = 0; i < n; ++i) {
+                            dots[i] = (v[i].x * d[0] + v[i].y * d[1] + v[i].z * d[2]) / nrm;
+                            if (dots[i] > mx) mx = dots[i];
+                        }
+                        for (int i = 0; i < n; ++i)
+                            if (mx - dots[i] <= slack) take[i] = 1;
+                    }
+                std::vector<unsigned char>& L = lists[(face * R + iu) * R + iw];
+                for (int i = 0; i < n; ++i)
+                    if (take[i]) L.push_back((unsigned char)i);
+            }
+    }
+    const size_t base = out.size();
+    out.resize(base + cells);
+    for (int c = 0; c < cells; ++c) {
+        std::vector<unsigned char>& L = lists[c];
+        size_t cnt = L.size();
+        if (cnt > 255) { L.resize(255); cnt = 255; }  // cannot happen for <= 255-vertex hulls
+        while (L.size() % 4) L.push_back(L.back());
+        const uint32_t off = (uint32_t)(out.size() - base);
+        out[base + c] = (off << 8) | (uint32_t)cnt;
+        for (size_t k = 0; k < L.size(); k += 4)
+            out.push_back((uint32_t)L[k] | ((uint32_t)L[k + 1] << 8) | ((uint32_t)L[k + 2] << 16) | ((uint32_t)L[k + 3] << 24));
+    }
+}
+
 struct SmEnv {
     int n = 0, device = 0;
     uint64_t seed = 0;
     DevScene host_scene;  // device pointers inside
     float4* d_verts = nullptr;
+    uint32_t* d_lut = nullptr;
     float4* d_ppos[SM_MAX_OBSTACLES] = {nullptr, nullptr};
     float4* d_pquat[SM_MAX_OBSTACLES] = {nullptr, nullptr};
     double* d_plocal = nullptr;
@@ -33,7 +95,14 @@ struct SmEnv {
     bool pools_filled = false;
     unsigned long long* d_counters = nullptr;
     float* d_scratch = nullptr;  // per-env hand-over between the phase kernels of a step
-    int* d_worklist = nullptr;   // [0] = count, [1..n] = envs flagged by the contact broad phase
+    int* d_worklist = nullptr;   // [0] = GJK item counter (cleared by joint_kernel), [1] = overflowed items
+    GjkItem* d_items = nullptr;  // work items of one step (smenv_plan.cuh -> smenv_gjk.cuh)
+    int item_capacity = 0;
+    unsigned* d_res = nullptr;   // [n][SM_RES_STRIDE] distance keys / first contact sub-step
+    int* h_flag = nullptr;       // mapped pinned host word set by finish_kernel when the item buffer overflowed
+    int* d_flag = nullptr;       // its device alias
+    size_t smem_bytes_gjk = 0;
+    int grid_gjk = 0;
     int* d_heavy = nullptr;      // [0] = count, [1..8n] = (env, joint) instances deferred to joint_heavy_kernel
     bool count = false;
     size_t smem_bytes = 0;        // kernels that stage the hull vertices
@@ -108,6 +177,7 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     std::vector<float4> verts(sc->n_verts);
     for (int i = 0; i < sc->n_verts; ++i)
         verts[i] = make_float4((float)sc->verts[3 * i], (float)sc->verts[3 * i + 1], (float)sc->verts[3 * i + 2], 0.f);
+    std::vector<uint32_t> lut;
     for (int s = 0; s < sc->n_shapes; ++s) {
         const SmShape& h = sc->shapes[s];
         DevShape& g = d.shapes[s];
@@ -124,6 +194,14 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
             g.bmin[2] = fminf(g.bmin[2], verts[i].z); g.bmax[2] = fmaxf(g.bmax[2], verts[i].z);
         }
         g.radius = r * (1.0f + 1e-6f) + 1e-7f;
+        double gs[3] = {0, 0, 0};
+        for (int i = h.vert_off; i < h.vert_off + h.vert_cnt; ++i) { gs[0] += verts[i].x; gs[1] += verts[i].y; gs[2] += verts[i].z; }
+        g.gx = (float)(gs[0] / h.vert_cnt); g.gy = (float)(gs[1] / h.vert_cnt); g.gz = (float)(gs[2] / h.vert_cnt);
+        g.lut = -1;
+        if (h.vert_cnt >= SM_LUT_MIN_VERTS && h.vert_cnt <= 255) {
+            g.lut = (int)lut.size();
+            build_lut(verts.data() + h.vert_off, h.vert_cnt, lut);
+        }
     }
     d.n_static_pairs = sc->n_static_pairs; d.n_self_pairs = sc->n_self_pairs;
     d.n_mov_reward = sc->n_mov_reward; d.n_mov_contact = sc->n_mov_contact;
@@ -190,6 +268,10 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     int rc = upload(&env->d_verts, verts);
     if (rc) { delete env; return rc; }
     d.verts = env->d_verts;
+    if (lut.empty()) lut.push_back(0u);
+    if ((rc = upload(&env->d_lut, lut))) { delete env; return rc; }
+    d.lut = env->d_lut;
+    d.n_lut_words = (int)lut.size();
     for (int o = 0; o < sc->n_obstacles; ++o) {
         if (sc->obst_kind[o] != SM_OBST_PLANET) continue;
         std::vector<float4> pp(sc->planet_steps), pq(sc->planet_steps);
@@ -216,8 +298,19 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     if (env->ball_pool_n) CU(cudaMalloc((void**)&env->d_ball_pool, (size_t)env->ball_pool_n * SM_BALL_STRIDE * sizeof(double)));
     CU(cudaMalloc((void**)&env->d_scratch, (size_t)num_envs * SM_SCRATCH_FLOATS * sizeof(float)));
     CU(cudaMemset(env->d_scratch, 0, (size_t)num_envs * SM_SCRATCH_FLOATS * sizeof(float)));
-    CU(cudaMalloc((void**)&env->d_worklist, ((size_t)num_envs + 1) * sizeof(int)));
-    CU(cudaMemset(env->d_worklist, 0, ((size_t)num_envs + 1) * sizeof(int)));
+    CU(cudaMalloc((void**)&env->d_worklist, 4 * sizeof(int)));
+    CU(cudaMemset(env->d_worklist, 0, 4 * sizeof(int)));
+    {   // item buffer: the mean is a few dozen items per env-step; sized generously, overflow is reported loudly
+        long long cap = (long long)num_envs * 192;
+        if (cap < 65536) cap = 65536;
+        env->item_capacity = (int)(cap > 0x7fffffffLL / 2 ? 0x7fffffffLL / 2 : cap);
+        CU(cudaMalloc((void**)&env->d_items, (size_t)env->item_capacity * sizeof(GjkItem)));
+        CU(cudaMalloc((void**)&env->d_res, (size_t)num_envs * SM_RES_STRIDE * sizeof(unsigned)));
+        CU(cudaMemset(env->d_res, 0xff, (size_t)num_envs * SM_RES_STRIDE * sizeof(unsigned)));
+        CU(cudaHostAlloc((void**)&env->h_flag, sizeof(int), cudaHostAllocMapped));
+        *env->h_flag = 0;
+        CU(cudaHostGetDevicePointer((void**)&env->d_flag, env->h_flag, 0));
+    }
     CU(cudaMalloc((void**)&env->d_heavy, ((size_t)num_envs * 8 + 1) * sizeof(int)));
     CU(cudaMemset(env->d_heavy, 0, ((size_t)num_envs * 8 + 1) * sizeof(int)));
     CU(cudaMalloc((void**)&env->d_counters, 16 * sizeof(unsigned long long)));
@@ -225,23 +318,25 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
 
     env->smem_bytes = smem_bytes_for(sc->n_verts, SM_WARPS_PER_BLOCK);
     env->smem_bytes_broad = smem_bytes_for(0, SM_WARPS_PER_BLOCK);
-    CU(cudaFuncSetAttribute(contact_narrow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
-    CU(cudaFuncSetAttribute(contact_narrow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
-    CU(cudaFuncSetAttribute(distance_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
-    CU(cudaFuncSetAttribute(distance_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
+    env->smem_bytes_gjk = gjk_smem_bytes(sc->n_verts, d.n_lut_words, sc->n_shapes);
+    CU(cudaFuncSetAttribute(gjk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_gjk));
+    CU(cudaFuncSetAttribute(gjk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_gjk));
     CU(cudaFuncSetAttribute(fill_ball_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
     CU(cudaFuncSetAttribute(fill_start_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
     CU(cudaFuncSetAttribute(distances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
     // persistent grid: as many CTAs as fit on the device at once (a multiple of the SM count), each looping over envs
     int sms = 0, per_sm = 0;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, distance_kernel<false>, SM_WARPS_PER_BLOCK * 32, env->smem_bytes));
-    if (per_sm < 1) { delete env; return fail(SM_ERR_CUDA, "distance kernel does not fit on an SM"); }
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, distances_kernel, SM_WARPS_PER_BLOCK * 32, env->smem_bytes));
+    if (per_sm < 1) { delete env; return fail(SM_ERR_CUDA, "pool kernels do not fit on an SM"); }
     env->grid = sms * per_sm;
     env->sms = sms;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, contact_broad_kernel<false>, SM_WARPS_PER_BLOCK * 32, env->smem_bytes_broad));
-    if (per_sm < 1) { delete env; return fail(SM_ERR_CUDA, "contact broad kernel does not fit on an SM"); }
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, distance_plan_kernel<false>, SM_WARPS_PER_BLOCK * 32, env->smem_bytes_broad));
+    if (per_sm < 1) { delete env; return fail(SM_ERR_CUDA, "planning kernels do not fit on an SM"); }
     env->grid_broad = sms * per_sm;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk_kernel<false>, 256, env->smem_bytes_gjk));
+    if (per_sm < 1) { delete env; return fail(SM_ERR_CUDA, "gjk kernel does not fit on an SM"); }
+    env->grid_gjk = sms * per_sm;
     *out = env;
     return SM_OK;
 }
@@ -250,8 +345,9 @@ extern "C" int smenv_destroy(SmEnv* env) {
     if (!env) return SM_OK;
     cudaSetDevice(env->device);
     if (g_active == env) g_active = nullptr;
-    cudaFree(env->d_verts); cudaFree(env->d_plocal); cudaFree(env->d_start_pool); cudaFree(env->d_ball_pool);
-    cudaFree(env->d_counters); cudaFree(env->d_scratch); cudaFree(env->d_worklist); cudaFree(env->d_heavy);
+    cudaFree(env->d_verts); cudaFree(env->d_lut); cudaFree(env->d_plocal); cudaFree(env->d_start_pool); cudaFree(env->d_ball_pool);
+    cudaFree(env->d_counters); cudaFree(env->d_scratch); cudaFree(env->d_worklist); cudaFree(env->d_heavy); cudaFree(env->d_items); cudaFree(env->d_res);
+    if (env->h_flag) cudaFreeHost(env->h_flag);
     for (int o = 0; o < SM_MAX_OBSTACLES; ++o) { cudaFree(env->d_ppos[o]); cudaFree(env->d_pquat[o]); }
     delete env;
     return SM_OK;
@@ -405,6 +501,10 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
     if (!env || !buf) return fail(SM_ERR_ARG, "smenv_step: null argument");
     if (!random_actions && !buf->actions) return fail(SM_ERR_ARG, "smenv_step: actions missing");
     if (auto_reset && !env->pools_filled) return fail(SM_ERR_STATE, "smenv_step: auto_reset needs smenv_fill_pools");
+    if (env->h_flag && *(volatile int*)env->h_flag != 0)
+        return fail(SM_ERR_STATE, "smenv_step: the GJK item buffer of an earlier step overflowed by " +
+                                      std::to_string(*(volatile int*)env->h_flag) + " items (capacity " +
+                                      std::to_string(env->item_capacity) + "); results since then are invalid");
     cudaStream_t stream = (cudaStream_t)s;
     int rc = activate(env, stream);
     if (rc) return rc;
@@ -413,7 +513,7 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
     JA.k0 = (uint32_t)env->seed; JA.k1 = (uint32_t)(env->seed >> 32);
     JA.step_counter = env->step_counter++;
     JA.scratch = env->d_scratch;
-    JA.worklist = env->d_worklist;
+    JA.worklist = env->d_worklist;  // clears the item counter and the overflow count
     JA.heavy = env->d_heavy;
     joint_kernel<<<(env->n * 8 + 255) / 256, 256, 0, stream>>>(JA);
     {   // the heavy list is at most 8 n long; blocks beyond its length exit at once
@@ -422,12 +522,22 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
         joint_heavy_kernel<<<hb, 128, 0, stream>>>(JA);
     }
     env->launches += 2;
+    PlanArgs P;
+    P.buf = *buf; P.n = env->n; P.scratch = env->d_scratch;
+    P.items = env->d_items; P.item_count = env->d_worklist; P.capacity = env->item_capacity;
+    P.overflow = env->d_worklist + 1; P.res = env->d_res;
+    P.kin = buf->kin; P.obst = buf->obst; P.advance = 1; P.counters = env->d_counters;
+    GjkArgs G;
+    G.items = env->d_items; G.n_items = env->d_worklist; G.capacity = env->item_capacity; G.res = env->d_res;
+    G.counters = env->d_counters;
     StepArgs A;
     A.buf = *buf; A.n = env->n; A.auto_reset = auto_reset;
     A.k0 = (uint32_t)env->seed; A.k1 = (uint32_t)(env->seed >> 32);
     A.scratch = env->d_scratch;
-    A.worklist = env->d_worklist;
+    A.res = env->d_res;
     A.heavy = env->d_heavy;
+    A.overflow = env->d_worklist + 1;
+    A.host_flag = env->d_flag;
     A.start_pool = env->pools_filled ? env->d_start_pool : nullptr;
     A.start_pool_n = env->pools_filled ? env->start_pool_n : 0;
     A.ball_pool = env->pools_filled ? env->d_ball_pool : nullptr;
@@ -435,26 +545,21 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
     A.counters = env->d_counters;
     const int T = SM_WARPS_PER_BLOCK * 32;
     const int blocks = (env->n + SM_WARPS_PER_BLOCK - 1) / SM_WARPS_PER_BLOCK;
-    const int grid = blocks < env->grid ? blocks : env->grid;
-    const int grid_b = blocks < env->grid_broad ? blocks : env->grid_broad;
+    const int grid_p = blocks < env->grid_broad ? blocks : env->grid_broad;
     const int grid_f = (env->n + 7) / 8;
     const bool contacts = env->host_scene.contact_stride > 0 && env->host_scene.n_obstacles > 0;
     if (env->count) {
-        if (contacts) {
-            contact_broad_kernel<true><<<grid_b, T, env->smem_bytes_broad, stream>>>(A);
-            contact_narrow_kernel<true><<<grid, T, env->smem_bytes, stream>>>(A);
-        }
-        distance_kernel<true><<<grid, T, env->smem_bytes, stream>>>(A);
+        if (contacts) contact_plan_kernel<true><<<grid_p, T, env->smem_bytes_broad, stream>>>(P);
+        distance_plan_kernel<true><<<grid_p, T, env->smem_bytes_broad, stream>>>(P);
+        gjk_kernel<true><<<env->grid_gjk, 256, env->smem_bytes_gjk, stream>>>(G);
         finish_kernel<true><<<grid_f, 256, 0, stream>>>(A);
     } else {
-        if (contacts) {
-            contact_broad_kernel<false><<<grid_b, T, env->smem_bytes_broad, stream>>>(A);
-            contact_narrow_kernel<false><<<grid, T, env->smem_bytes, stream>>>(A);
-        }
-        distance_kernel<false><<<grid, T, env->smem_bytes, stream>>>(A);
+        if (contacts) contact_plan_kernel<false><<<grid_p, T, env->smem_bytes_broad, stream>>>(P);
+        distance_plan_kernel<false><<<grid_p, T, env->smem_bytes_broad, stream>>>(P);
+        gjk_kernel<false><<<env->grid_gjk, 256, env->smem_bytes_gjk, stream>>>(G);
         finish_kernel<false><<<grid_f, 256, 0, stream>>>(A);
     }
-    env->launches += contacts ? 4 : 2;
+    env->launches += contacts ? 4 : 3;
     CU(cudaGetLastError());
     return SM_OK;
 }
@@ -479,11 +584,28 @@ extern "C" int smenv_safe_range(SmEnv* env, const double* kin, double* lo, doubl
 extern "C" int smenv_distances(SmEnv* env, const double* kin, const double* obst, float* d_static, float* d_self,
                                float* d_moving, int n, SmStream s) {
     if (!env || !kin || !obst || !d_static || !d_self || !d_moving) return fail(SM_ERR_ARG, "smenv_distances: null argument");
+    if (n > env->n) return fail(SM_ERR_ARG, "smenv_distances: n exceeds the env count the buffers were sized for");
     cudaStream_t stream = (cudaStream_t)s;
     int rc = activate(env, stream);
     if (rc) return rc;
-    distances_kernel<<<grid_for(env, n), SM_WARPS_PER_BLOCK * 32, env->smem_bytes, stream>>>(kin, obst, d_static, d_self, d_moving, n);
-    env->launches++;
+    // the same kernels as the step: plan the pair queries of the given poses, run them, decode the result records
+    CU(cudaMemsetAsync(env->d_worklist, 0, 2 * sizeof(int), stream));
+    PlanArgs P;
+    memset(&P, 0, sizeof(P));
+    P.n = n; P.scratch = env->d_scratch;
+    P.items = env->d_items; P.item_count = env->d_worklist; P.capacity = env->item_capacity;
+    P.overflow = env->d_worklist + 1; P.res = env->d_res;
+    P.kin = kin; P.obst = obst; P.advance = 0; P.counters = env->d_counters;
+    GjkArgs G;
+    G.items = env->d_items; G.n_items = env->d_worklist; G.capacity = env->item_capacity; G.res = env->d_res;
+    G.counters = env->d_counters;
+    const int T = SM_WARPS_PER_BLOCK * 32;
+    const int blocks = (n + SM_WARPS_PER_BLOCK - 1) / SM_WARPS_PER_BLOCK;
+    const int grid_p = blocks < env->grid_broad ? blocks : env->grid_broad;
+    distance_plan_kernel<false><<<grid_p, T, env->smem_bytes_broad, stream>>>(P);
+    gjk_kernel<false><<<env->grid_gjk, 256, env->smem_bytes_gjk, stream>>>(G);
+    distances_out_kernel<<<(n + 255) / 256, 256, 0, stream>>>(env->d_res, obst, d_static, d_self, d_moving, n);
+    env->launches += 3;
     CU(cudaGetLastError());
     return SM_OK;
 }

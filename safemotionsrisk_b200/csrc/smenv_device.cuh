@@ -25,7 +25,32 @@ struct DevShape {
     int frame, off, cnt, link;
     float margin, cx, cy, cz, radius;
     float bmin[3], bmax[3];  // axis-aligned box of the core vertices in frame coordinates
+    float gx, gy, gz;        // centroid of the vertices: a point inside the hull (upper bounds of pair distances)
+    int lut;                 // word offset of the shape's support-direction table in DevScene.lut, -1 = none
 };
+
+// Support-direction table ("LUT") of a hull: the unit sphere of directions is cut into 6 * SM_LUT_RES^2 cube-map
+// cells; per cell the table lists every vertex that is the support point for SOME direction of the cell, so that a
+// support query only scans that list (~20 of 252 vertices of an iiwa link).  Layout at word offset `lut`:
+//   cells[6 R R]  : (word offset of the list relative to `lut`) << 8 | number of candidates
+//   lists         : candidate vertex indices (local to the shape), one byte each, four per word, padded to a word
+//                   boundary by repeating the last candidate
+#define SM_LUT_RES 4
+#define SM_LUT_MIN_VERTS 33 /* smaller hulls are scanned directly */
+
+__host__ __device__ __forceinline__ int lut_cell(float dx, float dy, float dz) {
+    const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+    int face;
+    float m, u, w;
+    if (ax >= ay && ax >= az) { face = dx > 0.0f ? 0 : 1; m = ax; u = dy; w = dz; }
+    else if (ay >= az) { face = dy > 0.0f ? 2 : 3; m = ay; u = dz; w = dx; }
+    else { face = dz > 0.0f ? 4 : 5; m = az; u = dx; w = dy; }
+    const float s = (0.5f * SM_LUT_RES) / m;
+    int iu = (int)(u * s + 0.5f * SM_LUT_RES), iw = (int)(w * s + 0.5f * SM_LUT_RES);
+    iu = iu < 0 ? 0 : (iu > SM_LUT_RES - 1 ? SM_LUT_RES - 1 : iu);
+    iw = iw < 0 ? 0 : (iw > SM_LUT_RES - 1 ? SM_LUT_RES - 1 : iw);
+    return (face * SM_LUT_RES + iu) * SM_LUT_RES + iw;
+}
 
 struct DevScene {
     int n_joints, substeps, contact_stride, limit_velocity, limit_position;
@@ -69,6 +94,8 @@ struct DevScene {
     int ball_check_invalid, ball_random_initial, has_table;
     double min_start_self, ball_target_min_static, ball_target_min_self;
     const float4* verts;  // device, n_verts
+    const uint32_t* lut;  // device, n_lut_words (support-direction tables of all shapes that have one)
+    int n_lut_words;
 };
 
 // the library is one translation unit (smenv.cu), so the constant-memory scene is defined here

@@ -1,0 +1,234 @@
+// smenv_gjk.cuh -- the narrow phase of the env step: ONE THREAD PER CONVEX PAIR QUERY.
+//
+// The planning kernels (smenv_plan.cuh) turn every env step into a flat list of 64-byte work items, one per convex
+// pair that bounding volumes could not decide: "distance of robot shape A to obstacle shape B at the new knot"
+// (getClosestPoints call sites ctlp.py:3267, :3300, :3353) or "do A and B touch in sub-step k" (getContactPoints,
+// ctlp.py:4188, :4572).  gjk_kernel runs GJK on 32 different items per warp: the simplex arithmetic, which every
+// lane of the former warp-per-pair version repeated redundantly, now does 32 times the work per instruction, and a
+// support query scans only the ~20 candidates its direction's table cell lists (smenv_device.cuh, SM_LUT_RES)
+// instead of all 252 vertices of an iiwa link.
+//
+// Exact pruning survives the parallelism: items of the same (env, distance class) sit next to each other in the
+// list; the lanes that hold them form a group (match.any) and exchange, every iteration, the best upper bound any
+// of them has reached (redux.min).  A lane whose separating-plane lower bound passes that value stops -- its pair
+// cannot hold the minimum.  Every lane reports its last upper bound, so the group minimum is the exact minimum over
+// the pairs however the items are split over warps (atomicMin on the env's result slot merges the groups).
+#pragma once
+#include "smenv_geom.cuh"
+
+enum { GJK_STATIC = 0, GJK_SELF = 1, GJK_MOVING = 2, GJK_CONTACT = 3 };
+
+struct __align__(16) GjkItem {
+    int env;
+    uint32_t shapes;  // shape A | shape B << 16
+    uint32_t meta;    // class | (1-based sub-step of a contact item) << 8
+    float thr;        // distance classes: only distances <= thr count (query distance, tightened by the best upper
+                      // bound known at planning time); contact class: the manifold's contact threshold
+    float R[9];       // pose of B in the frame of A:  x_A = R x_B + t
+    float t[3];
+};
+static_assert(sizeof(GjkItem) == 64, "GjkItem must stay 64 bytes");
+
+#define SM_RES_STRIDE 4          /* per-env result record: static, self, moving distance keys, first contact sub-step */
+#define SM_RES_NO_CONTACT 0x7fffffffu
+
+struct GjkArgs {
+    const GjkItem* items;
+    const int* n_items;  // device counter written by the planning kernels
+    int capacity;
+    unsigned* res;       // [n][SM_RES_STRIDE]
+    unsigned long long* counters;
+};
+
+__device__ __forceinline__ float funkey(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// shared memory of gjk_kernel: hull vertices | direction tables | shapes
+struct GjkSmem {
+    float4* verts;
+    uint32_t* lut;
+    DevShape* shapes;
+};
+__device__ __forceinline__ GjkSmem gjk_carve(unsigned char* raw) {
+    GjkSmem G;
+    G.verts = reinterpret_cast<float4*>(raw);
+    size_t off = (size_t)c_sc.n_verts * sizeof(float4);
+    G.lut = reinterpret_cast<uint32_t*>(raw + off);
+    off += (((size_t)c_sc.n_lut_words * 4) + 15) & ~(size_t)15;
+    G.shapes = reinterpret_cast<DevShape*>(raw + off);
+    return G;
+}
+static size_t gjk_smem_bytes(int n_verts, int n_lut_words, int n_shapes) {
+    return (size_t)n_verts * sizeof(float4) + ((((size_t)n_lut_words * 4) + 15) & ~(size_t)15) +
+           (size_t)n_shapes * sizeof(DevShape);
+}
+
+// support vertex of a hull in (local) direction d, scanned by one thread
+__device__ __forceinline__ int support_thread(const float4* __restrict__ v, int n, const uint32_t* __restrict__ lut,
+                                              int lut_off, V3 d, unsigned& ndots) {
+    float best = -FLT_MAX;
+    int bi = 0;
+    if (lut_off >= 0) {
+        const uint32_t* L = lut + lut_off;
+        const uint32_t e = L[lut_cell(d.x, d.y, d.z)];
+        const uint32_t* w = L + (e >> 8);
+        const int cnt = (int)(e & 255u);
+        ndots += (unsigned)cnt;
+#pragma unroll 1
+        for (int c = 0; c < cnt; c += 4) {
+            const uint32_t word = *w++;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = (int)((word >> (8 * k)) & 255u);
+                const float4 p = v[i];
+                const float s = fmaf(p.x, d.x, fmaf(p.y, d.y, p.z * d.z));
+                if (s > best) { best = s; bi = i; }
+            }
+        }
+    } else {
+        ndots += (unsigned)n;
+#pragma unroll 2
+        for (int i = 0; i < n; ++i) {
+            const float4 p = v[i];
+            const float s = fmaf(p.x, d.x, fmaf(p.y, d.y, p.z * d.z));
+            if (s > best) { best = s; bi = i; }
+        }
+    }
+    return bi;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(256) gjk_kernel(GjkArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int n_items = *A.n_items;
+    if (n_items > A.capacity) n_items = A.capacity;
+    if ((int)(blockIdx.x * blockDim.x) >= n_items) return;  // nothing for this block: skip the staging
+    GjkSmem G = gjk_carve(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < c_sc.n_verts; i += blockDim.x) G.verts[i] = __ldg(c_sc.verts + i);
+    for (int i = tid; i < c_sc.n_lut_words; i += blockDim.x) G.lut[i] = __ldg(c_sc.lut + i);
+    for (int i = tid; i < (int)(sizeof(DevShape) / 4) * c_sc.n_shapes; i += blockDim.x)
+        reinterpret_cast<int*>(G.shapes)[i] = reinterpret_cast<const int*>(c_sc.shapes)[i];
+    __syncthreads();
+    unsigned c_iters = 0, c_dots = 0, c_calls = 0;
+#pragma unroll 1
+    for (int wbase = (blockIdx.x * blockDim.x + tid) & ~31; wbase < n_items; wbase += gridDim.x * blockDim.x) {
+        const int idx = wbase + lane;
+        const bool active = idx < n_items;
+        // ---------------- load the item (four 16-byte loads)
+        const float4* ip = reinterpret_cast<const float4*>(A.items + (active ? idx : wbase));
+        const float4 h0 = __ldg(ip), h1 = __ldg(ip + 1), h2 = __ldg(ip + 2), h3 = __ldg(ip + 3);
+        const int env = __float_as_int(h0.x);
+        const unsigned shp = __float_as_uint(h0.y), meta = __float_as_uint(h0.z);
+        const float thr = h0.w;
+        const int cls = (int)(meta & 255u);
+        const float r0 = h1.x, r1 = h1.y, r2 = h1.z, r3 = h1.w, r4 = h2.x, r5 = h2.y, r6 = h2.z, r7 = h2.w, r8 = h3.x;
+        const float tx = h3.y, ty = h3.z, tz = h3.w;
+        const DevShape& SA = G.shapes[shp & 0xffffu];
+        const DevShape& SB = G.shapes[shp >> 16];
+        const float4* vA = G.verts + SA.off;
+        const float4* vB = G.verts + SB.off;
+        const int nA = SA.cnt, nB = SB.cnt, lutA = SA.lut, lutB = SB.lut;
+        const float m = SA.margin + SB.margin;
+        // lanes with the same (env, distance class) prune each other; contact items and idle lanes stand alone
+        const unsigned gkey = (active && cls != GJK_CONTACT) ? (((unsigned)env << 2) | (unsigned)cls)
+                                                             : (0x80000000u | (unsigned)lane);
+        const unsigned peers = __match_any_sync(FULL, gkey);
+        const float lim_fixed = (cls == GJK_CONTACT ? thr + 1e-3f : thr) + m;  // on the distance between the cores
+        const float touch = cls == GJK_CONTACT ? thr + m : -1.0f;
+        float lim = lim_fixed;
+        // ---------------- GJK in the frame of A
+        Simplex S;
+        S.n = 0;
+        S.i0 = S.i1 = S.i2 = S.i3 = -1;
+        S.p0 = S.p1 = S.p2 = S.p3 = mk(0.f, 0.f, 0.f);
+        V3 v;
+        {   // first direction: between the bounding-sphere centres
+            const float bx = fmaf(r0, SB.cx, fmaf(r1, SB.cy, fmaf(r2, SB.cz, tx)));
+            const float by = fmaf(r3, SB.cx, fmaf(r4, SB.cy, fmaf(r5, SB.cz, ty)));
+            const float bz = fmaf(r6, SB.cx, fmaf(r7, SB.cy, fmaf(r8, SB.cz, tz)));
+            v = mk(SA.cx - bx, SA.cy - by, SA.cz - bz);
+        }
+        float vv = dot(v, v);
+        if (vv < 1e-12f) { v = mk(1.f, 0.f, 0.f); vv = 1.f; }
+        bool have_point = false;
+        bool done = !active;
+        if (COUNT && active) c_calls++;
+#pragma unroll 1
+        for (int it = 0; it < 32; ++it) {
+            if (!done) {
+                const int sa = support_thread(vA, nA, G.lut, lutA, mk(-v.x, -v.y, -v.z), c_dots);
+                const V3 dB = mk(fmaf(r0, v.x, fmaf(r3, v.y, r6 * v.z)), fmaf(r1, v.x, fmaf(r4, v.y, r7 * v.z)),
+                                 fmaf(r2, v.x, fmaf(r5, v.y, r8 * v.z)));  // R^T v
+                const int sb = support_thread(vB, nB, G.lut, lutB, dB, c_dots);
+                if (COUNT) c_iters++;
+                const float4 pa = vA[sa], pb = vB[sb];
+                const V3 w = mk(pa.x - fmaf(r0, pb.x, fmaf(r1, pb.y, fmaf(r2, pb.z, tx))),
+                                pa.y - fmaf(r3, pb.x, fmaf(r4, pb.y, fmaf(r5, pb.z, ty))),
+                                pa.z - fmaf(r6, pb.x, fmaf(r7, pb.y, fmaf(r8, pb.z, tz))));
+                const int id = (sa << 16) | sb;
+                if (!have_point) {  // the first iteration only seeds the simplex with a real point of A - B
+                    S.p0 = w; S.i0 = id; S.n = 1;
+                    v = w; vv = dot(v, v);
+                    have_point = true;
+                    if (vv <= touch * touch && touch >= 0.0f) done = true;
+                    if (vv <= 1e-20f) { vv = 0.0f; done = true; }
+                } else {
+                    const float vw = dot(v, w);
+                    const float nv = sqrtf(vv);
+                    if (vw > 0.0f && vw * vw >= lim * lim * vv) done = true;                      // pruned
+                    else if (vv - vw <= fmaxf(1e-6f * vv, 3e-7f * nv)) done = true;               // converged
+                    else if (id == S.i0 || id == S.i1 || id == S.i2 || id == S.i3) done = true;   // support repeats
+                    else {
+                        if (S.n == 1) { S.p1 = w; S.i1 = id; }
+                        else if (S.n == 2) { S.p2 = w; S.i2 = id; }
+                        else { S.p3 = w; S.i3 = id; }
+                        S.n++;
+                        V3 nvv;
+                        if (simplex_solve(S, nvv)) { vv = 0.0f; done = true; }
+                        else {
+                            if (S.n < 4) S.i3 = -1;
+                            if (S.n < 3) S.i2 = -1;
+                            if (S.n < 2) S.i1 = -1;
+                            const float nd = dot(nvv, nvv);
+                            if (!(nd < vv)) done = true;  // no progress (numerical floor) or a NaN
+                            else {
+                                v = nvv; vv = nd;
+                                if (vv <= 1e-20f) { vv = 0.0f; done = true; }
+                                if (touch >= 0.0f && vv <= touch * touch) done = true;
+                            }
+                        }
+                    }
+                }
+            }
+            // the group's best upper bound tightens every member's pruning limit
+            const unsigned ub = have_point ? fkey(sqrtf(vv) - m) : 0xffffffffu;
+            const unsigned gb = __reduce_min_sync(peers, ub);
+            if (cls != GJK_CONTACT && gb != 0xffffffffu) lim = fminf(lim_fixed, funkey(gb) + m);
+            if (__all_sync(FULL, done)) break;
+        }
+        // ---------------- results
+        const float d = sqrtf(vv) - m;
+        const bool counts = active && have_point && d <= thr;
+        if (cls == GJK_CONTACT) {
+            if (counts) atomicMin(&A.res[(size_t)env * SM_RES_STRIDE + 3], meta >> 8);
+        }
+        const unsigned gmin = __reduce_min_sync(peers, (counts && cls != GJK_CONTACT) ? fkey(d) : 0xffffffffu);
+        if (active && cls != GJK_CONTACT && gmin != 0xffffffffu && lane == __ffs(peers) - 1)
+            atomicMin(&A.res[(size_t)env * SM_RES_STRIDE + cls], gmin);
+    }
+    if (COUNT && A.counters) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            c_calls += __shfl_xor_sync(FULL, c_calls, o);
+            c_iters += __shfl_xor_sync(FULL, c_iters, o);
+            c_dots += __shfl_xor_sync(FULL, c_dots, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&A.counters[0], (unsigned long long)c_calls);
+            atomicAdd(&A.counters[1], (unsigned long long)c_iters);
+            atomicAdd(&A.counters[2], (unsigned long long)c_dots);
+        }
+    }
+}

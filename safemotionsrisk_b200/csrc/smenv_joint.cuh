@@ -28,7 +28,7 @@ struct JointArgs {
     int random_actions;
     uint32_t k0, k1, step_counter;
     float* scratch;  // [n][SM_SCRATCH_FLOATS]
-    int* worklist;   // [0] = number of envs flagged for the narrow phase (reset here), [1..] = their indices
+    int* worklist;   // [0] = GJK item counter, [1] = overflowed items of the step: both cleared here
     int* heavy;      // [0] = number of (env, joint) instances whose position bound needs the iterative solve,
                      // [1..] = env * 8 + joint (filled by joint_kernel, consumed by joint_heavy_kernel)
 };
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) joint_kernel(JointArgs A) {
         float val = j == SM_MISC_RCODE ? __int_as_float((int)rc) : j == SM_MISC_JERK ? jerk_rel : j == SM_MISC_UMAX ? um : 0.0f;
         scr[SM_MISC_OFF + j] = val;
     }
-    if (t == 0 && A.worklist) A.worklist[0] = 0;
+    if (t == 0 && A.worklist) { A.worklist[0] = 0; A.worklist[1] = 0; }
 }
 
 // Second pass: one thread per deferred (env, joint): the full range with the iterative position solve.

@@ -1,0 +1,341 @@
+// smenv_plan.cuh -- planning kernels of the env step: bounding-volume culling that turns each env's collision queries
+// into GJK work items (smenv_gjk.cuh).  One warp per env, no hull vertices touched here.
+//
+//   contact_plan_kernel   lane k = physics sub-step k+1: serial FK of the motor-tracked pose, robot link spheres
+//                         against the obstacle spheres (whole body first, then per convex part), one contact item per
+//                         (sub-step, link shape, obstacle part) whose spheres come within the manifold threshold
+//                         (ObstacleWrapperSim.update, ctlp.py:2590-2862; contact semantics SURVEY Appendix B.5)
+//   distance_plan_kernel  obstacle poses at the end of the step, FK of the new knot (warp scan), then lanes = pairs:
+//                         sphere lower bound and centroid upper bound per pair, class-wise best upper bound, one
+//                         distance item per pair that could still hold the class minimum
+//                         (get_minimum_distance ctlp.py:3282-3374, .._to_moving_obstacles :3217-3280)
+#pragma once
+#include "smenv_gjk.cuh"
+#include "smenv_joint.cuh"
+
+struct PlanArgs {
+    SmBuffers buf;
+    int n;
+    const float* scratch;    // [n][SM_SCRATCH_FLOATS] sub-step poses written by the joint kernels
+    GjkItem* items;
+    int* item_count;         // device counter
+    int capacity;
+    int* overflow;           // device flag: items that did not fit (the step's results are then invalid)
+    unsigned* res;           // [n][SM_RES_STRIDE]
+    const double* kin;       // kinematic records to plan for (buf.kin in the step, the caller's array in the hook)
+    const double* obst;      // obstacle records
+    int advance;             // 1: obstacle poses at the end of the step about to be finished; 0: poses as recorded
+    unsigned long long* counters;
+};
+
+// sub-steps (1-based) of a ball that still test contacts: all before the counters retire it (ctlp.py:2840-2848)
+__device__ __forceinline__ int ball_k_end(const double* ob) {
+    const int idx0 = (int)ob[SM_OB_INDEX];
+    int k1 = (int)ob[SM_OB_BALL_NMAX] - idx0 + 1, k2 = (int)ob[SM_OB_BALL_NHIT] - idx0;
+    int k_end = k1 < k2 ? k1 : k2;
+    return k_end < 1 ? 1 : k_end;
+}
+
+// pose of B in the frame of A
+__device__ __forceinline__ void rel_pose(const Xf& TA, const Xf& TB, float* R, float* t) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            R[3 * i + k] = fmaf(TA.r[i], TB.r[k], fmaf(TA.r[3 + i], TB.r[3 + k], TA.r[6 + i] * TB.r[6 + k]));
+        const float dx = TB.t[0] - TA.t[0], dy = TB.t[1] - TA.t[1], dz = TB.t[2] - TA.t[2];
+        t[i] = fmaf(TA.r[i], dx, fmaf(TA.r[3 + i], dy, TA.r[6 + i] * dz));
+    }
+}
+
+__device__ __forceinline__ void write_item(GjkItem* dst, int env, int ia, int ib, int cls, int sub, float thr,
+                                           const Xf& TA, const Xf& TB) {
+    float R[9], t[3];
+    rel_pose(TA, TB, R, t);
+    float4* o = reinterpret_cast<float4*>(dst);
+    o[0] = make_float4(__int_as_float(env), __uint_as_float((unsigned)ia | ((unsigned)ib << 16)),
+                       __uint_as_float((unsigned)cls | ((unsigned)sub << 8)), thr);
+    o[1] = make_float4(R[0], R[1], R[2], R[3]);
+    o[2] = make_float4(R[4], R[5], R[6], R[7]);
+    o[3] = make_float4(R[8], t[0], t[1], t[2]);
+}
+
+__device__ __forceinline__ int warp_exclusive_sum(int x, int lane, int& total) {
+    int s = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(FULL, s, o);
+        if (lane >= o) s += y;
+    }
+    total = __shfl_sync(FULL, s, 31);
+    return s - x;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// contacts of one sub-step (one lane): serial FK chain of the tracked pose; every contact shape against the obstacle
+// bounding spheres and then the spheres of the obstacle's convex parts, all inflated by the contact thresholds.
+// Poses are those Bullet's collision detection of that sub-step sees: tracked robot pose before integration, obstacle
+// pose of the previous update.  write == false counts the candidates, write == true emits them.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int contact_scan(const SceneSmem& sm, const float* __restrict__ qrow, const Xf& T0, const Xf& T1,
+                                         int use_mask, bool write, GjkItem* out, int env, int sub) {
+    int count = 0;
+    const V3 oc0 = xf_apply(T0, c_sc.obst_center[0][0], c_sc.obst_center[0][1], c_sc.obst_center[0][2]);
+    const V3 oc1 = xf_apply(T1, c_sc.obst_center[1][0], c_sc.obst_center[1][1], c_sc.obst_center[1][2]);
+    Xf F;
+    xf_identity(F);
+#pragma unroll 1
+    for (int f = 0; f <= c_sc.n_joints; ++f) {
+        if (f > 0) {  // serial chain: frame f hangs off frame f-1 (checked on the host)
+            const int j = f - 1;
+            float s, c;
+            sincosf(qrow[j], &s, &c);
+            Xf L, C;
+            float Rj[9];
+            axis_angle(sm.jaxis[j][0], sm.jaxis[j][1], sm.jaxis[j][2], c, s, Rj);
+            const float* A = sm.jR[j];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    L.r[3 * i + k] = fmaf(A[3 * i], Rj[k], fmaf(A[3 * i + 1], Rj[3 + k], A[3 * i + 2] * Rj[6 + k]));
+            L.t[0] = sm.jt[j][0]; L.t[1] = sm.jt[j][1]; L.t[2] = sm.jt[j][2];
+            xf_compose(F, L, C);
+            F = C;
+        }
+#pragma unroll 1
+        for (int slot = c_sc.contact_frame_start[f]; slot < c_sc.contact_frame_start[f + 1]; ++slot) {
+            const int ia = sm.mov_contact[slot];
+            const DevShape& sh = sm.shapes[ia];
+            const V3 c = xf_apply(F, sh.cx, sh.cy, sh.cz);
+            const float rr = sh.radius + sh.margin;
+#pragma unroll 1
+            for (int o = 0; o < 2; ++o) {
+                if (!((use_mask >> o) & 1)) continue;
+                const float th = sm.contact_thresh[o][slot];
+                const V3 dd = c - (o == 0 ? oc0 : oc1);
+                const float lim = rr + c_sc.obst_radius[o] + th;
+                if (dot(dd, dd) > lim * lim) continue;
+                const Xf& TB = o == 0 ? T0 : T1;
+                const int off = c_sc.obst_shape_off[o], cnt = c_sc.obst_shape_cnt[o];
+#pragma unroll 1
+                for (int s = 0; s < cnt; ++s) {
+                    const DevShape& ps = sm.shapes[off + s];
+                    const V3 e = c - xf_apply(TB, ps.cx, ps.cy, ps.cz);
+                    const float l2 = rr + ps.radius + ps.margin + th;
+                    if (dot(e, e) <= l2 * l2) {
+                        if (write) write_item(out + count, env, ia, off + s, GJK_CONTACT, sub, th, F, TB);
+                        ++count;
+                    }
+                }
+            }
+        }
+    }
+    return count;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) contact_plan_kernel(PlanArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemLayout L = block_prologue(smem_raw, false);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const SceneSmem& sm = L.bs->scene;
+    WarpScratch& W = L.scratch[warp];
+    const int S = c_sc.substeps, stride = c_sc.contact_stride;
+    const int kind = c_sc.n_obstacles > 0 ? c_sc.obst_kind[0] : SM_OBST_NONE;
+    const double dt = xdiv(c_sc.ts, (double)S);
+    unsigned n_flag = 0;
+#pragma unroll 1
+    for (int env = blockIdx.x * SM_WARPS_PER_BLOCK + warp; env < A.n; env += gridDim.x * SM_WARPS_PER_BLOCK) {
+        const float* scr = A.scratch + (size_t)env * SM_SCRATCH_FLOATS;
+        if (lane < SM_OBST_STRIDE) W.ob[lane] = A.obst[(size_t)env * SM_OBST_STRIDE + lane];
+        __syncwarp();
+        const int idx0 = (int)W.ob[SM_OB_INDEX];
+        bool test = false;
+        int use_mask = 0;
+        Xf T0, T1;
+        xf_identity(T0);
+        xf_identity(T1);
+        if (stride > 0 && W.ob[SM_OB_LATCH] == 0.0 && lane < S && ((lane + 1) % stride == 0)) {
+            if (kind == SM_OBST_PLANET && c_sc.terminate_moving) {
+                planet_pose(0, (idx0 + lane) % c_sc.planet_steps, T0);
+                use_mask = 1;
+                if (c_sc.n_obstacles > 1) { planet_pose(1, (idx0 + lane) % c_sc.planet_steps, T1); use_mask = 3; }
+                test = true;
+            } else if (kind == SM_OBST_BALL && W.ob[SM_OB_BALL_ACTIVE] != 0.0) {
+                const int sub = lane + 1, k_end = ball_k_end(W.ob);
+                if (sub <= k_end - 1) {
+                    // the test of sub-step `sub` happens after the ball moved to counter idx0+sub: the active area
+                    // uses the new position (ctlp.py:2851-2854), the manifold the previous one
+                    const double ball_t = W.ob[SM_OB_BALL_T];
+                    const double tn = ball_t + (double)sub * dt;
+                    const double px = W.ob[SM_OB_BALL_P0] + W.ob[SM_OB_BALL_V0] * tn;
+                    const double py = W.ob[SM_OB_BALL_P0 + 1] + W.ob[SM_OB_BALL_V0 + 1] * tn;
+                    if (sqrt(px * px + py * py) < c_sc.ball_active_xy) {
+                        ball_pose(W.ob, ball_t + (double)lane * dt, T0);
+                        use_mask = 1;
+                        test = true;
+                    }
+                }
+            }
+        }
+        // pass 0 counts the candidates of every sub-step, pass 1 (only if there are any) writes them
+        int cnt = 0, total = 0, off = 0, base = 0;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1) {
+                off = warp_exclusive_sum(cnt, lane, total);
+                if (total == 0) break;
+                if (lane == 0) base = atomicAdd(A.item_count, total);
+                base = __shfl_sync(FULL, base, 0);
+                if (COUNT) n_flag += (unsigned)total;
+                if (base + total > A.capacity) {
+                    if (lane == 0) atomicAdd(A.overflow, total);
+                    break;
+                }
+            }
+            if (test && (pass == 0 || cnt > 0)) {
+                const int c = contact_scan(sm, scr + lane * SM_MAX_JOINTS, T0, T1, use_mask, pass == 1,
+                                           A.items + base + off, env, lane + 1);
+                if (pass == 0) cnt = c;
+            }
+        }
+        __syncwarp();
+    }
+    if (COUNT && A.counters && lane == 0 && n_flag) atomicAdd(&A.counters[6], (unsigned long long)n_flag);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// decode pair p of the env's pair list: static pairs, self pairs, then (observed link shape x obstacle part) per
+// moving obstacle.  Returns the class, -1 past the end.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int decode_pair(const SceneSmem& sm, int p, bool moving, int& ia, int& ib) {
+    if (p < c_sc.n_static_pairs) { ia = sm.static_pairs[p][0]; ib = sm.static_pairs[p][1]; return GJK_STATIC; }
+    p -= c_sc.n_static_pairs;
+    if (p < c_sc.n_self_pairs) { ia = sm.self_pairs[p][0]; ib = sm.self_pairs[p][1]; return GJK_SELF; }
+    p -= c_sc.n_self_pairs;
+    if (!moving) return -1;
+#pragma unroll 1
+    for (int o = 0; o < c_sc.n_obstacles; ++o) {
+        const int cnt = c_sc.obst_shape_cnt[o], tot = c_sc.n_mov_reward * cnt;
+        if (p < tot) { ia = sm.mov_reward[p / cnt]; ib = c_sc.obst_shape_off[o] + p % cnt; return GJK_MOVING; }
+        p -= tot;
+    }
+    return -1;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) distance_plan_kernel(PlanArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemLayout L = block_prologue(smem_raw, false);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const SceneSmem& sm = L.bs->scene;
+    WarpScratch& W = L.scratch[warp];
+    const int S = c_sc.substeps;
+    const int kind = c_sc.n_obstacles > 0 ? c_sc.obst_kind[0] : SM_OBST_NONE;
+    const double dt = xdiv(c_sc.ts, (double)S);
+    const float cap = (float)c_sc.static_cap, query = (float)c_sc.moving_query;
+    const int n_fixed = c_sc.n_static_pairs + c_sc.n_self_pairs;
+    int n_pairs = n_fixed;
+    for (int o = 0; o < c_sc.n_obstacles; ++o) n_pairs += c_sc.n_mov_reward * c_sc.obst_shape_cnt[o];
+    unsigned n_emit = 0;
+#pragma unroll 1
+    for (int env = blockIdx.x * SM_WARPS_PER_BLOCK + warp; env < A.n; env += gridDim.x * SM_WARPS_PER_BLOCK) {
+        if (lane < SM_OBST_STRIDE) W.ob[lane] = A.obst[(size_t)env * SM_OBST_STRIDE + lane];
+        const double q1 = A.kin[(size_t)env * SM_KIN_STRIDE + (lane & 7)];  // joint angle of the (new) knot
+        __syncwarp();
+        // ---------------- obstacle poses the reward distance is taken at: the end of the step if no contact latches
+        // in it (a latched contact overrides the distance with 0 in finish_kernel, ctlp.py:3224-3234)
+        bool moving = c_sc.n_mov_reward > 0 && W.ob[SM_OB_LATCH] == 0.0;
+        if (kind == SM_OBST_PLANET) {
+            const int idx = A.advance ? ((int)W.ob[SM_OB_INDEX] + S) % c_sc.planet_steps : (int)W.ob[SM_OB_INDEX];
+            if (lane < c_sc.n_obstacles) planet_pose(lane, idx, W.obx[lane]);
+        } else if (kind == SM_OBST_BALL) {
+            double ball_t = W.ob[SM_OB_BALL_T];
+            bool active = W.ob[SM_OB_BALL_ACTIVE] != 0.0;
+            if (A.advance && active) {
+                const int k_end = ball_k_end(W.ob);
+                int adv = S;
+                if (k_end <= S) { adv = k_end; active = false; }  // retired inside the step without hitting the robot
+#pragma unroll 1
+                for (int i = 0; i < adv; ++i) ball_t = xadd(ball_t, dt);  // self._t += update_time_step
+            }
+            if (!active) moving = false;  // not in the list of observed obstacles (ctlp.py:3239-3245)
+            if (lane == 0) ball_pose(W.ob, ball_t, W.obx[0]);
+        } else {
+            moving = false;
+        }
+        frames_from_q64(sm, q1, W.fr, lane);
+        if (lane < SM_RES_STRIDE)
+            A.res[(size_t)env * SM_RES_STRIDE + lane] = lane == 3 ? SM_RES_NO_CONTACT
+                                                                   : fkey(lane == GJK_MOVING ? query + 0.002f : cap);
+        __syncwarp();
+        // ---------------- pass 1: the best upper bound of each class (distance of the hull centroids)
+        const int np = moving ? n_pairs : n_fixed;
+        float ub_s = cap, ub_e = cap, ub_m = query;
+#pragma unroll 1
+        for (int base = 0; base < np; base += 32) {
+            int ia = 0, ib = 0;
+            const int cls = base + lane < np ? decode_pair(sm, base + lane, moving, ia, ib) : -1;
+            if (cls >= 0) {
+                const DevShape& SA = sm.shapes[ia];
+                const DevShape& SB = sm.shapes[ib];
+                const V3 ga = xf_apply(*frame_ptr(SA, W.fr, W.obx), SA.gx, SA.gy, SA.gz);
+                const V3 gb = xf_apply(*frame_ptr(SB, W.fr, W.obx), SB.gx, SB.gy, SB.gz);
+                const V3 e = ga - gb;
+                const float ub = sqrtf(dot(e, e)) * (1.0f + 1e-6f) + 1e-7f - SA.margin - SB.margin;
+                if (cls == GJK_STATIC) ub_s = fminf(ub_s, ub);
+                else if (cls == GJK_SELF) ub_e = fminf(ub_e, ub);
+                else ub_m = fminf(ub_m, ub);
+            }
+        }
+        ub_s = funkey(__reduce_min_sync(FULL, fkey(ub_s)));
+        ub_e = funkey(__reduce_min_sync(FULL, fkey(ub_e)));
+        ub_m = funkey(__reduce_min_sync(FULL, fkey(ub_m)));
+        // ---------------- pass 2: one item per pair whose sphere lower bound is below its class' upper bound
+#pragma unroll 1
+        for (int base = 0; base < np; base += 32) {
+            int ia = 0, ib = 0;
+            const int cls = base + lane < np ? decode_pair(sm, base + lane, moving, ia, ib) : -1;
+            bool emit = false;
+            float thr = 0.0f;
+            if (cls >= 0) {
+                thr = cls == GJK_STATIC ? ub_s : cls == GJK_SELF ? ub_e : ub_m;
+                emit = pair_lower_bound(sm, ia, ib, W.fr, W.obx) <= thr;
+            }
+            const unsigned em = __ballot_sync(FULL, emit);
+            if (em) {
+                const int total = __popc(em);
+                int b0 = 0;
+                if (lane == 0) b0 = atomicAdd(A.item_count, total);
+                b0 = __shfl_sync(FULL, b0, 0);
+                if (b0 + total <= A.capacity) {
+                    if (emit) {
+                        const DevShape& SA = sm.shapes[ia];
+                        const DevShape& SB = sm.shapes[ib];
+                        write_item(A.items + b0 + __popc(em & ((1u << lane) - 1u)), env, ia, ib, cls, 0, thr,
+                                   *frame_ptr(SA, W.fr, W.obx), *frame_ptr(SB, W.fr, W.obx));
+                    }
+                } else if (lane == 0) {
+                    atomicAdd(A.overflow, total);
+                }
+                if (COUNT) n_emit += (unsigned)total;
+            }
+        }
+        __syncwarp();
+    }
+    if (COUNT && A.counters && lane == 0 && n_emit) atomicAdd(&A.counters[3], (unsigned long long)n_emit);
+}
+
+// the hook smenv_distances: results of the planned queries as the three distances (ctlp.py:3217-3374)
+__global__ void distances_out_kernel(const unsigned* res, const double* obst, float* d_static, float* d_self,
+                                     float* d_moving, int n) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= n) return;
+    const unsigned* r = res + (size_t)env * SM_RES_STRIDE;
+    d_static[env] = funkey(r[GJK_STATIC]);
+    d_self[env] = funkey(r[GJK_SELF]);
+    float dm = funkey(r[GJK_MOVING]);
+    if (obst[(size_t)env * SM_OBST_STRIDE + SM_OB_LATCH] != 0.0 || dm <= 0.0f) dm = 0.0f;  // ctlp.py:3224-3234, :3277
+    d_moving[env] = dm;
+}
