@@ -3,6 +3,8 @@
 #include <cstring>
 #include <string>
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "smenv_pools.cuh"
@@ -26,8 +28,25 @@ static int fail(int code, const std::string& msg) {
 // diam * (distance to the nearest sample) of the maximum -- then it is listed for every direction of the cell it
 // could win.  Float rounding of lut_cell on the device at a cell border is covered by the same slack.
 // ------------------------------------------------------------------------------------------------------------------
+static void build_lut_uncached(const float4* v, int n, std::vector<uint32_t>& out);
+
+// tables are cached per process (keyed by the vertex bytes): every env of a scene shares the same hulls
 static void build_lut(const float4* v, int n, std::vector<uint32_t>& out) {
-    const int R = SM_LUT_RES, SUB = 33, cells = 6 * R * R;
+    static std::mutex mu;
+    static std::map<std::string, std::vector<uint32_t>> cache;
+    const std::string key(reinterpret_cast<const char*>(v), (size_t)n * sizeof(float4));
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        std::vector<uint32_t> t;
+        build_lut_uncached(v, n, t);
+        it = cache.emplace(key, std::move(t)).first;
+    }
+    out.insert(out.end(), it->second.begin(), it->second.end());
+}
+
+static void build_lut_uncached(const float4* v, int n, std::vector<uint32_t>& out) {
+    const int R = SM_LUT_RES, SUB = 17, cells = 6 * R * R;
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     for (int i = 0; i < n; ++i) {
         const float p[3] = {v[i].x, v[i].y, v[i].z};

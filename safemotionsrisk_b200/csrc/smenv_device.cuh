@@ -35,7 +35,7 @@ struct DevShape {
 //   cells[6 R R]  : (word offset of the list relative to `lut`) << 8 | number of candidates
 //   lists         : candidate vertex indices (local to the shape), one byte each, four per word, padded to a word
 //                   boundary by repeating the last candidate
-#define SM_LUT_RES 4
+#define SM_LUT_RES 8
 #define SM_LUT_MIN_VERTS 33 /* smaller hulls are scanned directly */
 
 __host__ __device__ __forceinline__ int lut_cell(float dx, float dy, float dz) {

@@ -11,8 +11,13 @@
 // Exact pruning survives the parallelism: items of the same (env, distance class) sit next to each other in the
 // list; the lanes that hold them form a group (match.any) and exchange, every iteration, the best upper bound any
 // of them has reached (redux.min).  A lane whose separating-plane lower bound passes that value stops -- its pair
-// cannot hold the minimum.  Every lane reports its last upper bound, so the group minimum is the exact minimum over
-// the pairs however the items are split over warps (atomicMin on the env's result slot merges the groups).
+// cannot hold the minimum.  A finished pair reports its last upper bound with atomicMin on the env's result slot
+// (the exact distance if it converged), and a newly loaded pair starts from what the slot already holds, so the
+// slot ends up with the exact minimum over the pairs however the items are split over lanes, warps and time.
+//
+// Lanes finish at very different times (most pairs are pruned after one or two iterations, the closest pair of an
+// env runs to convergence), so a warp refills its idle lanes from its chunk of the list while the others keep
+// iterating: the first version, which ran 32 items to completion per warp, averaged 8.8 active lanes.
 #pragma once
 #include "smenv_geom.cuh"
 
@@ -98,125 +103,150 @@ __device__ __forceinline__ int support_thread(const float4* __restrict__ v, int 
     return bi;
 }
 
+#define GJK_REFILL_MIN 8 /* idle lanes of a warp before it fetches new items */
+
 template <bool COUNT>
 __global__ void __launch_bounds__(256) gjk_kernel(GjkArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int n_items = *A.n_items;
     if (n_items > A.capacity) n_items = A.capacity;
-    if ((int)(blockIdx.x * blockDim.x) >= n_items) return;  // nothing for this block: skip the staging
-    GjkSmem G = gjk_carve(smem_raw);
+    // static partition of the list: every warp of the grid owns one contiguous chunk (no global cursor to contend on;
+    // the items of an env stay together, so that lanes of a warp hold pairs that can prune each other)
     const int tid = threadIdx.x, lane = tid & 31;
+    const int n_warps = gridDim.x * (blockDim.x >> 5);
+    const int chunk = (n_items + n_warps - 1) / n_warps;
+    if ((long long)blockIdx.x * (blockDim.x >> 5) * chunk >= n_items) return;  // nothing for this block: no staging
+    GjkSmem G = gjk_carve(smem_raw);
     for (int i = tid; i < c_sc.n_verts; i += blockDim.x) G.verts[i] = __ldg(c_sc.verts + i);
     for (int i = tid; i < c_sc.n_lut_words; i += blockDim.x) G.lut[i] = __ldg(c_sc.lut + i);
     for (int i = tid; i < (int)(sizeof(DevShape) / 4) * c_sc.n_shapes; i += blockDim.x)
         reinterpret_cast<int*>(G.shapes)[i] = reinterpret_cast<const int*>(c_sc.shapes)[i];
     __syncthreads();
+    int cursor = (blockIdx.x * (blockDim.x >> 5) + (tid >> 5)) * chunk;
+    const int end = cursor + chunk < n_items ? cursor + chunk : n_items;
     unsigned c_iters = 0, c_dots = 0, c_calls = 0;
+
+    // ---------------- per-lane state of the pair in flight
+    bool busy = false, have_point = false;
+    int env = 0, cls = GJK_CONTACT, it = 0, nA = 0, nB = 0, lutA = -1, lutB = -1;
+    unsigned meta = 0;
+    float thr = 0.f, m = 0.f, lim_fixed = 0.f, lim = 0.f, touch = -1.f, vv = 0.f;
+    float r0 = 1.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, r4 = 1.f, r5 = 0.f, r6 = 0.f, r7 = 0.f, r8 = 1.f, tx = 0.f, ty = 0.f, tz = 0.f;
+    const float4* vA = G.verts;
+    const float4* vB = G.verts;
+    V3 v = mk(1.f, 0.f, 0.f);
+    Simplex S;
+    S.n = 0;
+    S.i0 = S.i1 = S.i2 = S.i3 = -1;
+    S.p0 = S.p1 = S.p2 = S.p3 = mk(0.f, 0.f, 0.f);
 #pragma unroll 1
-    for (int wbase = (blockIdx.x * blockDim.x + tid) & ~31; wbase < n_items; wbase += gridDim.x * blockDim.x) {
-        const int idx = wbase + lane;
-        const bool active = idx < n_items;
-        // ---------------- load the item (four 16-byte loads)
-        const float4* ip = reinterpret_cast<const float4*>(A.items + (active ? idx : wbase));
-        const float4 h0 = __ldg(ip), h1 = __ldg(ip + 1), h2 = __ldg(ip + 2), h3 = __ldg(ip + 3);
-        const int env = __float_as_int(h0.x);
-        const unsigned shp = __float_as_uint(h0.y), meta = __float_as_uint(h0.z);
-        const float thr = h0.w;
-        const int cls = (int)(meta & 255u);
-        const float r0 = h1.x, r1 = h1.y, r2 = h1.z, r3 = h1.w, r4 = h2.x, r5 = h2.y, r6 = h2.z, r7 = h2.w, r8 = h3.x;
-        const float tx = h3.y, ty = h3.z, tz = h3.w;
-        const DevShape& SA = G.shapes[shp & 0xffffu];
-        const DevShape& SB = G.shapes[shp >> 16];
-        const float4* vA = G.verts + SA.off;
-        const float4* vB = G.verts + SB.off;
-        const int nA = SA.cnt, nB = SB.cnt, lutA = SA.lut, lutB = SB.lut;
-        const float m = SA.margin + SB.margin;
-        // lanes with the same (env, distance class) prune each other; contact items and idle lanes stand alone
-        const unsigned gkey = (active && cls != GJK_CONTACT) ? (((unsigned)env << 2) | (unsigned)cls)
-                                                             : (0x80000000u | (unsigned)lane);
-        const unsigned peers = __match_any_sync(FULL, gkey);
-        const float lim_fixed = (cls == GJK_CONTACT ? thr + 1e-3f : thr) + m;  // on the distance between the cores
-        const float touch = cls == GJK_CONTACT ? thr + m : -1.0f;
-        float lim = lim_fixed;
-        // ---------------- GJK in the frame of A
-        Simplex S;
-        S.n = 0;
-        S.i0 = S.i1 = S.i2 = S.i3 = -1;
-        S.p0 = S.p1 = S.p2 = S.p3 = mk(0.f, 0.f, 0.f);
-        V3 v;
-        {   // first direction: between the bounding-sphere centres
-            const float bx = fmaf(r0, SB.cx, fmaf(r1, SB.cy, fmaf(r2, SB.cz, tx)));
-            const float by = fmaf(r3, SB.cx, fmaf(r4, SB.cy, fmaf(r5, SB.cz, ty)));
-            const float bz = fmaf(r6, SB.cx, fmaf(r7, SB.cy, fmaf(r8, SB.cz, tz)));
-            v = mk(SA.cx - bx, SA.cy - by, SA.cz - bz);
+    while (true) {
+        // ---------------- refill: idle lanes take the next items of the warp's chunk
+        const unsigned idle = __ballot_sync(FULL, !busy);
+        if (cursor < end && (idle == FULL || __popc(idle) >= GJK_REFILL_MIN)) {
+            const int my = cursor + __popc(idle & ((1u << lane) - 1u));
+            cursor += __popc(idle);
+            if (!busy && my < end) {
+                const float4* ip = reinterpret_cast<const float4*>(A.items + my);
+                const float4 h0 = __ldg(ip), h1 = __ldg(ip + 1), h2 = __ldg(ip + 2), h3 = __ldg(ip + 3);
+                env = __float_as_int(h0.x);
+                const unsigned shp = __float_as_uint(h0.y);
+                meta = __float_as_uint(h0.z);
+                thr = h0.w;
+                cls = (int)(meta & 255u);
+                r0 = h1.x; r1 = h1.y; r2 = h1.z; r3 = h1.w; r4 = h2.x; r5 = h2.y; r6 = h2.z; r7 = h2.w; r8 = h3.x;
+                tx = h3.y; ty = h3.z; tz = h3.w;
+                const DevShape& SA = G.shapes[shp & 0xffffu];
+                const DevShape& SB = G.shapes[shp >> 16];
+                vA = G.verts + SA.off; vB = G.verts + SB.off;
+                nA = SA.cnt; nB = SB.cnt; lutA = SA.lut; lutB = SB.lut;
+                m = SA.margin + SB.margin;
+                lim_fixed = (cls == GJK_CONTACT ? thr + 1e-3f : thr) + m;  // on the distance between the cores
+                touch = cls == GJK_CONTACT ? thr + m : -1.0f;
+                lim = lim_fixed;
+                if (cls != GJK_CONTACT) {  // what earlier pairs of the env already reached
+                    const unsigned prev = __ldcg(A.res + (size_t)env * SM_RES_STRIDE + cls);
+                    lim = fminf(lim_fixed, funkey(prev) + m);
+                }
+                // first direction: between the bounding-sphere centres (in the frame of A)
+                v = mk(SA.cx - fmaf(r0, SB.cx, fmaf(r1, SB.cy, fmaf(r2, SB.cz, tx))),
+                       SA.cy - fmaf(r3, SB.cx, fmaf(r4, SB.cy, fmaf(r5, SB.cz, ty))),
+                       SA.cz - fmaf(r6, SB.cx, fmaf(r7, SB.cy, fmaf(r8, SB.cz, tz))));
+                vv = dot(v, v);
+                if (vv < 1e-12f) { v = mk(1.f, 0.f, 0.f); vv = 1.f; }
+                S.n = 0;
+                S.i0 = S.i1 = S.i2 = S.i3 = -1;
+                have_point = false;
+                it = 0;
+                busy = true;
+                if (COUNT) c_calls++;
+            }
         }
-        float vv = dot(v, v);
-        if (vv < 1e-12f) { v = mk(1.f, 0.f, 0.f); vv = 1.f; }
-        bool have_point = false;
-        bool done = !active;
-        if (COUNT && active) c_calls++;
-#pragma unroll 1
-        for (int it = 0; it < 32; ++it) {
-            if (!done) {
-                const int sa = support_thread(vA, nA, G.lut, lutA, mk(-v.x, -v.y, -v.z), c_dots);
-                const V3 dB = mk(fmaf(r0, v.x, fmaf(r3, v.y, r6 * v.z)), fmaf(r1, v.x, fmaf(r4, v.y, r7 * v.z)),
-                                 fmaf(r2, v.x, fmaf(r5, v.y, r8 * v.z)));  // R^T v
-                const int sb = support_thread(vB, nB, G.lut, lutB, dB, c_dots);
-                if (COUNT) c_iters++;
-                const float4 pa = vA[sa], pb = vB[sb];
-                const V3 w = mk(pa.x - fmaf(r0, pb.x, fmaf(r1, pb.y, fmaf(r2, pb.z, tx))),
-                                pa.y - fmaf(r3, pb.x, fmaf(r4, pb.y, fmaf(r5, pb.z, ty))),
-                                pa.z - fmaf(r6, pb.x, fmaf(r7, pb.y, fmaf(r8, pb.z, tz))));
-                const int id = (sa << 16) | sb;
-                if (!have_point) {  // the first iteration only seeds the simplex with a real point of A - B
-                    S.p0 = w; S.i0 = id; S.n = 1;
-                    v = w; vv = dot(v, v);
-                    have_point = true;
-                    if (vv <= touch * touch && touch >= 0.0f) done = true;
-                    if (vv <= 1e-20f) { vv = 0.0f; done = true; }
-                } else {
-                    const float vw = dot(v, w);
-                    const float nv = sqrtf(vv);
-                    if (vw > 0.0f && vw * vw >= lim * lim * vv) done = true;                      // pruned
-                    else if (vv - vw <= fmaxf(1e-6f * vv, 3e-7f * nv)) done = true;               // converged
-                    else if (id == S.i0 || id == S.i1 || id == S.i2 || id == S.i3) done = true;   // support repeats
+        if (!__any_sync(FULL, busy)) break;
+        // lanes with the same (env, distance class) prune each other; contact items and idle lanes share one dummy
+        // group (redux over lane-dependent masks is serialised per distinct mask)
+        const bool dist = busy && cls != GJK_CONTACT;
+        const unsigned peers = __match_any_sync(FULL, dist ? (((unsigned)env << 2) | (unsigned)cls) : 0xffffffffu);
+        bool done = false;
+        if (busy) {
+            // ---------------- one GJK iteration in the frame of A
+            const int sa = support_thread(vA, nA, G.lut, lutA, mk(-v.x, -v.y, -v.z), c_dots);
+            const V3 dB = mk(fmaf(r0, v.x, fmaf(r3, v.y, r6 * v.z)), fmaf(r1, v.x, fmaf(r4, v.y, r7 * v.z)),
+                             fmaf(r2, v.x, fmaf(r5, v.y, r8 * v.z)));  // R^T v
+            const int sb = support_thread(vB, nB, G.lut, lutB, dB, c_dots);
+            if (COUNT) c_iters++;
+            const float4 pa = vA[sa], pb = vB[sb];
+            const V3 w = mk(pa.x - fmaf(r0, pb.x, fmaf(r1, pb.y, fmaf(r2, pb.z, tx))),
+                            pa.y - fmaf(r3, pb.x, fmaf(r4, pb.y, fmaf(r5, pb.z, ty))),
+                            pa.z - fmaf(r6, pb.x, fmaf(r7, pb.y, fmaf(r8, pb.z, tz))));
+            const int id = (sa << 16) | sb;
+            if (!have_point) {  // the first iteration only seeds the simplex with a real point of A - B
+                S.p0 = w; S.i0 = id; S.n = 1;
+                v = w; vv = dot(v, v);
+                have_point = true;
+                if (touch >= 0.0f && vv <= touch * touch) done = true;
+                if (vv <= 1e-20f) { vv = 0.0f; done = true; }
+            } else {
+                const float vw = dot(v, w);
+                const float nv = sqrtf(vv);
+                if (vw > 0.0f && vw * vw >= lim * lim * vv) done = true;                      // pruned
+                else if (vv - vw <= fmaxf(1e-6f * vv, 3e-7f * nv)) done = true;               // converged
+                else if (id == S.i0 || id == S.i1 || id == S.i2 || id == S.i3) done = true;   // support repeats
+                else {
+                    if (S.n == 1) { S.p1 = w; S.i1 = id; }
+                    else if (S.n == 2) { S.p2 = w; S.i2 = id; }
+                    else { S.p3 = w; S.i3 = id; }
+                    S.n++;
+                    V3 nvv;
+                    if (simplex_solve(S, nvv)) { vv = 0.0f; done = true; }
                     else {
-                        if (S.n == 1) { S.p1 = w; S.i1 = id; }
-                        else if (S.n == 2) { S.p2 = w; S.i2 = id; }
-                        else { S.p3 = w; S.i3 = id; }
-                        S.n++;
-                        V3 nvv;
-                        if (simplex_solve(S, nvv)) { vv = 0.0f; done = true; }
+                        if (S.n < 4) S.i3 = -1;
+                        if (S.n < 3) S.i2 = -1;
+                        if (S.n < 2) S.i1 = -1;
+                        const float nd = dot(nvv, nvv);
+                        if (!(nd < vv)) done = true;  // no progress (numerical floor) or a NaN
                         else {
-                            if (S.n < 4) S.i3 = -1;
-                            if (S.n < 3) S.i2 = -1;
-                            if (S.n < 2) S.i1 = -1;
-                            const float nd = dot(nvv, nvv);
-                            if (!(nd < vv)) done = true;  // no progress (numerical floor) or a NaN
-                            else {
-                                v = nvv; vv = nd;
-                                if (vv <= 1e-20f) { vv = 0.0f; done = true; }
-                                if (touch >= 0.0f && vv <= touch * touch) done = true;
-                            }
+                            v = nvv; vv = nd;
+                            if (vv <= 1e-20f) { vv = 0.0f; done = true; }
+                            if (touch >= 0.0f && vv <= touch * touch) done = true;
                         }
                     }
                 }
             }
-            // the group's best upper bound tightens every member's pruning limit
-            const unsigned ub = have_point ? fkey(sqrtf(vv) - m) : 0xffffffffu;
-            const unsigned gb = __reduce_min_sync(peers, ub);
-            if (cls != GJK_CONTACT && gb != 0xffffffffu) lim = fminf(lim_fixed, funkey(gb) + m);
-            if (__all_sync(FULL, done)) break;
+            if (++it >= 32) done = true;
         }
-        // ---------------- results
+        // ---------------- the group's best upper bound tightens every member's pruning limit
         const float d = sqrtf(vv) - m;
-        const bool counts = active && have_point && d <= thr;
-        if (cls == GJK_CONTACT) {
-            if (counts) atomicMin(&A.res[(size_t)env * SM_RES_STRIDE + 3], meta >> 8);
+        const unsigned gb = __reduce_min_sync(peers, (dist && have_point) ? fkey(d) : 0xffffffffu);
+        if (dist && gb != 0xffffffffu) lim = fminf(lim, funkey(gb) + m);
+        // ---------------- a finished pair reports its last upper bound (the exact distance if it converged)
+        if (done) {
+            if (have_point && d <= thr) {
+                if (cls == GJK_CONTACT) atomicMin(&A.res[(size_t)env * SM_RES_STRIDE + 3], meta >> 8);
+                else if (d + m <= lim) atomicMin(&A.res[(size_t)env * SM_RES_STRIDE + cls], fkey(d));  // group's best
+            }
+            busy = false;
         }
-        const unsigned gmin = __reduce_min_sync(peers, (counts && cls != GJK_CONTACT) ? fkey(d) : 0xffffffffu);
-        if (active && cls != GJK_CONTACT && gmin != 0xffffffffu && lane == __ffs(peers) - 1)
-            atomicMin(&A.res[(size_t)env * SM_RES_STRIDE + cls], gmin);
     }
     if (COUNT && A.counters) {
 #pragma unroll
