@@ -221,7 +221,8 @@ def main():
     stats_ms = 1e3 * (time.perf_counter() - t0)
     stats = stats.cpu().numpy()
 
-    # ---------------- roofline of the dominant kernel (step_kernel): algorithmic flops from device counters
+    # ---------------- roofline of the dominant kernel: algorithmic flops from device counters, kernel durations from
+    # CUDA events around each launch (measurement mode of the library, separate pass after the timed region)
     env.enable_counters(True)
     env.counters(reset=True)
     for _ in range(3):
@@ -230,14 +231,26 @@ def main():
     env.enable_counters(False)
     steps_counted = max(1, c["env_steps"])
     n_dot, n_iter = c["support_dots"] / steps_counted, c["gjk_iters"] / steps_counted
+    env.kernel_timing(True)
+    env.kernel_times(reset=True)
+    for i in range(min(args.steps, 50)):
+        flush.fill_(i & 0xff)
+        env.step_random()
+    ktimes, _ = env.kernel_times()
+    env.kernel_timing(False)
+    ksum = sum(ktimes.values())
+    # algorithmic flops per env-step attributed to each kernel
+    kflops = {"joint_kernel": 7 * 300 + 7 * 3 * 20, "joint_heavy_kernel": 0.0, "contact_plan_kernel": 24 * 600.0,
+              "distance_plan_kernel": 600.0, "gjk_kernel": 5.0 * n_dot + 100.0 * n_iter, "finish_kernel": 200.0}
     f_step = F_FIXED + 5.0 * n_dot + 100.0 * n_iter
-    kernel_ms = statistics.mean(step_ms)
-    per_gpu_steps_s = args.envs / (kernel_ms * 1e-3)
-    achieved_tflops = per_gpu_steps_s * f_step / 1e12
+    dom = max(ktimes, key=ktimes.get)
+    kernel_ms = ktimes[dom]
+    per_gpu_steps_s = args.envs / (statistics.mean(step_ms) * 1e-3)
+    achieved_tflops = args.envs * kflops[dom] / (kernel_ms * 1e-3) / 1e12
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     peak_tflops = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12  # FP32 pipe at the SM clock seen under load
     sc = env.scene.struct
-    bytes_step = 2 * (8 * 32 + 8 * 16 + 16 + 8) + 4 * sc.obs_size + 4 + 1 + 4 + 4 * 16
+    bytes_step = 2 * (8 * 32 + 8 * 16 + 16 + 8) + 4 * sc.n_joints + 4 * sc.obs_size + 4 + 1 + 4 + 4 * 16
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -245,12 +258,18 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    uncull = {"space": 1.51e6, "space_bm": 1.71e6, "ball": 0.15e6, "ball_bm": 0.35e6}[args.scene]
     roofline = {"bound": "fp32", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
                 "frac": achieved_tflops / peak_tflops, "traffic": None,
                 "peak_source": "148 SMs x 128 FP32 lanes x 2 x median SM clock under load ({} MHz)".format(sm_mhz),
-                "flops_per_env_step": f_step, "support_dots_per_env_step": n_dot, "gjk_iters_per_env_step": n_iter,
-                "gjk_calls_per_env_step": c["gjk_calls"] / steps_counted, "kernel": "distance_kernel<false>",
-                "kernel_ms": kernel_ms,
+                "kernel": dom, "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ksum,
+                "kernel_flops_per_env_step": kflops[dom],
+                "kernels_ms": ktimes, "flops_per_env_step": f_step, "support_dots_per_env_step": n_dot,
+                "gjk_iters_per_env_step": n_iter, "gjk_pairs_per_env_step": c["gjk_calls"] / steps_counted,
+                "whole_step": {"achieved": per_gpu_steps_s * f_step / 1e12,
+                               "frac": per_gpu_steps_s * f_step / 1e12 / peak_tflops,
+                               "unculled_reference_flops_per_env_step": uncull,
+                               "frac_at_unculled_count": per_gpu_steps_s * uncull / 1e12 / peak_tflops},
                 "hbm": {"achieved": per_gpu_steps_s * bytes_step / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": per_gpu_steps_s * bytes_step / 1e9 / hbm_peak, "bytes_per_env_step": bytes_step,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}

@@ -202,13 +202,22 @@ typedef struct SmBuffers {
 } SmBuffers;
 
 typedef struct SmCounters {
-    unsigned long long gjk_calls, gjk_iters, support_dots, culled_pairs, env_steps, contact_tests;
-    unsigned long long flagged_substeps, reserved;
-    /* SM clock cycles summed over warps, per phase of the geometry kernel (counting build only):
-     * 0 load, 1 contact broad phase, 2 contact narrow phase, 3 end-pose FK, 4 static+self distance,
-     * 5 moving distance, 6 reward/outputs, 7 observation/auto-reset */
-    unsigned long long phase_cycles[8];
+    unsigned long long gjk_calls;      /* convex pair queries run by the GJK kernel (= work items) */
+    unsigned long long gjk_iters;      /* GJK iterations summed over the pairs */
+    unsigned long long support_dots;   /* vertex . direction products evaluated in support searches */
+    unsigned long long distance_items; /* pairs the distance planning could not cull (emitted items) */
+    unsigned long long env_steps;
+    unsigned long long contact_tests;  /* reserved */
+    unsigned long long contact_items;  /* (sub-step, pair) contact candidates emitted by the contact planning */
+    unsigned long long reserved;
+    unsigned long long phase_cycles[8]; /* reserved */
 } SmCounters;
+
+/* Kernels of one step, in launch order (smenv_kernel_times). */
+enum SmKernel {
+    SM_K_JOINT = 0, SM_K_JOINT_HEAVY = 1, SM_K_CONTACT_PLAN = 2, SM_K_DISTANCE_PLAN = 3, SM_K_GJK = 4, SM_K_FINISH = 5,
+    SM_K_COUNT = 6
+};
 
 typedef struct SmEnv SmEnv;
 typedef void* SmStream; /* cudaStream_t */
@@ -249,6 +258,11 @@ int smenv_observation(SmEnv* env, const SmBuffers* buf, SmStream stream);
 int smenv_counters(SmEnv* env, SmCounters* out, int reset);
 int smenv_enable_counters(SmEnv* env, int enable);
 int smenv_launch_count(SmEnv* env, unsigned long long* out);
+/* Measurement mode: with enable != 0 every smenv_step brackets each of its kernels with CUDA events on the caller's
+ * stream and synchronises at the end of the step (so it is for measurement passes, not for the timed rollout).
+ * smenv_kernel_times returns the accumulated milliseconds per SmKernel and the number of steps accumulated. */
+int smenv_kernel_timing(SmEnv* env, int enable);
+int smenv_kernel_times(SmEnv* env, double* ms_out /* SM_K_COUNT */, int* steps_out, int reset);
 /* Debug: trace of one GJK call between shapes ia and ib for one env state given on the host (trace: 32 x 8 floats per
  * iteration = simplex size, |v|^2, v.w, support ids, v; result: distance, iterations, then the 9 robot frames). */
 int smenv_debug_gjk(SmEnv* env, const double* kin_host, const double* obst_host, int ia, int ib, float upper,

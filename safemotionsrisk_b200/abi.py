@@ -116,8 +116,8 @@ class SmBuffers(C.Structure):
 
 class SmCounters(C.Structure):
     _fields_ = [("gjk_calls", C.c_ulonglong), ("gjk_iters", C.c_ulonglong), ("support_dots", C.c_ulonglong),
-                ("culled_pairs", C.c_ulonglong), ("env_steps", C.c_ulonglong), ("contact_tests", C.c_ulonglong),
-                ("flagged_substeps", C.c_ulonglong), ("reserved", C.c_ulonglong), ("phase_cycles", C.c_ulonglong * 8)]
+                ("distance_items", C.c_ulonglong), ("env_steps", C.c_ulonglong), ("contact_tests", C.c_ulonglong),
+                ("contact_items", C.c_ulonglong), ("reserved", C.c_ulonglong), ("phase_cycles", C.c_ulonglong * 8)]
 
 
 # every extern "C" symbol include/smenv.h declares
@@ -125,5 +125,6 @@ EXPORTED_SYMBOLS = [
     "smenv_last_error", "smenv_abi_version", "smenv_sizeof_scene", "smenv_sizeof_shape", "smenv_create",
     "smenv_destroy", "smenv_pool_sizes", "smenv_fill_pools", "smenv_pool_ptrs", "smenv_copy_pools", "smenv_set_state", "smenv_reset",
     "smenv_step", "smenv_step_random", "smenv_safe_range", "smenv_distances", "smenv_observation",
-    "smenv_counters", "smenv_enable_counters", "smenv_launch_count", "smenv_debug_gjk",
+    "smenv_counters", "smenv_enable_counters", "smenv_launch_count", "smenv_debug_gjk", "smenv_kernel_timing",
+    "smenv_kernel_times",
 ]

@@ -38,6 +38,8 @@ def load():
     lib.smenv_counters.argtypes = [vp, C.POINTER(abi.SmCounters), i32]
     lib.smenv_enable_counters.argtypes = [vp, i32]
     lib.smenv_launch_count.argtypes = [vp, C.POINTER(C.c_ulonglong)]
+    lib.smenv_kernel_timing.argtypes = [vp, i32]
+    lib.smenv_kernel_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i32), i32]
     if lib.smenv_sizeof_scene() != C.sizeof(abi.SmScene) or lib.smenv_sizeof_shape() != C.sizeof(abi.SmShape):
         raise SmEnvError("SmScene layout mismatch between abi.py ({}) and libsmenv.so ({}); rebuild".format(
             C.sizeof(abi.SmScene), lib.smenv_sizeof_scene()))

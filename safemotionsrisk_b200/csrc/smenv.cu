@@ -122,6 +122,10 @@ struct SmEnv {
     int* d_flag = nullptr;       // its device alias
     size_t smem_bytes_gjk = 0;
     int grid_gjk = 0;
+    bool time_kernels = false;   // measurement mode (smenv_kernel_timing)
+    cudaEvent_t ev[SM_K_COUNT + 1] = {};
+    double kernel_ms[SM_K_COUNT] = {};
+    int timed_steps = 0;
     int* d_heavy = nullptr;      // [0] = count, [1..8n] = (env, joint) instances deferred to joint_heavy_kernel
     bool count = false;
     size_t smem_bytes = 0;        // kernels that stage the hull vertices
@@ -367,6 +371,7 @@ extern "C" int smenv_destroy(SmEnv* env) {
     cudaFree(env->d_verts); cudaFree(env->d_lut); cudaFree(env->d_plocal); cudaFree(env->d_start_pool); cudaFree(env->d_ball_pool);
     cudaFree(env->d_counters); cudaFree(env->d_scratch); cudaFree(env->d_worklist); cudaFree(env->d_heavy); cudaFree(env->d_items); cudaFree(env->d_res);
     if (env->h_flag) cudaFreeHost(env->h_flag);
+    for (int i = 0; i <= SM_K_COUNT; ++i) if (env->ev[i]) cudaEventDestroy(env->ev[i]);
     for (int o = 0; o < SM_MAX_OBSTACLES; ++o) { cudaFree(env->d_ppos[o]); cudaFree(env->d_pquat[o]); }
     delete env;
     return SM_OK;
@@ -534,7 +539,11 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
     JA.scratch = env->d_scratch;
     JA.worklist = env->d_worklist;  // clears the item counter and the overflow count
     JA.heavy = env->d_heavy;
+    const bool tk = env->time_kernels;
+#define SM_MARK(i) do { if (tk) cudaEventRecord(env->ev[i], stream); } while (0)
+    SM_MARK(SM_K_JOINT);
     joint_kernel<<<(env->n * 8 + 255) / 256, 256, 0, stream>>>(JA);
+    SM_MARK(SM_K_JOINT_HEAVY);
     {   // the heavy list is at most 8 n long; blocks beyond its length exit at once
         int hb = (env->n * 8 + 127) / 128;
         if (hb > 8 * env->sms) hb = 8 * env->sms;
@@ -567,16 +576,30 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
     const int grid_p = blocks < env->grid_broad ? blocks : env->grid_broad;
     const int grid_f = (env->n + 7) / 8;
     const bool contacts = env->host_scene.contact_stride > 0 && env->host_scene.n_obstacles > 0;
-    if (env->count) {
-        if (contacts) contact_plan_kernel<true><<<grid_p, T, env->smem_bytes_broad, stream>>>(P);
-        distance_plan_kernel<true><<<grid_p, T, env->smem_bytes_broad, stream>>>(P);
-        gjk_kernel<true><<<env->grid_gjk, 256, env->smem_bytes_gjk, stream>>>(G);
-        finish_kernel<true><<<grid_f, 256, 0, stream>>>(A);
-    } else {
-        if (contacts) contact_plan_kernel<false><<<grid_p, T, env->smem_bytes_broad, stream>>>(P);
-        distance_plan_kernel<false><<<grid_p, T, env->smem_bytes_broad, stream>>>(P);
-        gjk_kernel<false><<<env->grid_gjk, 256, env->smem_bytes_gjk, stream>>>(G);
-        finish_kernel<false><<<grid_f, 256, 0, stream>>>(A);
+    SM_MARK(SM_K_CONTACT_PLAN);
+    if (contacts) {
+        if (env->count) contact_plan_kernel<true><<<grid_p, T, env->smem_bytes_broad, stream>>>(P);
+        else contact_plan_kernel<false><<<grid_p, T, env->smem_bytes_broad, stream>>>(P);
+    }
+    SM_MARK(SM_K_DISTANCE_PLAN);
+    if (env->count) distance_plan_kernel<true><<<grid_p, T, env->smem_bytes_broad, stream>>>(P);
+    else distance_plan_kernel<false><<<grid_p, T, env->smem_bytes_broad, stream>>>(P);
+    SM_MARK(SM_K_GJK);
+    if (env->count) gjk_kernel<true><<<env->grid_gjk, 256, env->smem_bytes_gjk, stream>>>(G);
+    else gjk_kernel<false><<<env->grid_gjk, 256, env->smem_bytes_gjk, stream>>>(G);
+    SM_MARK(SM_K_FINISH);
+    if (env->count) finish_kernel<true><<<grid_f, 256, 0, stream>>>(A);
+    else finish_kernel<false><<<grid_f, 256, 0, stream>>>(A);
+    SM_MARK(SM_K_COUNT);
+#undef SM_MARK
+    if (tk) {
+        CU(cudaStreamSynchronize(stream));
+        for (int i = 0; i < SM_K_COUNT; ++i) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, env->ev[i], env->ev[i + 1]));
+            env->kernel_ms[i] += ms;
+        }
+        env->timed_steps++;
     }
     env->launches += contacts ? 4 : 3;
     CU(cudaGetLastError());
@@ -639,10 +662,28 @@ extern "C" int smenv_counters(SmEnv* env, SmCounters* out, int reset) {
     CU(cudaSetDevice(env->device));
     unsigned long long h[16];
     CU(cudaMemcpy(h, env->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
-    out->gjk_calls = h[0]; out->gjk_iters = h[1]; out->support_dots = h[2]; out->culled_pairs = h[3];
-    out->env_steps = h[4]; out->contact_tests = h[5]; out->flagged_substeps = h[6]; out->reserved = h[7];
+    out->gjk_calls = h[0]; out->gjk_iters = h[1]; out->support_dots = h[2]; out->distance_items = h[3];
+    out->env_steps = h[4]; out->contact_tests = h[5]; out->contact_items = h[6]; out->reserved = h[7];
     for (int i = 0; i < 8; ++i) out->phase_cycles[i] = h[8 + i];
     if (reset) CU(cudaMemset(env->d_counters, 0, sizeof(h)));
+    return SM_OK;
+}
+extern "C" int smenv_kernel_timing(SmEnv* env, int enable) {
+    if (!env) return fail(SM_ERR_ARG, "null env");
+    CU(cudaSetDevice(env->device));
+    if (enable && !env->ev[0])
+        for (int i = 0; i <= SM_K_COUNT; ++i) CU(cudaEventCreate(&env->ev[i]));
+    env->time_kernels = enable != 0;
+    return SM_OK;
+}
+extern "C" int smenv_kernel_times(SmEnv* env, double* ms_out, int* steps_out, int reset) {
+    if (!env || !ms_out || !steps_out) return fail(SM_ERR_ARG, "null argument");
+    for (int i = 0; i < SM_K_COUNT; ++i) ms_out[i] = env->kernel_ms[i];
+    *steps_out = env->timed_steps;
+    if (reset) {
+        for (int i = 0; i < SM_K_COUNT; ++i) env->kernel_ms[i] = 0.0;
+        env->timed_steps = 0;
+    }
     return SM_OK;
 }
 extern "C" int smenv_launch_count(SmEnv* env, unsigned long long* out) {

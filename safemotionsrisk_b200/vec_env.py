@@ -321,6 +321,21 @@ class SafeMotionsVecEnv:
         out["phase_cycles"] = [int(x) for x in c.phase_cycles]
         return out
 
+    KERNELS = ("joint_kernel", "joint_heavy_kernel", "contact_plan_kernel", "distance_plan_kernel", "gjk_kernel",
+               "finish_kernel")
+
+    def kernel_timing(self, enable=True):
+        """Measurement mode: every step brackets each of its kernels with CUDA events and synchronises."""
+        cabi.check(self._lib.smenv_kernel_timing(self._handle, int(enable)), "smenv_kernel_timing")
+
+    def kernel_times(self, reset=False):
+        """{kernel name: mean milliseconds per step} accumulated in measurement mode, and the number of steps."""
+        ms = (C.c_double * len(self.KERNELS))()
+        steps = C.c_int()
+        cabi.check(self._lib.smenv_kernel_times(self._handle, ms, C.byref(steps), int(reset)), "smenv_kernel_times")
+        n = max(1, steps.value)
+        return {k: ms[i] / n for i, k in enumerate(self.KERNELS)}, steps.value
+
     def launch_count(self):
         n = C.c_ulonglong()
         cabi.check(self._lib.smenv_launch_count(self._handle, C.byref(n)), "smenv_launch_count")

@@ -13,6 +13,10 @@ for scene in (sys.argv[1:] or ["ball", "space"]):
     env.enable_counters(True); env.counters(reset=True)
     for _ in range(5): env.step_random()
     c = env.counters(); n = c["env_steps"]
-    print(scene, "per env-step: gjk calls %.2f iters %.2f dots %.0f flagged sub-steps %.2f" % (
-        c["gjk_calls"]/n, c["gjk_iters"]/n, c["support_dots"]/n, c["flagged_substeps"]/n))
+    print(scene, "per env-step: gjk pairs %.2f (distance items %.2f, contact items %.2f) iters %.2f dots %.0f" % (
+        c["gjk_calls"]/n, c["distance_items"]/n, c["contact_items"]/n, c["gjk_iters"]/n, c["support_dots"]/n))
+    env.enable_counters(False); env.kernel_timing(True)
+    for _ in range(20): env.step_random()
+    t, k = env.kernel_times()
+    print("   kernel us/step:", {a: round(1e3*b, 1) for a, b in t.items()}, "sum %.1f" % (1e3*sum(t.values())))
     env.close()
