@@ -127,6 +127,7 @@ struct SmEnv {
     double kernel_ms[SM_K_COUNT] = {};
     int timed_steps = 0;
     int* d_heavy = nullptr;      // [0] = count, [1..8n] = (env, joint) instances deferred to joint_heavy_kernel
+    int* d_cwork = nullptr;      // [0] = count, [1..n] = envs the coarse contact phase could not clear
     bool count = false;
     size_t smem_bytes = 0;        // kernels that stage the hull vertices
     size_t smem_bytes_broad = 0;  // contact_broad_kernel: scene tables only
@@ -253,6 +254,24 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
         float mx = 0.f;
         for (int i = 0; i < SM_MAX_MOV_ROBOT; ++i) { d.contact_thresh[o][i] = (float)sc->contact_thresh[o][i]; mx = fmaxf(mx, d.contact_thresh[o][i]); }
         d.contact_thresh_max[o] = mx;
+        d.obst_center_norm[o] = sqrtf(d.obst_center[o][0] * d.obst_center[o][0] + d.obst_center[o][1] * d.obst_center[o][1] +
+                                      d.obst_center[o][2] * d.obst_center[o][2]) * (1.0f + 1e-6f);
+    }
+    // coarse contact phase: a change of joint j by dq moves the sphere centre of a contact slot in frame f by at most
+    // dq * (sum of the fixed joint offsets between frame j+1 and f, plus the centre's own offset)
+    for (int slot = 0; slot < sc->n_mov_contact; ++slot) {
+        const SmShape& h = sc->shapes[sc->mov_contact[slot]];
+        const float cn = sqrtf((float)(h.center[0] * h.center[0] + h.center[1] * h.center[1] + h.center[2] * h.center[2]));
+        for (int j = 0; j < SM_MAX_JOINTS; ++j) {
+            float rho = 0.f;
+            if (j < h.frame) {
+                rho = cn;
+                for (int i = j + 1; i < h.frame; ++i)
+                    rho += sqrtf(d.jt[i][0] * d.jt[i][0] + d.jt[i][1] * d.jt[i][1] + d.jt[i][2] * d.jt[i][2]);
+                rho *= 1.0f + 1e-5f;
+            }
+            d.contact_rho[slot][j] = rho;
+        }
     }
     d.planet_steps = sc->planet_steps; d.planet_shift = sc->planet_shift; d.obs_planet_size = sc->obs_planet_size;
     d.planet_obs_half[0] = sc->planet_obs_half[0]; d.planet_obs_half[1] = sc->planet_obs_half[1];
@@ -334,6 +353,8 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
         *env->h_flag = 0;
         CU(cudaHostGetDevicePointer((void**)&env->d_flag, env->h_flag, 0));
     }
+    CU(cudaMalloc((void**)&env->d_cwork, ((size_t)num_envs + 1) * sizeof(int)));
+    CU(cudaMemset(env->d_cwork, 0, ((size_t)num_envs + 1) * sizeof(int)));
     CU(cudaMalloc((void**)&env->d_heavy, ((size_t)num_envs * 8 + 1) * sizeof(int)));
     CU(cudaMemset(env->d_heavy, 0, ((size_t)num_envs * 8 + 1) * sizeof(int)));
     CU(cudaMalloc((void**)&env->d_counters, 16 * sizeof(unsigned long long)));
@@ -369,7 +390,7 @@ extern "C" int smenv_destroy(SmEnv* env) {
     cudaSetDevice(env->device);
     if (g_active == env) g_active = nullptr;
     cudaFree(env->d_verts); cudaFree(env->d_lut); cudaFree(env->d_plocal); cudaFree(env->d_start_pool); cudaFree(env->d_ball_pool);
-    cudaFree(env->d_counters); cudaFree(env->d_scratch); cudaFree(env->d_worklist); cudaFree(env->d_heavy); cudaFree(env->d_items); cudaFree(env->d_res);
+    cudaFree(env->d_counters); cudaFree(env->d_scratch); cudaFree(env->d_worklist); cudaFree(env->d_heavy); cudaFree(env->d_cwork); cudaFree(env->d_items); cudaFree(env->d_res);
     if (env->h_flag) cudaFreeHost(env->h_flag);
     for (int i = 0; i <= SM_K_COUNT; ++i) if (env->ev[i]) cudaEventDestroy(env->ev[i]);
     for (int o = 0; o < SM_MAX_OBSTACLES; ++o) { cudaFree(env->d_ppos[o]); cudaFree(env->d_pquat[o]); }
@@ -539,15 +560,16 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
     JA.scratch = env->d_scratch;
     JA.worklist = env->d_worklist;  // clears the item counter and the overflow count
     JA.heavy = env->d_heavy;
+    JA.cwork = env->d_cwork;
     const bool tk = env->time_kernels;
 #define SM_MARK(i) do { if (tk) cudaEventRecord(env->ev[i], stream); } while (0)
     SM_MARK(SM_K_JOINT);
     joint_kernel<<<(env->n * 8 + 255) / 256, 256, 0, stream>>>(JA);
     SM_MARK(SM_K_JOINT_HEAVY);
     {   // the heavy list is at most 8 n long; blocks beyond its length exit at once
-        int hb = (env->n * 8 + 127) / 128;
+        int hb = (env->n * 8 + SM_HEAVY_THREADS - 1) / SM_HEAVY_THREADS;
         if (hb > 8 * env->sms) hb = 8 * env->sms;
-        joint_heavy_kernel<<<hb, 128, 0, stream>>>(JA);
+        joint_heavy_kernel<<<hb, SM_HEAVY_THREADS, 0, stream>>>(JA);
     }
     env->launches += 2;
     PlanArgs P;
@@ -555,6 +577,7 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
     P.items = env->d_items; P.item_count = env->d_worklist; P.capacity = env->item_capacity;
     P.overflow = env->d_worklist + 1; P.res = env->d_res;
     P.kin = buf->kin; P.obst = buf->obst; P.advance = 1; P.counters = env->d_counters;
+    P.cwork = env->d_cwork;
     GjkArgs G;
     G.items = env->d_items; G.n_items = env->d_worklist; G.capacity = env->item_capacity; G.res = env->d_res;
     G.counters = env->d_counters;
@@ -578,8 +601,14 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
     const bool contacts = env->host_scene.contact_stride > 0 && env->host_scene.n_obstacles > 0;
     SM_MARK(SM_K_CONTACT_PLAN);
     if (contacts) {
-        if (env->count) contact_plan_kernel<true><<<grid_p, T, env->smem_bytes_broad, stream>>>(P);
-        else contact_plan_kernel<false><<<grid_p, T, env->smem_bytes_broad, stream>>>(P);
+        const int grid_c = (env->n * SM_COARSE_LANES + 255) / 256;
+        if (env->count) {
+            contact_coarse_kernel<true><<<grid_c, 256, env->smem_bytes_broad, stream>>>(P);
+            contact_plan_kernel<true><<<grid_p, T, env->smem_bytes_broad, stream>>>(P);
+        } else {
+            contact_coarse_kernel<false><<<grid_c, 256, env->smem_bytes_broad, stream>>>(P);
+            contact_plan_kernel<false><<<grid_p, T, env->smem_bytes_broad, stream>>>(P);
+        }
     }
     SM_MARK(SM_K_DISTANCE_PLAN);
     if (env->count) distance_plan_kernel<true><<<grid_p, T, env->smem_bytes_broad, stream>>>(P);
@@ -601,7 +630,7 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
         }
         env->timed_steps++;
     }
-    env->launches += contacts ? 4 : 3;
+    env->launches += contacts ? 5 : 3;
     CU(cudaGetLastError());
     return SM_OK;
 }

@@ -71,6 +71,8 @@ struct DevScene {
     float obst_center[SM_MAX_OBSTACLES][3], obst_radius[SM_MAX_OBSTACLES];
     float contact_thresh[SM_MAX_OBSTACLES][SM_MAX_MOV_ROBOT];
     float contact_thresh_max[SM_MAX_OBSTACLES];
+    float obst_center_norm[SM_MAX_OBSTACLES];              // |obst_center|: sphere about the body origin instead
+    float contact_rho[SM_MAX_MOV_ROBOT][SM_MAX_JOINTS];    // bound on |d centre(slot) / d q_j| (coarse contact phase)
     int planet_steps, planet_shift, obs_planet_size;
     const float4* planet_pos[SM_MAX_OBSTACLES];   // xyz, w unused
     const float4* planet_quat[SM_MAX_OBSTACLES];  // xyzw
@@ -182,10 +184,25 @@ __device__ __noinline__ double pos_peak(double p, double v, double a, double a1,
     return best;
 }
 
+// pos_upper in two halves (the same operations in the same order): the first evaluation decides whether the bound is
+// active at all, the second half is the iterative solve.  joint_heavy_kernel runs the halves in separate phases so
+// that the solve executes with densely packed lanes.
+__device__ __forceinline__ double pos_upper_first(double p, double v, double a, double pmax, double hi, double J,
+                                                  double A, double ts) {
+    return xsub(pos_peak(p, v, a, hi, J, A, ts), pmax);
+}
+__device__ __noinline__ double pos_upper_rest(double p, double v, double a, double pmax, double lo, double hi, double J,
+                                              double A, double ts, double fr);
+
 __device__ __noinline__ double pos_upper(double p, double v, double a, double pmax, double lo, double hi, double J, double A,
                             double ts) {
-    double fr = xsub(pos_peak(p, v, a, hi, J, A, ts), pmax);
+    double fr = pos_upper_first(p, v, a, pmax, hi, J, A, ts);
     if (fr <= 0.0) return SM_BIG;
+    return pos_upper_rest(p, v, a, pmax, lo, hi, J, A, ts, fr);
+}
+
+__device__ __noinline__ double pos_upper_rest(double p, double v, double a, double pmax, double lo, double hi, double J,
+                                              double A, double ts, double fr) {
     double fl = xsub(pos_peak(p, v, a, lo, J, A, ts), pmax);
     if (fl > 0.0) return fl > 1e-6 ? -SM_BIG : lo;
     double xl = lo, xr = hi;

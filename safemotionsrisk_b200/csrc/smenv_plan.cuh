@@ -25,6 +25,7 @@ struct PlanArgs {
     const double* kin;       // kinematic records to plan for (buf.kin in the step, the caller's array in the hook)
     const double* obst;      // obstacle records
     int advance;             // 1: obstacle poses at the end of the step about to be finished; 0: poses as recorded
+    int* cwork;              // [0] = count, [1..] = envs whose sub-step contacts need the fine planning
     unsigned long long* counters;
 };
 
@@ -71,6 +72,141 @@ __device__ __forceinline__ int warp_exclusive_sum(int x, int lane, int& total) {
     return s - x;
 }
 
+// one link of the serial chain: F <- F o [R_fix Rot(axis_j, q) | t_fix]
+__device__ __forceinline__ void fk_chain_step(const SceneSmem& sm, Xf& F, int j, float q) {
+    float s, c;
+    sincosf(q, &s, &c);
+    Xf L, C;
+    float Rj[9];
+    axis_angle(sm.jaxis[j][0], sm.jaxis[j][1], sm.jaxis[j][2], c, s, Rj);
+    const float* A = sm.jR[j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            L.r[3 * i + k] = fmaf(A[3 * i], Rj[k], fmaf(A[3 * i + 1], Rj[3 + k], A[3 * i + 2] * Rj[6 + k]));
+    L.t[0] = sm.jt[j][0]; L.t[1] = sm.jt[j][1]; L.t[2] = sm.jt[j][2];
+    xf_compose(F, L, C);
+    F = C;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Coarse contact phase: 8 threads per env, each clears a span of ceil(S / 8) consecutive sub-steps with ONE forward
+// kinematics (the pose of the span's middle sub-step): every contact sphere is inflated by what the joints move inside
+// the span (sum_j |dq_j| * contact_rho[slot][j]) and tested against the obstacle's whole-body sphere at each sub-step
+// of the span.  Only envs with a span that cannot be cleared go to the fine planning (contact_plan_kernel), which
+// needs a full warp per env; typically that is a small fraction of the envs.
+// ------------------------------------------------------------------------------------------------------------------
+#define SM_COARSE_LANES 8
+#define SM_COARSE_SPAN 4 /* max sub-steps per coarse thread: ceil(SM_MAX_SUB / SM_COARSE_LANES) */
+
+template <bool COUNT>
+__global__ void __launch_bounds__(256) contact_coarse_kernel(PlanArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemLayout L = block_prologue(smem_raw, false);
+    const SceneSmem& sm = L.bs->scene;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int t = blockIdx.x * blockDim.x + tid;
+    const int env = t / SM_COARSE_LANES, c = t % SM_COARSE_LANES;
+    const int S = c_sc.substeps, stride = c_sc.contact_stride;
+    const int kind = c_sc.n_obstacles > 0 ? c_sc.obst_kind[0] : SM_OBST_NONE;
+    const int span = (S + SM_COARSE_LANES - 1) / SM_COARSE_LANES;
+    bool flag = false;
+    if (env < A.n && stride > 0 && c * span < S) {
+        const double* ob = A.obst + (size_t)env * SM_OBST_STRIDE;
+        const int k0 = c * span, k1 = k0 + span < S ? k0 + span : S;
+        const int kc = (k0 + k1 - 1) >> 1;
+        V3 oc[2][SM_COARSE_SPAN];
+        unsigned valid = 0;  // bit (o * SM_COARSE_SPAN + i): obstacle o is tested at sub-step k0 + i
+        if (ob[SM_OB_LATCH] == 0.0) {
+            const int idx0 = (int)ob[SM_OB_INDEX];
+            if (kind == SM_OBST_PLANET && c_sc.terminate_moving) {
+#pragma unroll
+                for (int i = 0; i < SM_COARSE_SPAN; ++i) {
+                    if (k0 + i >= k1) continue;
+                    const int idx = (idx0 + k0 + i) % c_sc.planet_steps;
+                    const float4 p0 = __ldg(c_sc.planet_pos[0] + idx);
+                    oc[0][i] = mk(p0.x, p0.y, p0.z);
+                    valid |= 1u << i;
+                    if (c_sc.n_obstacles > 1) {
+                        int id1 = (idx + c_sc.planet_shift) % c_sc.planet_steps;
+                        if (id1 < 0) id1 += c_sc.planet_steps;
+                        const float4 p1 = __ldg(c_sc.planet_pos[1] + id1);
+                        oc[1][i] = mk(p1.x, p1.y, p1.z);
+                        valid |= 1u << (SM_COARSE_SPAN + i);
+                    }
+                }
+            } else if (kind == SM_OBST_BALL && ob[SM_OB_BALL_ACTIVE] != 0.0) {
+                const double dt = xdiv(c_sc.ts, (double)S);
+                const int k_end = ball_k_end(ob);
+                const double ball_t = ob[SM_OB_BALL_T];
+#pragma unroll
+                for (int i = 0; i < SM_COARSE_SPAN; ++i) {
+                    const int k = k0 + i, sub = k + 1;
+                    if (k >= k1 || sub > k_end - 1) continue;
+                    const double tn = ball_t + (double)sub * dt;  // active-area test on the new position
+                    const double px = ob[SM_OB_BALL_P0] + ob[SM_OB_BALL_V0] * tn;
+                    const double py = ob[SM_OB_BALL_P0 + 1] + ob[SM_OB_BALL_V0 + 1] * tn;
+                    if (!(sqrt(px * px + py * py) < c_sc.ball_active_xy)) continue;
+                    const double tk = ball_t + (double)k * dt;    // manifold of the previous position
+                    oc[0][i] = mk((float)(ob[SM_OB_BALL_P0] + ob[SM_OB_BALL_V0] * tk),
+                                  (float)(ob[SM_OB_BALL_P0 + 1] + ob[SM_OB_BALL_V0 + 1] * tk),
+                                  (float)(ob[SM_OB_BALL_P0 + 2] + ob[SM_OB_BALL_V0 + 2] * tk + (0.5 * -9.81) * (tk * tk)));
+                    valid |= 1u << i;
+                }
+            }
+        }
+        if (valid) {
+            const float* scr = A.scratch + (size_t)env * SM_SCRATCH_FLOATS;
+            float dq[SM_MAX_JOINTS];
+            const float* qc = scr + kc * SM_MAX_JOINTS;
+#pragma unroll
+            for (int j = 0; j < SM_MAX_JOINTS; ++j) {
+                float m = 0.f;
+                for (int k = k0; k < k1; ++k) m = fmaxf(m, fabsf(scr[k * SM_MAX_JOINTS + j] - qc[j]));
+                dq[j] = m;
+            }
+            Xf F;
+            xf_identity(F);
+#pragma unroll 1
+            for (int f = 0; f <= c_sc.n_joints && !flag; ++f) {
+                if (f > 0) fk_chain_step(sm, F, f - 1, qc[f - 1]);
+#pragma unroll 1
+                for (int slot = c_sc.contact_frame_start[f]; slot < c_sc.contact_frame_start[f + 1]; ++slot) {
+                    const DevShape& sh = sm.shapes[sm.mov_contact[slot]];
+                    const V3 ctr = xf_apply(F, sh.cx, sh.cy, sh.cz);
+                    float infl = 1e-5f;
+#pragma unroll
+                    for (int j = 0; j < SM_MAX_JOINTS; ++j) infl = fmaf(dq[j], c_sc.contact_rho[slot][j], infl);
+                    const float rr = sh.radius + sh.margin + infl;
+#pragma unroll
+                    for (int o = 0; o < 2; ++o) {
+                        const float lim = rr + c_sc.obst_radius[o] + c_sc.obst_center_norm[o] + sm.contact_thresh[o][slot];
+#pragma unroll
+                        for (int i = 0; i < SM_COARSE_SPAN; ++i) {
+                            if (!((valid >> (o * SM_COARSE_SPAN + i)) & 1u)) continue;
+                            const V3 e = ctr - oc[o][i];
+                            if (dot(e, e) <= lim * lim) flag = true;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // one list entry per env with a flagged span (the 8 lanes of an env sit in one warp)
+    const unsigned fm = __ballot_sync(FULL, flag);
+    const unsigned grp = (fm >> (lane & ~(SM_COARSE_LANES - 1))) & ((1u << SM_COARSE_LANES) - 1u);
+    const bool lead = grp != 0 && (lane & (SM_COARSE_LANES - 1)) == 0;
+    const unsigned lm = __ballot_sync(FULL, lead);
+    if (lm) {
+        int base = 0;
+        if (lane == __ffs(lm) - 1) base = atomicAdd(A.cwork, __popc(lm));
+        base = __shfl_sync(FULL, base, __ffs(lm) - 1);
+        if (lead) A.cwork[1 + base + __popc(lm & ((1u << lane) - 1u))] = env;
+        if (COUNT && A.counters && lane == __ffs(lm) - 1) atomicAdd(&A.counters[5], (unsigned long long)__popc(lm));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // contacts of one sub-step (one lane): serial FK chain of the tracked pose; every contact shape against the obstacle
 // bounding spheres and then the spheres of the obstacle's convex parts, all inflated by the contact thresholds.
@@ -86,23 +222,7 @@ __device__ __forceinline__ int contact_scan(const SceneSmem& sm, const float* __
     xf_identity(F);
 #pragma unroll 1
     for (int f = 0; f <= c_sc.n_joints; ++f) {
-        if (f > 0) {  // serial chain: frame f hangs off frame f-1 (checked on the host)
-            const int j = f - 1;
-            float s, c;
-            sincosf(qrow[j], &s, &c);
-            Xf L, C;
-            float Rj[9];
-            axis_angle(sm.jaxis[j][0], sm.jaxis[j][1], sm.jaxis[j][2], c, s, Rj);
-            const float* A = sm.jR[j];
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int k = 0; k < 3; ++k)
-                    L.r[3 * i + k] = fmaf(A[3 * i], Rj[k], fmaf(A[3 * i + 1], Rj[3 + k], A[3 * i + 2] * Rj[6 + k]));
-            L.t[0] = sm.jt[j][0]; L.t[1] = sm.jt[j][1]; L.t[2] = sm.jt[j][2];
-            xf_compose(F, L, C);
-            F = C;
-        }
+        if (f > 0) fk_chain_step(sm, F, f - 1, qrow[f - 1]);  // frame f hangs off frame f-1 (checked on the host)
 #pragma unroll 1
         for (int slot = c_sc.contact_frame_start[f]; slot < c_sc.contact_frame_start[f + 1]; ++slot) {
             const int ia = sm.mov_contact[slot];
@@ -137,6 +257,8 @@ __device__ __forceinline__ int contact_scan(const SceneSmem& sm, const float* __
 template <bool COUNT>
 __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) contact_plan_kernel(PlanArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n_work = A.cwork[0];
+    if (blockIdx.x * SM_WARPS_PER_BLOCK >= n_work) return;  // nothing for this block: skip the staging
     SmemLayout L = block_prologue(smem_raw, false);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const SceneSmem& sm = L.bs->scene;
@@ -146,7 +268,8 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) contact_plan_kernel(P
     const double dt = xdiv(c_sc.ts, (double)S);
     unsigned n_flag = 0;
 #pragma unroll 1
-    for (int env = blockIdx.x * SM_WARPS_PER_BLOCK + warp; env < A.n; env += gridDim.x * SM_WARPS_PER_BLOCK) {
+    for (int w = blockIdx.x * SM_WARPS_PER_BLOCK + warp; w < n_work; w += gridDim.x * SM_WARPS_PER_BLOCK) {
+        const int env = A.cwork[1 + w];
         const float* scr = A.scratch + (size_t)env * SM_SCRATCH_FLOATS;
         if (lane < SM_OBST_STRIDE) W.ob[lane] = A.obst[(size_t)env * SM_OBST_STRIDE + lane];
         __syncwarp();
