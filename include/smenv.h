@@ -207,10 +207,12 @@ typedef struct SmCounters {
     unsigned long long support_dots;   /* vertex . direction products evaluated in support searches */
     unsigned long long distance_items; /* pairs the distance planning could not cull (emitted items) */
     unsigned long long env_steps;
-    unsigned long long contact_tests;  /* reserved */
+    unsigned long long contact_envs;   /* envs the coarse contact phase passed on to the fine planning */
     unsigned long long contact_items;  /* (sub-step, pair) contact candidates emitted by the contact planning */
     unsigned long long reserved;
-    unsigned long long phase_cycles[8]; /* reserved */
+    unsigned long long heavy_joints;   /* (env, joint) instances that went through joint_heavy_kernel */
+    unsigned long long heavy_solves;   /* position bounds that needed the iterative solve */
+    unsigned long long aux[6];         /* reserved */
 } SmCounters;
 
 /* Kernels of one step, in launch order (smenv_kernel_times). */

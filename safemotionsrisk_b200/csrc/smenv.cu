@@ -128,6 +128,8 @@ struct SmEnv {
     int timed_steps = 0;
     int* d_heavy = nullptr;      // [0] = count, [1..8n] = (env, joint) instances deferred to joint_heavy_kernel
     int* d_cwork = nullptr;      // [0] = count, [1..n] = envs the coarse contact phase could not clear
+    int* d_tasks = nullptr;      // [0] = count, [1..16n] = position bounds to solve (joint_solve_kernel)
+    double* d_hpar = nullptr;    // [8n][SM_HPAR] hand-over records of the deferred joints
     bool count = false;
     size_t smem_bytes = 0;        // kernels that stage the hull vertices
     size_t smem_bytes_broad = 0;  // contact_broad_kernel: scene tables only
@@ -353,6 +355,9 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
         *env->h_flag = 0;
         CU(cudaHostGetDevicePointer((void**)&env->d_flag, env->h_flag, 0));
     }
+    CU(cudaMalloc((void**)&env->d_tasks, ((size_t)num_envs * 16 + 1) * sizeof(int)));
+    CU(cudaMemset(env->d_tasks, 0, ((size_t)num_envs * 16 + 1) * sizeof(int)));
+    CU(cudaMalloc((void**)&env->d_hpar, (size_t)num_envs * 8 * SM_HPAR * sizeof(double)));
     CU(cudaMalloc((void**)&env->d_cwork, ((size_t)num_envs + 1) * sizeof(int)));
     CU(cudaMemset(env->d_cwork, 0, ((size_t)num_envs + 1) * sizeof(int)));
     CU(cudaMalloc((void**)&env->d_heavy, ((size_t)num_envs * 8 + 1) * sizeof(int)));
@@ -390,7 +395,7 @@ extern "C" int smenv_destroy(SmEnv* env) {
     cudaSetDevice(env->device);
     if (g_active == env) g_active = nullptr;
     cudaFree(env->d_verts); cudaFree(env->d_lut); cudaFree(env->d_plocal); cudaFree(env->d_start_pool); cudaFree(env->d_ball_pool);
-    cudaFree(env->d_counters); cudaFree(env->d_scratch); cudaFree(env->d_worklist); cudaFree(env->d_heavy); cudaFree(env->d_cwork); cudaFree(env->d_items); cudaFree(env->d_res);
+    cudaFree(env->d_counters); cudaFree(env->d_scratch); cudaFree(env->d_worklist); cudaFree(env->d_heavy); cudaFree(env->d_cwork); cudaFree(env->d_tasks); cudaFree(env->d_hpar); cudaFree(env->d_items); cudaFree(env->d_res);
     if (env->h_flag) cudaFreeHost(env->h_flag);
     for (int i = 0; i <= SM_K_COUNT; ++i) if (env->ev[i]) cudaEventDestroy(env->ev[i]);
     for (int o = 0; o < SM_MAX_OBSTACLES; ++o) { cudaFree(env->d_ppos[o]); cudaFree(env->d_pquat[o]); }
@@ -561,17 +566,22 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
     JA.worklist = env->d_worklist;  // clears the item counter and the overflow count
     JA.heavy = env->d_heavy;
     JA.cwork = env->d_cwork;
+    JA.tasks = env->d_tasks;
+    JA.hpar = env->d_hpar;
+    JA.counters = env->count ? env->d_counters : nullptr;
     const bool tk = env->time_kernels;
 #define SM_MARK(i) do { if (tk) cudaEventRecord(env->ev[i], stream); } while (0)
     SM_MARK(SM_K_JOINT);
     joint_kernel<<<(env->n * 8 + 255) / 256, 256, 0, stream>>>(JA);
     SM_MARK(SM_K_JOINT_HEAVY);
-    {   // the heavy list is at most 8 n long; blocks beyond its length exit at once
+    {   // the lists are at most 8 n / 16 n long; blocks beyond their length exit at once
         int hb = (env->n * 8 + SM_HEAVY_THREADS - 1) / SM_HEAVY_THREADS;
         if (hb > 8 * env->sms) hb = 8 * env->sms;
-        joint_heavy_kernel<<<hb, SM_HEAVY_THREADS, 0, stream>>>(JA);
+        joint_first_kernel<<<hb, SM_HEAVY_THREADS, 0, stream>>>(JA);
+        joint_solve_kernel<<<hb, SM_HEAVY_THREADS, 0, stream>>>(JA);
+        joint_final_kernel<<<hb, SM_HEAVY_THREADS, 0, stream>>>(JA);
     }
-    env->launches += 2;
+    env->launches += 4;
     PlanArgs P;
     P.buf = *buf; P.n = env->n; P.scratch = env->d_scratch;
     P.items = env->d_items; P.item_count = env->d_worklist; P.capacity = env->item_capacity;
@@ -692,8 +702,9 @@ extern "C" int smenv_counters(SmEnv* env, SmCounters* out, int reset) {
     unsigned long long h[16];
     CU(cudaMemcpy(h, env->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
     out->gjk_calls = h[0]; out->gjk_iters = h[1]; out->support_dots = h[2]; out->distance_items = h[3];
-    out->env_steps = h[4]; out->contact_tests = h[5]; out->contact_items = h[6]; out->reserved = h[7];
-    for (int i = 0; i < 8; ++i) out->phase_cycles[i] = h[8 + i];
+    out->env_steps = h[4]; out->contact_envs = h[5]; out->contact_items = h[6]; out->reserved = h[7];
+    out->heavy_joints = h[8]; out->heavy_solves = h[9];
+    for (int i = 0; i < 6; ++i) out->aux[i] = h[10 + i];
     if (reset) CU(cudaMemset(env->d_counters, 0, sizeof(h)));
     return SM_OK;
 }

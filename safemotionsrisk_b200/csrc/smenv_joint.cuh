@@ -29,7 +29,10 @@ struct JointArgs {
     uint32_t k0, k1, step_counter;
     float* scratch;  // [n][SM_SCRATCH_FLOATS]
     int* worklist;   // [0] = GJK item counter, [1] = overflowed items of the step: both cleared here
+    unsigned long long* counters;  // device SmCounters in the counting mode, else NULL
     int* cwork;      // [0] = number of envs listed for the fine contact planning: cleared here
+    int* tasks;      // [0] = number of position bounds to solve (cleared here), [1..] = heavy index * 2 + side
+    double* hpar;    // [8 n][SM_HPAR] hand-over records of the deferred instances
     int* heavy;      // [0] = number of (env, joint) instances whose position bound needs the iterative solve,
                      // [1..] = env * 8 + joint (filled by joint_kernel, consumed by joint_heavy_kernel)
 };
@@ -114,74 +117,95 @@ __global__ void __launch_bounds__(256) joint_kernel(JointArgs A) {
     }
     if (t == 0 && A.worklist) { A.worklist[0] = 0; A.worklist[1] = 0; }
     if (t == 0 && A.cwork) A.cwork[0] = 0;
+    if (t == 0 && A.tasks) A.tasks[0] = 0;
 }
 
-// Second pass over the deferred (env, joint) instances, 128 per block and round, in three phases:
-//   1. every thread: the cheap bounds again and the first evaluation of both position bounds (is it active at all?)
-//   2. the active bounds of the block, compacted in shared memory: the iterative solve with densely packed lanes
-//   3. every thread: clamp, map the action, advance
-// (a single-phase version averaged 5.3 active lanes per instruction: few instances need the solve, and those need it
-// for very different numbers of iterations.)
+// Second pass over the deferred (env, joint) instances, as three small kernels so that each runs with densely
+// packed lanes (a single kernel averaged 5.3 active lanes per instruction: a third of the joints are deferred, a
+// tenth need the iterative solve, and those need it for very different numbers of iterations):
+//   joint_first_kernel   thread = deferred instance: the cheap bounds again and the FIRST evaluation of both position
+//                        bounds (is the bound active at all?); active bounds are appended to the task list
+//   joint_solve_kernel   thread = task: the iterative solve (pos_upper_rest)
+//   joint_final_kernel   thread = deferred instance: clamp, map the action, advance
+// Per-instance hand-over record (SM_HPAR doubles): lo, hi, code, fr_hi, fr_lo, res_hi, res_lo.
+#define SM_HPAR 8
 #define SM_HEAVY_THREADS 128
-__global__ void __launch_bounds__(SM_HEAVY_THREADS) joint_heavy_kernel(JointArgs A) {
-    __shared__ double s_par[SM_HEAVY_THREADS][6];   // p v a lo hi (joint index in [5])
-    __shared__ double s_fr[SM_HEAVY_THREADS][2];    // first evaluation of the upper / lower bound
-    __shared__ double s_res[SM_HEAVY_THREADS][2];   // pos_upper result of the upper / mirrored lower bound
-    __shared__ int s_task[2 * SM_HEAVY_THREADS];
-    __shared__ int s_ntask;
+
+__global__ void __launch_bounds__(SM_HEAVY_THREADS) joint_first_kernel(JointArgs A) {
     const int n_heavy = A.heavy[0];
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const double ts = c_sc.ts;
 #pragma unroll 1
-    for (int base = blockIdx.x * SM_HEAVY_THREADS; base < n_heavy; base += gridDim.x * SM_HEAVY_THREADS) {
-        if (tid == 0) s_ntask = 0;
-        __syncthreads();
-        const int i = base + tid;
-        const bool valid = i < n_heavy;
-        int t = 0, env = 0, j = 0, code = 0;
-        double q = 0, v = 0, a = 0, qa = 0, lo = 0, hi = 0;
-        if (valid) {
-            t = A.heavy[1 + i];
-            env = t >> 3; j = t & 7;
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < n_heavy; base += gridDim.x * blockDim.x) {
+        const int i = base + lane;
+        bool t_hi = false, t_lo = false;
+        if (i < n_heavy) {
+            const int t = A.heavy[1 + i];
+            const int env = t >> 3, j = t & 7;
             const double* kin = A.buf.kin + (size_t)env * SM_KIN_STRIDE;
-            q = kin[j]; v = kin[8 + j]; a = kin[16 + j]; qa = kin[24 + j];
+            const double q = kin[j], v = kin[8 + j], a = kin[16 + j];
+            double lo, hi;
+            int code;
             bool need_pos;
             safe_range_light(j, q, v, a, lo, hi, code, need_pos);
             const double J = c_sc.jerk_max[j], Am = c_sc.acc_max[j];
             const double fr_hi = pos_upper_first(q, v, a, c_sc.pos_hi[j], hi, J, Am, ts);
             const double fr_lo = pos_upper_first(-q, -v, -a, -c_sc.pos_lo[j], -lo, J, Am, ts);
-            s_par[tid][0] = q; s_par[tid][1] = v; s_par[tid][2] = a; s_par[tid][3] = lo; s_par[tid][4] = hi;
-            s_par[tid][5] = (double)j;
-            s_fr[tid][0] = fr_hi; s_fr[tid][1] = fr_lo;
-            s_res[tid][0] = SM_BIG; s_res[tid][1] = SM_BIG;
-            if (fr_hi > 0.0) s_task[atomicAdd(&s_ntask, 1)] = 2 * tid;
-            if (fr_lo > 0.0) s_task[atomicAdd(&s_ntask, 1)] = 2 * tid + 1;
+            double* hp = A.hpar + (size_t)i * SM_HPAR;
+            hp[0] = lo; hp[1] = hi; hp[2] = (double)code; hp[3] = fr_hi; hp[4] = fr_lo; hp[5] = SM_BIG; hp[6] = SM_BIG;
+            t_hi = fr_hi > 0.0;
+            t_lo = fr_lo > 0.0;
         }
-        __syncthreads();
-        const int ntask = s_ntask;
+        const unsigned mh = __ballot_sync(FULL, t_hi), ml = __ballot_sync(FULL, t_lo);
+        const int total = __popc(mh) + __popc(ml);
+        if (total) {
+            int b0 = 0;
+            if (lane == 0) b0 = atomicAdd(A.tasks, total);
+            b0 = __shfl_sync(FULL, b0, 0);
+            const unsigned below = (1u << lane) - 1u;
+            if (t_hi) A.tasks[1 + b0 + __popc(mh & below)] = 2 * i;
+            if (t_lo) A.tasks[1 + b0 + __popc(mh) + __popc(ml & below)] = 2 * i + 1;
+        }
+    }
+    if (A.counters && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&A.counters[8], (unsigned long long)n_heavy);
+}
+
+__global__ void __launch_bounds__(SM_HEAVY_THREADS) joint_solve_kernel(JointArgs A) {
+    const int n_task = A.tasks[0];
+    const double ts = c_sc.ts;
 #pragma unroll 1
-        for (int k = tid; k < ntask; k += SM_HEAVY_THREADS) {
-            const int task = s_task[k], owner = task >> 1, side = task & 1;
-            const double p = s_par[owner][0], vv = s_par[owner][1], aa = s_par[owner][2];
-            const double l = s_par[owner][3], h = s_par[owner][4];
-            const int jj = (int)s_par[owner][5];
-            const double J = c_sc.jerk_max[jj], Am = c_sc.acc_max[jj];
-            s_res[owner][side] = side == 0
-                ? pos_upper_rest(p, vv, aa, c_sc.pos_hi[jj], l, h, J, Am, ts, s_fr[owner][0])
-                : pos_upper_rest(-p, -vv, -aa, -c_sc.pos_lo[jj], -h, -l, J, Am, ts, s_fr[owner][1]);
-        }
-        __syncthreads();
-        if (valid) {
-            if (c_sc.limit_position)
-                clamp_range(lo, hi, -s_res[tid][1], s_res[tid][0], CODE_POS_HI, CODE_POS_LO, code);
-            double* kin = A.buf.kin + (size_t)env * SM_KIN_STRIDE;
-            float* scr = A.scratch + (size_t)env * SM_SCRATCH_FLOATS;
-            const float uf = joint_action(A, env, j);
-            const float jerk_rel = joint_advance(kin, scr, j, q, v, a, qa, lo, hi, uf);
-            // non-negative floats order like their bit patterns
-            atomicMax(reinterpret_cast<int*>(scr + SM_MISC_OFF + SM_MISC_JERK), __float_as_int(jerk_rel));
-            if (code) atomicOr(reinterpret_cast<int*>(scr + SM_MISC_OFF + SM_MISC_RCODE), code);
-        }
-        __syncthreads();
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_task; k += gridDim.x * blockDim.x) {
+        const int task = A.tasks[1 + k], i = task >> 1, side = task & 1;
+        const int t = A.heavy[1 + i];
+        const int env = t >> 3, j = t & 7;
+        const double* kin = A.buf.kin + (size_t)env * SM_KIN_STRIDE;
+        const double q = kin[j], v = kin[8 + j], a = kin[16 + j];
+        double* hp = A.hpar + (size_t)i * SM_HPAR;
+        const double lo = hp[0], hi = hp[1];
+        const double J = c_sc.jerk_max[j], Am = c_sc.acc_max[j];
+        hp[5 + side] = side == 0 ? pos_upper_rest(q, v, a, c_sc.pos_hi[j], lo, hi, J, Am, ts, hp[3])
+                                 : pos_upper_rest(-q, -v, -a, -c_sc.pos_lo[j], -hi, -lo, J, Am, ts, hp[4]);
+    }
+    if (A.counters && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&A.counters[9], (unsigned long long)n_task);
+}
+
+__global__ void __launch_bounds__(SM_HEAVY_THREADS) joint_final_kernel(JointArgs A) {
+    const int n_heavy = A.heavy[0];
+#pragma unroll 1
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_heavy; i += gridDim.x * blockDim.x) {
+        const int t = A.heavy[1 + i];
+        const int env = t >> 3, j = t & 7;
+        double* kin = A.buf.kin + (size_t)env * SM_KIN_STRIDE;
+        float* scr = A.scratch + (size_t)env * SM_SCRATCH_FLOATS;
+        const double q = kin[j], v = kin[8 + j], a = kin[16 + j], qa = kin[24 + j];
+        const double* hp = A.hpar + (size_t)i * SM_HPAR;
+        double lo = hp[0], hi = hp[1];
+        int code = (int)hp[2];
+        if (c_sc.limit_position) clamp_range(lo, hi, -hp[6], hp[5], CODE_POS_HI, CODE_POS_LO, code);
+        const float uf = joint_action(A, env, j);
+        const float jerk_rel = joint_advance(kin, scr, j, q, v, a, qa, lo, hi, uf);
+        // non-negative floats order like their bit patterns
+        atomicMax(reinterpret_cast<int*>(scr + SM_MISC_OFF + SM_MISC_JERK), __float_as_int(jerk_rel));
+        if (code) atomicOr(reinterpret_cast<int*>(scr + SM_MISC_OFF + SM_MISC_RCODE), code);
     }
 }

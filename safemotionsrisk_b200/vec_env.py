@@ -317,9 +317,7 @@ class SafeMotionsVecEnv:
         c = abi.SmCounters()
         torch.cuda.synchronize(self.device)
         cabi.check(self._lib.smenv_counters(self._handle, C.byref(c), int(reset)), "smenv_counters")
-        out = {k: int(getattr(c, k)) for k, _ in abi.SmCounters._fields_ if k != "phase_cycles"}
-        out["phase_cycles"] = [int(x) for x in c.phase_cycles]
-        return out
+        return {k: int(getattr(c, k)) for k, _ in abi.SmCounters._fields_ if k != "aux"}
 
     KERNELS = ("joint_kernel", "joint_heavy_kernel", "contact_plan_kernel", "distance_plan_kernel", "gjk_kernel",
                "finish_kernel")

@@ -47,9 +47,9 @@ def test_extension_is_loaded_and_counts_launches():
     env.set_state(q, q, q, np.zeros((32, 16)))
     env.step(np.zeros((32, 7), dtype=np.float32))
     torch.cuda.synchronize()
-    # set_state + observation, then the step: joint + joint heavy + contact coarse + contact plan + distance plan +
-    # gjk + finish kernels
-    assert env.launch_count() - n0 == 9
+    # set_state + observation, then the step: joint + joint first / solve / final + contact coarse + contact plan +
+    # distance plan + gjk + finish kernels
+    assert env.launch_count() - n0 == 11
     env.close()
 
 

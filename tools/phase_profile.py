@@ -15,6 +15,8 @@ for scene in (sys.argv[1:] or ["ball", "space"]):
     c = env.counters(); n = c["env_steps"]
     print(scene, "per env-step: gjk pairs %.2f (distance items %.2f, contact items %.2f) iters %.2f dots %.0f" % (
         c["gjk_calls"]/n, c["distance_items"]/n, c["contact_items"]/n, c["gjk_iters"]/n, c["support_dots"]/n))
+    print("   heavy joints %.2f (solves %.2f) per env-step, envs passed to the fine contact planning %.3f" % (
+        c["heavy_joints"]/n, c["heavy_solves"]/n, c["contact_envs"]/n))
     env.enable_counters(False); env.kernel_timing(True)
     for _ in range(20): env.step_random()
     t, k = env.kernel_times()
