@@ -396,6 +396,7 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) distance_plan_kernel(
         // ---------------- pass 1: the best upper bound of each class (distance of the hull centroids)
         const int np = moving ? n_pairs : n_fixed;
         float ub_s = cap, ub_e = cap, ub_m = query;
+        unsigned best_m = 0xffffffffu;  // the lane's moving pair with the smallest centroid distance
 #pragma unroll 1
         for (int base = 0; base < np; base += 32) {
             int ia = 0, ib = 0;
@@ -409,12 +410,31 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) distance_plan_kernel(
                 const float ub = sqrtf(dot(e, e)) * (1.0f + 1e-6f) + 1e-7f - SA.margin - SB.margin;
                 if (cls == GJK_STATIC) ub_s = fminf(ub_s, ub);
                 else if (cls == GJK_SELF) ub_e = fminf(ub_e, ub);
-                else ub_m = fminf(ub_m, ub);
+                else if (ub < ub_m) { ub_m = ub; best_m = (unsigned)ia | ((unsigned)ib << 16); }
             }
         }
         ub_s = funkey(__reduce_min_sync(FULL, fkey(ub_s)));
         ub_e = funkey(__reduce_min_sync(FULL, fkey(ub_e)));
-        ub_m = funkey(__reduce_min_sync(FULL, fkey(ub_m)));
+        {   // moving class: tighten the centroid bound with the two support points of the closest-centroid pair along
+            // the line between the centroids (two real points of the hulls: their distance bounds the minimum from
+            // above); the fewer pairs stay below the bound, the fewer items the GJK kernel has to run
+            const unsigned km = __reduce_min_sync(FULL, fkey(ub_m));
+            const unsigned has = __ballot_sync(FULL, best_m != 0xffffffffu && fkey(ub_m) == km);
+            ub_m = funkey(km);
+            if (has) {
+                const unsigned pr = __shfl_sync(FULL, best_m, __ffs(has) - 1);
+                const DevShape& SA = sm.shapes[pr & 0xffffu];
+                const DevShape& SB = sm.shapes[pr >> 16];
+                const Xf& TA = *frame_ptr(SA, W.fr, W.obx);
+                const Xf& TB = *frame_ptr(SB, W.fr, W.obx);
+                const V3 dir = xf_apply(TB, SB.gx, SB.gy, SB.gz) - xf_apply(TA, SA.gx, SA.gy, SA.gz);  // A towards B
+                const int sa = warp_support(c_sc.verts + SA.off, SA.cnt, xf_rot_t(TA, dir), lane);
+                const int sb = warp_support(c_sc.verts + SB.off, SB.cnt, xf_rot_t(TB, mk(-dir.x, -dir.y, -dir.z)), lane);
+                const float4 pa = __ldg(c_sc.verts + SA.off + sa), pb = __ldg(c_sc.verts + SB.off + sb);
+                const V3 e = xf_apply(TA, pa.x, pa.y, pa.z) - xf_apply(TB, pb.x, pb.y, pb.z);
+                ub_m = fminf(ub_m, sqrtf(dot(e, e)) * (1.0f + 1e-6f) + 1e-7f - SA.margin - SB.margin);
+            }
+        }
         // ---------------- pass 2: one item per pair whose sphere lower bound is below its class' upper bound
 #pragma unroll 1
         for (int base = 0; base < np; base += 32) {
