@@ -259,6 +259,21 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
         d.obst_center_norm[o] = sqrtf(d.obst_center[o][0] * d.obst_center[o][0] + d.obst_center[o][1] * d.obst_center[o][1] +
                                       d.obst_center[o][2] * d.obst_center[o][2]) * (1.0f + 1e-6f);
     }
+    {   // pair list of the distance planning
+        int np = 0;
+        auto push = [&](int a, int b, int cls) {
+            if (np < SM_MAX_PLAN_PAIRS) d.pair_tab[np] = (uint32_t)a | ((uint32_t)b << 12) | ((uint32_t)cls << 24);
+            ++np;
+        };
+        for (int i = 0; i < sc->n_static_pairs; ++i) push(sc->static_pairs[i][0], sc->static_pairs[i][1], 0);
+        for (int i = 0; i < sc->n_self_pairs; ++i) push(sc->self_pairs[i][0], sc->self_pairs[i][1], 1);
+        d.n_pairs_fixed = np;
+        for (int o = 0; o < sc->n_obstacles; ++o)
+            for (int r = 0; r < sc->n_mov_reward; ++r)
+                for (int k = 0; k < sc->obst_shape_cnt[o]; ++k) push(sc->mov_reward[r], sc->obst_shape_off[o] + k, 2);
+        d.n_pairs = np;
+        if (np > SM_MAX_PLAN_PAIRS) { delete env; return fail(SM_ERR_SCENE, "too many convex pairs per env for the distance planning (max 512)"); }
+    }
     // coarse contact phase: a change of joint j by dq moves the sphere centre of a contact slot in frame f by at most
     // dq * (sum of the fixed joint offsets between frame j+1 and f, plus the centre's own offset)
     for (int slot = 0; slot < sc->n_mov_contact; ++slot) {

@@ -35,6 +35,7 @@ struct DevShape {
 //   cells[6 R R]  : (word offset of the list relative to `lut`) << 8 | number of candidates
 //   lists         : candidate vertex indices (local to the shape), one byte each, four per word, padded to a word
 //                   boundary by repeating the last candidate
+#define SM_MAX_PLAN_PAIRS 512 /* entries of the per-env pair table of the distance planning */
 #define SM_LUT_RES 8
 #define SM_LUT_MIN_VERTS 33 /* smaller hulls are scanned directly */
 
@@ -96,6 +97,10 @@ struct DevScene {
     int ball_check_invalid, ball_random_initial, has_table;
     double min_start_self, ball_target_min_static, ball_target_min_self;
     const float4* verts;  // device, n_verts
+    // pair list of the distance planning: static pairs, self pairs, then (observed link shape x obstacle part) per
+    // moving obstacle; entry = shape A | shape B << 12 | class << 24
+    int n_pairs_fixed, n_pairs;
+    uint32_t pair_tab[SM_MAX_PLAN_PAIRS];
     const uint32_t* lut;  // device, n_lut_words (support-direction tables of all shapes that have one)
     int n_lut_words;
 };

@@ -18,6 +18,7 @@ struct WarpScratch {
 
 struct BlockShared {
     SceneSmem scene;
+    uint32_t pair_tab[SM_MAX_PLAN_PAIRS];
     double stats[16];
     unsigned long long counters[16];
 };
@@ -49,6 +50,7 @@ __device__ __forceinline__ SmemLayout block_prologue(unsigned char* raw, bool wi
     if (with_verts)
         for (int i = tid; i < c_sc.n_verts; i += blockDim.x) L.verts[i] = __ldg(c_sc.verts + i);
     stage_scene(L.bs->scene, tid, blockDim.x);
+    for (int i = tid; i < c_sc.n_pairs; i += blockDim.x) L.bs->pair_tab[i] = c_sc.pair_tab[i];
     if (tid < 16) L.bs->stats[tid] = 0.0;
     if (tid < 16) L.bs->counters[tid] = 0ull;
     __syncthreads();

@@ -328,25 +328,6 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) contact_plan_kernel(P
     if (COUNT && A.counters && lane == 0 && n_flag) atomicAdd(&A.counters[6], (unsigned long long)n_flag);
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// decode pair p of the env's pair list: static pairs, self pairs, then (observed link shape x obstacle part) per
-// moving obstacle.  Returns the class, -1 past the end.
-// ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int decode_pair(const SceneSmem& sm, int p, bool moving, int& ia, int& ib) {
-    if (p < c_sc.n_static_pairs) { ia = sm.static_pairs[p][0]; ib = sm.static_pairs[p][1]; return GJK_STATIC; }
-    p -= c_sc.n_static_pairs;
-    if (p < c_sc.n_self_pairs) { ia = sm.self_pairs[p][0]; ib = sm.self_pairs[p][1]; return GJK_SELF; }
-    p -= c_sc.n_self_pairs;
-    if (!moving) return -1;
-#pragma unroll 1
-    for (int o = 0; o < c_sc.n_obstacles; ++o) {
-        const int cnt = c_sc.obst_shape_cnt[o], tot = c_sc.n_mov_reward * cnt;
-        if (p < tot) { ia = sm.mov_reward[p / cnt]; ib = c_sc.obst_shape_off[o] + p % cnt; return GJK_MOVING; }
-        p -= tot;
-    }
-    return -1;
-}
-
 template <bool COUNT>
 __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) distance_plan_kernel(PlanArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -358,9 +339,8 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) distance_plan_kernel(
     const int kind = c_sc.n_obstacles > 0 ? c_sc.obst_kind[0] : SM_OBST_NONE;
     const double dt = xdiv(c_sc.ts, (double)S);
     const float cap = (float)c_sc.static_cap, query = (float)c_sc.moving_query;
-    const int n_fixed = c_sc.n_static_pairs + c_sc.n_self_pairs;
-    int n_pairs = n_fixed;
-    for (int o = 0; o < c_sc.n_obstacles; ++o) n_pairs += c_sc.n_mov_reward * c_sc.obst_shape_cnt[o];
+    const int n_fixed = c_sc.n_pairs_fixed, n_pairs = c_sc.n_pairs;
+    const uint32_t* pair_tab = L.bs->pair_tab;
     unsigned n_emit = 0;
 #pragma unroll 1
     for (int env = blockIdx.x * SM_WARPS_PER_BLOCK + warp; env < A.n; env += gridDim.x * SM_WARPS_PER_BLOCK) {
@@ -393,25 +373,22 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) distance_plan_kernel(
             A.res[(size_t)env * SM_RES_STRIDE + lane] = lane == 3 ? SM_RES_NO_CONTACT
                                                                    : fkey(lane == GJK_MOVING ? query + 0.002f : cap);
         __syncwarp();
-        // ---------------- pass 1: the best upper bound of each class (distance of the hull centroids)
+        // ---------------- pass 1 (lanes = pairs): the best upper bound of each class (distance of the hull centroids)
         const int np = moving ? n_pairs : n_fixed;
         float ub_s = cap, ub_e = cap, ub_m = query;
         unsigned best_m = 0xffffffffu;  // the lane's moving pair with the smallest centroid distance
 #pragma unroll 1
-        for (int base = 0; base < np; base += 32) {
-            int ia = 0, ib = 0;
-            const int cls = base + lane < np ? decode_pair(sm, base + lane, moving, ia, ib) : -1;
-            if (cls >= 0) {
-                const DevShape& SA = sm.shapes[ia];
-                const DevShape& SB = sm.shapes[ib];
-                const V3 ga = xf_apply(*frame_ptr(SA, W.fr, W.obx), SA.gx, SA.gy, SA.gz);
-                const V3 gb = xf_apply(*frame_ptr(SB, W.fr, W.obx), SB.gx, SB.gy, SB.gz);
-                const V3 e = ga - gb;
-                const float ub = sqrtf(dot(e, e)) * (1.0f + 1e-6f) + 1e-7f - SA.margin - SB.margin;
-                if (cls == GJK_STATIC) ub_s = fminf(ub_s, ub);
-                else if (cls == GJK_SELF) ub_e = fminf(ub_e, ub);
-                else if (ub < ub_m) { ub_m = ub; best_m = (unsigned)ia | ((unsigned)ib << 16); }
-            }
+        for (int p = lane; p < np; p += 32) {
+            const uint32_t e = pair_tab[p];
+            const int ia = (int)(e & 0xfffu), ib = (int)((e >> 12) & 0xfffu), cls = (int)(e >> 24);
+            const DevShape& SA = sm.shapes[ia];
+            const DevShape& SB = sm.shapes[ib];
+            const V3 g = xf_apply(*frame_ptr(SA, W.fr, W.obx), SA.gx, SA.gy, SA.gz) -
+                         xf_apply(*frame_ptr(SB, W.fr, W.obx), SB.gx, SB.gy, SB.gz);
+            const float ub = sqrtf(dot(g, g)) * (1.0f + 1e-6f) + 1e-7f - SA.margin - SB.margin;
+            if (cls == GJK_STATIC) ub_s = fminf(ub_s, ub);
+            else if (cls == GJK_SELF) ub_e = fminf(ub_e, ub);
+            else if (ub < ub_m) { ub_m = ub; best_m = (unsigned)ia | ((unsigned)ib << 16); }
         }
         ub_s = funkey(__reduce_min_sync(FULL, fkey(ub_s)));
         ub_e = funkey(__reduce_min_sync(FULL, fkey(ub_e)));
@@ -438,11 +415,13 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) distance_plan_kernel(
         // ---------------- pass 2: one item per pair whose sphere lower bound is below its class' upper bound
 #pragma unroll 1
         for (int base = 0; base < np; base += 32) {
-            int ia = 0, ib = 0;
-            const int cls = base + lane < np ? decode_pair(sm, base + lane, moving, ia, ib) : -1;
+            const int p = base + lane;
             bool emit = false;
             float thr = 0.0f;
-            if (cls >= 0) {
+            int ia = 0, ib = 0, cls = 0;
+            if (p < np) {
+                const uint32_t e = pair_tab[p];
+                ia = (int)(e & 0xfffu); ib = (int)((e >> 12) & 0xfffu); cls = (int)(e >> 24);
                 thr = cls == GJK_STATIC ? ub_s : cls == GJK_SELF ? ub_e : ub_m;
                 emit = pair_lower_bound(sm, ia, ib, W.fr, W.obx) <= thr;
             }
@@ -453,12 +432,9 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) distance_plan_kernel(
                 if (lane == 0) b0 = atomicAdd(A.item_count, total);
                 b0 = __shfl_sync(FULL, b0, 0);
                 if (b0 + total <= A.capacity) {
-                    if (emit) {
-                        const DevShape& SA = sm.shapes[ia];
-                        const DevShape& SB = sm.shapes[ib];
+                    if (emit)
                         write_item(A.items + b0 + __popc(em & ((1u << lane) - 1u)), env, ia, ib, cls, 0, thr,
-                                   *frame_ptr(SA, W.fr, W.obx), *frame_ptr(SB, W.fr, W.obx));
-                    }
+                                   *frame_ptr(sm.shapes[ia], W.fr, W.obx), *frame_ptr(sm.shapes[ib], W.fr, W.obx));
                 } else if (lane == 0) {
                     atomicAdd(A.overflow, total);
                 }
