@@ -96,8 +96,10 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_run(scene_name, envs_per_thread, steps, warmup, threads):
-    """Times the CPU oracle on `threads` host threads (ctypes releases the GIL); returns env-steps/s and a note."""
+def cpu_reference_run(scene_name, envs_per_thread, steps, warmup, threads, target_seconds=None):
+    """Times the CPU oracle on `threads` host threads (ctypes releases the GIL); returns env-steps/s and a note.
+    With target_seconds the number of timed steps is chosen from the duration of the warm-up steps so that the
+    sample is about that long (bounded sample of the same workload)."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import oracle
     from safemotionsrisk_b200.scene import Scene
@@ -125,14 +127,18 @@ def cpu_reference_run(scene_name, envs_per_thread, steps, warmup, threads):
         if done.any():  # episodes restart from the same pool of start states
             env.set_state(env._q0, np.zeros_like(env._q0), np.zeros_like(env._q0), env._ob0)
     with ThreadPoolExecutor(threads) as pool:
-        for _ in range(warmup):
+        tw = time.perf_counter()
+        for _ in range(max(1, warmup)):
             list(pool.map(one_step, shards))
+        tw = (time.perf_counter() - tw) / max(1, warmup)
+        if target_seconds is not None:
+            steps = int(min(max(2, target_seconds / max(tw, 1e-6)), 400))
         t0 = time.perf_counter()
         for _ in range(steps):
             list(pool.map(one_step, shards))
         dt = time.perf_counter() - t0
     total = threads * envs_per_thread * steps
-    return total / dt, dt, total
+    return total / dt, dt, total, steps
 
 
 def main():
@@ -158,9 +164,11 @@ def main():
         if rank != 0:
             return 0
         # bounded sample: small shards so that `steps` finish within minutes on the host cores
-        per_thread = 64 if args.scene.startswith("ball") else 2
+        per_thread = 1024 if args.scene.startswith("ball") else 64
+        # each of the K "steps" the driver asks for is one oracle step of the bounded sample; K is capped so that the
+        # run ends within minutes
         steps = max(1, min(args.steps, 40))
-        val, dt, total = cpu_reference_run(args.scene, per_thread, steps, min(args.warmup, 2), threads)
+        val, dt, total, steps = cpu_reference_run(args.scene, per_thread, steps, min(max(args.warmup, 1), 2), threads)
         sample = "{} host threads x {} envs x {} steps of the same scene ({} env-steps in {:.1f} s)".format(
             threads, per_thread, steps, total, dt)
         print(json.dumps({
@@ -231,6 +239,7 @@ def main():
     env.enable_counters(False)
     steps_counted = max(1, c["env_steps"])
     n_dot, n_iter = c["support_dots"] / steps_counted, c["gjk_iters"] / steps_counted
+    sc_nj = env.scene.struct.n_joints
     env.kernel_timing(True)
     env.kernel_times(reset=True)
     for i in range(min(args.steps, 50)):
@@ -240,8 +249,13 @@ def main():
     env.kernel_timing(False)
     ksum = sum(ktimes.values())
     # algorithmic flops per env-step attributed to each kernel
-    kflops = {"joint_kernel": 7 * 300 + 7 * 3 * 20, "joint_heavy_kernel": 0.0, "contact_plan_kernel": 24 * 600.0,
-              "distance_plan_kernel": 600.0, "gjk_kernel": 5.0 * n_dot + 100.0 * n_iter, "finish_kernel": 200.0}
+    # (joint kernels: 300 flops per joint range + 60 per joint interpolation; an iterative position solve
+    # is ~9 evaluations of the braking profile at ~120 flops)
+    hj, hs = c["heavy_joints"] / steps_counted, c["heavy_solves"] / steps_counted
+    kflops = {"joint_kernel": (sc_nj - hj) * 360.0, "joint_heavy_kernel": hj * 360.0 + hs * 9 * 120.0,
+              "contact_plan_kernel": 8 * 600.0, "distance_plan_kernel": 600.0,
+              "gjk_kernel": 5.0 * n_dot + 100.0 * n_iter, "finish_kernel": 200.0}
+    kbound = {"joint_kernel": "fp64", "joint_heavy_kernel": "fp64"}
     f_step = F_FIXED + 5.0 * n_dot + 100.0 * n_iter
     dom = max(ktimes, key=ktimes.get)
     kernel_ms = ktimes[dom]
@@ -249,6 +263,9 @@ def main():
     achieved_tflops = args.envs * kflops[dom] / (kernel_ms * 1e-3) / 1e12
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     peak_tflops = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12  # FP32 pipe at the SM clock seen under load
+    bound = kbound.get(dom, "fp32")
+    # FP64: 64 lanes per SM per clock on B200 (nominal 40 TFLOP/s class; not in MEASURED_PEAKS.json)
+    dom_peak = peak_tflops if bound == "fp32" else 148 * 64 * 2 * sm_mhz * 1e6 / 1e12
     sc = env.scene.struct
     bytes_step = 2 * (8 * 32 + 8 * 16 + 16 + 8) + 4 * sc.n_joints + 4 * sc.obs_size + 4 + 1 + 4 + 4 * 16
     peaks = {}
@@ -259,9 +276,11 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     uncull = {"space": 1.51e6, "space_bm": 1.71e6, "ball": 0.15e6, "ball_bm": 0.35e6}[args.scene]
-    roofline = {"bound": "fp32", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
-                "frac": achieved_tflops / peak_tflops, "traffic": None,
-                "peak_source": "148 SMs x 128 FP32 lanes x 2 x median SM clock under load ({} MHz)".format(sm_mhz),
+    roofline = {"bound": bound, "achieved": achieved_tflops, "peak": dom_peak, "unit": "TFLOP/s",
+                "frac": achieved_tflops / dom_peak, "traffic": None,
+                "peak_source": "148 SMs x {} lanes x 2 x median SM clock under load ({} MHz); nominal pipe width, "
+                               "MEASURED_PEAKS.json holds no FP32/FP64 vector peak".format(
+                                   128 if bound == "fp32" else 64, sm_mhz),
                 "kernel": dom, "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ksum,
                 "kernel_flops_per_env_step": kflops[dom],
                 "kernels_ms": ktimes, "flops_per_env_step": f_step, "support_dots_per_env_step": n_dot,
@@ -299,11 +318,11 @@ def main():
     # ---------------- CPU baseline beside it (rank 0, N = 1 only, bounded sample)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        per_thread = 64 if args.scene.startswith("ball") else 2
-        val, dt, total = cpu_reference_run(args.scene, per_thread, 20, 1, threads)
+        per_thread = 1024 if args.scene.startswith("ball") else 64
+        val, dt, total, csteps = cpu_reference_run(args.scene, per_thread, 20, 1, threads, target_seconds=15.0)
         cpu = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "{} host threads x {} envs x 20 steps of the same scene ({} env-steps in {:.1f} s)".format(
-                   threads, per_thread, total, dt),
+               "sample": "{} host threads x {} envs x {} steps of the same scene ({} env-steps in {:.1f} s)".format(
+                   threads, per_thread, csteps, total, dt),
                "note": "oracle restatement -- NOT the PyBullet reference (not installable here)"}
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

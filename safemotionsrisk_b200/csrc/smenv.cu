@@ -99,12 +99,44 @@ static void build_lut_uncached(const float4* v, int n, std::vector<uint32_t>& ou
     }
 }
 
+// support-width table of one hull about its bounding-sphere centre (layout: smenv_device.cuh), same cube-map cells and
+// sampling as the direction tables; the slack covers directions between the samples
+static void build_hwidth(const float4* v, int n, const float* c, float radius, std::vector<float>& out) {
+    const int R = SM_LUT_RES, SUB = 17;
+    const double spacing = 2.0 / R / (SUB - 1);
+    const double slack = (double)radius * spacing * 0.7072 * 1.05 + 1e-6;
+    for (int face = 0; face < 6; ++face) {
+        const int ax = face / 2, a = (ax + 1) % 3, b = (ax + 2) % 3;
+        const double sgn = (face % 2 == 0) ? 1.0 : -1.0;
+        for (int iu = 0; iu < R; ++iu)
+            for (int iw = 0; iw < R; ++iw) {
+                double hmax = 0.0;
+                for (int su = 0; su < SUB; ++su)
+                    for (int sw = 0; sw < SUB; ++sw) {
+                        double d[3];
+                        d[ax] = sgn;
+                        d[a] = -1.0 + 2.0 * (iu + (double)su / (SUB - 1)) / R;
+                        d[b] = -1.0 + 2.0 * (iw + (double)sw / (SUB - 1)) / R;
+                        const double nrm = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                        double mx = -1e300;
+                        for (int i = 0; i < n; ++i) {
+                            const double s = ((v[i].x - c[0]) * d[0] + (v[i].y - c[1]) * d[1] + (v[i].z - c[2]) * d[2]) / nrm;
+                            if (s > mx) mx = s;
+                        }
+                        if (mx > hmax) hmax = mx;
+                    }
+                out.push_back((float)((hmax + slack) * (1.0 + 1e-6)));
+            }
+    }
+}
+
 struct SmEnv {
     int n = 0, device = 0;
     uint64_t seed = 0;
     DevScene host_scene;  // device pointers inside
     float4* d_verts = nullptr;
     uint32_t* d_lut = nullptr;
+    float* d_hwidth = nullptr;
     float4* d_ppos[SM_MAX_OBSTACLES] = {nullptr, nullptr};
     float4* d_pquat[SM_MAX_OBSTACLES] = {nullptr, nullptr};
     double* d_plocal = nullptr;
@@ -204,6 +236,7 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     for (int i = 0; i < sc->n_verts; ++i)
         verts[i] = make_float4((float)sc->verts[3 * i], (float)sc->verts[3 * i + 1], (float)sc->verts[3 * i + 2], 0.f);
     std::vector<uint32_t> lut;
+    std::vector<float> hwidth;
     for (int s = 0; s < sc->n_shapes; ++s) {
         const SmShape& h = sc->shapes[s];
         DevShape& g = d.shapes[s];
@@ -223,6 +256,11 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
         double gs[3] = {0, 0, 0};
         for (int i = h.vert_off; i < h.vert_off + h.vert_cnt; ++i) { gs[0] += verts[i].x; gs[1] += verts[i].y; gs[2] += verts[i].z; }
         g.gx = (float)(gs[0] / h.vert_cnt); g.gy = (float)(gs[1] / h.vert_cnt); g.gz = (float)(gs[2] / h.vert_cnt);
+        g.hw = (int)hwidth.size();
+        {
+            const float cc[3] = {g.cx, g.cy, g.cz};
+            build_hwidth(verts.data() + h.vert_off, h.vert_cnt, cc, g.radius, hwidth);
+        }
         g.lut = -1;
         if (h.vert_cnt >= SM_LUT_MIN_VERTS && h.vert_cnt <= 255) {
             g.lut = (int)lut.size();
@@ -330,6 +368,8 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     if (lut.empty()) lut.push_back(0u);
     if ((rc = upload(&env->d_lut, lut))) { delete env; return rc; }
     d.lut = env->d_lut;
+    if ((rc = upload(&env->d_hwidth, hwidth))) { delete env; return rc; }
+    d.hwidth = env->d_hwidth;
     d.n_lut_words = (int)lut.size();
     for (int o = 0; o < sc->n_obstacles; ++o) {
         if (sc->obst_kind[o] != SM_OBST_PLANET) continue;
@@ -409,7 +449,7 @@ extern "C" int smenv_destroy(SmEnv* env) {
     if (!env) return SM_OK;
     cudaSetDevice(env->device);
     if (g_active == env) g_active = nullptr;
-    cudaFree(env->d_verts); cudaFree(env->d_lut); cudaFree(env->d_plocal); cudaFree(env->d_start_pool); cudaFree(env->d_ball_pool);
+    cudaFree(env->d_verts); cudaFree(env->d_lut); cudaFree(env->d_hwidth); cudaFree(env->d_plocal); cudaFree(env->d_start_pool); cudaFree(env->d_ball_pool);
     cudaFree(env->d_counters); cudaFree(env->d_scratch); cudaFree(env->d_worklist); cudaFree(env->d_heavy); cudaFree(env->d_cwork); cudaFree(env->d_tasks); cudaFree(env->d_hpar); cudaFree(env->d_items); cudaFree(env->d_res);
     if (env->h_flag) cudaFreeHost(env->h_flag);
     for (int i = 0; i <= SM_K_COUNT; ++i) if (env->ev[i]) cudaEventDestroy(env->ev[i]);

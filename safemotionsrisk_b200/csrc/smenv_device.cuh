@@ -27,6 +27,7 @@ struct DevShape {
     float bmin[3], bmax[3];  // axis-aligned box of the core vertices in frame coordinates
     float gx, gy, gz;        // centroid of the vertices: a point inside the hull (upper bounds of pair distances)
     int lut;                 // word offset of the shape's support-direction table in DevScene.lut, -1 = none
+    int hw;                  // offset of the shape's support-width table in DevScene.hwidth (6 R R floats)
 };
 
 // Support-direction table ("LUT") of a hull: the unit sphere of directions is cut into 6 * SM_LUT_RES^2 cube-map
@@ -36,7 +37,9 @@ struct DevShape {
 //   lists         : candidate vertex indices (local to the shape), one byte each, four per word, padded to a word
 //                   boundary by repeating the last candidate
 #define SM_MAX_PLAN_PAIRS 512 /* entries of the per-env pair table of the distance planning */
+#ifndef SM_LUT_RES
 #define SM_LUT_RES 8
+#endif
 #define SM_LUT_MIN_VERTS 33 /* smaller hulls are scanned directly */
 
 __host__ __device__ __forceinline__ int lut_cell(float dx, float dy, float dz) {
@@ -101,6 +104,10 @@ struct DevScene {
     // moving obstacle; entry = shape A | shape B << 12 | class << 24
     int n_pairs_fixed, n_pairs;
     uint32_t pair_tab[SM_MAX_PLAN_PAIRS];
+    // support-width tables: per shape and cube-map cell an upper bound of h(d) = max_v (v - centre) . d over the unit
+    // directions d of the cell.  centre distance - h_A(d) - h_B(-d) along the line of centres is a lower bound of the
+    // pair distance that is far tighter than bounding spheres for elongated hulls (planning kernels).
+    const float* hwidth;  // device
     const uint32_t* lut;  // device, n_lut_words (support-direction tables of all shapes that have one)
     int n_lut_words;
 };

@@ -49,6 +49,18 @@ __device__ __forceinline__ void rel_pose(const Xf& TA, const Xf& TB, float* R, f
     }
 }
 
+// Lower bound of the distance between shapes A and B (minus both margins) from the support-width tables: separation
+// along the line between the bounding-sphere centres.
+__device__ __forceinline__ float axis_lower_bound(const DevShape& SA, const DevShape& SB, const Xf& TA, const Xf& TB) {
+    const V3 d = xf_apply(TB, SB.cx, SB.cy, SB.cz) - xf_apply(TA, SA.cx, SA.cy, SA.cz);  // A towards B
+    const float dist = sqrtf(dot(d, d));
+    if (!(dist > 1e-9f)) return -FLT_MAX;
+    const V3 da = xf_rot_t(TA, d), db = xf_rot_t(TB, mk(-d.x, -d.y, -d.z));
+    const float ha = __ldg(c_sc.hwidth + SA.hw + lut_cell(da.x, da.y, da.z));
+    const float hb = __ldg(c_sc.hwidth + SB.hw + lut_cell(db.x, db.y, db.z));
+    return dist * (1.0f - 1e-6f) - ha - hb - SA.margin - SB.margin;
+}
+
 __device__ __forceinline__ void write_item(GjkItem* dst, int env, int ia, int ib, int cls, int sub, float thr,
                                            const Xf& TA, const Xf& TB) {
     float R[9], t[3];
@@ -243,7 +255,7 @@ __device__ __forceinline__ int contact_scan(const SceneSmem& sm, const float* __
                     const DevShape& ps = sm.shapes[off + s];
                     const V3 e = c - xf_apply(TB, ps.cx, ps.cy, ps.cz);
                     const float l2 = rr + ps.radius + ps.margin + th;
-                    if (dot(e, e) <= l2 * l2) {
+                    if (dot(e, e) <= l2 * l2 && axis_lower_bound(sh, ps, F, TB) <= th) {
                         if (write) write_item(out + count, env, ia, off + s, GJK_CONTACT, sub, th, F, TB);
                         ++count;
                     }
@@ -423,7 +435,9 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) distance_plan_kernel(
                 const uint32_t e = pair_tab[p];
                 ia = (int)(e & 0xfffu); ib = (int)((e >> 12) & 0xfffu); cls = (int)(e >> 24);
                 thr = cls == GJK_STATIC ? ub_s : cls == GJK_SELF ? ub_e : ub_m;
-                emit = pair_lower_bound(sm, ia, ib, W.fr, W.obx) <= thr;
+                emit = pair_lower_bound(sm, ia, ib, W.fr, W.obx) <= thr &&
+                       axis_lower_bound(sm.shapes[ia], sm.shapes[ib], *frame_ptr(sm.shapes[ia], W.fr, W.obx),
+                                        *frame_ptr(sm.shapes[ib], W.fr, W.obx)) <= thr;
             }
             const unsigned em = __ballot_sync(FULL, emit);
             if (em) {
