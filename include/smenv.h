@@ -207,7 +207,7 @@ typedef struct SmCounters {
     unsigned long long support_dots;   /* vertex . direction products evaluated in support searches */
     unsigned long long distance_items; /* pairs the distance planning could not cull (emitted items) */
     unsigned long long env_steps;
-    unsigned long long contact_envs;   /* envs the coarse contact phase passed on to the fine planning */
+    unsigned long long contact_envs;   /* spans of sub-steps the coarse contact phase passed on to the fine planning */
     unsigned long long contact_items;  /* (sub-step, pair) contact candidates emitted by the contact planning */
     unsigned long long reserved;
     unsigned long long heavy_joints;   /* (env, joint) instances that went through joint_heavy_kernel */

@@ -159,7 +159,7 @@ struct SmEnv {
     double kernel_ms[SM_K_COUNT] = {};
     int timed_steps = 0;
     int* d_heavy = nullptr;      // [0] = count, [1..8n] = (env, joint) instances deferred to joint_heavy_kernel
-    int* d_cwork = nullptr;      // [0] = count, [1..n] = envs the coarse contact phase could not clear
+    int* d_cwork = nullptr;      // [0] = count, [1..8n] = spans (env * 8 + span) the coarse contact phase could not clear
     int* d_tasks = nullptr;      // [0] = count, [1..16n] = position bounds to solve (joint_solve_kernel)
     double* d_hpar = nullptr;    // [8n][SM_HPAR] hand-over records of the deferred joints
     bool count = false;
@@ -413,8 +413,8 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     CU(cudaMalloc((void**)&env->d_tasks, ((size_t)num_envs * 16 + 1) * sizeof(int)));
     CU(cudaMemset(env->d_tasks, 0, ((size_t)num_envs * 16 + 1) * sizeof(int)));
     CU(cudaMalloc((void**)&env->d_hpar, (size_t)num_envs * 8 * SM_HPAR * sizeof(double)));
-    CU(cudaMalloc((void**)&env->d_cwork, ((size_t)num_envs + 1) * sizeof(int)));
-    CU(cudaMemset(env->d_cwork, 0, ((size_t)num_envs + 1) * sizeof(int)));
+    CU(cudaMalloc((void**)&env->d_cwork, ((size_t)num_envs * SM_COARSE_LANES + 1) * sizeof(int)));
+    CU(cudaMemset(env->d_cwork, 0, ((size_t)num_envs * SM_COARSE_LANES + 1) * sizeof(int)));
     CU(cudaMalloc((void**)&env->d_heavy, ((size_t)num_envs * 8 + 1) * sizeof(int)));
     CU(cudaMemset(env->d_heavy, 0, ((size_t)num_envs * 8 + 1) * sizeof(int)));
     CU(cudaMalloc((void**)&env->d_counters, 16 * sizeof(unsigned long long)));

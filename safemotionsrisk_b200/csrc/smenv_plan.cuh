@@ -25,7 +25,7 @@ struct PlanArgs {
     const double* kin;       // kinematic records to plan for (buf.kin in the step, the caller's array in the hook)
     const double* obst;      // obstacle records
     int advance;             // 1: obstacle poses at the end of the step about to be finished; 0: poses as recorded
-    int* cwork;              // [0] = count, [1..] = envs whose sub-step contacts need the fine planning
+    int* cwork;              // [0] = count, [1..] = spans (env * 8 + span) whose contacts need the fine planning
     unsigned long long* counters;
 };
 
@@ -193,9 +193,11 @@ __global__ void __launch_bounds__(256) contact_coarse_kernel(PlanArgs A) {
                     const float rr = sh.radius + sh.margin + infl;
 #pragma unroll
                     for (int o = 0; o < 2; ++o) {
+                        if (o >= c_sc.n_obstacles) continue;  // uniform: skips the unrolled body
                         const float lim = rr + c_sc.obst_radius[o] + c_sc.obst_center_norm[o] + sm.contact_thresh[o][slot];
 #pragma unroll
                         for (int i = 0; i < SM_COARSE_SPAN; ++i) {
+                            if (i >= span) continue;          // uniform
                             if (!((valid >> (o * SM_COARSE_SPAN + i)) & 1u)) continue;
                             const V3 e = ctr - oc[o][i];
                             if (dot(e, e) <= lim * lim) flag = true;
@@ -205,17 +207,14 @@ __global__ void __launch_bounds__(256) contact_coarse_kernel(PlanArgs A) {
             }
         }
     }
-    // one list entry per env with a flagged span (the 8 lanes of an env sit in one warp)
+    // one list entry per span that could not be cleared: env * SM_COARSE_LANES + span
     const unsigned fm = __ballot_sync(FULL, flag);
-    const unsigned grp = (fm >> (lane & ~(SM_COARSE_LANES - 1))) & ((1u << SM_COARSE_LANES) - 1u);
-    const bool lead = grp != 0 && (lane & (SM_COARSE_LANES - 1)) == 0;
-    const unsigned lm = __ballot_sync(FULL, lead);
-    if (lm) {
+    if (fm) {
         int base = 0;
-        if (lane == __ffs(lm) - 1) base = atomicAdd(A.cwork, __popc(lm));
-        base = __shfl_sync(FULL, base, __ffs(lm) - 1);
-        if (lead) A.cwork[1 + base + __popc(lm & ((1u << lane) - 1u))] = env;
-        if (COUNT && A.counters && lane == __ffs(lm) - 1) atomicAdd(&A.counters[5], (unsigned long long)__popc(lm));
+        if (lane == __ffs(fm) - 1) base = atomicAdd(A.cwork, __popc(fm));
+        base = __shfl_sync(FULL, base, __ffs(fm) - 1);
+        if (flag) A.cwork[1 + base + __popc(fm & ((1u << lane) - 1u))] = t;
+        if (COUNT && A.counters && lane == __ffs(fm) - 1) atomicAdd(&A.counters[5], (unsigned long long)__popc(fm));
     }
 }
 
@@ -223,10 +222,11 @@ __global__ void __launch_bounds__(256) contact_coarse_kernel(PlanArgs A) {
 // contacts of one sub-step (one lane): serial FK chain of the tracked pose; every contact shape against the obstacle
 // bounding spheres and then the spheres of the obstacle's convex parts, all inflated by the contact thresholds.
 // Poses are those Bullet's collision detection of that sub-step sees: tracked robot pose before integration, obstacle
-// pose of the previous update.  write == false counts the candidates, write == true emits them.
+// pose of the previous update.  A pair that neither the spheres nor the separating-axis bound
+// can clear becomes a contact item (appended with one atomic per item: they are rare, about one per env-step).
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int contact_scan(const SceneSmem& sm, const float* __restrict__ qrow, const Xf& T0, const Xf& T1,
-                                         int use_mask, bool write, GjkItem* out, int env, int sub) {
+                                            int use_mask, const PlanArgs& A, int env, int sub) {
     int count = 0;
     const V3 oc0 = xf_apply(T0, c_sc.obst_center[0][0], c_sc.obst_center[0][1], c_sc.obst_center[0][2]);
     const V3 oc1 = xf_apply(T1, c_sc.obst_center[1][0], c_sc.obst_center[1][1], c_sc.obst_center[1][2]);
@@ -250,13 +250,16 @@ __device__ __forceinline__ int contact_scan(const SceneSmem& sm, const float* __
                 if (dot(dd, dd) > lim * lim) continue;
                 const Xf& TB = o == 0 ? T0 : T1;
                 const int off = c_sc.obst_shape_off[o], cnt = c_sc.obst_shape_cnt[o];
+                const V3 cl = xf_rot_t(TB, mk(c.x - TB.t[0], c.y - TB.t[1], c.z - TB.t[2]));  // in the obstacle frame
 #pragma unroll 1
                 for (int s = 0; s < cnt; ++s) {
                     const DevShape& ps = sm.shapes[off + s];
-                    const V3 e = c - xf_apply(TB, ps.cx, ps.cy, ps.cz);
+                    const V3 e = mk(cl.x - ps.cx, cl.y - ps.cy, cl.z - ps.cz);
                     const float l2 = rr + ps.radius + ps.margin + th;
                     if (dot(e, e) <= l2 * l2 && axis_lower_bound(sh, ps, F, TB) <= th) {
-                        if (write) write_item(out + count, env, ia, off + s, GJK_CONTACT, sub, th, F, TB);
+                        const int idx = atomicAdd(A.item_count, 1);
+                        if (idx < A.capacity) write_item(A.items + idx, env, ia, off + s, GJK_CONTACT, sub, th, F, TB);
+                        else atomicAdd(A.overflow, 1);
                         ++count;
                     }
                 }
@@ -266,78 +269,64 @@ __device__ __forceinline__ int contact_scan(const SceneSmem& sm, const float* __
     return count;
 }
 
+// Fine contact planning over the spans the coarse phase listed: four lanes per span (one per sub-step of the span),
+// eight spans per warp.
 template <bool COUNT>
 __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) contact_plan_kernel(PlanArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n_work = A.cwork[0];
-    if (blockIdx.x * SM_WARPS_PER_BLOCK >= n_work) return;  // nothing for this block: skip the staging
+    const int n_units = A.cwork[0];
+    if (blockIdx.x * SM_WARPS_PER_BLOCK * 8 >= n_units) return;  // nothing for this block: skip the staging
     SmemLayout L = block_prologue(smem_raw, false);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const SceneSmem& sm = L.bs->scene;
-    WarpScratch& W = L.scratch[warp];
     const int S = c_sc.substeps, stride = c_sc.contact_stride;
+    const int span = (S + SM_COARSE_LANES - 1) / SM_COARSE_LANES;
     const int kind = c_sc.n_obstacles > 0 ? c_sc.obst_kind[0] : SM_OBST_NONE;
     const double dt = xdiv(c_sc.ts, (double)S);
     unsigned n_flag = 0;
 #pragma unroll 1
-    for (int w = blockIdx.x * SM_WARPS_PER_BLOCK + warp; w < n_work; w += gridDim.x * SM_WARPS_PER_BLOCK) {
-        const int env = A.cwork[1 + w];
+    for (int ub = (blockIdx.x * SM_WARPS_PER_BLOCK + warp) * 8; ub < n_units; ub += gridDim.x * SM_WARPS_PER_BLOCK * 8) {
+        const int u = ub + (lane >> 2), i = lane & 3;
+        if (u >= n_units || i >= span) continue;
+        const int unit = A.cwork[1 + u];
+        const int env = unit / SM_COARSE_LANES, k = (unit % SM_COARSE_LANES) * span + i;  // 0-based sub-step
+        if (k >= S || ((k + 1) % stride) != 0) continue;
         const float* scr = A.scratch + (size_t)env * SM_SCRATCH_FLOATS;
-        if (lane < SM_OBST_STRIDE) W.ob[lane] = A.obst[(size_t)env * SM_OBST_STRIDE + lane];
-        __syncwarp();
-        const int idx0 = (int)W.ob[SM_OB_INDEX];
+        const double* ob = A.obst + (size_t)env * SM_OBST_STRIDE;
+        if (ob[SM_OB_LATCH] != 0.0) continue;
+        const int idx0 = (int)ob[SM_OB_INDEX];
         bool test = false;
         int use_mask = 0;
         Xf T0, T1;
         xf_identity(T0);
         xf_identity(T1);
-        if (stride > 0 && W.ob[SM_OB_LATCH] == 0.0 && lane < S && ((lane + 1) % stride == 0)) {
-            if (kind == SM_OBST_PLANET && c_sc.terminate_moving) {
-                planet_pose(0, (idx0 + lane) % c_sc.planet_steps, T0);
-                use_mask = 1;
-                if (c_sc.n_obstacles > 1) { planet_pose(1, (idx0 + lane) % c_sc.planet_steps, T1); use_mask = 3; }
-                test = true;
-            } else if (kind == SM_OBST_BALL && W.ob[SM_OB_BALL_ACTIVE] != 0.0) {
-                const int sub = lane + 1, k_end = ball_k_end(W.ob);
-                if (sub <= k_end - 1) {
-                    // the test of sub-step `sub` happens after the ball moved to counter idx0+sub: the active area
-                    // uses the new position (ctlp.py:2851-2854), the manifold the previous one
-                    const double ball_t = W.ob[SM_OB_BALL_T];
-                    const double tn = ball_t + (double)sub * dt;
-                    const double px = W.ob[SM_OB_BALL_P0] + W.ob[SM_OB_BALL_V0] * tn;
-                    const double py = W.ob[SM_OB_BALL_P0 + 1] + W.ob[SM_OB_BALL_V0 + 1] * tn;
-                    if (sqrt(px * px + py * py) < c_sc.ball_active_xy) {
-                        ball_pose(W.ob, ball_t + (double)lane * dt, T0);
-                        use_mask = 1;
-                        test = true;
-                    }
+        if (kind == SM_OBST_PLANET && c_sc.terminate_moving) {
+            planet_pose(0, (idx0 + k) % c_sc.planet_steps, T0);
+            use_mask = 1;
+            if (c_sc.n_obstacles > 1) { planet_pose(1, (idx0 + k) % c_sc.planet_steps, T1); use_mask = 3; }
+            test = true;
+        } else if (kind == SM_OBST_BALL && ob[SM_OB_BALL_ACTIVE] != 0.0) {
+            const int sub = k + 1, k_end = ball_k_end(ob);
+            if (sub <= k_end - 1) {
+                // the test of sub-step `sub` happens after the ball moved to counter idx0+sub: the active area
+                // uses the new position (ctlp.py:2851-2854), the manifold the previous one
+                const double ball_t = ob[SM_OB_BALL_T];
+                const double tn = ball_t + (double)sub * dt;
+                const double px = ob[SM_OB_BALL_P0] + ob[SM_OB_BALL_V0] * tn;
+                const double py = ob[SM_OB_BALL_P0 + 1] + ob[SM_OB_BALL_V0 + 1] * tn;
+                if (sqrt(px * px + py * py) < c_sc.ball_active_xy) {
+                    ball_pose(ob, ball_t + (double)k * dt, T0);
+                    use_mask = 1;
+                    test = true;
                 }
             }
         }
-        // pass 0 counts the candidates of every sub-step, pass 1 (only if there are any) writes them
-        int cnt = 0, total = 0, off = 0, base = 0;
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-            if (pass == 1) {
-                off = warp_exclusive_sum(cnt, lane, total);
-                if (total == 0) break;
-                if (lane == 0) base = atomicAdd(A.item_count, total);
-                base = __shfl_sync(FULL, base, 0);
-                if (COUNT) n_flag += (unsigned)total;
-                if (base + total > A.capacity) {
-                    if (lane == 0) atomicAdd(A.overflow, total);
-                    break;
-                }
-            }
-            if (test && (pass == 0 || cnt > 0)) {
-                const int c = contact_scan(sm, scr + lane * SM_MAX_JOINTS, T0, T1, use_mask, pass == 1,
-                                           A.items + base + off, env, lane + 1);
-                if (pass == 0) cnt = c;
-            }
+        if (test) {
+            const int c = contact_scan(sm, scr + k * SM_MAX_JOINTS, T0, T1, use_mask, A, env, k + 1);
+            if (COUNT) n_flag += (unsigned)c;
         }
-        __syncwarp();
     }
-    if (COUNT && A.counters && lane == 0 && n_flag) atomicAdd(&A.counters[6], (unsigned long long)n_flag);
+    if (COUNT && A.counters && n_flag) atomicAdd(&A.counters[6], (unsigned long long)n_flag);
 }
 
 template <bool COUNT>
