@@ -1,5 +1,6 @@
 // smenv.cu -- C ABI of libsmenv.so (include/smenv.h): scene upload, pools, reset, step.  sm_100a only, no CPU path.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <algorithm>
@@ -402,6 +403,10 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     {   // item buffer: the mean is a few dozen items per env-step; sized generously, overflow is reported loudly
         long long cap = (long long)num_envs * 192;
         if (cap < 65536) cap = 65536;
+        if (const char* ov = getenv("SMENV_ITEM_CAPACITY")) {  // tests shrink the buffer to exercise the overflow report
+            const long long v = atoll(ov);
+            if (v > 0) cap = v;
+        }
         env->item_capacity = (int)(cap > 0x7fffffffLL / 2 ? 0x7fffffffLL / 2 : cap);
         CU(cudaMalloc((void**)&env->d_items, (size_t)env->item_capacity * sizeof(GjkItem)));
         CU(cudaMalloc((void**)&env->d_res, (size_t)num_envs * SM_RES_STRIDE * sizeof(unsigned)));

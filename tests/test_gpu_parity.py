@@ -13,7 +13,7 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 from oracle import oracle  # noqa: E402
-from safemotionsrisk_b200 import abi, ball_backup_config, space_backup_config  # noqa: E402
+from safemotionsrisk_b200 import abi, ball_backup_config, cabi, space_backup_config  # noqa: E402
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CONFIGS = {"space": lambda **k: space_backup_config(**k), "ball": lambda **k: ball_backup_config(**k),
@@ -341,4 +341,49 @@ def test_bad_arguments_raise():
     env = make_env("space", 8, fill_pools=False)
     with pytest.raises(cabi.SmEnvError):
         env.reset()                      # pools not filled
+    env.close()
+
+
+def test_item_buffer_overflow_is_reported_loudly(monkeypatch):
+    """The GJK work-item buffer is finite; if a step needs more items than fit, the next call must fail instead of
+    returning distances computed from a truncated list."""
+    monkeypatch.setenv("SMENV_ITEM_CAPACITY", "4")
+    env = make_env("space", 256, auto_reset=True)
+    env.reset()
+    env.step_random()
+    torch.cuda.synchronize()
+    with pytest.raises(cabi.SmEnvError, match="overflow"):
+        for _ in range(3):
+            env.step_random()
+            torch.cuda.synchronize()
+    env.close()
+
+
+def test_kernel_timing_mode_reports_every_kernel():
+    env = make_env("ball", 1024, auto_reset=True)
+    env.reset()
+    env.kernel_timing(True)
+    for _ in range(3):
+        env.step_random()
+    times, steps = env.kernel_times(reset=True)
+    env.kernel_timing(False)
+    assert steps == 3 and set(times) == set(env.KERNELS)
+    assert all(t > 0.0 for t in times.values())
+    env.close()
+
+
+def test_counters_account_for_the_planned_pairs():
+    env = make_env("space", 2048, auto_reset=True)
+    env.reset()
+    env.enable_counters(True)
+    env.counters(reset=True)
+    for _ in range(4):
+        env.step_random()
+    c = env.counters()
+    env.enable_counters(False)
+    assert c["env_steps"] == 4 * 2048
+    # every planned item is run exactly once by the GJK kernel
+    assert c["gjk_calls"] == c["distance_items"] + c["contact_items"]
+    assert c["gjk_iters"] >= c["gjk_calls"] and c["support_dots"] > 0
+    assert 0 < c["heavy_joints"] <= 7 * c["env_steps"] and c["heavy_solves"] <= 2 * c["heavy_joints"]
     env.close()
