@@ -638,7 +638,7 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
         int hb = (env->n * 8 + SM_HEAVY_THREADS - 1) / SM_HEAVY_THREADS;
         if (hb > 8 * env->sms) hb = 8 * env->sms;
         joint_first_kernel<<<hb, SM_HEAVY_THREADS, 0, stream>>>(JA);
-        joint_solve_kernel<<<hb, SM_HEAVY_THREADS, 0, stream>>>(JA);
+        joint_solve_kernel<<<16 * env->sms, SM_HEAVY_THREADS, 0, stream>>>(JA);  // warps take chunks of the task list
         joint_final_kernel<<<hb, SM_HEAVY_THREADS, 0, stream>>>(JA);
     }
     env->launches += 4;

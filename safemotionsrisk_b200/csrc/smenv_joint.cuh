@@ -170,21 +170,130 @@ __global__ void __launch_bounds__(SM_HEAVY_THREADS) joint_first_kernel(JointArgs
     if (A.counters && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&A.counters[8], (unsigned long long)n_heavy);
 }
 
+// The solves are nested loops of very different lengths (up to 40 regula-falsi steps, each simulating a braking
+// profile of 1..16 intervals), and a warp pays for the union of its lanes' paths: run task by task, a warp averaged
+// 6.7 active lanes.  Here the nest is flattened into a state machine whose single loop body is ONE interval of the
+// braking profile (the body of pos_peak), executed by all lanes in lockstep; a lane whose profile ends steps its
+// regula falsi, a lane whose task ends takes the next task of the warp's chunk.  The operations of every task are
+// exactly those of pos_upper_rest / pos_peak, in the same order (bit-identical results).
+#ifndef SM_SOLVE_CHUNK_MIN
+#define SM_SOLVE_CHUNK_MIN 32
+#endif
 __global__ void __launch_bounds__(SM_HEAVY_THREADS) joint_solve_kernel(JointArgs A) {
     const int n_task = A.tasks[0];
     const double ts = c_sc.ts;
+    const int lane = threadIdx.x & 31;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    int chunk = (n_task + n_warps - 1) / n_warps;
+    if (chunk < SM_SOLVE_CHUNK_MIN) chunk = SM_SOLVE_CHUNK_MIN;  // enough tasks per warp to keep its lanes refilled
+    int cursor = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * chunk;
+    const int end = cursor + chunk < n_task ? cursor + chunk : n_task;
+    // per-lane task state
+    bool busy = false;
+    double* out = nullptr;
+    double P0 = 0, V0 = 0, A0 = 0, pmax = 0, lo = 0, J = 1, Am = 1;   // the task (mirrored for a lower bound)
+    double xl = 0, xr = 0, fl = 0, fr = 0, x = 0;                      // regula falsi (Illinois)
+    int side = 0, iit = 0, phase = 0;                                  // phase 0: evaluating f(lo)
+    double p = 0, v = 0, a = 0, an = 0, best = 0;                      // braking profile under evaluation
+    int pit = 0;
 #pragma unroll 1
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_task; k += gridDim.x * blockDim.x) {
-        const int task = A.tasks[1 + k], i = task >> 1, side = task & 1;
-        const int t = A.heavy[1 + i];
-        const int env = t >> 3, j = t & 7;
-        const double* kin = A.buf.kin + (size_t)env * SM_KIN_STRIDE;
-        const double q = kin[j], v = kin[8 + j], a = kin[16 + j];
-        double* hp = A.hpar + (size_t)i * SM_HPAR;
-        const double lo = hp[0], hi = hp[1];
-        const double J = c_sc.jerk_max[j], Am = c_sc.acc_max[j];
-        hp[5 + side] = side == 0 ? pos_upper_rest(q, v, a, c_sc.pos_hi[j], lo, hi, J, Am, ts, hp[3])
-                                 : pos_upper_rest(-q, -v, -a, -c_sc.pos_lo[j], -hi, -lo, J, Am, ts, hp[4]);
+    while (true) {
+        const unsigned idle = __ballot_sync(FULL, !busy);
+        if (cursor < end && (idle == FULL || __popc(idle) >= 8)) {
+            const int my = cursor + __popc(idle & ((1u << lane) - 1u));
+            cursor += __popc(idle);
+            if (!busy && my < end) {
+                const int task = A.tasks[1 + my], i = task >> 1, sd = task & 1;
+                const int t = A.heavy[1 + i];
+                const int env = t >> 3, j = t & 7;
+                const double* kin = A.buf.kin + (size_t)env * SM_KIN_STRIDE;
+                double* hp = A.hpar + (size_t)i * SM_HPAR;
+                const double sg = sd == 0 ? 1.0 : -1.0;
+                P0 = sg * kin[j]; V0 = sg * kin[8 + j]; A0 = sg * kin[16 + j];
+                pmax = sd == 0 ? c_sc.pos_hi[j] : -c_sc.pos_lo[j];
+                lo = sd == 0 ? hp[0] : -hp[1];
+                xr = sd == 0 ? hp[1] : -hp[0];        // hi
+                fr = hp[3 + sd];
+                J = c_sc.jerk_max[j]; Am = c_sc.acc_max[j];
+                out = hp + 5 + sd;
+                phase = 0; x = lo;
+                p = P0; v = V0; a = A0; an = x; best = P0; pit = 0;
+                busy = true;
+            }
+        }
+        if (!__any_sync(FULL, busy)) break;
+        if (!busy) continue;
+        // ---------------- one interval of the braking profile (body of pos_peak)
+        bool eval_done = false;
+        {
+            const double j = xdiv(xsub(an, a), ts);
+            double tau = -1.0;
+            if (j == 0.0) {
+                if (a < 0.0 && v > 0.0) tau = xdiv(-v, a);
+            } else {
+                const double disc = xsub(xmul(a, a), xmul(xmul(2.0, j), v));
+                if (disc >= 0.0) {
+                    const double s = xsqrt(disc);
+                    if (a <= 0.0) {
+                        if (xsub(s, a) > 0.0) tau = xdiv(xmul(2.0, v), xsub(s, a));
+                    } else {
+                        tau = xdiv(xsub(-a, s), j);
+                    }
+                }
+            }
+            if (tau > 0.0 && tau <= ts) {
+                const double pk = xadd(xadd(xadd(p, xmul(v, tau)), xmul(xmul(xmul(0.5, a), tau), tau)),
+                                       xdiv(xmul(xmul(xmul(j, tau), tau), tau), 6.0));
+                if (pk > best) best = pk;
+            }
+            const double pn = xadd(xadd(p, xmul(v, ts)), xmul(xmul(xadd(xdiv(a, 3.0), xdiv(an, 6.0)), ts), ts));
+            const double vn = xadd(v, xmul(xmul(xadd(a, an), ts), 0.5));
+            p = pn; v = vn; a = an;
+            if (p > best) best = p;
+            if (a <= -Am) {
+                if (v > 0.0) {
+                    const double pk = xadd(p, xdiv(xmul(v, v), xmul(2.0, Am)));
+                    if (pk > best) best = pk;
+                }
+                eval_done = true;
+            } else if (v <= 0.0 && a <= 0.0) {
+                eval_done = true;
+            } else {
+                an = xsub(a, xmul(J, ts));
+                if (an < -Am) an = -Am;
+                if (++pit >= 16) eval_done = true;
+            }
+        }
+        if (!eval_done) continue;
+        // ---------------- the profile ended: one step of pos_upper_rest
+        const double f = xsub(best, pmax);
+        bool task_done = false;
+        double result = 0.0;
+        if (phase == 0) {
+            fl = f;
+            if (fl > 0.0) { result = fl > 1e-6 ? -SM_BIG : lo; task_done = true; }
+            else { xl = lo; side = 0; iit = 0; phase = 1; }
+        } else {
+            if (f <= 0.0) {
+                xl = x; fl = f;
+                if (side == -1) fr = xmul(fr, 0.5);
+                side = -1;
+            } else {
+                xr = x; fr = f;
+                if (side == 1) fl = xmul(fl, 0.5);
+                side = 1;
+            }
+            if (++iit >= 40) { result = xl; task_done = true; }
+        }
+        if (!task_done) {
+            if (xsub(xr, xl) <= 1e-9) { result = xl; task_done = true; }
+            else {
+                x = xsub(xr, xdiv(xmul(fr, xsub(xr, xl)), xsub(fr, fl)));
+                if (!(x > xl && x < xr)) x = xmul(0.5, xadd(xl, xr));
+                p = P0; v = V0; a = A0; an = x; best = P0; pit = 0;
+            }
+        }
+        if (task_done) { *out = result; busy = false; }
     }
     if (A.counters && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&A.counters[9], (unsigned long long)n_task);
 }
