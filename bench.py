@@ -276,8 +276,15 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     uncull = {"space": 1.51e6, "space_bm": 1.71e6, "ball": 0.15e6, "ball_bm": 0.35e6}[args.scene]
+    traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            traffic = json.load(f)["bytes_per_launch"].get(args.scene, {}).get(dom)
+    except Exception:
+        pass
     roofline = {"bound": bound, "achieved": achieved_tflops, "peak": dom_peak, "unit": "TFLOP/s",
-                "frac": achieved_tflops / dom_peak, "traffic": None,
+                "frac": achieved_tflops / dom_peak, "traffic": traffic,
+                "traffic_unit": "DRAM bytes per launch (profiles/r01_traffic.json, ncu --set full, 65536 envs)",
                 "peak_source": "148 SMs x {} lanes x 2 x median SM clock under load ({} MHz); nominal pipe width, "
                                "MEASURED_PEAKS.json holds no FP32/FP64 vector peak".format(
                                    128 if bound == "fp32" else 64, sm_mhz),
