@@ -265,6 +265,27 @@ int smenv_launch_count(SmEnv* env, unsigned long long* out);
  * smenv_kernel_times returns the accumulated milliseconds per SmKernel and the number of steps accumulated. */
 int smenv_kernel_timing(SmEnv* env, int enable);
 int smenv_kernel_times(SmEnv* env, double* ms_out /* SM_K_COUNT */, int* steps_out, int reset);
+/*
+ * Networks in the step loop (safe_motions_base.py:1498-1603, actions.py:303-340): batched inference on the tensor
+ * cores.  which: SM_NET_RISK = risk(obs, action) -> [0, 1]; SM_NET_BACKUP = backup policy, obs -> action mean.
+ * dims = { n_in, N_1 .. N_n_tc, n_out }: n_tc hidden Dense layers (widths multiples of 16, at most 256, or 512) and
+ * one output Dense layer (n_out <= 8).  weights (host, float32, Keras layout): per layer kernel [in][out] row-major
+ * followed by its bias.  hidden_act: 0 selu, 1 swish; out_act: 0 sigmoid, 1 tanh.
+ */
+enum SmNet { SM_NET_RISK = 0, SM_NET_BACKUP = 1 };
+int smenv_mlp_load(SmEnv* env, int which, int n_tc, const int32_t* dims, int hidden_act, int out_act,
+                   const float* weights);
+/* out[n][out_stride] = net([in0 row, in1 row]) for n rows; all device pointers (in1 may be NULL with in1_w = 0). */
+int smenv_mlp_forward(SmEnv* env, int which, const float* in0, int in0_w, const float* in1, int in1_w, float* out,
+                      int out_stride, int n, SmStream stream);
+/* Risk gate on buf->actions in place: risk(obs, action) >= threshold replaces the env's action by the backup policy's
+ * (obs = buf->obs, the observation the action was computed from).  risk_out [N] / risky_out [N] may be NULL. */
+int smenv_risk_gate(SmEnv* env, const SmBuffers* buf, float threshold, float* risk_out, uint8_t* risky_out,
+                    SmStream stream);
+/* Writes the U(-1,1) actions smenv_step_random would use for the next step into buf->actions (so that the gate can be
+ * applied to them; follow with smenv_step). */
+int smenv_random_actions(SmEnv* env, const SmBuffers* buf, SmStream stream);
+
 /* Debug: trace of one GJK call between shapes ia and ib for one env state given on the host (trace: 32 x 8 floats per
  * iteration = simplex size, |v|^2, v.w, support ids, v; result: distance, iterations, then the 9 robot frames). */
 int smenv_debug_gjk(SmEnv* env, const double* kin_host, const double* obst_host, int ia, int ib, float upper,

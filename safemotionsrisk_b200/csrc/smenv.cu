@@ -10,6 +10,7 @@
 
 #include "smenv_pools.cuh"
 #include "smenv_step.cuh"
+#include "smenv_mlp.cuh"
 
 static thread_local std::string g_error;
 static int fail(int code, const std::string& msg) {
@@ -155,6 +156,11 @@ struct SmEnv {
     int* d_flag = nullptr;       // its device alias
     size_t smem_bytes_gjk = 0;
     int grid_gjk = 0;
+    MlpNet nets[2];              // risk network, backup policy (smenv_mlp_load)
+    bool net_loaded[2] = {false, false};
+    std::vector<void*> net_allocs;
+    float* d_risk = nullptr;     // [n] risk of the proposed action
+    float* d_backup = nullptr;   // [n][MLP_MAX_OUT] action mean of the backup policy
     bool time_kernels = false;   // measurement mode (smenv_kernel_timing)
     cudaEvent_t ev[SM_K_COUNT + 1] = {};
     double kernel_ms[SM_K_COUNT] = {};
@@ -457,6 +463,8 @@ extern "C" int smenv_destroy(SmEnv* env) {
     cudaFree(env->d_verts); cudaFree(env->d_lut); cudaFree(env->d_hwidth); cudaFree(env->d_plocal); cudaFree(env->d_start_pool); cudaFree(env->d_ball_pool);
     cudaFree(env->d_counters); cudaFree(env->d_scratch); cudaFree(env->d_worklist); cudaFree(env->d_heavy); cudaFree(env->d_cwork); cudaFree(env->d_tasks); cudaFree(env->d_hpar); cudaFree(env->d_items); cudaFree(env->d_res);
     if (env->h_flag) cudaFreeHost(env->h_flag);
+    for (void* q : env->net_allocs) cudaFree(q);
+    cudaFree(env->d_risk); cudaFree(env->d_backup);
     for (int i = 0; i <= SM_K_COUNT; ++i) if (env->ev[i]) cudaEventDestroy(env->ev[i]);
     for (int o = 0; o < SM_MAX_OBSTACLES; ++o) { cudaFree(env->d_ppos[o]); cudaFree(env->d_pquat[o]); }
     delete env;
@@ -768,6 +776,133 @@ extern "C" int smenv_counters(SmEnv* env, SmCounters* out, int reset) {
     if (reset) CU(cudaMemset(env->d_counters, 0, sizeof(h)));
     return SM_OK;
 }
+// ------------------------------------------------------------------------------------------------------------------
+// networks (smenv_mlp.cuh)
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" int smenv_mlp_load(SmEnv* env, int which, int n_tc, const int32_t* dims, int hidden_act, int out_act,
+                              const float* weights) {
+    if (!env || !dims || !weights || which < 0 || which > 1) return fail(SM_ERR_ARG, "smenv_mlp_load: bad argument");
+    if (n_tc < 1 || n_tc > MLP_MAX_TC) return fail(SM_ERR_ARG, "smenv_mlp_load: 1..3 hidden layers are supported");
+    const int n_in = dims[0], n_out = dims[n_tc + 1];
+    const int k_in = n_in <= 16 ? 16 : n_in <= 32 ? 32 : 64;   // a power of two: divisible by every chunk width
+    if (n_in < 1 || n_in > 64) return fail(SM_ERR_ARG, "smenv_mlp_load: input width must be in 1..64");
+    if (n_out < 1 || n_out > MLP_MAX_OUT) return fail(SM_ERR_ARG, "smenv_mlp_load: output width must be in 1..8");
+    for (int l = 0; l < n_tc; ++l) {
+        const int N = dims[1 + l];
+        if (N % 16 != 0 || N < 16 || (N > 256 && N != 512))
+            return fail(SM_ERR_ARG, "smenv_mlp_load: hidden widths must be multiples of 16, at most 256, or 512");
+    }
+    CU(cudaSetDevice(env->device));
+    MlpNet net;
+    memset(&net, 0, sizeof(net));
+    net.n_tc = n_tc; net.n_in = n_in; net.k_in = k_in; net.hidden_act = hidden_act; net.out_act = out_act; net.n_out = n_out;
+    const float* wp = weights;
+    int K_real = n_in, Kp = k_in;
+    for (int l = 0; l < n_tc; ++l) {
+        const int N = dims[1 + l];
+        net.dims[l] = N;
+        const int chunk_k = mlp_chunk_k(N, Kp);
+        std::vector<__half> packed((size_t)N * Kp);
+        for (int k = 0; k < Kp; ++k)
+            for (int n = 0; n < N; ++n) {
+                const int c = k / chunk_k, kl = k % chunk_k;
+                const size_t off = (size_t)c * N * chunk_k * 2 + (size_t)(kl / 8) * (N / 8 * 128) + (size_t)(n / 8) * 128 +
+                                   (size_t)(n % 8) * 16 + (size_t)(kl % 8) * 2;
+                packed[off / 2] = __float2half_rn(k < K_real ? wp[(size_t)k * N + n] : 0.0f);
+            }
+        wp += (size_t)K_real * N;
+        __half* dw = nullptr;
+        float* db = nullptr;
+        CU(cudaMalloc((void**)&dw, packed.size() * sizeof(__half)));
+        env->net_allocs.push_back(dw);
+        CU(cudaMemcpy(dw, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        CU(cudaMalloc((void**)&db, N * sizeof(float)));
+        env->net_allocs.push_back(db);
+        CU(cudaMemcpy(db, wp, N * sizeof(float), cudaMemcpyHostToDevice));
+        wp += N;
+        net.w[l] = dw; net.b[l] = db;
+        K_real = N; Kp = N;
+    }
+    {   // output layer, padded to MLP_MAX_OUT columns
+        std::vector<float> wo((size_t)K_real * MLP_MAX_OUT, 0.0f), bo(MLP_MAX_OUT, 0.0f);
+        for (int k = 0; k < K_real; ++k)
+            for (int o = 0; o < n_out; ++o) wo[(size_t)k * MLP_MAX_OUT + o] = wp[(size_t)k * n_out + o];
+        wp += (size_t)K_real * n_out;
+        for (int o = 0; o < n_out; ++o) bo[o] = wp[o];
+        float *dwo = nullptr, *dbo = nullptr;
+        CU(cudaMalloc((void**)&dwo, wo.size() * sizeof(float)));
+        env->net_allocs.push_back(dwo);
+        CU(cudaMemcpy(dwo, wo.data(), wo.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CU(cudaMalloc((void**)&dbo, bo.size() * sizeof(float)));
+        env->net_allocs.push_back(dbo);
+        CU(cudaMemcpy(dbo, bo.data(), bo.size() * sizeof(float), cudaMemcpyHostToDevice));
+        net.w_out = dwo; net.b_out = dbo;
+    }
+    env->nets[which] = net;
+    env->net_loaded[which] = true;
+    if (!env->d_risk) {
+        CU(cudaMalloc((void**)&env->d_risk, (size_t)env->n * sizeof(float)));
+        CU(cudaMalloc((void**)&env->d_backup, (size_t)env->n * MLP_MAX_OUT * sizeof(float)));
+    }
+    CU(cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SM_BYTES));
+    return SM_OK;
+}
+
+static int mlp_launch(SmEnv* env, int which, const float* in0, int in0_w, const float* in1, int in1_w, float* out,
+                      int out_stride, int n, cudaStream_t stream) {
+    if (!env->net_loaded[which]) return fail(SM_ERR_STATE, "network not loaded (smenv_mlp_load)");
+    const MlpNet& net = env->nets[which];
+    if (in0_w + in1_w != net.n_in) return fail(SM_ERR_ARG, "network input width does not match the loaded weights");
+    MlpArgs M;
+    M.net = net; M.n = n; M.in0 = in0; M.in0_w = in0_w; M.in1 = in1; M.in1_w = in1_w; M.out = out; M.out_stride = out_stride;
+    const int tiles = (n + MLP_TILE_M - 1) / MLP_TILE_M;
+    const int grid = tiles < env->sms ? tiles : env->sms;   // one CTA per SM (202 KB of shared memory, all of TMEM)
+    mlp_kernel<<<grid, MLP_TILE_M, MLP_SM_BYTES, stream>>>(M);
+    env->launches++;
+    CU(cudaGetLastError());
+    return SM_OK;
+}
+
+extern "C" int smenv_mlp_forward(SmEnv* env, int which, const float* in0, int in0_w, const float* in1, int in1_w,
+                                 float* out, int out_stride, int n, SmStream s) {
+    if (!env || !in0 || !out || which < 0 || which > 1 || n <= 0) return fail(SM_ERR_ARG, "smenv_mlp_forward: bad argument");
+    cudaStream_t stream = (cudaStream_t)s;
+    int rc = activate(env, stream);
+    if (rc) return rc;
+    return mlp_launch(env, which, in0, in0_w, in1, in1 ? in1_w : 0, out, out_stride, n, stream);
+}
+
+extern "C" int smenv_risk_gate(SmEnv* env, const SmBuffers* buf, float threshold, float* risk_out, uint8_t* risky_out,
+                               SmStream s) {
+    if (!env || !buf || !buf->actions || !buf->obs) return fail(SM_ERR_ARG, "smenv_risk_gate: null argument");
+    cudaStream_t stream = (cudaStream_t)s;
+    int rc = activate(env, stream);
+    if (rc) return rc;
+    const int nj = env->host_scene.n_joints, ow = env->host_scene.obs_size;
+    float* risk = risk_out ? risk_out : env->d_risk;
+    if ((rc = mlp_launch(env, SM_NET_RISK, buf->obs, ow, buf->actions, nj, risk, 1, env->n, stream))) return rc;
+    if ((rc = mlp_launch(env, SM_NET_BACKUP, buf->obs, ow, nullptr, 0, env->d_backup, MLP_MAX_OUT, env->n, stream))) return rc;
+    risk_gate_kernel<<<(env->n + 255) / 256, 256, 0, stream>>>(const_cast<float*>(buf->actions), risk, env->d_backup,
+                                                               MLP_MAX_OUT, nj, env->n, threshold, risky_out);
+    env->launches++;
+    CU(cudaGetLastError());
+    return SM_OK;
+}
+
+extern "C" int smenv_random_actions(SmEnv* env, const SmBuffers* buf, SmStream s) {
+    if (!env || !buf || !buf->actions) return fail(SM_ERR_ARG, "smenv_random_actions: null argument");
+    cudaStream_t stream = (cudaStream_t)s;
+    int rc = activate(env, stream);
+    if (rc) return rc;
+    const int nj = env->host_scene.n_joints;
+    random_actions_kernel<<<(env->n * nj + 255) / 256, 256, 0, stream>>>(const_cast<float*>(buf->actions), nj, env->n,
+                                                                         env->step_counter, (uint32_t)env->seed,
+                                                                         (uint32_t)(env->seed >> 32));
+    env->launches++;
+    CU(cudaGetLastError());
+    return SM_OK;
+}
+
 extern "C" int smenv_kernel_timing(SmEnv* env, int enable) {
     if (!env) return fail(SM_ERR_ARG, "null env");
     CU(cudaSetDevice(env->device));

@@ -1,0 +1,291 @@
+// smenv_mlp.cuh -- the one dense contraction of the step loop on the 5th-generation tensor cores: batched inference of
+// the risk network and of the backup policy (safe_motions_base.py:1498-1603, actions.py:303-340;
+// keras_fcnet_last_layer_activation.py:86-136, :187-202; train_risk_network.py).
+//
+//   risk(obs, action) = sigmoid(W4 selu(W3 selu(W2 selu(W1 [obs, action]))))      30 -> 512 -> 256 -> 128 -> 1
+//   backup(obs)       = tanh(W3 swish(W2 swish(W1 obs)))[0:7]                      23 -> 256 -> 128 -> 14
+//
+// One CTA (128 threads) owns a tile of 128 envs = the 128 rows of a tcgen05.mma (cta_group::1, M = 128) and runs the
+// whole network on it without leaving the SM:
+//   * activations live in shared memory as fp16 in the canonical K-major no-swizzle UMMA layout (8x16-byte core
+//     matrices, SBO = 128 B between 8-row groups, LBO = 2048 B between 8-column groups), weights are packed into the
+//     same layout on the host once and streamed through shared memory in 64-column K chunks;
+//   * one thread issues tcgen05.mma.kind::f16 (fp16 x fp16 -> fp32) into TMEM (N = 512 as two N = 256 instructions),
+//     tcgen05.commit signals an mbarrier;
+//   * the epilogue reads the accumulator row of each env with tcgen05.ld (thread t <-> TMEM lane t), adds the bias,
+//     applies selu / swish and writes the next layer's operand straight back to shared memory; the last hidden layer
+//     is contracted with the tiny output layer on the CUDA cores while it is still in registers.
+// This first version runs copy -> MMA -> epilogue strictly in sequence per chunk (no double buffering, no TMA).
+#pragma once
+#include <cuda_fp16.h>
+
+#include "smenv_device.cuh"
+
+#define MLP_MAX_TC 3
+#define MLP_MAX_OUT 8
+#define MLP_TILE_M 128
+#define MLP_CHUNK_K 64
+#define MLP_MAX_WIDTH 512
+
+// K columns of a layer's weights staged per chunk: at most MLP_CHUNK_K and at most 32 KB of shared memory
+__host__ __device__ __forceinline__ int mlp_chunk_k(int N, int K) {
+    int c = K < MLP_CHUNK_K ? K : MLP_CHUNK_K;
+    const int cap = 16384 / N;   // 32768 bytes / (N rows * 2 bytes)
+    return c < cap ? c : cap;
+}
+
+enum { MLP_ACT_SELU = 0, MLP_ACT_SWISH = 1 };
+enum { MLP_OUT_SIGMOID = 0, MLP_OUT_TANH = 1 };
+
+struct MlpNet {
+    int n_tc;                 // tensor-core layers
+    int n_in, k_in;           // real and padded (16, 32 or 64) input width
+    int dims[MLP_MAX_TC];     // widths of the tensor-core layers (multiples of 16; > 256 only as 512)
+    int hidden_act, out_act;
+    int n_out;                // outputs of the final CUDA-core layer (<= MLP_MAX_OUT)
+    const __half* w[MLP_MAX_TC];  // packed K chunks, canonical layout
+    const float* b[MLP_MAX_TC];
+    const float* w_out;       // [dims[n_tc-1]][MLP_MAX_OUT]
+    const float* b_out;       // [MLP_MAX_OUT]
+};
+
+struct MlpArgs {
+    MlpNet net;
+    int n;                    // rows (envs)
+    const float* in0; int in0_w;   // input = [in0 row, in1 row, zero padding]
+    const float* in1; int in1_w;
+    float* out; int out_stride;
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor: K-major, no swizzle (layout type 0), version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// instruction descriptor of kind::f16: D = f32, A = B = f16, both K-major, M x N
+__device__ __forceinline__ uint32_t umma_idesc_f16(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+                 :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}\n"
+        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+// 32 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* r) {
+    uint32_t u[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+          "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
+          "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
+          "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[i] = __uint_as_float(u[i]);
+}
+
+__device__ __forceinline__ float mlp_hidden_act(float x, int act) {
+    if (act == MLP_ACT_SELU) return 1.0507009873554805f * (x > 0.0f ? x : 1.6732632423543772f * (__expf(x) - 1.0f));
+    return x / (1.0f + __expf(-x));  // swish
+}
+
+// shared memory carve-up (bytes)
+#define MLP_SM_ACT 0                                       /* 128 x 512 fp16 */
+#define MLP_SM_W (MLP_TILE_M * MLP_MAX_WIDTH * 2)         /* one weight chunk: <= 512 x 32 or 256 x 64 fp16 */
+#define MLP_SM_IN (MLP_SM_W + 32768)                       /* 128 x 64 fp16 */
+#define MLP_SM_WOUT (MLP_SM_IN + MLP_TILE_M * 64 * 2)      /* MLP_MAX_WIDTH x MLP_MAX_OUT floats */
+#define MLP_SM_BIAS (MLP_SM_WOUT + MLP_MAX_WIDTH * MLP_MAX_OUT * 4)
+#define MLP_SM_BAR (MLP_SM_BIAS + MLP_MAX_TC * MLP_MAX_WIDTH * 4)
+#define MLP_SM_BYTES (MLP_SM_BAR + 64)
+
+__global__ void __launch_bounds__(MLP_TILE_M, 1) mlp_kernel(MlpArgs A) {
+    extern __shared__ __align__(1024) unsigned char mlp_smem[];
+    unsigned char* a_act = mlp_smem + MLP_SM_ACT;
+    unsigned char* w_buf = mlp_smem + MLP_SM_W;
+    unsigned char* a_in = mlp_smem + MLP_SM_IN;
+    float* w_out = reinterpret_cast<float*>(mlp_smem + MLP_SM_WOUT);
+    float* bias = reinterpret_cast<float*>(mlp_smem + MLP_SM_BIAS);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(mlp_smem + MLP_SM_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mlp_smem + MLP_SM_BAR + 16);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const MlpNet& net = A.net;
+    const int n_last = net.dims[net.n_tc - 1];
+
+    // ---------------- one-time setup: barrier, tensor memory, small parameters
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" :: "r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    for (int l = 0; l < net.n_tc; ++l)
+        for (int i = tid; i < net.dims[l]; i += MLP_TILE_M) bias[l * MLP_MAX_WIDTH + i] = __ldg(net.b[l] + i);
+    for (int i = tid; i < n_last * MLP_MAX_OUT; i += MLP_TILE_M) w_out[i] = __ldg(net.w_out + i);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    uint32_t phase = 0;
+    const int n_tiles = (A.n + MLP_TILE_M - 1) / MLP_TILE_M;
+    // this thread's slot inside an 8-row core-matrix group (row = tid): byte offset of its 16-byte row segment
+    const uint32_t row_off = (uint32_t)(tid >> 3) * 128u + (uint32_t)(tid & 7) * 16u;
+
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row = tile * MLP_TILE_M + tid;
+        const bool valid = row < A.n;
+        // ---------------- input rows -> fp16 operand of the first layer
+        for (int kc = 0; kc < net.k_in / 8; ++kc) {
+            __align__(16) __half h[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = kc * 8 + i;
+                float x = 0.0f;
+                if (valid) {
+                    if (k < A.in0_w) x = A.in0[(size_t)row * A.in0_w + k];
+                    else if (k < A.in0_w + A.in1_w) x = A.in1[(size_t)row * A.in1_w + (k - A.in0_w)];
+                }
+                h[i] = __float2half_rn(x);
+            }
+            *reinterpret_cast<uint4*>(a_in + kc * 2048 + row_off) = *reinterpret_cast<const uint4*>(h);
+        }
+        fence_async_smem();
+        __syncthreads();
+        uint32_t a_src = smem_u32(a_in);
+        int K = net.k_in;
+        float acc_out[MLP_MAX_OUT];
+#pragma unroll
+        for (int o = 0; o < MLP_MAX_OUT; ++o) acc_out[o] = 0.0f;
+#pragma unroll 1
+        for (int l = 0; l < net.n_tc; ++l) {
+            const int N = net.dims[l];
+            const int chunk_k = mlp_chunk_k(N, K);
+            const int n_chunks = K / chunk_k;
+            const int chunk_vec = N * chunk_k * 2 / 16;  // 16-byte vectors per weight chunk
+            const uint32_t lbo_b = (uint32_t)(N / 8) * 128u;
+#pragma unroll 1
+            for (int c = 0; c < n_chunks; ++c) {
+                // ---- weights of this K chunk -> shared memory (already in the canonical layout)
+                const uint4* src = reinterpret_cast<const uint4*>(net.w[l]) + (size_t)c * chunk_vec;
+                uint4* dst = reinterpret_cast<uint4*>(w_buf);
+                for (int i = tid; i < chunk_vec; i += MLP_TILE_M) dst[i] = __ldg(src + i);
+                fence_async_smem();
+                __syncthreads();
+                // ---- one thread issues the MMAs of the chunk
+                if (tid == 0) {
+                    tc_fence_after();
+                    for (int kk = 0; kk < chunk_k / 16; ++kk) {
+                        const uint64_t adesc = umma_desc(a_src + (uint32_t)((c * chunk_k + kk * 16) / 8) * 2048u, 2048u, 128u);
+                        for (int nh = 0; nh * 256 < N; ++nh) {
+                            const int n_mma = N - nh * 256 < 256 ? N - nh * 256 : 256;
+                            const uint64_t bdesc = umma_desc(smem_u32(w_buf) + (uint32_t)(kk * 2) * lbo_b + (uint32_t)nh * 32u * 128u,
+                                                             lbo_b, 128u);
+                            umma_f16(tmem + (uint32_t)nh * 256u, adesc, bdesc, umma_idesc_f16(MLP_TILE_M, n_mma),
+                                     (c > 0 || kk > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(bar);
+                }
+                mbar_wait(bar, phase);   // the chunk's MMAs are done: w_buf may be overwritten, TMEM may be read
+                phase ^= 1u;
+            }
+            tc_fence_after();
+            // ---------------- epilogue: accumulator row of this env -> bias, activation -> next operand / output
+            const bool last = l == net.n_tc - 1;
+            const float* bl = bias + l * MLP_MAX_WIDTH;
+#pragma unroll 1
+            for (int c0 = 0; c0 < N; c0 += 32) {
+                float r[32];
+                tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = mlp_hidden_act(r[j] + bl[c0 + j], net.hidden_act);
+                if (!last) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        __align__(16) __half h[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) h[i] = __float2half_rn(r[8 * g + i]);
+                        *reinterpret_cast<uint4*>(a_act + (uint32_t)((c0 + 8 * g) / 8) * 2048u + row_off) =
+                            *reinterpret_cast<const uint4*>(h);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+#pragma unroll
+                        for (int o = 0; o < MLP_MAX_OUT; ++o)
+                            if (o < net.n_out) acc_out[o] = fmaf(r[j], w_out[(c0 + j) * MLP_MAX_OUT + o], acc_out[o]);
+                }
+            }
+            tc_fence_before();
+            fence_async_smem();
+            __syncthreads();   // operand of the next layer complete; accumulator free for the next MMAs
+            a_src = smem_u32(a_act);
+            K = N;
+        }
+        if (valid) {
+            for (int o = 0; o < net.n_out; ++o) {
+                const float x = acc_out[o] + __ldg(net.b_out + o);
+                A.out[(size_t)row * A.out_stride + o] = net.out_act == MLP_OUT_SIGMOID ? 1.0f / (1.0f + __expf(-x)) : tanhf(x);
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" :: "r"(tmem) : "memory");
+}
+
+// risky actions are replaced by the backup policy's (actions.py:328-337); risk >= threshold (safe_motions_base.py:1601)
+__global__ void risk_gate_kernel(float* actions, const float* risk, const float* backup, int backup_stride, int nj, int n,
+                                 float threshold, uint8_t* risky) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= n) return;
+    const bool r = risk[env] >= threshold;
+    if (risky) risky[env] = r ? 1 : 0;
+    if (r)
+        for (int j = 0; j < nj; ++j) actions[(size_t)env * nj + j] = backup[(size_t)env * backup_stride + j];
+}
+
+// get_random_action (safe_motions_base.py:1327-1328) materialised, for the gate in front of smenv_step_random
+__global__ void random_actions_kernel(float* actions, int nj, int n, uint32_t step_counter, uint32_t k0, uint32_t k1) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int env = t / nj, j = t % nj;
+    if (env >= n) return;
+    uint4 r = philox((uint32_t)env, step_counter, (uint32_t)j, 0xAC71u, k0, k1);
+    actions[t] = 2.0f * u01f(r.x) - 1.0f;
+}

@@ -319,6 +319,68 @@ class SafeMotionsVecEnv:
         cabi.check(self._lib.smenv_counters(self._handle, C.byref(c), int(reset)), "smenv_counters")
         return {k: int(getattr(c, k)) for k, _ in abi.SmCounters._fields_ if k != "aux"}
 
+    # ------------------------------------------------------------------ networks in the step loop (risk gate)
+    def load_networks(self, source=None):
+        """Loads the risk network and the backup policy (weights exported from the reference's checkpoints by
+        tools/export_networks.py).  source: path of an .npz, or None for the packaged weights of the env's scene."""
+        if source is None:
+            scene = "ball" if self.config.use_moving_objects else "space"
+            source = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets",
+                                  "networks_{}.npz".format(scene))
+        w = np.load(source)
+        nj = self.scene.n_joints
+        risk = [(w["risk/dense_{}/kernel".format(i)], w["risk/dense_{}/bias".format(i)]) for i in range(4)]
+        pol = [(w["backup/{}/kernel".format(n)], w["backup/{}/bias".format(n)]) for n in ("fc_1", "fc_2", "fc_out")]
+        pol[-1] = (pol[-1][0][:, :nj], pol[-1][1][:nj])  # deterministic action = the mean head
+        if risk[0][0].shape[0] != self.scene.obs_size + nj or pol[0][0].shape[0] != self.scene.obs_size:
+            raise ValueError("networks expect observation size {}, the env produces {}".format(
+                pol[0][0].shape[0], self.scene.obs_size))
+        for which, layers, hidden, out_act in ((0, risk, 0, 0), (1, pol, 1, 1)):
+            dims = np.array([layers[0][0].shape[0]] + [k.shape[1] for k, _ in layers], dtype=np.int32)
+            flat = np.concatenate([np.concatenate([k.astype(np.float32).ravel(), b.astype(np.float32).ravel()])
+                                   for k, b in layers])
+            cabi.check(self._lib.smenv_mlp_load(self._handle, which, len(layers) - 1, dims.ctypes.data, hidden, out_act,
+                                                flat.ctypes.data), "smenv_mlp_load")
+        self.risk = torch.zeros(self.num_envs, dtype=torch.float32, device=self.device)
+        self.risky = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+        self._networks = True
+
+    def mlp_forward(self, which, in0, in1=None, n_out=1):
+        """Parity hook: the loaded network `which` (0 risk, 1 backup policy) on caller-supplied rows."""
+        in0 = torch.as_tensor(in0, dtype=torch.float32, device=self.device).contiguous()
+        n = in0.shape[0]
+        out = torch.zeros((n, n_out), dtype=torch.float32, device=self.device)
+        p1, w1 = None, 0
+        if in1 is not None:
+            in1 = torch.as_tensor(in1, dtype=torch.float32, device=self.device).contiguous()
+            p1, w1 = C.c_void_p(in1.data_ptr()), in1.shape[1]
+        cabi.check(self._lib.smenv_mlp_forward(self._handle, which, in0.data_ptr(), in0.shape[1], p1, w1,
+                                               out.data_ptr(), n_out, n, self._stream()), "smenv_mlp_forward")
+        return out
+
+    def risk_gate(self, threshold=None):
+        """Replaces, in self.actions, every action the risk network rates >= threshold by the backup policy's action
+        for the current observation (actions.py:303-340).  Returns (risk [N], risky [N])."""
+        thr = float(self.config.risk_threshold if threshold is None else threshold)
+        cabi.check(self._lib.smenv_risk_gate(self._handle, C.byref(self._buf), thr, self.risk.data_ptr(),
+                                             self.risky.data_ptr(), self._stream()), "smenv_risk_gate")
+        return self.risk, self.risky
+
+    def step_gated(self, actions=None, threshold=None):
+        """One env step with the risk gate in front: actions (or device-generated random actions if None) are
+        filtered by risk_gate, then stepped."""
+        if actions is None:
+            cabi.check(self._lib.smenv_random_actions(self._handle, C.byref(self._buf), self._stream()),
+                       "smenv_random_actions")
+        elif torch.is_tensor(actions) and actions.device == self.device:
+            self.actions.copy_(actions.reshape(self.num_envs, -1), non_blocking=True)
+        else:
+            self.actions.copy_(torch.from_numpy(np.asarray(actions, dtype=np.float32).reshape(self.num_envs, -1)))
+        self.risk_gate(threshold)
+        cabi.check(self._lib.smenv_step(self._handle, C.byref(self._buf), int(self.auto_reset), self._stream()),
+                   "smenv_step")
+        return self._outputs()
+
     KERNELS = ("joint_kernel", "joint_heavy_kernel", "contact_plan_kernel", "distance_plan_kernel", "gjk_kernel",
                "finish_kernel")
 

@@ -387,3 +387,56 @@ def test_counters_account_for_the_planned_pairs():
     assert c["gjk_iters"] >= c["gjk_calls"] and c["support_dots"] > 0
     assert 0 < c["heavy_joints"] <= 7 * c["env_steps"] and c["heavy_solves"] <= 2 * c["heavy_joints"]
     env.close()
+
+
+# ---------------------------------------------------------------------------------------------- networks (risk gate)
+@pytest.mark.parametrize("name", ["space_bm", "ball_bm"])
+def test_networks_match_the_float32_reference(name):
+    """tcgen05 fp16 x fp16 -> fp32 inference of the shipped risk network / backup policy against a NumPy float32
+    forward pass (oracle/mlp.py).  Tolerance: fp16 operands carry 11 significant bits and the error passes through
+    three layers with unbounded selu activations: 3e-2 absolute at most (rare rows where the sigmoid is steepest,
+    risk around 0.5), 1e-3 on average, on outputs that live in [0, 1] / [-1, 1].  Near the gate thresholds of the
+    reference (0.06 - 0.105) the sigmoid is flat and the error stays below 4e-3 (next test)."""
+    from oracle import mlp
+    env = make_env(name, 1000)   # not a multiple of the 128-row tile
+    env.load_networks()
+    w = np.load(os.path.join(os.path.dirname(GOLDEN), "..", "safemotionsrisk_b200", "assets",
+                             "networks_{}.npz".format("ball" if name.startswith("ball") else "space")))
+    rng = np.random.default_rng(5)
+    obs = rng.uniform(-1, 1, (1000, env.scene.obs_size)).astype(np.float32)
+    act = rng.uniform(-1, 1, (1000, 7)).astype(np.float32)
+    risk = env.mlp_forward(0, obs, act, n_out=1).cpu().numpy()[:, 0]
+    pol = env.mlp_forward(1, obs, None, n_out=7).cpu().numpy()
+    e_risk, e_pol = np.abs(risk - mlp.risk_forward(w, obs, act)), np.abs(pol - mlp.backup_forward(w, obs))
+    assert e_risk.max() < 3e-2 and e_risk.mean() < 1e-3
+    assert e_pol.max() < 3e-2 and e_pol.mean() < 1e-3
+    env.close()
+
+
+def test_risk_gate_replaces_exactly_the_risky_actions():
+    from oracle import mlp
+    n, thr = 4096, 0.065    # README.md:223 risk_threshold of the Space task
+    env = make_env("space_bm", n, auto_reset=True)
+    env.load_networks()
+    env.reset()
+    for _ in range(5):
+        env.step_random()
+    w = np.load(os.path.join(os.path.dirname(GOLDEN), "..", "safemotionsrisk_b200", "assets", "networks_space.npz"))
+    obs = env.obs.cpu().numpy().copy()
+    act = np.random.default_rng(9).uniform(-1, 1, (n, 7)).astype(np.float32)
+    env.actions.copy_(torch.from_numpy(act))
+    risk, risky = env.risk_gate(thr)
+    torch.cuda.synchronize()
+    o_act, o_risk, o_risky = mlp.gate(w, obs, act, thr)
+    risk, risky, gated = risk.cpu().numpy(), risky.cpu().numpy().astype(bool), env.actions.cpu().numpy()
+    assert np.abs(risk - o_risk).max() < 3e-2
+    clear = np.abs(o_risk - thr) > 4e-3          # decisions may differ only on the knife edge
+    assert np.array_equal(risky[clear], o_risky[clear])
+    assert 0 < risky.sum() < n                   # the gate fires on some envs, not on all
+    same = risky == o_risky
+    assert np.abs(gated[same] - o_act[same]).max() < 3e-2
+    assert np.array_equal(gated[~risky], act[~risky])   # safe actions pass through untouched
+    # and the gated step runs end to end
+    env.step_gated(threshold=thr)
+    torch.cuda.synchronize()
+    env.close()
