@@ -792,6 +792,7 @@ extern "C" int smenv_mlp_load(SmEnv* env, int which, int n_tc, const int32_t* di
         if (N % 16 != 0 || N < 16 || (N > 256 && N != 512))
             return fail(SM_ERR_ARG, "smenv_mlp_load: hidden widths must be multiples of 16, at most 256, or 512");
     }
+    if (dims[n_tc] > MLP_MAX_LAST) return fail(SM_ERR_ARG, "smenv_mlp_load: the last hidden layer may be at most 256 wide");
     CU(cudaSetDevice(env->device));
     MlpNet net;
     memset(&net, 0, sizeof(net));
@@ -857,7 +858,7 @@ static int mlp_launch(SmEnv* env, int which, const float* in0, int in0_w, const 
     M.net = net; M.n = n; M.in0 = in0; M.in0_w = in0_w; M.in1 = in1; M.in1_w = in1_w; M.out = out; M.out_stride = out_stride;
     const int tiles = (n + MLP_TILE_M - 1) / MLP_TILE_M;
     const int grid = tiles < env->sms ? tiles : env->sms;   // one CTA per SM (202 KB of shared memory, all of TMEM)
-    mlp_kernel<<<grid, MLP_TILE_M, MLP_SM_BYTES, stream>>>(M);
+    mlp_kernel<<<grid, MLP_THREADS, MLP_SM_BYTES, stream>>>(M);
     env->launches++;
     CU(cudaGetLastError());
     return SM_OK;

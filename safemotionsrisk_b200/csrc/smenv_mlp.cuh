@@ -5,17 +5,20 @@
 //   risk(obs, action) = sigmoid(W4 selu(W3 selu(W2 selu(W1 [obs, action]))))      30 -> 512 -> 256 -> 128 -> 1
 //   backup(obs)       = tanh(W3 swish(W2 swish(W1 obs)))[0:7]                      23 -> 256 -> 128 -> 14
 //
-// One CTA (128 threads) owns a tile of 128 envs = the 128 rows of a tcgen05.mma (cta_group::1, M = 128) and runs the
+// One CTA (256 threads) owns a tile of 128 envs = the 128 rows of a tcgen05.mma (cta_group::1, M = 128) and runs the
 // whole network on it without leaving the SM:
 //   * activations live in shared memory as fp16 in the canonical K-major no-swizzle UMMA layout (8x16-byte core
 //     matrices, SBO = 128 B between 8-row groups, LBO = 2048 B between 8-column groups), weights are packed into the
 //     same layout on the host once and streamed through shared memory in 64-column K chunks;
 //   * one thread issues tcgen05.mma.kind::f16 (fp16 x fp16 -> fp32) into TMEM (N = 512 as two N = 256 instructions),
 //     tcgen05.commit signals an mbarrier;
-//   * the epilogue reads the accumulator row of each env with tcgen05.ld (thread t <-> TMEM lane t), adds the bias,
+//   * the epilogue reads the accumulator row of each env with tcgen05.ld (two threads per TMEM lane, half of the
+//     columns each), adds the bias,
 //     applies selu / swish and writes the next layer's operand straight back to shared memory; the last hidden layer
 //     is contracted with the tiny output layer on the CUDA cores while it is still in registers.
-// This first version runs copy -> MMA -> epilogue strictly in sequence per chunk (no double buffering, no TMA).
+//   * the weight chunks stream through two 32 KB buffers with 1-D bulk TMA (cp.async.bulk -> mbarrier complete_tx),
+//     issued two chunks ahead by the MMA-issuing thread, across layer and tile boundaries, so that the copies overlap
+//     the MMAs and the epilogues.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -24,6 +27,7 @@
 #define MLP_MAX_TC 3
 #define MLP_MAX_OUT 8
 #define MLP_TILE_M 128
+#define MLP_THREADS 256 /* two warps per TMEM lane quarter: each handles half of the accumulator columns */
 #define MLP_CHUNK_K 64
 #define MLP_MAX_WIDTH 512
 
@@ -125,30 +129,48 @@ __device__ __forceinline__ float mlp_hidden_act(float x, int act) {
 }
 
 // shared memory carve-up (bytes)
+#define MLP_W_BUF_BYTES 32768
+#define MLP_MAX_LAST 256                                   /* widest last hidden layer */
 #define MLP_SM_ACT 0                                       /* 128 x 512 fp16 */
-#define MLP_SM_W (MLP_TILE_M * MLP_MAX_WIDTH * 2)         /* one weight chunk: <= 512 x 32 or 256 x 64 fp16 */
-#define MLP_SM_IN (MLP_SM_W + 32768)                       /* 128 x 64 fp16 */
-#define MLP_SM_WOUT (MLP_SM_IN + MLP_TILE_M * 64 * 2)      /* MLP_MAX_WIDTH x MLP_MAX_OUT floats */
-#define MLP_SM_BIAS (MLP_SM_WOUT + MLP_MAX_WIDTH * MLP_MAX_OUT * 4)
-#define MLP_SM_BAR (MLP_SM_BIAS + MLP_MAX_TC * MLP_MAX_WIDTH * 4)
+#define MLP_SM_W (MLP_TILE_M * MLP_MAX_WIDTH * 2)         /* two weight chunks: <= 512 x 32 or 256 x 64 fp16 each */
+#define MLP_SM_IN (MLP_SM_W + 2 * MLP_W_BUF_BYTES)         /* 128 x 64 fp16 */
+#define MLP_SM_WOUT (MLP_SM_IN + MLP_TILE_M * 64 * 2)      /* MLP_MAX_LAST x MLP_MAX_OUT floats */
+#define MLP_SM_BIAS (MLP_SM_WOUT + MLP_MAX_LAST * MLP_MAX_OUT * 4)
+#define MLP_SM_PART (MLP_SM_BIAS + MLP_MAX_TC * MLP_MAX_WIDTH * 4)   /* 128 x MLP_MAX_OUT partial outputs */
+#define MLP_SM_BAR (MLP_SM_PART + MLP_TILE_M * MLP_MAX_OUT * 4)
 #define MLP_SM_BYTES (MLP_SM_BAR + 64)
 
-__global__ void __launch_bounds__(MLP_TILE_M, 1) mlp_kernel(MlpArgs A) {
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(MlpArgs A) {
     extern __shared__ __align__(1024) unsigned char mlp_smem[];
     unsigned char* a_act = mlp_smem + MLP_SM_ACT;
     unsigned char* w_buf = mlp_smem + MLP_SM_W;
     unsigned char* a_in = mlp_smem + MLP_SM_IN;
     float* w_out = reinterpret_cast<float*>(mlp_smem + MLP_SM_WOUT);
     float* bias = reinterpret_cast<float*>(mlp_smem + MLP_SM_BIAS);
+    float* part = reinterpret_cast<float*>(mlp_smem + MLP_SM_PART);
     uint64_t* bar = reinterpret_cast<uint64_t*>(mlp_smem + MLP_SM_BAR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mlp_smem + MLP_SM_BAR + 16);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mlp_smem + MLP_SM_BAR + 48);
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int rtid = tid & (MLP_TILE_M - 1);   // row of the tile this thread serves
+    const int half = tid >> 7;                 // which half of the columns / input segments
+    const int quarter = warp & 3;              // TMEM lane quarter the warp may access
     const MlpNet& net = A.net;
     const int n_last = net.dims[net.n_tc - 1];
 
     // ---------------- one-time setup: barrier, tensor memory, small parameters
+    uint64_t* bar_full = bar;        // [2] weight chunk landed in buffer b
+    uint64_t* bar_empty = bar + 2;   // [2] the MMAs reading buffer b are done
+    uint64_t* bar_done = bar + 4;    // all MMAs of a layer are done
     if (tid == 0) {
-        mbar_init(bar, 1);
+        for (int i = 0; i < 5; ++i) mbar_init(bar + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 0) {
@@ -156,23 +178,50 @@ __global__ void __launch_bounds__(MLP_TILE_M, 1) mlp_kernel(MlpArgs A) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
     for (int l = 0; l < net.n_tc; ++l)
-        for (int i = tid; i < net.dims[l]; i += MLP_TILE_M) bias[l * MLP_MAX_WIDTH + i] = __ldg(net.b[l] + i);
-    for (int i = tid; i < n_last * MLP_MAX_OUT; i += MLP_TILE_M) w_out[i] = __ldg(net.w_out + i);
+        for (int i = tid; i < net.dims[l]; i += MLP_THREADS) bias[l * MLP_MAX_WIDTH + i] = __ldg(net.b[l] + i);
+    for (int i = tid; i < n_last * MLP_MAX_OUT; i += MLP_THREADS) w_out[i] = __ldg(net.w_out + i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    uint32_t phase = 0;
+    uint32_t done_phase = 0;
     const int n_tiles = (A.n + MLP_TILE_M - 1) / MLP_TILE_M;
+    // ---------------- weight streaming state of the issuing thread: chunks are numbered g = 0, 1, ... over all layers
+    // of all tiles of this CTA; chunk g uses buffer g & 1 for the (g >> 1)-th time
+    int chunks_per_tile = 0;
+    {
+        int K = net.k_in;
+        for (int l = 0; l < net.n_tc; ++l) { chunks_per_tile += K / mlp_chunk_k(net.dims[l], K); K = net.dims[l]; }
+    }
+    const int my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    int pf_left = chunks_per_tile * my_tiles, pf_g = 0, pf_layer = 0, pf_chunk = 0, pf_K = net.k_in;  // prefetch cursor
+    int g = 0;                                                                                      // consume cursor
+    auto prefetch = [&]() {
+        if (pf_left == 0) return;
+        const int b = pf_g & 1, u = pf_g >> 1;
+        if (u > 0) mbar_wait(&bar_empty[b], (uint32_t)(u - 1) & 1u);   // the previous user of the buffer is done
+        const int N = net.dims[pf_layer];
+        const int ck = mlp_chunk_k(N, pf_K);
+        const uint32_t bytes = (uint32_t)(N * ck * 2);
+        mbar_expect_tx(&bar_full[b], bytes);
+        tma_bulk_g2s(w_buf + b * MLP_W_BUF_BYTES, reinterpret_cast<const unsigned char*>(net.w[pf_layer]) + (size_t)pf_chunk * bytes,
+                     bytes, &bar_full[b]);
+        ++pf_g; --pf_left;
+        if (++pf_chunk == pf_K / ck) {
+            pf_chunk = 0; pf_K = N;
+            if (++pf_layer == net.n_tc) { pf_layer = 0; pf_K = net.k_in; }
+        }
+    };
+    if (tid == 0) { prefetch(); prefetch(); }
     // this thread's slot inside an 8-row core-matrix group (row = tid): byte offset of its 16-byte row segment
-    const uint32_t row_off = (uint32_t)(tid >> 3) * 128u + (uint32_t)(tid & 7) * 16u;
+    const uint32_t row_off = (uint32_t)(rtid >> 3) * 128u + (uint32_t)(rtid & 7) * 16u;
 
 #pragma unroll 1
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int row = tile * MLP_TILE_M + tid;
+        const int row = tile * MLP_TILE_M + rtid;
         const bool valid = row < A.n;
         // ---------------- input rows -> fp16 operand of the first layer
-        for (int kc = 0; kc < net.k_in / 8; ++kc) {
+        for (int kc = half; kc < net.k_in / 8; kc += 2) {
             __align__(16) __half h[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -198,42 +247,40 @@ __global__ void __launch_bounds__(MLP_TILE_M, 1) mlp_kernel(MlpArgs A) {
             const int N = net.dims[l];
             const int chunk_k = mlp_chunk_k(N, K);
             const int n_chunks = K / chunk_k;
-            const int chunk_vec = N * chunk_k * 2 / 16;  // 16-byte vectors per weight chunk
             const uint32_t lbo_b = (uint32_t)(N / 8) * 128u;
+            // ---- one thread: wait for each weight chunk, issue its MMAs, release the buffer, fetch two chunks ahead
+            if (tid == 0) {
 #pragma unroll 1
-            for (int c = 0; c < n_chunks; ++c) {
-                // ---- weights of this K chunk -> shared memory (already in the canonical layout)
-                const uint4* src = reinterpret_cast<const uint4*>(net.w[l]) + (size_t)c * chunk_vec;
-                uint4* dst = reinterpret_cast<uint4*>(w_buf);
-                for (int i = tid; i < chunk_vec; i += MLP_TILE_M) dst[i] = __ldg(src + i);
-                fence_async_smem();
-                __syncthreads();
-                // ---- one thread issues the MMAs of the chunk
-                if (tid == 0) {
+                for (int c = 0; c < n_chunks; ++c) {
+                    const int b = g & 1;
+                    mbar_wait(&bar_full[b], (uint32_t)(g >> 1) & 1u);
                     tc_fence_after();
+                    const uint32_t wb = smem_u32(w_buf + b * MLP_W_BUF_BYTES);
                     for (int kk = 0; kk < chunk_k / 16; ++kk) {
                         const uint64_t adesc = umma_desc(a_src + (uint32_t)((c * chunk_k + kk * 16) / 8) * 2048u, 2048u, 128u);
                         for (int nh = 0; nh * 256 < N; ++nh) {
                             const int n_mma = N - nh * 256 < 256 ? N - nh * 256 : 256;
-                            const uint64_t bdesc = umma_desc(smem_u32(w_buf) + (uint32_t)(kk * 2) * lbo_b + (uint32_t)nh * 32u * 128u,
-                                                             lbo_b, 128u);
+                            const uint64_t bdesc = umma_desc(wb + (uint32_t)(kk * 2) * lbo_b + (uint32_t)nh * 32u * 128u, lbo_b, 128u);
                             umma_f16(tmem + (uint32_t)nh * 256u, adesc, bdesc, umma_idesc_f16(MLP_TILE_M, n_mma),
                                      (c > 0 || kk > 0) ? 1u : 0u);
                         }
                     }
-                    umma_commit(bar);
+                    umma_commit(&bar_empty[b]);
+                    ++g;
+                    if (c == n_chunks - 1) umma_commit(bar_done);
+                    prefetch();
                 }
-                mbar_wait(bar, phase);   // the chunk's MMAs are done: w_buf may be overwritten, TMEM may be read
-                phase ^= 1u;
             }
+            mbar_wait(bar_done, done_phase);   // all MMAs of the layer are done: the accumulator may be read
+            done_phase ^= 1u;
             tc_fence_after();
             // ---------------- epilogue: accumulator row of this env -> bias, activation -> next operand / output
             const bool last = l == net.n_tc - 1;
             const float* bl = bias + l * MLP_MAX_WIDTH;
 #pragma unroll 1
-            for (int c0 = 0; c0 < N; c0 += 32) {
+            for (int c0 = half * (N / 2); c0 < (half + 1) * (N / 2); c0 += 32) {
                 float r[32];
-                tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+                tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) r[j] = mlp_hidden_act(r[j] + bl[c0 + j], net.hidden_act);
                 if (!last) {
@@ -259,9 +306,13 @@ __global__ void __launch_bounds__(MLP_TILE_M, 1) mlp_kernel(MlpArgs A) {
             a_src = smem_u32(a_act);
             K = N;
         }
-        if (valid) {
+        // the two column halves of a row meet in shared memory
+        if (half == 1)
+            for (int o = 0; o < net.n_out; ++o) part[rtid * MLP_MAX_OUT + o] = acc_out[o];
+        __syncthreads();
+        if (valid && half == 0) {
             for (int o = 0; o < net.n_out; ++o) {
-                const float x = acc_out[o] + __ldg(net.b_out + o);
+                const float x = acc_out[o] + part[rtid * MLP_MAX_OUT + o] + __ldg(net.b_out + o);
                 A.out[(size_t)row * A.out_stride + o] = net.out_act == MLP_OUT_SIGMOID ? 1.0f / (1.0f + __expf(-x)) : tanhf(x);
             }
         }
