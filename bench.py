@@ -151,6 +151,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--risk-gate", action="store_true",
+                    help="risk network + backup policy (tensor cores) in front of every step (BASELINE.json configs[3])")
+    ap.add_argument("--risk-threshold", type=float, default=None)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -190,10 +193,24 @@ def main():
     dev = torch.device("cuda", local_rank)
     cfg = scene_config(args.scene)
     env = SafeMotionsVecEnv(num_envs=args.envs, device=dev, seed=1000 * rank, auto_reset=True, config=cfg)
+    gate_thr = None
+    if args.risk_gate:
+        env.load_networks()
+        gate_thr = args.risk_threshold if args.risk_threshold is not None else \
+            (0.105 if args.scene.startswith("ball") else 0.065)   # README.md:223-229
+        config["risk_gate"] = {"threshold": gate_thr, "networks": "risk 30/34-512-256-128-1 selu + backup policy "
+                               "23/27-256-128-14 swish/tanh, fp16 x fp16 -> fp32 on tcgen05"}
+        config["workload"] += " + state-action risk network and backup policy in the step loop"
+
+    def one_step():
+        if gate_thr is None:
+            env.step_random()
+        else:
+            env.step_gated(threshold=gate_thr)
     env.reset()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     for _ in range(max(3, args.warmup)):
-        env.step_random()
+        one_step()
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
@@ -205,7 +222,7 @@ def main():
     for i in range(args.steps):
         flush.fill_(i & 0xff)  # evict the env state from L2 (outside the timed region of the step)
         starts[i].record()
-        env.step_random()
+        one_step()
         ends[i].record()
     torch.cuda.synchronize(dev)
     t_wall1 = time.time()
@@ -300,20 +317,38 @@ def main():
                         "frac": per_gpu_steps_s * bytes_step / 1e9 / hbm_peak, "bytes_per_env_step": bytes_step,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
 
+    if gate_thr is not None:  # the tensor-core part: time of the gate alone, dense flops against the bf16/fp16 peak
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        env.step_gated(threshold=gate_thr)
+        g0.record()
+        for _ in range(10):
+            env.risk_gate(gate_thr)
+        g1.record()
+        torch.cuda.synchronize(dev)
+        gate_ms = g0.elapsed_time(g1) / 10
+        ow = sc.obs_size
+        gflop = 2.0 * args.envs * ((ow + sc_nj) * 512 + 512 * 256 + 256 * 128 + 128 + ow * 256 + 256 * 128 + 128 * sc_nj)
+        tpeak = peaks.get("bf16_tflops", 2250.0)
+        roofline["risk_gate"] = {"bound": "tensor", "kernel": "mlp_kernel x2 + risk_gate_kernel", "ms": gate_ms,
+                                 "achieved": gflop / (gate_ms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                                 "frac": gflop / (gate_ms * 1e-3) / 1e12 / tpeak,
+                                 "peak_source": "MEASURED_PEAKS.json bf16_tflops" if peaks else "nominal",
+                                 "risky_fraction": float(env.risky.float().mean().item())}
+
     # ---------------- end to end through the host-buffer API
     e2e = None
     if not args.no_e2e:
         rng = np.random.default_rng(rank)
         acts = rng.uniform(-1, 1, (args.envs, sc.n_joints)).astype(np.float32)
         for _ in range(3):
-            env.step_host(acts)
+            env.step_host(acts, gate_thr)
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
         k_e2e = min(args.steps, 100)
         t0 = time.perf_counter()
         for _ in range(k_e2e):
-            env.step_host(acts)
+            env.step_host(acts, gate_thr)
         torch.cuda.synchronize(dev)
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:

@@ -211,10 +211,13 @@ class SafeMotionsVecEnv:
                                                self._stream()), "smenv_step_random")
         return self._outputs()
 
-    def step_host(self, actions_np):
-        """Host-buffer API: NumPy actions in, NumPy (obs, reward, done) out through pinned staging buffers."""
+    def step_host(self, actions_np, gate_threshold=None):
+        """Host-buffer API: NumPy actions in, NumPy (obs, reward, done) out through pinned staging buffers.
+        gate_threshold: apply the risk gate (load_networks first) to the actions before the step."""
         self._h_actions.numpy()[...] = np.asarray(actions_np, dtype=np.float32).reshape(self.num_envs, -1)
         self.actions.copy_(self._h_actions, non_blocking=True)
+        if gate_threshold is not None:
+            self.risk_gate(gate_threshold)
         cabi.check(self._lib.smenv_step(self._handle, C.byref(self._buf), int(self.auto_reset), self._stream()),
                    "smenv_step")
         self._h_obs.copy_(self.obs, non_blocking=True)
