@@ -139,6 +139,7 @@ struct SmEnv {
     float4* d_verts = nullptr;
     uint32_t* d_lut = nullptr;
     float* d_hwidth = nullptr;
+    SceneImage* d_scene_img = nullptr;
     float4* d_ppos[SM_MAX_OBSTACLES] = {nullptr, nullptr};
     float4* d_pquat[SM_MAX_OBSTACLES] = {nullptr, nullptr};
     double* d_plocal = nullptr;
@@ -372,7 +373,7 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     int rc = upload(&env->d_verts, verts);
     if (rc) { delete env; return rc; }
     d.verts = env->d_verts;
-    if (lut.empty()) lut.push_back(0u);
+    while (lut.empty() || lut.size() % 4) lut.push_back(0u);   // staged in 16-byte vectors
     if ((rc = upload(&env->d_lut, lut))) { delete env; return rc; }
     d.lut = env->d_lut;
     if ((rc = upload(&env->d_hwidth, hwidth))) { delete env; return rc; }
@@ -395,6 +396,21 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
         std::vector<double> pl(sc->planet_local_xy, sc->planet_local_xy + 2 * sc->planet_steps);
         if ((rc = upload(&env->d_plocal, pl))) { delete env; return rc; }
         d.planet_local_xy = env->d_plocal;
+    }
+    {   // image of the shared-memory tables of the geometry kernels
+        std::vector<SceneImage> img(1);
+        memset(img.data(), 0, sizeof(SceneImage));
+        SceneSmem& si = img[0].scene;
+        memcpy(si.shapes, d.shapes, sizeof(si.shapes));
+        memcpy(si.jR, d.jR, sizeof(si.jR)); memcpy(si.jt, d.jt, sizeof(si.jt)); memcpy(si.jaxis, d.jaxis, sizeof(si.jaxis));
+        memcpy(si.static_pairs, d.static_pairs, sizeof(si.static_pairs));
+        memcpy(si.self_pairs, d.self_pairs, sizeof(si.self_pairs));
+        memcpy(si.mov_reward, d.mov_reward, sizeof(si.mov_reward));
+        memcpy(si.mov_contact, d.mov_contact, sizeof(si.mov_contact));
+        memcpy(si.contact_thresh, d.contact_thresh, sizeof(si.contact_thresh));
+        memcpy(img[0].pair_tab, d.pair_tab, sizeof(img[0].pair_tab));
+        if ((rc = upload(&env->d_scene_img, img))) { delete env; return rc; }
+        d.scene_img = reinterpret_cast<const uint4*>(env->d_scene_img);
     }
     // pools: one start state per env is plenty of variety up to 65536; balls are consumed faster
     env->start_pool_n = num_envs < 65536 ? (num_envs < 1024 ? 1024 : num_envs) : 65536;
@@ -460,7 +476,7 @@ extern "C" int smenv_destroy(SmEnv* env) {
     if (!env) return SM_OK;
     cudaSetDevice(env->device);
     if (g_active == env) g_active = nullptr;
-    cudaFree(env->d_verts); cudaFree(env->d_lut); cudaFree(env->d_hwidth); cudaFree(env->d_plocal); cudaFree(env->d_start_pool); cudaFree(env->d_ball_pool);
+    cudaFree(env->d_verts); cudaFree(env->d_lut); cudaFree(env->d_hwidth); cudaFree(env->d_scene_img); cudaFree(env->d_plocal); cudaFree(env->d_start_pool); cudaFree(env->d_ball_pool);
     cudaFree(env->d_counters); cudaFree(env->d_scratch); cudaFree(env->d_worklist); cudaFree(env->d_heavy); cudaFree(env->d_cwork); cudaFree(env->d_tasks); cudaFree(env->d_hpar); cudaFree(env->d_items); cudaFree(env->d_res);
     if (env->h_flag) cudaFreeHost(env->h_flag);
     for (void* q : env->net_allocs) cudaFree(q);

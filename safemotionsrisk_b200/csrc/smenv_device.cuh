@@ -107,6 +107,7 @@ struct DevScene {
     // support-width tables: per shape and cube-map cell an upper bound of h(d) = max_v (v - centre) . d over the unit
     // directions d of the cell.  centre distance - h_A(d) - h_B(-d) along the line of centres is a lower bound of the
     // pair distance that is far tighter than bounding spheres for elongated hulls (planning kernels).
+    const uint4* scene_img;  // device image of the tables every geometry CTA stages into shared memory (SceneImage)
     const float* hwidth;  // device
     const uint32_t* lut;  // device, n_lut_words (support-direction tables of all shapes that have one)
     int n_lut_words;

@@ -77,26 +77,13 @@ struct SceneSmem {
     float contact_thresh[SM_MAX_OBSTACLES][SM_MAX_MOV_ROBOT];
 };
 
-__device__ __forceinline__ void stage_scene(SceneSmem& s, int tid, int nthreads) {
-    // word-wise copy of the (contiguous, 4-byte aligned) pieces out of constant memory
-    for (int i = tid; i < (int)(sizeof(DevShape) / 4) * c_sc.n_shapes; i += nthreads)
-        reinterpret_cast<int*>(s.shapes)[i] = reinterpret_cast<const int*>(c_sc.shapes)[i];
-    for (int i = tid; i < SM_MAX_JOINTS * 9; i += nthreads) (&s.jR[0][0])[i] = (&c_sc.jR[0][0])[i];
-    for (int i = tid; i < SM_MAX_JOINTS * 3; i += nthreads) {
-        (&s.jt[0][0])[i] = (&c_sc.jt[0][0])[i];
-        (&s.jaxis[0][0])[i] = (&c_sc.jaxis[0][0])[i];
-    }
-    for (int i = tid; i < SM_MAX_PAIRS * 2; i += nthreads) {
-        (&s.static_pairs[0][0])[i] = (&c_sc.static_pairs[0][0])[i];
-        (&s.self_pairs[0][0])[i] = (&c_sc.self_pairs[0][0])[i];
-    }
-    for (int i = tid; i < SM_MAX_MOV_ROBOT; i += nthreads) {
-        s.mov_reward[i] = c_sc.mov_reward[i];
-        s.mov_contact[i] = c_sc.mov_contact[i];
-    }
-    for (int i = tid; i < SM_MAX_OBSTACLES * SM_MAX_MOV_ROBOT; i += nthreads)
-        (&s.contact_thresh[0][0])[i] = (&c_sc.contact_thresh[0][0])[i];
-}
+// What a geometry CTA stages into shared memory, as one contiguous image in global memory (built on the host in
+// smenv_create): 16-byte vector copies instead of divergent (serialised) constant-memory reads.
+struct SceneImage {
+    SceneSmem scene;
+    uint32_t pair_tab[SM_MAX_PLAN_PAIRS];
+};
+static_assert(sizeof(SceneImage) % 16 == 0, "SceneImage is copied in 16-byte vectors");
 
 // ------------------------------------------------------------------------------------------------------------------
 // forward kinematics of the serial chain by a warp scan:  lane j builds L_j = [R_fix Rot(axis, q_j) | t_fix], an

@@ -50,6 +50,7 @@ __device__ __forceinline__ float funkey(unsigned k) {
 }
 
 // shared memory of gjk_kernel: hull vertices | direction tables | shapes
+static_assert(sizeof(DevShape) % 16 == 0, "DevShape is copied in 16-byte vectors");
 struct GjkSmem {
     float4* verts;
     uint32_t* lut;
@@ -123,9 +124,10 @@ __global__ void __launch_bounds__(256, GJK_MIN_BLOCKS) gjk_kernel(GjkArgs A) {
     if ((long long)blockIdx.x * (blockDim.x >> 5) * chunk >= n_items) return;  // nothing for this block: no staging
     GjkSmem G = gjk_carve(smem_raw);
     for (int i = tid; i < c_sc.n_verts; i += blockDim.x) G.verts[i] = __ldg(c_sc.verts + i);
-    for (int i = tid; i < c_sc.n_lut_words; i += blockDim.x) G.lut[i] = __ldg(c_sc.lut + i);
-    for (int i = tid; i < (int)(sizeof(DevShape) / 4) * c_sc.n_shapes; i += blockDim.x)
-        reinterpret_cast<int*>(G.shapes)[i] = reinterpret_cast<const int*>(c_sc.shapes)[i];
+    for (int i = tid; i < c_sc.n_lut_words / 4; i += blockDim.x)   // n_lut_words is padded to a multiple of 4
+        reinterpret_cast<uint4*>(G.lut)[i] = __ldg(reinterpret_cast<const uint4*>(c_sc.lut) + i);
+    for (int i = tid; i < (int)(sizeof(DevShape) / 16) * c_sc.n_shapes; i += blockDim.x)  // SceneImage starts with the shapes
+        reinterpret_cast<uint4*>(G.shapes)[i] = __ldg(c_sc.scene_img + i);
     __syncthreads();
     int cursor = (blockIdx.x * (blockDim.x >> 5) + (tid >> 5)) * chunk;
     const int end = cursor + chunk < n_items ? cursor + chunk : n_items;

@@ -17,8 +17,8 @@ struct WarpScratch {
 };
 
 struct BlockShared {
-    SceneSmem scene;
-    uint32_t pair_tab[SM_MAX_PLAN_PAIRS];
+    SceneSmem scene;                        // \ the first two members mirror SceneImage
+    uint32_t pair_tab[SM_MAX_PLAN_PAIRS];   // /
     double stats[16];
     unsigned long long counters[16];
 };
@@ -49,8 +49,8 @@ __device__ __forceinline__ SmemLayout block_prologue(unsigned char* raw, bool wi
     const int tid = threadIdx.x;
     if (with_verts)
         for (int i = tid; i < c_sc.n_verts; i += blockDim.x) L.verts[i] = __ldg(c_sc.verts + i);
-    stage_scene(L.bs->scene, tid, blockDim.x);
-    for (int i = tid; i < c_sc.n_pairs; i += blockDim.x) L.bs->pair_tab[i] = c_sc.pair_tab[i];
+    for (int i = tid; i < (int)(sizeof(SceneImage) / 16); i += blockDim.x)
+        reinterpret_cast<uint4*>(L.bs)[i] = __ldg(c_sc.scene_img + i);   // BlockShared starts with the SceneImage members
     if (tid < 16) L.bs->stats[tid] = 0.0;
     if (tid < 16) L.bs->counters[tid] = 0ull;
     __syncthreads();
