@@ -123,12 +123,20 @@ __global__ void __launch_bounds__(256, GJK_MIN_BLOCKS) gjk_kernel(GjkArgs A) {
     const int chunk = (n_items + n_warps - 1) / n_warps;
     if ((long long)blockIdx.x * (blockDim.x >> 5) * chunk >= n_items) return;  // nothing for this block: no staging
     GjkSmem G = gjk_carve(smem_raw);
-    for (int i = tid; i < c_sc.n_verts; i += blockDim.x) G.verts[i] = __ldg(c_sc.verts + i);
-    for (int i = tid; i < c_sc.n_lut_words / 4; i += blockDim.x)   // n_lut_words is padded to a multiple of 4
-        reinterpret_cast<uint4*>(G.lut)[i] = __ldg(reinterpret_cast<const uint4*>(c_sc.lut) + i);
-    for (int i = tid; i < (int)(sizeof(DevShape) / 16) * c_sc.n_shapes; i += blockDim.x)  // SceneImage starts with the shapes
-        reinterpret_cast<uint4*>(G.shapes)[i] = __ldg(c_sc.scene_img + i);
-    __syncthreads();
+    // hulls, direction tables and shapes -> shared memory: three bulk TMA copies issued by one thread
+    __shared__ __align__(8) uint64_t stage_bar;
+    if (tid == 0) {
+        mbar_init(&stage_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        const uint32_t b_verts = (uint32_t)c_sc.n_verts * 16u, b_lut = (uint32_t)c_sc.n_lut_words * 4u,
+                       b_shapes = (uint32_t)c_sc.n_shapes * (uint32_t)sizeof(DevShape);
+        mbar_expect_tx(&stage_bar, b_verts + b_lut + b_shapes);
+        tma_bulk_g2s(G.verts, c_sc.verts, b_verts, &stage_bar);
+        tma_bulk_g2s(G.lut, c_sc.lut, b_lut, &stage_bar);
+        tma_bulk_g2s(G.shapes, c_sc.scene_img, b_shapes, &stage_bar);   // SceneImage starts with the shapes
+    }
+    __syncthreads();                 // the barrier init is visible to everyone
+    mbar_wait(&stage_bar, 0);
     int cursor = (blockIdx.x * (blockDim.x >> 5) + (tid >> 5)) * chunk;
     const int end = cursor + chunk < n_items ? cursor + chunk : n_items;
     unsigned c_iters = 0, c_dots = 0, c_calls = 0;
