@@ -229,6 +229,11 @@ __device__ __forceinline__ void frames_from_q64(const SceneSmem& sm, double q, X
     sincos(q, &s, &c);
     fk_scan(sm, (float)c, (float)s, out, lane);
 }
+__device__ __forceinline__ void frames_from_q32f(const SceneSmem& sm, float q, Xf* out, int lane) {
+    float s, c;
+    sincosf(q, &s, &c);
+    fk_scan(sm, c, s, out, lane);
+}
 __device__ __forceinline__ void frames_from_q32(const SceneSmem& sm, const float* qrow, Xf* out, int lane) {
     float s, c;
     sincosf(qrow[lane & 7], &s, &c);

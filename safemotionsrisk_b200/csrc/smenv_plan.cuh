@@ -361,15 +361,15 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) distance_plan_kernel(
                 const int k_end = ball_k_end(W.ob);
                 int adv = S;
                 if (k_end <= S) { adv = k_end; active = false; }  // retired inside the step without hitting the robot
-#pragma unroll 1
-                for (int i = 0; i < adv; ++i) ball_t = xadd(ball_t, dt);  // self._t += update_time_step
+                ball_t += (double)adv * dt;   // pose for the float32 geometry only: the exact repeated addition of
+                                              // self._t happens in finish_kernel, where the state is written
             }
             if (!active) moving = false;  // not in the list of observed obstacles (ctlp.py:3239-3245)
             if (lane == 0) ball_pose(W.ob, ball_t, W.obx[0]);
         } else {
             moving = false;
         }
-        frames_from_q64(sm, q1, W.fr, lane);
+        frames_from_q32f(sm, (float)q1, W.fr, lane);
         if (lane < SM_RES_STRIDE)
             A.res[(size_t)env * SM_RES_STRIDE + lane] = lane == 3 ? SM_RES_NO_CONTACT
                                                                    : fkey(lane == GJK_MOVING ? query + 0.002f : cap);

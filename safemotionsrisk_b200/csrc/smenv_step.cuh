@@ -93,15 +93,17 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
         if (ds < c_sc.collision_dist) { ds = 0.0; c_static = 1; }
         if (dse < c_sc.collision_dist) { dse = 0.0; c_self = 1; }
         if (dm < c_sc.collision_dist) { dm = 0.0; c_moving = 1; }
+        // distance rewards and action punishment in float32: their inputs are float32 (GJK distances, the action)
+        // and the contract on rewards is 1e-4 relative, not bit-exactness (only the state is float64-exact)
         double r_self = 0.0, r_static = 0.0, r_moving;
-        if (c_sc.w_self != 0.0) { double r = fmin(1.0, dse / c_sc.d_self); r_self = r * r; }
-        if (c_sc.w_static != 0.0) { double r = fmin(1.0, ds / c_sc.d_static); r_static = r * r; }
-        { double r = fmin(1.0, dm / c_sc.d_moving); r_moving = r * r; }
+        if (c_sc.w_self != 0.0) { float r = fminf(1.0f, (float)dse / (float)c_sc.d_self); r_self = (double)(r * r); }
+        if (c_sc.w_static != 0.0) { float r = fminf(1.0f, (float)ds / (float)c_sc.d_static); r_static = (double)(r * r); }
+        { float r = fminf(1.0f, (float)dm / (float)c_sc.d_moving); r_moving = (double)(r * r); }
         double action_punishment = 1.0;
         if (c_sc.punish_action) {
-            double pu = ((double)umax - c_sc.action_thresh) / (1.0 - c_sc.action_thresh);  // rewards.py:18-21
-            pu = fmax(0.0, fmin(1.0, pu));
-            action_punishment = pu * pu;
+            float pu = (umax - (float)c_sc.action_thresh) / (1.0f - (float)c_sc.action_thresh);  // rewards.py:18-21
+            pu = fmaxf(0.0f, fminf(1.0f, pu));
+            action_punishment = (double)(pu * pu);
         }
         double low_acc = 0.0, low_vel = 0.0;
         if (c_sc.w_low_acc != 0.0 || c_sc.w_low_vel != 0.0) {  // rewards.py:448-460
