@@ -14,6 +14,8 @@ struct WarpScratch {
     Xf fr2[1 + SM_MAX_JOINTS];              // robot frames of one sub-step (narrow phase)
     Xf obx[SM_MAX_OBSTACLES];               // obstacle poses at the end of the step
     Xf obx2[SM_MAX_OBSTACLES];              // obstacle poses of one sub-step
+    float pc[SM_MAX_SHAPES][3];             // world position of every shape's bounding-sphere centre (distance planning)
+    float pg[SM_MAX_SHAPES][3];             // world position of every shape's centroid
 };
 
 struct BlockShared {

@@ -51,14 +51,17 @@ __device__ __forceinline__ void rel_pose(const Xf& TA, const Xf& TB, float* R, f
 
 // Lower bound of the distance between shapes A and B (minus both margins) from the support-width tables: separation
 // along the line between the bounding-sphere centres.
-__device__ __forceinline__ float axis_lower_bound(const DevShape& SA, const DevShape& SB, const Xf& TA, const Xf& TB) {
-    const V3 d = xf_apply(TB, SB.cx, SB.cy, SB.cz) - xf_apply(TA, SA.cx, SA.cy, SA.cz);  // A towards B
+__device__ __forceinline__ float axis_lower_bound_d(const DevShape& SA, const DevShape& SB, const Xf& TA, const Xf& TB,
+                                                    V3 d /* centre of B - centre of A, world frame */) {
     const float dist = sqrtf(dot(d, d));
     if (!(dist > 1e-9f)) return -FLT_MAX;
     const V3 da = xf_rot_t(TA, d), db = xf_rot_t(TB, mk(-d.x, -d.y, -d.z));
     const float ha = __ldg(c_sc.hwidth + SA.hw + lut_cell(da.x, da.y, da.z));
     const float hb = __ldg(c_sc.hwidth + SB.hw + lut_cell(db.x, db.y, db.z));
     return dist * (1.0f - 1e-6f) - ha - hb - SA.margin - SB.margin;
+}
+__device__ __forceinline__ float axis_lower_bound(const DevShape& SA, const DevShape& SB, const Xf& TA, const Xf& TB) {
+    return axis_lower_bound_d(SA, SB, TA, TB, xf_apply(TB, SB.cx, SB.cy, SB.cz) - xf_apply(TA, SA.cx, SA.cy, SA.cz));
 }
 
 __device__ __forceinline__ void write_item(GjkItem* dst, int env, int ia, int ib, int cls, int sub, float thr,
@@ -374,6 +377,16 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) distance_plan_kernel(
             A.res[(size_t)env * SM_RES_STRIDE + lane] = lane == 3 ? SM_RES_NO_CONTACT
                                                                    : fkey(lane == GJK_MOVING ? query + 0.002f : cap);
         __syncwarp();
+        // ---------------- world positions of every shape's sphere centre and centroid, once per env
+#pragma unroll 1
+        for (int sI = lane; sI < c_sc.n_shapes; sI += 32) {
+            const DevShape& sh = sm.shapes[sI];
+            const Xf& T = *frame_ptr(sh, W.fr, W.obx);
+            const V3 c = xf_apply(T, sh.cx, sh.cy, sh.cz), g = xf_apply(T, sh.gx, sh.gy, sh.gz);
+            W.pc[sI][0] = c.x; W.pc[sI][1] = c.y; W.pc[sI][2] = c.z;
+            W.pg[sI][0] = g.x; W.pg[sI][1] = g.y; W.pg[sI][2] = g.z;
+        }
+        __syncwarp();
         // ---------------- pass 1 (lanes = pairs): the best upper bound of each class (distance of the hull centroids)
         const int np = moving ? n_pairs : n_fixed;
         float ub_s = cap, ub_e = cap, ub_m = query;
@@ -384,8 +397,7 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) distance_plan_kernel(
             const int ia = (int)(e & 0xfffu), ib = (int)((e >> 12) & 0xfffu), cls = (int)(e >> 24);
             const DevShape& SA = sm.shapes[ia];
             const DevShape& SB = sm.shapes[ib];
-            const V3 g = xf_apply(*frame_ptr(SA, W.fr, W.obx), SA.gx, SA.gy, SA.gz) -
-                         xf_apply(*frame_ptr(SB, W.fr, W.obx), SB.gx, SB.gy, SB.gz);
+            const V3 g = mk(W.pg[ia][0] - W.pg[ib][0], W.pg[ia][1] - W.pg[ib][1], W.pg[ia][2] - W.pg[ib][2]);
             const float ub = sqrtf(dot(g, g)) * (1.0f + 1e-6f) + 1e-7f - SA.margin - SB.margin;
             if (cls == GJK_STATIC) ub_s = fminf(ub_s, ub);
             else if (cls == GJK_SELF) ub_e = fminf(ub_e, ub);
@@ -424,9 +436,20 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) distance_plan_kernel(
                 const uint32_t e = pair_tab[p];
                 ia = (int)(e & 0xfffu); ib = (int)((e >> 12) & 0xfffu); cls = (int)(e >> 24);
                 thr = cls == GJK_STATIC ? ub_s : cls == GJK_SELF ? ub_e : ub_m;
-                emit = pair_lower_bound(sm, ia, ib, W.fr, W.obx) <= thr &&
-                       axis_lower_bound(sm.shapes[ia], sm.shapes[ib], *frame_ptr(sm.shapes[ia], W.fr, W.obx),
-                                        *frame_ptr(sm.shapes[ib], W.fr, W.obx)) <= thr;
+                const DevShape& SA = sm.shapes[ia];
+                const DevShape& SB = sm.shapes[ib];
+                const V3 ca = mk(W.pc[ia][0], W.pc[ia][1], W.pc[ia][2]);
+                if (SB.frame == 0) {  // static shape in the world frame: sphere against its axis-aligned box
+                    const float dx = fmaxf(fmaxf(SB.bmin[0] - ca.x, ca.x - SB.bmax[0]), 0.f);
+                    const float dy = fmaxf(fmaxf(SB.bmin[1] - ca.y, ca.y - SB.bmax[1]), 0.f);
+                    const float dz = fmaxf(fmaxf(SB.bmin[2] - ca.z, ca.z - SB.bmax[2]), 0.f);
+                    emit = sqrtf(dx * dx + dy * dy + dz * dz) - SA.radius - SA.margin - SB.margin <= thr;
+                } else {
+                    const V3 d = mk(W.pc[ib][0] - ca.x, W.pc[ib][1] - ca.y, W.pc[ib][2] - ca.z);
+                    emit = sqrtf(dot(d, d)) - SA.radius - SB.radius - SA.margin - SB.margin <= thr;
+                }
+                if (emit) emit = axis_lower_bound_d(SA, SB, *frame_ptr(SA, W.fr, W.obx), *frame_ptr(SB, W.fr, W.obx),
+                                                    mk(W.pc[ib][0] - ca.x, W.pc[ib][1] - ca.y, W.pc[ib][2] - ca.z)) <= thr;
             }
             const unsigned em = __ballot_sync(FULL, emit);
             if (em) {
