@@ -5,15 +5,15 @@
 //   risk(obs, action) = sigmoid(W4 selu(W3 selu(W2 selu(W1 [obs, action]))))      30 -> 512 -> 256 -> 128 -> 1
 //   backup(obs)       = tanh(W3 swish(W2 swish(W1 obs)))[0:7]                      23 -> 256 -> 128 -> 14
 //
-// One CTA (256 threads) owns a tile of 128 envs = the 128 rows of a tcgen05.mma (cta_group::1, M = 128) and runs the
+// One CTA (512 threads) owns a tile of 128 envs = the 128 rows of a tcgen05.mma (cta_group::1, M = 128) and runs the
 // whole network on it without leaving the SM:
 //   * activations live in shared memory as fp16 in the canonical K-major no-swizzle UMMA layout (8x16-byte core
 //     matrices, SBO = 128 B between 8-row groups, LBO = 2048 B between 8-column groups), weights are packed into the
 //     same layout on the host once and streamed through shared memory in 64-column K chunks;
 //   * one thread issues tcgen05.mma.kind::f16 (fp16 x fp16 -> fp32) into TMEM (N = 512 as two N = 256 instructions),
 //     tcgen05.commit signals an mbarrier;
-//   * the epilogue reads the accumulator row of each env with tcgen05.ld (two threads per TMEM lane, half of the
-//     columns each), adds the bias,
+//   * the epilogue reads the accumulator row of each env with tcgen05.ld (four threads per TMEM lane, a quarter of
+//     the columns each: the epilogue is latency-bound, more warps hide it), adds the bias,
 //     applies selu / swish and writes the next layer's operand straight back to shared memory; the last hidden layer
 //     is contracted with the tiny output layer on the CUDA cores while it is still in registers.
 //   * the weight chunks stream through two 32 KB buffers with 1-D bulk TMA (cp.async.bulk -> mbarrier complete_tx),
@@ -27,7 +27,8 @@
 #define MLP_MAX_TC 3
 #define MLP_MAX_OUT 8
 #define MLP_TILE_M 128
-#define MLP_THREADS 256 /* two warps per TMEM lane quarter: each handles half of the accumulator columns */
+#define MLP_THREADS 512 /* four warps per TMEM lane quarter: each handles a quarter of the accumulator columns */
+#define MLP_PARTS (MLP_THREADS / MLP_TILE_M)
 #define MLP_CHUNK_K 64
 #define MLP_MAX_WIDTH 512
 
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(MlpArgs A) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mlp_smem + MLP_SM_BAR + 48);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int rtid = tid & (MLP_TILE_M - 1);   // row of the tile this thread serves
-    const int half = tid >> 7;                 // which half of the columns / input segments
+    const int half = tid >> 7;                 // which quarter of the columns / input segments this thread handles
     const int quarter = warp & 3;              // TMEM lane quarter the warp may access
     const MlpNet& net = A.net;
     const int n_last = net.dims[net.n_tc - 1];
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(MlpArgs A) {
         const int row = tile * MLP_TILE_M + rtid;
         const bool valid = row < A.n;
         // ---------------- input rows -> fp16 operand of the first layer
-        for (int kc = half; kc < net.k_in / 8; kc += 2) {
+        for (int kc = half; kc < net.k_in / 8; kc += MLP_PARTS) {
             __align__(16) __half h[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(MlpArgs A) {
             const bool last = l == net.n_tc - 1;
             const float* bl = bias + l * MLP_MAX_WIDTH;
 #pragma unroll 1
-            for (int c0 = half * (N / 2); c0 < (half + 1) * (N / 2); c0 += 32) {
+            for (int c0 = half * (N / MLP_PARTS); c0 < (half + 1) * (N / MLP_PARTS); c0 += 32) {
                 float r[32];
                 tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
 #pragma unroll
@@ -270,11 +271,20 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(MlpArgs A) {
                             *reinterpret_cast<const uint4*>(h);
                     }
                 } else {
+                    if (net.n_out == 1) {   // the risk network: one output column
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
+                        for (int j = 0; j < 32; ++j) acc_out[0] = fmaf(r[j], w_out[(c0 + j) * MLP_MAX_OUT], acc_out[0]);
+                    } else {
 #pragma unroll
-                        for (int o = 0; o < MLP_MAX_OUT; ++o)
-                            if (o < net.n_out) acc_out[o] = fmaf(r[j], w_out[(c0 + j) * MLP_MAX_OUT + o], acc_out[o]);
+                        for (int j = 0; j < 32; ++j) {
+                            const float4 wa = *reinterpret_cast<const float4*>(w_out + (c0 + j) * MLP_MAX_OUT);
+                            const float4 wb = *reinterpret_cast<const float4*>(w_out + (c0 + j) * MLP_MAX_OUT + 4);
+                            acc_out[0] = fmaf(r[j], wa.x, acc_out[0]); acc_out[1] = fmaf(r[j], wa.y, acc_out[1]);
+                            acc_out[2] = fmaf(r[j], wa.z, acc_out[2]); acc_out[3] = fmaf(r[j], wa.w, acc_out[3]);
+                            acc_out[4] = fmaf(r[j], wb.x, acc_out[4]); acc_out[5] = fmaf(r[j], wb.y, acc_out[5]);
+                            acc_out[6] = fmaf(r[j], wb.z, acc_out[6]); acc_out[7] = fmaf(r[j], wb.w, acc_out[7]);
+                        }
+                    }
                 }
             }
             tc_fence_before();
@@ -283,13 +293,16 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(MlpArgs A) {
             a_src = smem_u32(a_act);
             K = N;
         }
-        // the two column halves of a row meet in shared memory
-        if (half == 1)
-            for (int o = 0; o < net.n_out; ++o) part[rtid * MLP_MAX_OUT + o] = acc_out[o];
+        // the column quarters of a row meet in shared memory
+        if (half == 0)
+            for (int o = 0; o < MLP_MAX_OUT; ++o) part[rtid * MLP_MAX_OUT + o] = acc_out[o];
+        __syncthreads();
+        if (half != 0)
+            for (int o = 0; o < net.n_out; ++o) atomicAdd(&part[rtid * MLP_MAX_OUT + o], acc_out[o]);
         __syncthreads();
         if (valid && half == 0) {
             for (int o = 0; o < net.n_out; ++o) {
-                const float x = acc_out[o] + part[rtid * MLP_MAX_OUT + o] + __ldg(net.b_out + o);
+                const float x = part[rtid * MLP_MAX_OUT + o] + __ldg(net.b_out + o);
                 A.out[(size_t)row * A.out_stride + o] = net.out_act == MLP_OUT_SIGMOID ? 1.0f / (1.0f + __expf(-x)) : tanhf(x);
             }
         }
