@@ -68,7 +68,7 @@ enum SmInfoSlot {
     SM_INFO_RANGE_CODE = 12,    /* OR of the per-joint violation codes of the range used for this step */
     SM_INFO_CONTACT_LATCH = 13, /* 1 if a sub-step contact with a moving obstacle was latched (ctlp.py:2631-2637) */
     SM_INFO_MAX_JERK_REL = 14,  /* max_j |jerk_j| / jerk_max_j of the step (rewards.py:181-203) */
-    SM_INFO_RESERVED = 15
+    SM_INFO_TP_REWARD = 15      /* target_point_reward (rewards.py:345-348) */
 };
 
 /* Slots of the per-env obstacle record (SM_OBST_STRIDE doubles per env; integers are stored exactly as doubles). */
@@ -183,8 +183,33 @@ typedef struct SmScene {
     double ball_target_min_static; /* clearances of the random pose a ball is aimed at (ctlp.py:1725-1728) */
     double ball_target_min_self;
     int32_t has_table;             /* obstacle_scene != 0 (ctlp.py:1890) */
-    int32_t reserved2;
+    int32_t start_at_rest;         /* not collision_avoidance_mode: start states have zero velocity and acceleration
+                                      (ctlp.py:1461-1500) */
+    /* --- target points of the reaching task (SafeMotionsEnv / TargetPointReachingReward: rewards.py:303-396;
+     *     ctlp.py:1658-1720, :2210-2350, :2787-2821); single robot, target_point_sequence 0 */
+    int32_t use_target_points;
+    int32_t tp_normalize;          /* normalize_reward_to_initial_target_point_distance */
+    int32_t obs_add_tp_pos, obs_add_tp_rel; /* obs_add_target_point_pos / _relative_pos (observations.py:326-340) */
+    double tp_radius;              /* target_point_radius */
+    double tp_bonus;               /* target_point_reached_reward_bonus */
+    double tp_reward_factor;       /* target_point_reward_factor */
+    double tp_box_min[3], tp_box_max[3]; /* target_point_cartesian_range (sampling and position normalisation) */
+    double tp_rel_min[3], tp_rel_max[3]; /* target_point_relative_pos_min_max (ctlp.py:184) */
+    double tp_min_static, tp_min_self;   /* clearances of the pose a target point is sampled from (ctlp.py:1661-1664) */
 } SmScene;
+
+#define SM_TP_STRIDE 12 /* doubles per env in the target-point record */
+/* Slots of the per-env target-point record (SmBuffers.target). */
+enum SmTargetSlot {
+    SM_TP_POS = 0,        /* target point xyz */
+    SM_TP_LAST_DIST = 3,  /* _last_target_point_distance_list (ctlp.py:2242) */
+    SM_TP_INIT_DIST = 4,  /* _initial_target_point_distance_list[-1] (ctlp.py:2244-2245) */
+    SM_TP_ACTIVE = 5,     /* _target_point_active_list */
+    SM_TP_REACHED_N = 6,  /* _num_target_points_reached_list */
+    SM_TP_LINK_POS = 7,   /* _target_link_pos_list: target link point at the current knot (setpoint pose) xyz */
+    SM_TP_DRAWS = 10,     /* target points drawn from the pool so far (Philox counter) */
+    SM_TP_REACHED = 11    /* 1 if the target point was reached in the step just finished */
+};
 
 /* Device buffers of one call (all caller-owned, N = num_envs). */
 typedef struct SmBuffers {
@@ -199,6 +224,7 @@ typedef struct SmBuffers {
     int32_t* term_reason; /* [N] */
     float* info;          /* [N][SM_INFO_STRIDE] */
     double* stats;        /* [32] episode statistics accumulated with atomics (train.py:59-117); may be NULL */
+    double* target;       /* [N][SM_TP_STRIDE] target-point records; NULL unless the scene uses target points */
 } SmBuffers;
 
 typedef struct SmCounters {
@@ -242,6 +268,10 @@ int smenv_copy_pools(SmEnv* env, double* host_start, double* host_ball);
 /* Injects a start state (parity protocol).  Host or device pointers are both accepted; mask==NULL means all envs. */
 int smenv_set_state(SmEnv* env, const SmBuffers* buf, const double* q, const double* v, const double* a,
                     const double* obst, const uint8_t* mask, SmStream stream);
+/* Reaching task: injects the first target point of every (masked) env ([N][3], host or device) after smenv_set_state
+ * (parity protocol; the reference samples it by rejection, ctlp.py:1658-1720) and rewrites the observation. */
+int smenv_set_targets(SmEnv* env, const SmBuffers* buf, const double* first_target, const uint8_t* mask,
+                      SmStream stream);
 /* Resets the masked envs (NULL = all) from the pools and writes their first observation. */
 int smenv_reset(SmEnv* env, const SmBuffers* buf, const uint8_t* mask, SmStream stream);
 /* One env step for all N envs.  auto_reset != 0 re-initialises finished envs from the pools inside the same launch

@@ -110,8 +110,9 @@ class OracleEnvs:
         self.done = np.zeros(n, dtype=np.uint8)
         self.term = np.zeros(n, dtype=np.int32)
         self.info = np.zeros((n, abi.SM_INFO_STRIDE), dtype=np.float32)
+        self.tp = np.zeros((n, abi.SM_TP_STRIDE)) if scene.struct.use_target_points else None
 
-    def set_state(self, q, v, a, obst=None):
+    def set_state(self, q, v, a, obst=None, first_target=None):
         nj = self.scene.n_joints
         self.kin[:] = 0
         self.kin[:, 0:nj], self.kin[:, 8:8 + nj], self.kin[:, 16:16 + nj] = q, v, a
@@ -123,20 +124,42 @@ class OracleEnvs:
             self.obst[:] = obst
         self.episode[:] = 0
         self.ep_return[:] = 0
+        if self.tp is not None:
+            ft = np.ascontiguousarray(first_target, dtype=np.float64).reshape(self.n, 3)
+            for e in range(self.n):
+                lib().smo_target_init(self.scene.pointer(), _p(self.kin[e], C.c_double), _p(self.tp[e], C.c_double),
+                                      _p(ft[e], C.c_double))
         for e in range(self.n):
-            self.obs[e] = observation(self.scene, self.kin[e], self.obst[e])
+            if self.tp is not None:
+                lib().smo_observation_tp(self.scene.pointer(), _p(self.kin[e], C.c_double), _p(self.obst[e], C.c_double),
+                                         _p(self.tp[e], C.c_double), _p(self.obs[e], C.c_float))
+            else:
+                self.obs[e] = observation(self.scene, self.kin[e], self.obst[e])
 
-    def step(self, actions, next_ball=None):
+    def step(self, actions, next_ball=None, next_target=None):
         actions = np.ascontiguousarray(actions, dtype=np.float32)
         nb = None
         if next_ball is not None:
             nb = np.ascontiguousarray(next_ball, dtype=np.float64)
-        lib().smo_step_batch(self.scene.pointer(), self.n, _p(self.kin, C.c_double), _p(self.obst, C.c_double),
-                             _p(self.episode, C.c_int32), _p(self.ep_return, C.c_double), _p(actions, C.c_float),
-                             _p(nb, C.c_double) if nb is not None else None, _p(self.obs, C.c_float),
-                             _p(self.reward, C.c_float), _p(self.done, C.c_uint8), _p(self.term, C.c_int32),
-                             _p(self.info, C.c_float))
+        nt = None
+        if next_target is not None:
+            nt = np.ascontiguousarray(next_target, dtype=np.float64).reshape(self.n, 3)
+        lib().smo_step_batch_tp(self.scene.pointer(), self.n, _p(self.kin, C.c_double), _p(self.obst, C.c_double),
+                                _p(self.tp, C.c_double) if self.tp is not None else None,
+                                _p(self.episode, C.c_int32), _p(self.ep_return, C.c_double), _p(actions, C.c_float),
+                                _p(nb, C.c_double) if nb is not None else None,
+                                _p(nt, C.c_double) if nt is not None else None, _p(self.obs, C.c_float),
+                                _p(self.reward, C.c_float), _p(self.done, C.c_uint8), _p(self.term, C.c_int32),
+                                _p(self.info, C.c_float))
         return self.obs, self.reward, self.done, self.term, self.info
+
+
+def target_link_point(scene, q):
+    out = np.zeros(3)
+    qq = np.zeros(8)
+    qq[:scene.n_joints] = q
+    lib().smo_target_link_point(scene.pointer(), _p(qq, C.c_double), _p(out, C.c_double))
+    return out
 
 
 def philox(c0, c1, c2, c3, k0, k1):

@@ -563,12 +563,22 @@ static float clip1(double x) {
     if (f < -1.0f) f = -1.0f;
     return f;
 }
-void smo_observation(const SmScene* sc, const double* kin, const double* ob, float* obs) {
+void smo_observation_tp(const SmScene* sc, const double* kin, const double* ob, const double* tp, float* obs) {
     int nj = sc->n_joints, k = 0;
     const double *q = kin, *v = kin + 8, *a = kin + 16;
     for (int j = 0; j < nj; ++j) obs[k++] = clip1(-1.0 + 2.0 * (q[j] - sc->pos_lo[j]) / (sc->pos_hi[j] - sc->pos_lo[j]));
     for (int j = 0; j < nj; ++j) obs[k++] = clip1(v[j] / sc->vel_max[j]);
     for (int j = 0; j < nj; ++j) obs[k++] = clip1(a[j] / sc->acc_max[j]);
+    if (sc->use_target_points && tp) { /* observations.py:326-340; ctlp.py:2247-2271 (the target point is active) */
+        if (sc->obs_add_tp_pos)
+            for (int i = 0; i < 3; ++i)
+                obs[k++] = clip1(-1.0 + 2.0 * (tp[SM_TP_POS + i] - sc->tp_box_min[i]) / (sc->tp_box_max[i] - sc->tp_box_min[i]));
+        if (sc->obs_add_tp_rel)
+            for (int i = 0; i < 3; ++i) {
+                double rel = tp[SM_TP_POS + i] - tp[SM_TP_LINK_POS + i];
+                obs[k++] = clip1(-1.0 + 2.0 * (rel - sc->tp_rel_min[i]) / (sc->tp_rel_max[i] - sc->tp_rel_min[i]));
+            }
+    }
     for (int o = 0; o < sc->n_obstacles; ++o) {
         if (sc->obst_kind[o] == SM_OBST_BALL) { /* position then velocity, both normalised (ctlp.py:2364-2377) */
             double p[3], t = ob[SM_OB_BALL_T];
@@ -596,6 +606,22 @@ void smo_observation(const SmScene* sc, const double* kin, const double* ob, flo
     }
 }
 
+void smo_observation(const SmScene* sc, const double* kin, const double* ob, float* obs) {
+    smo_observation_tp(sc, kin, ob, 0, obs);
+}
+
+/* target link point of a pose: frame of the last joint o fixed transform to the target link o target_link_offset
+ * (LinkPointBase.get_position, ctlp.py:4962-5075) */
+void smo_target_link_point(const SmScene* sc, const double* q, double* p) {
+    Xf fr[1 + SM_MAX_JOINTS];
+    smo_fk(sc, q, fr);
+    double loc[3], w[3];
+    mat_vec(sc->target_R, sc->target_offset, loc);
+    for (int i = 0; i < 3; ++i) loc[i] += sc->target_t[i];
+    mat_vec(fr[sc->n_joints].R, loc, w);
+    for (int i = 0; i < 3; ++i) p[i] = w[i] + fr[sc->n_joints].t[i];
+}
+
 /* ------------------------------------------------------------------------------------------------------------
  * 8. One env step  (safe_motions_base.py:1043-1227)
  * ---------------------------------------------------------------------------------------------------------- */
@@ -610,8 +636,10 @@ typedef struct SmoStepOut {
 } SmoStepOut;
 
 /* kin: [q8 v8 a8 qact8], ob: obstacle record, episode_length in/out.  u: n_joints actions as doubles. */
-void smo_step(const SmScene* sc, double* kin, double* ob, int32_t* episode_length, double* ep_return,
-              const double* u, const double* next_ball, float* obs, SmoStepOut* out) {
+/* tp: target-point record (SM_TP_STRIDE doubles) or NULL; next_target: the target point that replaces a reached one
+ * (drawn by the caller, like next_ball, because the reference samples it with data-dependent rejection sampling). */
+void smo_step_tp(const SmScene* sc, double* kin, double* ob, double* tp, int32_t* episode_length, double* ep_return,
+                 const double* u, const double* next_ball, const double* next_target, float* obs, SmoStepOut* out) {
     int nj = sc->n_joints, S = sc->substeps;
     double *q = kin, *v = kin + 8, *a = kin + 16, *qa = kin + 24;
     int32_t code[SM_MAX_JOINTS];
@@ -640,10 +668,26 @@ void smo_step(const SmScene* sc, double* kin, double* ob, int32_t* episode_lengt
             }
         }
         /* motor tracking: q+ = q + kp (q_set - q) + track_vel dt v_set   */
+        double qset[SM_MAX_JOINTS];
         for (int j = 0; j < nj; ++j) {
             double qs, vs, as;
             interpolate(sc, q[j], v[j], a[j], out->a1[j], t, &qs, &vs, &as);
+            qset[j] = qs;
             qa[j] = qa[j] + sc->track_kp * (qs - qa[j]) + (sc->track_vel * dt) * vs;
+        }
+        /* target point reached? (ctlp.py:2787-2821; target link point of the setpoint pose,
+         * target_point_use_actual_position = False) */
+        if (sc->use_target_points && tp) {
+            smo_target_link_point(sc, qset, tp + SM_TP_LINK_POS);
+            if (tp[SM_TP_ACTIVE] != 0.0) {
+                double dx = tp[SM_TP_LINK_POS] - tp[SM_TP_POS], dy = tp[SM_TP_LINK_POS + 1] - tp[SM_TP_POS + 1],
+                       dz = tp[SM_TP_LINK_POS + 2] - tp[SM_TP_POS + 2];
+                if (sqrt(dx * dx + dy * dy + dz * dz) < sc->tp_radius) {
+                    tp[SM_TP_REACHED] = 1.0;
+                    tp[SM_TP_ACTIVE] = 0.0;
+                    tp[SM_TP_REACHED_N] += 1.0;
+                }
+            }
         }
         /* obstacle_wrapper.update (ctlp.py:2590-2862) */
         for (int o = 0; o < sc->n_obstacles; ++o) {
@@ -716,6 +760,24 @@ void smo_step(const SmScene* sc, double* kin, double* ob, int32_t* episode_lengt
     double reward = (1.0 - action_punishment) * sc->action_max_punishment + r_self * sc->w_self +
                     r_static * sc->w_static + r_moving * sc->w_moving + low_acc * sc->w_low_acc +
                     low_vel * sc->w_low_vel + bonus + punish;                         /* rewards.py:481-488 */
+    double tp_reward = 0.0;
+    if (sc->use_target_points && tp) { /* TargetPointReachingReward (rewards.py:303-396; ctlp.py:2309-2350) */
+        double norm = 1.0;
+        if ((tp[SM_TP_ACTIVE] != 0.0 || tp[SM_TP_REACHED] != 0.0) && sc->tp_normalize) {
+            norm = tp[SM_TP_INIT_DIST];
+            if (norm == 0.0) norm += 0.0000001;
+        }
+        if (tp[SM_TP_ACTIVE] != 0.0) {
+            double dx = tp[SM_TP_POS] - tp[SM_TP_LINK_POS], dy = tp[SM_TP_POS + 1] - tp[SM_TP_LINK_POS + 1],
+                   dz = tp[SM_TP_POS + 2] - tp[SM_TP_LINK_POS + 2];
+            tp_reward = (tp[SM_TP_LAST_DIST] - sqrt(dx * dx + dy * dy + dz * dz)) / (sc->ts * norm);
+        } else if (tp[SM_TP_REACHED] != 0.0) {
+            tp_reward = tp[SM_TP_LAST_DIST] / (sc->ts * norm) + sc->tp_bonus;
+        }
+        double pun = sc->punish_action ? action_punishment : 0.0; /* rewards.py:307, :317-318 */
+        reward = tp_reward * sc->tp_reward_factor - pun * sc->action_max_punishment + r_self * sc->w_self +
+                 r_static * sc->w_static + r_moving * sc->w_moving;               /* rewards.py:354-361 */
+    }
     /* --- termination priority self -> static -> moving -> length (safe_motions_base.py:1775-1799) */
     int done = 0, reason = SM_TERM_UNSET;
     if (sc->terminate_self && c_self) { done = 1; reason = SM_TERM_SELF_COLLISION; }
@@ -741,6 +803,7 @@ void smo_step(const SmScene* sc, double* kin, double* ob, int32_t* episode_lengt
     out->info[SM_INFO_RANGE_CODE] = (float)rcode;
     out->info[SM_INFO_CONTACT_LATCH] = (float)(ob[SM_OB_LATCH] != 0.0);
     out->info[SM_INFO_MAX_JERK_REL] = (float)jerk_rel;
+    out->info[SM_INFO_TP_REWARD] = (float)tp_reward;
     /* a ball that reached a final state is replaced when the next observation is taken (ctlp.py:2354-2360,
      * :2893-2895); the new launch (release point, speed vector, orientation, hit times) is an input here because
      * the reference draws it with data-dependent rejection sampling (ctlp.py:1723-1931). */
@@ -753,7 +816,40 @@ void smo_step(const SmScene* sc, double* kin, double* ob, int32_t* episode_lengt
         ob[SM_OB_BALL_NMAX] = next_ball[10];
         ob[SM_OB_BALL_NHIT] = next_ball[11];
     }
-    if (obs) smo_observation(sc, kin, ob, obs);
+    /* get_target_point_observation (ctlp.py:2210-2271): a reached point is replaced, distances are recorded */
+    if (sc->use_target_points && tp) {
+        if (tp[SM_TP_REACHED] != 0.0 && next_target) {
+            memcpy(tp + SM_TP_POS, next_target, 3 * sizeof(double));
+            tp[SM_TP_ACTIVE] = 1.0;
+            tp[SM_TP_INIT_DIST] = NAN;
+            tp[SM_TP_DRAWS] += 1.0;
+        }
+        tp[SM_TP_REACHED] = 0.0;
+        if (tp[SM_TP_ACTIVE] != 0.0) {
+            double dx = tp[SM_TP_POS] - tp[SM_TP_LINK_POS], dy = tp[SM_TP_POS + 1] - tp[SM_TP_LINK_POS + 1],
+                   dz = tp[SM_TP_POS + 2] - tp[SM_TP_LINK_POS + 2];
+            tp[SM_TP_LAST_DIST] = sqrt(dx * dx + dy * dy + dz * dz);
+            if (isnan(tp[SM_TP_INIT_DIST])) tp[SM_TP_INIT_DIST] = tp[SM_TP_LAST_DIST];
+        }
+    }
+    if (obs) smo_observation_tp(sc, kin, ob, tp, obs);
+}
+
+void smo_step(const SmScene* sc, double* kin, double* ob, int32_t* episode_length, double* ep_return,
+              const double* u, const double* next_ball, float* obs, SmoStepOut* out) {
+    smo_step_tp(sc, kin, ob, 0, episode_length, ep_return, u, next_ball, 0, obs, out);
+}
+
+/* start of an episode with target points: the first target point and its distances (ctlp.py:2216-2245) */
+void smo_target_init(const SmScene* sc, const double* kin, double* tp, const double* first_target) {
+    memset(tp, 0, SM_TP_STRIDE * sizeof(double));
+    smo_target_link_point(sc, kin, tp + SM_TP_LINK_POS);
+    memcpy(tp + SM_TP_POS, first_target, 3 * sizeof(double));
+    tp[SM_TP_ACTIVE] = 1.0;
+    tp[SM_TP_DRAWS] = 1.0;
+    double dx = tp[SM_TP_POS] - tp[SM_TP_LINK_POS], dy = tp[SM_TP_POS + 1] - tp[SM_TP_LINK_POS + 1],
+           dz = tp[SM_TP_POS + 2] - tp[SM_TP_LINK_POS + 2];
+    tp[SM_TP_LAST_DIST] = tp[SM_TP_INIT_DIST] = sqrt(dx * dx + dy * dy + dz * dz);
 }
 
 /* batch driver used by bench.py's CPU baseline and by the tests: steps n envs once. */
@@ -767,6 +863,24 @@ void smo_step_batch(const SmScene* sc, int n, double* kin, double* ob, int32_t* 
         smo_step(sc, kin + (size_t)e * SM_KIN_STRIDE, ob + (size_t)e * SM_OBST_STRIDE, episode + 4 * e,
                  ep_return + e, u, next_ball ? next_ball + (size_t)e * 12 : 0,
                  obs ? obs + (size_t)e * sc->obs_size : 0, &out);
+        reward[e] = out.reward;
+        done[e] = (uint8_t)out.done;
+        term[e] = out.term_reason;
+        memcpy(info + (size_t)e * SM_INFO_STRIDE, out.info, sizeof(out.info));
+    }
+}
+
+void smo_step_batch_tp(const SmScene* sc, int n, double* kin, double* ob, double* tp, int32_t* episode,
+                       double* ep_return, const float* actions, const double* next_ball, const double* next_target,
+                       float* obs, float* reward, uint8_t* done, int32_t* term, float* info) {
+    for (int e = 0; e < n; ++e) {
+        double u[SM_MAX_JOINTS];
+        SmoStepOut out;
+        for (int j = 0; j < sc->n_joints; ++j) u[j] = (double)actions[e * sc->n_joints + j];
+        smo_step_tp(sc, kin + (size_t)e * SM_KIN_STRIDE, ob + (size_t)e * SM_OBST_STRIDE,
+                    tp ? tp + (size_t)e * SM_TP_STRIDE : 0, episode + 4 * e, ep_return + e, u,
+                    next_ball ? next_ball + (size_t)e * 12 : 0, next_target ? next_target + (size_t)e * 3 : 0,
+                    obs ? obs + (size_t)e * sc->obs_size : 0, &out);
         reward[e] = out.reward;
         done[e] = (uint8_t)out.done;
         term[e] = out.term_reason;

@@ -13,6 +13,8 @@ SM_MAX_MOV_ROBOT = 24
 SM_KIN_STRIDE = 32
 SM_OBST_STRIDE = 16
 SM_INFO_STRIDE = 16
+SM_TP_STRIDE = 12
+TP_POS, TP_LAST_DIST, TP_INIT_DIST, TP_ACTIVE, TP_REACHED_N, TP_LINK_POS, TP_DRAWS, TP_REACHED = 0, 3, 4, 5, 6, 7, 10, 11
 
 SM_OBST_NONE, SM_OBST_PLANET, SM_OBST_BALL = 0, 1, 2
 
@@ -27,7 +29,7 @@ TERMINATION_COLLISION_WITH_MOVING_OBSTACLE = 5
 
 INFO_SLOTS = ["d_static", "d_self", "d_moving", "coll_static", "coll_self", "coll_moving", "action_punishment",
               "r_static", "r_self", "r_moving", "episode_length", "episode_return", "range_code", "contact_latch",
-              "max_jerk_rel", "reserved"]
+              "max_jerk_rel", "tp_reward"]
 INFO = {name: i for i, name in enumerate(INFO_SLOTS)}
 
 OB_INDEX, OB_LATCH, OB_BALL_P0, OB_BALL_V0, OB_BALL_EULER0, OB_BALL_OMEGA, OB_BALL_T, OB_BALL_ACTIVE, \
@@ -102,7 +104,11 @@ class SmScene(C.Structure):
         ("plane_z", d),
         ("ball_check_invalid", i32), ("ball_random_initial", i32),
         ("min_start_self", d), ("ball_target_min_static", d), ("ball_target_min_self", d),
-        ("has_table", i32), ("reserved2", i32),
+        ("has_table", i32), ("start_at_rest", i32),
+        ("use_target_points", i32), ("tp_normalize", i32), ("obs_add_tp_pos", i32), ("obs_add_tp_rel", i32),
+        ("tp_radius", d), ("tp_bonus", d), ("tp_reward_factor", d),
+        ("tp_box_min", d * 3), ("tp_box_max", d * 3), ("tp_rel_min", d * 3), ("tp_rel_max", d * 3),
+        ("tp_min_static", d), ("tp_min_self", d),
     ]
 
 
@@ -110,7 +116,7 @@ class SmBuffers(C.Structure):
     _fields_ = [
         ("kin", C.c_void_p), ("obst", C.c_void_p), ("episode", C.c_void_p), ("ep_return", C.c_void_p),
         ("actions", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p),
-        ("term_reason", C.c_void_p), ("info", C.c_void_p), ("stats", C.c_void_p),
+        ("term_reason", C.c_void_p), ("info", C.c_void_p), ("stats", C.c_void_p), ("target", C.c_void_p),
     ]
 
 
@@ -126,5 +132,5 @@ EXPORTED_SYMBOLS = [
     "smenv_destroy", "smenv_pool_sizes", "smenv_fill_pools", "smenv_pool_ptrs", "smenv_copy_pools", "smenv_set_state", "smenv_reset",
     "smenv_step", "smenv_step_random", "smenv_safe_range", "smenv_distances", "smenv_observation",
     "smenv_counters", "smenv_enable_counters", "smenv_launch_count", "smenv_debug_gjk", "smenv_kernel_timing",
-    "smenv_kernel_times", "smenv_mlp_load", "smenv_mlp_forward", "smenv_risk_gate", "smenv_random_actions",
+    "smenv_kernel_times", "smenv_set_targets", "smenv_mlp_load", "smenv_mlp_forward", "smenv_risk_gate", "smenv_random_actions",
 ]

@@ -38,6 +38,7 @@ def load():
     lib.smenv_counters.argtypes = [vp, C.POINTER(abi.SmCounters), i32]
     lib.smenv_enable_counters.argtypes = [vp, i32]
     lib.smenv_launch_count.argtypes = [vp, C.POINTER(C.c_ulonglong)]
+    lib.smenv_set_targets.argtypes = [vp, C.POINTER(abi.SmBuffers), vp, vp, vp]
     lib.smenv_mlp_load.argtypes = [vp, i32, i32, vp, i32, i32, vp]
     lib.smenv_mlp_forward.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, i32, vp]
     lib.smenv_risk_gate.argtypes = [vp, C.POINTER(abi.SmBuffers), C.c_float, vp, vp, vp]

@@ -33,7 +33,6 @@ _DEFAULTS = dict(
     moving_object_speed_meter_per_second=1.0, moving_object_aim_at_current_robot_position=False,
     moving_object_check_invalid_target_link_point_positions=False, moving_object_active_number_single=1,
     moving_object_random_initial_position=False, moving_object_high_launch_angle_probability=1.0,
-    target_point_cartesian_range_scene=0,
     # human
     human_network_checkpoint=None,
     # termination / collision avoidance mode
@@ -54,7 +53,13 @@ _DEFAULTS = dict(
     normalize_reward_to_frequency=False,
     # braking-trajectory method and target points: not part of the hot path this package implements
     check_braking_trajectory_collisions=False, check_braking_trajectory_torque_limits=False,
-    use_target_points=False, risk_config_dir=None, risk_config=None, risk_threshold=None,
+    risk_config_dir=None, risk_config=None, risk_threshold=None,
+    # target points of the reaching task (safe_motions_base.py:131-137, rewards.py:231-266)
+    use_target_points=False, target_point_cartesian_range_scene=0, target_point_relative_pos_scene=0,
+    target_point_radius=0.05, target_point_sequence=0, target_point_reached_reward_bonus=0.0,
+    target_point_use_actual_position=False, target_point_reward_factor=1.0,
+    normalize_reward_to_initial_target_point_distance=False, obs_add_target_point_pos=False,
+    obs_add_target_point_relative_pos=False,
     # misc accepted-and-ignored (rendering, logging, real robot)
     use_gui=False, render_video=False, use_real_robot=False, seed=None, random_agent=False, logging_level="WARNING",
     solver_iterations=None, episodes_per_simulation_reset=None, log_obstacle_data=False,
@@ -86,6 +91,8 @@ class EnvConfig(dict):
                                       "only robot_scene 0 and 9 (robot_scene_base.py:169-183)")
         if self["moving_object_sequence"] != 0 and self["use_moving_objects"]:
             raise NotImplementedError("moving_object_sequence != 0 is not implemented")
+        if self["use_target_points"] and (self["target_point_sequence"] != 0 or self["target_point_use_actual_position"]):
+            raise NotImplementedError("target points: only target_point_sequence=0 on the setpoint pose is implemented")
         if self["trajectory_time_step"] <= 0:
             raise ValueError("trajectory_time_step must be positive")
 
@@ -142,5 +149,25 @@ def ball_backup_config(**overrides):
                moving_object_sphere_angle_min_max=[0, 6.2831], moving_object_speed_meter_per_second=6.0,
                moving_object_check_invalid_target_link_point_positions=True,
                moving_object_random_initial_position=True, use_moving_objects=True)
+    cfg.update(overrides)
+    return EnvConfig(**cfg)
+
+
+def space_task_config(**overrides):
+    """The Space reaching task of README.md:223 (SafeMotionsEnv with target points; the env the risk gate wraps)."""
+    cfg = dict(acc_limit_factor=1.0, action_max_punishment=0.4, action_punishment_min_threshold=0.95,
+               closest_point_safety_distance=0.01, collision_check_time=0.033, jerk_limit_factor=1.0,
+               normalize_reward_to_initial_target_point_distance=True, obs_add_target_point_pos=True,
+               obs_add_target_point_relative_pos=True, obstacle_scene=5, pos_limit_factor=1.0, punish_action=True,
+               robot_scene=0, solver_iterations=50, starting_point_cartesian_range_scene=1,
+               target_point_cartesian_range_scene=0, target_point_radius=0.065, target_point_reached_reward_bonus=5,
+               target_point_relative_pos_scene=0, target_point_sequence=0,
+               terminate_on_collision_with_moving_obstacle=True, terminate_on_collision_with_static_obstacle=True,
+               terminate_on_self_collision=True, trajectory_duration=8.0, trajectory_time_step=0.1,
+               use_controller_target_velocities=True, use_target_points=True, vel_limit_factor=1.0,
+               experiment_name="reaching_task_space", obs_planet_size_per_planet=2, planet_mode=True,
+               planet_one_center=[-0.1, 0.0, 0.8], planet_one_euler_angles=[0.35, 0, 0], planet_one_period=5.0,
+               planet_one_radius_xy=[0.65, 0.8], planet_two_center=[-0.1, 0, 0.8],
+               planet_two_euler_angles=[-0.35, 0, 0], planet_two_radius_xy=[0.75, 0.8], planet_two_time_shift=-2.0)
     cfg.update(overrides)
     return EnvConfig(**cfg)

@@ -145,6 +145,8 @@ struct SmEnv {
     double* d_plocal = nullptr;
     double* d_start_pool = nullptr;
     double* d_ball_pool = nullptr;
+    double* d_target_pool = nullptr;   // [target_pool_n][4] target points of the reaching task
+    int target_pool_n = 0;
     int start_pool_n = 0, ball_pool_n = 0;
     bool pools_filled = false;
     unsigned long long* d_counters = nullptr;
@@ -305,6 +307,29 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
         d.obst_center_norm[o] = sqrtf(d.obst_center[o][0] * d.obst_center[o][0] + d.obst_center[o][1] * d.obst_center[o][1] +
                                       d.obst_center[o][2] * d.obst_center[o][2]) * (1.0f + 1e-6f);
     }
+    d.use_target_points = sc->use_target_points; d.tp_normalize = sc->tp_normalize;
+    d.obs_add_tp_pos = sc->obs_add_tp_pos; d.obs_add_tp_rel = sc->obs_add_tp_rel; d.start_at_rest = sc->start_at_rest;
+    d.tp_radius = sc->tp_radius; d.tp_bonus = sc->tp_bonus; d.tp_reward_factor = sc->tp_reward_factor;
+    d.tp_min_static = sc->tp_min_static; d.tp_min_self = sc->tp_min_self;
+    for (int i = 0; i < 3; ++i) {
+        d.tp_box_min[i] = sc->tp_box_min[i]; d.tp_box_max[i] = sc->tp_box_max[i];
+        d.tp_rel_min[i] = sc->tp_rel_min[i]; d.tp_rel_max[i] = sc->tp_rel_max[i];
+        d.tp_local[i] = (float)(sc->target_t[i] + sc->target_R[3 * i] * sc->target_offset[0] +
+                                sc->target_R[3 * i + 1] * sc->target_offset[1] + sc->target_R[3 * i + 2] * sc->target_offset[2]);
+    }
+    {   // a change of joint j by dq moves the target link point by at most dq * tp_rho[j]
+        const float ln = sqrtf(d.tp_local[0] * d.tp_local[0] + d.tp_local[1] * d.tp_local[1] + d.tp_local[2] * d.tp_local[2]);
+        for (int j = 0; j < SM_MAX_JOINTS; ++j) {
+            float rho = 0.f;
+            if (j < sc->n_joints) {
+                rho = ln;
+                for (int i = j + 1; i < sc->n_joints; ++i)
+                    rho += sqrtf(d.jt[i][0] * d.jt[i][0] + d.jt[i][1] * d.jt[i][1] + d.jt[i][2] * d.jt[i][2]);
+                rho *= 1.0f + 1e-5f;
+            }
+            d.tp_rho[j] = rho;
+        }
+    }
     {   // pair list of the distance planning
         int np = 0;
         auto push = [&](int a, int b, int cls) {
@@ -418,6 +443,11 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     CU(cudaMalloc((void**)&env->d_start_pool, (size_t)env->start_pool_n * SM_POOL_STRIDE * sizeof(double)));
     CU(cudaMemset(env->d_start_pool, 0, (size_t)env->start_pool_n * SM_POOL_STRIDE * sizeof(double)));
     if (env->ball_pool_n) CU(cudaMalloc((void**)&env->d_ball_pool, (size_t)env->ball_pool_n * SM_BALL_STRIDE * sizeof(double)));
+    if (sc->use_target_points) {
+        env->target_pool_n = 4 * env->start_pool_n;
+        CU(cudaMalloc((void**)&env->d_target_pool, (size_t)env->target_pool_n * 4 * sizeof(double)));
+        CU(cudaMemset(env->d_target_pool, 0, (size_t)env->target_pool_n * 4 * sizeof(double)));
+    }
     CU(cudaMalloc((void**)&env->d_scratch, (size_t)num_envs * SM_SCRATCH_FLOATS * sizeof(float)));
     CU(cudaMemset(env->d_scratch, 0, (size_t)num_envs * SM_SCRATCH_FLOATS * sizeof(float)));
     CU(cudaMalloc((void**)&env->d_worklist, 4 * sizeof(int)));
@@ -454,6 +484,7 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     CU(cudaFuncSetAttribute(gjk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_gjk));
     CU(cudaFuncSetAttribute(fill_ball_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
     CU(cudaFuncSetAttribute(fill_start_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
+    CU(cudaFuncSetAttribute(fill_target_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
     CU(cudaFuncSetAttribute(distances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
     // persistent grid: as many CTAs as fit on the device at once (a multiple of the SM count), each looping over envs
     int sms = 0, per_sm = 0;
@@ -476,7 +507,7 @@ extern "C" int smenv_destroy(SmEnv* env) {
     if (!env) return SM_OK;
     cudaSetDevice(env->device);
     if (g_active == env) g_active = nullptr;
-    cudaFree(env->d_verts); cudaFree(env->d_lut); cudaFree(env->d_hwidth); cudaFree(env->d_scene_img); cudaFree(env->d_plocal); cudaFree(env->d_start_pool); cudaFree(env->d_ball_pool);
+    cudaFree(env->d_verts); cudaFree(env->d_lut); cudaFree(env->d_hwidth); cudaFree(env->d_scene_img); cudaFree(env->d_plocal); cudaFree(env->d_start_pool); cudaFree(env->d_ball_pool); cudaFree(env->d_target_pool);
     cudaFree(env->d_counters); cudaFree(env->d_scratch); cudaFree(env->d_worklist); cudaFree(env->d_heavy); cudaFree(env->d_cwork); cudaFree(env->d_tasks); cudaFree(env->d_hpar); cudaFree(env->d_items); cudaFree(env->d_res);
     if (env->h_flag) cudaFreeHost(env->h_flag);
     for (void* q : env->net_allocs) cudaFree(q);
@@ -530,6 +561,11 @@ extern "C" int smenv_fill_pools(SmEnv* env, uint64_t seed, SmStream s) {
     }
     fill_start_pool_kernel<<<grid_for(env, env->start_pool_n), SM_WARPS_PER_BLOCK * 32, env->smem_bytes, stream>>>(A);
     env->launches++;
+    if (env->target_pool_n) {
+        fill_target_pool_kernel<<<grid_for(env, env->target_pool_n), SM_WARPS_PER_BLOCK * 32, env->smem_bytes, stream>>>(
+            env->d_target_pool, env->target_pool_n, (uint32_t)seed, (uint32_t)(seed >> 32));
+        env->launches++;
+    }
     CU(cudaGetLastError());
     env->pools_filled = true;
     return SM_OK;
@@ -594,6 +630,13 @@ extern "C" int smenv_set_state(SmEnv* env, const SmBuffers* buf, const double* q
                                                                (const uint8_t*)dm, tvdt);
     env->launches++;
     CU(cudaGetLastError());
+    if (env->host_scene.use_target_points && buf->target) {  // first target point from the pool (if it is filled)
+        target_init_kernel<<<(n + 255) / 256, 256, 0, stream>>>(*buf, n, nullptr, (const uint8_t*)dm,
+                                                                env->pools_filled ? env->d_target_pool : nullptr,
+                                                                env->pools_filled ? env->target_pool_n : 0,
+                                                                (uint32_t)env->seed, (uint32_t)(env->seed >> 32));
+        env->launches++;
+    }
     if (buf->obs) {
         observation_kernel<<<(n * 32 + 255) / 256, 256, 0, stream>>>(*buf, n);
         env->launches++;
@@ -603,6 +646,34 @@ extern "C" int smenv_set_state(SmEnv* env, const SmBuffers* buf, const double* q
         CU(cudaStreamSynchronize(stream));
         for (void* p : tmp) cudaFree(p);
     }
+    return SM_OK;
+}
+
+extern "C" int smenv_set_targets(SmEnv* env, const SmBuffers* buf, const double* first_target, const uint8_t* mask,
+                                 SmStream s) {
+    if (!env || !buf || !buf->target || !first_target) return fail(SM_ERR_ARG, "smenv_set_targets: null argument");
+    if (!env->host_scene.use_target_points) return fail(SM_ERR_STATE, "smenv_set_targets: the scene has no target points");
+    if (mask && !is_device_ptr(mask)) return fail(SM_ERR_ARG, "smenv_set_targets: mask must be a device pointer");
+    cudaStream_t stream = (cudaStream_t)s;
+    int rc = activate(env, stream);
+    if (rc) return rc;
+    const int n = env->n;
+    double* tmp = nullptr;
+    const double* dft = first_target;
+    if (!is_device_ptr(first_target)) {
+        CU(cudaMalloc((void**)&tmp, (size_t)n * 3 * sizeof(double)));
+        CU(cudaMemcpyAsync(tmp, first_target, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, stream));
+        dft = tmp;
+    }
+    target_init_kernel<<<(n + 255) / 256, 256, 0, stream>>>(*buf, n, dft, mask, nullptr, 0, (uint32_t)env->seed,
+                                                            (uint32_t)(env->seed >> 32));
+    env->launches++;
+    if (buf->obs) {
+        observation_kernel<<<(n * 32 + 255) / 256, 256, 0, stream>>>(*buf, n);
+        env->launches++;
+    }
+    CU(cudaGetLastError());
+    if (tmp) { CU(cudaStreamSynchronize(stream)); cudaFree(tmp); }
     return SM_OK;
 }
 
@@ -624,7 +695,8 @@ extern "C" int smenv_reset(SmEnv* env, const SmBuffers* buf, const uint8_t* mask
     cudaStream_t stream = (cudaStream_t)s;
     int rc = activate(env, stream);
     if (rc) return rc;
-    ResetArgs A{*buf, env->n, mask, env->d_start_pool, env->start_pool_n, (uint32_t)env->seed, (uint32_t)(env->seed >> 32)};
+    ResetArgs A{*buf, env->n, mask, env->d_start_pool, env->start_pool_n, env->d_target_pool, env->target_pool_n,
+                (uint32_t)env->seed, (uint32_t)(env->seed >> 32)};
     reset_kernel<<<(env->n * 32 + 255) / 256, 256, 0, stream>>>(A);
     env->launches++;
     CU(cudaGetLastError());
@@ -654,7 +726,17 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
     JA.hpar = env->d_hpar;
     JA.counters = env->count ? env->d_counters : nullptr;
     const bool tk = env->time_kernels;
-#define SM_MARK(i) do { if (tk) cudaEventRecord(env->ev[i], stream); } while (0)
+    static const bool dbg_sync = getenv("SMENV_DEBUG_SYNC") != nullptr;  // locate a faulting kernel: sync after each
+#define SM_MARK(i)                                                                                           \
+    do {                                                                                                     \
+        if (tk) cudaEventRecord(env->ev[i], stream);                                                         \
+        if (dbg_sync) {                                                                                      \
+            cudaError_t e_ = cudaStreamSynchronize(stream);                                                  \
+            if (e_ != cudaSuccess)                                                                           \
+                return fail(SM_ERR_CUDA, std::string("kernel before mark ") + std::to_string(i) + ": " +     \
+                                             cudaGetErrorString(e_));                                        \
+        }                                                                                                    \
+    } while (0)
     SM_MARK(SM_K_JOINT);
     joint_kernel<<<(env->n * 8 + 255) / 256, 256, 0, stream>>>(JA);
     SM_MARK(SM_K_JOINT_HEAVY);
@@ -672,6 +754,7 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
     P.overflow = env->d_worklist + 1; P.res = env->d_res;
     P.kin = buf->kin; P.obst = buf->obst; P.advance = 1; P.counters = env->d_counters;
     P.cwork = env->d_cwork;
+    P.target = buf->target;
     GjkArgs G;
     G.items = env->d_items; G.n_items = env->d_worklist; G.capacity = env->item_capacity; G.res = env->d_res;
     G.counters = env->d_counters;
@@ -687,6 +770,8 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
     A.start_pool_n = env->pools_filled ? env->start_pool_n : 0;
     A.ball_pool = env->pools_filled ? env->d_ball_pool : nullptr;
     A.ball_pool_n = env->pools_filled ? env->ball_pool_n : 0;
+    A.target_pool = env->pools_filled ? env->d_target_pool : nullptr;
+    A.target_pool_n = env->pools_filled ? env->target_pool_n : 0;
     A.counters = env->d_counters;
     const int T = SM_WARPS_PER_BLOCK * 32;
     const int blocks = (env->n + SM_WARPS_PER_BLOCK - 1) / SM_WARPS_PER_BLOCK;

@@ -107,6 +107,12 @@ struct DevScene {
     // support-width tables: per shape and cube-map cell an upper bound of h(d) = max_v (v - centre) . d over the unit
     // directions d of the cell.  centre distance - h_A(d) - h_B(-d) along the line of centres is a lower bound of the
     // pair distance that is far tighter than bounding spheres for elongated hulls (planning kernels).
+    // target points of the reaching task (include/smenv.h)
+    int use_target_points, tp_normalize, obs_add_tp_pos, obs_add_tp_rel, start_at_rest;
+    double tp_radius, tp_bonus, tp_reward_factor, tp_box_min[3], tp_box_max[3], tp_rel_min[3], tp_rel_max[3];
+    double tp_min_static, tp_min_self;
+    float tp_local[3];               // target link point in the frame of the last joint
+    float tp_rho[SM_MAX_JOINTS];     // bound on |d target link point / d q_j|
     const uint4* scene_img;  // device image of the tables every geometry CTA stages into shared memory (SceneImage)
     const float* hwidth;  // device
     const uint32_t* lut;  // device, n_lut_words (support-direction tables of all shapes that have one)

@@ -10,7 +10,8 @@
 #pragma once
 #include "smenv_kernels.cuh"
 
-#define SM_SCRATCH_FLOATS (SM_MAX_SUB * SM_MAX_JOINTS + 16) /* qsub[32][8] + misc[16] */
+#define SM_SCRATCH_FLOATS (2 * SM_MAX_SUB * SM_MAX_JOINTS + 16) /* qsub[32][8] + misc[16] + qset[32][8] */
+#define SM_QSET_OFF (SM_MAX_SUB * SM_MAX_JOINTS + 16) /* setpoint pose of every sub-step (target points only) */
 #define SM_MISC_OFF (SM_MAX_SUB * SM_MAX_JOINTS)
 #define SM_MISC_RCODE 0     /* joint_kernel: OR of the violation codes */
 #define SM_MISC_JERK 1      /* joint_kernel: max relative jerk */
@@ -61,6 +62,7 @@ __device__ __forceinline__ float joint_advance(double* kin, float* scr, int j, d
         double vs = xadd(xadd(v, xmul(a, tk)), xmul(xmul(hj, tk), tk));
         double qs = xadd(xadd(xadd(q, xmul(v, tk)), xmul(xmul(ha, tk), tk)), xmul(xmul(xmul(sj, tk), tk), tk));
         scr[(k - 1) * SM_MAX_JOINTS + j] = (float)qa;    // pose seen by the collision detection of sub-step k
+        if (c_sc.use_target_points) scr[SM_QSET_OFF + (k - 1) * SM_MAX_JOINTS + j] = (float)qs;  // ctlp.py:2787-2791
         qa = xadd(xadd(qa, xmul(c_sc.track_kp, xsub(qs, qa))), xmul(tvdt, vs));
         q1 = qs; v1 = vs;                                // k == S: the new knot
     }

@@ -188,8 +188,11 @@ __device__ __forceinline__ double normalize_mm(double x, double lo, double hi) {
     return xadd(-1.0, xdiv(xmul(2.0, xsub(x, lo)), xsub(hi, lo)));
 }
 // kin: the env's kinematic record in global memory (q[8] v[8] a[8] ...); ob: obstacle record (16 doubles)
-__device__ __noinline__ void write_observation(float* obs, const double* kin, const double* ob, int lane) {
+// tp: the env's target-point record (NULL unless the scene uses target points)
+__device__ __noinline__ void write_observation(float* obs, const double* kin, const double* ob, const double* tp,
+                                               int lane) {
     const int nj = c_sc.n_joints;
+    const int n_tp = (c_sc.use_target_points && tp) ? 3 * c_sc.obs_add_tp_pos + 3 * c_sc.obs_add_tp_rel : 0;
 #pragma unroll 1
     for (int i = lane; i < c_sc.obs_size; i += 32) {
         double val = 0.0;
@@ -198,8 +201,16 @@ __device__ __noinline__ void write_observation(float* obs, const double* kin, co
             double x = kin[grp * 8 + j];
             val = grp == 0 ? normalize_mm(x, c_sc.pos_lo[j], c_sc.pos_hi[j])
                            : xdiv(x, grp == 1 ? c_sc.vel_max[j] : c_sc.acc_max[j]);
-        } else {
+        } else if (i < 3 * nj + n_tp) {  // observations.py:326-340; ctlp.py:2247-2271
             int r = i - 3 * nj;
+            if (c_sc.obs_add_tp_pos && r < 3) {
+                val = normalize_mm(tp[SM_TP_POS + r], c_sc.tp_box_min[r], c_sc.tp_box_max[r]);
+            } else {
+                if (c_sc.obs_add_tp_pos) r -= 3;
+                val = normalize_mm(xsub(tp[SM_TP_POS + r], tp[SM_TP_LINK_POS + r]), c_sc.tp_rel_min[r], c_sc.tp_rel_max[r]);
+            }
+        } else {
+            int r = i - 3 * nj - n_tp;
             if (c_sc.n_obstacles > 0 && c_sc.obst_kind[0] == SM_OBST_BALL) {
                 double t = ob[SM_OB_BALL_T];
                 if (r < 3) {
@@ -223,6 +234,52 @@ __device__ __noinline__ void write_observation(float* obs, const double* kin, co
         }
         obs[i] = clip1(val);
     }
+}
+
+// target link point of the pose q (float64 joint angles in global memory), computed serially by one thread from the
+// constant-memory chain (LinkPointBase.get_position, ctlp.py:4962-5075); used where an episode starts
+__device__ __noinline__ V3 target_link_point_serial(const double* q) {
+    Xf F;
+    xf_identity(F);
+#pragma unroll 1
+    for (int j = 0; j < c_sc.n_joints; ++j) {
+        float s, c;
+        sincosf((float)q[j], &s, &c);
+        Xf L, C;
+        float Rj[9];
+        axis_angle(c_sc.jaxis[j][0], c_sc.jaxis[j][1], c_sc.jaxis[j][2], c, s, Rj);
+        const float* A = c_sc.jR[j];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                L.r[3 * i + k] = fmaf(A[3 * i], Rj[k], fmaf(A[3 * i + 1], Rj[3 + k], A[3 * i + 2] * Rj[6 + k]));
+        L.t[0] = c_sc.jt[j][0]; L.t[1] = c_sc.jt[j][1]; L.t[2] = c_sc.jt[j][2];
+        xf_compose(F, L, C);
+        F = C;
+    }
+    return xf_apply(F, c_sc.tp_local[0], c_sc.tp_local[1], c_sc.tp_local[2]);
+}
+
+// start of an episode with target points: link point of the start pose, first target point (given, or drawn from the
+// pool with the env's Philox counter), distances (ctlp.py:2216-2245).  One thread.
+__device__ __forceinline__ void target_episode_start(double* tp, const double* kin, const double* first_target,
+                                                     const double* pool, int pool_n, int env, uint32_t k0, uint32_t k1) {
+    const V3 p = target_link_point_serial(kin);
+    double draws = tp[SM_TP_DRAWS];
+    double t[3] = {0.0, 0.0, 0.0};
+    if (first_target) { t[0] = first_target[0]; t[1] = first_target[1]; t[2] = first_target[2]; }
+    else if (pool && pool_n > 0) {
+        uint4 r = philox((uint32_t)env, (uint32_t)draws, 0x7A26u, 2u, k0, k1);
+        const double* e = pool + (size_t)(r.x % (uint32_t)pool_n) * 4;
+        t[0] = e[0]; t[1] = e[1]; t[2] = e[2];
+    }
+    const double dx = t[0] - (double)p.x, dy = t[1] - (double)p.y, dz = t[2] - (double)p.z;
+    const double dist = sqrt(dx * dx + dy * dy + dz * dz);
+    tp[SM_TP_POS] = t[0]; tp[SM_TP_POS + 1] = t[1]; tp[SM_TP_POS + 2] = t[2];
+    tp[SM_TP_LAST_DIST] = dist; tp[SM_TP_INIT_DIST] = dist; tp[SM_TP_ACTIVE] = 1.0; tp[SM_TP_REACHED_N] = 0.0;
+    tp[SM_TP_LINK_POS] = (double)p.x; tp[SM_TP_LINK_POS + 1] = (double)p.y; tp[SM_TP_LINK_POS + 2] = (double)p.z;
+    tp[SM_TP_DRAWS] = draws + 1.0; tp[SM_TP_REACHED] = 0.0;
 }
 
 // lane j holds joint angle q_j in float64 (the state): sin/cos in float64, chain in float32

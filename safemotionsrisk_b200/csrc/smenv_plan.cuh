@@ -26,6 +26,7 @@ struct PlanArgs {
     const double* obst;      // obstacle records
     int advance;             // 1: obstacle poses at the end of the step about to be finished; 0: poses as recorded
     int* cwork;              // [0] = count, [1..] = spans (env * 8 + span) whose contacts need the fine planning
+    double* target;          // [n][SM_TP_STRIDE] target-point records (the step only), or NULL
     unsigned long long* counters;
 };
 
@@ -377,6 +378,46 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) distance_plan_kernel(
             A.res[(size_t)env * SM_RES_STRIDE + lane] = lane == 3 ? SM_RES_NO_CONTACT
                                                                    : fkey(lane == GJK_MOVING ? query + 0.002f : cap);
         __syncwarp();
+        // ---------------- target point of the reaching task: was it reached in one of the S sub-steps?
+        // (ctlp.py:2787-2821; target link point of the sub-step's setpoint pose)
+        if (c_sc.use_target_points && A.target && A.advance) {
+            double* tp = A.target + (size_t)env * SM_TP_STRIDE;
+            const int nj = c_sc.n_joints;
+            const V3 p1 = xf_apply(W.fr[nj], c_sc.tp_local[0], c_sc.tp_local[1], c_sc.tp_local[2]);
+            bool reached = false;
+            if (tp[SM_TP_ACTIVE] != 0.0) {
+                const V3 T = mk((float)tp[SM_TP_POS], (float)tp[SM_TP_POS + 1], (float)tp[SM_TP_POS + 2]);
+                const float* qs = A.scratch + (size_t)env * SM_SCRATCH_FLOATS + SM_QSET_OFF;
+                // every sub-step's link point lies within infl of the new knot's: sum_j max_k |q_j(k) - q_j(S)| rho_j
+                float infl = 1e-5f;
+                const float q1f = (float)q1;
+#pragma unroll 1
+                for (int j = 0; j < nj; ++j) {
+                    const float q1j = __shfl_sync(FULL, q1f, j);   // lane j holds joint j of the new knot
+                    const float dq = lane < S ? fabsf(qs[lane * SM_MAX_JOINTS + j] - q1j) : 0.0f;
+                    infl = fmaf(__uint_as_float(__reduce_max_sync(FULL, __float_as_uint(dq))), c_sc.tp_rho[j], infl);
+                }
+                const V3 e1 = p1 - T;
+                if (sqrtf(dot(e1, e1)) - infl < (float)c_sc.tp_radius) {   // exact: lane k = sub-step k + 1
+                    bool hit = false;
+                    if (lane < S) {
+                        Xf F;
+                        xf_identity(F);
+#pragma unroll 1
+                        for (int j = 0; j < nj; ++j) fk_chain_step(sm, F, j, qs[lane * SM_MAX_JOINTS + j]);
+                        const V3 e = xf_apply(F, c_sc.tp_local[0], c_sc.tp_local[1], c_sc.tp_local[2]) - T;
+                        hit = sqrtf(dot(e, e)) < (float)c_sc.tp_radius;
+                    }
+                    reached = __any_sync(FULL, hit);
+                }
+            }
+            if (lane == 0) {
+                tp[SM_TP_LINK_POS] = (double)p1.x; tp[SM_TP_LINK_POS + 1] = (double)p1.y; tp[SM_TP_LINK_POS + 2] = (double)p1.z;
+                tp[SM_TP_REACHED] = reached ? 1.0 : 0.0;
+                if (reached) { tp[SM_TP_ACTIVE] = 0.0; tp[SM_TP_REACHED_N] += 1.0; }
+            }
+            __syncwarp();
+        }
         // ---------------- world positions of every shape's sphere centre and centroid, once per env
 #pragma unroll 1
         for (int sI = lane; sI < c_sc.n_shapes; sI += 32) {

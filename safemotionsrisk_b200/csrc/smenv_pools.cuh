@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) fill_start_pool_kerne
             V3 tgt;
             q = sample_free_pose(rng, verts, sm, W, c_sc.start_box_min, c_sc.start_box_max, thr_s, thr_self, tgt, lane);
             v = 0.0; a = 0.0;
+            if (c_sc.start_at_rest) break;   // not collision_avoidance_mode: the pose at rest (ctlp.py:1461-1500)
             if (rng.uniform() < c_sc.kinematic_sampling_probability) {
                 // per joint: up to 5 velocities x 10 accelerations with violation code 0 (ctlp.py:1503-1525)
                 bool found = false;
@@ -325,8 +326,43 @@ struct ResetArgs {
     const uint8_t* mask;
     const double* start_pool;
     int start_pool_n;
+    const double* target_pool;
+    int target_pool_n;
     uint32_t k0, k1;
 };
+
+// injected first target points (parity protocol) or, with first_target == NULL, draws from the pool
+__global__ void target_init_kernel(SmBuffers buf, int n, const double* first_target, const uint8_t* mask,
+                                   const double* pool, int pool_n, uint32_t k0, uint32_t k1) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= n || !buf.target || (mask && !mask[env])) return;
+    double* tp = buf.target + (size_t)env * SM_TP_STRIDE;
+    target_episode_start(tp, buf.kin + (size_t)env * SM_KIN_STRIDE, first_target ? first_target + 3 * (size_t)env : nullptr,
+                         pool, pool_n, env, k0, k1);
+}
+
+// target points of the reaching task: the target link point of a random collision-free pose inside the target box
+// (_add_target_point, ctlp.py:1658-1676 -> _get_collision_free_robot_position); the torque check of the sampler is
+// not reproduced
+__global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) fill_target_pool_kernel(double* pool, int pool_n, uint32_t k0,
+                                                                                    uint32_t k1) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemLayout L = block_prologue(smem_raw, true);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    WarpScratch& W = L.scratch[warp];
+#pragma unroll 1
+    for (int e = blockIdx.x * SM_WARPS_PER_BLOCK + warp; e < pool_n; e += gridDim.x * SM_WARPS_PER_BLOCK) {
+        Rng rng(key64(k0, k1), (uint32_t)e, 0x7A27u);
+        V3 tgt;
+        sample_free_pose(rng, L.verts, L.bs->scene, W, c_sc.tp_box_min, c_sc.tp_box_max, (float)c_sc.tp_min_static,
+                         (float)c_sc.tp_min_self, tgt, lane);
+        if (lane == 0) {
+            double* o = pool + (size_t)e * 4;
+            o[0] = (double)tgt.x; o[1] = (double)tgt.y; o[2] = (double)tgt.z; o[3] = 0.0;
+        }
+        __syncwarp();
+    }
+}
 __global__ void __launch_bounds__(256) reset_kernel(ResetArgs A) {
     const int lane = threadIdx.x & 31;
     const int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -342,7 +378,12 @@ __global__ void __launch_bounds__(256) reset_kernel(ResetArgs A) {
         A.buf.ep_return[env] = 0.0;
         if (A.buf.done) A.buf.done[env] = 0;
     }
-    write_observation(A.buf.obs + (size_t)env * c_sc.obs_size, e, e + SM_KIN_STRIDE, lane);
+    double* tp = (c_sc.use_target_points && A.buf.target) ? A.buf.target + (size_t)env * SM_TP_STRIDE : nullptr;
+    if (tp) {
+        if (lane == 0) target_episode_start(tp, e, nullptr, A.target_pool, A.target_pool_n, env, A.k0, A.k1);
+        __syncwarp();
+    }
+    write_observation(A.buf.obs + (size_t)env * c_sc.obs_size, e, e + SM_KIN_STRIDE, tp, lane);
 }
 
 // observation only (after smenv_set_state)
@@ -351,7 +392,8 @@ __global__ void __launch_bounds__(256) observation_kernel(SmBuffers buf, int n) 
     const int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (env >= n) return;
     write_observation(buf.obs + (size_t)env * c_sc.obs_size, buf.kin + (size_t)env * SM_KIN_STRIDE,
-                      buf.obst + (size_t)env * SM_OBST_STRIDE, lane);
+                      buf.obst + (size_t)env * SM_OBST_STRIDE,
+                      (c_sc.use_target_points && buf.target) ? buf.target + (size_t)env * SM_TP_STRIDE : nullptr, lane);
 }
 
 // ---------------- parity hooks: pieces of the step on caller-supplied states

@@ -28,6 +28,8 @@ struct StepArgs {
     int start_pool_n;
     const double* ball_pool;
     int ball_pool_n;
+    const double* target_pool;     // [target_pool_n][4] target points sampled on the device (reaching task)
+    int target_pool_n;
     unsigned long long* counters;  // device SmCounters, or NULL
 };
 
@@ -121,9 +123,32 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
         const bool finished = ep_len >= c_sc.episode_steps;  // trajectory_manager.py:187-192
         const double bonus = (finished && !term_coll) ? c_sc.termination_bonus : 0.0;
         const double punish = term_coll ? c_sc.early_termination_punishment : 0.0;
-        const double reward = (1.0 - action_punishment) * c_sc.action_max_punishment + r_self * c_sc.w_self +
-                              r_static * c_sc.w_static + r_moving * c_sc.w_moving + low_acc * c_sc.w_low_acc +
-                              low_vel * c_sc.w_low_vel + bonus + punish;
+        double reward = (1.0 - action_punishment) * c_sc.action_max_punishment + r_self * c_sc.w_self +
+                        r_static * c_sc.w_static + r_moving * c_sc.w_moving + low_acc * c_sc.w_low_acc +
+                        low_vel * c_sc.w_low_vel + bonus + punish;
+        // ---------------- reaching task: TargetPointReachingReward (rewards.py:303-396; ctlp.py:2309-2350)
+        double* tp = (c_sc.use_target_points && A.buf.target) ? A.buf.target + (size_t)env * SM_TP_STRIDE : nullptr;
+        double tp_reward = 0.0;
+        bool tp_reached = false;
+        if (tp) {
+            const bool active = tp[SM_TP_ACTIVE] != 0.0;
+            tp_reached = tp[SM_TP_REACHED] != 0.0;
+            double norm = 1.0;
+            if ((active || tp_reached) && c_sc.tp_normalize) {
+                norm = tp[SM_TP_INIT_DIST];
+                if (norm == 0.0) norm += 0.0000001;
+            }
+            if (active) {
+                const double dx = tp[SM_TP_POS] - tp[SM_TP_LINK_POS], dy = tp[SM_TP_POS + 1] - tp[SM_TP_LINK_POS + 1],
+                             dz = tp[SM_TP_POS + 2] - tp[SM_TP_LINK_POS + 2];
+                tp_reward = (tp[SM_TP_LAST_DIST] - sqrt(dx * dx + dy * dy + dz * dz)) / (c_sc.ts * norm);
+            } else if (tp_reached) {
+                tp_reward = tp[SM_TP_LAST_DIST] / (c_sc.ts * norm) + c_sc.tp_bonus;
+            }
+            const double pun = c_sc.punish_action ? action_punishment : 0.0;
+            reward = tp_reward * c_sc.tp_reward_factor - pun * c_sc.action_max_punishment + r_self * c_sc.w_self +
+                     r_static * c_sc.w_static + r_moving * c_sc.w_moving;
+        }
         int done = 0, reason = SM_TERM_UNSET;
         if (c_sc.terminate_self && c_self) { done = 1; reason = SM_TERM_SELF_COLLISION; }
         else if (c_sc.terminate_static && c_static) { done = 1; reason = SM_TERM_STATIC_COLLISION; }
@@ -155,6 +180,7 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
                 case SM_INFO_RANGE_CODE: val = rcode; break;
                 case SM_INFO_CONTACT_LATCH: val = latch != 0.0 ? 1.0f : 0.0f; break;
                 case SM_INFO_MAX_JERK_REL: val = jerk_rel; break;
+                case SM_INFO_TP_REWARD: val = (float)tp_reward; break;
                 default: break;
             }
             A.buf.info[(size_t)env * SM_INFO_STRIDE + lane] = val;
@@ -198,6 +224,32 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
             ret_new = 0.0;
         }
         __syncwarp();
+        const bool was_reset = kin_obs != kin;
+        if (tp) {  // get_target_point_observation (ctlp.py:2210-2271): replace a reached point, record the distances
+            __syncwarp();
+            if (lane == 0) {
+                if (was_reset) {
+                    target_episode_start(tp, kin_obs, nullptr, A.target_pool, A.target_pool_n, env, A.k0, A.k1);
+                } else {
+                    if (tp_reached && A.target_pool_n > 0) {
+                        uint4 r = philox((uint32_t)env, (uint32_t)tp[SM_TP_DRAWS], 0x7A26u, 2u, A.k0, A.k1);
+                        const double* e = A.target_pool + (size_t)(r.x % (uint32_t)A.target_pool_n) * 4;
+                        tp[SM_TP_POS] = e[0]; tp[SM_TP_POS + 1] = e[1]; tp[SM_TP_POS + 2] = e[2];
+                        tp[SM_TP_ACTIVE] = 1.0;
+                        tp[SM_TP_INIT_DIST] = nan("");
+                        tp[SM_TP_DRAWS] += 1.0;
+                    }
+                    tp[SM_TP_REACHED] = 0.0;
+                    if (tp[SM_TP_ACTIVE] != 0.0) {
+                        const double dx = tp[SM_TP_POS] - tp[SM_TP_LINK_POS], dy = tp[SM_TP_POS + 1] - tp[SM_TP_LINK_POS + 1],
+                                     dz = tp[SM_TP_POS + 2] - tp[SM_TP_LINK_POS + 2];
+                        tp[SM_TP_LAST_DIST] = sqrt(dx * dx + dy * dy + dz * dz);
+                        if (isnan(tp[SM_TP_INIT_DIST])) tp[SM_TP_INIT_DIST] = tp[SM_TP_LAST_DIST];
+                    }
+                }
+            }
+            __syncwarp();
+        }
         if (ob_changed && lane < SM_OBST_STRIDE) {
             A.buf.obst[(size_t)env * SM_OBST_STRIDE + lane] = ob_new;
             ob[lane] = ob_new;
@@ -208,7 +260,7 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
         }
         __syncwarp();
         // ---------------- observation of the state the next action acts on (observations.py:313-351)
-        write_observation(A.buf.obs + (size_t)env * c_sc.obs_size, kin_obs, ob, lane);
+        write_observation(A.buf.obs + (size_t)env * c_sc.obs_size, kin_obs, ob, tp, lane);
     }
     __syncthreads();
     if (A.buf.stats && tid < 16 && s_stats[tid] != 0.0) atomicAdd(&A.buf.stats[tid], s_stats[tid]);

@@ -393,6 +393,29 @@ class Scene:
             obs_size += 6
         if cfg.planet_mode:
             obs_size += sc.obs_planet_size  # planet two is phase-coupled (observations.py:94-98)
+        # ---------------- target points of the reaching task (observations.py:56-77; ctlp.py:184-235)
+        sc.use_target_points = int(bool(cfg.use_target_points))
+        self.obs_target_size = 0
+        if cfg.use_target_points:
+            sc.obs_add_tp_pos = int(bool(cfg.obs_add_target_point_pos))
+            sc.obs_add_tp_rel = int(bool(cfg.obs_add_target_point_relative_pos))
+            self.obs_target_size = 3 * sc.obs_add_tp_pos + 3 * sc.obs_add_tp_rel
+            obs_size += self.obs_target_size
+            sc.tp_normalize = int(bool(cfg.normalize_reward_to_initial_target_point_distance))
+            sc.tp_radius = float(cfg.target_point_radius)
+            sc.tp_bonus = float(cfg.target_point_reached_reward_bonus)
+            sc.tp_reward_factor = float(cfg.target_point_reward_factor)
+            tbox = {0: [[-0.6, 0.6], [-0.8, 0.8], [0.1, 1]], 1: [[-0.6, 0.6], [-0.3, 0.3], [0.1, 1]],
+                    2: [[-0.4, 0.4], [-0.4, 0.4], [0.1, 1]]}.get(cfg.target_point_cartesian_range_scene)
+            if tbox is None or cfg.target_point_relative_pos_scene != 0:
+                raise NotImplementedError("target_point_cartesian_range_scene / target_point_relative_pos_scene")
+            rel = [[-1.6, -2, -1.5], [1.6, 2, 1.5]]                         # ctlp.py:184
+            for i in range(3):
+                sc.tp_box_min[i], sc.tp_box_max[i] = tbox[i][0], tbox[i][1]
+                sc.tp_rel_min[i], sc.tp_rel_max[i] = rel[0][i], rel[1][i]
+            sc.tp_min_static = cfg.closest_point_safety_distance + 0.09     # ctlp.py:1661-1662
+            sc.tp_min_self = cfg.closest_point_safety_distance              # ctlp.py:2220
+        sc.start_at_rest = int(not cfg.collision_avoidance_mode)            # ctlp.py:1461-1500
         sc.obs_size = obs_size
         self.obs_size = obs_size
 

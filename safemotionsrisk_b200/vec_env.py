@@ -89,11 +89,15 @@ class SafeMotionsVecEnv:
         self.term_reason = torch.full((n,), -1, dtype=torch.int32, device=dev)
         self.info = torch.zeros((n, abi.SM_INFO_STRIDE), dtype=torch.float32, device=dev)
         self.stats = torch.zeros(32, dtype=torch.float64, device=dev)
+        # target-point records of the reaching task (use_target_points), else absent
+        self.target = torch.zeros((n, abi.SM_TP_STRIDE), dtype=torch.float64, device=dev) \
+            if self.scene.struct.use_target_points else None
         self._buf = abi.SmBuffers(
             kin=self.kin.data_ptr(), obst=self.obst.data_ptr(), episode=self.episode.data_ptr(),
             ep_return=self.ep_return.data_ptr(), actions=self.actions.data_ptr(), obs=self.obs.data_ptr(),
             reward=self.reward.data_ptr(), done=self.done.data_ptr(), term_reason=self.term_reason.data_ptr(),
-            info=self.info.data_ptr(), stats=self.stats.data_ptr())
+            info=self.info.data_ptr(), stats=self.stats.data_ptr(),
+            target=self.target.data_ptr() if self.target is not None else None)
         # pinned host staging for the host-buffer API (step_host)
         self._h_actions = torch.zeros((n, nj), dtype=torch.float32).pin_memory()
         self._h_obs = torch.zeros((n, d), dtype=torch.float32).pin_memory()
@@ -178,8 +182,9 @@ class SafeMotionsVecEnv:
             return self.obs[0].cpu().numpy()
         return self.obs
 
-    def set_state(self, q, v, a, obst=None, mask=None):
-        """Injects start states (parity protocol): q, v, a [N, n_joints] float64, obst [N, 16] or None."""
+    def set_state(self, q, v, a, obst=None, mask=None, first_target=None):
+        """Injects start states (parity protocol, SURVEY 8c): q, v, a [N, n_joints] float64, obst [N, 16] or None;
+        first_target [N, 3]: the first target point of every env (reaching task), else drawn from the pool."""
         def prep(x, cols):
             if x is None:
                 return None
@@ -191,6 +196,10 @@ class SafeMotionsVecEnv:
         ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
         cabi.check(self._lib.smenv_set_state(self._handle, C.byref(self._buf), ptr(tq), ptr(tv), ptr(ta), ptr(tob),
                                              ptr(tm), self._stream()), "smenv_set_state")
+        if first_target is not None:
+            ft = prep(first_target, 3)
+            cabi.check(self._lib.smenv_set_targets(self._handle, C.byref(self._buf), ptr(ft), ptr(tm), self._stream()),
+                       "smenv_set_targets")
         self.done.zero_()
         return self.obs
 

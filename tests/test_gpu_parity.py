@@ -13,10 +13,11 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 from oracle import oracle  # noqa: E402
-from safemotionsrisk_b200 import abi, ball_backup_config, cabi, space_backup_config  # noqa: E402
+from safemotionsrisk_b200 import abi, ball_backup_config, cabi, space_backup_config, space_task_config  # noqa: E402
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CONFIGS = {"space": lambda **k: space_backup_config(**k), "ball": lambda **k: ball_backup_config(**k),
+CONFIGS = {"space_task": lambda **k: space_task_config(**k),
+           "space": lambda **k: space_backup_config(**k), "ball": lambda **k: ball_backup_config(**k),
            "space_bm": lambda **k: space_backup_config(ball_machine_mode=True, **k),
            "ball_bm": lambda **k: ball_backup_config(ball_machine_mode=True, **k)}
 I = abi.INFO
@@ -439,4 +440,77 @@ def test_risk_gate_replaces_exactly_the_risky_actions():
     # and the gated step runs end to end
     env.step_gated(threshold=thr)
     torch.cuda.synchronize()
+    env.close()
+
+
+# ---------------------------------------------------------------------------------------------- reaching task
+def test_reaching_task_rollout_matches_oracle():
+    """Space reaching task (README.md:223): target-point observation (29 entries), TargetPointReachingReward,
+    reached points replaced from the device pool.  Start poses come from the device pool; the first target of some envs
+    is placed 2-8 cm from the target link point so that points are reached (radius 6.5 cm) within the rollout."""
+    n, steps = 256, 12
+    env = make_env("space_task", n, auto_reset=False)
+    assert env.scene.obs_size == 29
+    start, _ = env.pools()
+    q, v, a, ob = start[:n, 0:7], start[:n, 8:15], start[:n, 16:23], start[:n, 32:48]
+    assert np.all(v == 0) and np.all(a == 0)          # not collision_avoidance_mode: start at rest
+    rng = np.random.default_rng(11)
+    link = np.array([oracle.target_link_point(env.scene, q[e]) for e in range(n)])
+    ft = link + rng.uniform(-0.3, 0.3, (n, 3))
+    near = rng.random(n) < 0.4
+    direction = rng.normal(size=(n, 3))
+    direction /= np.linalg.norm(direction, axis=1, keepdims=True)
+    ft[near] = link[near] + direction[near] * rng.uniform(0.02, 0.08, (near.sum(), 1))
+    env.set_state(q, v, a, ob, first_target=ft)
+    orc = oracle.OracleEnvs(env.scene, n)
+    orc.set_state(q, v, a, ob, first_target=ft)
+    tp = env.target.cpu().numpy()
+    assert np.abs(tp[:, abi.TP_LINK_POS:abi.TP_LINK_POS + 3] - orc.tp[:, abi.TP_LINK_POS:abi.TP_LINK_POS + 3]).max() < 1e-5
+    assert np.abs(env.obs.cpu().numpy() - orc.obs).max() < 1e-5
+    alive = np.ones(n, dtype=bool)
+    reached_total = 0
+    for s in range(steps):
+        act = rng.uniform(-1, 1, (n, 7)).astype(np.float32)
+        obs, rew, done, info = env.step(act)
+        torch.cuda.synchronize()
+        tp = env.target.cpu().numpy()
+        o_obs, o_rew, o_done, _, o_info = orc.step(act, None, tp[:, 0:3])   # the targets the device drew
+        edge = np.abs(np.linalg.norm(orc.tp[:, 7:10] - orc.tp[:, 0:3], axis=1) - env.scene.struct.tp_radius) < 1e-4
+        ok = alive & ~edge
+        assert np.array_equal(env.kin.cpu().numpy()[ok], orc.kin[ok])                       # joint state bit-exact
+        assert np.array_equal(tp[ok, abi.TP_REACHED_N], orc.tp[ok, abi.TP_REACHED_N])       # same points reached
+        assert np.array_equal(tp[ok, abi.TP_ACTIVE], orc.tp[ok, abi.TP_ACTIVE])
+        assert np.abs(tp[ok, 7:10] - orc.tp[ok, 7:10]).max() < 1e-5                         # target link point
+        assert np.abs(tp[ok, 3:5] - orc.tp[ok, 3:5]).max() < 1e-5                           # distances
+        i_gpu = info.cpu().numpy()
+        knife = knife_edge(np.stack([o_info[:, 0], o_info[:, 1], o_info[:, 2]], 1),
+                           (env.scene.struct.static_cap, env.scene.struct.static_cap, env.scene.struct.moving_query))
+        ok2 = ok & ~knife
+        assert np.array_equal(done.cpu().numpy()[ok2], o_done[ok2])
+        # reward: (last - current) / (ts * initial distance); float32 link point -> 1e-3 absolute at distances of cm
+        assert np.allclose(rew.cpu().numpy()[ok2], o_rew[ok2], rtol=1e-3, atol=2e-3)
+        d_obs = np.abs(obs.cpu().numpy() - o_obs)
+        d_obs[~ok2] = 0
+        assert d_obs.max() < 1e-5, (s, np.unravel_index(d_obs.argmax(), d_obs.shape), d_obs.max(),
+                                    obs.cpu().numpy()[d_obs.max(1).argmax()], o_obs[d_obs.max(1).argmax()],
+                                    tp[d_obs.max(1).argmax()], orc.tp[d_obs.max(1).argmax()])
+        reached_total = int(orc.tp[:, abi.TP_REACHED_N].sum())
+        alive &= (o_done == 0) & (done.cpu().numpy() == 0)
+    assert reached_total > 10          # the rollout exercised the reached / replace path
+    env.close()
+
+
+def test_reaching_task_full_size_invariants():
+    env = make_env("space_task", 65536, auto_reset=True)
+    env.reset()
+    for _ in range(30):
+        obs, rew, done, info = env.step_random()
+    torch.cuda.synchronize()
+    tp = env.target.cpu().numpy()
+    assert bool((obs.abs() <= 1).all()) and bool(torch.isfinite(rew).all())
+    assert np.all(tp[:, abi.TP_ACTIVE] == 1.0)                       # a reached point is replaced at once
+    lo, hi = np.array(env.scene.struct.tp_box_min), np.array(env.scene.struct.tp_box_max)
+    assert np.all(tp[:, 0:3] >= lo - 1e-6) and np.all(tp[:, 0:3] <= hi + 1e-6)   # sampled inside the target box
+    assert np.allclose(tp[:, abi.TP_LAST_DIST], np.linalg.norm(tp[:, 0:3] - tp[:, 7:10], axis=1), atol=1e-9)
+    assert tp[:, abi.TP_REACHED_N].sum() > 0
     env.close()

@@ -133,3 +133,33 @@ def test_philox_known_answer():
     assert oracle.philox(0, 0, 0, 0, 0, 0) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
     assert oracle.philox(0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff) == \
         [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+
+
+def test_target_point_reward_and_replacement():
+    """TargetPointReachingReward on the oracle (rewards.py:303-396; ctlp.py:2309-2350): progress reward
+    (last - current) / (ts * initial), reached reward last / (ts * initial) + bonus, replacement by the next target."""
+    from safemotionsrisk_b200.config import space_task_config
+    sc = Scene(space_task_config(punish_action=False))
+    env = oracle.OracleEnvs(sc, 2)
+    q = np.tile(np.array([0.3, 0.5, -0.2, -1.0, 0.1, 0.8, 0.0]), (2, 1))
+    z = np.zeros_like(q)
+    ob = np.zeros((2, 16))
+    ob[:, 0] = 300           # planets far from this pose
+    link = oracle.target_link_point(sc, q[0])
+    ft = np.stack([link + [0.2, 0.0, 0.0], link + [0.03, 0.0, 0.0]])   # env 1 starts inside the radius (6.5 cm)
+    env.set_state(q, z, z, ob, ft)
+    assert env.obs.shape[1] == 29
+    assert np.allclose(env.tp[:, 3], [0.2, 0.03]) and np.allclose(env.tp[:, 4], [0.2, 0.03])
+    nxt = np.tile([0.3, 0.3, 0.5], (2, 1))
+    obs, rew, done, term, info = env.step(np.zeros((2, 7), dtype=np.float32), None, nxt)
+    # env 1: reached in the first sub-step -> 0.03 / (0.1 * 0.03) + 5
+    assert abs(rew[1] - 15.0) < 1e-4 and env.tp[1, 6] == 1 and np.allclose(env.tp[1, 0:3], nxt[1])
+    # env 0: progress reward from the distances before / after the step
+    d_after = np.linalg.norm(ft[0] - env.tp[0, 7:10])
+    assert abs(rew[0] - (0.2 - d_after) / (0.1 * 0.2)) < 1e-4
+    assert abs(env.tp[0, 3] - d_after) < 1e-12 and abs(env.tp[0, 4] - 0.2) < 1e-12   # last updated, initial kept
+    # observation: target position and relative position, normalised (observations.py:326-340)
+    lo, hi = np.array(sc.struct.tp_box_min), np.array(sc.struct.tp_box_max)
+    assert np.allclose(obs[0, 21:24], np.clip(-1 + 2 * (ft[0] - lo) / (hi - lo), -1, 1), atol=1e-6)
+    rlo, rhi = np.array(sc.struct.tp_rel_min), np.array(sc.struct.tp_rel_max)
+    assert np.allclose(obs[0, 24:27], -1 + 2 * ((ft[0] - env.tp[0, 7:10]) - rlo) / (rhi - rlo), atol=1e-6)
