@@ -37,6 +37,12 @@ def scene_config(name):
         return ball_backup_config()
     if name == "space":
         return space_backup_config()
+    if name == "space_task":
+        from safemotionsrisk_b200 import space_task_config
+        return space_task_config()
+    if name == "space_task_bm":
+        from safemotionsrisk_b200 import space_task_config
+        return space_task_config(ball_machine_mode=True)
     if name == "space_bm":
         return space_backup_config(ball_machine_mode=True)
     if name == "ball_bm":
@@ -48,7 +54,9 @@ WORKLOAD = {"ball": "Ball env (moving ball obstacles) batched random-action roll
                     "(BASELINE.json configs[1])",
             "space": "Space env (planet_mode, obstacle_scene=5) batched random-action rollout",
             "space_bm": "Space env, ball_machine_mode (shipped checkpoints' robot)",
-            "ball_bm": "Ball env, ball_machine_mode (shipped checkpoints' robot)"}
+            "ball_bm": "Ball env, ball_machine_mode (shipped checkpoints' robot)",
+            "space_task": "Space reaching task (SafeMotionsEnv with target points, README.md:223)",
+            "space_task_bm": "Space reaching task, ball_machine_mode (BASELINE.json configs[3] env)"}
 
 
 class ClockSampler:
@@ -116,16 +124,17 @@ def cpu_reference_run(scene_name, envs_per_thread, steps, warmup, threads, targe
         elif scene.struct.n_obstacles:
             ob[:, 2:5], ob[:, 5:8] = [2.4, 0.3, 1.0], [-5.5, -0.6, 1.5]
             ob[:, 13], ob[:, 14], ob[:, 15] = 1, 200, 150
-        env.set_state(q, np.zeros_like(q), np.zeros_like(q), ob)
-        env._q0, env._ob0 = q, ob
+        tgt = np.tile([0.3, 0.3, 0.5], (envs_per_thread, 1)) if scene.struct.use_target_points else None
+        env.set_state(q, np.zeros_like(q), np.zeros_like(q), ob, tgt)
+        env._q0, env._ob0, env._tgt = q, ob, tgt
         shards.append(env)
     acts = rng.uniform(-1, 1, (envs_per_thread, scene.n_joints)).astype(np.float32)
     nb = np.tile(np.array([2.4, 0.3, 1.0, -5.5, -0.6, 1.5, 0.3, 0.1, 0.0, 1.0, 200, 150.0]), (envs_per_thread, 1))
 
     def one_step(env):
-        _, _, done, _, _ = env.step(acts, nb)
+        _, _, done, _, _ = env.step(acts, nb, env._tgt)
         if done.any():  # episodes restart from the same pool of start states
-            env.set_state(env._q0, np.zeros_like(env._q0), np.zeros_like(env._q0), env._ob0)
+            env.set_state(env._q0, np.zeros_like(env._q0), np.zeros_like(env._q0), env._ob0, env._tgt)
     with ThreadPoolExecutor(threads) as pool:
         tw = time.perf_counter()
         for _ in range(max(1, warmup)):
@@ -168,6 +177,7 @@ def main():
             return 0
         # bounded sample: small shards so that `steps` finish within minutes on the host cores
         per_thread = 1024 if args.scene.startswith("ball") else 64
+
         # each of the K "steps" the driver asks for is one oracle step of the bounded sample; K is capped so that the
         # run ends within minutes
         steps = max(1, min(args.steps, 40))
@@ -292,7 +302,8 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    uncull = {"space": 1.51e6, "space_bm": 1.71e6, "ball": 0.15e6, "ball_bm": 0.35e6}[args.scene]
+    uncull = {"space": 1.51e6, "space_bm": 1.71e6, "ball": 0.15e6, "ball_bm": 0.35e6, "space_task": 1.51e6,
+              "space_task_bm": 1.71e6}[args.scene]
     traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
     try:
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
@@ -361,6 +372,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         per_thread = 1024 if args.scene.startswith("ball") else 64
+
         val, dt, total, csteps = cpu_reference_run(args.scene, per_thread, 20, 1, threads, target_seconds=15.0)
         cpu = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "{} host threads x {} envs x {} steps of the same scene ({} env-steps in {:.1f} s)".format(

@@ -950,13 +950,16 @@ extern "C" int smenv_mlp_load(SmEnv* env, int which, int n_tc, const int32_t* di
     return SM_OK;
 }
 
-static int mlp_launch(SmEnv* env, int which, const float* in0, int in0_w, const float* in1, int in1_w, float* out,
-                      int out_stride, int n, cudaStream_t stream) {
+struct MlpSeg { const float* p; int stride, w; };
+static int mlp_launch(SmEnv* env, int which, MlpSeg s0, MlpSeg s1, MlpSeg s2, float* out, int out_stride, int n,
+                      cudaStream_t stream) {
     if (!env->net_loaded[which]) return fail(SM_ERR_STATE, "network not loaded (smenv_mlp_load)");
     const MlpNet& net = env->nets[which];
-    if (in0_w + in1_w != net.n_in) return fail(SM_ERR_ARG, "network input width does not match the loaded weights");
+    if (s0.w + s1.w + s2.w != net.n_in) return fail(SM_ERR_ARG, "network input width does not match the loaded weights");
     MlpArgs M;
-    M.net = net; M.n = n; M.in0 = in0; M.in0_w = in0_w; M.in1 = in1; M.in1_w = in1_w; M.out = out; M.out_stride = out_stride;
+    M.net = net; M.n = n; M.out = out; M.out_stride = out_stride;
+    const MlpSeg segs[3] = {s0, s1, s2};
+    for (int i = 0; i < 3; ++i) { M.in[i] = segs[i].p; M.in_stride[i] = segs[i].stride; M.in_w[i] = segs[i].w; }
     const int tiles = (n + MLP_TILE_M - 1) / MLP_TILE_M;
     const int grid = tiles < env->sms ? tiles : env->sms;   // one CTA per SM (202 KB of shared memory, all of TMEM)
     mlp_kernel<<<grid, MLP_THREADS, MLP_SM_BYTES, stream>>>(M);
@@ -971,7 +974,8 @@ extern "C" int smenv_mlp_forward(SmEnv* env, int which, const float* in0, int in
     cudaStream_t stream = (cudaStream_t)s;
     int rc = activate(env, stream);
     if (rc) return rc;
-    return mlp_launch(env, which, in0, in0_w, in1, in1 ? in1_w : 0, out, out_stride, n, stream);
+    return mlp_launch(env, which, MlpSeg{in0, in0_w, in0_w}, MlpSeg{in1, in1 ? in1_w : 0, in1 ? in1_w : 0},
+                      MlpSeg{nullptr, 0, 0}, out, out_stride, n, stream);
 }
 
 extern "C" int smenv_risk_gate(SmEnv* env, const SmBuffers* buf, float threshold, float* risk_out, uint8_t* risky_out,
@@ -981,9 +985,15 @@ extern "C" int smenv_risk_gate(SmEnv* env, const SmBuffers* buf, float threshold
     int rc = activate(env, stream);
     if (rc) return rc;
     const int nj = env->host_scene.n_joints, ow = env->host_scene.obs_size;
+    // the risk observation is the observation without the target-point entries (observations.py:419-431): joint
+    // position / velocity / acceleration, then the obstacle entries
+    const DevScene& hs = env->host_scene;
+    const int n_tp = hs.use_target_points ? 3 * hs.obs_add_tp_pos + 3 * hs.obs_add_tp_rel : 0;
+    const MlpSeg kinem{buf->obs, ow, 3 * nj}, rest{buf->obs + 3 * nj + n_tp, ow, ow - 3 * nj - n_tp};
     float* risk = risk_out ? risk_out : env->d_risk;
-    if ((rc = mlp_launch(env, SM_NET_RISK, buf->obs, ow, buf->actions, nj, risk, 1, env->n, stream))) return rc;
-    if ((rc = mlp_launch(env, SM_NET_BACKUP, buf->obs, ow, nullptr, 0, env->d_backup, MLP_MAX_OUT, env->n, stream))) return rc;
+    if ((rc = mlp_launch(env, SM_NET_RISK, kinem, rest, MlpSeg{buf->actions, nj, nj}, risk, 1, env->n, stream))) return rc;
+    if ((rc = mlp_launch(env, SM_NET_BACKUP, kinem, rest, MlpSeg{nullptr, 0, 0}, env->d_backup, MLP_MAX_OUT, env->n, stream)))
+        return rc;
     risk_gate_kernel<<<(env->n + 255) / 256, 256, 0, stream>>>(const_cast<float*>(buf->actions), risk, env->d_backup,
                                                                MLP_MAX_OUT, nj, env->n, threshold, risky_out);
     env->launches++;

@@ -57,8 +57,8 @@ struct MlpNet {
 struct MlpArgs {
     MlpNet net;
     int n;                    // rows (envs)
-    const float* in0; int in0_w;   // input = [in0 row, in1 row, zero padding]
-    const float* in1; int in1_w;
+    const float* in[3];            // input row = [segment 0, segment 1, segment 2, zero padding]
+    int in_stride[3], in_w[3];     // row stride (floats) and width of every segment (pointers are pre-offset)
     float* out; int out_stride;
 };
 
@@ -206,8 +206,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(MlpArgs A) {
                 const int k = kc * 8 + i;
                 float x = 0.0f;
                 if (valid) {
-                    if (k < A.in0_w) x = A.in0[(size_t)row * A.in0_w + k];
-                    else if (k < A.in0_w + A.in1_w) x = A.in1[(size_t)row * A.in1_w + (k - A.in0_w)];
+                    if (k < A.in_w[0]) x = A.in[0][(size_t)row * A.in_stride[0] + k];
+                    else if (k < A.in_w[0] + A.in_w[1]) x = A.in[1][(size_t)row * A.in_stride[1] + (k - A.in_w[0])];
+                    else if (k < A.in_w[0] + A.in_w[1] + A.in_w[2])
+                        x = A.in[2][(size_t)row * A.in_stride[2] + (k - A.in_w[0] - A.in_w[1])];
                 }
                 h[i] = __float2half_rn(x);
             }

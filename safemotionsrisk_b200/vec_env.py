@@ -344,9 +344,10 @@ class SafeMotionsVecEnv:
         risk = [(w["risk/dense_{}/kernel".format(i)], w["risk/dense_{}/bias".format(i)]) for i in range(4)]
         pol = [(w["backup/{}/kernel".format(n)], w["backup/{}/bias".format(n)]) for n in ("fc_1", "fc_2", "fc_out")]
         pol[-1] = (pol[-1][0][:, :nj], pol[-1][1][:nj])  # deterministic action = the mean head
-        if risk[0][0].shape[0] != self.scene.obs_size + nj or pol[0][0].shape[0] != self.scene.obs_size:
-            raise ValueError("networks expect observation size {}, the env produces {}".format(
-                pol[0][0].shape[0], self.scene.obs_size))
+        risk_obs = self.scene.obs_size - self.scene.obs_target_size   # without the target-point entries
+        if risk[0][0].shape[0] != risk_obs + nj or pol[0][0].shape[0] != risk_obs:
+            raise ValueError("networks expect a risk observation of size {}, the env produces {}".format(
+                pol[0][0].shape[0], risk_obs))
         for which, layers, hidden, out_act in ((0, risk, 0, 0), (1, pol, 1, 1)):
             dims = np.array([layers[0][0].shape[0]] + [k.shape[1] for k, _ in layers], dtype=np.int32)
             flat = np.concatenate([np.concatenate([k.astype(np.float32).ravel(), b.astype(np.float32).ravel()])

@@ -514,3 +514,26 @@ def test_reaching_task_full_size_invariants():
     assert np.allclose(tp[:, abi.TP_LAST_DIST], np.linalg.norm(tp[:, 0:3] - tp[:, 7:10], axis=1), atol=1e-9)
     assert tp[:, abi.TP_REACHED_N].sum() > 0
     env.close()
+
+
+def test_risk_gate_on_the_reaching_task_uses_the_risk_observation():
+    """In the task env the networks see the observation WITHOUT the target-point entries (observations.py:419-431)."""
+    from oracle import mlp
+    n, thr = 2048, 0.065
+    env = make_env("space_task", n, auto_reset=True, cfg=dict(ball_machine_mode=True))
+    env.load_networks()
+    env.reset()
+    for _ in range(3):
+        env.step_random()
+    w = np.load(os.path.join(os.path.dirname(GOLDEN), "..", "safemotionsrisk_b200", "assets", "networks_space.npz"))
+    obs = env.obs.cpu().numpy().copy()
+    risk_obs = np.concatenate([obs[:, :21], obs[:, 27:]], axis=1)
+    assert risk_obs.shape[1] == 23
+    act = np.random.default_rng(2).uniform(-1, 1, (n, 7)).astype(np.float32)
+    env.actions.copy_(torch.from_numpy(act))
+    risk, risky = env.risk_gate(thr)
+    torch.cuda.synchronize()
+    assert np.abs(risk.cpu().numpy() - mlp.risk_forward(w, risk_obs, act)).max() < 3e-2
+    env.step_gated(threshold=thr)
+    torch.cuda.synchronize()
+    env.close()
