@@ -394,6 +394,57 @@ class SafeMotionsVecEnv:
                    "smenv_step")
         return self._outputs()
 
+    # ------------------------------------------------------------------ backup-client look-ahead (risk ground truth)
+    _STATE = ("kin", "obst", "episode", "ep_return", "target", "stats", "obs", "reward", "done", "term_reason", "info")
+
+    def snapshot(self):
+        """Copy of the whole env state (the reference clones its Bullet state into a "backup client" with
+        saveBullet / restoreState plus attribute copies, safe_motions_base.py:1801-1891; here it is a tensor copy)."""
+        return {k: getattr(self, k).clone() for k in self._STATE if getattr(self, k) is not None}
+
+    def restore(self, snap):
+        for k, v in snap.items():
+            getattr(self, k).copy_(v)
+
+    def risk_observation(self):
+        """The observation without the target-point entries (observations.py:419-431): what the networks see."""
+        nt = self.scene.obs_target_size
+        if nt == 0:
+            return self.obs
+        k = 3 * self.scene.n_joints
+        return torch.cat([self.obs[:, :k], self.obs[:, k + nt:]], dim=1).contiguous()
+
+    def backup_policy_actions(self):
+        """Deterministic actions of the backup policy for the current observations (explore=False)."""
+        return self.mlp_forward(1, self.risk_observation(), None, n_out=self.scene.n_joints)
+
+    def risk_ground_truth(self, actions, backup_steps=20):
+        """Ground truth of the state-action risk (RISK_CHECK_NEXT_STATE_SIMULATE_NEXT_STEP_AND_BACKUP_TRAJECTORY,
+        safe_motions_base.py:1520-1592): from a copy of the current state, apply `actions`, then let the backup policy
+        act for `backup_steps` steps; an env is risky (1.0) if its episode ends in that window for any reason other
+        than the trajectory length.  The env state is restored afterwards.  Returns (risk_observation, actions, risk)
+        as device tensors -- one row of the reference's risk data set per env (safe_motions_base.py:1413-1461)."""
+        state = self.risk_observation().clone()
+        act = torch.as_tensor(actions, dtype=torch.float32, device=self.device).reshape(self.num_envs, -1).clone()
+        snap = self.snapshot()
+        auto = self.auto_reset
+        self.auto_reset = False
+        try:
+            risky = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
+            alive = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
+            a = act
+            for i in range(1 + int(backup_steps)):
+                self.step(a)
+                done = self.done.bool()
+                risky |= alive & done & (self.term_reason != self.TERMINATION_TRAJECTORY_LENGTH)
+                alive &= ~done
+                if i < backup_steps:
+                    a = self.backup_policy_actions()
+        finally:
+            self.restore(snap)
+            self.auto_reset = auto
+        return state, act, risky.float()
+
     KERNELS = ("joint_kernel", "joint_heavy_kernel", "contact_plan_kernel", "distance_plan_kernel", "gjk_kernel",
                "finish_kernel")
 

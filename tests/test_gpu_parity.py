@@ -537,3 +537,39 @@ def test_risk_gate_on_the_reaching_task_uses_the_risk_observation():
     env.step_gated(threshold=thr)
     torch.cuda.synchronize()
     env.close()
+
+
+def test_backup_look_ahead_labels_and_restores_the_state():
+    """Risk ground truth by rolling the backup policy in a copy of the state (safe_motions_base.py:1520-1592): the
+    state is restored bit for bit, the labels are deterministic, and they agree with the same look-ahead done by the
+    CPU oracle with the NumPy policy (the two policies differ by fp16 rounding, so a few borderline envs may flip)."""
+    from oracle import mlp
+    n, steps = 512, 20
+    env = make_env("space_bm", n, auto_reset=True)
+    env.load_networks()
+    env.reset()
+    for _ in range(4):
+        env.step_random()
+    before = {k: v.clone() for k, v in env.snapshot().items()}
+    act = np.random.default_rng(4).uniform(-1, 1, (n, 7)).astype(np.float32)
+    state, a, risk = env.risk_ground_truth(act, steps)
+    after = env.snapshot()
+    for k in before:
+        assert torch.equal(before[k], after[k]), k
+    state2, a2, risk2 = env.risk_ground_truth(act, steps)
+    assert torch.equal(risk, risk2) and torch.equal(state, state2)
+    risk = risk.cpu().numpy()
+    assert 0.02 < risk.mean() < 0.98
+    # the same look-ahead on the oracle
+    w = np.load(os.path.join(os.path.dirname(GOLDEN), "..", "safemotionsrisk_b200", "assets", "networks_space.npz"))
+    orc = oracle.OracleEnvs(env.scene, n)
+    orc.kin[:], orc.obst[:] = env.kin.cpu().numpy(), env.obst.cpu().numpy()
+    orc.episode[:], orc.ep_return[:] = env.episode.cpu().numpy(), env.ep_return.cpu().numpy()
+    o_risky, alive, a_o = np.zeros(n, bool), np.ones(n, bool), act
+    for i in range(1 + steps):
+        o_obs, _, o_done, o_term, _ = orc.step(a_o)
+        o_risky |= alive & (o_done != 0) & (o_term != abi.TERMINATION_TRAJECTORY_LENGTH)
+        alive &= o_done == 0
+        a_o = mlp.backup_forward(w, o_obs).astype(np.float32)
+    assert (o_risky != (risk > 0.5)).mean() < 0.05
+    env.close()
