@@ -160,6 +160,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--host-chunks", type=int, default=4,
+                    help="env ranges of the host-buffer step whose copies and kernels overlap (smenv_step_host)")
     ap.add_argument("--risk-gate", action="store_true",
                     help="risk network + backup policy (tensor cores) in front of every step (BASELINE.json configs[3])")
     ap.add_argument("--risk-threshold", type=float, default=None)
@@ -352,21 +354,23 @@ def main():
         rng = np.random.default_rng(rank)
         acts = rng.uniform(-1, 1, (args.envs, sc.n_joints)).astype(np.float32)
         for _ in range(3):
-            env.step_host(acts, gate_thr)
+            env.step_host(acts, gate_thr, chunks=args.host_chunks)
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
         k_e2e = min(args.steps, 100)
         t0 = time.perf_counter()
         for _ in range(k_e2e):
-            env.step_host(acts, gate_thr)
+            env.step_host(acts, gate_thr, chunks=args.host_chunks)
         torch.cuda.synchronize(dev)
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": world * args.envs * k_e2e / float(te.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(acts.nbytes), "d2h_bytes_per_step": int(args.envs * (4 * sc.obs_size + 4 + 1)),
-               "steps": k_e2e, "api": "SafeMotionsVecEnv.step_host (pinned host buffers)"}
+               "steps": k_e2e, "host_chunks": args.host_chunks if gate_thr is None else 1,
+               "api": "SafeMotionsVecEnv.step_host -> smenv_step_host (pageable NumPy actions copied to the pinned "
+                      "buffer, H2D, step, D2H of obs / reward / done, all inside the timed region)"}
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only, bounded sample)
     cpu = None

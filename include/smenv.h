@@ -279,6 +279,14 @@ int smenv_reset(SmEnv* env, const SmBuffers* buf, const uint8_t* mask, SmStream 
 int smenv_step(SmEnv* env, const SmBuffers* buf, int auto_reset, SmStream stream);
 /* Same launch with device-generated U(-1,1) actions (get_random_action, safe_motions_base.py:1327-1328). */
 int smenv_step_random(SmEnv* env, const SmBuffers* buf, int auto_reset, SmStream stream);
+/* The step as an RL sampler calls it, with HOST buffers (pinned for full speed): actions [N][n_joints] in, observation
+ * [N][obs_size], reward [N] and done [N] out; the state stays on the device in `buf` (buf->actions / obs / reward / done
+ * are the device staging buffers).  The envs are cut into `chunks` (1..8) ranges that run on internal streams, so the
+ * host<->device copies of one range overlap the kernels of the others; results do not depend on `chunks`.  Ordered
+ * after the work already queued on `stream`; returns when the host buffers are complete.
+ * Replaces the per-env `env.step(action)` loop of the RLlib sampler / evaluate.py:198-303 over num_envs envs. */
+int smenv_step_host(SmEnv* env, const SmBuffers* buf, const float* h_actions, float* h_obs, float* h_reward,
+                    uint8_t* h_done, int auto_reset, int chunks, SmStream stream);
 
 /* Pieces of the step exposed for parity tests. */
 int smenv_safe_range(SmEnv* env, const double* kin, double* range_lo, double* range_hi, int32_t* code, int n,

@@ -168,6 +168,17 @@ struct SmEnv {
     cudaEvent_t ev[SM_K_COUNT + 1] = {};
     double kernel_ms[SM_K_COUNT] = {};
     int timed_steps = 0;
+    cudaStream_t chunk_streams[8] = {};  // smenv_step_host: one stream per env range in flight
+    cudaEvent_t chunk_done[8] = {};
+    cudaEvent_t chunk_fork = nullptr;
+    cudaStream_t side_streams[8] = {};   // contact planning next to the distance planning, per env range
+    cudaEvent_t side_fork[8] = {}, side_join[8] = {};
+    cudaStream_t host_stream = nullptr;  // origin stream of the host-step graph
+    cudaEvent_t host_order = nullptr;
+    cudaGraphExec_t host_graph = nullptr;
+    unsigned char host_graph_key[sizeof(SmBuffers) + 4 * sizeof(void*) + 4 * sizeof(int) + 16] = {};
+    int host_graph_kernels = 0;
+    int list_layout = 1;         // number of env ranges of the last step (where the counts of the work lists sit)
     int* d_heavy = nullptr;      // [0] = count, [1..8n] = (env, joint) instances deferred to joint_heavy_kernel
     int* d_cwork = nullptr;      // [0] = count, [1..8n] = spans (env * 8 + span) the coarse contact phase could not clear
     int* d_tasks = nullptr;      // [0] = count, [1..16n] = position bounds to solve (joint_solve_kernel)
@@ -304,6 +315,12 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
         float mx = 0.f;
         for (int i = 0; i < SM_MAX_MOV_ROBOT; ++i) { d.contact_thresh[o][i] = (float)sc->contact_thresh[o][i]; mx = fmaxf(mx, d.contact_thresh[o][i]); }
         d.contact_thresh_max[o] = mx;
+        for (int k = 0; k < 3; ++k) { d.obst_bmin[o][k] = FLT_MAX; d.obst_bmax[o][k] = -FLT_MAX; }
+        for (int sI = d.obst_shape_off[o]; sI < d.obst_shape_off[o] + d.obst_shape_cnt[o] && o < sc->n_obstacles; ++sI)
+            for (int k = 0; k < 3; ++k) {
+                d.obst_bmin[o][k] = fminf(d.obst_bmin[o][k], d.shapes[sI].bmin[k] - d.shapes[sI].margin - 1e-6f);
+                d.obst_bmax[o][k] = fmaxf(d.obst_bmax[o][k], d.shapes[sI].bmax[k] + d.shapes[sI].margin + 1e-6f);
+            }
         d.obst_center_norm[o] = sqrtf(d.obst_center[o][0] * d.obst_center[o][0] + d.obst_center[o][1] * d.obst_center[o][1] +
                                       d.obst_center[o][2] * d.obst_center[o][2]) * (1.0f + 1e-6f);
     }
@@ -450,8 +467,8 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     }
     CU(cudaMalloc((void**)&env->d_scratch, (size_t)num_envs * SM_SCRATCH_FLOATS * sizeof(float)));
     CU(cudaMemset(env->d_scratch, 0, (size_t)num_envs * SM_SCRATCH_FLOATS * sizeof(float)));
-    CU(cudaMalloc((void**)&env->d_worklist, 4 * sizeof(int)));
-    CU(cudaMemset(env->d_worklist, 0, 4 * sizeof(int)));
+    CU(cudaMalloc((void**)&env->d_worklist, 2 * 8 * sizeof(int)));  // per env range: item counter, overflow count
+    CU(cudaMemset(env->d_worklist, 0, 2 * 8 * sizeof(int)));
     {   // item buffer: the mean is a few dozen items per env-step; sized generously, overflow is reported loudly
         long long cap = (long long)num_envs * 192;
         if (cap < 65536) cap = 65536;
@@ -467,13 +484,18 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
         *env->h_flag = 0;
         CU(cudaHostGetDevicePointer((void**)&env->d_flag, env->h_flag, 0));
     }
-    CU(cudaMalloc((void**)&env->d_tasks, ((size_t)num_envs * 16 + 1) * sizeof(int)));
-    CU(cudaMemset(env->d_tasks, 0, ((size_t)num_envs * 16 + 1) * sizeof(int)));
+    CU(cudaMalloc((void**)&env->d_tasks, ((size_t)num_envs * 16 + 8) * sizeof(int)));
+    CU(cudaMemset(env->d_tasks, 0, ((size_t)num_envs * 16 + 8) * sizeof(int)));
     CU(cudaMalloc((void**)&env->d_hpar, (size_t)num_envs * 8 * SM_HPAR * sizeof(double)));
-    CU(cudaMalloc((void**)&env->d_cwork, ((size_t)num_envs * SM_COARSE_LANES + 1) * sizeof(int)));
-    CU(cudaMemset(env->d_cwork, 0, ((size_t)num_envs * SM_COARSE_LANES + 1) * sizeof(int)));
-    CU(cudaMalloc((void**)&env->d_heavy, ((size_t)num_envs * 8 + 1) * sizeof(int)));
-    CU(cudaMemset(env->d_heavy, 0, ((size_t)num_envs * 8 + 1) * sizeof(int)));
+    CU(cudaMalloc((void**)&env->d_cwork, ((size_t)num_envs * SM_COARSE_LANES + 8) * sizeof(int)));
+    CU(cudaMemset(env->d_cwork, 0, ((size_t)num_envs * SM_COARSE_LANES + 8) * sizeof(int)));
+    for (int c = 0; c < 8; ++c) {
+        CU(cudaStreamCreateWithFlags(&env->side_streams[c], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&env->side_fork[c], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&env->side_join[c], cudaEventDisableTiming));
+    }
+    CU(cudaMalloc((void**)&env->d_heavy, ((size_t)num_envs * 8 + 8) * sizeof(int)));
+    CU(cudaMemset(env->d_heavy, 0, ((size_t)num_envs * 8 + 8) * sizeof(int)));
     CU(cudaMalloc((void**)&env->d_counters, 16 * sizeof(unsigned long long)));
     CU(cudaMemset(env->d_counters, 0, 16 * sizeof(unsigned long long)));
 
@@ -513,6 +535,19 @@ extern "C" int smenv_destroy(SmEnv* env) {
     for (void* q : env->net_allocs) cudaFree(q);
     cudaFree(env->d_risk); cudaFree(env->d_backup);
     for (int i = 0; i <= SM_K_COUNT; ++i) if (env->ev[i]) cudaEventDestroy(env->ev[i]);
+    for (int c = 0; c < 8; ++c) {
+        if (env->chunk_streams[c]) cudaStreamDestroy(env->chunk_streams[c]);
+        if (env->chunk_done[c]) cudaEventDestroy(env->chunk_done[c]);
+    }
+    if (env->chunk_fork) cudaEventDestroy(env->chunk_fork);
+    for (int c = 0; c < 8; ++c) {
+        if (env->side_streams[c]) cudaStreamDestroy(env->side_streams[c]);
+        if (env->side_fork[c]) cudaEventDestroy(env->side_fork[c]);
+        if (env->side_join[c]) cudaEventDestroy(env->side_join[c]);
+    }
+    if (env->host_graph) cudaGraphExecDestroy(env->host_graph);
+    if (env->host_order) cudaEventDestroy(env->host_order);
+    if (env->host_stream) cudaStreamDestroy(env->host_stream);
     for (int o = 0; o < SM_MAX_OBSTACLES; ++o) { cudaFree(env->d_ppos[o]); cudaFree(env->d_pquat[o]); }
     delete env;
     return SM_OK;
@@ -703,29 +738,53 @@ extern "C" int smenv_reset(SmEnv* env, const SmBuffers* buf, const uint8_t* mask
     return SM_OK;
 }
 
-static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int random_actions, SmStream s) {
-    if (!env || !buf) return fail(SM_ERR_ARG, "smenv_step: null argument");
-    if (!random_actions && !buf->actions) return fail(SM_ERR_ARG, "smenv_step: actions missing");
-    if (auto_reset && !env->pools_filled) return fail(SM_ERR_STATE, "smenv_step: auto_reset needs smenv_fill_pools");
-    if (env->h_flag && *(volatile int*)env->h_flag != 0)
-        return fail(SM_ERR_STATE, "smenv_step: the GJK item buffer of an earlier step overflowed by " +
-                                      std::to_string(*(volatile int*)env->h_flag) + " items (capacity " +
-                                      std::to_string(env->item_capacity) + "); results since then are invalid");
-    cudaStream_t stream = (cudaStream_t)s;
-    int rc = activate(env, stream);
-    if (rc) return rc;
+#define SM_MAX_CHUNKS 8 /* env ranges that can be in flight at once (smenv_step_host) */
+
+// SmBuffers as seen by a launch over the envs [e0, e0 + m)
+static SmBuffers buffers_at(const SmBuffers& b, int e0, int nj, int obs_size) {
+    SmBuffers o = b;
+    o.kin = b.kin + (size_t)e0 * SM_KIN_STRIDE;
+    o.obst = b.obst + (size_t)e0 * SM_OBST_STRIDE;
+    o.episode = b.episode + (size_t)e0 * 4;
+    o.ep_return = b.ep_return + e0;
+    if (b.actions) o.actions = b.actions + (size_t)e0 * nj;
+    if (b.obs) o.obs = b.obs + (size_t)e0 * obs_size;
+    if (b.reward) o.reward = b.reward + e0;
+    if (b.done) o.done = b.done + e0;
+    if (b.term_reason) o.term_reason = b.term_reason + e0;
+    if (b.info) o.info = b.info + (size_t)e0 * SM_INFO_STRIDE;
+    if (b.target) o.target = b.target + (size_t)e0 * SM_TP_STRIDE;
+    return o;
+}
+
+// The kernels of one env step over the envs [e0, e0 + m) on `stream`, with the work lists of slot `chunk`: every list
+// of the whole env ([0] = count, [1..k n] = entries) holds the sub-lists of the ranges back to back, the range's
+// sub-list starting at entry k * e0 + chunk (its own count first).  Ranges in flight at once need distinct slots.
+static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chunk, int auto_reset, int random_actions,
+                      uint32_t step_counter, bool tk, cudaStream_t stream) {
+    const SmBuffers buf_v = buffers_at(*full, e0, env->host_scene.n_joints, env->host_scene.obs_size);
+    const SmBuffers* buf = &buf_v;
+    const int per_env_items = env->item_capacity / env->n;
+    int* worklist = env->d_worklist + 2 * chunk;
+    float* scratch = env->d_scratch + (size_t)e0 * SM_SCRATCH_FLOATS;
+    unsigned* res = env->d_res + (size_t)e0 * SM_RES_STRIDE;
+    GjkItem* items = env->d_items + (size_t)e0 * per_env_items;
+    const int capacity = e0 == 0 && m == env->n ? env->item_capacity : m * per_env_items;
+    int* heavy = env->d_heavy + (size_t)e0 * 8 + chunk;
+    int* cwork = env->d_cwork + (size_t)e0 * SM_COARSE_LANES + chunk;
+    int* tasks = env->d_tasks + (size_t)e0 * 16 + chunk;
     JointArgs JA;
-    JA.buf = *buf; JA.n = env->n; JA.random_actions = random_actions;
+    JA.buf = *buf; JA.n = m; JA.random_actions = random_actions;
     JA.k0 = (uint32_t)env->seed; JA.k1 = (uint32_t)(env->seed >> 32);
-    JA.step_counter = env->step_counter++;
-    JA.scratch = env->d_scratch;
-    JA.worklist = env->d_worklist;  // clears the item counter and the overflow count
-    JA.heavy = env->d_heavy;
-    JA.cwork = env->d_cwork;
-    JA.tasks = env->d_tasks;
-    JA.hpar = env->d_hpar;
+    JA.step_counter = step_counter;
+    JA.env_base = e0;
+    JA.scratch = scratch;
+    JA.worklist = worklist;  // clears the item counter and the overflow count
+    JA.heavy = heavy;
+    JA.cwork = cwork;
+    JA.tasks = tasks;
+    JA.hpar = env->d_hpar + (size_t)e0 * 8 * SM_HPAR;
     JA.counters = env->count ? env->d_counters : nullptr;
-    const bool tk = env->time_kernels;
     static const bool dbg_sync = getenv("SMENV_DEBUG_SYNC") != nullptr;  // locate a faulting kernel: sync after each
 #define SM_MARK(i)                                                                                           \
     do {                                                                                                     \
@@ -738,10 +797,10 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
         }                                                                                                    \
     } while (0)
     SM_MARK(SM_K_JOINT);
-    joint_kernel<<<(env->n * 8 + 255) / 256, 256, 0, stream>>>(JA);
+    joint_kernel<<<(m * 8 + 255) / 256, 256, 0, stream>>>(JA);
     SM_MARK(SM_K_JOINT_HEAVY);
-    {   // the lists are at most 8 n / 16 n long; blocks beyond their length exit at once
-        int hb = (env->n * 8 + SM_HEAVY_THREADS - 1) / SM_HEAVY_THREADS;
+    {   // the lists are at most 8 m / 16 m long; blocks beyond their length exit at once
+        int hb = (m * 8 + SM_HEAVY_THREADS - 1) / SM_HEAVY_THREADS;
         if (hb > 8 * env->sms) hb = 8 * env->sms;
         joint_first_kernel<<<hb, SM_HEAVY_THREADS, 0, stream>>>(JA);
         joint_solve_kernel<<<16 * env->sms, SM_HEAVY_THREADS, 0, stream>>>(JA);  // warps take chunks of the task list
@@ -749,22 +808,23 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
     }
     env->launches += 4;
     PlanArgs P;
-    P.buf = *buf; P.n = env->n; P.scratch = env->d_scratch;
-    P.items = env->d_items; P.item_count = env->d_worklist; P.capacity = env->item_capacity;
-    P.overflow = env->d_worklist + 1; P.res = env->d_res;
+    P.buf = *buf; P.n = m; P.scratch = scratch;
+    P.items = items; P.item_count = worklist; P.capacity = capacity;
+    P.overflow = worklist + 1; P.res = res;
     P.kin = buf->kin; P.obst = buf->obst; P.advance = 1; P.counters = env->d_counters;
-    P.cwork = env->d_cwork;
+    P.cwork = cwork;
     P.target = buf->target;
     GjkArgs G;
-    G.items = env->d_items; G.n_items = env->d_worklist; G.capacity = env->item_capacity; G.res = env->d_res;
+    G.items = items; G.n_items = worklist; G.capacity = capacity; G.res = res;
     G.counters = env->d_counters;
     StepArgs A;
-    A.buf = *buf; A.n = env->n; A.auto_reset = auto_reset;
+    A.buf = *buf; A.n = m; A.auto_reset = auto_reset;
     A.k0 = (uint32_t)env->seed; A.k1 = (uint32_t)(env->seed >> 32);
-    A.scratch = env->d_scratch;
-    A.res = env->d_res;
-    A.heavy = env->d_heavy;
-    A.overflow = env->d_worklist + 1;
+    A.env_base = e0;
+    A.scratch = scratch;
+    A.res = res;
+    A.heavy = heavy;
+    A.overflow = worklist + 1;
     A.host_flag = env->d_flag;
     A.start_pool = env->pools_filled ? env->d_start_pool : nullptr;
     A.start_pool_n = env->pools_filled ? env->start_pool_n : 0;
@@ -774,24 +834,38 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
     A.target_pool_n = env->pools_filled ? env->target_pool_n : 0;
     A.counters = env->d_counters;
     const int T = SM_WARPS_PER_BLOCK * 32;
-    const int blocks = (env->n + SM_WARPS_PER_BLOCK - 1) / SM_WARPS_PER_BLOCK;
+    const int blocks = (m + SM_WARPS_PER_BLOCK - 1) / SM_WARPS_PER_BLOCK;
     const int grid_p = blocks < env->grid_broad ? blocks : env->grid_broad;
-    const int grid_f = (env->n + 7) / 8;
+    const int grid_f = (m + 7) / 8;
     const bool contacts = env->host_scene.contact_stride > 0 && env->host_scene.n_obstacles > 0;
     SM_MARK(SM_K_CONTACT_PLAN);
+    // The contact planning and the distance planning are independent (both only append to the item list): outside the
+    // measurement modes they run side by side, the contact kernels on the slot's side stream.
+    static const bool no_fork = getenv("SMENV_NO_FORK") != nullptr;
+    const bool fork = contacts && !tk && !dbg_sync && !no_fork;
+    cudaStream_t cstream = stream;
+    if (fork) {
+        cstream = env->side_streams[chunk];
+        CU(cudaEventRecord(env->side_fork[chunk], stream));
+        CU(cudaStreamWaitEvent(cstream, env->side_fork[chunk], 0));
+    }
     if (contacts) {
-        const int grid_c = (env->n * SM_COARSE_LANES + 255) / 256;
+        const int grid_c = (m * SM_COARSE_LANES + 255) / 256;
         if (env->count) {
-            contact_coarse_kernel<true><<<grid_c, 256, env->smem_bytes_broad, stream>>>(P);
-            contact_plan_kernel<true><<<grid_p, T, env->smem_bytes_broad, stream>>>(P);
+            contact_coarse_kernel<true><<<grid_c, 256, env->smem_bytes_broad, cstream>>>(P);
+            contact_plan_kernel<true><<<grid_p, T, env->smem_bytes_broad, cstream>>>(P);
         } else {
-            contact_coarse_kernel<false><<<grid_c, 256, env->smem_bytes_broad, stream>>>(P);
-            contact_plan_kernel<false><<<grid_p, T, env->smem_bytes_broad, stream>>>(P);
+            contact_coarse_kernel<false><<<grid_c, 256, env->smem_bytes_broad, cstream>>>(P);
+            contact_plan_kernel<false><<<grid_p, T, env->smem_bytes_broad, cstream>>>(P);
         }
     }
     SM_MARK(SM_K_DISTANCE_PLAN);
     if (env->count) distance_plan_kernel<true><<<grid_p, T, env->smem_bytes_broad, stream>>>(P);
     else distance_plan_kernel<false><<<grid_p, T, env->smem_bytes_broad, stream>>>(P);
+    if (fork) {
+        CU(cudaEventRecord(env->side_join[chunk], cstream));
+        CU(cudaStreamWaitEvent(stream, env->side_join[chunk], 0));
+    }
     SM_MARK(SM_K_GJK);
     if (env->count) gjk_kernel<true><<<env->grid_gjk, 256, env->smem_bytes_gjk, stream>>>(G);
     else gjk_kernel<false><<<env->grid_gjk, 256, env->smem_bytes_gjk, stream>>>(G);
@@ -800,6 +874,44 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
     else finish_kernel<false><<<grid_f, 256, 0, stream>>>(A);
     SM_MARK(SM_K_COUNT);
 #undef SM_MARK
+    env->launches += contacts ? 5 : 3;
+    CU(cudaGetLastError());
+    return SM_OK;
+}
+
+// The count of the deferred-joint list is cleared by the finish kernel of the previous step; when the number of ranges
+// changes, the new count slots lie inside the old lists and have to be cleared once.
+static int set_list_layout(SmEnv* env, int chunks, cudaStream_t stream) {
+    if (env->list_layout == chunks) return SM_OK;
+    const int per = (env->n + chunks - 1) / chunks;
+    for (int c = 0; c < chunks && c * per < env->n; ++c)
+        CU(cudaMemsetAsync(env->d_heavy + (size_t)c * per * 8 + c, 0, sizeof(int), stream));
+    env->list_layout = chunks;
+    return SM_OK;
+}
+
+static int step_check(SmEnv* env, const SmBuffers* buf, int auto_reset, bool need_actions) {
+    if (!env || !buf) return fail(SM_ERR_ARG, "smenv_step: null argument");
+    if (need_actions && !buf->actions) return fail(SM_ERR_ARG, "smenv_step: actions missing");
+    if (auto_reset && !env->pools_filled) return fail(SM_ERR_STATE, "smenv_step: auto_reset needs smenv_fill_pools");
+    if (env->h_flag && *(volatile int*)env->h_flag != 0)
+        return fail(SM_ERR_STATE, "smenv_step: the GJK item buffer of an earlier step overflowed by " +
+                                      std::to_string(*(volatile int*)env->h_flag) + " items (capacity " +
+                                      std::to_string(env->item_capacity) + "); results since then are invalid");
+    return SM_OK;
+}
+
+static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int random_actions, SmStream s) {
+    int rc = step_check(env, buf, auto_reset, !random_actions);
+    if (rc) return rc;
+    cudaStream_t stream = (cudaStream_t)s;
+    rc = activate(env, stream);
+    if (rc) return rc;
+    const bool tk = env->time_kernels;
+    rc = set_list_layout(env, 1, stream);
+    if (rc) return rc;
+    rc = step_range(env, buf, 0, env->n, 0, auto_reset, random_actions, env->step_counter++, tk, stream);
+    if (rc) return rc;
     if (tk) {
         CU(cudaStreamSynchronize(stream));
         for (int i = 0; i < SM_K_COUNT; ++i) {
@@ -809,8 +921,113 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
         }
         env->timed_steps++;
     }
-    env->launches += contacts ? 5 : 3;
-    CU(cudaGetLastError());
+    return SM_OK;
+}
+
+// Host-buffer step (the call an RL sampler makes): the envs are cut into `chunks` ranges, each on its own stream:
+// actions host -> device, the step's kernels, observation / reward / done device -> host.  The copies of one range
+// overlap the kernels of the others (the two copy engines and the SMs work at the same time), so the PCIe time hides
+// behind the compute instead of adding to it.  The whole fork / join (chunks x (4 copies + 11 kernels)) is captured
+// once into a CUDA graph and replayed with one launch per step: issued call by call it is bound by the host's launch
+// rate.  Returns when the host buffers are complete.
+struct HostStepKey {
+    SmBuffers buf;
+    const void* h[4];
+    int auto_reset, chunks, count, pools;
+};
+
+static int host_step_enqueue(SmEnv* env, const SmBuffers* buf, const float* h_actions, float* h_obs, float* h_reward,
+                             uint8_t* h_done, int auto_reset, int chunks, uint32_t counter, cudaStream_t origin) {
+    const int nj = env->host_scene.n_joints, od = env->host_scene.obs_size;
+    CU(cudaEventRecord(env->chunk_fork, origin));
+    const int per = (env->n + chunks - 1) / chunks;
+    for (int c = 0; c < chunks; ++c) {
+        const int e0 = c * per, m = e0 + per <= env->n ? per : env->n - e0;
+        if (m <= 0) break;
+        cudaStream_t cs = env->chunk_streams[c];
+        CU(cudaStreamWaitEvent(cs, env->chunk_fork, 0));
+        CU(cudaMemcpyAsync((float*)buf->actions + (size_t)e0 * nj, h_actions + (size_t)e0 * nj,
+                           (size_t)m * nj * sizeof(float), cudaMemcpyHostToDevice, cs));
+        int rc = step_range(env, buf, e0, m, c, auto_reset, 0, counter, false, cs);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(h_obs + (size_t)e0 * od, buf->obs + (size_t)e0 * od, (size_t)m * od * sizeof(float),
+                           cudaMemcpyDeviceToHost, cs));
+        CU(cudaMemcpyAsync(h_reward + e0, buf->reward + e0, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, cs));
+        CU(cudaMemcpyAsync(h_done + e0, buf->done + e0, (size_t)m, cudaMemcpyDeviceToHost, cs));
+        CU(cudaEventRecord(env->chunk_done[c], cs));
+        CU(cudaStreamWaitEvent(origin, env->chunk_done[c], 0));
+    }
+    return SM_OK;
+}
+
+extern "C" int smenv_step_host(SmEnv* env, const SmBuffers* buf, const float* h_actions, float* h_obs, float* h_reward,
+                               uint8_t* h_done, int auto_reset, int chunks, SmStream s) {
+    int rc = step_check(env, buf, auto_reset, true);
+    if (rc) return rc;
+    if (!h_actions || !h_obs || !h_reward || !h_done || !buf->obs || !buf->reward || !buf->done)
+        return fail(SM_ERR_ARG, "smenv_step_host: null host or device buffer");
+    if (chunks < 1) chunks = 1;
+    if (chunks > SM_MAX_CHUNKS) chunks = SM_MAX_CHUNKS;
+    if (chunks > env->n) chunks = env->n;
+    cudaStream_t stream = (cudaStream_t)s;
+    rc = activate(env, stream);
+    if (rc) return rc;
+    if (!env->chunk_streams[0]) {
+        // earlier ranges get the higher stream priority: their kernels are scheduled first, they finish first, and
+        // their device -> host copies run while the later ranges still compute (without priorities all ranges finish
+        // together and the copies pile up at the end)
+        int pr_least = 0, pr_greatest = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
+        for (int c = 0; c < SM_MAX_CHUNKS; ++c) {
+            const int prio = pr_greatest + c < pr_least ? pr_greatest + c : pr_least;
+            CU(cudaStreamCreateWithPriority(&env->chunk_streams[c], cudaStreamNonBlocking, prio));
+            CU(cudaEventCreateWithFlags(&env->chunk_done[c], cudaEventDisableTiming));
+        }
+        CU(cudaEventCreateWithFlags(&env->chunk_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&env->host_order, cudaEventDisableTiming));
+        CU(cudaStreamCreateWithFlags(&env->host_stream, cudaStreamNonBlocking));
+    }
+    const uint32_t counter = env->step_counter++;
+    rc = set_list_layout(env, chunks, stream);
+    if (rc) return rc;
+    // the internal origin stream comes after the work already queued on the caller's stream
+    CU(cudaEventRecord(env->host_order, stream));
+    CU(cudaStreamWaitEvent(env->host_stream, env->host_order, 0));
+    static const bool no_graph = getenv("SMENV_DEBUG_SYNC") != nullptr || getenv("SMENV_NO_GRAPH") != nullptr;
+    if (no_graph) {
+        rc = host_step_enqueue(env, buf, h_actions, h_obs, h_reward, h_done, auto_reset, chunks, counter, env->host_stream);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(env->host_stream));
+        return SM_OK;
+    }
+    static_assert(sizeof(HostStepKey) <= sizeof(env->host_graph_key), "host_graph_key too small");
+    HostStepKey key;
+    memset(&key, 0, sizeof(key));
+    key.buf = *buf;
+    key.h[0] = h_actions; key.h[1] = h_obs; key.h[2] = h_reward; key.h[3] = h_done;
+    key.auto_reset = auto_reset; key.chunks = chunks; key.count = env->count ? 1 : 0; key.pools = env->pools_filled ? 1 : 0;
+    if (!env->host_graph || memcmp(&key, env->host_graph_key, sizeof(key)) != 0) {
+        if (env->host_graph) { cudaGraphExecDestroy(env->host_graph); env->host_graph = nullptr; }
+        const unsigned long long launches0 = env->launches;
+        CU(cudaStreamBeginCapture(env->host_stream, cudaStreamCaptureModeThreadLocal));
+        rc = host_step_enqueue(env, buf, h_actions, h_obs, h_reward, h_done, auto_reset, chunks, counter, env->host_stream);
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(env->host_stream, &graph);
+        env->host_graph_kernels = (int)(env->launches - launches0);
+        env->launches = launches0;
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return fail(SM_ERR_CUDA, std::string("smenv_step_host: graph capture: ") + cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&env->host_graph, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) {
+            env->host_graph = nullptr;
+            return fail(SM_ERR_CUDA, std::string("smenv_step_host: graph instantiate: ") + cudaGetErrorString(ce));
+        }
+        memcpy(env->host_graph_key, &key, sizeof(key));
+    }
+    CU(cudaGraphLaunch(env->host_graph, env->host_stream));
+    env->launches += env->host_graph_kernels;
+    CU(cudaStreamSynchronize(env->host_stream));
     return SM_OK;
 }
 extern "C" int smenv_step(SmEnv* env, const SmBuffers* buf, int auto_reset, SmStream s) {

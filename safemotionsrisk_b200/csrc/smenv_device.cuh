@@ -75,6 +75,7 @@ struct DevScene {
     float obst_center[SM_MAX_OBSTACLES][3], obst_radius[SM_MAX_OBSTACLES];
     float contact_thresh[SM_MAX_OBSTACLES][SM_MAX_MOV_ROBOT];
     float contact_thresh_max[SM_MAX_OBSTACLES];
+    float obst_bmin[SM_MAX_OBSTACLES][3], obst_bmax[SM_MAX_OBSTACLES][3];  // box of all parts (cores + margins), body frame
     float obst_center_norm[SM_MAX_OBSTACLES];              // |obst_center|: sphere about the body origin instead
     float contact_rho[SM_MAX_MOV_ROBOT][SM_MAX_JOINTS];    // bound on |d centre(slot) / d q_j| (coarse contact phase)
     int planet_steps, planet_shift, obs_planet_size;

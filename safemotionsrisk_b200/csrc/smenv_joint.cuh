@@ -28,6 +28,7 @@ struct JointArgs {
     int n;
     int random_actions;
     uint32_t k0, k1, step_counter;
+    int env_base;    // index of env 0 of this launch in the whole vector env (Philox counters use the global index)
     float* scratch;  // [n][SM_SCRATCH_FLOATS]
     int* worklist;   // [0] = GJK item counter, [1] = overflowed items of the step: both cleared here
     unsigned long long* counters;  // device SmCounters in the counting mode, else NULL
@@ -40,7 +41,7 @@ struct JointArgs {
 
 __device__ __forceinline__ float joint_action(const JointArgs& A, int env, int j) {
     if (A.random_actions) {  // get_random_action (safe_motions_base.py:1327-1328)
-        uint4 r = philox((uint32_t)env, A.step_counter, (uint32_t)j, 0xAC71u, A.k0, A.k1);
+        uint4 r = philox((uint32_t)(env + A.env_base), A.step_counter, (uint32_t)j, 0xAC71u, A.k0, A.k1);
         return 2.0f * u01f(r.x) - 1.0f;
     }
     return A.buf.actions[(size_t)env * c_sc.n_joints + j];

@@ -50,6 +50,14 @@ __device__ __forceinline__ void rel_pose(const Xf& TA, const Xf& TB, float* R, f
     }
 }
 
+// squared distance of point p to the axis-aligned box [lo, hi]
+__device__ __forceinline__ float box_dist2(V3 p, const float* lo, const float* hi) {
+    const float dx = fmaxf(fmaxf(lo[0] - p.x, p.x - hi[0]), 0.f);
+    const float dy = fmaxf(fmaxf(lo[1] - p.y, p.y - hi[1]), 0.f);
+    const float dz = fmaxf(fmaxf(lo[2] - p.z, p.z - hi[2]), 0.f);
+    return fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+}
+
 // Lower bound of the distance between shapes A and B (minus both margins) from the support-width tables: separation
 // along the line between the bounding-sphere centres.
 __device__ __forceinline__ float axis_lower_bound_d(const DevShape& SA, const DevShape& SB, const Xf& TA, const Xf& TB,
@@ -255,12 +263,18 @@ __device__ __forceinline__ int contact_scan(const SceneSmem& sm, const float* __
                 const Xf& TB = o == 0 ? T0 : T1;
                 const int off = c_sc.obst_shape_off[o], cnt = c_sc.obst_shape_cnt[o];
                 const V3 cl = xf_rot_t(TB, mk(c.x - TB.t[0], c.y - TB.t[1], c.z - TB.t[2]));  // in the obstacle frame
+                {   // the link's sphere against the box of the whole obstacle in its own frame (flat, long bodies)
+                    const float l1 = (rr + th) * (1.0f + 1e-6f) + 1e-6f;
+                    if (box_dist2(cl, c_sc.obst_bmin[o], c_sc.obst_bmax[o]) > l1 * l1) continue;
+                }
 #pragma unroll 1
                 for (int s = 0; s < cnt; ++s) {
                     const DevShape& ps = sm.shapes[off + s];
                     const V3 e = mk(cl.x - ps.cx, cl.y - ps.cy, cl.z - ps.cz);
                     const float l2 = rr + ps.radius + ps.margin + th;
-                    if (dot(e, e) <= l2 * l2 && axis_lower_bound(sh, ps, F, TB) <= th) {
+                    const float l3 = (rr + ps.margin + th) * (1.0f + 1e-6f) + 1e-6f;   // against the box of the part's core
+                    if (dot(e, e) <= l2 * l2 && box_dist2(cl, ps.bmin, ps.bmax) <= l3 * l3 &&
+                        axis_lower_bound(sh, ps, F, TB) <= th) {
                         const int idx = atomicAdd(A.item_count, 1);
                         if (idx < A.capacity) write_item(A.items + idx, env, ia, off + s, GJK_CONTACT, sub, th, F, TB);
                         else atomicAdd(A.overflow, 1);
@@ -273,25 +287,27 @@ __device__ __forceinline__ int contact_scan(const SceneSmem& sm, const float* __
     return count;
 }
 
-// Fine contact planning over the spans the coarse phase listed: four lanes per span (one per sub-step of the span),
-// eight spans per warp.
+// Fine contact planning over the spans the coarse phase listed: one lane per sub-step of a span, 32 / span spans per
+// warp (ten at 24 sub-steps).
 template <bool COUNT>
 __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) contact_plan_kernel(PlanArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n_units = A.cwork[0];
-    if (blockIdx.x * SM_WARPS_PER_BLOCK * 8 >= n_units) return;  // nothing for this block: skip the staging
+    const int span = (c_sc.substeps + SM_COARSE_LANES - 1) / SM_COARSE_LANES;
+    const int upw = 32 / span;                                      // spans per warp: one lane per sub-step of a span
+    if (blockIdx.x * SM_WARPS_PER_BLOCK * upw >= n_units) return;  // nothing for this block: skip the staging
     SmemLayout L = block_prologue(smem_raw, false);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const SceneSmem& sm = L.bs->scene;
     const int S = c_sc.substeps, stride = c_sc.contact_stride;
-    const int span = (S + SM_COARSE_LANES - 1) / SM_COARSE_LANES;
     const int kind = c_sc.n_obstacles > 0 ? c_sc.obst_kind[0] : SM_OBST_NONE;
     const double dt = xdiv(c_sc.ts, (double)S);
     unsigned n_flag = 0;
+    const int lu = lane / span, i = lane - lu * span;
 #pragma unroll 1
-    for (int ub = (blockIdx.x * SM_WARPS_PER_BLOCK + warp) * 8; ub < n_units; ub += gridDim.x * SM_WARPS_PER_BLOCK * 8) {
-        const int u = ub + (lane >> 2), i = lane & 3;
-        if (u >= n_units || i >= span) continue;
+    for (int ub = (blockIdx.x * SM_WARPS_PER_BLOCK + warp) * upw; ub < n_units; ub += gridDim.x * SM_WARPS_PER_BLOCK * upw) {
+        const int u = ub + lu;
+        if (u >= n_units || lu >= upw) continue;
         const int unit = A.cwork[1 + u];
         const int env = unit / SM_COARSE_LANES, k = (unit % SM_COARSE_LANES) * span + i;  // 0-based sub-step
         if (k >= S || ((k + 1) % stride) != 0) continue;

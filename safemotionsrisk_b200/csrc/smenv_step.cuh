@@ -19,6 +19,7 @@ struct StepArgs {
     int n;
     int auto_reset;
     uint32_t k0, k1;   // Philox key (seed)
+    int env_base;      // index of env 0 of this launch in the whole vector env (the Philox counter uses the global index)
     float* scratch;    // [n][SM_SCRATCH_FLOATS]
     const unsigned* res;  // [n][SM_RES_STRIDE] written by distance_plan_kernel / gjk_kernel
     int* heavy;        // joint_heavy_kernel's list; its counter is cleared here for the next step
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
         bool ob_changed = true;  // the bookkeeping above always changes the record
         double ob_new = lane < SM_OBST_STRIDE ? ob[lane] : 0.0;
         if (kind == SM_OBST_BALL && ball_active == 0.0 && A.ball_pool_n > 0) {
-            uint4 r = philox((uint32_t)env, (uint32_t)ball_draws, 0xBA11u, 0u, A.k0, A.k1);
+            uint4 r = philox((uint32_t)(env + A.env_base), (uint32_t)ball_draws, 0xBA11u, 0u, A.k0, A.k1);
             const double* e = A.ball_pool + (size_t)(r.x % (uint32_t)A.ball_pool_n) * SM_BALL_STRIDE;
             ball_draws++;
             if (lane >= SM_OB_BALL_P0 && lane < SM_OB_BALL_P0 + 10) ob_new = e[lane - SM_OB_BALL_P0];
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
         double ret_new = ep_return;
         const double* kin_obs = kin;
         if (done && A.auto_reset && A.start_pool_n > 0) {
-            uint4 r = philox((uint32_t)env, (uint32_t)resets, 0x5E7u, 1u, A.k0, A.k1);
+            uint4 r = philox((uint32_t)(env + A.env_base), (uint32_t)resets, 0x5E7u, 1u, A.k0, A.k1);
             const double* e = A.start_pool + (size_t)(r.x % (uint32_t)A.start_pool_n) * SM_POOL_STRIDE;
             A.buf.kin[(size_t)env * SM_KIN_STRIDE + lane] = e[lane];
             if (lane < SM_OBST_STRIDE) ob_new = e[SM_KIN_STRIDE + lane];
@@ -229,10 +230,10 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
             __syncwarp();
             if (lane == 0) {
                 if (was_reset) {
-                    target_episode_start(tp, kin_obs, nullptr, A.target_pool, A.target_pool_n, env, A.k0, A.k1);
+                    target_episode_start(tp, kin_obs, nullptr, A.target_pool, A.target_pool_n, env + A.env_base, A.k0, A.k1);
                 } else {
                     if (tp_reached && A.target_pool_n > 0) {
-                        uint4 r = philox((uint32_t)env, (uint32_t)tp[SM_TP_DRAWS], 0x7A26u, 2u, A.k0, A.k1);
+                        uint4 r = philox((uint32_t)(env + A.env_base), (uint32_t)tp[SM_TP_DRAWS], 0x7A26u, 2u, A.k0, A.k1);
                         const double* e = A.target_pool + (size_t)(r.x % (uint32_t)A.target_pool_n) * 4;
                         tp[SM_TP_POS] = e[0]; tp[SM_TP_POS + 1] = e[1]; tp[SM_TP_POS + 2] = e[2];
                         tp[SM_TP_ACTIVE] = 1.0;

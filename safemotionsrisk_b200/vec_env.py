@@ -100,6 +100,7 @@ class SafeMotionsVecEnv:
             target=self.target.data_ptr() if self.target is not None else None)
         # pinned host staging for the host-buffer API (step_host)
         self._h_actions = torch.zeros((n, nj), dtype=torch.float32).pin_memory()
+        self.host_actions = self._h_actions.numpy()   # pinned input buffer of step_host
         self._h_obs = torch.zeros((n, d), dtype=torch.float32).pin_memory()
         self._h_reward = torch.zeros(n, dtype=torch.float32).pin_memory()
         self._h_done = torch.zeros(n, dtype=torch.uint8).pin_memory()
@@ -220,19 +221,28 @@ class SafeMotionsVecEnv:
                                                self._stream()), "smenv_step_random")
         return self._outputs()
 
-    def step_host(self, actions_np, gate_threshold=None):
+    def step_host(self, actions_np, gate_threshold=None, chunks=4):
         """Host-buffer API: NumPy actions in, NumPy (obs, reward, done) out through pinned staging buffers.
-        gate_threshold: apply the risk gate (load_networks first) to the actions before the step."""
-        self._h_actions.numpy()[...] = np.asarray(actions_np, dtype=np.float32).reshape(self.num_envs, -1)
-        self.actions.copy_(self._h_actions, non_blocking=True)
+        `host_actions` is the pinned input buffer itself: a sampler that writes its actions there (and passes it, or
+        None) saves the host-side copy.  chunks: env ranges whose copies and kernels overlap (smenv_step_host); the
+        results do not depend on it.  gate_threshold: apply the risk gate (load_networks first) to the actions before
+        the step (whole batch on one stream)."""
+        if actions_np is not None and actions_np is not self.host_actions:
+            self.host_actions[...] = np.asarray(actions_np, dtype=np.float32).reshape(self.num_envs, -1)
         if gate_threshold is not None:
+            self.actions.copy_(self._h_actions, non_blocking=True)
             self.risk_gate(gate_threshold)
-        cabi.check(self._lib.smenv_step(self._handle, C.byref(self._buf), int(self.auto_reset), self._stream()),
-                   "smenv_step")
-        self._h_obs.copy_(self.obs, non_blocking=True)
-        self._h_reward.copy_(self.reward, non_blocking=True)
-        self._h_done.copy_(self.done, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+            cabi.check(self._lib.smenv_step(self._handle, C.byref(self._buf), int(self.auto_reset), self._stream()),
+                       "smenv_step")
+            self._h_obs.copy_(self.obs, non_blocking=True)
+            self._h_reward.copy_(self.reward, non_blocking=True)
+            self._h_done.copy_(self.done, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        else:
+            cabi.check(self._lib.smenv_step_host(self._handle, C.byref(self._buf), self._h_actions.data_ptr(),
+                                                 self._h_obs.data_ptr(), self._h_reward.data_ptr(),
+                                                 self._h_done.data_ptr(), int(self.auto_reset), int(chunks),
+                                                 self._stream()), "smenv_step_host")
         return self._h_obs.numpy(), self._h_reward.numpy(), self._h_done.numpy()
 
     def _outputs(self):

@@ -573,3 +573,36 @@ def test_backup_look_ahead_labels_and_restores_the_state():
         a_o = mlp.backup_forward(w, o_obs).astype(np.float32)
     assert (o_risky != (risk > 0.5)).mean() < 0.05
     env.close()
+
+
+@pytest.mark.parametrize("scene", ["ball", "space_bm", "space_task"])
+def test_host_step_in_ranges_equals_the_device_step(scene):
+    """smenv_step_host cuts the envs into ranges on separate streams (copies overlap kernels); every range count gives
+    bit-identical states, observations and rewards to the one-launch device step, including auto-resets and ball /
+    target replacements (their Philox counters use the global env index) and changes of the range count between steps."""
+    n = 1000   # not a multiple of the range counts: ragged last range
+    ref = make_env(scene, n, auto_reset=True)
+    ref.reset()
+    envs = {c: make_env(scene, n, auto_reset=True) for c in (1, 3, 4, 8)}
+    for e in envs.values():
+        e.reset()
+    mixed = make_env(scene, n, auto_reset=True)
+    mixed.reset()
+    rng = np.random.default_rng(11)
+    for step in range(45):
+        act = rng.uniform(-1, 1, (n, 7)).astype(np.float32)
+        ref.step(torch.from_numpy(act).cuda())
+        torch.cuda.synchronize()
+        want = (ref.obs.cpu().numpy(), ref.reward.cpu().numpy(), ref.done.cpu().numpy())
+        for c, e in list(envs.items()) + [(1 + step % 5, mixed)]:
+            if e is mixed and step % 7 == 3:
+                e.step(torch.from_numpy(act).cuda())   # the device step in between: the list layout goes back to one range
+                got = (e.obs.cpu().numpy(), e.reward.cpu().numpy(), e.done.cpu().numpy())
+            else:
+                got = e.step_host(act, chunks=c)
+            for w, g in zip(want, got):
+                assert np.array_equal(w, g), (scene, c, step)
+            assert torch.equal(e.kin, ref.kin) and torch.equal(e.obst, ref.obst) and torch.equal(e.episode, ref.episode)
+    assert ref.stats[0].item() > 0   # episodes ended and were reset on the way
+    for e in list(envs.values()) + [mixed, ref]:
+        e.close()
