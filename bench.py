@@ -160,7 +160,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--host-chunks", type=int, default=4,
+    ap.add_argument("--host-chunks", type=int, default=2,
                     help="env ranges of the host-buffer step whose copies and kernels overlap (smenv_step_host)")
     ap.add_argument("--risk-gate", action="store_true",
                     help="risk network + backup policy (tensor cores) in front of every step (BASELINE.json configs[3])")

@@ -107,6 +107,10 @@ static double pos_peak(double p, double v, double a, double a1, double J, double
     return best;
 }
 
+/* Stopping rule of the position-bound solve next to the bracket width: a safe a1 (peak <= pmax) whose peak comes within
+ * this many rad of the limit ends the search.  The bracket of the Illinois iteration narrows much later than its
+ * iterates converge (mean 14 evaluations against 8 with this rule, worst case 40 against 26). */
+#define POS_SOLVE_TOL 1e-10
 /* Largest a1 in [lo, hi] whose position peak stays <= pmax; +BIG if hi itself is fine, -BIG if not even lo is. */
 static double pos_upper(double p, double v, double a, double pmax, double lo, double hi, double J, double A,
                         double ts) {
@@ -122,6 +126,7 @@ static double pos_upper(double p, double v, double a, double pmax, double lo, do
         double x = xr - fr * (xr - xl) / (fr - fl);
         if (!(x > xl && x < xr)) x = 0.5 * (xl + xr);
         double f = pos_peak(p, v, a, x, J, A, ts) - pmax;
+        if (f <= 0.0 && f > -POS_SOLVE_TOL) return x; /* the peak rides within 1e-10 rad below the limit: good enough */
         if (f <= 0.0) {
             xl = x; fl = f;
             if (side == -1) fr *= 0.5;

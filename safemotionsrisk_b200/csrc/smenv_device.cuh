@@ -238,6 +238,10 @@ __device__ __forceinline__ double pos_upper_first(double p, double v, double a, 
                                                   double A, double ts) {
     return xsub(pos_peak(p, v, a, hi, J, A, ts), pmax);
 }
+// Stopping rule of the position-bound solve next to the bracket width: a safe a1 (peak <= pmax) whose peak comes
+// within this many rad of the limit ends the search (the Illinois bracket narrows much later than its iterates
+// converge: mean 14 evaluations against 8 with this rule, worst case 40 against 26).
+#define SM_POS_SOLVE_TOL 1e-10
 __device__ __noinline__ double pos_upper_rest(double p, double v, double a, double pmax, double lo, double hi, double J,
                                               double A, double ts, double fr);
 
@@ -259,6 +263,7 @@ __device__ __noinline__ double pos_upper_rest(double p, double v, double a, doub
         double x = xsub(xr, xdiv(xmul(fr, xsub(xr, xl)), xsub(fr, fl)));
         if (!(x > xl && x < xr)) x = xmul(0.5, xadd(xl, xr));
         double f = xsub(pos_peak(p, v, a, x, J, A, ts), pmax);
+        if (f <= 0.0 && f > -SM_POS_SOLVE_TOL) return x;   // safe and within 1e-10 rad of the limit
         if (f <= 0.0) {
             xl = x; fl = f;
             if (side == -1) fr = xmul(fr, 0.5);

@@ -276,6 +276,8 @@ __global__ void __launch_bounds__(SM_HEAVY_THREADS) joint_solve_kernel(JointArgs
             fl = f;
             if (fl > 0.0) { result = fl > 1e-6 ? -SM_BIG : lo; task_done = true; }
             else { xl = lo; side = 0; iit = 0; phase = 1; }
+        } else if (f <= 0.0 && f > -SM_POS_SOLVE_TOL) {
+            result = x; task_done = true;   // safe and within 1e-10 rad of the limit
         } else {
             if (f <= 0.0) {
                 xl = x; fl = f;

@@ -221,7 +221,7 @@ class SafeMotionsVecEnv:
                                                self._stream()), "smenv_step_random")
         return self._outputs()
 
-    def step_host(self, actions_np, gate_threshold=None, chunks=4):
+    def step_host(self, actions_np, gate_threshold=None, chunks=2):
         """Host-buffer API: NumPy actions in, NumPy (obs, reward, done) out through pinned staging buffers.
         `host_actions` is the pinned input buffer itself: a sampler that writes its actions there (and passes it, or
         None) saves the host-side copy.  chunks: env ranges whose copies and kernels overlap (smenv_step_host); the
