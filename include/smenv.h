@@ -279,6 +279,10 @@ int smenv_reset(SmEnv* env, const SmBuffers* buf, const uint8_t* mask, SmStream 
 int smenv_step(SmEnv* env, const SmBuffers* buf, int auto_reset, SmStream stream);
 /* Same launch with device-generated U(-1,1) actions (get_random_action, safe_motions_base.py:1327-1328). */
 int smenv_step_random(SmEnv* env, const SmBuffers* buf, int auto_reset, SmStream stream);
+/* Number of env ranges (1..8) smenv_step / smenv_step_random run side by side on internal streams (joined on the
+ * caller's stream before the call returns control of it).  Results do not depend on it.  Default: 2 from 16 384 envs,
+ * else 1.  The measurement mode (smenv_kernel_timing) always uses one range. */
+int smenv_set_step_ranges(SmEnv* env, int ranges);
 /* The step as an RL sampler calls it, with HOST buffers (pinned for full speed): actions [N][n_joints] in, observation
  * [N][obs_size], reward [N] and done [N] out; the state stays on the device in `buf` (buf->actions / obs / reward / done
  * are the device staging buffers).  The envs are cut into `chunks` (1..8) ranges that run on internal streams, so the

@@ -32,6 +32,7 @@ def load():
     lib.smenv_reset.argtypes = [vp, C.POINTER(abi.SmBuffers), vp, vp]
     lib.smenv_step.argtypes = [vp, C.POINTER(abi.SmBuffers), i32, vp]
     lib.smenv_step_random.argtypes = [vp, C.POINTER(abi.SmBuffers), i32, vp]
+    lib.smenv_set_step_ranges.argtypes = [vp, i32]
     lib.smenv_step_host.argtypes = [vp, C.POINTER(abi.SmBuffers), vp, vp, vp, vp, i32, i32, vp]
     lib.smenv_safe_range.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     lib.smenv_distances.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]

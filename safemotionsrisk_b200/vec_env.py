@@ -221,6 +221,10 @@ class SafeMotionsVecEnv:
                                                self._stream()), "smenv_step_random")
         return self._outputs()
 
+    def set_step_ranges(self, ranges):
+        """Env ranges the device step runs side by side (smenv_set_step_ranges); results do not depend on it."""
+        cabi.check(self._lib.smenv_set_step_ranges(self._handle, int(ranges)), "smenv_set_step_ranges")
+
     def step_host(self, actions_np, gate_threshold=None, chunks=2):
         """Host-buffer API: NumPy actions in, NumPy (obs, reward, done) out through pinned staging buffers.
         `host_actions` is the pinned input buffer itself: a sampler that writes its actions there (and passes it, or

@@ -588,6 +588,9 @@ def test_host_step_in_ranges_equals_the_device_step(scene):
         e.reset()
     mixed = make_env(scene, n, auto_reset=True)
     mixed.reset()
+    ref.set_step_ranges(1)
+    envs[3].set_step_ranges(3)   # its device-side steps (none here) and ...
+    mixed.set_step_ranges(3)     # ... the device steps in between run as three ranges side by side
     rng = np.random.default_rng(11)
     for step in range(45):
         act = rng.uniform(-1, 1, (n, 7)).astype(np.float32)
