@@ -173,12 +173,12 @@ __global__ void __launch_bounds__(SM_HEAVY_THREADS) joint_first_kernel(JointArgs
     if (A.counters && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&A.counters[8], (unsigned long long)n_heavy);
 }
 
-// The solves are nested loops of very different lengths (up to 40 regula-falsi steps, each simulating a braking
-// profile of 1..16 intervals), and a warp pays for the union of its lanes' paths: run task by task, a warp averaged
-// 6.7 active lanes.  Here the nest is flattened into a state machine whose single loop body is ONE interval of the
-// braking profile (the body of pos_peak), executed by all lanes in lockstep; a lane whose profile ends steps its
-// regula falsi, a lane whose task ends takes the next task of the warp's chunk.  The operations of every task are
-// exactly those of pos_upper_rest / pos_peak, in the same order (bit-identical results).
+// The solves are nested loops of very different lengths (up to 40 Newton steps, each simulating a braking profile of
+// 1..16 intervals), and a warp pays for the union of its lanes' paths: run task by task, a warp averaged 6.7 active
+// lanes.  Here the nest is flattened into a state machine whose single loop body is ONE interval of the braking
+// profile (the body of pos_peak_impl<true>), executed by all lanes in lockstep; a lane whose profile ends steps its
+// root search, a lane whose task ends takes the next task of the warp's chunk.  The operations of every task are
+// exactly those of pos_upper_rest / pos_peak_d, in the same order (bit-identical results).
 #ifndef SM_SOLVE_CHUNK_MIN
 #define SM_SOLVE_CHUNK_MIN 32
 #endif
@@ -195,9 +195,10 @@ __global__ void __launch_bounds__(SM_HEAVY_THREADS) joint_solve_kernel(JointArgs
     bool busy = false;
     double* out = nullptr;
     double P0 = 0, V0 = 0, A0 = 0, pmax = 0, lo = 0, J = 1, Am = 1;   // the task (mirrored for a lower bound)
-    double xl = 0, xr = 0, fl = 0, fr = 0, x = 0;                      // regula falsi (Illinois)
-    int side = 0, iit = 0, phase = 0;                                  // phase 0: evaluating f(lo)
+    double xl = 0, xr = 0, fr = 0, x = 0;                              // bracket, current iterate
+    int iit = 0, phase = 0;                                            // phase 0: evaluating f(lo)
     double p = 0, v = 0, a = 0, an = 0, best = 0;                      // braking profile under evaluation
+    double dp = 0, dv = 0, da = 0, dan = 1, dbest = 0;                 // its derivative with respect to the iterate
     int pit = 0;
 #pragma unroll 1
     while (true) {
@@ -221,15 +222,17 @@ __global__ void __launch_bounds__(SM_HEAVY_THREADS) joint_solve_kernel(JointArgs
                 out = hp + 5 + sd;
                 phase = 0; x = lo;
                 p = P0; v = V0; a = A0; an = x; best = P0; pit = 0;
+                dp = 0.0; dv = 0.0; da = 0.0; dan = 1.0; dbest = 0.0;
                 busy = true;
             }
         }
         if (!__any_sync(FULL, busy)) break;
         if (!busy) continue;
-        // ---------------- one interval of the braking profile (body of pos_peak)
+        // ---------------- one interval of the braking profile (body of pos_peak_impl<true>)
         bool eval_done = false;
         {
             const double j = xdiv(xsub(an, a), ts);
+            const double dj = xdiv(xsub(dan, da), ts);
             double tau = -1.0;
             if (j == 0.0) {
                 if (a < 0.0 && v > 0.0) tau = xdiv(-v, a);
@@ -247,23 +250,30 @@ __global__ void __launch_bounds__(SM_HEAVY_THREADS) joint_solve_kernel(JointArgs
             if (tau > 0.0 && tau <= ts) {
                 const double pk = xadd(xadd(xadd(p, xmul(v, tau)), xmul(xmul(xmul(0.5, a), tau), tau)),
                                        xdiv(xmul(xmul(xmul(j, tau), tau), tau), 6.0));
-                if (pk > best) best = pk;
+                if (pk > best) {
+                    best = pk;
+                    dbest = xadd(xadd(xadd(dp, xmul(dv, tau)), xmul(xmul(xmul(0.5, da), tau), tau)),
+                                 xdiv(xmul(xmul(xmul(dj, tau), tau), tau), 6.0));
+                }
             }
             const double pn = xadd(xadd(p, xmul(v, ts)), xmul(xmul(xadd(xdiv(a, 3.0), xdiv(an, 6.0)), ts), ts));
             const double vn = xadd(v, xmul(xmul(xadd(a, an), ts), 0.5));
+            const double dpn = xadd(xadd(dp, xmul(dv, ts)), xmul(xmul(xadd(xdiv(da, 3.0), xdiv(dan, 6.0)), ts), ts));
+            const double dvn = xadd(dv, xmul(xmul(xadd(da, dan), ts), 0.5));
             p = pn; v = vn; a = an;
-            if (p > best) best = p;
+            dp = dpn; dv = dvn; da = dan;
+            if (p > best) { best = p; dbest = dp; }
             if (a <= -Am) {
                 if (v > 0.0) {
                     const double pk = xadd(p, xdiv(xmul(v, v), xmul(2.0, Am)));
-                    if (pk > best) best = pk;
+                    if (pk > best) { best = pk; dbest = xadd(dp, xdiv(xmul(v, dv), Am)); }
                 }
                 eval_done = true;
             } else if (v <= 0.0 && a <= 0.0) {
                 eval_done = true;
             } else {
                 an = xsub(a, xmul(J, ts));
-                if (an < -Am) an = -Am;
+                if (an < -Am) { an = -Am; dan = 0.0; }
                 if (++pit >= 16) eval_done = true;
             }
         }
@@ -272,33 +282,32 @@ __global__ void __launch_bounds__(SM_HEAVY_THREADS) joint_solve_kernel(JointArgs
         const double f = xsub(best, pmax);
         bool task_done = false;
         double result = 0.0;
+        double xn = 0.0;
         if (phase == 0) {
-            fl = f;
+            const double fl = f;
             if (fl > 0.0) { result = fl > 1e-6 ? -SM_BIG : lo; task_done = true; }
-            else { xl = lo; side = 0; iit = 0; phase = 1; }
+            else {
+                xl = lo; iit = 0; phase = 1;
+                xn = xsub(xr, xdiv(xmul(fr, xsub(xr, xl)), xsub(fr, fl)));   // first iterate: secant of the bracket
+                if (!(xn > xl && xn < xr)) xn = xmul(0.5, xadd(xl, xr));
+            }
         } else if (f <= 0.0 && f > -SM_POS_SOLVE_TOL) {
             result = x; task_done = true;   // safe and within 1e-10 rad of the limit
         } else {
-            if (f <= 0.0) {
-                xl = x; fl = f;
-                if (side == -1) fr = xmul(fr, 0.5);
-                side = -1;
-            } else {
-                xr = x; fr = f;
-                if (side == 1) fl = xmul(fl, 0.5);
-                side = 1;
-            }
-            if (++iit >= 40) { result = xl; task_done = true; }
-        }
-        if (!task_done) {
-            if (xsub(xr, xl) <= 1e-9) { result = xl; task_done = true; }
+            if (f <= 0.0) xl = x; else xr = x;
+            if (xsub(xr, xl) <= 1e-9 || ++iit >= 40) { result = xl; task_done = true; }
             else {
-                x = xsub(xr, xdiv(xmul(fr, xsub(xr, xl)), xsub(fr, fl)));
-                if (!(x > xl && x < xr)) x = xmul(0.5, xadd(xl, xr));
-                p = P0; v = V0; a = A0; an = x; best = P0; pit = 0;
+                xn = xl;
+                if (dbest > 0.0) xn = xsub(x, xdiv(xadd(f, 0.5 * SM_POS_SOLVE_TOL), dbest));   // Newton step
+                if (!(xn > xl && xn < xr)) xn = xmul(0.5, xadd(xl, xr));
             }
         }
         if (task_done) { *out = result; busy = false; }
+        else {
+            x = xn;
+            p = P0; v = V0; a = A0; an = x; best = P0; pit = 0;
+            dp = 0.0; dv = 0.0; da = 0.0; dan = 1.0; dbest = 0.0;
+        }
     }
     if (A.counters && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&A.counters[9], (unsigned long long)n_task);
 }
