@@ -238,7 +238,7 @@ typedef struct SmCounters {
     unsigned long long reserved;
     unsigned long long heavy_joints;   /* (env, joint) instances that went through joint_heavy_kernel */
     unsigned long long heavy_solves;   /* position bounds that needed the iterative solve */
-    unsigned long long aux[6];         /* reserved */
+    unsigned long long aux[6];         /* GJK pairs by iteration count: <= 4, <= 8, <= 12, <= 16, <= 24, more */
 } SmCounters;
 
 /* Kernels of one step, in launch order (smenv_kernel_times). */

@@ -159,103 +159,96 @@ __device__ __forceinline__ float4 closest_segment(V3 a, V3 b) {
     return make_float4(p.x, p.y, p.z, __int_as_float(3));
 }
 
-// closest point to the origin on triangle abc; w = kept-vertex mask (bit 0 = a, 1 = b, 2 = c).
-// Robust float32 formulation: the answer is either the foot of the perpendicular (when it falls inside the triangle)
-// or the closest point of one of the three edges; all candidates are evaluated and the nearest wins.  Voronoi-region
-// tests (Ericson 5.1.5) misclassify thin triangles in float32 and then return a point that is not the minimum, which
-// stalls GJK with a support vertex that is "already in the simplex" (seen as 1.6e-4 m distance errors on the table).
-__device__ __noinline__ float4 closest_triangle(V3 a, V3 b, V3 c) {
-    float4 best = closest_segment(a, b);                                                  // a = 1, b = 2
-    float qb = best.x * best.x + best.y * best.y + best.z * best.z;
-    float4 p2 = closest_segment(a, c);                                                    // a = 1, c = 4
-    float q2 = p2.x * p2.x + p2.y * p2.y + p2.z * p2.z;
-    if (q2 < qb) {
-        int m = __float_as_int(p2.w);
-        p2.w = __int_as_float((m & 1) | ((m & 2) << 1));
-        best = p2; qb = q2;
-    }
-    float4 p3 = closest_segment(b, c);                                                    // b = 2, c = 4
-    float q3 = p3.x * p3.x + p3.y * p3.y + p3.z * p3.z;
-    if (q3 < qb) {
-        p3.w = __int_as_float(__float_as_int(p3.w) << 1);
-        best = p3; qb = q3;
-    }
-    V3 ab = b - a, ac = c - a;
-    V3 n = cross(ab, ac);
-    float nn = dot(n, n);
-    if (nn > 1e-12f * dot(ab, ab) * dot(ac, ac)) {  // usable area: foot of the perpendicular p = n (a.n) / |n|^2
-        float s = dot(a, n) / nn;
-        V3 p = s * n;
-        // inside test with the edge functions, all against the same normal
-        float w0 = dot(cross(b - p, c - p), n), w1 = dot(cross(c - p, a - p), n), w2 = dot(cross(a - p, b - p), n);
-        float qi = dot(p, p);
-        if (w0 >= 0.0f && w1 >= 0.0f && w2 >= 0.0f && qi < qb) return make_float4(p.x, p.y, p.z, __int_as_float(7));
-    }
-    return best;
-}
-
 struct Simplex {
     V3 p0, p1, p2, p3;
     int i0, i1, i2, i3;  // (vertex of A << 16 | vertex of B) of each simplex point
     int n;
 };
 
-__device__ __forceinline__ void simplex_keep3(Simplex& S, V3 a, V3 b, V3 c, int ia, int ib, int ic, int mask) {
-    int k = 0;
-    if (mask & 1) { S.p0 = a; S.i0 = ia; k = 1; }
-    if (mask & 2) { if (k == 0) { S.p0 = b; S.i0 = ib; } else { S.p1 = b; S.i1 = ib; } ++k; }
-    if (mask & 4) {
-        if (k == 0) { S.p0 = c; S.i0 = ic; } else if (k == 1) { S.p1 = c; S.i1 = ic; } else { S.p2 = c; S.i2 = ic; }
-        ++k;
+// Candidates of the closest boundary point of a simplex to the origin.  Robust float32 formulation: the answer is the
+// foot of a perpendicular onto a face (when it falls inside the face) or the closest point of an edge; ALL candidates
+// are evaluated and the nearest wins.  Voronoi-region tests (Ericson 5.1.5) misclassify thin triangles in float32 and
+// then return a point that is not the minimum, which stalls GJK with a support vertex that is "already in the
+// simplex" (seen as 1.6e-4 m distance errors on the table).
+//   bits: the simplex vertices the candidate keeps (bit i = point i)
+__device__ __forceinline__ void edge_candidate(V3 a, V3 b, int bit_a, int bit_b, float& qb, V3& bv, int& bm) {
+    const float4 p = closest_segment(a, b);
+    const float q = p.x * p.x + p.y * p.y + p.z * p.z;
+    if (q < qb) {
+        const int m = __float_as_int(p.w);
+        qb = q; bv = mk(p.x, p.y, p.z);
+        bm = ((m & 1) ? bit_a : 0) | ((m & 2) ? bit_b : 0);
     }
-    S.n = k;
+}
+__device__ __forceinline__ void face_candidate(V3 a, V3 b, V3 c, int bits, float& qb, V3& bv, int& bm) {
+    const V3 ab = b - a, ac = c - a;
+    const V3 n = cross(ab, ac);
+    const float nn = dot(n, n);
+    if (nn > 1e-12f * dot(ab, ab) * dot(ac, ac)) {  // usable area: foot of the perpendicular p = n (a.n) / |n|^2
+        const float s = dot(a, n) / nn;
+        const V3 p = s * n;
+        // inside test with the edge functions, all against the same normal
+        const float w0 = dot(cross(b - p, c - p), n), w1 = dot(cross(c - p, a - p), n), w2 = dot(cross(a - p, b - p), n);
+        const float qi = dot(p, p);
+        if (w0 >= 0.0f && w1 >= 0.0f && w2 >= 0.0f && qi < qb) { qb = qi; bv = p; bm = bits; }
+    }
+}
+// does the origin lie on the same side of face abc as the fourth vertex d?
+__device__ __forceinline__ bool same_side(V3 a, V3 b, V3 c, V3 d) {
+    const V3 nrm = cross(b - a, c - a);
+    const float sd = dot(d - a, nrm), so = -dot(a, nrm);
+    return so * sd > 0.0f;
 }
 
-// closest point of the simplex to the origin; reduces the simplex to the supporting face.  true = origin enclosed
+// closest point of the simplex to the origin; reduces the simplex to the supporting face.  true = origin enclosed.
+// One straight-line body for the segment, triangle and tetrahedron cases (6 edges, 4 faces, each evaluated once): the
+// lanes of a warp hold simplices of different sizes, and a body per case would run the three one after the other
+// (the tetrahedron, done face by face, evaluated every edge twice).
 __device__ __forceinline__ bool simplex_solve(Simplex& S, V3& v) {
-    if (S.n == 2) {
-        float4 p = closest_segment(S.p0, S.p1);
-        int m = __float_as_int(p.w);
-        if (m == 2) { S.p0 = S.p1; S.i0 = S.i1; }
-        S.n = (m == 3) ? 2 : 1;
-        v = mk(p.x, p.y, p.z);
-        return false;
-    }
-    if (S.n == 3) {
-        float4 p = closest_triangle(S.p0, S.p1, S.p2);
-        v = mk(p.x, p.y, p.z);
-        simplex_keep3(S, S.p0, S.p1, S.p2, S.i0, S.i1, S.i2, __float_as_int(p.w));
-        return false;
-    }
-    // tetrahedron: faces (012|3) (013|2) (023|1) (123|0).  The closest boundary point is taken over all four faces;
-    // the origin counts as enclosed only if every face test says "inside" AND the tetrahedron is not flat -- in
-    // float32 a sliver of four nearly coplanar support points must never certify a penetration.
-    V3 A = S.p0, B = S.p1, Cc = S.p2, D = S.p3;
-    int ia = S.i0, ib = S.i1, ic = S.i2, id = S.i3;
-    float best = FLT_MAX;
+    const V3 A = S.p0, B = S.p1, C = S.p2, D = S.p3;
+    const int ia = S.i0, ib = S.i1, ic = S.i2, id = S.i3;
+    const int n = S.n;
+    float qb = FLT_MAX;
     V3 bv = mk(0.f, 0.f, 0.f);
-    int bmask = 0, bf = 0;
-    bool inside_all = true;
-#pragma unroll 1
-    for (int f = 0; f < 4; ++f) {
-        V3 a = f == 3 ? B : A, b = f < 2 ? B : Cc, c = f == 0 ? Cc : D, d = f == 0 ? D : f == 1 ? Cc : f == 2 ? B : A;
-        V3 nrm = cross(b - a, c - a);
-        float sd = dot(d - a, nrm), so = -dot(a, nrm);
-        if (!(so * sd > 0.0f)) inside_all = false;
-        float4 p = closest_triangle(a, b, c);
-        float dd = p.x * p.x + p.y * p.y + p.z * p.z;
-        if (dd < best) { best = dd; bv = mk(p.x, p.y, p.z); bmask = __float_as_int(p.w); bf = f; }
+    int bm = 1;
+    edge_candidate(A, B, 1, 2, qb, bv, bm);
+    if (n >= 3) {
+        edge_candidate(A, C, 1, 4, qb, bv, bm);
+        edge_candidate(B, C, 2, 4, qb, bv, bm);
+        if (n >= 4) {
+            edge_candidate(A, D, 1, 8, qb, bv, bm);
+            edge_candidate(B, D, 2, 8, qb, bv, bm);
+            edge_candidate(C, D, 4, 8, qb, bv, bm);
+        }
+        face_candidate(A, B, C, 7, qb, bv, bm);
+        if (n >= 4) {
+            face_candidate(A, B, D, 11, qb, bv, bm);
+            face_candidate(A, C, D, 13, qb, bv, bm);
+            face_candidate(B, C, D, 14, qb, bv, bm);
+            // The origin counts as enclosed only if every face test says "inside" AND the tetrahedron is not flat: in
+            // float32 a sliver of four nearly coplanar support points must never certify a penetration.
+            if (same_side(A, B, C, D) && same_side(A, B, D, C) && same_side(A, C, D, B) && same_side(B, C, D, A)) {
+                const V3 e1 = B - A, e2 = C - A, e3 = D - A;
+                const float det = dot(e3, cross(e1, e2));
+                const float scale2 = dot(e1, e1) * dot(e2, e2) * dot(e3, e3);
+                if (det * det > 1e-8f * scale2) return true;  // normalised volume above 1e-4: a genuine enclosure
+            }
+        }
     }
-    if (inside_all) {
-        V3 e1 = B - A, e2 = Cc - A, e3 = D - A;
-        float det = dot(e3, cross(e1, e2));
-        float scale2 = dot(e1, e1) * dot(e2, e2) * dot(e3, e3);
-        if (det * det > 1e-8f * scale2) return true;  // normalised volume above 1e-4: a genuine enclosure
+    // keep the vertices of the supporting feature, in their order
+    int k = 0;
+    if (bm & 1) k = 1;
+    if (bm & 2) { if (k == 0) { S.p0 = B; S.i0 = ib; } else { S.p1 = B; S.i1 = ib; } ++k; }
+    if (bm & 4) {
+        if (k == 0) { S.p0 = C; S.i0 = ic; } else if (k == 1) { S.p1 = C; S.i1 = ic; } else { S.p2 = C; S.i2 = ic; }
+        ++k;
     }
-    if (bf == 0) simplex_keep3(S, A, B, Cc, ia, ib, ic, bmask);
-    else if (bf == 1) simplex_keep3(S, A, B, D, ia, ib, id, bmask);
-    else if (bf == 2) simplex_keep3(S, A, Cc, D, ia, ic, id, bmask);
-    else simplex_keep3(S, B, Cc, D, ib, ic, id, bmask);
+    if (bm & 8) {
+        if (k == 0) { S.p0 = D; S.i0 = id; } else if (k == 1) { S.p1 = D; S.i1 = id; } else { S.p2 = D; S.i2 = id; }
+        ++k;
+    }
+    (void)ia;
+    S.n = k;
     v = bv;
     return false;
 }

@@ -261,6 +261,8 @@ __global__ void __launch_bounds__(256, GJK_MIN_BLOCKS) gjk_kernel(GjkArgs A) {
                 else if (d + m <= lim) atomicMin(&A.res[(size_t)env * SM_RES_STRIDE + cls], fkey(d));  // group's best
             }
             busy = false;
+            if (COUNT && A.counters)   // histogram of the iterations per pair: <= 4, 8, 12, 16, 24, more
+                atomicAdd(&A.counters[10 + (it <= 4 ? 0 : it <= 8 ? 1 : it <= 12 ? 2 : it <= 16 ? 3 : it <= 24 ? 4 : 5)], 1ull);
         }
     }
     if (COUNT && A.counters) {

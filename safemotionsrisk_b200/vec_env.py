@@ -343,7 +343,9 @@ class SafeMotionsVecEnv:
         c = abi.SmCounters()
         torch.cuda.synchronize(self.device)
         cabi.check(self._lib.smenv_counters(self._handle, C.byref(c), int(reset)), "smenv_counters")
-        return {k: int(getattr(c, k)) for k, _ in abi.SmCounters._fields_ if k != "aux"}
+        out = {k: int(getattr(c, k)) for k, _ in abi.SmCounters._fields_ if k != "aux"}
+        out["gjk_iteration_histogram"] = [int(x) for x in c.aux]   # pairs with <= 4, 8, 12, 16, 24, more iterations
+        return out
 
     # ------------------------------------------------------------------ networks in the step loop (risk gate)
     def load_networks(self, source=None):

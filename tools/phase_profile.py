@@ -17,6 +17,7 @@ for scene in (sys.argv[1:] or ["ball", "space"]):
         c["gjk_calls"]/n, c["distance_items"]/n, c["contact_items"]/n, c["gjk_iters"]/n, c["support_dots"]/n))
     print("   heavy joints %.2f (solves %.2f) per env-step, envs passed to the fine contact planning %.3f" % (
         c["heavy_joints"]/n, c["heavy_solves"]/n, c["contact_envs"]/n))
+    print("   gjk pairs by iterations (<=4, 8, 12, 16, 24, more):", [round(x / max(1, c["gjk_calls"]), 4) for x in c["gjk_iteration_histogram"]])
     env.enable_counters(False); env.kernel_timing(True)
     for _ in range(20): env.step_random()
     t, k = env.kernel_times()
