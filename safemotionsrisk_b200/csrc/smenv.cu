@@ -238,6 +238,11 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     for (int j = 0; j < SM_MAX_JOINTS; ++j) {
         d.joint_parent[j] = sc->joint_parent[j];
         for (int i = 0; i < 9; ++i) d.jR[j][i] = (float)sc->joint_R[j][i];
+        {
+            bool ident = true;
+            for (int i = 0; i < 9; ++i) ident = ident && d.jR[j][i] == ((i % 4 == 0) ? 1.0f : 0.0f);
+            if (ident) d.jr_identity |= 1 << j;
+        }
         for (int i = 0; i < 3; ++i) { d.jt[j][i] = (float)sc->joint_t[j][i]; d.jaxis[j][i] = (float)sc->joint_axis[j][i]; }
         d.pos_lo[j] = sc->pos_lo[j]; d.pos_hi[j] = sc->pos_hi[j]; d.vel_max[j] = sc->vel_max[j];
         d.acc_max[j] = sc->acc_max[j]; d.jerk_max[j] = sc->jerk_max[j];

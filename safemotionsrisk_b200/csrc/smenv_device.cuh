@@ -60,6 +60,7 @@ struct DevScene {
     int n_joints, substeps, contact_stride, limit_velocity, limit_position;
     int joint_parent[SM_MAX_JOINTS];
     float jR[SM_MAX_JOINTS][9], jt[SM_MAX_JOINTS][3], jaxis[SM_MAX_JOINTS][3];
+    int jr_identity;   // bit j: the fixed rotation of joint j is exactly the identity (all iiwa joints: rpy = 0)
     double pos_lo[SM_MAX_JOINTS], pos_hi[SM_MAX_JOINTS], vel_max[SM_MAX_JOINTS], acc_max[SM_MAX_JOINTS],
         jerk_max[SM_MAX_JOINTS];
     double ts, action_mapping_factor, track_kp, track_vel;

@@ -103,12 +103,17 @@ __device__ __forceinline__ void fk_chain_step(const SceneSmem& sm, Xf& F, int j,
     Xf L, C;
     float Rj[9];
     axis_angle(sm.jaxis[j][0], sm.jaxis[j][1], sm.jaxis[j][2], c, s, Rj);
-    const float* A = sm.jR[j];
+    if ((c_sc.jr_identity >> j) & 1) {   // uniform: no fixed rotation in front of the joint (x * 1 + 0 drops out exactly)
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < 9; ++i) L.r[i] = Rj[i];
+    } else {
+        const float* A = sm.jR[j];
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-            L.r[3 * i + k] = fmaf(A[3 * i], Rj[k], fmaf(A[3 * i + 1], Rj[3 + k], A[3 * i + 2] * Rj[6 + k]));
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                L.r[3 * i + k] = fmaf(A[3 * i], Rj[k], fmaf(A[3 * i + 1], Rj[3 + k], A[3 * i + 2] * Rj[6 + k]));
+    }
     L.t[0] = sm.jt[j][0]; L.t[1] = sm.jt[j][1]; L.t[2] = sm.jt[j][2];
     xf_compose(F, L, C);
     F = C;
@@ -180,6 +185,25 @@ __global__ void __launch_bounds__(256) contact_coarse_kernel(PlanArgs A) {
                 }
             }
         }
+        // one sphere per obstacle for the whole span: centre = mean of the tested sub-step positions, radius grown by
+        // the largest deviation from it (a planet travels ~1 cm in a span, the ball ~7 cm)
+        V3 om[2];
+        float otr[2] = {0.f, 0.f};
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+            V3 sum = mk(0.f, 0.f, 0.f);
+            int cnt = 0;
+#pragma unroll
+            for (int i = 0; i < SM_COARSE_SPAN; ++i)
+                if ((valid >> (o * SM_COARSE_SPAN + i)) & 1u) { sum = sum + oc[o][i]; ++cnt; }
+            om[o] = cnt ? (1.0f / (float)cnt) * sum : mk(0.f, 0.f, 0.f);
+            float d2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < SM_COARSE_SPAN; ++i)
+                if ((valid >> (o * SM_COARSE_SPAN + i)) & 1u) { const V3 e = oc[o][i] - om[o]; d2 = fmaxf(d2, dot(e, e)); }
+            otr[o] = sqrtf(d2) * (1.0f + 1e-6f) + 1e-6f;
+        }
+        const unsigned omask = ((valid & ((1u << SM_COARSE_SPAN) - 1u)) ? 1u : 0u) | ((valid >> SM_COARSE_SPAN) ? 2u : 0u);
         if (valid) {
             const float* scr = A.scratch + (size_t)env * SM_SCRATCH_FLOATS;
             float dq[SM_MAX_JOINTS];
@@ -206,14 +230,10 @@ __global__ void __launch_bounds__(256) contact_coarse_kernel(PlanArgs A) {
 #pragma unroll
                     for (int o = 0; o < 2; ++o) {
                         if (o >= c_sc.n_obstacles) continue;  // uniform: skips the unrolled body
-                        const float lim = rr + c_sc.obst_radius[o] + c_sc.obst_center_norm[o] + sm.contact_thresh[o][slot];
-#pragma unroll
-                        for (int i = 0; i < SM_COARSE_SPAN; ++i) {
-                            if (i >= span) continue;          // uniform
-                            if (!((valid >> (o * SM_COARSE_SPAN + i)) & 1u)) continue;
-                            const V3 e = ctr - oc[o][i];
-                            if (dot(e, e) <= lim * lim) flag = true;
-                        }
+                        if (!((omask >> o) & 1u)) continue;
+                        const float lim = rr + c_sc.obst_radius[o] + c_sc.obst_center_norm[o] + sm.contact_thresh[o][slot] + otr[o];
+                        const V3 e = ctr - om[o];
+                        if (dot(e, e) <= lim * lim) flag = true;
                     }
                 }
             }
