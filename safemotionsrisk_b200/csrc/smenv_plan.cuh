@@ -207,18 +207,29 @@ __global__ void __launch_bounds__(256) contact_coarse_kernel(PlanArgs A) {
         if (valid) {
             const float* scr = A.scratch + (size_t)env * SM_SCRATCH_FLOATS;
             float dq[SM_MAX_JOINTS];
-            const float* qc = scr + kc * SM_MAX_JOINTS;
+            float qc[SM_MAX_JOINTS];
+            static_assert(SM_MAX_JOINTS == 8, "rows of the sub-step poses are read as two float4");
+            {   // rows of 8 floats, 32-byte aligned: two 16-byte loads per sub-step
+                const float4* rows = reinterpret_cast<const float4*>(scr);
+                const float4 c0 = rows[2 * kc], c1 = rows[2 * kc + 1];
+                qc[0] = c0.x; qc[1] = c0.y; qc[2] = c0.z; qc[3] = c0.w; qc[4] = c1.x; qc[5] = c1.y; qc[6] = c1.z; qc[7] = c1.w;
 #pragma unroll
-            for (int j = 0; j < SM_MAX_JOINTS; ++j) {
-                float m = 0.f;
-                for (int k = k0; k < k1; ++k) m = fmaxf(m, fabsf(scr[k * SM_MAX_JOINTS + j] - qc[j]));
-                dq[j] = m;
+                for (int j = 0; j < SM_MAX_JOINTS; ++j) dq[j] = 0.f;
+#pragma unroll
+                for (int i = 0; i < SM_COARSE_SPAN; ++i) {
+                    if (k0 + i >= k1) continue;
+                    const float4 a0 = rows[2 * (k0 + i)], a1 = rows[2 * (k0 + i) + 1];
+                    dq[0] = fmaxf(dq[0], fabsf(a0.x - qc[0])); dq[1] = fmaxf(dq[1], fabsf(a0.y - qc[1]));
+                    dq[2] = fmaxf(dq[2], fabsf(a0.z - qc[2])); dq[3] = fmaxf(dq[3], fabsf(a0.w - qc[3]));
+                    dq[4] = fmaxf(dq[4], fabsf(a1.x - qc[4])); dq[5] = fmaxf(dq[5], fabsf(a1.y - qc[5]));
+                    dq[6] = fmaxf(dq[6], fabsf(a1.z - qc[6])); dq[7] = fmaxf(dq[7], fabsf(a1.w - qc[7]));
+                }
             }
             Xf F;
             xf_identity(F);
 #pragma unroll 1
             for (int f = 0; f <= c_sc.n_joints && !flag; ++f) {
-                if (f > 0) fk_chain_step(sm, F, f - 1, qc[f - 1]);
+                if (f > 0) fk_chain_step(sm, F, f - 1, scr[kc * SM_MAX_JOINTS + f - 1]);   // (cached) re-read: no dynamic index into registers
 #pragma unroll 1
                 for (int slot = c_sc.contact_frame_start[f]; slot < c_sc.contact_frame_start[f + 1]; ++slot) {
                     const DevShape& sh = sm.shapes[sm.mov_contact[slot]];
