@@ -846,7 +846,7 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
     const int T = SM_WARPS_PER_BLOCK * 32;
     const int blocks = (m + SM_WARPS_PER_BLOCK - 1) / SM_WARPS_PER_BLOCK;
     const int grid_p = blocks < env->grid_broad ? blocks : env->grid_broad;
-    const int grid_f = (m + 7) / 8;
+    const int grid_f = (m + SM_FINISH_ENVS_PER_BLOCK - 1) / SM_FINISH_ENVS_PER_BLOCK;
     const bool contacts = env->host_scene.contact_stride > 0 && env->host_scene.n_obstacles > 0;
     SM_MARK(SM_K_CONTACT_PLAN);
     // The contact planning and the distance planning are independent (both only append to the item list): outside the

@@ -189,12 +189,13 @@ __device__ __forceinline__ double normalize_mm(double x, double lo, double hi) {
 }
 // kin: the env's kinematic record in global memory (q[8] v[8] a[8] ...); ob: obstacle record (16 doubles)
 // tp: the env's target-point record (NULL unless the scene uses target points)
+// The entries are spread over `stride` lanes, `lane` = 0 .. stride - 1 (a warp per env, or 8 lanes per env).
 __device__ __noinline__ void write_observation(float* obs, const double* kin, const double* ob, const double* tp,
-                                               int lane) {
+                                               int lane, int stride = 32) {
     const int nj = c_sc.n_joints;
     const int n_tp = (c_sc.use_target_points && tp) ? 3 * c_sc.obs_add_tp_pos + 3 * c_sc.obs_add_tp_rel : 0;
 #pragma unroll 1
-    for (int i = lane; i < c_sc.obs_size; i += 32) {
+    for (int i = lane; i < c_sc.obs_size; i += stride) {
         double val = 0.0;
         if (i < 3 * nj) {
             int grp = i / nj, j = i - grp * nj;

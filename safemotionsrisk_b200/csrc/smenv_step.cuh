@@ -1,4 +1,4 @@
-// smenv_step.cuh -- last kernel of the env step, one warp per env (SafeMotionsBase.step, safe_motions_base.py:
+// smenv_step.cuh -- last kernel of the env step, eight lanes per env (SafeMotionsBase.step, safe_motions_base.py:
 // 1043-1227): obstacle bookkeeping of the 24 sub-steps, reward, termination, info, ball replacement, auto reset,
 // observation (ctlp.py:2590-2862; rewards.py:432-502; safe_motions_base.py:1775-1799; observations.py:313-351).
 //
@@ -35,25 +35,36 @@ struct StepArgs {
 };
 
 // ------------------------------------------------------------------------------------------------------------------
+// EIGHT LANES PER ENV, four envs per warp, 32 per block: almost everything here is scalar work per env (bookkeeping,
+// reward algebra, termination), which a warp per env repeated on 32 lanes; the per-env records are 16 or 32 words, so
+// a lane moves two or four of them.  Lane group g of a warp owns env 4 * warp_index + g; `sl` is the lane inside its
+// group.  Groups past the last env run along on the last env with every store masked (`valid`), so that all lanes reach
+// the warp-wide synchronisations.
+#define SM_FINISH_ENVS_PER_BLOCK 32
 template <bool COUNT>
 __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
     __shared__ double s_stats[16];
-    __shared__ double s_ob[8][SM_OBST_STRIDE];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ double s_ob[SM_FINISH_ENVS_PER_BLOCK][SM_OBST_STRIDE];
+    const int tid = threadIdx.x, lane = tid & 31, sl = lane & 7;
+    const unsigned gmask = 0xffu << (lane & 24);   // the lanes of this env's group
     if (tid < 16) s_stats[tid] = 0.0;
     if (blockIdx.x == 0 && tid == 0) {
         if (A.heavy) A.heavy[0] = 0;
         if (A.overflow && *A.overflow != 0 && A.host_flag) *A.host_flag = *A.overflow;
     }
     __syncthreads();
-    const int env = blockIdx.x * 8 + warp;
+    const int env_raw = blockIdx.x * SM_FINISH_ENVS_PER_BLOCK + (tid >> 3);
+    const bool valid = env_raw < A.n;
+    const int env = valid ? env_raw : A.n - 1;
     const int nj = c_sc.n_joints;
     const int kind = c_sc.n_obstacles > 0 ? c_sc.obst_kind[0] : SM_OBST_NONE;
-    if (env < A.n) {
+    {
         const double* kin = A.buf.kin + (size_t)env * SM_KIN_STRIDE;
         const float* scr = A.scratch + (size_t)env * SM_SCRATCH_FLOATS + SM_MISC_OFF;
-        double* ob = s_ob[warp];
-        if (lane < SM_OBST_STRIDE) ob[lane] = A.buf.obst[(size_t)env * SM_OBST_STRIDE + lane];
+        double* ob = s_ob[tid >> 3];
+        static_assert(SM_OBST_STRIDE == 16 && SM_KIN_STRIDE == 32 && SM_INFO_STRIDE == 16, "record sizes of the 8-lane layout");
+        ob[sl] = A.buf.obst[(size_t)env * SM_OBST_STRIDE + sl];
+        ob[sl + 8] = A.buf.obst[(size_t)env * SM_OBST_STRIDE + sl + 8];
         const int4 ep = *reinterpret_cast<const int4*>(A.buf.episode + 4 * (size_t)env);
         const int ep_len = ep.x + 1;  // safe_motions_base.py:1044
         const float rcode = (float)__float_as_int(scr[SM_MISC_RCODE]), jerk_rel = scr[SM_MISC_JERK], umax = scr[SM_MISC_UMAX];
@@ -81,7 +92,7 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
                 for (int i = 0; i < adv; ++i) ball_t = xadd(ball_t, dt);   // self._t += update_time_step
             }
             __syncwarp();
-            if (lane == 0) {
+            if (sl == 0) {
                 ob[SM_OB_INDEX] = (double)idx_new;
                 ob[SM_OB_LATCH] = latch;
                 if (kind == SM_OBST_BALL) { ob[SM_OB_BALL_T] = ball_t; ob[SM_OB_BALL_ACTIVE] = ball_active; }
@@ -110,11 +121,10 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
         }
         double low_acc = 0.0, low_vel = 0.0;
         if (c_sc.w_low_acc != 0.0 || c_sc.w_low_vel != 0.0) {  // rewards.py:448-460
-            const int j = lane & 7;
-            float ra = lane < nj ? (float)fabs(kin[16 + j] / c_sc.acc_max[j]) : 0.0f;
-            float rv = lane < nj ? (float)fabs(kin[8 + j] / c_sc.vel_max[j]) : 0.0f;
-            ra = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(ra)));
-            rv = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(rv)));
+            float ra = sl < nj ? (float)fabs(kin[16 + sl] / c_sc.acc_max[sl]) : 0.0f;
+            float rv = sl < nj ? (float)fabs(kin[8 + sl] / c_sc.vel_max[sl]) : 0.0f;
+            ra = __uint_as_float(__reduce_max_sync(gmask, __float_as_uint(ra)));
+            rv = __uint_as_float(__reduce_max_sync(gmask, __float_as_uint(rv)));
             double da = fmin(1.0, (double)ra / c_sc.thr_low_acc), dv = fmin(1.0, (double)rv / c_sc.thr_low_vel);
             if (c_sc.w_low_acc != 0.0) low_acc = (da - 1.0) * (da - 1.0);
             if (c_sc.w_low_vel != 0.0) low_vel = (dv - 1.0) * (dv - 1.0);
@@ -156,16 +166,19 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
         else if (c_sc.terminate_moving && c_moving) { done = 1; reason = SM_TERM_MOVING_COLLISION; }
         else if (finished) { done = 1; reason = SM_TERM_TRAJECTORY_LENGTH; }
         const double ep_return = A.buf.ep_return[env] + reward;
+        __syncwarp();   // every lane has read the target-point record and the running return before lane 0 updates them
 
         // ---------------- outputs of the finished step
-        if (lane == 0) {
+        if (sl == 0 && valid) {
             A.buf.reward[env] = (float)reward;
             A.buf.done[env] = (uint8_t)done;
             A.buf.term_reason[env] = reason;
         }
-        if (lane < SM_INFO_STRIDE) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int slot = sl + 8 * h;
             float val = 0.0f;
-            switch (lane) {
+            switch (slot) {
                 case SM_INFO_D_STATIC: val = (float)ds; break;
                 case SM_INFO_D_SELF: val = (float)dse; break;
                 case SM_INFO_D_MOVING: val = (float)dm; break;
@@ -184,9 +197,9 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
                 case SM_INFO_TP_REWARD: val = (float)tp_reward; break;
                 default: break;
             }
-            A.buf.info[(size_t)env * SM_INFO_STRIDE + lane] = val;
+            if (valid) A.buf.info[(size_t)env * SM_INFO_STRIDE + slot] = val;
         }
-        if (lane == 0 && done) {  // episode statistics (train.py:59-117), aggregated per block first
+        if (sl == 0 && done && valid) {  // episode statistics (train.py:59-117), aggregated per block first
             atomicAdd(&s_stats[0], 1.0);
             atomicAdd(&s_stats[1], ep_return);
             atomicAdd(&s_stats[2], (double)ep_len);
@@ -196,18 +209,20 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
         // ---------------- a ball that reached a final state is replaced when the observation is taken
         // (ctlp.py:2354-2360, :2893-2895); the launch comes from the device-resident ball pool
         int ball_draws = ep.z;
-        bool ob_changed = true;  // the bookkeeping above always changes the record
-        double ob_new = lane < SM_OBST_STRIDE ? ob[lane] : 0.0;
+        double ob_new[2] = {ob[sl], ob[sl + 8]};   // the lane's two words of the obstacle record
         if (kind == SM_OBST_BALL && ball_active == 0.0 && A.ball_pool_n > 0) {
             uint4 r = philox((uint32_t)(env + A.env_base), (uint32_t)ball_draws, 0xBA11u, 0u, A.k0, A.k1);
             const double* e = A.ball_pool + (size_t)(r.x % (uint32_t)A.ball_pool_n) * SM_BALL_STRIDE;
             ball_draws++;
-            if (lane >= SM_OB_BALL_P0 && lane < SM_OB_BALL_P0 + 10) ob_new = e[lane - SM_OB_BALL_P0];
-            if (lane == SM_OB_INDEX || lane == SM_OB_BALL_T || lane == SM_OB_LATCH) ob_new = 0.0;
-            if (lane == SM_OB_BALL_ACTIVE) ob_new = 1.0;
-            if (lane == SM_OB_BALL_NMAX) ob_new = e[10];
-            if (lane == SM_OB_BALL_NHIT) ob_new = e[11];
-            ob_changed = true;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int w = sl + 8 * h;
+                if (w >= SM_OB_BALL_P0 && w < SM_OB_BALL_P0 + 10) ob_new[h] = e[w - SM_OB_BALL_P0];
+                if (w == SM_OB_INDEX || w == SM_OB_BALL_T || w == SM_OB_LATCH) ob_new[h] = 0.0;
+                if (w == SM_OB_BALL_ACTIVE) ob_new[h] = 1.0;
+                if (w == SM_OB_BALL_NMAX) ob_new[h] = e[10];
+                if (w == SM_OB_BALL_NHIT) ob_new[h] = e[11];
+            }
         }
         // ---------------- vector-env auto reset from the device-resident start pool
         int ep_len_new = ep_len, resets = ep.y;
@@ -216,9 +231,12 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
         if (done && A.auto_reset && A.start_pool_n > 0) {
             uint4 r = philox((uint32_t)(env + A.env_base), (uint32_t)resets, 0x5E7u, 1u, A.k0, A.k1);
             const double* e = A.start_pool + (size_t)(r.x % (uint32_t)A.start_pool_n) * SM_POOL_STRIDE;
-            A.buf.kin[(size_t)env * SM_KIN_STRIDE + lane] = e[lane];
-            if (lane < SM_OBST_STRIDE) ob_new = e[SM_KIN_STRIDE + lane];
-            ob_changed = true;
+            if (valid) {
+#pragma unroll
+                for (int h = 0; h < 4; ++h) A.buf.kin[(size_t)env * SM_KIN_STRIDE + sl + 8 * h] = e[sl + 8 * h];
+            }
+            ob_new[0] = e[SM_KIN_STRIDE + sl];
+            ob_new[1] = e[SM_KIN_STRIDE + sl + 8];
             kin_obs = e;
             ep_len_new = 0;
             resets++;
@@ -227,8 +245,7 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
         __syncwarp();
         const bool was_reset = kin_obs != kin;
         if (tp) {  // get_target_point_observation (ctlp.py:2210-2271): replace a reached point, record the distances
-            __syncwarp();
-            if (lane == 0) {
+            if (sl == 0 && valid) {
                 if (was_reset) {
                     target_episode_start(tp, kin_obs, nullptr, A.target_pool, A.target_pool_n, env + A.env_base, A.k0, A.k1);
                 } else {
@@ -248,26 +265,29 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
                         if (isnan(tp[SM_TP_INIT_DIST])) tp[SM_TP_INIT_DIST] = tp[SM_TP_LAST_DIST];
                     }
                 }
+                __threadfence_block();
             }
             __syncwarp();
         }
-        if (ob_changed && lane < SM_OBST_STRIDE) {
-            A.buf.obst[(size_t)env * SM_OBST_STRIDE + lane] = ob_new;
-            ob[lane] = ob_new;
-        }
-        if (lane == 0) {
-            *reinterpret_cast<int4*>(A.buf.episode + 4 * (size_t)env) = make_int4(ep_len_new, resets, ball_draws, ep.w);
-            A.buf.ep_return[env] = ret_new;
+        ob[sl] = ob_new[0];
+        ob[sl + 8] = ob_new[1];
+        if (valid) {
+            A.buf.obst[(size_t)env * SM_OBST_STRIDE + sl] = ob_new[0];
+            A.buf.obst[(size_t)env * SM_OBST_STRIDE + sl + 8] = ob_new[1];
+            if (sl == 0) {
+                *reinterpret_cast<int4*>(A.buf.episode + 4 * (size_t)env) = make_int4(ep_len_new, resets, ball_draws, ep.w);
+                A.buf.ep_return[env] = ret_new;
+            }
         }
         __syncwarp();
         // ---------------- observation of the state the next action acts on (observations.py:313-351)
-        write_observation(A.buf.obs + (size_t)env * c_sc.obs_size, kin_obs, ob, tp, lane);
+        if (valid) write_observation(A.buf.obs + (size_t)env * c_sc.obs_size, kin_obs, ob, tp, sl, 8);
     }
     __syncthreads();
     if (A.buf.stats && tid < 16 && s_stats[tid] != 0.0) atomicAdd(&A.buf.stats[tid], s_stats[tid]);
     if (COUNT && A.counters && tid == 0) {
-        int first = blockIdx.x * 8;
-        int cntb = A.n - first < 8 ? A.n - first : 8;
+        int first = blockIdx.x * SM_FINISH_ENVS_PER_BLOCK;
+        int cntb = A.n - first < SM_FINISH_ENVS_PER_BLOCK ? A.n - first : SM_FINISH_ENVS_PER_BLOCK;
         if (cntb > 0) atomicAdd(&A.counters[4], (unsigned long long)cntb);
     }
 }
