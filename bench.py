@@ -150,7 +150,26 @@ def cpu_reference_run(scene_name, envs_per_thread, steps, warmup, threads, targe
     return total / dt, dt, total, steps
 
 
+_STDOUT_FD = None
+
+
+def _quiet_stdout():
+    """Everything printed to stdout from here on (NCCL's version banner, library chatter) goes to stderr; the one JSON
+    line of the contract is written to the real stdout by _emit."""
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    os.write(_STDOUT_FD if _STDOUT_FD is not None else 1, (line + "\n").encode())
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -186,7 +205,7 @@ def main():
         val, dt, total, steps = cpu_reference_run(args.scene, per_thread, steps, min(max(args.warmup, 1), 2), threads)
         sample = "{} host threads x {} envs x {} steps of the same scene ({} env-steps in {:.1f} s)".format(
             threads, per_thread, steps, total, dt)
-        print(json.dumps({
+        _emit(json.dumps({
             "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
@@ -385,7 +404,7 @@ def main():
                    threads, per_thread, csteps, total, dt),
                "note": "oracle restatement -- NOT the PyBullet reference (not installable here)"}
     if rank == 0:
-        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        out = {"impl": "b200", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": max(3, args.warmup), "ms_per_step": tmax_ms / args.steps, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f64 joint space / f32 geometry",
                "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
@@ -394,7 +413,7 @@ def main():
                                  "mean_length": float(stats[2] / max(stats[0], 1)),
                                  "by_termination_reason": {str(r): float(stats[3 + r]) for r in range(1, 6)},
                                  "allreduce_ms": stats_ms}}
-        print(json.dumps(out))
+        _emit(json.dumps(out))
     env.close()
     if world > 1:
         dist.destroy_process_group()
