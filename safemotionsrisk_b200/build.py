@@ -6,6 +6,7 @@ import subprocess
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.environ.get("SMENV_LIB") or os.path.join(CSRC, "libsmenv.so")  # SMENV_LIB: experiment builds
 SOURCES = ["smenv.cu", "smenv_device.cuh", "smenv_geom.cuh", "smenv_kernels.cuh", "smenv_joint.cuh", "smenv_step.cuh",
+           "smenv_gjk.cuh", "smenv_plan.cuh", "smenv_mlp.cuh",
            "smenv_pools.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared"]

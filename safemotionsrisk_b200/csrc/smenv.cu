@@ -524,7 +524,7 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, distance_plan_kernel<false>, SM_WARPS_PER_BLOCK * 32, env->smem_bytes_broad));
     if (per_sm < 1) { delete env; return fail(SM_ERR_CUDA, "planning kernels do not fit on an SM"); }
     env->grid_broad = sms * per_sm;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk_kernel<false>, 256, env->smem_bytes_gjk));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk_kernel<false>, GJK_THREADS, env->smem_bytes_gjk));
     if (per_sm < 1) { delete env; return fail(SM_ERR_CUDA, "gjk kernel does not fit on an SM"); }
     env->grid_gjk = sms * per_sm;
     // big batches step as two env ranges side by side: the latency-bound tails of one range's kernels (the longest
@@ -877,8 +877,8 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
         CU(cudaStreamWaitEvent(stream, env->side_join[chunk], 0));
     }
     SM_MARK(SM_K_GJK);
-    if (env->count) gjk_kernel<true><<<env->grid_gjk, 256, env->smem_bytes_gjk, stream>>>(G);
-    else gjk_kernel<false><<<env->grid_gjk, 256, env->smem_bytes_gjk, stream>>>(G);
+    if (env->count) gjk_kernel<true><<<env->grid_gjk, GJK_THREADS, env->smem_bytes_gjk, stream>>>(G);
+    else gjk_kernel<false><<<env->grid_gjk, GJK_THREADS, env->smem_bytes_gjk, stream>>>(G);
     SM_MARK(SM_K_FINISH);
     if (env->count) finish_kernel<true><<<grid_f, 256, 0, stream>>>(A);
     else finish_kernel<false><<<grid_f, 256, 0, stream>>>(A);
@@ -1109,7 +1109,7 @@ extern "C" int smenv_distances(SmEnv* env, const double* kin, const double* obst
     const int blocks = (n + SM_WARPS_PER_BLOCK - 1) / SM_WARPS_PER_BLOCK;
     const int grid_p = blocks < env->grid_broad ? blocks : env->grid_broad;
     distance_plan_kernel<false><<<grid_p, T, env->smem_bytes_broad, stream>>>(P);
-    gjk_kernel<false><<<env->grid_gjk, 256, env->smem_bytes_gjk, stream>>>(G);
+    gjk_kernel<false><<<env->grid_gjk, GJK_THREADS, env->smem_bytes_gjk, stream>>>(G);
     distances_out_kernel<<<(n + 255) / 256, 256, 0, stream>>>(env->d_res, obst, d_static, d_self, d_moving, n);
     env->launches += 3;
     CU(cudaGetLastError());

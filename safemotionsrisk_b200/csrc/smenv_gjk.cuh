@@ -110,9 +110,12 @@ __device__ __forceinline__ int support_thread(const float4* __restrict__ v, int 
 #ifndef GJK_MIN_BLOCKS
 #define GJK_MIN_BLOCKS 2 /* resident CTAs per SM the register allocation aims for */
 #endif
+#ifndef GJK_THREADS
+#define GJK_THREADS 256  /* threads per CTA */
+#endif
 
 template <bool COUNT>
-__global__ void __launch_bounds__(256, GJK_MIN_BLOCKS) gjk_kernel(GjkArgs A) {
+__global__ void __launch_bounds__(GJK_THREADS, GJK_MIN_BLOCKS) gjk_kernel(GjkArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int n_items = *A.n_items;
     if (n_items > A.capacity) n_items = A.capacity;
