@@ -168,6 +168,11 @@ static void clamp_range(double* lo, double* hi, double blo, double bhi, int code
     *lo = nlo; *hi = nhi;
 }
 
+/* test hook: the braking-profile peak and its derivative with respect to the next-knot acceleration */
+double smo_pos_peak(double p, double v, double a, double a1, double J, double A, double ts, double* dpeak) {
+    return pos_peak_d(p, v, a, a1, J, A, ts, dpeak);
+}
+
 void smo_safe_range_joint(const SmScene* sc, int j, double p, double v, double a, double* out_lo, double* out_hi,
                           int32_t* out_code) {
     double ts = sc->ts, J = sc->jerk_max[j], A = sc->acc_max[j], V = sc->vel_max[j];

@@ -183,3 +183,33 @@ def test_interpolation_matches_reference_twins(space_scene):
     # v1 = v0 + (a0 + a1) dt / 2 and p1 = p0 + v0 dt + (a0/3 + a1/6) dt^2 (klimits model)
     assert np.allclose(env.kin[:, 8:15], v + 0.5 * (a + a1) * TS, atol=1e-12)
     assert np.allclose(env.kin[:, 0:7], q + v * TS + (a / 3 + a1 / 6) * TS ** 2, atol=1e-12)
+
+
+def test_peak_derivative_matches_finite_differences():
+    """The position-bound solve is a Newton iteration on peak(a1) - limit with the derivative carried along the
+    simulated braking profile (oracle/smenv_oracle.c: pos_peak_d): away from the kinks of the profile the derivative
+    agrees with a central difference, and the peak is non-decreasing in a1."""
+    import ctypes as C
+    lib = oracle.lib()
+    lib.smo_pos_peak.restype = C.c_double
+    lib.smo_pos_peak.argtypes = [C.c_double] * 7 + [C.POINTER(C.c_double)]
+    rng = np.random.default_rng(5)
+    ts, checked = 0.1, 0
+    for _ in range(4000):
+        J, A = rng.choice([150.0, 200.0, 300.0, 400.0]), rng.choice([7.5, 10.0, 15.0, 20.0])
+        p, v, a = rng.uniform(-2.5, 2.5), rng.uniform(-1.7, 1.7), rng.uniform(-A, A)
+        a1 = rng.uniform(max(-A, a - J * ts), min(A, a + J * ts))
+        d = C.c_double()
+        f0 = lib.smo_pos_peak(p, v, a, a1, J, A, ts, C.byref(d))
+        h = 1e-5
+        dm, dp_ = C.c_double(), C.c_double()
+        fm = lib.smo_pos_peak(p, v, a, a1 - h, J, A, ts, C.byref(dm))
+        fp = lib.smo_pos_peak(p, v, a, a1 + h, J, A, ts, C.byref(dp_))
+        assert fp >= fm - 1e-12                       # monotone
+        assert f0 >= p                                # the peak is at least the start position
+        if abs(dm.value - dp_.value) > 1e-6 * max(1.0, abs(d.value)):
+            continue                                  # a kink of the profile between a1 - h and a1 + h
+        fd = (fp - fm) / (2 * h)
+        assert abs(fd - d.value) <= 1e-6 + 1e-4 * abs(d.value), (p, v, a, a1, fd, d.value)
+        checked += 1
+    assert checked > 2000
