@@ -109,6 +109,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* r) {
     for (int i = 0; i < 32; ++i) r[i] = __uint_as_float(u[i]);
 }
 
+// 16 consecutive accumulator columns, asynchronously: the registers are valid after tmem_wait16 on the same array (the
+// wait names them as in/out operands, so the compiler cannot move their uses in front of it)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* u) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+          "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait16(uint32_t* u) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+                 : "+r"(u[0]), "+r"(u[1]), "+r"(u[2]), "+r"(u[3]), "+r"(u[4]), "+r"(u[5]), "+r"(u[6]), "+r"(u[7]),
+                   "+r"(u[8]), "+r"(u[9]), "+r"(u[10]), "+r"(u[11]), "+r"(u[12]), "+r"(u[13]), "+r"(u[14]), "+r"(u[15])
+                 :: "memory");
+}
+
 __device__ __forceinline__ float mlp_hidden_act(float x, int act) {
     if (act == MLP_ACT_SELU) return 1.0507009873554805f * (x > 0.0f ? x : 1.6732632423543772f * (__expf(x) - 1.0f));
     return x / (1.0f + __expf(-x));  // swish
@@ -257,36 +274,51 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(MlpArgs A) {
             // ---------------- epilogue: accumulator row of this env -> bias, activation -> next operand / output
             const bool last = l == net.n_tc - 1;
             const float* bl = bias + l * MLP_MAX_WIDTH;
-#pragma unroll 1
-            for (int c0 = half * (N / MLP_PARTS); c0 < (half + 1) * (N / MLP_PARTS); c0 += 32) {
-                float r[32];
-                tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+            // 16 columns at a time, the next 16 in flight while these go through the activation (the load latency of
+            // the tensor memory hides behind the arithmetic)
+            {
+                const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16);
+                const int cbeg = half * (N / MLP_PARTS), cend = (half + 1) * (N / MLP_PARTS);
+                const int hidden_act = net.hidden_act, n_out = net.n_out;
+                auto process16 = [&](const uint32_t* u, int c) {
+                    float r[16];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = mlp_hidden_act(r[j] + bl[c0 + j], net.hidden_act);
-                if (!last) {
+                    for (int j = 0; j < 16; ++j) r[j] = mlp_hidden_act(__uint_as_float(u[j]) + bl[c + j], hidden_act);
+                    if (!last) {
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        __align__(16) __half h[8];
+                        for (int g2 = 0; g2 < 2; ++g2) {
+                            __align__(16) __half h[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) h[i] = __float2half_rn(r[8 * g + i]);
-                        *reinterpret_cast<uint4*>(a_act + (uint32_t)((c0 + 8 * g) / 8) * 2048u + row_off) =
-                            *reinterpret_cast<const uint4*>(h);
-                    }
-                } else {
-                    if (net.n_out == 1) {   // the risk network: one output column
+                            for (int i = 0; i < 8; ++i) h[i] = __float2half_rn(r[8 * g2 + i]);
+                            *reinterpret_cast<uint4*>(a_act + (uint32_t)((c + 8 * g2) / 8) * 2048u + row_off) =
+                                *reinterpret_cast<const uint4*>(h);
+                        }
+                    } else if (n_out == 1) {   // the risk network: one output column
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) acc_out[0] = fmaf(r[j], w_out[(c0 + j) * MLP_MAX_OUT], acc_out[0]);
+                        for (int j = 0; j < 16; ++j) acc_out[0] = fmaf(r[j], w_out[(c + j) * MLP_MAX_OUT], acc_out[0]);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float4 wa = *reinterpret_cast<const float4*>(w_out + (c0 + j) * MLP_MAX_OUT);
-                            const float4 wb = *reinterpret_cast<const float4*>(w_out + (c0 + j) * MLP_MAX_OUT + 4);
+                        for (int j = 0; j < 16; ++j) {
+                            const float4 wa = *reinterpret_cast<const float4*>(w_out + (c + j) * MLP_MAX_OUT);
+                            const float4 wb = *reinterpret_cast<const float4*>(w_out + (c + j) * MLP_MAX_OUT + 4);
                             acc_out[0] = fmaf(r[j], wa.x, acc_out[0]); acc_out[1] = fmaf(r[j], wa.y, acc_out[1]);
                             acc_out[2] = fmaf(r[j], wa.z, acc_out[2]); acc_out[3] = fmaf(r[j], wa.w, acc_out[3]);
                             acc_out[4] = fmaf(r[j], wb.x, acc_out[4]); acc_out[5] = fmaf(r[j], wb.y, acc_out[5]);
                             acc_out[6] = fmaf(r[j], wb.z, acc_out[6]); acc_out[7] = fmaf(r[j], wb.w, acc_out[7]);
                         }
                     }
+                };
+                uint32_t ua[16], ub[16];
+                tmem_ld16_issue(tbase + (uint32_t)cbeg, ua);
+                tmem_wait16(ua);
+#pragma unroll 1
+                for (int c0 = cbeg; c0 < cend; c0 += 32) {
+                    tmem_ld16_issue(tbase + (uint32_t)(c0 + 16), ub);
+                    process16(ua, c0);
+                    tmem_wait16(ub);
+                    if (c0 + 32 < cend) tmem_ld16_issue(tbase + (uint32_t)(c0 + 32), ua);
+                    process16(ub, c0 + 16);
+                    if (c0 + 32 < cend) tmem_wait16(ua);
                 }
             }
             tc_fence_before();
