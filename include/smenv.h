@@ -36,7 +36,7 @@ extern "C" {
 #define SM_MAX_OBS 64
 #define SM_KIN_STRIDE 32  /* doubles per env in the kinematic record: q[8] v[8] a[8] q_act[8] */
 #define SM_OBST_STRIDE 16 /* doubles per env in the obstacle record */
-#define SM_INFO_STRIDE 16 /* floats per env in the step-info record */
+#define SM_INFO_STRIDE 32 /* floats per env in the step-info record */
 
 enum SmStatus { SM_OK = 0, SM_ERR_ARG = -1, SM_ERR_CUDA = -2, SM_ERR_SCENE = -3, SM_ERR_STATE = -4 };
 enum SmObstacleKind { SM_OBST_NONE = 0, SM_OBST_PLANET = 1, SM_OBST_BALL = 2 };
@@ -68,7 +68,12 @@ enum SmInfoSlot {
     SM_INFO_RANGE_CODE = 12,    /* OR of the per-joint violation codes of the range used for this step */
     SM_INFO_CONTACT_LATCH = 13, /* 1 if a sub-step contact with a moving obstacle was latched (ctlp.py:2631-2637) */
     SM_INFO_MAX_JERK_REL = 14,  /* max_j |jerk_j| / jerk_max_j of the step (rewards.py:181-203) */
-    SM_INFO_TP_REWARD = 15      /* target_point_reward (rewards.py:345-348) */
+    SM_INFO_TP_REWARD = 15,     /* target_point_reward (rewards.py:345-348) */
+    SM_INFO_RISKY_ACTION = 16,  /* risky_action_rate of the step: 1 if the risk gate replaced the action (actions.py:335-340) */
+    SM_INFO_RISK = 17,          /* the risk network's prediction for the proposed action (safe_motions_base.py:1600) */
+    SM_INFO_FIRST_RISKY_STEP = 18, /* risk_network_first_risky_action_step of the episode, -1 = none so far
+                                      (actions.py:337-338, safe_motions_base.py:1378) */
+    SM_INFO_REWARD_RAW = 19     /* reward before normalize_reward_to_frequency (rewards.py:172-176) */
 };
 
 /* Slots of the per-env obstacle record (SM_OBST_STRIDE doubles per env; integers are stored exactly as doubles). */
@@ -196,6 +201,7 @@ typedef struct SmScene {
     double tp_box_min[3], tp_box_max[3]; /* target_point_cartesian_range (sampling and position normalisation) */
     double tp_rel_min[3], tp_rel_max[3]; /* target_point_relative_pos_min_max (ctlp.py:184) */
     double tp_min_static, tp_min_self;   /* clearances of the pose a target point is sampled from (ctlp.py:1661-1664) */
+    double reward_scale;           /* trajectory_time_step / 0.1 with normalize_reward_to_frequency, else 1 (rewards.py:172-176) */
 } SmScene;
 
 #define SM_TP_STRIDE 12 /* doubles per env in the target-point record */
@@ -215,7 +221,7 @@ enum SmTargetSlot {
 typedef struct SmBuffers {
     double* kin;          /* [N][SM_KIN_STRIDE]  q, v, a, q_act */
     double* obst;         /* [N][SM_OBST_STRIDE] */
-    int32_t* episode;     /* [N][4]  episode_length, reset_count, reserved, reserved */
+    int32_t* episode;     /* [N][4]  episode_length, reset_count, ball draws, 1 + first risky step of the episode (0 = none) */
     double* ep_return;    /* [N] running episode return */
     const float* actions; /* [N][n_joints] in [-1, 1] */
     float* obs;           /* [N][obs_size] */
@@ -257,6 +263,10 @@ int smenv_sizeof_shape(void);
 
 int smenv_create(const SmScene* scene, int num_envs, int device, uint64_t seed, SmEnv** out);
 int smenv_destroy(SmEnv* env);
+/* SafeMotionsBase.set_seed (safe_motions_base.py:1704-1710): new Philox key for every draw made from now on (pool
+ * picks of resets / balls / target points, random actions); the step counter of the random actions restarts at 0.
+ * Re-draw the pools with smenv_fill_pools(seed) to reproduce an env created with that seed. */
+int smenv_set_seed(SmEnv* env, uint64_t seed);
 
 /* Start-state / ball pools, sampled on the device (rejection sampling with Philox). */
 int smenv_pool_sizes(SmEnv* env, int* start_pool, int* ball_pool);
@@ -311,10 +321,11 @@ int smenv_kernel_times(SmEnv* env, double* ms_out /* SM_K_COUNT */, int* steps_o
  * Networks in the step loop (safe_motions_base.py:1498-1603, actions.py:303-340): batched inference on the tensor
  * cores.  which: SM_NET_RISK = risk(obs, action) -> [0, 1]; SM_NET_BACKUP = backup policy, obs -> action mean.
  * dims = { n_in, N_1 .. N_n_tc, n_out }: n_tc hidden Dense layers (widths multiples of 16, at most 256, or 512) and
- * one output Dense layer (n_out <= 8).  weights (host, float32, Keras layout): per layer kernel [in][out] row-major
+ * one output Dense layer (n_out <= 16; SM_NET_HUMAN: the human's stochastic policy, means and log-std outputs,
+ * ctlp.py:4647-4762).  weights (host, float32, Keras layout): per layer kernel [in][out] row-major
  * followed by its bias.  hidden_act: 0 selu, 1 swish; out_act: 0 sigmoid, 1 tanh.
  */
-enum SmNet { SM_NET_RISK = 0, SM_NET_BACKUP = 1 };
+enum SmNet { SM_NET_RISK = 0, SM_NET_BACKUP = 1, SM_NET_HUMAN = 2, SM_NET_COUNT = 3 };
 int smenv_mlp_load(SmEnv* env, int which, int n_tc, const int32_t* dims, int hidden_act, int out_act,
                    const float* weights);
 /* out[n][out_stride] = net([in0 row, in1 row]) for n rows; all device pointers (in1 may be NULL with in1_w = 0). */
@@ -324,6 +335,12 @@ int smenv_mlp_forward(SmEnv* env, int which, const float* in0, int in0_w, const 
  * (obs = buf->obs, the observation the action was computed from).  risk_out [N] / risky_out [N] may be NULL. */
 int smenv_risk_gate(SmEnv* env, const SmBuffers* buf, float threshold, float* risk_out, uint8_t* risky_out,
                     SmStream stream);
+/* Risk gate inside the step (actions.py:303-340): with threshold >= 0 every smenv_step / smenv_step_random /
+ * smenv_step_host first rates buf->actions with the risk network on buf->obs and executes the backup policy's action
+ * in the envs rated >= threshold.  buf->actions keeps the proposed action (the action punishment of the reward is
+ * computed from it, safe_motions_base.py:1066); info slots SM_INFO_RISKY_ACTION / RISK / FIRST_RISKY_STEP report the
+ * gate.  Needs both networks (smenv_mlp_load).  threshold < 0 switches the gate off (default). */
+int smenv_set_risk_gate(SmEnv* env, float threshold);
 /* Writes the U(-1,1) actions smenv_step_random would use for the next step into buf->actions (so that the gate can be
  * applied to them; follow with smenv_step). */
 int smenv_random_actions(SmEnv* env, const SmBuffers* buf, SmStream stream);

@@ -809,8 +809,12 @@ void smo_step_tp(const SmScene* sc, double* kin, double* ob, double* tp, int32_t
     else if (sc->terminate_static && c_static) { done = 1; reason = SM_TERM_STATIC_COLLISION; }
     else if (sc->terminate_moving && c_moving) { done = 1; reason = SM_TERM_MOVING_COLLISION; }
     else if (finished) { done = 1; reason = SM_TERM_TRAJECTORY_LENGTH; }
+    double reward_raw = reward;
+    if (sc->reward_scale != 0.0) reward *= sc->reward_scale;                          /* rewards.py:172-176 */
     *ep_return += reward;
     out->reward = (float)reward;
+    out->info[SM_INFO_REWARD_RAW] = (float)reward_raw;
+    out->info[SM_INFO_FIRST_RISKY_STEP] = -1.0f; /* the gate is not part of the oracle step: tests apply it in NumPy */
     out->done = done;
     out->term_reason = reason;
     out->info[SM_INFO_D_STATIC] = (float)ds;

@@ -12,7 +12,7 @@ SM_MAX_PAIRS = 48
 SM_MAX_MOV_ROBOT = 24
 SM_KIN_STRIDE = 32
 SM_OBST_STRIDE = 16
-SM_INFO_STRIDE = 16
+SM_INFO_STRIDE = 32
 SM_TP_STRIDE = 12
 TP_POS, TP_LAST_DIST, TP_INIT_DIST, TP_ACTIVE, TP_REACHED_N, TP_LINK_POS, TP_DRAWS, TP_REACHED = 0, 3, 4, 5, 6, 7, 10, 11
 
@@ -29,7 +29,7 @@ TERMINATION_COLLISION_WITH_MOVING_OBSTACLE = 5
 
 INFO_SLOTS = ["d_static", "d_self", "d_moving", "coll_static", "coll_self", "coll_moving", "action_punishment",
               "r_static", "r_self", "r_moving", "episode_length", "episode_return", "range_code", "contact_latch",
-              "max_jerk_rel", "tp_reward"]
+              "max_jerk_rel", "tp_reward", "risky_action", "risk", "first_risky_step", "reward_raw"]
 INFO = {name: i for i, name in enumerate(INFO_SLOTS)}
 
 OB_INDEX, OB_LATCH, OB_BALL_P0, OB_BALL_V0, OB_BALL_EULER0, OB_BALL_OMEGA, OB_BALL_T, OB_BALL_ACTIVE, \
@@ -109,6 +109,7 @@ class SmScene(C.Structure):
         ("tp_radius", d), ("tp_bonus", d), ("tp_reward_factor", d),
         ("tp_box_min", d * 3), ("tp_box_max", d * 3), ("tp_rel_min", d * 3), ("tp_rel_max", d * 3),
         ("tp_min_static", d), ("tp_min_self", d),
+        ("reward_scale", d),
     ]
 
 
@@ -133,4 +134,5 @@ EXPORTED_SYMBOLS = [
     "smenv_step", "smenv_step_random", "smenv_step_host", "smenv_set_step_ranges", "smenv_safe_range", "smenv_distances", "smenv_observation",
     "smenv_counters", "smenv_enable_counters", "smenv_launch_count", "smenv_debug_gjk", "smenv_kernel_timing",
     "smenv_kernel_times", "smenv_set_targets", "smenv_mlp_load", "smenv_mlp_forward", "smenv_risk_gate", "smenv_random_actions",
+    "smenv_set_seed", "smenv_set_risk_gate",
 ]

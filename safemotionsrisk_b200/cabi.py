@@ -44,6 +44,8 @@ def load():
     lib.smenv_mlp_load.argtypes = [vp, i32, i32, vp, i32, i32, vp]
     lib.smenv_mlp_forward.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, i32, vp]
     lib.smenv_risk_gate.argtypes = [vp, C.POINTER(abi.SmBuffers), C.c_float, vp, vp, vp]
+    lib.smenv_set_seed.argtypes = [vp, u64]
+    lib.smenv_set_risk_gate.argtypes = [vp, C.c_float]
     lib.smenv_random_actions.argtypes = [vp, C.POINTER(abi.SmBuffers), vp]
     lib.smenv_kernel_timing.argtypes = [vp, i32]
     lib.smenv_kernel_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i32), i32]

@@ -5,7 +5,8 @@ Mirrors the constructor keywords of the reference env stack (``SafeMotionsBase._
 rewards.py:40-54, :409-417, ``SafeObservation`` observations.py:46-49) with the same names and defaults, so a
 ``params.json`` of a reference checkpoint can be passed unchanged.  Unknown keys are swallowed exactly like the
 reference's ``**kwargs`` (safe_motions_base.py:207).  Keys that select parts of the reference
-this package does not implement raise ``NotImplementedError`` instead of being silently ignored.
+this package does not implement raise ``NotImplementedError`` as soon as their value differs from the reference
+default, instead of being silently ignored (``_UNSUPPORTED_UNLESS``).
 """
 import json
 
@@ -33,8 +34,11 @@ _DEFAULTS = dict(
     moving_object_speed_meter_per_second=1.0, moving_object_aim_at_current_robot_position=False,
     moving_object_check_invalid_target_link_point_positions=False, moving_object_active_number_single=1,
     moving_object_random_initial_position=False, moving_object_high_launch_angle_probability=1.0,
-    # human
-    human_network_checkpoint=None,
+    # human (robot_scene_base.py:96-99, ctlp.py:4647-4959)
+    human_network_checkpoint=None, human_network_use_full_observation=False,
+    human_network_use_collision_avoidance_starting_point_sampling=False,
+    human_network_collision_avoidance_kinematic_state_sampling_probability=0.3,
+    human_network_collision_avoidance_stay_in_state_probability=0.3,
     # termination / collision avoidance mode
     terminate_on_self_collision=False, terminate_on_collision_with_static_obstacle=False,
     terminate_on_collision_with_moving_obstacle=False,
@@ -53,7 +57,20 @@ _DEFAULTS = dict(
     normalize_reward_to_frequency=False,
     # braking-trajectory method and target points: not part of the hot path this package implements
     check_braking_trajectory_collisions=False, check_braking_trajectory_torque_limits=False,
-    risk_config_dir=None, risk_config=None, risk_threshold=None,
+    risk_config_dir=None, risk_config=None, risk_threshold=None, risk_state_config=0,
+    risk_state_backup_trajectory_steps=None, risk_check_initial_backup_trajectory=False,
+    risk_state_initial_backup_trajectory_steps=None, risk_use_backup_agent_for_initial_backup_trajectory_only=False,
+    risk_state_deterministic_backup_trajectory=False, risk_store_ground_truth=False,
+    risk_ignore_estimation_probability=0.0,
+    # reward terms of TargetPointReachingReward that belong to the braking-trajectory / torque machinery
+    # (rewards.py:231-266, :316-375)
+    punish_adaptation=False, punish_end_min_distance=False, punish_end_max_torque=False,
+    punish_braking_trajectory_min_distance=False, punish_braking_trajectory_max_torque=False,
+    # other keys of the reference constructor that change the behaviour of the path (safe_motions_base.py:85-207)
+    obstacle_use_computed_actual_values=False, distance_calculation_check_observed_points=False,
+    collision_avoidance_new_state_sample_time_range=None, always_use_collision_avoidance_starting_point_sampling=False,
+    terminate_on_robot_stop=False, max_resampling_attempts=0, static_robot=False, activate_obstacle_collisions=False,
+    observed_link_point_scene=0, control_time_step=None,
     # target points of the reaching task (safe_motions_base.py:131-137, rewards.py:231-266)
     use_target_points=False, target_point_cartesian_range_scene=0, target_point_relative_pos_scene=0,
     target_point_radius=0.05, target_point_sequence=0, target_point_reached_reward_bonus=0.0,
@@ -67,8 +84,28 @@ _DEFAULTS = dict(
     contact_check_stride=1,
 )
 
-_UNSUPPORTED_TRUE = ["check_braking_trajectory_collisions", "check_braking_trajectory_torque_limits",
-                     "use_real_robot", "moving_object_aim_at_current_robot_position"]
+# Keys that select parts of the reference this package does not implement: any value other than the listed
+# (reference default) one raises instead of being silently ignored.  A key whose non-default value is a no-op for the
+# path (rendering, logging, file output) is not listed.
+_UNSUPPORTED_UNLESS = dict(
+    check_braking_trajectory_collisions=False, check_braking_trajectory_torque_limits=False, use_real_robot=False,
+    moving_object_aim_at_current_robot_position=False,
+    # klimits constructor arguments (actions.py:97-106) that the range model here does not have a knob for: the range is
+    # the exact set of accelerations from which the limits stay satisfiable (deviation 1)
+    acceleration_after_max_vel_limit_factor=0.01, set_velocity_after_max_pos_to_zero=True,
+    action_preprocessing_function=None,   # "tanh" is computed and discarded by the reference; others unknown
+    punish_adaptation=False, punish_end_min_distance=False, punish_end_max_torque=False,
+    punish_braking_trajectory_min_distance=False, punish_braking_trajectory_max_torque=False,
+    obstacle_use_computed_actual_values=False, distance_calculation_check_observed_points=False,
+    collision_avoidance_new_state_sample_time_range=None, always_use_collision_avoidance_starting_point_sampling=False,
+    terminate_on_robot_stop=False, max_resampling_attempts=0, static_robot=False, activate_obstacle_collisions=False,
+    observed_link_point_scene=0, control_time_step=None,
+    human_network_use_full_observation=False,
+    risk_state_config=0, risk_use_backup_agent_for_initial_backup_trajectory_only=False,
+    risk_state_deterministic_backup_trajectory=False, risk_store_ground_truth=False,
+    risk_ignore_estimation_probability=0.0, risk_config=None,
+)
+_ALSO_ACCEPTED = dict(action_preprocessing_function=("tanh",))   # equivalent to the default
 
 
 class EnvConfig(dict):
@@ -82,10 +119,13 @@ class EnvConfig(dict):
                 self[key] = value
             else:
                 self.ignored[key] = value  # swallowed like the reference's **kwargs
-        for key in _UNSUPPORTED_TRUE:
-            if self[key]:
-                raise NotImplementedError("env_config key '{}' selects a part of the reference outside the hot path "
-                                          "implemented here (see DESIGN.md, out of scope)".format(key))
+        for key, default in _UNSUPPORTED_UNLESS.items():
+            if self[key] != default and self[key] not in _ALSO_ACCEPTED.get(key, ()):
+                raise NotImplementedError("env_config key '{}' = {!r} selects a part of the reference this package does "
+                                          "not implement (only {!r} is supported; see DESIGN.md)".format(
+                                              key, self[key], default))
+        if (self["risk_config_dir"] is None) != (self["risk_threshold"] is None) and self["risk_config_dir"] is not None:
+            raise ValueError("risk_config_dir needs risk_threshold (safe_motions_base.py:527-579, README.md:223-235)")
         if self["robot_scene"] != 0:
             raise NotImplementedError("only robot_scene=0 (one iiwa7) is implemented; the reference itself defines "
                                       "only robot_scene 0 and 9 (robot_scene_base.py:169-183)")

@@ -159,11 +159,14 @@ struct SmEnv {
     int* d_flag = nullptr;       // its device alias
     size_t smem_bytes_gjk = 0;
     int grid_gjk = 0;
-    MlpNet nets[2];              // risk network, backup policy (smenv_mlp_load)
-    bool net_loaded[2] = {false, false};
+    MlpNet nets[SM_NET_COUNT];   // risk network, backup policy, human policy (smenv_mlp_load)
+    bool net_loaded[SM_NET_COUNT] = {};
     std::vector<void*> net_allocs;
     float* d_risk = nullptr;     // [n] risk of the proposed action
     float* d_backup = nullptr;   // [n][MLP_MAX_OUT] action mean of the backup policy
+    float* d_exec = nullptr;     // [n][n_joints] actions executed when the gate is on (smenv_set_risk_gate)
+    uint8_t* d_risky = nullptr;  // [n] 1 where the gate replaced the action
+    float gate_threshold = -1.0f;  // < 0: gate off
     bool time_kernels = false;   // measurement mode (smenv_kernel_timing)
     cudaEvent_t ev[SM_K_COUNT + 1] = {};
     double kernel_ms[SM_K_COUNT] = {};
@@ -192,16 +195,33 @@ struct SmEnv {
     unsigned long long launches = 0;
 };
 
-static SmEnv* g_active = nullptr;  // whose scene currently sits in constant memory
+// The scene of the env being driven sits in constant memory (c_sc), one copy per device.  Every entry point that
+// launches kernels holds the device's lock for the duration of the call (all launches are asynchronous, so calls are
+// short) and, when another env's scene is loaded, waits for that env's outstanding work before replacing it: several
+// envs, also on different host threads or streams, can share a device and only pay a device synchronisation when the
+// driven env changes.
+#define SM_MAX_DEVICES 64
+static std::recursive_mutex g_dev_mu[SM_MAX_DEVICES];
+static SmEnv* g_active[SM_MAX_DEVICES] = {};   // whose scene currently sits in the device's constant memory
+static size_t g_smem_geom[SM_MAX_DEVICES] = {}, g_smem_gjk[SM_MAX_DEVICES] = {};  // opt-in limits set so far (never lowered)
+
+struct DevLock {
+    std::unique_lock<std::recursive_mutex> l;
+    explicit DevLock(const SmEnv* env);
+};
 
 static int activate(SmEnv* env, cudaStream_t stream) {
     CU(cudaSetDevice(env->device));
-    if (g_active != env) {
+    SmEnv*& active = g_active[env->device % SM_MAX_DEVICES];
+    if (active != env) {
+        if (active) CU(cudaDeviceSynchronize());   // kernels of the previous env may still read its scene
         CU(cudaMemcpyToSymbolAsync(c_sc, &env->host_scene, sizeof(DevScene), 0, cudaMemcpyHostToDevice, stream));
-        g_active = env;
+        active = env;
     }
     return SM_OK;
 }
+
+DevLock::DevLock(const SmEnv* env) : l(g_dev_mu[(env ? env->device : 0) % SM_MAX_DEVICES]) {}
 
 extern "C" const char* smenv_last_error(void) { return g_error.c_str(); }
 extern "C" int smenv_abi_version(void) { return 1; }
@@ -215,6 +235,13 @@ static int upload(T** dst, const std::vector<T>& src) {
     return SM_OK;
 }
 
+extern "C" int smenv_destroy(SmEnv* env);
+// frees a half-built env on every early return of smenv_create
+struct CreateGuard {
+    SmEnv* env;
+    ~CreateGuard() { if (env) smenv_destroy(env); }
+};
+
 extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_t seed, SmEnv** out) {
     if (!sc || !out || num_envs <= 0) return fail(SM_ERR_ARG, "smenv_create: bad argument");
     if (sc->n_joints <= 0 || sc->n_joints > 7) return fail(SM_ERR_SCENE, "n_joints must be in 1..7");
@@ -227,7 +254,11 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     CU(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(SM_ERR_ARG, "smenv_create: no such CUDA device");
     CU(cudaSetDevice(device));
+    if (device >= SM_MAX_DEVICES) return fail(SM_ERR_ARG, "smenv_create: device index too large");
     SmEnv* env = new SmEnv();
+    CreateGuard guard{env};
+    env->device = device;
+    DevLock dev_lock_(env);
     env->n = num_envs;
     env->device = device;
     env->seed = seed;
@@ -307,7 +338,7 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
         d.contact_frame_start[0] = 0;
         for (int slot = 0; slot < sc->n_mov_contact; ++slot) {
             int fr = sc->shapes[sc->mov_contact[slot]].frame;
-            if (fr < f || fr > sc->n_joints) { delete env; return fail(SM_ERR_SCENE, "mov_contact must be sorted by frame"); }
+            if (fr < f || fr > sc->n_joints) { return fail(SM_ERR_SCENE, "mov_contact must be sorted by frame"); }
             while (f < fr) d.contact_frame_start[++f] = slot;
         }
         while (f <= sc->n_joints) d.contact_frame_start[++f] = sc->n_mov_contact;
@@ -366,7 +397,7 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
             for (int r = 0; r < sc->n_mov_reward; ++r)
                 for (int k = 0; k < sc->obst_shape_cnt[o]; ++k) push(sc->mov_reward[r], sc->obst_shape_off[o] + k, 2);
         d.n_pairs = np;
-        if (np > SM_MAX_PLAN_PAIRS) { delete env; return fail(SM_ERR_SCENE, "too many convex pairs per env for the distance planning (max 512)"); }
+        if (np > SM_MAX_PLAN_PAIRS) { return fail(SM_ERR_SCENE, "too many convex pairs per env for the distance planning (max 512)"); }
     }
     // coarse contact phase: a change of joint j by dq moves the sphere centre of a contact slot in frame f by at most
     // dq * (sum of the fixed joint offsets between frame j+1 and f, plus the centre's own offset)
@@ -406,6 +437,7 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     d.terminate_static = sc->terminate_static; d.terminate_moving = sc->terminate_moving;
     d.action_thresh = sc->action_thresh; d.action_max_punishment = sc->action_max_punishment;
     d.termination_bonus = sc->termination_bonus; d.early_termination_punishment = sc->early_termination_punishment;
+    d.reward_scale = sc->reward_scale != 0.0 ? sc->reward_scale : 1.0;
     d.episode_steps = sc->episode_steps; d.obs_size = sc->obs_size;
     d.kinematic_sampling_probability = sc->kinematic_sampling_probability;
     d.stay_in_state_probability = sc->stay_in_state_probability;
@@ -419,12 +451,12 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     d.has_table = sc->has_table;
 
     int rc = upload(&env->d_verts, verts);
-    if (rc) { delete env; return rc; }
+    if (rc) return rc;
     d.verts = env->d_verts;
     while (lut.empty() || lut.size() % 4) lut.push_back(0u);   // staged in 16-byte vectors
-    if ((rc = upload(&env->d_lut, lut))) { delete env; return rc; }
+    if ((rc = upload(&env->d_lut, lut))) { return rc; }
     d.lut = env->d_lut;
-    if ((rc = upload(&env->d_hwidth, hwidth))) { delete env; return rc; }
+    if ((rc = upload(&env->d_hwidth, hwidth))) { return rc; }
     d.hwidth = env->d_hwidth;
     d.n_lut_words = (int)lut.size();
     for (int o = 0; o < sc->n_obstacles; ++o) {
@@ -436,13 +468,13 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
             pq[i] = make_float4((float)sc->planet_quat[o][4 * i], (float)sc->planet_quat[o][4 * i + 1],
                                 (float)sc->planet_quat[o][4 * i + 2], (float)sc->planet_quat[o][4 * i + 3]);
         }
-        if ((rc = upload(&env->d_ppos[o], pp)) || (rc = upload(&env->d_pquat[o], pq))) { delete env; return rc; }
+        if ((rc = upload(&env->d_ppos[o], pp)) || (rc = upload(&env->d_pquat[o], pq))) { return rc; }
         d.planet_pos[o] = env->d_ppos[o];
         d.planet_quat[o] = env->d_pquat[o];
     }
     if (sc->n_obstacles > 0 && sc->obst_kind[0] == SM_OBST_PLANET) {
         std::vector<double> pl(sc->planet_local_xy, sc->planet_local_xy + 2 * sc->planet_steps);
-        if ((rc = upload(&env->d_plocal, pl))) { delete env; return rc; }
+        if ((rc = upload(&env->d_plocal, pl))) { return rc; }
         d.planet_local_xy = env->d_plocal;
     }
     {   // image of the shared-memory tables of the geometry kernels
@@ -457,7 +489,7 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
         memcpy(si.mov_contact, d.mov_contact, sizeof(si.mov_contact));
         memcpy(si.contact_thresh, d.contact_thresh, sizeof(si.contact_thresh));
         memcpy(img[0].pair_tab, d.pair_tab, sizeof(img[0].pair_tab));
-        if ((rc = upload(&env->d_scene_img, img))) { delete env; return rc; }
+        if ((rc = upload(&env->d_scene_img, img))) { return rc; }
         d.scene_img = reinterpret_cast<const uint4*>(env->d_scene_img);
     }
     // pools: one start state per env is plenty of variety up to 65536; balls are consumed faster
@@ -508,42 +540,59 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     env->smem_bytes = smem_bytes_for(sc->n_verts, SM_WARPS_PER_BLOCK);
     env->smem_bytes_broad = smem_bytes_for(0, SM_WARPS_PER_BLOCK);
     env->smem_bytes_gjk = gjk_smem_bytes(sc->n_verts, d.n_lut_words, sc->n_shapes);
-    CU(cudaFuncSetAttribute(gjk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_gjk));
-    CU(cudaFuncSetAttribute(gjk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_gjk));
-    CU(cudaFuncSetAttribute(fill_ball_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
-    CU(cudaFuncSetAttribute(fill_start_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
-    CU(cudaFuncSetAttribute(fill_target_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
-    CU(cudaFuncSetAttribute(distances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
+    {   // opt-in shared-memory limits are per function and process wide: only ever raised, so that an env created
+        // earlier with bigger tables keeps launching
+        size_t& lim_gjk = g_smem_gjk[device % SM_MAX_DEVICES];
+        size_t& lim_geom = g_smem_geom[device % SM_MAX_DEVICES];
+        if (env->smem_bytes_gjk > lim_gjk) {
+            CU(cudaFuncSetAttribute(gjk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_gjk));
+            CU(cudaFuncSetAttribute(gjk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_gjk));
+            lim_gjk = env->smem_bytes_gjk;
+        }
+        if (env->smem_bytes > lim_geom) {
+            CU(cudaFuncSetAttribute(fill_ball_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
+            CU(cudaFuncSetAttribute(fill_start_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
+            CU(cudaFuncSetAttribute(fill_target_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
+            CU(cudaFuncSetAttribute(distances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
+            CU(cudaFuncSetAttribute(debug_gjk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
+            lim_geom = env->smem_bytes;
+        }
+    }
     // persistent grid: as many CTAs as fit on the device at once (a multiple of the SM count), each looping over envs
     int sms = 0, per_sm = 0;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, distances_kernel, SM_WARPS_PER_BLOCK * 32, env->smem_bytes));
-    if (per_sm < 1) { delete env; return fail(SM_ERR_CUDA, "pool kernels do not fit on an SM"); }
+    if (per_sm < 1) { return fail(SM_ERR_CUDA, "pool kernels do not fit on an SM"); }
     env->grid = sms * per_sm;
     env->sms = sms;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, distance_plan_kernel<false>, SM_WARPS_PER_BLOCK * 32, env->smem_bytes_broad));
-    if (per_sm < 1) { delete env; return fail(SM_ERR_CUDA, "planning kernels do not fit on an SM"); }
+    if (per_sm < 1) { return fail(SM_ERR_CUDA, "planning kernels do not fit on an SM"); }
     env->grid_broad = sms * per_sm;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk_kernel<false>, GJK_THREADS, env->smem_bytes_gjk));
-    if (per_sm < 1) { delete env; return fail(SM_ERR_CUDA, "gjk kernel does not fit on an SM"); }
+    if (per_sm < 1) { return fail(SM_ERR_CUDA, "gjk kernel does not fit on an SM"); }
     env->grid_gjk = sms * per_sm;
     // big batches step as two env ranges side by side: the latency-bound tails of one range's kernels (the longest
     // position-bound solve, the last GJK pairs) hide behind the other's (Space, 65 536 envs: 799 -> 748 us per step)
     if (const char* e = getenv("SMENV_STEP_RANGES")) env->step_ranges = atoi(e) < 1 ? 1 : (atoi(e) > 8 ? 8 : atoi(e));
     else env->step_ranges = num_envs >= 16384 ? 2 : 1;
+    guard.env = nullptr;
     *out = env;
     return SM_OK;
 }
 
 extern "C" int smenv_destroy(SmEnv* env) {
     if (!env) return SM_OK;
-    cudaSetDevice(env->device);
-    if (g_active == env) g_active = nullptr;
+    {
+        DevLock dev_lock_(env);
+        cudaSetDevice(env->device);
+        SmEnv*& active = g_active[env->device % SM_MAX_DEVICES];
+        if (active == env) { cudaDeviceSynchronize(); active = nullptr; }
+    }
     cudaFree(env->d_verts); cudaFree(env->d_lut); cudaFree(env->d_hwidth); cudaFree(env->d_scene_img); cudaFree(env->d_plocal); cudaFree(env->d_start_pool); cudaFree(env->d_ball_pool); cudaFree(env->d_target_pool);
     cudaFree(env->d_counters); cudaFree(env->d_scratch); cudaFree(env->d_worklist); cudaFree(env->d_heavy); cudaFree(env->d_cwork); cudaFree(env->d_tasks); cudaFree(env->d_hpar); cudaFree(env->d_items); cudaFree(env->d_res);
     if (env->h_flag) cudaFreeHost(env->h_flag);
     for (void* q : env->net_allocs) cudaFree(q);
-    cudaFree(env->d_risk); cudaFree(env->d_backup);
+    cudaFree(env->d_risk); cudaFree(env->d_backup); cudaFree(env->d_exec); cudaFree(env->d_risky);
     for (int i = 0; i <= SM_K_COUNT; ++i) if (env->ev[i]) cudaEventDestroy(env->ev[i]);
     for (int c = 0; c < 8; ++c) {
         if (env->chunk_streams[c]) cudaStreamDestroy(env->chunk_streams[c]);
@@ -597,7 +646,7 @@ extern "C" int smenv_copy_pools(SmEnv* env, double* host_start, double* host_bal
 extern "C" int smenv_fill_pools(SmEnv* env, uint64_t seed, SmStream s) {
     if (!env) return fail(SM_ERR_ARG, "null env");
     cudaStream_t stream = (cudaStream_t)s;
-    int rc = activate(env, stream);
+    DevLock dev_lock_(env); int rc = activate(env, stream);
     if (rc) return rc;
     PoolArgs A{env->d_start_pool, env->start_pool_n, env->d_ball_pool, env->ball_pool_n, (uint32_t)seed, (uint32_t)(seed >> 32)};
     if (env->ball_pool_n) {
@@ -641,6 +690,7 @@ __global__ void set_state_kernel(SmBuffers buf, int n, int nj, const double* q, 
     if (lane == 0) {
         int* ep = buf.episode + 4 * (size_t)env;
         ep[0] = 0;
+        ep[3] = 0;   // no risky action yet in this episode
         buf.ep_return[env] = 0.0;
     }
 }
@@ -649,7 +699,7 @@ extern "C" int smenv_set_state(SmEnv* env, const SmBuffers* buf, const double* q
                                const double* obst, const uint8_t* mask, SmStream s) {
     if (!env || !buf || !q || !v || !a) return fail(SM_ERR_ARG, "smenv_set_state: null argument");
     cudaStream_t stream = (cudaStream_t)s;
-    int rc = activate(env, stream);
+    DevLock dev_lock_(env); int rc = activate(env, stream);
     if (rc) return rc;
     const int n = env->n, nj = env->host_scene.n_joints;
     // host pointers are staged through temporary device buffers
@@ -700,7 +750,7 @@ extern "C" int smenv_set_targets(SmEnv* env, const SmBuffers* buf, const double*
     if (!env->host_scene.use_target_points) return fail(SM_ERR_STATE, "smenv_set_targets: the scene has no target points");
     if (mask && !is_device_ptr(mask)) return fail(SM_ERR_ARG, "smenv_set_targets: mask must be a device pointer");
     cudaStream_t stream = (cudaStream_t)s;
-    int rc = activate(env, stream);
+    DevLock dev_lock_(env); int rc = activate(env, stream);
     if (rc) return rc;
     const int n = env->n;
     double* tmp = nullptr;
@@ -725,7 +775,7 @@ extern "C" int smenv_set_targets(SmEnv* env, const SmBuffers* buf, const double*
 extern "C" int smenv_observation(SmEnv* env, const SmBuffers* buf, SmStream s) {
     if (!env || !buf || !buf->obs) return fail(SM_ERR_ARG, "smenv_observation: null argument");
     cudaStream_t stream = (cudaStream_t)s;
-    int rc = activate(env, stream);
+    DevLock dev_lock_(env); int rc = activate(env, stream);
     if (rc) return rc;
     observation_kernel<<<(env->n * 32 + 255) / 256, 256, 0, stream>>>(*buf, env->n);
     env->launches++;
@@ -738,7 +788,7 @@ extern "C" int smenv_reset(SmEnv* env, const SmBuffers* buf, const uint8_t* mask
     if (!env->pools_filled) return fail(SM_ERR_STATE, "smenv_reset: call smenv_fill_pools first");
     if (mask && !is_device_ptr(mask)) return fail(SM_ERR_ARG, "smenv_reset: mask must be a device pointer");
     cudaStream_t stream = (cudaStream_t)s;
-    int rc = activate(env, stream);
+    DevLock dev_lock_(env); int rc = activate(env, stream);
     if (rc) return rc;
     ResetArgs A{*buf, env->n, mask, env->d_start_pool, env->start_pool_n, env->d_target_pool, env->target_pool_n,
                 (uint32_t)env->seed, (uint32_t)(env->seed >> 32)};
@@ -765,6 +815,44 @@ static SmBuffers buffers_at(const SmBuffers& b, int e0, int nj, int obs_size) {
     if (b.info) o.info = b.info + (size_t)e0 * SM_INFO_STRIDE;
     if (b.target) o.target = b.target + (size_t)e0 * SM_TP_STRIDE;
     return o;
+}
+
+struct MlpSeg { const float* p; int stride, w; };
+static int mlp_launch(SmEnv* env, int which, MlpSeg s0, MlpSeg s1, MlpSeg s2, float* out, int out_stride, int n,
+                      cudaStream_t stream) {
+    if (!env->net_loaded[which]) return fail(SM_ERR_STATE, "network not loaded (smenv_mlp_load)");
+    const MlpNet& net = env->nets[which];
+    if (s0.w + s1.w + s2.w != net.n_in) return fail(SM_ERR_ARG, "network input width does not match the loaded weights");
+    MlpArgs M;
+    M.net = net; M.n = n; M.out = out; M.out_stride = out_stride;
+    const MlpSeg segs[3] = {s0, s1, s2};
+    for (int i = 0; i < 3; ++i) { M.in[i] = segs[i].p; M.in_stride[i] = segs[i].stride; M.in_w[i] = segs[i].w; }
+    const int tiles = (n + MLP_TILE_M - 1) / MLP_TILE_M;
+    const int grid = tiles < env->sms ? tiles : env->sms;   // one CTA per SM (202 KB of shared memory, all of TMEM)
+    mlp_kernel<<<grid, MLP_THREADS, MLP_SM_BYTES, stream>>>(M);
+    env->launches++;
+    CU(cudaGetLastError());
+    return SM_OK;
+}
+
+
+// The risk gate over the envs of `bv` (a view of m envs): risk network on (risk observation, proposed action), backup
+// policy on the risk observation, then the executed actions into `exec` (== bv.actions: in place).
+static int gate_launch(SmEnv* env, const SmBuffers& bv, int m, float threshold, float* risk, uint8_t* risky, float* backup,
+                       float* exec, cudaStream_t stream) {
+    const DevScene& hs = env->host_scene;
+    const int nj = hs.n_joints, ow = hs.obs_size;
+    // the risk observation is the observation without the target-point entries (observations.py:419-431): joint
+    // position / velocity / acceleration, then the obstacle entries
+    const int n_tp = hs.use_target_points ? 3 * hs.obs_add_tp_pos + 3 * hs.obs_add_tp_rel : 0;
+    const MlpSeg kinem{bv.obs, ow, 3 * nj}, rest{bv.obs + 3 * nj + n_tp, ow, ow - 3 * nj - n_tp};
+    int rc;
+    if ((rc = mlp_launch(env, SM_NET_RISK, kinem, rest, MlpSeg{bv.actions, nj, nj}, risk, 1, m, stream))) return rc;
+    if ((rc = mlp_launch(env, SM_NET_BACKUP, kinem, rest, MlpSeg{nullptr, 0, 0}, backup, MLP_MAX_OUT, m, stream))) return rc;
+    risk_gate_kernel<<<(m + 255) / 256, 256, 0, stream>>>(bv.actions, exec, risk, backup, MLP_MAX_OUT, nj, m, threshold, risky);
+    env->launches++;
+    CU(cudaGetLastError());
+    return SM_OK;
 }
 
 // The kernels of one env step over the envs [e0, e0 + m) on `stream`, with the work lists of slot `chunk`: every list
@@ -795,6 +883,24 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
     JA.tasks = tasks;
     JA.hpar = env->d_hpar + (size_t)e0 * 8 * SM_HPAR;
     JA.counters = env->count ? env->d_counters : nullptr;
+    JA.exec = nullptr;
+    const bool gate = env->gate_threshold >= 0.0f;
+    if (gate) {   // actions.py:303-340: rate the proposed action, execute the backup policy's where it is risky
+        if (!buf->obs) return fail(SM_ERR_ARG, "smenv_step: the risk gate needs the observation buffer");
+        if (random_actions) {
+            if (!buf->actions) return fail(SM_ERR_ARG, "smenv_step: the risk gate needs the action buffer");
+            random_actions_kernel<<<(m * env->host_scene.n_joints + 255) / 256, 256, 0, stream>>>(
+                const_cast<float*>(buf->actions), env->host_scene.n_joints, m, e0, step_counter, (uint32_t)env->seed,
+                (uint32_t)(env->seed >> 32));
+            env->launches++;
+            JA.random_actions = 0;
+        }
+        float* exec = env->d_exec + (size_t)e0 * env->host_scene.n_joints;
+        int rc = gate_launch(env, buf_v, m, env->gate_threshold, env->d_risk + e0, env->d_risky + e0,
+                             env->d_backup + (size_t)e0 * MLP_MAX_OUT, exec, stream);
+        if (rc) return rc;
+        JA.exec = exec;
+    }
     static const bool dbg_sync = getenv("SMENV_DEBUG_SYNC") != nullptr;  // locate a faulting kernel: sync after each
 #define SM_MARK(i)                                                                                           \
     do {                                                                                                     \
@@ -843,6 +949,8 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
     A.target_pool = env->pools_filled ? env->d_target_pool : nullptr;
     A.target_pool_n = env->pools_filled ? env->target_pool_n : 0;
     A.counters = env->d_counters;
+    A.risk = gate ? env->d_risk + e0 : nullptr;
+    A.risky = gate ? env->d_risky + e0 : nullptr;
     const int T = SM_WARPS_PER_BLOCK * 32;
     const int blocks = (m + SM_WARPS_PER_BLOCK - 1) / SM_WARPS_PER_BLOCK;
     const int grid_p = blocks < env->grid_broad ? blocks : env->grid_broad;
@@ -930,7 +1038,7 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
     int rc = step_check(env, buf, auto_reset, !random_actions);
     if (rc) return rc;
     cudaStream_t stream = (cudaStream_t)s;
-    rc = activate(env, stream);
+    DevLock dev_lock_(env); rc = activate(env, stream);
     if (rc) return rc;
     const bool tk = env->time_kernels;
     int ranges = tk ? 1 : env->step_ranges;
@@ -980,6 +1088,7 @@ struct HostStepKey {
     SmBuffers buf;
     const void* h[4];
     int auto_reset, chunks, count, pools;
+    float gate;
 };
 
 static int host_step_enqueue(SmEnv* env, const SmBuffers* buf, const float* h_actions, float* h_obs, float* h_reward,
@@ -1016,7 +1125,7 @@ extern "C" int smenv_step_host(SmEnv* env, const SmBuffers* buf, const float* h_
     if (chunks > SM_MAX_CHUNKS) chunks = SM_MAX_CHUNKS;
     if (chunks > env->n) chunks = env->n;
     cudaStream_t stream = (cudaStream_t)s;
-    rc = activate(env, stream);
+    DevLock dev_lock_(env); rc = activate(env, stream);
     if (rc) return rc;
     rc = ensure_chunk_streams(env);
     if (rc) return rc;
@@ -1038,7 +1147,7 @@ extern "C" int smenv_step_host(SmEnv* env, const SmBuffers* buf, const float* h_
     memset(&key, 0, sizeof(key));
     key.buf = *buf;
     key.h[0] = h_actions; key.h[1] = h_obs; key.h[2] = h_reward; key.h[3] = h_done;
-    key.auto_reset = auto_reset; key.chunks = chunks; key.count = env->count ? 1 : 0; key.pools = env->pools_filled ? 1 : 0;
+    key.auto_reset = auto_reset; key.chunks = chunks; key.count = env->count ? 1 : 0; key.pools = env->pools_filled ? 1 : 0; key.gate = env->gate_threshold;
     if (!env->host_graph || memcmp(&key, env->host_graph_key, sizeof(key)) != 0) {
         if (env->host_graph) { cudaGraphExecDestroy(env->host_graph); env->host_graph = nullptr; }
         const unsigned long long launches0 = env->launches;
@@ -1079,7 +1188,7 @@ extern "C" int smenv_step_random(SmEnv* env, const SmBuffers* buf, int auto_rese
 extern "C" int smenv_safe_range(SmEnv* env, const double* kin, double* lo, double* hi, int32_t* code, int n, SmStream s) {
     if (!env || !kin || !lo || !hi || !code) return fail(SM_ERR_ARG, "smenv_safe_range: null argument");
     cudaStream_t stream = (cudaStream_t)s;
-    int rc = activate(env, stream);
+    DevLock dev_lock_(env); int rc = activate(env, stream);
     if (rc) return rc;
     safe_range_kernel<<<(n * 8 + 127) / 128, 128, 0, stream>>>(kin, lo, hi, code, n);
     env->launches++;
@@ -1092,7 +1201,7 @@ extern "C" int smenv_distances(SmEnv* env, const double* kin, const double* obst
     if (!env || !kin || !obst || !d_static || !d_self || !d_moving) return fail(SM_ERR_ARG, "smenv_distances: null argument");
     if (n > env->n) return fail(SM_ERR_ARG, "smenv_distances: n exceeds the env count the buffers were sized for");
     cudaStream_t stream = (cudaStream_t)s;
-    int rc = activate(env, stream);
+    DevLock dev_lock_(env); int rc = activate(env, stream);
     if (rc) return rc;
     // the same kernels as the step: plan the pair queries of the given poses, run them, decode the result records
     CU(cudaMemsetAsync(env->d_worklist, 0, 2 * sizeof(int), stream));
@@ -1138,12 +1247,15 @@ extern "C" int smenv_counters(SmEnv* env, SmCounters* out, int reset) {
 // ------------------------------------------------------------------------------------------------------------------
 extern "C" int smenv_mlp_load(SmEnv* env, int which, int n_tc, const int32_t* dims, int hidden_act, int out_act,
                               const float* weights) {
-    if (!env || !dims || !weights || which < 0 || which > 1) return fail(SM_ERR_ARG, "smenv_mlp_load: bad argument");
+    if (!env || !dims || !weights || which < 0 || which >= SM_NET_COUNT) return fail(SM_ERR_ARG, "smenv_mlp_load: bad argument");
     if (n_tc < 1 || n_tc > MLP_MAX_TC) return fail(SM_ERR_ARG, "smenv_mlp_load: 1..3 hidden layers are supported");
     const int n_in = dims[0], n_out = dims[n_tc + 1];
     const int k_in = n_in <= 16 ? 16 : n_in <= 32 ? 32 : 64;   // a power of two: divisible by every chunk width
     if (n_in < 1 || n_in > 64) return fail(SM_ERR_ARG, "smenv_mlp_load: input width must be in 1..64");
-    if (n_out < 1 || n_out > MLP_MAX_OUT) return fail(SM_ERR_ARG, "smenv_mlp_load: output width must be in 1..8");
+    if (n_out < 1 || n_out > MLP_MAX_OUT) return fail(SM_ERR_ARG, "smenv_mlp_load: output width must be in 1..16");
+    const int out_pad = n_out <= 8 ? 8 : 16;
+    if (dims[n_tc] * out_pad > MLP_WOUT_FLOATS)
+        return fail(SM_ERR_ARG, "smenv_mlp_load: last hidden width x padded output width exceeds 2048");
     for (int l = 0; l < n_tc; ++l) {
         const int N = dims[1 + l];
         if (N % 16 != 0 || N < 16 || (N > 256 && N != 512))
@@ -1153,7 +1265,7 @@ extern "C" int smenv_mlp_load(SmEnv* env, int which, int n_tc, const int32_t* di
     CU(cudaSetDevice(env->device));
     MlpNet net;
     memset(&net, 0, sizeof(net));
-    net.n_tc = n_tc; net.n_in = n_in; net.k_in = k_in; net.hidden_act = hidden_act; net.out_act = out_act; net.n_out = n_out;
+    net.n_tc = n_tc; net.n_in = n_in; net.k_in = k_in; net.hidden_act = hidden_act; net.out_act = out_act; net.n_out = n_out; net.out_pad = out_pad;
     const float* wp = weights;
     int K_real = n_in, Kp = k_in;
     for (int l = 0; l < n_tc; ++l) {
@@ -1181,10 +1293,10 @@ extern "C" int smenv_mlp_load(SmEnv* env, int which, int n_tc, const int32_t* di
         net.w[l] = dw; net.b[l] = db;
         K_real = N; Kp = N;
     }
-    {   // output layer, padded to MLP_MAX_OUT columns
-        std::vector<float> wo((size_t)K_real * MLP_MAX_OUT, 0.0f), bo(MLP_MAX_OUT, 0.0f);
+    {   // output layer, padded to out_pad columns
+        std::vector<float> wo((size_t)K_real * out_pad, 0.0f), bo(out_pad, 0.0f);
         for (int k = 0; k < K_real; ++k)
-            for (int o = 0; o < n_out; ++o) wo[(size_t)k * MLP_MAX_OUT + o] = wp[(size_t)k * n_out + o];
+            for (int o = 0; o < n_out; ++o) wo[(size_t)k * out_pad + o] = wp[(size_t)k * n_out + o];
         wp += (size_t)K_real * n_out;
         for (int o = 0; o < n_out; ++o) bo[o] = wp[o];
         float *dwo = nullptr, *dbo = nullptr;
@@ -1201,34 +1313,19 @@ extern "C" int smenv_mlp_load(SmEnv* env, int which, int n_tc, const int32_t* di
     if (!env->d_risk) {
         CU(cudaMalloc((void**)&env->d_risk, (size_t)env->n * sizeof(float)));
         CU(cudaMalloc((void**)&env->d_backup, (size_t)env->n * MLP_MAX_OUT * sizeof(float)));
+        CU(cudaMalloc((void**)&env->d_exec, (size_t)env->n * SM_MAX_JOINTS * sizeof(float)));
+        CU(cudaMalloc((void**)&env->d_risky, (size_t)env->n));
+        CU(cudaMemset(env->d_risky, 0, (size_t)env->n));
     }
     CU(cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SM_BYTES));
     return SM_OK;
 }
 
-struct MlpSeg { const float* p; int stride, w; };
-static int mlp_launch(SmEnv* env, int which, MlpSeg s0, MlpSeg s1, MlpSeg s2, float* out, int out_stride, int n,
-                      cudaStream_t stream) {
-    if (!env->net_loaded[which]) return fail(SM_ERR_STATE, "network not loaded (smenv_mlp_load)");
-    const MlpNet& net = env->nets[which];
-    if (s0.w + s1.w + s2.w != net.n_in) return fail(SM_ERR_ARG, "network input width does not match the loaded weights");
-    MlpArgs M;
-    M.net = net; M.n = n; M.out = out; M.out_stride = out_stride;
-    const MlpSeg segs[3] = {s0, s1, s2};
-    for (int i = 0; i < 3; ++i) { M.in[i] = segs[i].p; M.in_stride[i] = segs[i].stride; M.in_w[i] = segs[i].w; }
-    const int tiles = (n + MLP_TILE_M - 1) / MLP_TILE_M;
-    const int grid = tiles < env->sms ? tiles : env->sms;   // one CTA per SM (202 KB of shared memory, all of TMEM)
-    mlp_kernel<<<grid, MLP_THREADS, MLP_SM_BYTES, stream>>>(M);
-    env->launches++;
-    CU(cudaGetLastError());
-    return SM_OK;
-}
-
 extern "C" int smenv_mlp_forward(SmEnv* env, int which, const float* in0, int in0_w, const float* in1, int in1_w,
                                  float* out, int out_stride, int n, SmStream s) {
-    if (!env || !in0 || !out || which < 0 || which > 1 || n <= 0) return fail(SM_ERR_ARG, "smenv_mlp_forward: bad argument");
+    if (!env || !in0 || !out || which < 0 || which >= SM_NET_COUNT || n <= 0) return fail(SM_ERR_ARG, "smenv_mlp_forward: bad argument");
     cudaStream_t stream = (cudaStream_t)s;
-    int rc = activate(env, stream);
+    DevLock dev_lock_(env); int rc = activate(env, stream);
     if (rc) return rc;
     return mlp_launch(env, which, MlpSeg{in0, in0_w, in0_w}, MlpSeg{in1, in1 ? in1_w : 0, in1 ? in1_w : 0},
                       MlpSeg{nullptr, 0, 0}, out, out_stride, n, stream);
@@ -1237,33 +1334,37 @@ extern "C" int smenv_mlp_forward(SmEnv* env, int which, const float* in0, int in
 extern "C" int smenv_risk_gate(SmEnv* env, const SmBuffers* buf, float threshold, float* risk_out, uint8_t* risky_out,
                                SmStream s) {
     if (!env || !buf || !buf->actions || !buf->obs) return fail(SM_ERR_ARG, "smenv_risk_gate: null argument");
+    if (!env->net_loaded[0] || !env->net_loaded[1]) return fail(SM_ERR_STATE, "smenv_risk_gate: load both networks first");
     cudaStream_t stream = (cudaStream_t)s;
-    int rc = activate(env, stream);
+    DevLock dev_lock_(env); int rc = activate(env, stream);
     if (rc) return rc;
-    const int nj = env->host_scene.n_joints, ow = env->host_scene.obs_size;
-    // the risk observation is the observation without the target-point entries (observations.py:419-431): joint
-    // position / velocity / acceleration, then the obstacle entries
-    const DevScene& hs = env->host_scene;
-    const int n_tp = hs.use_target_points ? 3 * hs.obs_add_tp_pos + 3 * hs.obs_add_tp_rel : 0;
-    const MlpSeg kinem{buf->obs, ow, 3 * nj}, rest{buf->obs + 3 * nj + n_tp, ow, ow - 3 * nj - n_tp};
-    float* risk = risk_out ? risk_out : env->d_risk;
-    if ((rc = mlp_launch(env, SM_NET_RISK, kinem, rest, MlpSeg{buf->actions, nj, nj}, risk, 1, env->n, stream))) return rc;
-    if ((rc = mlp_launch(env, SM_NET_BACKUP, kinem, rest, MlpSeg{nullptr, 0, 0}, env->d_backup, MLP_MAX_OUT, env->n, stream)))
-        return rc;
-    risk_gate_kernel<<<(env->n + 255) / 256, 256, 0, stream>>>(const_cast<float*>(buf->actions), risk, env->d_backup,
-                                                               MLP_MAX_OUT, nj, env->n, threshold, risky_out);
-    env->launches++;
-    CU(cudaGetLastError());
+    return gate_launch(env, *buf, env->n, threshold, risk_out ? risk_out : env->d_risk, risky_out, env->d_backup,
+                       const_cast<float*>(buf->actions), stream);
+}
+
+extern "C" int smenv_set_risk_gate(SmEnv* env, float threshold) {
+    if (!env) return fail(SM_ERR_ARG, "smenv_set_risk_gate: null env");
+    if (threshold >= 0.0f && (!env->net_loaded[0] || !env->net_loaded[1]))
+        return fail(SM_ERR_STATE, "smenv_set_risk_gate: load the risk network and the backup policy first (smenv_mlp_load)");
+    env->gate_threshold = threshold >= 0.0f ? threshold : -1.0f;
+    return SM_OK;
+}
+
+extern "C" int smenv_set_seed(SmEnv* env, uint64_t seed) {
+    if (!env) return fail(SM_ERR_ARG, "smenv_set_seed: null env");
+    env->seed = seed;
+    env->step_counter = 0;
+    if (env->host_graph) { cudaGraphExecDestroy(env->host_graph); env->host_graph = nullptr; }   // the key is baked in
     return SM_OK;
 }
 
 extern "C" int smenv_random_actions(SmEnv* env, const SmBuffers* buf, SmStream s) {
     if (!env || !buf || !buf->actions) return fail(SM_ERR_ARG, "smenv_random_actions: null argument");
     cudaStream_t stream = (cudaStream_t)s;
-    int rc = activate(env, stream);
+    DevLock dev_lock_(env); int rc = activate(env, stream);
     if (rc) return rc;
     const int nj = env->host_scene.n_joints;
-    random_actions_kernel<<<(env->n * nj + 255) / 256, 256, 0, stream>>>(const_cast<float*>(buf->actions), nj, env->n,
+    random_actions_kernel<<<(env->n * nj + 255) / 256, 256, 0, stream>>>(const_cast<float*>(buf->actions), nj, env->n, 0,
                                                                          env->step_counter, (uint32_t)env->seed,
                                                                          (uint32_t)(env->seed >> 32));
     env->launches++;
@@ -1299,14 +1400,13 @@ extern "C" int smenv_launch_count(SmEnv* env, unsigned long long* out) {
 extern "C" int smenv_debug_gjk(SmEnv* env, const double* kin_host, const double* obst_host, int ia, int ib, float upper,
                                float* trace_host /* 32 x 8 */, float* result_host /* 4 + 12 * 9 */) {
     if (!env || !kin_host || !obst_host || !trace_host || !result_host) return fail(SM_ERR_ARG, "null argument");
-    int rc = activate(env, 0);
+    DevLock dev_lock_(env); int rc = activate(env, 0);
     if (rc) return rc;
     double *dk, *dob; float *dt, *dr;
     CU(cudaMalloc((void**)&dk, 32 * 8)); CU(cudaMalloc((void**)&dob, 16 * 8));
     CU(cudaMalloc((void**)&dt, 256 * 4)); CU(cudaMalloc((void**)&dr, 128 * 4));
     CU(cudaMemcpy(dk, kin_host, 32 * 8, cudaMemcpyHostToDevice)); CU(cudaMemcpy(dob, obst_host, 16 * 8, cudaMemcpyHostToDevice));
     CU(cudaMemset(dt, 0, 256 * 4)); CU(cudaMemset(dr, 0, 128 * 4));
-    CU(cudaFuncSetAttribute(debug_gjk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
     debug_gjk_kernel<<<1, 32, env->smem_bytes, 0>>>(dk, dob, ia, ib, upper, dt, dr);
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(trace_host, dt, 256 * 4, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(result_host, dr, 128 * 4, cudaMemcpyDeviceToHost));

@@ -89,7 +89,7 @@ struct DevScene {
     double static_cap, moving_query, collision_dist;
     double w_self, w_static, w_moving, d_self, d_static, d_moving, w_low_acc, thr_low_acc, w_low_vel, thr_low_vel;
     int punish_action, terminate_self, terminate_static, terminate_moving;
-    double action_thresh, action_max_punishment, termination_bonus, early_termination_punishment;
+    double action_thresh, action_max_punishment, termination_bonus, early_termination_punishment, reward_scale;
     int episode_steps, obs_size;
     // sampling
     double start_box_min[3], start_box_max[3];

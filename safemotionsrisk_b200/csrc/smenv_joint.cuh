@@ -37,8 +37,15 @@ struct JointArgs {
     double* hpar;    // [8 n][SM_HPAR] hand-over records of the deferred instances
     int* heavy;      // [0] = number of (env, joint) instances whose position bound needs the iterative solve,
                      // [1..] = env * 8 + joint (filled by joint_kernel, consumed by joint_heavy_kernel)
+    const float* exec;  // [n][n_joints] actions to execute when the risk gate is on (the backup policy's where the
+                        // proposed action was rated risky), else NULL: buf.actions are executed.  The action punishment
+                        // always rates the proposed action (safe_motions_base.py:1066, actions.py:328-331)
 };
 
+// the action the motors execute: the gated one if the risk gate is on
+__device__ __forceinline__ float joint_exec_action(const JointArgs& A, int env, int j, float proposed) {
+    return A.exec ? A.exec[(size_t)env * c_sc.n_joints + j] : proposed;
+}
 __device__ __forceinline__ float joint_action(const JointArgs& A, int env, int j) {
     if (A.random_actions) {  // get_random_action (safe_motions_base.py:1327-1328)
         uint4 r = philox((uint32_t)(env + A.env_base), A.step_counter, (uint32_t)j, 0xAC71u, A.k0, A.k1);
@@ -92,7 +99,7 @@ __global__ void __launch_bounds__(256) joint_kernel(JointArgs A) {
         uf = joint_action(A, env, j);
         double lo, hi;
         safe_range_light(j, q, v, a, lo, hi, code, defer);
-        if (!defer) jerk_rel = joint_advance(kin, scr, j, q, v, a, qa, lo, hi, uf);
+        if (!defer) jerk_rel = joint_advance(kin, scr, j, q, v, a, qa, lo, hi, joint_exec_action(A, env, j, uf));
         else code = 0;  // reported by joint_heavy_kernel
     } else if (valid) {
         for (int k = 0; k < c_sc.substeps; ++k) scr[k * SM_MAX_JOINTS + j] = 0.0f;
@@ -325,7 +332,7 @@ __global__ void __launch_bounds__(SM_HEAVY_THREADS) joint_final_kernel(JointArgs
         double lo = hp[0], hi = hp[1];
         int code = (int)hp[2];
         if (c_sc.limit_position) clamp_range(lo, hi, -hp[6], hp[5], CODE_POS_HI, CODE_POS_LO, code);
-        const float uf = joint_action(A, env, j);
+        const float uf = joint_exec_action(A, env, j, joint_action(A, env, j));
         const float jerk_rel = joint_advance(kin, scr, j, q, v, a, qa, lo, hi, uf);
         // non-negative floats order like their bit patterns
         atomicMax(reinterpret_cast<int*>(scr + SM_MISC_OFF + SM_MISC_JERK), __float_as_int(jerk_rel));

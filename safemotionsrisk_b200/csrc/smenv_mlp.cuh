@@ -25,7 +25,8 @@
 #include "smenv_device.cuh"
 
 #define MLP_MAX_TC 3
-#define MLP_MAX_OUT 8
+#define MLP_MAX_OUT 16 /* outputs of the CUDA-core output layer; stored padded to 8 or 16 columns (MlpNet.out_pad) */
+#define MLP_WOUT_FLOATS 2048 /* shared-memory floats of the output layer: last hidden width x out_pad */
 #define MLP_TILE_M 128
 #define MLP_THREADS 512 /* four warps per TMEM lane quarter: each handles a quarter of the accumulator columns */
 #define MLP_PARTS (MLP_THREADS / MLP_TILE_M)
@@ -48,10 +49,11 @@ struct MlpNet {
     int dims[MLP_MAX_TC];     // widths of the tensor-core layers (multiples of 16; > 256 only as 512)
     int hidden_act, out_act;
     int n_out;                // outputs of the final CUDA-core layer (<= MLP_MAX_OUT)
+    int out_pad;              // 8 or 16: column stride of w_out / b_out
     const __half* w[MLP_MAX_TC];  // packed K chunks, canonical layout
     const float* b[MLP_MAX_TC];
-    const float* w_out;       // [dims[n_tc-1]][MLP_MAX_OUT]
-    const float* b_out;       // [MLP_MAX_OUT]
+    const float* w_out;       // [dims[n_tc-1]][out_pad]
+    const float* b_out;       // [out_pad]
 };
 
 struct MlpArgs {
@@ -137,10 +139,9 @@ __device__ __forceinline__ float mlp_hidden_act(float x, int act) {
 #define MLP_SM_ACT 0                                       /* 128 x 512 fp16 */
 #define MLP_SM_W (MLP_TILE_M * MLP_MAX_WIDTH * 2)         /* two weight chunks: <= 512 x 32 or 256 x 64 fp16 each */
 #define MLP_SM_IN (MLP_SM_W + 2 * MLP_W_BUF_BYTES)         /* 128 x 64 fp16 */
-#define MLP_SM_WOUT (MLP_SM_IN + MLP_TILE_M * 64 * 2)      /* MLP_MAX_LAST x MLP_MAX_OUT floats */
-#define MLP_SM_BIAS (MLP_SM_WOUT + MLP_MAX_LAST * MLP_MAX_OUT * 4)
-#define MLP_SM_PART (MLP_SM_BIAS + MLP_MAX_TC * MLP_MAX_WIDTH * 4)   /* 128 x MLP_MAX_OUT partial outputs */
-#define MLP_SM_BAR (MLP_SM_PART + MLP_TILE_M * MLP_MAX_OUT * 4)
+#define MLP_SM_WOUT (MLP_SM_IN + MLP_TILE_M * 64 * 2)      /* last hidden width x out_pad floats (<= MLP_WOUT_FLOATS) */
+#define MLP_SM_BIAS (MLP_SM_WOUT + MLP_WOUT_FLOATS * 4)
+#define MLP_SM_BAR (MLP_SM_BIAS + MLP_MAX_TC * MLP_MAX_WIDTH * 4)
 #define MLP_SM_BYTES (MLP_SM_BAR + 64)
 
 __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(MlpArgs A) {
@@ -150,7 +151,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(MlpArgs A) {
     unsigned char* a_in = mlp_smem + MLP_SM_IN;
     float* w_out = reinterpret_cast<float*>(mlp_smem + MLP_SM_WOUT);
     float* bias = reinterpret_cast<float*>(mlp_smem + MLP_SM_BIAS);
-    float* part = reinterpret_cast<float*>(mlp_smem + MLP_SM_PART);
+    // partial outputs of the column quarters of a row: [MLP_PARTS][128][MLP_MAX_OUT] floats in the activation buffer,
+    // which is free once the MMAs of the last tensor-core layer are done
+    float* part = reinterpret_cast<float*>(mlp_smem + MLP_SM_ACT);
     uint64_t* bar = reinterpret_cast<uint64_t*>(mlp_smem + MLP_SM_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mlp_smem + MLP_SM_BAR + 48);
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -174,7 +177,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(MlpArgs A) {
     }
     for (int l = 0; l < net.n_tc; ++l)
         for (int i = tid; i < net.dims[l]; i += MLP_THREADS) bias[l * MLP_MAX_WIDTH + i] = __ldg(net.b[l] + i);
-    for (int i = tid; i < n_last * MLP_MAX_OUT; i += MLP_THREADS) w_out[i] = __ldg(net.w_out + i);
+    const int out_pad = net.out_pad;
+    for (int i = tid; i < n_last * out_pad; i += MLP_THREADS) w_out[i] = __ldg(net.w_out + i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -295,16 +299,24 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(MlpArgs A) {
                         }
                     } else if (n_out == 1) {   // the risk network: one output column
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) acc_out[0] = fmaf(r[j], w_out[(c + j) * MLP_MAX_OUT], acc_out[0]);
+                        for (int j = 0; j < 16; ++j) acc_out[0] = fmaf(r[j], w_out[(c + j) * out_pad], acc_out[0]);
                     } else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const float4 wa = *reinterpret_cast<const float4*>(w_out + (c + j) * MLP_MAX_OUT);
-                            const float4 wb = *reinterpret_cast<const float4*>(w_out + (c + j) * MLP_MAX_OUT + 4);
+                            const float4 wa = *reinterpret_cast<const float4*>(w_out + (c + j) * out_pad);
+                            const float4 wb = *reinterpret_cast<const float4*>(w_out + (c + j) * out_pad + 4);
                             acc_out[0] = fmaf(r[j], wa.x, acc_out[0]); acc_out[1] = fmaf(r[j], wa.y, acc_out[1]);
                             acc_out[2] = fmaf(r[j], wa.z, acc_out[2]); acc_out[3] = fmaf(r[j], wa.w, acc_out[3]);
                             acc_out[4] = fmaf(r[j], wb.x, acc_out[4]); acc_out[5] = fmaf(r[j], wb.y, acc_out[5]);
                             acc_out[6] = fmaf(r[j], wb.z, acc_out[6]); acc_out[7] = fmaf(r[j], wb.w, acc_out[7]);
+                            if (out_pad == 16) {   // stochastic policies: means and log-std outputs (16 columns)
+                                const float4 wc = *reinterpret_cast<const float4*>(w_out + (c + j) * 16 + 8);
+                                const float4 wd = *reinterpret_cast<const float4*>(w_out + (c + j) * 16 + 12);
+                                acc_out[8] = fmaf(r[j], wc.x, acc_out[8]); acc_out[9] = fmaf(r[j], wc.y, acc_out[9]);
+                                acc_out[10] = fmaf(r[j], wc.z, acc_out[10]); acc_out[11] = fmaf(r[j], wc.w, acc_out[11]);
+                                acc_out[12] = fmaf(r[j], wd.x, acc_out[12]); acc_out[13] = fmaf(r[j], wd.y, acc_out[13]);
+                                acc_out[14] = fmaf(r[j], wd.z, acc_out[14]); acc_out[15] = fmaf(r[j], wd.w, acc_out[15]);
+                            }
                         }
                     }
                 };
@@ -327,40 +339,47 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(MlpArgs A) {
             a_src = smem_u32(a_act);
             K = N;
         }
-        // the column quarters of a row meet in shared memory
-        if (half == 0)
-            for (int o = 0; o < MLP_MAX_OUT; ++o) part[rtid * MLP_MAX_OUT + o] = acc_out[o];
-        __syncthreads();
-        if (half != 0)
-            for (int o = 0; o < net.n_out; ++o) atomicAdd(&part[rtid * MLP_MAX_OUT + o], acc_out[o]);
+        // the column quarters of a row meet in shared memory and are added in a fixed order (bit-reproducible results;
+        // the MMAs that read the activation buffer are done, the next tile writes it only after two more barriers)
+#pragma unroll
+        for (int o = 0; o < MLP_MAX_OUT; ++o) part[(half * MLP_TILE_M + rtid) * MLP_MAX_OUT + o] = acc_out[o];
         __syncthreads();
         if (valid && half == 0) {
             for (int o = 0; o < net.n_out; ++o) {
-                const float x = part[rtid * MLP_MAX_OUT + o] + __ldg(net.b_out + o);
+                float x = part[rtid * MLP_MAX_OUT + o];
+#pragma unroll
+                for (int q = 1; q < MLP_PARTS; ++q) x += part[(q * MLP_TILE_M + rtid) * MLP_MAX_OUT + o];
+                x += __ldg(net.b_out + o);
                 A.out[(size_t)row * A.out_stride + o] = net.out_act == MLP_OUT_SIGMOID ? 1.0f / (1.0f + __expf(-x)) : tanhf(x);
             }
         }
+        __syncthreads();   // the partial sums are read before the next tile's first layer overwrites the buffer
     }
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" :: "r"(tmem) : "memory");
 }
 
-// risky actions are replaced by the backup policy's (actions.py:328-337); risk >= threshold (safe_motions_base.py:1601)
-__global__ void risk_gate_kernel(float* actions, const float* risk, const float* backup, int backup_stride, int nj, int n,
-                                 float threshold, uint8_t* risky) {
+// risky actions are replaced by the backup policy's (actions.py:328-337); risk >= threshold (safe_motions_base.py:1601).
+// exec == actions: in place (the stand-alone gate); otherwise the executed actions go to their own buffer and `actions`
+// keeps what the policy proposed (the reward's action punishment rates the proposal, safe_motions_base.py:1066).
+__global__ void risk_gate_kernel(const float* actions, float* exec, const float* risk, const float* backup, int backup_stride,
+                                 int nj, int n, float threshold, uint8_t* risky) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= n) return;
     const bool r = risk[env] >= threshold;
     if (risky) risky[env] = r ? 1 : 0;
-    if (r)
-        for (int j = 0; j < nj; ++j) actions[(size_t)env * nj + j] = backup[(size_t)env * backup_stride + j];
+    for (int j = 0; j < nj; ++j) {
+        const float u = r ? backup[(size_t)env * backup_stride + j] : actions[(size_t)env * nj + j];
+        if (r || exec != actions) exec[(size_t)env * nj + j] = u;
+    }
 }
 
 // get_random_action (safe_motions_base.py:1327-1328) materialised, for the gate in front of smenv_step_random
-__global__ void random_actions_kernel(float* actions, int nj, int n, uint32_t step_counter, uint32_t k0, uint32_t k1) {
+__global__ void random_actions_kernel(float* actions, int nj, int n, int env_base, uint32_t step_counter, uint32_t k0,
+                                      uint32_t k1) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int env = t / nj, j = t % nj;
     if (env >= n) return;
-    uint4 r = philox((uint32_t)env, step_counter, (uint32_t)j, 0xAC71u, k0, k1);
+    uint4 r = philox((uint32_t)(env + env_base), step_counter, (uint32_t)j, 0xAC71u, k0, k1);
     actions[t] = 2.0f * u01f(r.x) - 1.0f;
 }

@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(256) reset_kernel(ResetArgs A) {
     A.buf.kin[(size_t)env * SM_KIN_STRIDE + lane] = e[lane];
     if (lane < SM_OBST_STRIDE) A.buf.obst[(size_t)env * SM_OBST_STRIDE + lane] = e[SM_KIN_STRIDE + lane];
     if (lane == 0) {
-        *reinterpret_cast<int4*>(A.buf.episode + 4 * (size_t)env) = make_int4(0, ep.y + 1, ep.z, ep.w);
+        *reinterpret_cast<int4*>(A.buf.episode + 4 * (size_t)env) = make_int4(0, ep.y + 1, ep.z, 0);
         A.buf.ep_return[env] = 0.0;
         if (A.buf.done) A.buf.done[env] = 0;
     }

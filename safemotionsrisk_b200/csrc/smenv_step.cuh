@@ -32,6 +32,8 @@ struct StepArgs {
     const double* target_pool;     // [target_pool_n][4] target points sampled on the device (reaching task)
     int target_pool_n;
     unsigned long long* counters;  // device SmCounters, or NULL
+    const float* risk;             // [n] risk of the proposed action, or NULL when the gate is off
+    const uint8_t* risky;          // [n] 1 where the gate replaced the action
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
         const double* kin = A.buf.kin + (size_t)env * SM_KIN_STRIDE;
         const float* scr = A.scratch + (size_t)env * SM_SCRATCH_FLOATS + SM_MISC_OFF;
         double* ob = s_ob[tid >> 3];
-        static_assert(SM_OBST_STRIDE == 16 && SM_KIN_STRIDE == 32 && SM_INFO_STRIDE == 16, "record sizes of the 8-lane layout");
+        static_assert(SM_OBST_STRIDE == 16 && SM_KIN_STRIDE == 32 && SM_INFO_STRIDE == 32, "record sizes of the 8-lane layout");
         ob[sl] = A.buf.obst[(size_t)env * SM_OBST_STRIDE + sl];
         ob[sl + 8] = A.buf.obst[(size_t)env * SM_OBST_STRIDE + sl + 8];
         const int4 ep = *reinterpret_cast<const int4*>(A.buf.episode + 4 * (size_t)env);
@@ -165,7 +167,13 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
         else if (c_sc.terminate_static && c_static) { done = 1; reason = SM_TERM_STATIC_COLLISION; }
         else if (c_sc.terminate_moving && c_moving) { done = 1; reason = SM_TERM_MOVING_COLLISION; }
         else if (finished) { done = 1; reason = SM_TERM_TRAJECTORY_LENGTH; }
+        const double reward_raw = reward;
+        reward *= c_sc.reward_scale;   // normalize_reward_to_frequency (rewards.py:172-176)
         const double ep_return = A.buf.ep_return[env] + reward;
+        // risk gate bookkeeping (actions.py:335-340): ep.w = 1 + first risky step of the episode (0 = none so far)
+        const int risky_now = A.risky ? (int)A.risky[env] : 0;
+        int first_risky = ep.w;
+        if (risky_now && first_risky == 0) first_risky = ep_len;   // episode_length - 1 of the reference, plus one
         __syncwarp();   // every lane has read the target-point record and the running return before lane 0 updates them
 
         // ---------------- outputs of the finished step
@@ -175,10 +183,14 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
             A.buf.term_reason[env] = reason;
         }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < 4; ++h) {
             const int slot = sl + 8 * h;
             float val = 0.0f;
             switch (slot) {
+                case SM_INFO_RISKY_ACTION: val = (float)risky_now; break;
+                case SM_INFO_RISK: val = A.risk ? A.risk[env] : 0.0f; break;
+                case SM_INFO_FIRST_RISKY_STEP: val = (float)(first_risky - 1); break;
+                case SM_INFO_REWARD_RAW: val = (float)reward_raw; break;
                 case SM_INFO_D_STATIC: val = (float)ds; break;
                 case SM_INFO_D_SELF: val = (float)dse; break;
                 case SM_INFO_D_MOVING: val = (float)dm; break;
@@ -241,6 +253,7 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
             ep_len_new = 0;
             resets++;
             ret_new = 0.0;
+            first_risky = 0;
         }
         __syncwarp();
         const bool was_reset = kin_obs != kin;
@@ -275,7 +288,7 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
             A.buf.obst[(size_t)env * SM_OBST_STRIDE + sl] = ob_new[0];
             A.buf.obst[(size_t)env * SM_OBST_STRIDE + sl + 8] = ob_new[1];
             if (sl == 0) {
-                *reinterpret_cast<int4*>(A.buf.episode + 4 * (size_t)env) = make_int4(ep_len_new, resets, ball_draws, ep.w);
+                *reinterpret_cast<int4*>(A.buf.episode + 4 * (size_t)env) = make_int4(ep_len_new, resets, ball_draws, first_risky);
                 A.buf.ep_return[env] = ret_new;
             }
         }

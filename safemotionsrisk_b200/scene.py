@@ -388,6 +388,7 @@ class Scene:
         sc.termination_bonus = cfg.collision_avoidance_episode_termination_bonus
         sc.early_termination_punishment = cfg.collision_avoidance_episode_early_termination_punishment
         sc.episode_steps = int(round(cfg.trajectory_duration / ts))   # trajectory_manager.py:87, :187-192
+        sc.reward_scale = ts / 0.1 if cfg.normalize_reward_to_frequency else 1.0   # rewards.py:172-176
         obs_size = 3 * nj                                            # observations.py:54-110
         if cfg.use_moving_objects:
             obs_size += 6

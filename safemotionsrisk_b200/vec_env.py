@@ -109,8 +109,18 @@ class SafeMotionsVecEnv:
         self.episode_counter = 0
         self.pid = os.getpid()
         self._pools_filled = False
+        self._networks = False
+        self._gate_threshold = None
+        self._auto_reset_done = None   # envs the last step re-initialised on the device (see reset_at)
         if fill_pools:
             self.fill_pools(self._seed)
+        # risk gate as the reference wires it (safe_motions_base.py:527-579, actions.py:303-340): risk_config_dir names
+        # the risk network (its backup policy comes with it), risk_threshold switches the gate on inside step()
+        if self.config.risk_config_dir is not None:
+            self.load_networks(self._resolve_risk_config_dir(self.config.risk_config_dir))
+            self.set_risk_gate(self.config.risk_threshold)
+            if self.config.risk_check_initial_backup_trajectory and not fill_pools:
+                raise ValueError("risk_check_initial_backup_trajectory needs the start pools (fill_pools=True)")
 
     # ------------------------------------------------------------------ reference helper surface
     @property
@@ -135,11 +145,36 @@ class SafeMotionsVecEnv:
         return self.scene.obs_size
 
     def set_seed(self, seed=None):
-        """safe_motions_base.py:1704-1710: re-seeds the sampling streams (pools are re-drawn)."""
+        """safe_motions_base.py:1704-1710: re-seeds every sampling stream: the library's Philox key (pool picks of
+        resets / balls / target points, random actions), the per-env draw counters and the pools, so that the env
+        continues exactly like one constructed with this seed."""
         if seed is not None:
             self._seed = int(seed)
+            cabi.check(self._lib.smenv_set_seed(self._handle, self._seed), "smenv_set_seed")
+            self.episode.zero_()
+            if self.target is not None:
+                self.target[:, abi.TP_DRAWS] = 0.0
             self.fill_pools(self._seed)
         return [seed]
+
+    def _resolve_risk_config_dir(self, path):
+        """risk_config_dir of the reference (a Keras SavedModel directory under trained_networks/risk_networks/
+        state_action/<scene>, README.md:223-235) -> the packaged export of that scene's networks, or an .npz path."""
+        if str(path).endswith(".npz") and os.path.isfile(path):
+            return path
+        name = os.path.basename(os.path.normpath(str(path)))
+        packaged = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets", "networks_{}.npz".format(name))
+        if name in ("space", "ball", "human") and os.path.isfile(packaged):
+            return packaged
+        raise ValueError("risk_config_dir {!r}: expected .../state_action/<space|ball|human> (the networks exported by "
+                         "tools/export_networks.py) or the path of an exported .npz".format(path))
+
+    def set_risk_gate(self, threshold):
+        """Switches the risk gate inside step() / step_random() / step_host() on (threshold in [0, 1]) or off (None);
+        smenv_set_risk_gate.  The networks must be loaded (load_networks, or risk_config_dir in the env_config)."""
+        thr = -1.0 if threshold is None else float(threshold)
+        cabi.check(self._lib.smenv_set_risk_gate(self._handle, thr), "smenv_set_risk_gate")
+        self._gate_threshold = None if threshold is None else float(threshold)
 
     def close(self):
         if self._handle:
@@ -179,9 +214,46 @@ class SafeMotionsVecEnv:
         cabi.check(self._lib.smenv_reset(self._handle, C.byref(self._buf), C.c_void_p(m.data_ptr()) if m is not None
                                          else None, self._stream()), "smenv_reset")
         self.episode_counter += self.num_envs if m is None else int(m.sum().item())
+        if self.config.risk_check_initial_backup_trajectory and self._networks:
+            self._recheck_initial_states(m)
         if self._squeeze:
             return self.obs[0].cpu().numpy()
         return self.obs
+
+    def initial_backup_trajectory_unsafe(self, steps=None):
+        """risk_check_initial_backup_trajectory (observations.py:155-185): from a copy of the current state the backup
+        policy acts for `steps` steps (default: the episode length of the backup policy's training env, 20); an env is
+        unsafe if its episode ends in that window for a reason other than the trajectory length.  The state is
+        restored.  Returns a bool tensor [N]."""
+        steps = int(steps or self.config.risk_state_initial_backup_trajectory_steps or
+                    self.config.risk_state_backup_trajectory_steps or 20)
+        snap = self.snapshot()
+        auto, gate = self.auto_reset, self._gate_threshold
+        self.auto_reset = False
+        self.set_risk_gate(None)
+        try:
+            self.episode[:, 0] = 0        # switch_to_backup_client: _episode_length = 0 (safe_motions_base.py:1818-1822)
+            unsafe = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
+            for _ in range(steps):
+                self._step_device(self.backup_policy_actions())
+                unsafe |= self.done.bool() & (self.term_reason != self.TERMINATION_TRAJECTORY_LENGTH)
+        finally:
+            self.restore(snap)
+            self.auto_reset = auto
+            self.set_risk_gate(gate)
+        return unsafe
+
+    def _recheck_initial_states(self, mask, max_rounds=8):
+        """Re-resets the (masked) envs whose start state has no valid backup trajectory (observations.py:181-183)."""
+        for _ in range(max_rounds):
+            unsafe = self.initial_backup_trajectory_unsafe()
+            if mask is not None:
+                unsafe &= mask.bool()
+            if not bool(unsafe.any().item()):
+                return
+            um = unsafe.to(torch.uint8).contiguous()
+            cabi.check(self._lib.smenv_reset(self._handle, C.byref(self._buf), C.c_void_p(um.data_ptr()),
+                                             self._stream()), "smenv_reset")
 
     def set_state(self, q, v, a, obst=None, mask=None, first_target=None):
         """Injects start states (parity protocol, SURVEY 8c): q, v, a [N, n_joints] float64, obst [N, 16] or None;
@@ -204,21 +276,46 @@ class SafeMotionsVecEnv:
         self.done.zero_()
         return self.obs
 
-    def step(self, actions):
-        """One env step for all envs.  actions: [N, n_joints] in [-1, 1] (torch on the env's device, or array-like)."""
+    def _step_device(self, actions):
         if torch.is_tensor(actions) and actions.device == self.device:
             self.actions.copy_(actions.reshape(self.num_envs, -1), non_blocking=True)
         else:
             arr = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, -1)
             self.actions.copy_(torch.from_numpy(arr), non_blocking=False)
-        cabi.check(self._lib.smenv_step(self._handle, C.byref(self._buf), int(self.auto_reset), self._stream()),
-                   "smenv_step")
+        cabi.check(self._lib.smenv_step(self._handle, C.byref(self._buf), int(self._device_auto_reset()),
+                                        self._stream()), "smenv_step")
+
+    def _device_auto_reset(self):
+        # with risk_check_initial_backup_trajectory every new start state has to pass the backup-trajectory check, so
+        # finished envs are re-initialised by reset(mask) after the step instead of inside the finish kernel
+        return self.auto_reset and not (self.config.risk_check_initial_backup_trajectory and self._networks)
+
+    def _after_step(self):
+        self._auto_reset_done = self.done if self._device_auto_reset() else None
+        if self.auto_reset and not self._device_auto_reset():
+            done = self.done.clone()
+            if bool(done.any().item()):
+                out = (self.reward.clone(), self.term_reason.clone(), self.info.clone())
+                self.reset(done)
+                self.done.copy_(done)
+                self.reward.copy_(out[0]); self.term_reason.copy_(out[1]); self.info.copy_(out[2])
+                self._auto_reset_done = done
+
+    def step(self, actions):
+        """One env step for all envs.  actions: [N, n_joints] in [-1, 1] (torch on the env's device, or array-like).
+        With ``random_agent`` in the env_config the actions are ignored and drawn on the device
+        (safe_motions_base.py:1047-1048); with the risk gate on, risky actions are replaced (actions.py:303-340)."""
+        if self.config.random_agent:
+            return self.step_random()
+        self._step_device(actions)
+        self._after_step()
         return self._outputs()
 
     def step_random(self):
         """Step with device-generated U(-1, 1) actions (``random_agent``, safe_motions_base.py:1047-1048)."""
-        cabi.check(self._lib.smenv_step_random(self._handle, C.byref(self._buf), int(self.auto_reset),
+        cabi.check(self._lib.smenv_step_random(self._handle, C.byref(self._buf), int(self._device_auto_reset()),
                                                self._stream()), "smenv_step_random")
+        self._after_step()
         return self._outputs()
 
     def set_step_ranges(self, ranges):
@@ -229,24 +326,22 @@ class SafeMotionsVecEnv:
         """Host-buffer API: NumPy actions in, NumPy (obs, reward, done) out through pinned staging buffers.
         `host_actions` is the pinned input buffer itself: a sampler that writes its actions there (and passes it, or
         None) saves the host-side copy.  chunks: env ranges whose copies and kernels overlap (smenv_step_host); the
-        results do not depend on it.  gate_threshold: apply the risk gate (load_networks first) to the actions before
-        the step (whole batch on one stream)."""
+        results do not depend on it.  gate_threshold: run this step with the risk gate at that threshold (default: the
+        env's own gate setting)."""
         if actions_np is not None and actions_np is not self.host_actions:
             self.host_actions[...] = np.asarray(actions_np, dtype=np.float32).reshape(self.num_envs, -1)
-        if gate_threshold is not None:
-            self.actions.copy_(self._h_actions, non_blocking=True)
-            self.risk_gate(gate_threshold)
-            cabi.check(self._lib.smenv_step(self._handle, C.byref(self._buf), int(self.auto_reset), self._stream()),
-                       "smenv_step")
-            self._h_obs.copy_(self.obs, non_blocking=True)
-            self._h_reward.copy_(self.reward, non_blocking=True)
-            self._h_done.copy_(self.done, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
-        else:
+        prev = self._gate_threshold
+        if gate_threshold is not None and gate_threshold != prev:
+            self.set_risk_gate(gate_threshold)
+        try:   # the gate runs inside the env ranges of the host step (same CUDA graph as the ungated step)
             cabi.check(self._lib.smenv_step_host(self._handle, C.byref(self._buf), self._h_actions.data_ptr(),
                                                  self._h_obs.data_ptr(), self._h_reward.data_ptr(),
-                                                 self._h_done.data_ptr(), int(self.auto_reset), int(chunks),
+                                                 self._h_done.data_ptr(), int(self._device_auto_reset()), int(chunks),
                                                  self._stream()), "smenv_step_host")
+        finally:
+            if gate_threshold is not None and gate_threshold != prev:
+                self.set_risk_gate(prev)
+        self._auto_reset_done = self.done if self._device_auto_reset() else None
         return self._h_obs.numpy(), self._h_reward.numpy(), self._h_done.numpy()
 
     def _outputs(self):
@@ -298,6 +393,10 @@ class SafeMotionsVecEnv:
         return list(self.reset().cpu().numpy())
 
     def reset_at(self, index):
+        """RLlib calls this for every env that reported done.  An env that the last step already re-initialised on the
+        device (auto_reset) is not reset a second time: its first observation is returned as it is."""
+        if self._auto_reset_done is not None and bool(self._auto_reset_done[index].item()):
+            return self.obs[index].cpu().numpy()
         mask = np.zeros(self.num_envs, dtype=np.uint8)
         mask[index] = 1
         self.reset(mask)
@@ -373,6 +472,7 @@ class SafeMotionsVecEnv:
         self.risk = torch.zeros(self.num_envs, dtype=torch.float32, device=self.device)
         self.risky = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
         self._networks = True
+        self._network_source = source
 
     def mlp_forward(self, which, in0, in1=None, n_out=1):
         """Parity hook: the loaded network `which` (0 risk, 1 backup policy) on caller-supplied rows."""
@@ -396,19 +496,16 @@ class SafeMotionsVecEnv:
         return self.risk, self.risky
 
     def step_gated(self, actions=None, threshold=None):
-        """One env step with the risk gate in front: actions (or device-generated random actions if None) are
-        filtered by risk_gate, then stepped."""
-        if actions is None:
-            cabi.check(self._lib.smenv_random_actions(self._handle, C.byref(self._buf), self._stream()),
-                       "smenv_random_actions")
-        elif torch.is_tensor(actions) and actions.device == self.device:
-            self.actions.copy_(actions.reshape(self.num_envs, -1), non_blocking=True)
-        else:
-            self.actions.copy_(torch.from_numpy(np.asarray(actions, dtype=np.float32).reshape(self.num_envs, -1)))
-        self.risk_gate(threshold)
-        cabi.check(self._lib.smenv_step(self._handle, C.byref(self._buf), int(self.auto_reset), self._stream()),
-                   "smenv_step")
-        return self._outputs()
+        """One env step with the risk gate at `threshold` (the env's own gate setting is restored afterwards): the
+        proposed actions (device-generated random actions if None) stay in self.actions, the executed ones differ where
+        info[:, risky_action] is 1."""
+        thr = float(self.config.risk_threshold if threshold is None else threshold)
+        prev = self._gate_threshold
+        self.set_risk_gate(thr)
+        try:
+            return self.step_random() if actions is None else self.step(actions)
+        finally:
+            self.set_risk_gate(prev)
 
     # ------------------------------------------------------------------ backup-client look-ahead (risk ground truth)
     _STATE = ("kin", "obst", "episode", "ep_return", "target", "stats", "obs", "reward", "done", "term_reason", "info")
@@ -445,20 +542,27 @@ class SafeMotionsVecEnv:
         snap = self.snapshot()
         auto = self.auto_reset
         self.auto_reset = False
+        gate = self._gate_threshold
+        self.set_risk_gate(None)
         try:
+            # the look-ahead runs on its own episode clock (switch_to_backup_client: _episode_length = 0 and
+            # trajectory_length = backup_steps + 2, safe_motions_base.py:1818-1822): the end of the real episode never
+            # cuts the window short, and only a collision ends an env's look-ahead
+            self.episode[:, 0] = 0
             risky = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
             alive = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
             a = act
             for i in range(1 + int(backup_steps)):
-                self.step(a)
-                done = self.done.bool()
-                risky |= alive & done & (self.term_reason != self.TERMINATION_TRAJECTORY_LENGTH)
-                alive &= ~done
+                self._step_device(a)
+                collided = self.done.bool() & (self.term_reason != self.TERMINATION_TRAJECTORY_LENGTH)
+                risky |= alive & collided
+                alive &= ~collided
                 if i < backup_steps:
                     a = self.backup_policy_actions()
         finally:
             self.restore(snap)
             self.auto_reset = auto
+            self.set_risk_gate(gate)
         return state, act, risky.float()
 
     KERNELS = ("joint_kernel", "joint_heavy_kernel", "contact_plan_kernel", "distance_plan_kernel", "gjk_kernel",

@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+    config.addinivalue_line("markers", "needs_pybullet: needs the reference's pybullet / klimits / gym (skipped without)")
 
 
 @pytest.fixture(scope="session")

@@ -89,3 +89,29 @@ def test_contact_thresholds_are_millimetres(space_scene, ball_scene):
         th = np.array([[s.struct.contact_thresh[o][i] for i in range(s.struct.n_mov_contact)]
                        for o in range(s.struct.n_obstacles)])
         assert (th > 5e-4).all() and (th < 1e-2).all()
+
+
+@pytest.mark.parametrize("key,value", [
+    ("acceleration_after_max_vel_limit_factor", 0.05), ("set_velocity_after_max_pos_to_zero", False),
+    ("punish_adaptation", True), ("punish_end_min_distance", True), ("punish_end_max_torque", True),
+    ("punish_braking_trajectory_min_distance", True), ("punish_braking_trajectory_max_torque", True),
+    ("obstacle_use_computed_actual_values", True), ("check_braking_trajectory_torque_limits", True),
+    ("risk_state_config", 2), ("risk_store_ground_truth", True), ("human_network_use_full_observation", True),
+    ("terminate_on_robot_stop", True), ("max_resampling_attempts", 3), ("action_preprocessing_function", "clip"),
+])
+def test_keys_that_change_unimplemented_behaviour_raise(key, value):
+    """A params.json that sets one of these keys away from the reference default would silently get different rewards
+    or limits: every one of them raises instead."""
+    with pytest.raises(NotImplementedError):
+        EnvConfig(**{key: value})
+    EnvConfig(**{key: EnvConfig()[key]})   # the default value itself is accepted
+
+
+def test_accepted_keys_have_an_effect_or_are_no_ops():
+    assert Scene(space_backup_config(normalize_reward_to_frequency=True, trajectory_time_step=0.05)
+                 ).struct.reward_scale == pytest.approx(0.5)
+    assert Scene(space_backup_config()).struct.reward_scale == 1.0
+    EnvConfig(action_preprocessing_function="tanh")     # computed and discarded by the reference (SURVEY Q1)
+    EnvConfig(no_self_collision=True)                    # a Bullet loading flag of the dynamics, which are not modelled
+    with pytest.raises(ValueError):
+        EnvConfig(risk_config_dir="risk_networks/state_action/space")   # needs risk_threshold

@@ -609,3 +609,186 @@ def test_host_step_in_ranges_equals_the_device_step(scene):
     assert ref.stats[0].item() > 0   # episodes ended and were reset on the way
     for e in list(envs.values()) + [mixed, ref]:
         e.close()
+
+
+# ---------------------------------------------------------------------------------------------- round 2: gate wiring
+def _assets(name):
+    return os.path.join(os.path.dirname(GOLDEN), "..", "safemotionsrisk_b200", "assets", "networks_{}.npz".format(name))
+
+
+def test_gate_inside_step_keeps_the_proposed_action_for_the_reward():
+    """actions.py:303-340 / safe_motions_base.py:1066: the gate replaces the executed action only; the action
+    punishment of the reward still rates what the policy proposed.  Env A steps with the gate switched on inside the
+    step; env B gets the same proposal gated by hand (risk_gate in place) and steps ungated: the joint trajectories are
+    identical, the rewards differ exactly by the punishment of the proposal vs the punishment of the backup action."""
+    n, thr = 2048, 0.065
+    cfg = dict(risk_config_dir="risk_networks/state_action/space", risk_threshold=thr)
+    a_env = make_env("space_task", n, auto_reset=False, cfg=dict(ball_machine_mode=True, **cfg))
+    b_env = make_env("space_task", n, auto_reset=False, cfg=dict(ball_machine_mode=True))
+    b_env.load_networks()
+    assert a_env._gate_threshold == thr and b_env._gate_threshold is None
+    a_env.reset()
+    b_env.restore(a_env.snapshot())
+    rng = np.random.default_rng(2)
+    prop = rng.uniform(-1, 1, (n, 7)).astype(np.float32)
+    prop[: n // 4] *= 0.5          # some proposals without punishment
+    a_env.step(prop)
+    b_env.actions.copy_(torch.from_numpy(prop))
+    _, risky = b_env.risk_gate(thr)
+    gated = b_env.actions.clone()
+    b_env._step_device(gated)
+    torch.cuda.synchronize()
+    risky = risky.cpu().numpy().astype(bool)
+    assert 0 < risky.sum() < n
+    assert np.array_equal(a_env.kin.cpu().numpy(), b_env.kin.cpu().numpy())          # same executed actions
+    assert np.array_equal(a_env.actions.cpu().numpy(), prop)                          # the proposal is kept
+    ia, ib = a_env.info.cpu().numpy(), b_env.info.cpu().numpy()
+    assert np.array_equal(ia[:, I["risky_action"]].astype(bool), risky)
+    assert np.array_equal(ib[:, I["risky_action"]], np.zeros(n, dtype=np.float32))
+    pun = lambda u: np.clip((np.abs(u).max(1) - 0.95) / 0.05, 0, 1) ** 2
+    assert np.allclose(ia[:, I["action_punishment"]], pun(prop), atol=1e-5)
+    assert np.allclose(ib[:, I["action_punishment"]], pun(gated.cpu().numpy()), atol=1e-5)
+    dr = a_env.reward.cpu().numpy() - b_env.reward.cpu().numpy()
+    assert np.allclose(dr, -0.4 * (pun(prop) - pun(gated.cpu().numpy())), atol=1e-4)
+    first = ia[:, I["first_risky_step"]]
+    assert np.array_equal(first >= 0, risky) and (first[risky] == 0).all()
+    # host-buffer step with the gate: same decisions through the chunked graph path
+    a_env.restore(b_env.snapshot())
+    b_snap = b_env.snapshot()
+    prop2 = rng.uniform(-1, 1, (n, 7)).astype(np.float32)
+    a_env.step_host(prop2, chunks=2)
+    b_env.restore(b_snap)
+    b_env.set_risk_gate(thr)
+    b_env.step(prop2)
+    torch.cuda.synchronize()
+    assert np.array_equal(a_env.kin.cpu().numpy(), b_env.kin.cpu().numpy())
+    assert np.array_equal(a_env.info.cpu().numpy()[:, I["risky_action"]], b_env.info.cpu().numpy()[:, I["risky_action"]])
+    a_env.close()
+    b_env.close()
+
+
+def test_set_seed_reproduces_an_env_built_with_that_seed():
+    a = make_env("ball", 512, seed=5, auto_reset=True)
+    b = make_env("ball", 512, seed=9, auto_reset=True)
+    b.reset()
+    for _ in range(3):
+        b.step_random()
+    b.set_seed(5)
+    a.reset()
+    b.reset()
+    for _ in range(25):       # past the first auto-resets and ball replacements
+        a.step_random()
+        b.step_random()
+    torch.cuda.synchronize()
+    assert np.array_equal(a.kin.cpu().numpy(), b.kin.cpu().numpy())
+    assert np.array_equal(a.obst.cpu().numpy(), b.obst.cpu().numpy())
+    a.close()
+    b.close()
+
+
+def test_two_envs_of_different_scenes_alternate_in_one_process():
+    """The scene constants live in one per-device constant-memory block and the opt-in shared-memory limit is per
+    function: a big scene created first must keep working after a small one is created, and alternating steps of two
+    envs must give what each gives alone."""
+    big = make_env("space_bm", 256, seed=1, auto_reset=True)
+    small = make_env("ball", 256, seed=1, auto_reset=True)
+    big_alone = make_env("space_bm", 256, seed=1, auto_reset=True)
+    small_alone = make_env("ball", 256, seed=1, auto_reset=True)
+    for e in (big, small, big_alone, small_alone):
+        e.reset()
+    side = torch.cuda.Stream()
+    for i in range(6):
+        big.step_random()
+        with torch.cuda.stream(side):
+            small.step_random()
+    for i in range(6):
+        big_alone.step_random()
+    for i in range(6):
+        small_alone.step_random()
+    torch.cuda.synchronize()
+    assert np.array_equal(big.kin.cpu().numpy(), big_alone.kin.cpu().numpy())
+    assert np.array_equal(small.kin.cpu().numpy(), small_alone.kin.cpu().numpy())
+    assert np.array_equal(big.reward.cpu().numpy(), big_alone.reward.cpu().numpy())
+    for e in (big, small, big_alone, small_alone):
+        e.close()
+
+
+def test_reset_at_does_not_reset_an_auto_reset_env_twice():
+    env = make_env("ball", 64, auto_reset=True)
+    env.reset()
+    done = None
+    for _ in range(20):
+        obs, rew, done, _ = env.vector_step(np.zeros((64, 7), dtype=np.float32))
+    assert all(done)                                   # 20-step episodes end together
+    resets = env.episode.cpu().numpy()[:, 1].copy()
+    first_obs = env.obs.cpu().numpy().copy()
+    for i in range(64):
+        assert np.array_equal(env.reset_at(i), first_obs[i])
+    assert np.array_equal(env.episode.cpu().numpy()[:, 1], resets)   # no second reset, no second episode counted
+    env.step(np.zeros((64, 7), dtype=np.float32))
+    env.reset_at(3)                                    # not done in the last step: a real reset
+    assert env.episode.cpu().numpy()[3, 1] == resets[3] + 1
+    env.close()
+
+
+def test_risk_ground_truth_window_ignores_the_end_of_the_real_episode():
+    """The look-ahead runs on its own episode clock (safe_motions_base.py:1818-1822): an env three steps before its
+    episode end is labelled like the same state at the start of an episode."""
+    n = 1024
+    env = make_env("space_bm", n, auto_reset=False)
+    env.load_networks()
+    env.reset()
+    for _ in range(4):
+        env.step_random()
+    act = np.random.default_rng(4).uniform(-1, 1, (n, 7)).astype(np.float32)
+    _, _, risk_early = env.risk_ground_truth(act, backup_steps=20)
+    env.episode[:, 0] = 17                              # same state, three steps before the end of the real episode
+    _, _, risk_late = env.risk_ground_truth(act, backup_steps=20)
+    assert int(env.episode[0, 0].item()) == 17          # the state is restored
+    assert torch.equal(risk_early, risk_late)
+    assert 0 < float(risk_early.mean().item()) < 1
+    env.close()
+
+
+def test_initial_backup_trajectory_check_filters_start_states():
+    """risk_check_initial_backup_trajectory (observations.py:155-185): after reset() no env starts from a state in
+    which the backup policy itself collides within its 20 steps."""
+    n = 2048
+    env = make_env("space_bm", n, auto_reset=True,
+                   cfg=dict(risk_config_dir="risk_networks/state_action/space", risk_threshold=0.065,
+                            risk_check_initial_backup_trajectory=True))
+    plain = make_env("space_bm", n, auto_reset=True)
+    plain.load_networks()
+    plain.reset()
+    unsafe_plain = float(plain.initial_backup_trajectory_unsafe().float().mean().item())
+    env.reset()
+    unsafe = float(env.initial_backup_trajectory_unsafe().float().mean().item())
+    assert unsafe == 0.0 and unsafe_plain >= 0.0
+    env.close()
+    plain.close()
+
+
+@pytest.mark.parametrize("name", ["space_bm", "ball_bm"])
+def test_behavioural_pin_shipped_backup_policy_avoids_collisions(name):
+    """The only reference-held artefacts that can pin the restated env are the shipped network weights (SURVEY 8c item
+    5): the backup policy, trained in the real PyBullet env, must keep most 20-step episodes collision free in THIS env,
+    and far more of them than random actions do."""
+    n = 16384
+    rates = {}
+    for mode in ("policy", "random"):
+        env = make_env(name, n, seed=11, auto_reset=True)
+        env.load_networks()
+        env.reset()
+        env.stats.zero_()
+        for _ in range(60):
+            if mode == "policy":
+                env.step(env.backup_policy_actions())
+            else:
+                env.step_random()
+        s = env.episode_statistics().cpu().numpy()
+        rates[mode] = float((s[3 + 3] + s[3 + 4] + s[3 + 5]) / max(s[0], 1))
+        env.close()
+    print(name, "collision-termination rate: backup policy {:.4f}, random actions {:.4f}".format(
+        rates["policy"], rates["random"]))
+    assert rates["policy"] < 0.5 * rates["random"]
+    assert rates["policy"] < 0.25

@@ -157,8 +157,15 @@ def main():
     ref = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     nets = os.path.join(ref, "safemotions", "trained_networks")
     out_dir = os.path.join(ROOT, "safemotionsrisk_b200", "assets")
-    for scene in ("space", "ball"):
+    for scene in ("space", "ball", "human"):
         out = {}
+        if scene == "human":   # the policy that moves the human's arms (ctlp.py:4647-4762): 38 -> 256 -> 128 -> 16
+            hp = read_rllib_policy(os.path.join(nets, "human_network", "checkpoint", "checkpoint"))
+            for name in ("fc_1", "fc_2", "fc_out"):
+                out["human/{}/kernel".format(name)] = hp[name + "/kernel"].astype(np.float32)
+                out["human/{}/bias".format(name)] = hp[name + "/bias"].astype(np.float32)
+            hcfg = json.load(open(os.path.join(nets, "human_network", "params.json")))
+            out["human/log_std_range"] = np.asarray(hcfg["model"]["custom_model_config"]["log_std_range"], np.float32)
         pol = read_rllib_policy(os.path.join(nets, "backup_networks", scene, "checkpoint", "checkpoint"))
         for name in ("fc_1", "fc_2", "fc_out"):
             out["backup/{}/kernel".format(name)] = pol[name + "/kernel"].astype(np.float32)
