@@ -47,6 +47,12 @@ def scene_config(name):
         return space_backup_config(ball_machine_mode=True)
     if name == "ball_bm":
         return ball_backup_config(ball_machine_mode=True)
+    if name == "human":
+        from safemotionsrisk_b200 import human_backup_config
+        return human_backup_config()
+    if name == "human_bm":
+        from safemotionsrisk_b200 import human_backup_config
+        return human_backup_config(ball_machine_mode=True)
     raise SystemExit("unknown scene " + name)
 
 
@@ -55,6 +61,9 @@ WORKLOAD = {"ball": "Ball env (moving ball obstacles) batched random-action roll
             "space": "Space env (planet_mode, obstacle_scene=5) batched random-action rollout",
             "space_bm": "Space env, ball_machine_mode (shipped checkpoints' robot)",
             "ball_bm": "Ball env, ball_machine_mode (shipped checkpoints' robot)",
+            "human": "Human env (human arms moved by the shipped human policy, braking-trajectory check of the nested "
+                     "env) batched random-action rollout, 65,536 envs per B200 (BASELINE.json configs[2])",
+            "human_bm": "Human env, ball_machine_mode (shipped checkpoints' robot)",
             "space_task": "Space reaching task (SafeMotionsEnv with target points, README.md:223)",
             "space_task_bm": "Space reaching task, ball_machine_mode (BASELINE.json configs[3] env)"}
 
@@ -184,6 +193,9 @@ def main():
     ap.add_argument("--risk-gate", action="store_true",
                     help="risk network + backup policy (tensor cores) in front of every step (BASELINE.json configs[3])")
     ap.add_argument("--risk-threshold", type=float, default=None)
+    ap.add_argument("--scenes", default="space,space_bm,ball",
+                    help="further scenes measured (device-timed, shorter) after the main one and reported under 'scenes'")
+    ap.add_argument("--no-scenes", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -197,7 +209,7 @@ def main():
         if rank != 0:
             return 0
         # bounded sample: small shards so that `steps` finish within minutes on the host cores
-        per_thread = 1024 if args.scene.startswith("ball") else 64
+        per_thread = 1024 if args.scene.startswith("ball") else 8 if args.scene.startswith("human") else 64
 
         # each of the K "steps" the driver asks for is one oracle step of the bounded sample; K is capped so that the
         # run ends within minutes
@@ -217,27 +229,70 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from safemotionsrisk_b200.vec_env import SafeMotionsVecEnv
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    cfg = scene_config(args.scene)
+    fma_peaks = measure_fma_peaks(local_rank)
+    main = measure_scene(args.scene, args, dev, rank, world, local_rank, fma_peaks, steps=args.steps,
+                         full=True, with_cpu=(rank == 0 and world == 1 and not args.no_cpu_baseline))
+    # the other scenes of BASELINE.json on the same box, so that the driver's record carries the north-star scene (Space,
+    # also with the robot of the shipped checkpoints) next to the headline workload: shorter runs, device-timed only
+    extra = {}
+    if not args.no_scenes:
+        for name in [x for x in args.scenes.split(",") if x and x != args.scene]:
+            r = measure_scene(name, args, dev, rank, world, local_rank, fma_peaks, steps=min(args.steps, 100),
+                              full=False, with_cpu=False)
+            if rank == 0:
+                extra[name] = {k: r[k] for k in ("value", "ms_per_step", "workload", "gpu_launches", "roofline")}
+                extra[name]["e2e"] = r["e2e"]
+    if rank == 0:
+        out = {"impl": "b200", "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world,
+               "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": main["ms_per_step"],
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f64 joint space / f32 geometry", "data": "synthetic", "config": main["config"],
+               "clocks": main["clocks"], "e2e": main["e2e"], "gpu_launches": main["gpu_launches"],
+               "roofline": main["roofline"], "cpu_baseline": main["cpu_baseline"], "episode_stats": main["episode_stats"],
+               "scenes": extra}
+        _emit(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def measure_fma_peaks(device_index):
+    """FP32 / FP64 FMA throughput of this GPU measured by the library's micro-benchmark (TFLOP/s)."""
+    import ctypes as C
+    from safemotionsrisk_b200 import cabi
+    f32, f64 = C.c_double(), C.c_double()
+    cabi.check(cabi.load().smenv_measure_fma_peaks(int(device_index), C.byref(f32), C.byref(f64)), "smenv_measure_fma_peaks")
+    return {"fp32": f32.value, "fp64": f64.value}
+
+
+def measure_scene(scene_name, args, dev, rank, world, local_rank, fma_peaks, steps, full, with_cpu):
+    """One workload on this rank's GPU: K device-timed steps (max over ranks), roofline of the dominant kernel, and (full)
+    the end-to-end number through the host-buffer API."""
+    import torch
+    import torch.distributed as dist
+    from safemotionsrisk_b200.vec_env import SafeMotionsVecEnv
+    threads = os.cpu_count() or 1
+    config = {"workload": WORKLOAD[scene_name], "scene": scene_name, "envs_per_gpu": args.envs,
+              "actions": "device Philox U(-1,1)", "auto_reset": True, "parallelism": "env-shards x{}".format(world),
+              "l2": "flushed between timed steps (256 MiB write)"}
+    cfg = scene_config(scene_name)
     env = SafeMotionsVecEnv(num_envs=args.envs, device=dev, seed=1000 * rank, auto_reset=True, config=cfg)
     gate_thr = None
-    if args.risk_gate:
+    if args.risk_gate and full:
         env.load_networks()
         gate_thr = args.risk_threshold if args.risk_threshold is not None else \
-            (0.105 if args.scene.startswith("ball") else 0.065)   # README.md:223-229
-        config["risk_gate"] = {"threshold": gate_thr, "networks": "risk 30/34-512-256-128-1 selu + backup policy "
-                               "23/27-256-128-14 swish/tanh, fp16 x fp16 -> fp32 on tcgen05"}
+            (0.105 if scene_name.startswith("ball") else 0.06 if scene_name.startswith("human") else 0.065)  # README.md:223-235
+        env.set_risk_gate(gate_thr)
+        config["risk_gate"] = {"threshold": gate_thr, "networks": "risk obs+7-512-256-128-1 selu + backup policy "
+                               "obs-256-128-14 swish/tanh, fp16 x fp16 -> fp32 on tcgen05, inside the step"}
         config["workload"] += " + state-action risk network and backup policy in the step loop"
 
     def one_step():
-        if gate_thr is None:
-            env.step_random()
-        else:
-            env.step_gated(threshold=gate_thr)
+        env.step_random()
     env.reset()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     for _ in range(max(3, args.warmup)):
@@ -246,11 +301,11 @@ def main():
     if world > 1:
         dist.barrier()
     launches0 = env.launch_count()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     sampler = ClockSampler(local_rank) if rank == 0 else None
     t_wall0 = time.time()
-    for i in range(args.steps):
+    for i in range(steps):
         flush.fill_(i & 0xff)  # evict the env state from L2 (outside the timed region of the step)
         starts[i].record()
         one_step()
@@ -266,7 +321,7 @@ def main():
         dist.barrier()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     tmax_ms = float(t.item())
-    value = world * args.envs * args.steps / (tmax_ms * 1e-3)
+    value = world * args.envs * steps / (tmax_ms * 1e-3)
 
     # end-of-iteration episode statistics: the only collective of the design (train.py:59-117 custom_metrics)
     stats = env.episode_statistics()
@@ -279,6 +334,8 @@ def main():
 
     # ---------------- roofline of the dominant kernel: algorithmic flops from device counters, kernel durations from
     # CUDA events around each launch (measurement mode of the library, separate pass after the timed region)
+    if gate_thr is not None:
+        env.set_risk_gate(None)
     env.enable_counters(True)
     env.counters(reset=True)
     for _ in range(3):
@@ -290,32 +347,39 @@ def main():
     sc_nj = env.scene.struct.n_joints
     env.kernel_timing(True)
     env.kernel_times(reset=True)
-    for i in range(min(args.steps, 50)):
+    for i in range(min(steps, 50)):
         flush.fill_(i & 0xff)
         env.step_random()
     ktimes, _ = env.kernel_times()
     env.kernel_timing(False)
     ksum = sum(ktimes.values())
-    # algorithmic flops per env-step attributed to each kernel
-    # (joint kernels: 300 flops per joint range + 60 per joint interpolation; an iterative position solve
-    # is ~9 evaluations of the braking profile at ~120 flops)
+    # algorithmic flops per env-step attributed to each kernel (300 flops per joint range + 60 per joint
+    # interpolation; a position-bound solve costs what its braking-profile intervals cost, ~60 flops each, counted on
+    # the device)
     hj, hs = c["heavy_joints"] / steps_counted, c["heavy_solves"] / steps_counted
-    kflops = {"joint_kernel": (sc_nj - hj) * 360.0, "joint_heavy_kernel": hj * 360.0 + hs * 9 * 120.0,
+    intervals = c["reserved"] / steps_counted      # braking-profile intervals evaluated by joint_solve_kernel
+    kflops = {"joint_kernel": (sc_nj - hj) * 360.0, "joint_heavy_kernel": hj * 360.0 + intervals * 60.0,
               "contact_plan_kernel": 8 * 600.0, "distance_plan_kernel": 600.0,
-              "gjk_kernel": 5.0 * n_dot + 100.0 * n_iter, "finish_kernel": 200.0}
-    kbound = {"joint_kernel": "fp64", "joint_heavy_kernel": "fp64"}
+              "gjk_kernel": 5.0 * n_dot + 100.0 * n_iter, "finish_kernel": 200.0,
+              # Human scene: policy 2 x 44 544 MAC on the tensor cores; range + braking steps of 8 joints; ~11 poses x
+              # (FK 600 + 203 pair bounds x 30); GJK counted with the main GJK launch
+              "human_policy": 2.0 * 44544.0, "human_joint_kernels": 8 * 360.0, "human_brake_traj_kernel": 8 * 3 * 360.0,
+              "human_brake_plan_kernel": 11 * (600.0 + 203 * 30.0), "human_brake_gjk": 0.0,
+              "human_advance_outcome": 8 * 60.0 + 24 * 300.0}
+    ktimes = {k: v for k, v in ktimes.items() if v > 0.0 or not k.startswith("human")}
+    kbound = {"joint_kernel": "fp64", "joint_heavy_kernel": "fp64", "human_joint_kernels": "fp64",
+              "human_brake_traj_kernel": "fp64"}
     f_step = F_FIXED + 5.0 * n_dot + 100.0 * n_iter
     dom = max(ktimes, key=ktimes.get)
     kernel_ms = ktimes[dom]
     per_gpu_steps_s = args.envs / (statistics.mean(step_ms) * 1e-3)
     achieved_tflops = args.envs * kflops[dom] / (kernel_ms * 1e-3) / 1e12
-    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    peak_tflops = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12  # FP32 pipe at the SM clock seen under load
     bound = kbound.get(dom, "fp32")
-    # FP64: 64 lanes per SM per clock on B200 (nominal 40 TFLOP/s class; not in MEASURED_PEAKS.json)
-    dom_peak = peak_tflops if bound == "fp32" else 148 * 64 * 2 * sm_mhz * 1e6 / 1e12
+    dom_peak = fma_peaks[bound]
     sc = env.scene.struct
-    bytes_step = 2 * (8 * 32 + 8 * 16 + 16 + 8) + 4 * sc.n_joints + 4 * sc.obs_size + 4 + 1 + 4 + 4 * 16
+    bytes_step = 2 * (8 * 32 + 8 * 16 + 16 + 8) + 4 * sc.n_joints + 4 * sc.obs_size + 4 + 1 + 4 + 4 * 32
+    if sc.human.enabled:   # + state of the nested env in and out, its observation and actions
+        bytes_step += 2 * (8 * 32 + 8 * 32) + 4 * 40 + 4 * 8 + 2 * 8 * 8 * 3
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -324,34 +388,39 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     uncull = {"space": 1.51e6, "space_bm": 1.71e6, "ball": 0.15e6, "ball_bm": 0.35e6, "space_task": 1.51e6,
-              "space_task_bm": 1.71e6}[args.scene]
+              "space_task_bm": 1.71e6, "human": 3.6e6, "human_bm": 3.8e6}[scene_name]
     traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            traffic = json.load(f)["bytes_per_launch"].get(args.scene, {}).get(dom)
-    except Exception:
-        pass
+    for tf in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", tf)) as f:
+                traffic = json.load(f)["bytes_per_launch"].get(scene_name, {}).get(dom)
+            if traffic is not None:
+                break
+        except Exception:
+            pass
     roofline = {"bound": bound, "achieved": achieved_tflops, "peak": dom_peak, "unit": "TFLOP/s",
                 "frac": achieved_tflops / dom_peak, "traffic": traffic,
-                "traffic_unit": "DRAM bytes per launch (profiles/r01_traffic.json, ncu --set full, 65536 envs)",
-                "peak_source": "148 SMs x {} lanes x 2 x median SM clock under load ({} MHz); nominal pipe width, "
-                               "MEASURED_PEAKS.json holds no FP32/FP64 vector peak".format(
-                                   128 if bound == "fp32" else 64, sm_mhz),
+                "traffic_unit": "DRAM bytes per launch (profiles/r0*_traffic.json, ncu --set full, 65536 envs)",
+                "peak_source": "measured on this GPU before the run: dependent-free {} FMA chains on all SMs "
+                               "(smenv_measure_fma_peaks); MEASURED_PEAKS.json holds no vector-pipe entry".format(bound),
+                "measured_fma_peaks_tflops": fma_peaks,
                 "kernel": dom, "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ksum,
                 "kernel_flops_per_env_step": kflops[dom],
                 "kernels_ms": ktimes, "flops_per_env_step": f_step, "support_dots_per_env_step": n_dot,
                 "gjk_iters_per_env_step": n_iter, "gjk_pairs_per_env_step": c["gjk_calls"] / steps_counted,
+                "position_solve_intervals_per_env_step": intervals,
                 "whole_step": {"achieved": per_gpu_steps_s * f_step / 1e12,
-                               "frac": per_gpu_steps_s * f_step / 1e12 / peak_tflops,
-                               "unculled_reference_flops_per_env_step": uncull,
-                               "frac_at_unculled_count": per_gpu_steps_s * uncull / 1e12 / peak_tflops},
+                               "frac": per_gpu_steps_s * f_step / 1e12 / fma_peaks["fp32"],
+                               "unculled_reference_flops_per_env_step": uncull},
                 "hbm": {"achieved": per_gpu_steps_s * bytes_step / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": per_gpu_steps_s * bytes_step / 1e9 / hbm_peak, "bytes_per_env_step": bytes_step,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+    if gate_thr is not None:
+        env.set_risk_gate(gate_thr)
 
     if gate_thr is not None:  # the tensor-core part: time of the gate alone, dense flops against the bf16/fp16 peak
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        env.step_gated(threshold=gate_thr)
+        env.step_random()
         g0.record()
         for _ in range(10):
             env.risk_gate(gate_thr)
@@ -365,7 +434,7 @@ def main():
                                  "achieved": gflop / (gate_ms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
                                  "frac": gflop / (gate_ms * 1e-3) / 1e12 / tpeak,
                                  "peak_source": "MEASURED_PEAKS.json bf16_tflops" if peaks else "nominal",
-                                 "risky_fraction": float(env.risky.float().mean().item())}
+                                 "risky_fraction": float(env.info[:, 16].mean().item())}
 
     # ---------------- end to end through the host-buffer API
     e2e = None
@@ -375,49 +444,45 @@ def main():
         env.host_actions[...] = acts   # the step's inputs sit in the pinned host buffer the sampler writes into
         acts = None                    # step_host(None): no pageable -> pinned copy, the H2D copy happens every step
         for _ in range(3):
-            env.step_host(acts, gate_thr, chunks=args.host_chunks)
+            env.step_host(acts, None, chunks=args.host_chunks)
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
-        k_e2e = min(args.steps, 100)
+        k_e2e = min(steps, 100 if full else 40)
         t0 = time.perf_counter()
         for _ in range(k_e2e):
-            env.step_host(acts, gate_thr, chunks=args.host_chunks)
+            env.step_host(acts, None, chunks=args.host_chunks)
         torch.cuda.synchronize(dev)
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": world * args.envs * k_e2e / float(te.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(env.host_actions.nbytes), "d2h_bytes_per_step": int(args.envs * (4 * sc.obs_size + 4 + 1)),
-               "steps": k_e2e, "host_chunks": args.host_chunks if gate_thr is None else 1,
+               "steps": k_e2e, "host_chunks": args.host_chunks,
                "api": "SafeMotionsVecEnv.step_host -> smenv_step_host (actions in the pinned host buffer, H2D, step, "
                       "D2H of obs / reward / done into pinned host buffers, all inside the timed region)"}
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only, bounded sample)
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        per_thread = 1024 if args.scene.startswith("ball") else 64
-
-        val, dt, total, csteps = cpu_reference_run(args.scene, per_thread, 20, 1, threads, target_seconds=15.0)
+    if with_cpu:
+        per_thread = 1024 if scene_name.startswith("ball") else 8 if scene_name.startswith("human") else 64
+        val, dt, total, csteps = cpu_reference_run(scene_name, per_thread, 20, 1, threads, target_seconds=15.0)
         cpu = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "{} host threads x {} envs x {} steps of the same scene ({} env-steps in {:.1f} s)".format(
                    threads, per_thread, csteps, total, dt),
-               "note": "oracle restatement -- NOT the PyBullet reference (not installable here)"}
-    if rank == 0:
-        out = {"impl": "b200", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-               "warmup": max(3, args.warmup), "ms_per_step": tmax_ms / args.steps, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f64 joint space / f32 geometry",
-               "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-               "roofline": roofline, "cpu_baseline": cpu,
-               "episode_stats": {"episodes": float(stats[0]), "mean_return": float(stats[1] / max(stats[0], 1)),
-                                 "mean_length": float(stats[2] / max(stats[0], 1)),
-                                 "by_termination_reason": {str(r): float(stats[3 + r]) for r in range(1, 6)},
-                                 "allreduce_ms": stats_ms}}
-        _emit(json.dumps(out))
+               "note": "oracle restatement (C, -O2) -- NOT the PyBullet reference (not installable here); its start states "
+                       "are a fixed synthetic set (mid-range poses at rest, one ball launch), not the pool distribution "
+                       "of the GPU run: same scene and step function, simpler state distribution"}
+    out = {"value": value, "ms_per_step": tmax_ms / steps, "workload": config["workload"], "config": config,
+           "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+           "episode_stats": {"episodes": float(stats[0]), "mean_return": float(stats[1] / max(stats[0], 1)),
+                             "mean_length": float(stats[2] / max(stats[0], 1)),
+                             "by_termination_reason": {str(r): float(stats[3 + r]) for r in range(1, 6)},
+                             "allreduce_ms": stats_ms}}
     env.close()
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+    del env, flush
+    torch.cuda.empty_cache()
+    return out
 
 
 if __name__ == "__main__":

@@ -39,7 +39,7 @@ extern "C" {
 #define SM_INFO_STRIDE 32 /* floats per env in the step-info record */
 
 enum SmStatus { SM_OK = 0, SM_ERR_ARG = -1, SM_ERR_CUDA = -2, SM_ERR_SCENE = -3, SM_ERR_STATE = -4 };
-enum SmObstacleKind { SM_OBST_NONE = 0, SM_OBST_PLANET = 1, SM_OBST_BALL = 2 };
+enum SmObstacleKind { SM_OBST_NONE = 0, SM_OBST_PLANET = 1, SM_OBST_BALL = 2, SM_OBST_HUMAN = 3 };
 
 /* Termination reasons: SafeMotionsBase.TERMINATION_* (safe_motions_base.py:64-70). */
 enum SmTermination {
@@ -91,8 +91,61 @@ enum SmObstSlot {
     SM_OB_BALL_NHIT = 15    /* obstacle_hit_time (ctlp.py:1889-1917) */
 };
 
+/* ---- Human scene (Human, ctlp.py:4647-4959: a nested SafeMotionsEnv(robot_scene=9) drives a human's two arms) ---- */
+#define SM_HUMAN_JOINTS 8      /* two arms x (flexion, adduction, rotation, forearm), description/urdf/human.urdf:140-416 */
+#define SM_MAX_OBST_FRAMES 9   /* frames of obstacle shapes: 100 = obstacle 0 (human: its base), 101 = obstacle 1 (human:
+                                  child link of human joint 0), ..., 108 = child link of human joint 7 */
+#define SM_MAX_HLINKS 16       /* human URDF links carrying collision shapes */
+#define SM_MAX_HPAIRS 256      /* convex pairs of the human's braking-trajectory collision check */
+#define SM_HBRAKE_STEPS 24     /* stored braking accelerations per env (braking timeout 2 s = 21 steps, ctlp.py:3467-3473) */
+#define SM_HBRAKE_POSES 72     /* poses one braking-trajectory check can visit: 3 per step x (1 + 21 braking steps), rounded up */
+#define SM_HSTATE_STRIDE 32    /* doubles per env in the human's state record */
+#define SM_HOBS_STRIDE 40      /* floats per env in the human's observation record (38 used, observations.py:54-117) */
+/* Slots of the human's state record (SmBuffers.hstate).  Per arm r (0, 1) a target-point block at 12 * r with the
+ * layout of SmTargetSlot up to SM_TP_LINK_POS, then: */
+#define SM_HTP_SAMPLE_NEW 10   /* _sample_new_target_point_list[r] (ctlp.py:2813-2818) */
+#define SM_HTP_REACHED 11      /* _target_point_reached_list[r] */
+enum SmHumanSlot {
+    SM_HS_BRAKE_COUNT = 24,    /* accelerations left in _valid_braking_trajectories['current'] (0 = None, ctlp.py:3000-3024) */
+    SM_HS_DRAWS = 25,          /* target points drawn from the pool so far (Philox counter) */
+    SM_HS_BRAKED = 26,         /* 1 if the last step executed the stored braking trajectory (adaptation_punishment) */
+    SM_HS_STEPS = 27           /* steps of the nested env in this episode (Philox counter of the policy noise) */
+};
+
+typedef struct SmHuman {
+    int32_t enabled;
+    int32_t n_joints;                          /* 8 */
+    int32_t joint_parent[SM_HUMAN_JOINTS];     /* parent human frame: 0 = base, 1 + j = child link of joint j */
+    double base_R[9], base_t[3];               /* world pose of the human's root link (robot_scene_base.py:175-183) */
+    double joint_R[SM_HUMAN_JOINTS][9], joint_t[SM_HUMAN_JOINTS][3], joint_axis[SM_HUMAN_JOINTS][3];
+    double pos_lo[SM_HUMAN_JOINTS], pos_hi[SM_HUMAN_JOINTS], vel_max[SM_HUMAN_JOINTS], acc_max[SM_HUMAN_JOINTS],
+        jerk_max[SM_HUMAN_JOINTS];             /* robot_scene_base.py:24-25, :347-371 (no safety buffer for the human) */
+    int32_t shape_off, n_arm_shapes, n_shapes; /* SmScene.shapes[shape_off ...]: first the parts of upper arm / forearm / hand
+                                                  of both arms (the obstacle links, ctlp.py:4772-4774), then the body parts */
+    int32_t shape_link[64];                    /* per human shape: index of its URDF link in contact_thresh */
+    double contact_thresh[SM_MAX_HLINKS][SM_MAX_MOV_ROBOT]; /* manifold threshold per (human link, robot contact slot) */
+    /* braking-trajectory collision check of the nested env (ctlp.py:3026-3207; human_network/params.json) */
+    int32_t check_braking;
+    int32_t brake_checks;                      /* collision_checks_per_time_step (ctlp.py:99-103) */
+    int32_t n_brake_pairs;
+    int32_t brake_pairs[SM_MAX_HPAIRS][2];     /* (human shape, static obstacle shape or human shape), ctlp.py:3282-3374 */
+    double brake_safety;                       /* closest_point_safety_distance of the nested env */
+    double brake_timeout;                      /* 2.0 s (ctlp.py:3467-3473) */
+    /* target points of the nested env: target_point_sequence = 1, alternating between the arms (ctlp.py:2210-2350) */
+    double tp_local[2][3];                     /* target link point ("hand" + target_link_offset) in the frame of the
+                                                  arm's last joint */
+    double tp_box_min[3], tp_box_max[3], tp_rel_min[3], tp_rel_max[3], tp_radius;
+    double tp_min_static, tp_min_self;         /* clearances of the pose a target point is sampled from */
+    /* stochastic policy head (keras_fcnet_last_layer_activation.py:187-202) */
+    double log_std_lo, log_std_hi;
+    /* start-state sampling of the nested env (ctlp.py:1461-1656 with the human_network_* keys) */
+    double start_box_min[3], start_box_max[3];
+    double kinematic_sampling_probability, stay_in_state_probability, min_start_static, min_start_self;
+    int32_t obs_size, reserved;                /* 38 */
+} SmHuman;
+
 typedef struct SmShape {
-    int32_t frame;    /* 0 = world, 1..n_joints = robot link frame of joint (frame-1), 100+k = obstacle k */
+    int32_t frame;    /* 0 = world, 1..n_joints = robot link frame of joint (frame-1), 100+k = obstacle frame k */
     int32_t vert_off; /* first vertex in SmScene.verts */
     int32_t vert_cnt;
     int32_t link;     /* URDF link index of the robot link carrying the shape, -1 for obstacles */
@@ -202,6 +255,7 @@ typedef struct SmScene {
     double tp_rel_min[3], tp_rel_max[3]; /* target_point_relative_pos_min_max (ctlp.py:184) */
     double tp_min_static, tp_min_self;   /* clearances of the pose a target point is sampled from (ctlp.py:1661-1664) */
     double reward_scale;           /* trajectory_time_step / 0.1 with normalize_reward_to_frequency, else 1 (rewards.py:172-176) */
+    SmHuman human;                 /* the human obstacle (human_network_checkpoint), else enabled = 0 */
 } SmScene;
 
 #define SM_TP_STRIDE 12 /* doubles per env in the target-point record */
@@ -231,6 +285,13 @@ typedef struct SmBuffers {
     float* info;          /* [N][SM_INFO_STRIDE] */
     double* stats;        /* [32] episode statistics accumulated with atomics (train.py:59-117); may be NULL */
     double* target;       /* [N][SM_TP_STRIDE] target-point records; NULL unless the scene uses target points */
+    /* Human scene only (else NULL): state of the nested env that moves the human's arms */
+    double* hkin;         /* [N][SM_KIN_STRIDE]  q, v, a, q_act of the human's joints */
+    double* hstate;       /* [N][SM_HSTATE_STRIDE] target points of both arms, braking-trajectory bookkeeping */
+    double* hbrake;       /* [N][SM_HBRAKE_STEPS][SM_HUMAN_JOINTS] accelerations of the stored braking trajectory */
+    float* hobs;          /* [N][SM_HOBS_STRIDE] observation of the nested env (input of the human's policy) */
+    float* hactions;      /* [N][SM_HUMAN_JOINTS] actions of the human's policy: written by the step (policy network +
+                             Philox noise), or read from here when smenv_set_human_actions_external(1) (parity tests) */
 } SmBuffers;
 
 typedef struct SmCounters {
@@ -241,7 +302,7 @@ typedef struct SmCounters {
     unsigned long long env_steps;
     unsigned long long contact_envs;   /* spans of sub-steps the coarse contact phase passed on to the fine planning */
     unsigned long long contact_items;  /* (sub-step, pair) contact candidates emitted by the contact planning */
-    unsigned long long reserved;
+    unsigned long long reserved;       /* braking-profile intervals evaluated by the iterative position-bound solves */
     unsigned long long heavy_joints;   /* (env, joint) instances that went through joint_heavy_kernel */
     unsigned long long heavy_solves;   /* position bounds that needed the iterative solve */
     unsigned long long aux[6];         /* GJK pairs by iteration count: <= 4, <= 8, <= 12, <= 16, <= 24, more */
@@ -249,8 +310,12 @@ typedef struct SmCounters {
 
 /* Kernels of one step, in launch order (smenv_kernel_times). */
 enum SmKernel {
-    SM_K_JOINT = 0, SM_K_JOINT_HEAVY = 1, SM_K_CONTACT_PLAN = 2, SM_K_DISTANCE_PLAN = 3, SM_K_GJK = 4, SM_K_FINISH = 5,
-    SM_K_COUNT = 6
+    /* Human scene only (zero elsewhere): policy network + noise, safe range of the human's joints, braking trajectory in
+     * joint space, its pose checks (planning, GJK), bookkeeping + setpoints + outcome of the nested env */
+    SM_K_HUMAN_POLICY = 0, SM_K_HUMAN_JOINT = 1, SM_K_HUMAN_BRAKE_TRAJ = 2, SM_K_HUMAN_BRAKE_PLAN = 3,
+    SM_K_HUMAN_BRAKE_GJK = 4, SM_K_HUMAN_ADVANCE = 5,
+    SM_K_JOINT = 6, SM_K_JOINT_HEAVY = 7, SM_K_CONTACT_PLAN = 8, SM_K_DISTANCE_PLAN = 9, SM_K_GJK = 10, SM_K_FINISH = 11,
+    SM_K_COUNT = 12
 };
 
 typedef struct SmEnv SmEnv;
@@ -305,9 +370,21 @@ int smenv_step_host(SmEnv* env, const SmBuffers* buf, const float* h_actions, fl
 /* Pieces of the step exposed for parity tests. */
 int smenv_safe_range(SmEnv* env, const double* kin, double* range_lo, double* range_hi, int32_t* code, int n,
                      SmStream stream);
-int smenv_distances(SmEnv* env, const double* kin, const double* obst, float* d_static, float* d_self,
+/* hkin: [n][SM_KIN_STRIDE] joint state of the human (Human scene), else NULL */
+int smenv_distances(SmEnv* env, const double* kin, const double* obst, const double* hkin, float* d_static, float* d_self,
                     float* d_moving, int n, SmStream stream);
 int smenv_observation(SmEnv* env, const SmBuffers* buf, SmStream stream);
+
+/* Human scene: with external != 0 the step takes the human's actions from buf->hactions instead of evaluating the
+ * human's policy (parity protocol: the reference samples them from a stochastic policy, ctlp.py:4701, :4827). */
+int smenv_set_human_actions_external(SmEnv* env, int external);
+/* Human scene: injects the nested env's start state after smenv_set_state (hq, hv, ha [N][8]; first target point of the
+ * active arm [N][3]; active_arm [N] int32), host or device pointers, and rewrites both observations. */
+int smenv_set_human_state(SmEnv* env, const SmBuffers* buf, const double* hq, const double* hv, const double* ha,
+                          const double* first_target, const int32_t* active_arm, const uint8_t* mask, SmStream stream);
+/* Human scene: pools of the nested env's start states / target points (sampled by smenv_fill_pools). */
+int smenv_human_pool_sizes(SmEnv* env, int* start_pool, int* target_pool);
+int smenv_copy_human_pools(SmEnv* env, double* host_start /* [P][64] */, double* host_target /* [2][T][4] */);
 
 int smenv_counters(SmEnv* env, SmCounters* out, int reset);
 int smenv_enable_counters(SmEnv* env, int enable);
@@ -344,6 +421,10 @@ int smenv_set_risk_gate(SmEnv* env, float threshold);
 /* Writes the U(-1,1) actions smenv_step_random would use for the next step into buf->actions (so that the gate can be
  * applied to them; follow with smenv_step). */
 int smenv_random_actions(SmEnv* env, const SmBuffers* buf, SmStream stream);
+
+/* Measured peaks of the FP32 and FP64 FMA pipes of `device` in TFLOP/s (a micro-benchmark of dependent-free FMA chains
+ * on all SMs): the denominators of bench.py's roofline for the vector-pipe-bound kernels. */
+int smenv_measure_fma_peaks(int device, double* tflops_fp32, double* tflops_fp64);
 
 /* Debug: trace of one GJK call between shapes ia and ib for one env state given on the host (trace: 32 x 8 floats per
  * iteration = simplex size, |v|^2, v.w, support ids, v; result: distance, iterations, then the 9 robot frames). */

@@ -111,6 +111,41 @@ class OracleEnvs:
         self.term = np.zeros(n, dtype=np.int32)
         self.info = np.zeros((n, abi.SM_INFO_STRIDE), dtype=np.float32)
         self.tp = np.zeros((n, abi.SM_TP_STRIDE)) if scene.struct.use_target_points else None
+        self.human = bool(scene.struct.human.enabled)
+        if self.human:   # state of the nested env that moves the human (ctlp.py:4647-4959)
+            self.hkin = np.zeros((n, abi.SM_KIN_STRIDE))
+            self.hstate = np.zeros((n, abi.SM_HSTATE_STRIDE))
+            self.hbrake = np.zeros((n, abi.SM_HBRAKE_STEPS * abi.SM_HUMAN_JOINTS))
+            self.hobs = np.zeros((n, abi.SM_HOBS_STRIDE), dtype=np.float32)
+            self.hinfo = np.zeros((n, 4), dtype=np.int32)
+
+    def set_human_state(self, hq, hv, ha, first_target, active_arm):
+        """Start state of the nested env: joint state [n, 8], first target point [n, 3] of arm active_arm [n]."""
+        hq, hv, ha = (np.ascontiguousarray(x, dtype=np.float64).reshape(self.n, 8) for x in (hq, hv, ha))
+        ft = np.ascontiguousarray(first_target, dtype=np.float64).reshape(self.n, 3)
+        arm = np.asarray(active_arm, dtype=np.int32).reshape(self.n)
+        self.hbrake[:] = 0
+        for e in range(self.n):
+            lib().smo_human_init(self.scene.pointer(), _p(self.hkin[e], C.c_double), _p(self.hstate[e], C.c_double),
+                                 _p(hq[e], C.c_double), _p(hv[e], C.c_double), _p(ha[e], C.c_double),
+                                 _p(ft[e], C.c_double), int(arm[e]), _p(self.hobs[e], C.c_float))
+        nh = 3 * abi.SM_HUMAN_JOINTS
+        self.obs[:, self.scene.obs_size - nh:] = self.hobs[:, :nh]
+
+    def step_human(self, actions, hactions, next_target=None):
+        """One step of the Human scene: robot actions [n, 7], actions of the human's policy [n, 8], the target point
+        [n, 3] that replaces a reached one."""
+        actions = np.ascontiguousarray(actions, dtype=np.float32)
+        hact = np.ascontiguousarray(hactions, dtype=np.float32).reshape(self.n, abi.SM_HUMAN_JOINTS)
+        nt = None if next_target is None else np.ascontiguousarray(next_target, dtype=np.float64).reshape(self.n, 3)
+        lib().smo_step_batch_human(self.scene.pointer(), self.n, _p(self.kin, C.c_double), _p(self.obst, C.c_double),
+                                   _p(self.hkin, C.c_double), _p(self.hstate, C.c_double), _p(self.hbrake, C.c_double),
+                                   _p(self.episode, C.c_int32), _p(self.ep_return, C.c_double), _p(actions, C.c_float),
+                                   _p(hact, C.c_float), _p(nt, C.c_double) if nt is not None else None,
+                                   _p(self.obs, C.c_float), _p(self.hobs, C.c_float), _p(self.reward, C.c_float),
+                                   _p(self.done, C.c_uint8), _p(self.term, C.c_int32), _p(self.info, C.c_float),
+                                   _p(self.hinfo, C.c_int32))
+        return self.obs, self.reward, self.done, self.term, self.info
 
     def set_state(self, q, v, a, obst=None, first_target=None):
         nj = self.scene.n_joints
@@ -152,6 +187,46 @@ class OracleEnvs:
                                 _p(self.reward, C.c_float), _p(self.done, C.c_uint8), _p(self.term, C.c_int32),
                                 _p(self.info, C.c_float))
         return self.obs, self.reward, self.done, self.term, self.info
+
+
+def human_fk(scene, hq):
+    """Frames [9, 12] of the human (base, then the child link of every joint) for one joint vector [8]."""
+    out = np.zeros((1 + abi.SM_HUMAN_JOINTS, 12))
+    hq = np.ascontiguousarray(hq, dtype=np.float64)
+    lib().smo_human_fk_flat(scene.pointer(), _p(hq, C.c_double), _p(out, C.c_double))
+    return out
+
+
+def human_link_points(scene, hq):
+    out = np.zeros((2, 3))
+    hq = np.ascontiguousarray(hq, dtype=np.float64)
+    lib().smo_human_link_points(scene.pointer(), _p(hq, C.c_double), _p(out, C.c_double))
+    return out
+
+
+def human_safe_range(scene, q, v, a):
+    q, v, a = (np.ascontiguousarray(x, dtype=np.float64) for x in (q, v, a))
+    lo, hi, code = np.zeros(8), np.zeros(8), np.zeros(8, dtype=np.int32)
+    lib().smo_human_safe_range(scene.pointer(), _p(q, C.c_double), _p(v, C.c_double), _p(a, C.c_double),
+                               _p(lo, C.c_double), _p(hi, C.c_double), _p(code, C.c_int32))
+    return lo, hi, code
+
+
+def human_pose_collides(scene, hq):
+    hq = np.ascontiguousarray(hq, dtype=np.float64)
+    return bool(lib().smo_human_pose_collides(scene.pointer(), _p(hq, C.c_double)))
+
+
+def human_check_braking(scene, q, v, a, a_target):
+    """(execute braking?, braking accelerations [k, 8], poses visited, first colliding pose) of the nested env's
+    braking-trajectory check (ctlp.py:3026-3207)."""
+    q, v, a, at = (np.ascontiguousarray(x, dtype=np.float64) for x in (q, v, a, a_target))
+    acc = np.zeros((abi.SM_HBRAKE_STEPS, 8))
+    k, poses, coll = C.c_int(), C.c_int(), C.c_int()
+    ex = lib().smo_human_check_braking(scene.pointer(), _p(q, C.c_double), _p(v, C.c_double), _p(a, C.c_double),
+                                       _p(at, C.c_double), _p(acc, C.c_double), C.byref(k), C.byref(poses),
+                                       C.byref(coll))
+    return bool(ex), acc[:min(k.value, abi.SM_HBRAKE_STEPS)], poses.value, coll.value
 
 
 def target_link_point(scene, q):

@@ -173,9 +173,10 @@ double smo_pos_peak(double p, double v, double a, double a1, double J, double A,
     return pos_peak_d(p, v, a, a1, J, A, ts, dpeak);
 }
 
-void smo_safe_range_joint(const SmScene* sc, int j, double p, double v, double a, double* out_lo, double* out_hi,
-                          int32_t* out_code) {
-    double ts = sc->ts, J = sc->jerk_max[j], A = sc->acc_max[j], V = sc->vel_max[j];
+/* range of one joint with limits (J, A, V, [plo, phi]) */
+static void safe_range_limits(double ts, double J, double A, double V, double plo, double phi, int limit_velocity,
+                              int limit_position, double p, double v, double a, double* out_lo, double* out_hi,
+                              int32_t* out_code) {
     int code = 0;
     double lo = a - J * ts, hi = a + J * ts;
     if (lo < -A) lo = -A;
@@ -184,17 +185,23 @@ void smo_safe_range_joint(const SmScene* sc, int j, double p, double v, double a
         code |= CODE_ACC;
         if (a > 0.0) lo = hi; else hi = lo;
     }
-    if (sc->limit_velocity) {
+    if (limit_velocity) {
         double bhi = vel_upper(v, a, V, J, A, ts);
         double blo = -vel_upper(-v, -a, V, J, A, ts);
         clamp_range(&lo, &hi, blo, bhi, CODE_VEL_HI, CODE_VEL_LO, &code);
     }
-    if (sc->limit_position) {
-        double bhi = pos_upper(p, v, a, sc->pos_hi[j], lo, hi, J, A, ts);
-        double blo = -pos_upper(-p, -v, -a, -sc->pos_lo[j], -hi, -lo, J, A, ts);
+    if (limit_position) {
+        double bhi = pos_upper(p, v, a, phi, lo, hi, J, A, ts);
+        double blo = -pos_upper(-p, -v, -a, -plo, -hi, -lo, J, A, ts);
         clamp_range(&lo, &hi, blo, bhi, CODE_POS_HI, CODE_POS_LO, &code);
     }
     *out_lo = lo; *out_hi = hi; *out_code = code;
+}
+
+void smo_safe_range_joint(const SmScene* sc, int j, double p, double v, double a, double* out_lo, double* out_hi,
+                          int32_t* out_code) {
+    safe_range_limits(sc->ts, sc->jerk_max[j], sc->acc_max[j], sc->vel_max[j], sc->pos_lo[j], sc->pos_hi[j],
+                      sc->limit_velocity, sc->limit_position, p, v, a, out_lo, out_hi, out_code);
 }
 
 void smo_safe_range(const SmScene* sc, const double* q, const double* v, const double* a, double* lo, double* hi,
@@ -524,19 +531,30 @@ static double pair_distance(const SmScene* sc, int ia, int ib, const Xf* robot, 
 /* ------------------------------------------------------------------------------------------------------------
  * 6. Distances  (get_minimum_distance ctlp.py:3282-3374, get_minimum_distance_to_moving_obstacles :3217-3280)
  * ---------------------------------------------------------------------------------------------------------- */
-static void obstacle_poses(const SmScene* sc, const double* ob, Xf* obst) {
+void smo_human_fk(const SmScene* sc, const double* hq, Xf* fr);
+/* hq: joint angles of the human (Human scene), else NULL */
+static void obstacle_poses_h(const SmScene* sc, const double* ob, const double* hq, Xf* obst) {
     for (int o = 0; o < sc->n_obstacles; ++o) {
+        if (sc->obst_kind[o] == SM_OBST_HUMAN) { if (hq) smo_human_fk(sc, hq, obst); continue; }
         if (sc->obst_kind[o] == SM_OBST_PLANET) planet_pose(sc, o, (int)ob[SM_OB_INDEX], &obst[o]);
         else if (sc->obst_kind[o] == SM_OBST_BALL) ball_pose(ob, ob[SM_OB_BALL_T], &obst[o]);
         else xf_identity(&obst[o]);
     }
 }
 
+
+void smo_distances_h(const SmScene* sc, const double* q, const double* ob, const double* hq, double* d_static,
+                     double* d_self, double* d_moving);
 void smo_distances(const SmScene* sc, const double* q, const double* ob, double* d_static, double* d_self,
                    double* d_moving) {
-    Xf robot[1 + SM_MAX_JOINTS], obst[SM_MAX_OBSTACLES];
+    smo_distances_h(sc, q, ob, (const double*)0, d_static, d_self, d_moving);
+}
+/* hq: setpoint pose of the human (set_position_in_obstacle_client_to_setpoints, ctlp.py:3246-3251), else NULL */
+void smo_distances_h(const SmScene* sc, const double* q, const double* ob, const double* hq, double* d_static,
+                     double* d_self, double* d_moving) {
+    Xf robot[1 + SM_MAX_JOINTS], obst[SM_MAX_OBST_FRAMES];
     smo_fk(sc, q, robot);
-    obstacle_poses(sc, ob, obst);
+    obstacle_poses_h(sc, ob, hq, obst);
     /* static and self: start at the cap, points beyond the query distance are not returned (ctlp.py:3290-3320) */
     double ds = sc->static_cap, dself = sc->static_cap;
     for (int i = 0; i < sc->n_static_pairs; ++i) {
@@ -648,6 +666,340 @@ void smo_target_link_point(const SmScene* sc, const double* q, double* p) {
 }
 
 /* ------------------------------------------------------------------------------------------------------------
+ * 7b. Human  (Human, ctlp.py:4647-4959): a nested SafeMotionsEnv(robot_scene = 9) moves the two arms of a human
+ *     (description/urdf/human.urdf:140-416); configuration in trained_networks/human_network/params.json.
+ *     Per step of the main env the nested env runs (ctlp.py:962-976, :4818-4882; safe_motions_base.py:1043-1227):
+ *       step:     action of the human's policy -> end acceleration (actions.py:268-280) -> braking-trajectory
+ *                 collision check (ctlp.py:3026-3207; utils/braking_trajectory_generator.py) -> setpoints
+ *       24 x      prepare_sim_step (motor control), update (target point reached?), contact human <-> robot
+ *       outcome:  new knot, target-point bookkeeping, observation (38 entries)
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct SmoHumanIO {
+    double* hkin;              /* [SM_KIN_STRIDE] q v a q_act of the human */
+    double* hstate;            /* [SM_HSTATE_STRIDE] */
+    double* hbrake;            /* [SM_HBRAKE_STEPS][SM_HUMAN_JOINTS] */
+    const double* uh;          /* [8] action of the human's policy for this step */
+    const double* next_target; /* [3] target point for the arm that becomes active when a point is reached (the
+                                  reference samples it by rejection, ctlp.py:1658-1720), or NULL */
+    float* hobs;               /* [SM_HOBS_STRIDE] out: observation of the nested env */
+    int32_t braked;            /* out: 1 if the stored braking trajectory was executed */
+    int32_t brake_poses;       /* out: poses the braking-trajectory check visited */
+    int32_t brake_collision;   /* out: 1-based index of the first pose in collision, 0 = none, -1 = timeout */
+    double a1[SM_HUMAN_JOINTS];/* out: end acceleration of the step */
+} SmoHumanIO;
+
+int smo_sizeof_human_io(void) { return (int)sizeof(SmoHumanIO); }
+
+/* frames of the human: [0] = base, [1 + j] = child link of joint j (same convention as smo_fk) */
+void smo_human_fk(const SmScene* sc, const double* hq, Xf* fr /* [SM_MAX_OBST_FRAMES] */) {
+    const SmHuman* h = &sc->human;
+    memcpy(fr[0].R, h->base_R, sizeof(h->base_R));
+    memcpy(fr[0].t, h->base_t, sizeof(h->base_t));
+    for (int j = 0; j < h->n_joints; ++j) {
+        const Xf* P = &fr[h->joint_parent[j]];
+        double Rj[9], R1[9], tp[3];
+        mat_mul(P->R, h->joint_R[j], R1);
+        mat_vec(P->R, h->joint_t[j], tp);
+        axis_angle(h->joint_axis[j], hq[j], Rj);
+        mat_mul(R1, Rj, fr[1 + j].R);
+        for (int i = 0; i < 3; ++i) fr[1 + j].t[i] = P->t[i] + tp[i];
+    }
+}
+void smo_human_fk_flat(const SmScene* sc, const double* hq, double* out) {
+    Xf fr[SM_MAX_OBST_FRAMES];
+    smo_human_fk(sc, hq, fr);
+    for (int f = 0; f <= sc->human.n_joints; ++f) {
+        memcpy(out + 12 * f, fr[f].R, 9 * sizeof(double));
+        memcpy(out + 12 * f + 9, fr[f].t, 3 * sizeof(double));
+    }
+}
+
+/* target link point of arm r ("hand" + target_link_offset, LinkPointBase.get_position ctlp.py:4962-5075) */
+static void human_link_point(const SmScene* sc, const Xf* fr, int r, double* p) {
+    const Xf* F = &fr[4 * (r + 1)];
+    double w[3];
+    mat_vec(F->R, sc->human.tp_local[r], w);
+    for (int i = 0; i < 3; ++i) p[i] = w[i] + F->t[i];
+}
+void smo_human_link_points(const SmScene* sc, const double* hq, double* out /* [2][3] */) {
+    Xf fr[SM_MAX_OBST_FRAMES];
+    smo_human_fk(sc, hq, fr);
+    human_link_point(sc, fr, 0, out);
+    human_link_point(sc, fr, 1, out + 3);
+}
+
+void smo_human_safe_range(const SmScene* sc, const double* q, const double* v, const double* a, double* lo, double* hi,
+                          int32_t* code) {
+    const SmHuman* h = &sc->human;
+    for (int j = 0; j < h->n_joints; ++j)
+        safe_range_limits(sc->ts, h->jerk_max[j], h->acc_max[j], h->vel_max[j], h->pos_lo[j], h->pos_hi[j], 1, 1, q[j],
+                          v[j], a[j], &lo[j], &hi[j], &code[j]);
+}
+
+/* get_minimum_distance as the braking-trajectory check uses it (ctlp.py:3282-3374): is some observed pair closer than
+ * the safety distance?  (table x forearm / hand, self-collision link pairs with forearm or hand) */
+int smo_human_pose_collides(const SmScene* sc, const double* hq) {
+    const SmHuman* h = &sc->human;
+    Xf world[1 + SM_MAX_JOINTS], fr[SM_MAX_OBST_FRAMES];
+    xf_identity(&world[0]);
+    smo_human_fk(sc, hq, fr);
+    for (int i = 0; i < h->n_brake_pairs; ++i) {
+        double d = pair_distance(sc, h->brake_pairs[i][0], h->brake_pairs[i][1], world, fr, h->brake_safety + 1e-3);
+        if (d < h->brake_safety) return 1;
+    }
+    return 0;
+}
+
+/* BrakingTrajectoryGenerator.get_braking_acceleration for one joint (utils/braking_trajectory_generator.py:44-78): a
+ * second limiter with velocity limits [0, 0] picks the next acceleration that brings the joint to rest.  Restated as:
+ * the next-knot acceleration a1 from which the acceleration can be ramped back to zero at full jerk, in whole time
+ * steps, so that velocity AND acceleration reach zero together:
+ *     a1, a1 + r, ..., 0  (n ramp intervals, r = J ts)   =>   v_end = v + a ts / 2 + n ts a1 + ts r n (n - 1) / 2 = 0
+ * with the smallest n whose a1 needs no more than n ramp intervals; clipped to the jerk / acceleration interval like
+ * every bound of the limiter. */
+static double brake_target(double v, double a, double J, double A, double ts) {
+    double s0 = v + a * ts * 0.5;
+    double sg = s0 < 0.0 ? -1.0 : 1.0;
+    double S = sg * s0, r = J * ts;
+    double a1 = 0.0;
+    for (int n = 1; n <= 8; ++n) {
+        double dn = (double)n;
+        a1 = (S + ts * r * dn * (dn - 1.0) * 0.5) / (dn * ts);
+        if (a1 <= dn * r) break;
+    }
+    a1 = -sg * a1;
+    double lo = a - J * ts, hi = a + J * ts;
+    if (lo < -A) lo = -A;
+    if (hi > A) hi = A;
+    if (lo > hi) { if (a > 0.0) lo = hi; else hi = lo; }
+    if (a1 < lo) a1 = lo;
+    if (a1 > hi) a1 = hi;
+    return a1;
+}
+
+/* _compute_braking_acceleration (ctlp.py:3495-3507) + get_clipped_braking_acceleration: returns robot_stopped */
+static int human_braking_acceleration(const SmScene* sc, const double* q, const double* v, const double* a,
+                                      double* a_end) {
+    const SmHuman* h = &sc->human;
+    int all_small = 1;
+    for (int j = 0; j < h->n_joints; ++j)
+        if (!(fabs(v[j]) < 0.01 && fabs(a[j]) < 0.01)) all_small = 0;
+    if (all_small) {
+        for (int j = 0; j < h->n_joints; ++j) a_end[j] = 0.0;
+        return 1;
+    }
+    for (int j = 0; j < h->n_joints; ++j) {
+        double lo, hi;
+        int32_t code;
+        safe_range_limits(sc->ts, h->jerk_max[j], h->acc_max[j], h->vel_max[j], h->pos_lo[j], h->pos_hi[j], 1, 1, q[j],
+                          v[j], a[j], &lo, &hi, &code);
+        double e = brake_target(v[j], a[j], h->jerk_max[j], h->acc_max[j], sc->ts);
+        if (fabs(v[j]) < 0.01 && fabs(a[j]) < 0.01) e = 0.0;
+        if (e < lo) e = lo; /* np.clip(end_acceleration, next_acc_min, next_acc_max) */
+        if (e > hi) e = hi;
+        a_end[j] = e;
+    }
+    return 0;
+}
+
+/* check_braking_trajectory_method / _check_if_braking_trajectory_is_collision_free (ctlp.py:3026-3053, :3155-3207):
+ * execute the next step with a_target, then brake; every step is checked at brake_checks poses.  Returns 1 if the
+ * braking trajectory has to be executed instead (collision or timeout).  brake_acc receives the braking accelerations
+ * b_1 .. b_k that follow a_target (the part adapt_action keeps, ctlp.py:3096-3119), *k_out their number. */
+int smo_human_check_braking(const SmScene* sc, const double* q0, const double* v0, const double* a0,
+                            const double* a_target, double* brake_acc /* [SM_HBRAKE_STEPS][8] */, int* k_out,
+                            int* poses_out, int* collision_out) {
+    const SmHuman* h = &sc->human;
+    const int nj = h->n_joints, C = h->brake_checks;
+    double ts = sc->ts;
+    double q[SM_HUMAN_JOINTS], v[SM_HUMAN_JOINTS], as[SM_HUMAN_JOINTS], ae[SM_HUMAN_JOINTS];
+    memcpy(q, q0, sizeof(q)); memcpy(v, v0, sizeof(v)); memcpy(as, a0, sizeof(as)); memcpy(ae, a_target, sizeof(ae));
+    int k = 0, poses = 0;
+    *collision_out = 0;
+    for (;;) {
+        /* np.linspace(ts / C, ts, C) */
+        double pend[SM_HUMAN_JOINTS];
+        for (int m = 1; m <= C; ++m) {
+            double t;
+            if (C <= 1 || m == C) t = ts;
+            else { double start = ts / C, step = (ts - start) / (double)(C - 1); t = start + (double)(m - 1) * step; }
+            double pm[SM_HUMAN_JOINTS];
+            for (int j = 0; j < nj; ++j) { double vv, aa; interpolate(sc, q[j], v[j], as[j], ae[j], t, &pm[j], &vv, &aa); }
+            ++poses;
+            if (smo_human_pose_collides(sc, pm)) { *collision_out = poses; *k_out = k; *poses_out = poses; return 1; }
+            if (m == C) memcpy(pend, pm, sizeof(pm));
+        }
+        /* _compute_next_braking_trajectory_time_step (ctlp.py:3467-3493) */
+        if ((double)k * ts > h->brake_timeout) { *collision_out = -1; *k_out = k; *poses_out = poses; return 1; }
+        double vend[SM_HUMAN_JOINTS], anext[SM_HUMAN_JOINTS];
+        for (int j = 0; j < nj; ++j) { double qq, aa; interpolate(sc, q[j], v[j], as[j], ae[j], ts, &qq, &vend[j], &aa); }
+        int stopped = human_braking_acceleration(sc, pend, vend, ae, anext);
+        if (stopped) break;
+        if (k < SM_HBRAKE_STEPS) memcpy(brake_acc + (size_t)k * SM_HUMAN_JOINTS, anext, sizeof(anext));
+        ++k;
+        memcpy(q, pend, sizeof(q)); memcpy(v, vend, sizeof(v)); memcpy(as, ae, sizeof(as)); memcpy(ae, anext, sizeof(ae));
+    }
+    *k_out = k; *poses_out = poses;
+    return 0;
+}
+
+/* the nested env's step up to the setpoints: range, action mapping, braking-trajectory method (actions.py:282-376) */
+static void human_pre_step(const SmScene* sc, SmoHumanIO* H) {
+    const SmHuman* h = &sc->human;
+    double *q = H->hkin, *v = H->hkin + 8, *a = H->hkin + 16;
+    double lo[SM_HUMAN_JOINTS], hi[SM_HUMAN_JOINTS];
+    int32_t code[SM_HUMAN_JOINTS];
+    smo_human_safe_range(sc, q, v, a, lo, hi, code);
+    for (int j = 0; j < h->n_joints; ++j) H->a1[j] = lo[j] + 0.5 * (H->uh[j] + 1.0) * (hi[j] - lo[j]);
+    H->braked = 0; H->brake_poses = 0; H->brake_collision = 0;
+    H->hstate[SM_HS_STEPS] += 1.0;
+    if (!h->check_braking) return;
+    double bacc[SM_HBRAKE_STEPS * SM_HUMAN_JOINTS];
+    int k = 0, poses = 0, coll = 0;
+    int execute = smo_human_check_braking(sc, q, v, a, H->a1, bacc, &k, &poses, &coll);
+    H->brake_poses = poses; H->brake_collision = coll;
+    int count = (int)H->hstate[SM_HS_BRAKE_COUNT];
+    if (execute) { /* get_braking_acceleration (ctlp.py:3000-3024): next acceleration of the stored trajectory */
+        H->braked = 1;
+        if (count > 0) {
+            memcpy(H->a1, H->hbrake, SM_HUMAN_JOINTS * sizeof(double));
+            memmove(H->hbrake, H->hbrake + SM_HUMAN_JOINTS, (size_t)(count - 1) * SM_HUMAN_JOINTS * sizeof(double));
+            H->hstate[SM_HS_BRAKE_COUNT] = (double)(count - 1);
+        } else {
+            for (int j = 0; j < h->n_joints; ++j) H->a1[j] = 0.0;
+        }
+    } else { /* adapt_action: the checked trajectory becomes the valid one (ctlp.py:3096-3119) */
+        if (k > SM_HBRAKE_STEPS) k = SM_HBRAKE_STEPS;
+        memcpy(H->hbrake, bacc, (size_t)k * SM_HUMAN_JOINTS * sizeof(double));
+        H->hstate[SM_HS_BRAKE_COUNT] = (double)k;
+    }
+    H->hstate[SM_HS_BRAKED] = (double)H->braked;
+}
+
+/* one 1/240 s sub-step of the human: setpoint, motor tracking (Human.prepare_sim_step ctlp.py:4850-4860), then the
+ * nested wrapper's update: is the active target point reached? (ctlp.py:2787-2821) */
+static void human_substep(const SmScene* sc, SmoHumanIO* H, double t, double dt) {
+    const SmHuman* h = &sc->human;
+    double *q = H->hkin, *v = H->hkin + 8, *a = H->hkin + 16, *qa = H->hkin + 24;
+    double qset[SM_HUMAN_JOINTS];
+    for (int j = 0; j < h->n_joints; ++j) {
+        double qs, vs, as;
+        interpolate(sc, q[j], v[j], a[j], H->a1[j], t, &qs, &vs, &as);
+        qset[j] = qs;
+        qa[j] = qa[j] + sc->track_kp * (qs - qa[j]) + (0.87 * dt) * vs; /* use_controller_target_velocities = true */
+    }
+    Xf fr[SM_MAX_OBST_FRAMES];
+    smo_human_fk(sc, qset, fr);
+    for (int r = 0; r < 2; ++r) human_link_point(sc, fr, r, H->hstate + 12 * r + SM_TP_LINK_POS);
+    for (int r = 0; r < 2; ++r) {
+        double* tp = H->hstate + 12 * r;
+        if (tp[SM_TP_ACTIVE] == 0.0) continue;
+        double dx = tp[SM_TP_LINK_POS] - tp[SM_TP_POS], dy = tp[SM_TP_LINK_POS + 1] - tp[SM_TP_POS + 1],
+               dz = tp[SM_TP_LINK_POS + 2] - tp[SM_TP_POS + 2];
+        if (sqrt(dx * dx + dy * dy + dz * dz) < h->tp_radius) {
+            tp[SM_HTP_REACHED] = 1.0;
+            tp[SM_TP_ACTIVE] = 0.0;
+            tp[SM_TP_REACHED_N] += 1.0;
+            H->hstate[12 * ((r + 1) % 2) + SM_HTP_SAMPLE_NEW] = 1.0; /* alternating target points (ctlp.py:2815-2817) */
+        }
+    }
+}
+
+/* observation of the nested env (observations.py:313-351 with two arms and alternating target points) */
+void smo_human_observation(const SmScene* sc, const double* hkin, const double* hstate, float* hobs) {
+    const SmHuman* h = &sc->human;
+    int k = 0;
+    for (int j = 0; j < 8; ++j) hobs[k++] = clip1(-1.0 + 2.0 * (hkin[j] - h->pos_lo[j]) / (h->pos_hi[j] - h->pos_lo[j]));
+    for (int j = 0; j < 8; ++j) hobs[k++] = clip1(hkin[8 + j] / h->vel_max[j]);
+    for (int j = 0; j < 8; ++j) hobs[k++] = clip1(hkin[16 + j] / h->acc_max[j]);
+    for (int r = 0; r < 2; ++r) {
+        const double* tp = hstate + 12 * r;
+        for (int i = 0; i < 3; ++i)
+            hobs[k++] = tp[SM_TP_ACTIVE] != 0.0
+                            ? clip1(-1.0 + 2.0 * (tp[SM_TP_POS + i] - h->tp_box_min[i]) / (h->tp_box_max[i] - h->tp_box_min[i]))
+                            : 0.0f;
+    }
+    for (int r = 0; r < 2; ++r) {
+        const double* tp = hstate + 12 * r;
+        for (int i = 0; i < 3; ++i) {
+            double rel = tp[SM_TP_POS + i] - tp[SM_TP_LINK_POS + i];
+            hobs[k++] = tp[SM_TP_ACTIVE] != 0.0
+                            ? clip1(-1.0 + 2.0 * (rel - h->tp_rel_min[i]) / (h->tp_rel_max[i] - h->tp_rel_min[i])) : 0.0f;
+        }
+    }
+    for (int r = 0; r < 2; ++r) hobs[k++] = hstate[12 * r + SM_TP_ACTIVE] != 0.0 ? 1.0f : 0.0f;
+    while (k < SM_HOBS_STRIDE) hobs[k++] = 0.0f;
+}
+
+/* process_step_outcome of the nested env: new knot, target points (get_target_point_observation ctlp.py:2210-2271) */
+static void human_post_step(const SmScene* sc, SmoHumanIO* H) {
+    const SmHuman* h = &sc->human;
+    double *q = H->hkin, *v = H->hkin + 8, *a = H->hkin + 16;
+    for (int j = 0; j < h->n_joints; ++j) {
+        double qs, vs, as;
+        interpolate(sc, q[j], v[j], a[j], H->a1[j], substep_time(sc, sc->substeps), &qs, &vs, &as);
+        q[j] = qs; v[j] = vs; a[j] = H->a1[j];
+    }
+    for (int r = 0; r < 2; ++r) {
+        double* tp = H->hstate + 12 * r;
+        tp[SM_HTP_REACHED] = 0.0;
+        if (tp[SM_HTP_SAMPLE_NEW] != 0.0 && H->next_target) {
+            memcpy(tp + SM_TP_POS, H->next_target, 3 * sizeof(double));
+            tp[SM_HTP_SAMPLE_NEW] = 0.0;
+            tp[SM_TP_ACTIVE] = 1.0;
+            tp[SM_TP_INIT_DIST] = NAN;
+            H->hstate[SM_HS_DRAWS] += 1.0;
+        }
+    }
+    for (int r = 0; r < 2; ++r) {
+        double* tp = H->hstate + 12 * r;
+        if (tp[SM_TP_ACTIVE] == 0.0) continue;
+        double dx = tp[SM_TP_POS] - tp[SM_TP_LINK_POS], dy = tp[SM_TP_POS + 1] - tp[SM_TP_LINK_POS + 1],
+               dz = tp[SM_TP_POS + 2] - tp[SM_TP_LINK_POS + 2];
+        tp[SM_TP_LAST_DIST] = sqrt(dx * dx + dy * dy + dz * dz);
+        if (isnan(tp[SM_TP_INIT_DIST])) tp[SM_TP_INIT_DIST] = tp[SM_TP_LAST_DIST];
+    }
+    if (H->hobs) smo_human_observation(sc, H->hkin, H->hstate, H->hobs);
+}
+
+/* start of an episode of the nested env (ObstacleWrapperBase.reset, ctlp.py:1020-1048): one arm gets the first target
+ * point, nothing is stored from earlier braking checks */
+void smo_human_init(const SmScene* sc, double* hkin, double* hstate, const double* hq, const double* hv,
+                    const double* ha, const double* first_target, int active_arm, float* hobs) {
+    memset(hkin, 0, SM_KIN_STRIDE * sizeof(double));
+    memset(hstate, 0, SM_HSTATE_STRIDE * sizeof(double));
+    double dt = sc->ts / (double)sc->substeps;
+    for (int j = 0; j < sc->human.n_joints; ++j) {
+        hkin[j] = hq[j]; hkin[8 + j] = hv[j]; hkin[16 + j] = ha[j];
+        hkin[24 + j] = hq[j] + (0.87 * dt) * hv[j]; /* as the robot: one stepSimulation with the start state as target */
+    }
+    double lp[6];
+    smo_human_link_points(sc, hq, lp);
+    for (int r = 0; r < 2; ++r) memcpy(hstate + 12 * r + SM_TP_LINK_POS, lp + 3 * r, 3 * sizeof(double));
+    double* tp = hstate + 12 * active_arm;
+    memcpy(tp + SM_TP_POS, first_target, 3 * sizeof(double));
+    tp[SM_TP_ACTIVE] = 1.0;
+    double dx = tp[SM_TP_POS] - tp[SM_TP_LINK_POS], dy = tp[SM_TP_POS + 1] - tp[SM_TP_LINK_POS + 1],
+           dz = tp[SM_TP_POS + 2] - tp[SM_TP_LINK_POS + 2];
+    tp[SM_TP_LAST_DIST] = tp[SM_TP_INIT_DIST] = sqrt(dx * dx + dy * dy + dz * dz);
+    hstate[SM_HS_DRAWS] = 1.0;
+    if (hobs) smo_human_observation(sc, hkin, hstate, hobs);
+}
+
+/* getContactPoints(bodyA = human, bodyB = robot) in the simulation client (ctlp.py:4888-4898): both at their
+ * motor-tracked poses; every human link (also the body) against every robot link */
+static int human_contact_exists(const SmScene* sc, const Xf* robot, const Xf* hfr) {
+    const SmHuman* h = &sc->human;
+    for (int r = 0; r < sc->n_mov_contact; ++r)
+        for (int s = 0; s < h->n_shapes; ++s) {
+            double th = h->contact_thresh[h->shape_link[s]][r];
+            double d = pair_distance(sc, sc->mov_contact[r], h->shape_off + s, robot, hfr, th + 1e-3);
+            if (d <= th) return 1;
+        }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------------
  * 8. One env step  (safe_motions_base.py:1043-1227)
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct SmoStepOut {
@@ -663,8 +1015,9 @@ typedef struct SmoStepOut {
 /* kin: [q8 v8 a8 qact8], ob: obstacle record, episode_length in/out.  u: n_joints actions as doubles. */
 /* tp: target-point record (SM_TP_STRIDE doubles) or NULL; next_target: the target point that replaces a reached one
  * (drawn by the caller, like next_ball, because the reference samples it with data-dependent rejection sampling). */
-void smo_step_tp(const SmScene* sc, double* kin, double* ob, double* tp, int32_t* episode_length, double* ep_return,
-                 const double* u, const double* next_ball, const double* next_target, float* obs, SmoStepOut* out) {
+static void step_core(const SmScene* sc, double* kin, double* ob, double* tp, SmoHumanIO* H, int32_t* episode_length,
+                      double* ep_return, const double* u, const double* next_ball, const double* next_target, float* obs,
+                      SmoStepOut* out) {
     int nj = sc->n_joints, S = sc->substeps;
     double *q = kin, *v = kin + 8, *a = kin + 16, *qa = kin + 24;
     int32_t code[SM_MAX_JOINTS];
@@ -674,21 +1027,23 @@ void smo_step_tp(const SmScene* sc, double* kin, double* ob, double* tp, int32_t
     smo_map_action(sc, u, out->range_lo, out->range_hi, out->a1); /* actions.py:291 */
     int rcode = 0;
     for (int j = 0; j < nj; ++j) rcode |= code[j];
+    if (H) human_pre_step(sc, H); /* obstacle_wrapper.step() -> Human.step (ctlp.py:962-966, :4818-4840) */
 
     /* --- 24 sub-steps (safe_motions_base.py:1233-1277).  Inside sub-step k Bullet first detects collisions on the
      * poses left by sub-step k-1 (tracked robot pose, obstacle pose of the previous update), then integrates the
      * motor-controlled joints; afterwards obstacle_wrapper.update advances the obstacles and reads the manifolds. */
     double dt = sc->ts / (double)S;
-    Xf robot[1 + SM_MAX_JOINTS], obst[SM_MAX_OBSTACLES];
+    Xf robot[1 + SM_MAX_JOINTS], obst[SM_MAX_OBST_FRAMES];
     for (int k = 1; k <= S; ++k) {
         double t = substep_time(sc, k);
         int test_contacts = (sc->contact_stride > 0) && (k % sc->contact_stride == 0);
         int contact[SM_MAX_OBSTACLES] = {0, 0};
         if (test_contacts && ob[SM_OB_LATCH] == 0.0) {
             smo_fk(sc, qa, robot);
-            obstacle_poses(sc, ob, obst);
+            obstacle_poses_h(sc, ob, H ? H->hkin + 24 : (const double*)0, obst); /* the human at its tracked pose */
             for (int o = 0; o < sc->n_obstacles; ++o) {
                 if (sc->obst_kind[o] == SM_OBST_BALL && ob[SM_OB_BALL_ACTIVE] == 0.0) continue;
+                if (sc->obst_kind[o] == SM_OBST_HUMAN) { contact[o] = H ? human_contact_exists(sc, robot, obst) : 0; continue; }
                 contact[o] = contact_exists(sc, o, robot, obst);
             }
         }
@@ -716,7 +1071,10 @@ void smo_step_tp(const SmScene* sc, double* kin, double* ob, double* tp, int32_t
         }
         /* obstacle_wrapper.update (ctlp.py:2590-2862) */
         for (int o = 0; o < sc->n_obstacles; ++o) {
-            if (sc->obst_kind[o] == SM_OBST_PLANET) {
+            if (sc->obst_kind[o] == SM_OBST_HUMAN && H) { /* ctlp.py:2613-2615: Human.update, then the contact latch */
+                human_substep(sc, H, t, dt);
+                if (contact[o]) ob[SM_OB_LATCH] = 1.0;
+            } else if (sc->obst_kind[o] == SM_OBST_PLANET) {
                 if (o == 0) ob[SM_OB_INDEX] = (double)(((int)ob[SM_OB_INDEX] + 1) % sc->planet_steps);
                 if (contact[o] && sc->terminate_moving) ob[SM_OB_LATCH] = 1.0; /* ctlp.py:2631-2637 */
             } else if (sc->obst_kind[o] == SM_OBST_BALL && ob[SM_OB_BALL_ACTIVE] != 0.0) {
@@ -744,8 +1102,9 @@ void smo_step_tp(const SmScene* sc, double* kin, double* ob, double* tp, int32_t
         if (jr > jerk_rel) jerk_rel = jr;
         q[j] = qs; v[j] = vs; a[j] = out->a1[j];
     }
+    if (H) human_post_step(sc, H); /* obstacle_wrapper.process_step_outcome -> Human.process_step_outcome */
     /* --- reward (rewards.py:95-169, :432-502) */
-    smo_distances(sc, q, ob, &out->d_static, &out->d_self, &out->d_moving);
+    smo_distances_h(sc, q, ob, H ? H->hkin : (const double*)0, &out->d_static, &out->d_self, &out->d_moving);
     double ds = out->d_static, dself = out->d_self, dm = out->d_moving;
     int c_static = 0, c_self = 0, c_moving = 0;
     if (ds < sc->collision_dist) { ds = 0.0; c_static = 1; }
@@ -861,7 +1220,51 @@ void smo_step_tp(const SmScene* sc, double* kin, double* ob, double* tp, int32_t
             if (isnan(tp[SM_TP_INIT_DIST])) tp[SM_TP_INIT_DIST] = tp[SM_TP_LAST_DIST];
         }
     }
-    if (obs) smo_observation_tp(sc, kin, ob, tp, obs);
+    if (obs) {
+        smo_observation_tp(sc, kin, ob, tp, obs);
+        if (H && H->hobs) /* Human.kinematic_observation: the first 3 x 8 entries of the nested env's observation */
+            memcpy(obs + sc->obs_size - 3 * sc->human.n_joints, H->hobs, 3 * sc->human.n_joints * sizeof(float));
+    }
+}
+
+void smo_step_tp(const SmScene* sc, double* kin, double* ob, double* tp, int32_t* episode_length, double* ep_return,
+                 const double* u, const double* next_ball, const double* next_target, float* obs, SmoStepOut* out) {
+    step_core(sc, kin, ob, tp, (SmoHumanIO*)0, episode_length, ep_return, u, next_ball, next_target, obs, out);
+}
+
+/* Human scene: one step of the main env including the nested env of the human */
+void smo_step_human(const SmScene* sc, double* kin, double* ob, SmoHumanIO* H, int32_t* episode_length,
+                    double* ep_return, const double* u, float* obs, SmoStepOut* out) {
+    step_core(sc, kin, ob, (double*)0, H, episode_length, ep_return, u, (const double*)0, (const double*)0, obs, out);
+}
+
+/* batch driver of the Human scene.  hactions [n][8]; next_target [n][3] or NULL; hinfo [n][4] = braked, poses visited by
+ * the braking-trajectory check, first colliding pose (0 none, -1 timeout), reserved */
+void smo_step_batch_human(const SmScene* sc, int n, double* kin, double* ob, double* hkin, double* hstate, double* hbrake,
+                          int32_t* episode, double* ep_return, const float* actions, const float* hactions,
+                          const double* next_target, float* obs, float* hobs, float* reward, uint8_t* done,
+                          int32_t* term, float* info, int32_t* hinfo) {
+    for (int e = 0; e < n; ++e) {
+        double u[SM_MAX_JOINTS], uh[SM_HUMAN_JOINTS];
+        SmoStepOut out;
+        SmoHumanIO H;
+        memset(&H, 0, sizeof(H));
+        for (int j = 0; j < sc->n_joints; ++j) u[j] = (double)actions[e * sc->n_joints + j];
+        for (int j = 0; j < SM_HUMAN_JOINTS; ++j) uh[j] = (double)hactions[e * SM_HUMAN_JOINTS + j];
+        H.hkin = hkin + (size_t)e * SM_KIN_STRIDE;
+        H.hstate = hstate + (size_t)e * SM_HSTATE_STRIDE;
+        H.hbrake = hbrake + (size_t)e * SM_HBRAKE_STEPS * SM_HUMAN_JOINTS;
+        H.uh = uh;
+        H.next_target = next_target ? next_target + (size_t)e * 3 : 0;
+        H.hobs = hobs + (size_t)e * SM_HOBS_STRIDE;
+        smo_step_human(sc, kin + (size_t)e * SM_KIN_STRIDE, ob + (size_t)e * SM_OBST_STRIDE, &H, episode + 4 * e,
+                       ep_return + e, u, obs ? obs + (size_t)e * sc->obs_size : 0, &out);
+        reward[e] = out.reward;
+        done[e] = (uint8_t)out.done;
+        term[e] = out.term_reason;
+        memcpy(info + (size_t)e * SM_INFO_STRIDE, out.info, sizeof(out.info));
+        if (hinfo) { hinfo[4 * e] = H.braked; hinfo[4 * e + 1] = H.brake_poses; hinfo[4 * e + 2] = H.brake_collision; hinfo[4 * e + 3] = 0; }
+    }
 }
 
 void smo_step(const SmScene* sc, double* kin, double* ob, int32_t* episode_length, double* ep_return,

@@ -16,7 +16,11 @@ SM_INFO_STRIDE = 32
 SM_TP_STRIDE = 12
 TP_POS, TP_LAST_DIST, TP_INIT_DIST, TP_ACTIVE, TP_REACHED_N, TP_LINK_POS, TP_DRAWS, TP_REACHED = 0, 3, 4, 5, 6, 7, 10, 11
 
-SM_OBST_NONE, SM_OBST_PLANET, SM_OBST_BALL = 0, 1, 2
+SM_OBST_NONE, SM_OBST_PLANET, SM_OBST_BALL, SM_OBST_HUMAN = 0, 1, 2, 3
+SM_HUMAN_JOINTS, SM_MAX_OBST_FRAMES, SM_MAX_HLINKS, SM_MAX_HPAIRS, SM_HBRAKE_STEPS, SM_HBRAKE_POSES = 8, 9, 16, 256, 24, 72
+SM_HSTATE_STRIDE, SM_HOBS_STRIDE = 32, 40
+HTP_SAMPLE_NEW, HTP_REACHED, HS_BRAKE_COUNT, HS_DRAWS, HS_BRAKED, HS_STEPS = 10, 11, 24, 25, 26, 27
+SM_NET_RISK, SM_NET_BACKUP, SM_NET_HUMAN = 0, 1, 2
 
 # termination reasons (safe_motions_base.py:64-70)
 TERMINATION_UNSET = -1
@@ -42,6 +46,32 @@ dp = C.POINTER(C.c_double)
 class SmShape(C.Structure):
     _fields_ = [("frame", i32), ("vert_off", i32), ("vert_cnt", i32), ("link", i32), ("margin", d),
                 ("center", d * 3), ("radius", d)]
+
+
+class SmHuman(C.Structure):
+    _fields_ = [
+        ("enabled", i32), ("n_joints", i32),
+        ("joint_parent", i32 * SM_HUMAN_JOINTS),
+        ("base_R", d * 9), ("base_t", d * 3),
+        ("joint_R", (d * 9) * SM_HUMAN_JOINTS), ("joint_t", (d * 3) * SM_HUMAN_JOINTS),
+        ("joint_axis", (d * 3) * SM_HUMAN_JOINTS),
+        ("pos_lo", d * SM_HUMAN_JOINTS), ("pos_hi", d * SM_HUMAN_JOINTS), ("vel_max", d * SM_HUMAN_JOINTS),
+        ("acc_max", d * SM_HUMAN_JOINTS), ("jerk_max", d * SM_HUMAN_JOINTS),
+        ("shape_off", i32), ("n_arm_shapes", i32), ("n_shapes", i32),
+        ("shape_link", i32 * 64),
+        ("contact_thresh", (d * SM_MAX_MOV_ROBOT) * SM_MAX_HLINKS),
+        ("check_braking", i32), ("brake_checks", i32), ("n_brake_pairs", i32),
+        ("brake_pairs", (i32 * 2) * SM_MAX_HPAIRS),
+        ("brake_safety", d), ("brake_timeout", d),
+        ("tp_local", (d * 3) * 2),
+        ("tp_box_min", d * 3), ("tp_box_max", d * 3), ("tp_rel_min", d * 3), ("tp_rel_max", d * 3), ("tp_radius", d),
+        ("tp_min_static", d), ("tp_min_self", d),
+        ("log_std_lo", d), ("log_std_hi", d),
+        ("start_box_min", d * 3), ("start_box_max", d * 3),
+        ("kinematic_sampling_probability", d), ("stay_in_state_probability", d),
+        ("min_start_static", d), ("min_start_self", d),
+        ("obs_size", i32), ("reserved", i32),
+    ]
 
 
 class SmScene(C.Structure):
@@ -110,6 +140,7 @@ class SmScene(C.Structure):
         ("tp_box_min", d * 3), ("tp_box_max", d * 3), ("tp_rel_min", d * 3), ("tp_rel_max", d * 3),
         ("tp_min_static", d), ("tp_min_self", d),
         ("reward_scale", d),
+        ("human", SmHuman),
     ]
 
 
@@ -118,6 +149,8 @@ class SmBuffers(C.Structure):
         ("kin", C.c_void_p), ("obst", C.c_void_p), ("episode", C.c_void_p), ("ep_return", C.c_void_p),
         ("actions", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p),
         ("term_reason", C.c_void_p), ("info", C.c_void_p), ("stats", C.c_void_p), ("target", C.c_void_p),
+        ("hkin", C.c_void_p), ("hstate", C.c_void_p), ("hbrake", C.c_void_p), ("hobs", C.c_void_p),
+        ("hactions", C.c_void_p),
     ]
 
 
@@ -134,5 +167,6 @@ EXPORTED_SYMBOLS = [
     "smenv_step", "smenv_step_random", "smenv_step_host", "smenv_set_step_ranges", "smenv_safe_range", "smenv_distances", "smenv_observation",
     "smenv_counters", "smenv_enable_counters", "smenv_launch_count", "smenv_debug_gjk", "smenv_kernel_timing",
     "smenv_kernel_times", "smenv_set_targets", "smenv_mlp_load", "smenv_mlp_forward", "smenv_risk_gate", "smenv_random_actions",
-    "smenv_set_seed", "smenv_set_risk_gate",
+    "smenv_set_seed", "smenv_set_risk_gate", "smenv_set_human_actions_external", "smenv_set_human_state",
+    "smenv_human_pool_sizes", "smenv_copy_human_pools", "smenv_measure_fma_peaks",
 ]

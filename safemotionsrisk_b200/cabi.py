@@ -35,7 +35,7 @@ def load():
     lib.smenv_set_step_ranges.argtypes = [vp, i32]
     lib.smenv_step_host.argtypes = [vp, C.POINTER(abi.SmBuffers), vp, vp, vp, vp, i32, i32, vp]
     lib.smenv_safe_range.argtypes = [vp, vp, vp, vp, vp, i32, vp]
-    lib.smenv_distances.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]
+    lib.smenv_distances.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, vp]
     lib.smenv_observation.argtypes = [vp, C.POINTER(abi.SmBuffers), vp]
     lib.smenv_counters.argtypes = [vp, C.POINTER(abi.SmCounters), i32]
     lib.smenv_enable_counters.argtypes = [vp, i32]
@@ -44,6 +44,11 @@ def load():
     lib.smenv_mlp_load.argtypes = [vp, i32, i32, vp, i32, i32, vp]
     lib.smenv_mlp_forward.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, i32, vp]
     lib.smenv_risk_gate.argtypes = [vp, C.POINTER(abi.SmBuffers), C.c_float, vp, vp, vp]
+    lib.smenv_set_human_actions_external.argtypes = [vp, i32]
+    lib.smenv_set_human_state.argtypes = [vp, C.POINTER(abi.SmBuffers), vp, vp, vp, vp, vp, vp, vp]
+    lib.smenv_human_pool_sizes.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+    lib.smenv_copy_human_pools.argtypes = [vp, vp, vp]
+    lib.smenv_measure_fma_peaks.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.smenv_set_seed.argtypes = [vp, u64]
     lib.smenv_set_risk_gate.argtypes = [vp, C.c_float]
     lib.smenv_random_actions.argtypes = [vp, C.POINTER(abi.SmBuffers), vp]

@@ -211,3 +211,16 @@ def space_task_config(**overrides):
                planet_two_euler_angles=[-0.35, 0, 0], planet_two_radius_xy=[0.75, 0.8], planet_two_time_shift=-2.0)
     cfg.update(overrides)
     return EnvConfig(**cfg)
+
+
+def human_backup_config(**overrides):
+    """The Human backup-policy env (trained_networks/backup_networks/human/params.json; BASELINE.json configs[2]): the
+    iiwa next to a human whose arms are moved by the shipped human policy."""
+    cfg = dict(_BACKUP_COMMON, experiment_name="Backup_Human", trajectory_duration=3.0,
+               human_network_checkpoint="human_network/checkpoint/checkpoint",
+               human_network_use_collision_avoidance_starting_point_sampling=True,
+               human_network_collision_avoidance_kinematic_state_sampling_probability=0.3,
+               human_network_collision_avoidance_stay_in_state_probability=0.3,
+               human_network_use_full_observation=False)
+    cfg.update(overrides)
+    return EnvConfig(**cfg)

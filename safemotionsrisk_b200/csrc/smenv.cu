@@ -11,6 +11,7 @@
 #include "smenv_pools.cuh"
 #include "smenv_step.cuh"
 #include "smenv_mlp.cuh"
+#include "smenv_human.cuh"
 
 static thread_local std::string g_error;
 static int fail(int code, const std::string& msg) {
@@ -167,6 +168,21 @@ struct SmEnv {
     float* d_exec = nullptr;     // [n][n_joints] actions executed when the gate is on (smenv_set_risk_gate)
     uint8_t* d_risky = nullptr;  // [n] 1 where the gate replaced the action
     float gate_threshold = -1.0f;  // < 0: gate off
+    // Human scene (smenv_human.cuh)
+    bool human = false;
+    int human_external = 0;        // the human's actions come from buf->hactions (parity protocol)
+    short* d_hpairs = nullptr;     // pair list of the braking-trajectory check
+    float* d_hthresh = nullptr;    // contact thresholds per (human link, robot contact slot)
+    double* d_hrange = nullptr;    // [n][8][4]
+    double* d_hbacc = nullptr;     // [n][SM_HBRAKE_STEPS][8]
+    float* d_hposes = nullptr;     // [n][SM_HBRAKE_POSES][8]
+    int* d_hbinfo = nullptr;       // [n][4]
+    float* d_hscratch = nullptr;   // [n][SM_SCRATCH_FLOATS]
+    float* d_hpolicy = nullptr;    // [n][16]
+    double* d_hstart_pool = nullptr;   // [start_pool_n][SM_HPOOL_STRIDE]
+    double* d_htarget_pool = nullptr;  // [2][htarget_pool_n][4]
+    int htarget_pool_n = 0;
+    size_t smem_bytes_hplan = 0;
     bool time_kernels = false;   // measurement mode (smenv_kernel_timing)
     cudaEvent_t ev[SM_K_COUNT + 1] = {};
     double kernel_ms[SM_K_COUNT] = {};
@@ -320,10 +336,21 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
             build_hwidth(verts.data() + h.vert_off, h.vert_cnt, cc, g.radius, hwidth);
         }
         g.lut = -1;
-        if (h.vert_cnt >= SM_LUT_MIN_VERTS && h.vert_cnt <= 255) {
-            g.lut = (int)lut.size();
-            build_lut(verts.data() + h.vert_off, h.vert_cnt, lut);
+    }
+    // support-direction tables for the hulls that profit most (many vertices), as long as the GJK kernel's shared-memory
+    // image (vertices + tables + shapes) fits into an SM: the threshold doubles until it does (Human scene: 50 shapes,
+    // 4000 vertices -> tables only for the robot links)
+    for (int min_verts = SM_LUT_MIN_VERTS;; min_verts = 2 * min_verts - 1) {
+        lut.clear();
+        for (int s = 0; s < sc->n_shapes; ++s) {
+            const SmShape& h = sc->shapes[s];
+            d.shapes[s].lut = -1;
+            if (h.vert_cnt >= min_verts && h.vert_cnt <= 255) {
+                d.shapes[s].lut = (int)lut.size();
+                build_lut(verts.data() + h.vert_off, h.vert_cnt, lut);
+            }
         }
+        if (gjk_smem_bytes(sc->n_verts, (int)lut.size() + 4, sc->n_shapes) <= 200 * 1024 || min_verts > 255) break;
     }
     d.n_static_pairs = sc->n_static_pairs; d.n_self_pairs = sc->n_self_pairs;
     d.n_mov_reward = sc->n_mov_reward; d.n_mov_contact = sc->n_mov_contact;
@@ -449,6 +476,103 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     d.ball_high_angle_probability = sc->ball_high_angle_probability; d.plane_z = sc->plane_z;
     d.ball_check_invalid = sc->ball_check_invalid; d.ball_random_initial = sc->ball_random_initial;
     d.has_table = sc->has_table;
+    // ---------------- the human obstacle (SmHuman -> DevHuman)
+    std::vector<short> hpairs;
+    std::vector<float> hthresh;
+    if (sc->human.enabled) {
+        const SmHuman& h = sc->human;
+        DevHuman& u = d.hu;
+        if (h.n_joints != SM_HUMAN_JOINTS) return fail(SM_ERR_SCENE, "the human must have 8 joints");
+        if (sc->n_obstacles != 1 || sc->obst_kind[0] != SM_OBST_HUMAN) return fail(SM_ERR_SCENE, "a human scene has the human as its only moving obstacle");
+        if (h.brake_checks < 1 || h.brake_checks > 7) return fail(SM_ERR_SCENE, "human brake_checks must be in 1..7");
+        if (h.brake_checks * 22 > SM_HBRAKE_POSES) return fail(SM_ERR_SCENE, "too many collision checks per step for the pose buffer");
+        for (int j = 0; j < 8; ++j)
+            if (h.joint_parent[j] != ((j & 3) == 0 ? 0 : j)) return fail(SM_ERR_SCENE, "the human is expected as two serial arms of four joints");
+        env->human = true;
+        u.enabled = 1; u.n_joints = h.n_joints; u.check_braking = h.check_braking; u.brake_checks = h.brake_checks;
+        u.n_brake_pairs = h.n_brake_pairs; u.shape_off = h.shape_off; u.n_arm_shapes = h.n_arm_shapes; u.n_shapes = h.n_shapes;
+        for (int i = 0; i < 9; ++i) u.baseR[i] = (float)h.base_R[i];
+        for (int i = 0; i < 3; ++i) u.baset[i] = (float)h.base_t[i];
+        for (int j = 0; j < 8; ++j) {
+            u.joint_parent[j] = h.joint_parent[j];
+            for (int i = 0; i < 9; ++i) u.jR[j][i] = (float)h.joint_R[j][i];
+            for (int i = 0; i < 3; ++i) { u.jt[j][i] = (float)h.joint_t[j][i]; u.jaxis[j][i] = (float)h.joint_axis[j][i]; }
+            u.lim.pos_lo[j] = h.pos_lo[j]; u.lim.pos_hi[j] = h.pos_hi[j]; u.lim.vel_max[j] = h.vel_max[j];
+            u.lim.acc_max[j] = h.acc_max[j]; u.lim.jerk_max[j] = h.jerk_max[j];
+        }
+        u.brake_safety = h.brake_safety; u.brake_timeout = h.brake_timeout; u.tp_radius = h.tp_radius;
+        u.log_std_lo = h.log_std_lo; u.log_std_hi = h.log_std_hi;
+        for (int i = 0; i < 3; ++i) {
+            u.tp_box_min[i] = h.tp_box_min[i]; u.tp_box_max[i] = h.tp_box_max[i];
+            u.tp_rel_min[i] = h.tp_rel_min[i]; u.tp_rel_max[i] = h.tp_rel_max[i];
+            u.start_box_min[i] = h.start_box_min[i]; u.start_box_max[i] = h.start_box_max[i];
+            for (int r = 0; r < 2; ++r) u.tp_local[r][i] = (float)h.tp_local[r][i];
+        }
+        u.kinematic_sampling_probability = h.kinematic_sampling_probability;
+        u.stay_in_state_probability = h.stay_in_state_probability;
+        u.min_start_static = h.min_start_static; u.min_start_self = h.min_start_self;
+        u.tp_min_static = h.tp_min_static; u.tp_min_self = h.tp_min_self;
+        {   // np.linspace(ts / C, ts, C) of the braking-trajectory check (ctlp.py:3166-3168), operation by operation
+            const int C = h.brake_checks;
+            volatile double start = sc->ts / (double)C;
+            volatile double step = C > 1 ? (sc->ts - start) / (double)(C - 1) : 0.0;
+            for (int m = 1; m <= C; ++m) {
+                volatile double prod = (double)(m - 1) * step;
+                u.brake_t[m] = (C <= 1 || m == C) ? sc->ts : start + prod;
+            }
+        }
+        for (int s = 0; s < h.n_shapes && s < 64; ++s) u.shape_link[s] = (unsigned char)h.shape_link[s];
+        float tmax = 0.f;
+        hthresh.resize((size_t)SM_MAX_HLINKS * SM_MAX_MOV_ROBOT, 0.f);
+        for (int l = 0; l < SM_MAX_HLINKS; ++l)
+            for (int r = 0; r < SM_MAX_MOV_ROBOT; ++r) {
+                hthresh[(size_t)l * SM_MAX_MOV_ROBOT + r] = (float)h.contact_thresh[l][r];
+                tmax = fmaxf(tmax, (float)h.contact_thresh[l][r]);
+            }
+        u.contact_thresh_max = tmax;
+        for (int i = 0; i < h.n_brake_pairs; ++i) { hpairs.push_back((short)h.brake_pairs[i][0]); hpairs.push_back((short)h.brake_pairs[i][1]); }
+        // link groups: runs of consecutive human shapes in the same frame, with a bounding sphere in frame coordinates
+        int ng = 0;
+        for (int s = 0; s < h.n_shapes;) {
+            const int fr = sc->shapes[h.shape_off + s].frame;
+            int e = s;
+            while (e < h.n_shapes && sc->shapes[h.shape_off + e].frame == fr) ++e;
+            if (ng >= SM_HGROUPS) return fail(SM_ERR_SCENE, "the human has more link groups than expected");
+            float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+            for (int q = s; q < e; ++q) {
+                const SmShape& sh = sc->shapes[h.shape_off + q];
+                for (int i = sh.vert_off; i < sh.vert_off + sh.vert_cnt; ++i)
+                    for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], (float)sc->verts[3 * i + k]); hi[k] = fmaxf(hi[k], (float)sc->verts[3 * i + k]); }
+            }
+            float cc[3], rad = 0.f, mrg = 0.f;
+            for (int k = 0; k < 3; ++k) cc[k] = 0.5f * (lo[k] + hi[k]);
+            for (int q = s; q < e; ++q) {
+                const SmShape& sh = sc->shapes[h.shape_off + q];
+                mrg = fmaxf(mrg, (float)sh.margin);
+                for (int i = sh.vert_off; i < sh.vert_off + sh.vert_cnt; ++i) {
+                    const float dx = (float)sc->verts[3 * i] - cc[0], dy = (float)sc->verts[3 * i + 1] - cc[1], dz = (float)sc->verts[3 * i + 2] - cc[2];
+                    rad = fmaxf(rad, sqrtf(dx * dx + dy * dy + dz * dz));
+                }
+            }
+            u.grp_frame[ng] = fr - 100; u.grp_off[ng] = s; u.grp_cnt[ng] = e - s;
+            for (int k = 0; k < 3; ++k) u.grp_c[ng][k] = cc[k];
+            u.grp_r[ng] = rad * (1.0f + 1e-6f) + mrg + 1e-6f;
+            const float cn = sqrtf(cc[0] * cc[0] + cc[1] * cc[1] + cc[2] * cc[2]);
+            for (int j = 0; j < 8; ++j) {
+                float rho = 0.f;
+                const int jf = fr - 101;   // the joint that moves the group's frame (-1: the base)
+                if (jf >= 0 && (j >> 2) == (jf >> 2) && j <= jf) {
+                    rho = cn;
+                    for (int i = j + 1; i <= jf; ++i) rho += sqrtf(u.jt[i][0] * u.jt[i][0] + u.jt[i][1] * u.jt[i][1] + u.jt[i][2] * u.jt[i][2]);
+                    rho *= 1.0f + 1e-5f;
+                }
+                u.grp_rho[ng][j] = rho;
+            }
+            ++ng;
+            s = e;
+        }
+        for (int g = ng; g < SM_HGROUPS; ++g) { u.grp_frame[g] = 0; u.grp_off[g] = 0; u.grp_cnt[g] = 0; u.grp_r[g] = -1e9f; }
+    }
 
     int rc = upload(&env->d_verts, verts);
     if (rc) return rc;
@@ -459,6 +583,23 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     if ((rc = upload(&env->d_hwidth, hwidth))) { return rc; }
     d.hwidth = env->d_hwidth;
     d.n_lut_words = (int)lut.size();
+    if (env->human) {
+        if ((rc = upload(&env->d_hpairs, hpairs))) return rc;
+        if ((rc = upload(&env->d_hthresh, hthresh))) return rc;
+        d.hu.brake_pairs = env->d_hpairs;
+        d.hu.contact_thresh = env->d_hthresh;
+        const size_t N = (size_t)num_envs;
+        CU(cudaMalloc((void**)&env->d_hrange, N * 8 * 4 * sizeof(double)));
+        CU(cudaMalloc((void**)&env->d_hbacc, N * SM_HBRAKE_STEPS * 8 * sizeof(double)));
+        CU(cudaMalloc((void**)&env->d_hposes, N * SM_HBRAKE_POSES * 8 * sizeof(float)));
+        CU(cudaMalloc((void**)&env->d_hbinfo, N * 4 * sizeof(int)));
+        CU(cudaMemset(env->d_hbinfo, 0, N * 4 * sizeof(int)));
+        CU(cudaMalloc((void**)&env->d_hscratch, N * SM_SCRATCH_FLOATS * sizeof(float)));
+        CU(cudaMemset(env->d_hscratch, 0, N * SM_SCRATCH_FLOATS * sizeof(float)));
+        CU(cudaMalloc((void**)&env->d_hpolicy, N * 16 * sizeof(float)));
+        CU(cudaMemset(env->d_hpolicy, 0, N * 16 * sizeof(float)));
+        env->smem_bytes_hplan = sizeof(HumanBlockShared);
+    }
     for (int o = 0; o < sc->n_obstacles; ++o) {
         if (sc->obst_kind[o] != SM_OBST_PLANET) continue;
         std::vector<float4> pp(sc->planet_steps), pq(sc->planet_steps);
@@ -498,6 +639,13 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     CU(cudaMalloc((void**)&env->d_start_pool, (size_t)env->start_pool_n * SM_POOL_STRIDE * sizeof(double)));
     CU(cudaMemset(env->d_start_pool, 0, (size_t)env->start_pool_n * SM_POOL_STRIDE * sizeof(double)));
     if (env->ball_pool_n) CU(cudaMalloc((void**)&env->d_ball_pool, (size_t)env->ball_pool_n * SM_BALL_STRIDE * sizeof(double)));
+    if (env->human) {
+        env->htarget_pool_n = 2 * env->start_pool_n;
+        CU(cudaMalloc((void**)&env->d_hstart_pool, (size_t)env->start_pool_n * SM_HPOOL_STRIDE * sizeof(double)));
+        CU(cudaMemset(env->d_hstart_pool, 0, (size_t)env->start_pool_n * SM_HPOOL_STRIDE * sizeof(double)));
+        CU(cudaMalloc((void**)&env->d_htarget_pool, (size_t)2 * env->htarget_pool_n * 4 * sizeof(double)));
+        CU(cudaMemset(env->d_htarget_pool, 0, (size_t)2 * env->htarget_pool_n * 4 * sizeof(double)));
+    }
     if (sc->use_target_points) {
         env->target_pool_n = 4 * env->start_pool_n;
         CU(cudaMalloc((void**)&env->d_target_pool, (size_t)env->target_pool_n * 4 * sizeof(double)));
@@ -555,6 +703,7 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
             CU(cudaFuncSetAttribute(fill_target_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
             CU(cudaFuncSetAttribute(distances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
             CU(cudaFuncSetAttribute(debug_gjk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
+            CU(cudaFuncSetAttribute(fill_human_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes));
             lim_geom = env->smem_bytes;
         }
     }
@@ -593,6 +742,8 @@ extern "C" int smenv_destroy(SmEnv* env) {
     if (env->h_flag) cudaFreeHost(env->h_flag);
     for (void* q : env->net_allocs) cudaFree(q);
     cudaFree(env->d_risk); cudaFree(env->d_backup); cudaFree(env->d_exec); cudaFree(env->d_risky);
+    cudaFree(env->d_hpairs); cudaFree(env->d_hthresh); cudaFree(env->d_hrange); cudaFree(env->d_hbacc); cudaFree(env->d_hposes);
+    cudaFree(env->d_hbinfo); cudaFree(env->d_hscratch); cudaFree(env->d_hpolicy); cudaFree(env->d_hstart_pool); cudaFree(env->d_htarget_pool);
     for (int i = 0; i <= SM_K_COUNT; ++i) if (env->ev[i]) cudaEventDestroy(env->ev[i]);
     for (int c = 0; c < 8; ++c) {
         if (env->chunk_streams[c]) cudaStreamDestroy(env->chunk_streams[c]);
@@ -648,7 +799,15 @@ extern "C" int smenv_fill_pools(SmEnv* env, uint64_t seed, SmStream s) {
     cudaStream_t stream = (cudaStream_t)s;
     DevLock dev_lock_(env); int rc = activate(env, stream);
     if (rc) return rc;
-    PoolArgs A{env->d_start_pool, env->start_pool_n, env->d_ball_pool, env->ball_pool_n, (uint32_t)seed, (uint32_t)(seed >> 32)};
+    PoolArgs A{env->d_start_pool, env->start_pool_n, env->d_ball_pool, env->ball_pool_n, (uint32_t)seed, (uint32_t)(seed >> 32),
+               env->human ? env->d_hstart_pool : nullptr};
+    if (env->human) {   // the nested env's pools first: the robot's start poses keep clear of the human's
+        HumanPoolArgs H{env->d_hstart_pool, env->start_pool_n, env->d_htarget_pool, env->htarget_pool_n, (uint32_t)seed,
+                        (uint32_t)(seed >> 32)};
+        fill_human_pool_kernel<<<grid_for(env, env->start_pool_n + 2 * env->htarget_pool_n), SM_WARPS_PER_BLOCK * 32,
+                                 env->smem_bytes, stream>>>(H);
+        env->launches++;
+    }
     if (env->ball_pool_n) {
         fill_ball_pool_kernel<<<grid_for(env, env->ball_pool_n), SM_WARPS_PER_BLOCK * 32, env->smem_bytes, stream>>>(A);
         env->launches++;
@@ -794,7 +953,83 @@ extern "C" int smenv_reset(SmEnv* env, const SmBuffers* buf, const uint8_t* mask
                 (uint32_t)env->seed, (uint32_t)(env->seed >> 32)};
     reset_kernel<<<(env->n * 32 + 255) / 256, 256, 0, stream>>>(A);
     env->launches++;
+    if (env->human) {
+        if (!buf->hkin || !buf->hstate || !buf->hbrake || !buf->hobs)
+            return fail(SM_ERR_ARG, "smenv_reset: the Human scene needs the hkin / hstate / hbrake / hobs buffers");
+        HumanArgs H;
+        memset(&H, 0, sizeof(H));
+        H.buf = *buf; H.n = env->n; H.env_base = 0; H.k0 = (uint32_t)env->seed; H.k1 = (uint32_t)(env->seed >> 32);
+        H.mask = mask; H.start_pool = env->d_hstart_pool; H.start_pool_n = env->start_pool_n;
+        H.target_pool = env->d_htarget_pool; H.target_pool_n = env->htarget_pool_n;
+        human_reset_kernel<<<(env->n + 255) / 256, 256, 0, stream>>>(H, 0);
+        env->launches++;
+    }
     CU(cudaGetLastError());
+    return SM_OK;
+}
+
+extern "C" int smenv_set_human_actions_external(SmEnv* env, int external) {
+    if (!env) return fail(SM_ERR_ARG, "null env");
+    if (!env->human) return fail(SM_ERR_STATE, "smenv_set_human_actions_external: the scene has no human");
+    env->human_external = external != 0;
+    if (env->host_graph) { cudaGraphExecDestroy(env->host_graph); env->host_graph = nullptr; }
+    return SM_OK;
+}
+
+extern "C" int smenv_human_pool_sizes(SmEnv* env, int* start_pool, int* target_pool) {
+    if (!env) return fail(SM_ERR_ARG, "null env");
+    if (start_pool) *start_pool = env->human ? env->start_pool_n : 0;
+    if (target_pool) *target_pool = env->human ? env->htarget_pool_n : 0;
+    return SM_OK;
+}
+
+extern "C" int smenv_copy_human_pools(SmEnv* env, double* host_start, double* host_target) {
+    if (!env) return fail(SM_ERR_ARG, "null env");
+    if (!env->human) return fail(SM_ERR_STATE, "smenv_copy_human_pools: the scene has no human");
+    CU(cudaSetDevice(env->device));
+    CU(cudaDeviceSynchronize());
+    if (host_start)
+        CU(cudaMemcpy(host_start, env->d_hstart_pool, (size_t)env->start_pool_n * SM_HPOOL_STRIDE * sizeof(double), cudaMemcpyDeviceToHost));
+    if (host_target)
+        CU(cudaMemcpy(host_target, env->d_htarget_pool, (size_t)2 * env->htarget_pool_n * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+    return SM_OK;
+}
+
+extern "C" int smenv_set_human_state(SmEnv* env, const SmBuffers* buf, const double* hq, const double* hv, const double* ha,
+                                     const double* first_target, const int32_t* active_arm, const uint8_t* mask, SmStream s) {
+    if (!env || !buf || !hq || !hv || !ha || !first_target) return fail(SM_ERR_ARG, "smenv_set_human_state: null argument");
+    if (!env->human) return fail(SM_ERR_STATE, "smenv_set_human_state: the scene has no human");
+    if (!buf->hkin || !buf->hstate || !buf->hbrake || !buf->hobs) return fail(SM_ERR_ARG, "smenv_set_human_state: human buffers missing");
+    cudaStream_t stream = (cudaStream_t)s;
+    DevLock dev_lock_(env); int rc = activate(env, stream);
+    if (rc) return rc;
+    const int n = env->n;
+    std::vector<void*> tmp;
+    auto stage = [&](const void* p, size_t bytes, const void** out) -> int {
+        if (!p || is_device_ptr(p)) { *out = p; return SM_OK; }
+        void* dptr = nullptr;
+        CU(cudaMalloc(&dptr, bytes));
+        tmp.push_back(dptr);
+        CU(cudaMemcpyAsync(dptr, p, bytes, cudaMemcpyHostToDevice, stream));
+        *out = dptr;
+        return SM_OK;
+    };
+    const void *dq, *dv, *da, *dt, *dar, *dm;
+    if ((rc = stage(hq, (size_t)n * 64, &dq)) || (rc = stage(hv, (size_t)n * 64, &dv)) || (rc = stage(ha, (size_t)n * 64, &da)) ||
+        (rc = stage(first_target, (size_t)n * 24, &dt)) || (rc = stage(active_arm, (size_t)n * 4, &dar)) ||
+        (rc = stage(mask, (size_t)n, &dm)))
+        return rc;
+    HumanArgs H;
+    memset(&H, 0, sizeof(H));
+    H.buf = *buf; H.n = n; H.mask = (const uint8_t*)dm;
+    human_set_state_kernel<<<(n + 255) / 256, 256, 0, stream>>>(H, (const double*)dq, (const double*)dv, (const double*)da,
+                                                               (const double*)dt, (const int32_t*)dar);
+    env->launches++;
+    CU(cudaGetLastError());
+    if (!tmp.empty()) {
+        CU(cudaStreamSynchronize(stream));
+        for (void* p : tmp) cudaFree(p);
+    }
     return SM_OK;
 }
 
@@ -814,6 +1049,11 @@ static SmBuffers buffers_at(const SmBuffers& b, int e0, int nj, int obs_size) {
     if (b.term_reason) o.term_reason = b.term_reason + e0;
     if (b.info) o.info = b.info + (size_t)e0 * SM_INFO_STRIDE;
     if (b.target) o.target = b.target + (size_t)e0 * SM_TP_STRIDE;
+    if (b.hkin) o.hkin = b.hkin + (size_t)e0 * SM_KIN_STRIDE;
+    if (b.hstate) o.hstate = b.hstate + (size_t)e0 * SM_HSTATE_STRIDE;
+    if (b.hbrake) o.hbrake = b.hbrake + (size_t)e0 * SM_HBRAKE_STEPS * SM_HUMAN_JOINTS;
+    if (b.hobs) o.hobs = b.hobs + (size_t)e0 * SM_HOBS_STRIDE;
+    if (b.hactions) o.hactions = b.hactions + (size_t)e0 * SM_HUMAN_JOINTS;
     return o;
 }
 
@@ -884,6 +1124,9 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
     JA.hpar = env->d_hpar + (size_t)e0 * 8 * SM_HPAR;
     JA.counters = env->count ? env->d_counters : nullptr;
     JA.exec = nullptr;
+    JA.set = 0; JA.nj = env->host_scene.n_joints; JA.defer = 0; JA.range_out = nullptr;
+    JA.track_vel = env->host_scene.track_vel; JA.store_qset = env->host_scene.use_target_points;
+    JA.keep_overflow = env->human ? 1 : 0;
     const bool gate = env->gate_threshold >= 0.0f;
     if (gate) {   // actions.py:303-340: rate the proposed action, execute the backup policy's where it is risky
         if (!buf->obs) return fail(SM_ERR_ARG, "smenv_step: the risk gate needs the observation buffer");
@@ -912,6 +1155,74 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
                                              cudaGetErrorString(e_));                                        \
         }                                                                                                    \
     } while (0)
+    HumanArgs HA;
+    memset(&HA, 0, sizeof(HA));
+    if (!env->human && tk)
+        for (int i = SM_K_HUMAN_POLICY; i < SM_K_JOINT; ++i) cudaEventRecord(env->ev[i], stream);
+    if (env->human) {
+        // ---------------- the nested env of the human up to its setpoints (Human.step, ctlp.py:4818-4840)
+        if (!buf->hkin || !buf->hstate || !buf->hbrake || !buf->hobs || !buf->hactions)
+            return fail(SM_ERR_ARG, "smenv_step: the Human scene needs the hkin / hstate / hbrake / hobs / hactions buffers");
+        HA.buf = *buf; HA.n = m; HA.env_base = e0;
+        HA.k0 = (uint32_t)env->seed; HA.k1 = (uint32_t)(env->seed >> 32); HA.step_counter = step_counter;
+        HA.policy_out = env->d_hpolicy + (size_t)e0 * 16;
+        HA.range = env->d_hrange + (size_t)e0 * 32;
+        HA.bacc = env->d_hbacc + (size_t)e0 * SM_HBRAKE_STEPS * 8;
+        HA.poses = env->d_hposes + (size_t)e0 * SM_HBRAKE_POSES * 8;
+        HA.binfo = env->d_hbinfo + (size_t)e0 * 4;
+        HA.hscratch = env->d_hscratch + (size_t)e0 * SM_SCRATCH_FLOATS;
+        HA.scratch = scratch;
+        HA.items = items; HA.item_count = worklist; HA.capacity = capacity; HA.overflow = worklist + 1;
+        HA.res = res;
+        HA.target_pool = env->pools_filled ? env->d_htarget_pool : nullptr;
+        HA.target_pool_n = env->pools_filled ? env->htarget_pool_n : 0;
+        HA.start_pool = env->pools_filled ? env->d_hstart_pool : nullptr;
+        HA.start_pool_n = env->pools_filled ? env->start_pool_n : 0;
+        HA.cwork = cwork;
+        HA.counters = env->count ? env->d_counters : nullptr;
+        SM_MARK(SM_K_HUMAN_POLICY);
+        if (!env->human_external) {
+            if (!env->net_loaded[SM_NET_HUMAN])
+                return fail(SM_ERR_STATE, "smenv_step: load the human's policy (smenv_mlp_load, SM_NET_HUMAN) or supply its "
+                                          "actions (smenv_set_human_actions_external)");
+            int rcm = mlp_launch(env, SM_NET_HUMAN, MlpSeg{buf->hobs, SM_HOBS_STRIDE, env->nets[SM_NET_HUMAN].n_in},
+                                 MlpSeg{nullptr, 0, 0}, MlpSeg{nullptr, 0, 0}, env->d_hpolicy + (size_t)e0 * 16, 16, m, stream);
+            if (rcm) return rcm;
+            human_action_kernel<<<(m * 8 + 255) / 256, 256, 0, stream>>>(HA);
+            env->launches++;
+        }
+        JointArgs JH = JA;
+        JH.set = 1; JH.nj = SM_HUMAN_JOINTS; JH.defer = 1; JH.range_out = HA.range; JH.random_actions = 0; JH.exec = nullptr;
+        JH.track_vel = 0.87; JH.store_qset = 1; JH.keep_overflow = 0;
+        JH.scratch = HA.hscratch;
+        const int hb = std::min((m * 8 + SM_HEAVY_THREADS - 1) / SM_HEAVY_THREADS, 8 * env->sms);
+        SM_MARK(SM_K_HUMAN_JOINT);
+        joint_kernel<<<(m * 8 + 255) / 256, 256, 0, stream>>>(JH);
+        joint_first_kernel<<<hb, SM_HEAVY_THREADS, 0, stream>>>(JH);
+        joint_solve_kernel<<<16 * env->sms, SM_HEAVY_THREADS, 0, stream>>>(JH);
+        joint_final_kernel<<<hb, SM_HEAVY_THREADS, 0, stream>>>(JH);
+        CU(cudaMemsetAsync(heavy, 0, sizeof(int), stream));   // the robot's pass reuses the deferred-joint list
+        SM_MARK(SM_K_HUMAN_BRAKE_TRAJ);
+        human_brake_traj_kernel<<<(m * 8 + 127) / 128, 128, 0, stream>>>(HA);
+        env->launches += 5;
+        SM_MARK(SM_K_HUMAN_BRAKE_PLAN);
+        if (env->host_scene.hu.check_braking) {
+            const int blocks_h = (m + SM_WARPS_PER_BLOCK - 1) / SM_WARPS_PER_BLOCK;
+            human_brake_plan_kernel<<<std::min(blocks_h, 4 * env->sms), SM_WARPS_PER_BLOCK * 32, env->smem_bytes_hplan, stream>>>(HA);
+            SM_MARK(SM_K_HUMAN_BRAKE_GJK);
+            GjkArgs GB;
+            GB.items = items; GB.n_items = worklist; GB.capacity = capacity; GB.res = res; GB.counters = env->d_counters;
+            if (env->count) gjk_kernel<true><<<env->grid_gjk, GJK_THREADS, env->smem_bytes_gjk, stream>>>(GB);
+            else gjk_kernel<false><<<env->grid_gjk, GJK_THREADS, env->smem_bytes_gjk, stream>>>(GB);
+            env->launches += 2;
+        }
+        else SM_MARK(SM_K_HUMAN_BRAKE_GJK);
+        SM_MARK(SM_K_HUMAN_ADVANCE);
+        human_advance_kernel<<<(m * 8 + 255) / 256, 256, 0, stream>>>(HA);
+        human_outcome_kernel<<<(m * 8 + 255) / 256, 256, 0, stream>>>(HA);
+        env->launches += 2;
+        CU(cudaGetLastError());
+    }
     SM_MARK(SM_K_JOINT);
     joint_kernel<<<(m * 8 + 255) / 256, 256, 0, stream>>>(JA);
     SM_MARK(SM_K_JOINT_HEAVY);
@@ -930,6 +1241,7 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
     P.kin = buf->kin; P.obst = buf->obst; P.advance = 1; P.counters = env->d_counters;
     P.cwork = cwork;
     P.target = buf->target;
+    P.hkin = buf->hkin;
     GjkArgs G;
     G.items = items; G.n_items = worklist; G.capacity = capacity; G.res = res;
     G.counters = env->d_counters;
@@ -967,7 +1279,11 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
         CU(cudaEventRecord(env->side_fork[chunk], stream));
         CU(cudaStreamWaitEvent(cstream, env->side_fork[chunk], 0));
     }
-    if (contacts) {
+    if (contacts && env->human) {
+        const int grid_c = (m * SM_COARSE_LANES + 255) / 256;
+        hcontact_coarse_kernel<<<grid_c, 256, sizeof(SceneSmem), cstream>>>(HA);
+        hcontact_plan_kernel<<<grid_p, T, sizeof(SceneSmem), cstream>>>(HA);
+    } else if (contacts) {
         const int grid_c = (m * SM_COARSE_LANES + 255) / 256;
         if (env->count) {
             contact_coarse_kernel<true><<<grid_c, 256, env->smem_bytes_broad, cstream>>>(P);
@@ -990,6 +1306,10 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
     SM_MARK(SM_K_FINISH);
     if (env->count) finish_kernel<true><<<grid_f, 256, 0, stream>>>(A);
     else finish_kernel<false><<<grid_f, 256, 0, stream>>>(A);
+    if (env->human && auto_reset && env->pools_filled) {   // the nested env restarts with the main env
+        human_reset_kernel<<<(m + 255) / 256, 256, 0, stream>>>(HA, 1);
+        env->launches++;
+    }
     SM_MARK(SM_K_COUNT);
 #undef SM_MARK
     env->launches += contacts ? 5 : 3;
@@ -1196,8 +1516,8 @@ extern "C" int smenv_safe_range(SmEnv* env, const double* kin, double* lo, doubl
     return SM_OK;
 }
 
-extern "C" int smenv_distances(SmEnv* env, const double* kin, const double* obst, float* d_static, float* d_self,
-                               float* d_moving, int n, SmStream s) {
+extern "C" int smenv_distances(SmEnv* env, const double* kin, const double* obst, const double* hkin, float* d_static,
+                               float* d_self, float* d_moving, int n, SmStream s) {
     if (!env || !kin || !obst || !d_static || !d_self || !d_moving) return fail(SM_ERR_ARG, "smenv_distances: null argument");
     if (n > env->n) return fail(SM_ERR_ARG, "smenv_distances: n exceeds the env count the buffers were sized for");
     cudaStream_t stream = (cudaStream_t)s;
@@ -1211,6 +1531,8 @@ extern "C" int smenv_distances(SmEnv* env, const double* kin, const double* obst
     P.items = env->d_items; P.item_count = env->d_worklist; P.capacity = env->item_capacity;
     P.overflow = env->d_worklist + 1; P.res = env->d_res;
     P.kin = kin; P.obst = obst; P.advance = 0; P.counters = env->d_counters;
+    P.hkin = hkin;
+    if (env->human && !hkin) return fail(SM_ERR_ARG, "smenv_distances: the Human scene needs the human's joint state");
     GjkArgs G;
     G.items = env->d_items; G.n_items = env->d_worklist; G.capacity = env->item_capacity; G.res = env->d_res;
     G.counters = env->d_counters;
@@ -1412,4 +1734,57 @@ extern "C" int smenv_debug_gjk(SmEnv* env, const double* kin_host, const double*
     CU(cudaMemcpy(trace_host, dt, 256 * 4, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(result_host, dr, 128 * 4, cudaMemcpyDeviceToHost));
     cudaFree(dk); cudaFree(dob); cudaFree(dt); cudaFree(dr);
     return SM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// measured peaks of the vector pipes (bench.py's roofline denominators): dependent-free FMA chains, 8 accumulators per
+// thread, all SMs filled; flops = 2 per FMA
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T b) {
+    T x0 = (T)threadIdx.x, x1 = x0 + (T)1, x2 = x0 + (T)2, x3 = x0 + (T)3, x4 = x0 + (T)4, x5 = x0 + (T)5, x6 = x0 + (T)6, x7 = x0 + (T)7;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = x0 * a + b; x1 = x1 * a + b; x2 = x2 * a + b; x3 = x3 * a + b;
+            x4 = x4 * a + b; x5 = x5 * a + b; x6 = x6 * a + b; x7 = x7 * a + b;
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+template <typename T>
+static int measure_fma(int sms, int iters, double* tflops) {
+    const int blocks = sms * 8, threads = 256;
+    T* d = nullptr;
+    CU(cudaMalloc((void**)&d, (size_t)blocks * threads * sizeof(T)));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    fma_peak_kernel<T><<<blocks, threads>>>(d, iters / 8, (T)0.999, (T)0.001);   // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(cudaEventRecord(e0));
+        fma_peak_kernel<T><<<blocks, threads>>>(d, iters, (T)0.999, (T)0.001);
+        CU(cudaEventRecord(e1));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = 2.0 * 64.0 * (double)iters * (double)blocks * threads;
+        if (ms > 0.f && fl / (ms * 1e-3) / 1e12 > best) best = fl / (ms * 1e-3) / 1e12;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = best;
+    return SM_OK;
+}
+
+extern "C" int smenv_measure_fma_peaks(int device, double* tflops_fp32, double* tflops_fp64) {
+    if (!tflops_fp32 || !tflops_fp64) return fail(SM_ERR_ARG, "smenv_measure_fma_peaks: null argument");
+    CU(cudaSetDevice(device));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    int rc = measure_fma<float>(sms, 4096, tflops_fp32);
+    if (rc) return rc;
+    return measure_fma<double>(sms, 1024, tflops_fp64);
 }

@@ -56,13 +56,49 @@ __host__ __device__ __forceinline__ int lut_cell(float dx, float dy, float dz) {
     return (face * SM_LUT_RES + iu) * SM_LUT_RES + iw;
 }
 
+// limits of one set of joints: the robot's, or the human's (nested env, ctlp.py:4647-4959)
+struct JointLim {
+    double pos_lo[SM_MAX_JOINTS], pos_hi[SM_MAX_JOINTS], vel_max[SM_MAX_JOINTS], acc_max[SM_MAX_JOINTS],
+        jerk_max[SM_MAX_JOINTS];
+};
+
+// the human obstacle (include/smenv.h SmHuman) as the kernels use it
+#define SM_HGROUPS 5 /* human link groups of the coarse tests: trunk, upper arm / forearm + hand of each arm */
+struct DevHuman {
+    int enabled, n_joints, check_braking, brake_checks, n_brake_pairs, shape_off, n_arm_shapes, n_shapes;
+    int joint_parent[SM_HUMAN_JOINTS];
+    float baseR[9], baset[3];
+    float jR[SM_HUMAN_JOINTS][9], jt[SM_HUMAN_JOINTS][3], jaxis[SM_HUMAN_JOINTS][3];
+    JointLim lim;
+    double brake_safety, brake_timeout, tp_radius, log_std_lo, log_std_hi;
+    double tp_box_min[3], tp_box_max[3], tp_rel_min[3], tp_rel_max[3];
+    double brake_t[8];                 // np.linspace(ts / C, ts, C) of the braking-trajectory check (ctlp.py:3166-3168)
+    float tp_local[2][3];
+    float tp_rho[2][4];                // bound on |d target link point of arm r / d q_(4 r + i)|
+    const short* brake_pairs;          // device [n_brake_pairs][2]
+    const float* contact_thresh;       // device [SM_MAX_HLINKS][SM_MAX_MOV_ROBOT]
+    unsigned char shape_link[64];
+    // link groups: the shapes of one human frame (frames 0, 3, 4, 7, 8 carry shapes), bounding sphere in frame coordinates
+    int grp_frame[SM_HGROUPS], grp_off[SM_HGROUPS], grp_cnt[SM_HGROUPS];   // shape ranges are contiguous per group
+    float grp_c[SM_HGROUPS][3], grp_r[SM_HGROUPS];
+    float grp_rho[SM_HGROUPS][SM_HUMAN_JOINTS];   // bound on |d group centre / d q_j|
+    float contact_thresh_max;
+    double start_box_min[3], start_box_max[3], kinematic_sampling_probability, stay_in_state_probability,
+        min_start_static, min_start_self, tp_min_static, tp_min_self;
+};
+
 struct DevScene {
     int n_joints, substeps, contact_stride, limit_velocity, limit_position;
     int joint_parent[SM_MAX_JOINTS];
     float jR[SM_MAX_JOINTS][9], jt[SM_MAX_JOINTS][3], jaxis[SM_MAX_JOINTS][3];
     int jr_identity;   // bit j: the fixed rotation of joint j is exactly the identity (all iiwa joints: rpy = 0)
-    double pos_lo[SM_MAX_JOINTS], pos_hi[SM_MAX_JOINTS], vel_max[SM_MAX_JOINTS], acc_max[SM_MAX_JOINTS],
-        jerk_max[SM_MAX_JOINTS];
+    union {
+        struct {
+            double pos_lo[SM_MAX_JOINTS], pos_hi[SM_MAX_JOINTS], vel_max[SM_MAX_JOINTS], acc_max[SM_MAX_JOINTS],
+                jerk_max[SM_MAX_JOINTS];
+        };
+        JointLim lim;   // the same five arrays as one record
+    };
     double ts, action_mapping_factor, track_kp, track_vel;
     double sub_t[33];  // np.linspace(ts / S, ts, S)[k - 1] at index k (actions.py:420-421), computed on the host
     int n_shapes, n_verts;
@@ -119,6 +155,7 @@ struct DevScene {
     const float* hwidth;  // device
     const uint32_t* lut;  // device, n_lut_words (support-direction tables of all shapes that have one)
     int n_lut_words;
+    DevHuman hu;
 };
 
 // the library is one translation unit (smenv.cu), so the constant-memory scene is defined here
@@ -335,9 +372,9 @@ __device__ __forceinline__ bool pos_bound_inactive(double p, double v, double a,
 
 // Cheap part of the range: jerk, acceleration and velocity bounds.  Returns through need_pos whether one of the two
 // position bounds may be active (then safe_range_joint has to run the iterative solve).
-__device__ __forceinline__ void safe_range_light(int j, double p, double v, double a, double& lo, double& hi, int& code,
-                                                 bool& need_pos) {
-    double ts = c_sc.ts, J = c_sc.jerk_max[j], A = c_sc.acc_max[j], V = c_sc.vel_max[j];
+__device__ __forceinline__ void safe_range_light(const JointLim& L, int j, double p, double v, double a, double& lo,
+                                                 double& hi, int& code, bool& need_pos) {
+    double ts = c_sc.ts, J = L.jerk_max[j], A = L.acc_max[j], V = L.vel_max[j];
     code = 0;
     lo = xsub(a, xmul(J, ts)); hi = xadd(a, xmul(J, ts));
     if (lo < -A) lo = -A;
@@ -354,13 +391,18 @@ __device__ __forceinline__ void safe_range_light(int j, double p, double v, doub
     need_pos = false;
     if (c_sc.limit_position) {
         const bool vg = c_sc.limit_velocity && code == 0 && fabs(v) <= V;
-        need_pos = !(pos_bound_inactive(p, v, a, hi, c_sc.pos_hi[j], J, A, V, ts, vg) &&
-                     pos_bound_inactive(-p, -v, -a, -lo, -c_sc.pos_lo[j], J, A, V, ts, vg));
+        need_pos = !(pos_bound_inactive(p, v, a, hi, L.pos_hi[j], J, A, V, ts, vg) &&
+                     pos_bound_inactive(-p, -v, -a, -lo, -L.pos_lo[j], J, A, V, ts, vg));
     }
 }
+__device__ __forceinline__ void safe_range_light(int j, double p, double v, double a, double& lo, double& hi, int& code,
+                                                 bool& need_pos) {
+    safe_range_light(c_sc.lim, j, p, v, a, lo, hi, code, need_pos);
+}
 
-__device__ void safe_range_joint(int j, double p, double v, double a, double& out_lo, double& out_hi, int& out_code) {
-    double ts = c_sc.ts, J = c_sc.jerk_max[j], A = c_sc.acc_max[j], V = c_sc.vel_max[j];
+__device__ void safe_range_joint(const JointLim& L, int j, double p, double v, double a, double& out_lo, double& out_hi,
+                                 int& out_code) {
+    double ts = c_sc.ts, J = L.jerk_max[j], A = L.acc_max[j], V = L.vel_max[j];
     int code = 0;
     double lo = xsub(a, xmul(J, ts)), hi = xadd(a, xmul(J, ts));
     if (lo < -A) lo = -A;
@@ -375,11 +417,15 @@ __device__ void safe_range_joint(int j, double p, double v, double a, double& ou
         clamp_range(lo, hi, blo, bhi, CODE_VEL_HI, CODE_VEL_LO, code);
     }
     if (c_sc.limit_position) {
-        double bhi = pos_upper(p, v, a, c_sc.pos_hi[j], lo, hi, J, A, ts);
-        double blo = -pos_upper(-p, -v, -a, -c_sc.pos_lo[j], -hi, -lo, J, A, ts);
+        double bhi = pos_upper(p, v, a, L.pos_hi[j], lo, hi, J, A, ts);
+        double blo = -pos_upper(-p, -v, -a, -L.pos_lo[j], -hi, -lo, J, A, ts);
         clamp_range(lo, hi, blo, bhi, CODE_POS_HI, CODE_POS_LO, code);
     }
     out_lo = lo; out_hi = hi; out_code = code;
+}
+__device__ __forceinline__ void safe_range_joint(int j, double p, double v, double a, double& out_lo, double& out_hi,
+                                                 int& out_code) {
+    safe_range_joint(c_sc.lim, j, p, v, a, out_lo, out_hi, out_code);
 }
 
 // actions.py:268-280

@@ -21,7 +21,9 @@
 #pragma once
 #include "smenv_geom.cuh"
 
-enum { GJK_STATIC = 0, GJK_SELF = 1, GJK_MOVING = 2, GJK_CONTACT = 3 };
+enum { GJK_STATIC = 0, GJK_SELF = 1, GJK_MOVING = 2, GJK_CONTACT = 3, GJK_BRAKE = 4 };
+// GJK_BRAKE: "is this pair closer than the safety distance at pose k of the human's braking trajectory" (ctlp.py:3155-3207);
+// a touch test like GJK_CONTACT, reported as the first such pose in result slot 4
 
 struct __align__(16) GjkItem {
     int env;
@@ -34,7 +36,8 @@ struct __align__(16) GjkItem {
 };
 static_assert(sizeof(GjkItem) == 64, "GjkItem must stay 64 bytes");
 
-#define SM_RES_STRIDE 4          /* per-env result record: static, self, moving distance keys, first contact sub-step */
+#define SM_RES_STRIDE 8          /* per-env result record: static, self, moving distance keys, first contact sub-step,
+                                    first colliding pose of the human's braking trajectory, 3 spare */
 #define SM_RES_NO_CONTACT 0x7fffffffu
 
 struct GjkArgs {
@@ -179,10 +182,10 @@ __global__ void __launch_bounds__(GJK_THREADS, GJK_MIN_BLOCKS) gjk_kernel(GjkArg
                 vA = G.verts + SA.off; vB = G.verts + SB.off;
                 nA = SA.cnt; nB = SB.cnt; lutA = SA.lut; lutB = SB.lut;
                 m = SA.margin + SB.margin;
-                lim_fixed = (cls == GJK_CONTACT ? thr + 1e-3f : thr) + m;  // on the distance between the cores
-                touch = cls == GJK_CONTACT ? thr + m : -1.0f;
+                lim_fixed = (cls >= GJK_CONTACT ? thr + 1e-3f : thr) + m;  // on the distance between the cores
+                touch = cls >= GJK_CONTACT ? thr + m : -1.0f;
                 lim = lim_fixed;
-                if (cls != GJK_CONTACT) {  // what earlier pairs of the env already reached
+                if (cls < GJK_CONTACT) {  // what earlier pairs of the env already reached
                     const unsigned prev = __ldcg(A.res + (size_t)env * SM_RES_STRIDE + cls);
                     lim = fminf(lim_fixed, funkey(prev) + m);
                 }
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(GJK_THREADS, GJK_MIN_BLOCKS) gjk_kernel(GjkArg
         if (!__any_sync(FULL, busy)) break;
         // lanes with the same (env, distance class) prune each other; contact items and idle lanes share one dummy
         // group (redux over lane-dependent masks is serialised per distinct mask)
-        const bool dist = busy && cls != GJK_CONTACT;
+        const bool dist = busy && cls < GJK_CONTACT;
         const unsigned peers = __match_any_sync(FULL, dist ? (((unsigned)env << 2) | (unsigned)cls) : 0xffffffffu);
         bool done = false;
         if (busy) {
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(GJK_THREADS, GJK_MIN_BLOCKS) gjk_kernel(GjkArg
         // ---------------- a finished pair reports its last upper bound (the exact distance if it converged)
         if (done) {
             if (have_point && d <= thr) {
-                if (cls == GJK_CONTACT) atomicMin(&A.res[(size_t)env * SM_RES_STRIDE + 3], meta >> 8);
+                if (cls >= GJK_CONTACT) atomicMin(&A.res[(size_t)env * SM_RES_STRIDE + cls], meta >> 8);
                 else if (d + m <= lim) atomicMin(&A.res[(size_t)env * SM_RES_STRIDE + cls], fkey(d));  // group's best
             }
             busy = false;

@@ -1,0 +1,794 @@
+// smenv_human.cuh -- the Human scene (Human, ctlp.py:4647-4959): a nested SafeMotionsEnv(robot_scene = 9) moves the two
+// arms of a human next to the robot (description/urdf/human.urdf:140-416, trained_networks/human_network/params.json).
+//
+// Per step of the main env, in launch order (smenv.cu step_range):
+//   mlp_kernel (SM_NET_HUMAN)      the human's policy 38 -> 256 -> 128 -> 16 on the tensor cores        (smenv_mlp.cuh)
+//   human_action_kernel            stochastic head: mean + exp(log_std) * eps, Philox normal noise, clipped
+//                                  (keras_fcnet_last_layer_activation.py:187-202; explore = True, ctlp.py:4701)
+//   joint_kernel .. joint_final    safe range of the 8 human joints and the mapped acceleration (set = 1, deferred advance)
+//   human_brake_traj_kernel        braking trajectory that would follow the step, in joint space
+//                                  (ctlp.py:3155-3207, :3467-3507; utils/braking_trajectory_generator.py:44-93)
+//   human_brake_plan_kernel        FK of every checked pose, bounding-volume culling -> GJK_BRAKE items
+//   gjk_kernel                     "closer than the safety distance?" per item                             (smenv_gjk.cuh)
+//   human_advance_kernel           adapt_action bookkeeping (ctlp.py:3055-3153, :3000-3024), 24 setpoints + tracked pose
+//   human_outcome_kernel           target point reached? (ctlp.py:2787-2821), new knot bookkeeping, new target point from
+//                                  the pool, observation of the nested env (observations.py:313-351)
+//   hcontact_coarse / _plan        contacts robot <-> human at the 24 tracked sub-step poses -> GJK_CONTACT items
+//                                  (ctlp.py:2613-2615, :4888-4898)
+// The distance planning and the finish kernel of the main env take the human's frames / kinematic observation from the
+// records written here.
+#pragma once
+#include "smenv_pools.cuh"
+#include "smenv_step.cuh"
+
+struct HumanArgs {
+    SmBuffers buf;
+    int n, env_base;
+    uint32_t k0, k1, step_counter;
+    const float* policy_out;   // [n][16] outputs of the human's policy (tanh), NULL: buf.hactions come from the caller
+    double* range;             // [n][8][4] lo, hi, mapped acceleration of every human joint (joint kernels, deferred)
+    double* bacc;              // [n][SM_HBRAKE_STEPS][8] braking accelerations of the trajectory under check
+    float* poses;              // [n][SM_HBRAKE_POSES][8] poses the check visits
+    int* binfo;                // [n][4] braking steps k, poses, timeout, reserved
+    float* hscratch;           // [n][SM_SCRATCH_FLOATS] sub-step poses of the human (tracked, setpoints)
+    const float* scratch;      // [n][SM_SCRATCH_FLOATS] sub-step poses of the robot
+    GjkItem* items;
+    int* item_count;
+    int capacity;
+    int* overflow;
+    unsigned* res;             // [n][SM_RES_STRIDE]
+    const double* target_pool; // [2][target_pool_n][4] target points per arm
+    int target_pool_n;
+    const double* start_pool;  // [start_pool_n][SM_HPOOL_STRIDE] start states of the nested env
+    int start_pool_n;
+    int* cwork;                // contact planning: [0] = count, [1..] = env * 8 + span
+    const uint8_t* mask;       // reset: envs to reset (NULL = by done flag / all)
+    unsigned long long* counters;
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// the human's stochastic policy head (keras_fcnet_last_layer_activation.py:187-202; RLlib clips actions to [-1, 1])
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void human_action_kernel(HumanArgs A) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int env = t >> 3, j = t & 7;
+    if (env >= A.n) return;
+    const float* o = A.policy_out + (size_t)env * 16;
+    const float mean = o[j];
+    const float log_std = (float)c_sc.hu.log_std_lo + 0.5f * (o[8 + j] + 1.0f) * (float)(c_sc.hu.log_std_hi - c_sc.hu.log_std_lo);
+    const uint4 r = philox((uint32_t)(env + A.env_base), A.step_counter, (uint32_t)j, 0x4057u, A.k0, A.k1);
+    const float u1 = fmaxf(u01f(r.x), 5.9604645e-8f), u2 = u01f(r.y);
+    const float eps = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);   // Box-Muller
+    A.buf.hactions[(size_t)env * SM_HUMAN_JOINTS + j] = fminf(1.0f, fmaxf(-1.0f, mean + expf(log_std) * eps));
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// braking trajectory of the nested env in joint space: thread = (env, joint), the eight lanes of an env in lockstep
+// ------------------------------------------------------------------------------------------------------------------
+// BrakingTrajectoryGenerator.get_braking_acceleration for one joint: the next acceleration from which the acceleration
+// can be ramped back to zero at full jerk, in whole time steps, so that velocity and acceleration reach zero together
+// (same operations as brake_target of the oracle)
+__device__ __forceinline__ double brake_target(double v, double a, double J, double Am, double ts) {
+    const double s0 = xadd(v, xmul(xmul(a, ts), 0.5));
+    const double sg = s0 < 0.0 ? -1.0 : 1.0;
+    const double S = sg * s0, r = xmul(J, ts);
+    double a1 = 0.0;
+#pragma unroll 1
+    for (int n = 1; n <= 8; ++n) {
+        const double dn = (double)n;
+        a1 = xdiv(xadd(S, xmul(xmul(xmul(xmul(ts, r), dn), xsub(dn, 1.0)), 0.5)), xmul(dn, ts));
+        if (a1 <= xmul(dn, r)) break;
+    }
+    a1 = -sg * a1;
+    double lo = xsub(a, xmul(J, ts)), hi = xadd(a, xmul(J, ts));
+    if (lo < -Am) lo = -Am;
+    if (hi > Am) hi = Am;
+    if (lo > hi) { if (a > 0.0) lo = hi; else hi = lo; }
+    if (a1 < lo) a1 = lo;
+    if (a1 > hi) a1 = hi;
+    return a1;
+}
+
+__global__ void __launch_bounds__(128) human_brake_traj_kernel(HumanArgs A) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int env_raw = t >> 3, j = t & 7;
+    const bool valid = env_raw < A.n;
+    const size_t env = valid ? (size_t)env_raw : (size_t)(A.n - 1);
+    const JointLim& L = c_sc.hu.lim;
+    const double ts = c_sc.ts, J = L.jerk_max[j], Am = L.acc_max[j];
+    const int C = c_sc.hu.brake_checks;
+    const double* kin = A.buf.hkin + env * SM_KIN_STRIDE;
+    double q = kin[j], v = kin[8 + j], as = kin[16 + j], ae = A.range[(env * 8 + j) * 4 + 2];
+    float* poses = A.poses + env * SM_HBRAKE_POSES * 8;
+    double* bacc = A.bacc + env * SM_HBRAKE_STEPS * 8;
+    int k = 0, np = 0, timeout = 0;
+    bool done = !valid || !c_sc.hu.check_braking;
+    const int gsh = lane & 24;   // first lane of this env's group of eight
+#pragma unroll 1
+    while (true) {
+        double pend = q, vend = v;
+        bool small_j = true;
+        if (!done) {
+#pragma unroll 1
+            for (int m = 1; m <= C; ++m) {   // poses of this step (ctlp.py:3166-3178)
+                double pm, vv, aa;
+                interpolate(q, v, as, ae, c_sc.hu.brake_t[m], pm, vv, aa);
+                if (np + m - 1 < SM_HBRAKE_POSES) poses[(np + m - 1) * 8 + j] = (float)pm;
+                pend = pm;
+            }
+            np += C;
+            if ((double)k * ts > c_sc.hu.brake_timeout) { timeout = 1; done = true; }   // ctlp.py:3471-3473
+            else {
+                double qq, aa;
+                interpolate(q, v, as, ae, ts, qq, vend, aa);
+                small_j = fabs(vend) < 0.01 && fabs(ae) < 0.01;
+            }
+        }
+        // robot_stopped: every joint of the env slow and without acceleration (braking_trajectory_generator.py:45-47)
+        const unsigned sm_all = __ballot_sync(FULL, done || small_j);
+        const bool stopped = ((sm_all >> gsh) & 0xffu) == 0xffu;
+        if (!done) {
+            if (stopped) done = true;
+            else {
+                double lo, hi;
+                int code;
+                safe_range_joint(L, j, pend, vend, ae, lo, hi, code);   // _acc_range_function (ctlp.py:3496-3499)
+                double e = brake_target(vend, ae, J, Am, ts);
+                if (small_j) e = 0.0;
+                if (e < lo) e = lo;                                      // np.clip(end_acceleration, next_acc_min, next_acc_max)
+                if (e > hi) e = hi;
+                if (k < SM_HBRAKE_STEPS) bacc[k * 8 + j] = e;
+                ++k;
+                q = pend; v = vend; as = ae; ae = e;
+            }
+        }
+        if (__all_sync(FULL, done)) break;
+    }
+    if (valid && j == 0) {
+        int* bi = A.binfo + env * 4;
+        bi[0] = k; bi[1] = np < SM_HBRAKE_POSES ? np : SM_HBRAKE_POSES; bi[2] = timeout; bi[3] = 0;
+        A.res[env * SM_RES_STRIDE + GJK_BRAKE] = SM_RES_NO_CONTACT;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// geometry of the braking-trajectory check: one warp per env, poses one after the other; per pose the frames (warp scan),
+// the world centres of the shapes, then lanes = the pairs of get_minimum_distance (ctlp.py:3282-3374) with the sphere and
+// separating-axis bounds of the distance planning.  A pair that may be closer than the safety distance becomes a
+// GJK_BRAKE item carrying the pose number.
+// ------------------------------------------------------------------------------------------------------------------
+struct HumanWarpScratch {
+    Xf fr[SM_MAX_OBST_FRAMES];
+    float pc[64 + 4][3];   // world centres of the human shapes, then of the static shape(s) of the pair list
+};
+struct HumanBlockShared {
+    SceneSmem scene;
+    short pairs[SM_MAX_HPAIRS][2];
+    HumanWarpScratch w[SM_WARPS_PER_BLOCK];
+};
+
+__global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) human_brake_plan_kernel(HumanArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    HumanBlockShared* bs = reinterpret_cast<HumanBlockShared*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < (int)(sizeof(SceneSmem) / 16); i += blockDim.x)
+        reinterpret_cast<uint4*>(&bs->scene)[i] = __ldg(c_sc.scene_img + i);
+    const int npairs = c_sc.hu.n_brake_pairs;
+    for (int i = tid; i < npairs * 2; i += blockDim.x) (&bs->pairs[0][0])[i] = c_sc.hu.brake_pairs[i];
+    __syncthreads();
+    const SceneSmem& sm = bs->scene;
+    HumanWarpScratch& W = bs->w[warp];
+    const int hoff = c_sc.hu.shape_off, hn = c_sc.hu.n_shapes;
+    const float safety = (float)c_sc.hu.brake_safety;
+    Xf world;
+    xf_identity(world);
+#pragma unroll 1
+    for (int env = blockIdx.x * SM_WARPS_PER_BLOCK + warp; env < A.n; env += gridDim.x * SM_WARPS_PER_BLOCK) {
+        const int np = A.binfo[(size_t)env * 4 + 1];
+        const float* poses = A.poses + (size_t)env * SM_HBRAKE_POSES * 8;
+#pragma unroll 1
+        for (int p = 0; p < np; ++p) {
+            human_fk_scan(poses[p * 8 + (lane & 7)], W.fr, lane);
+#pragma unroll 1
+            for (int s = lane; s < hn; s += 32) {
+                const DevShape& sh = sm.shapes[hoff + s];
+                const V3 c = xf_apply(W.fr[sh.frame - 100], sh.cx, sh.cy, sh.cz);
+                W.pc[s][0] = c.x; W.pc[s][1] = c.y; W.pc[s][2] = c.z;
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int base = 0; base < npairs; base += 32) {
+                const int i = base + lane;
+                bool emit = false;
+                int ia = 0, ib = 0;
+                if (i < npairs) {
+                    ia = bs->pairs[i][0]; ib = bs->pairs[i][1];
+                    const DevShape& SA = sm.shapes[ia];
+                    const DevShape& SB = sm.shapes[ib];
+                    const V3 ca = mk(W.pc[ia - hoff][0], W.pc[ia - hoff][1], W.pc[ia - hoff][2]);
+                    if (SB.frame == 0) {   // the table: sphere against its axis-aligned box
+                        emit = sqrtf(box_dist2(ca, SB.bmin, SB.bmax)) - SA.radius - SA.margin - SB.margin <= safety;
+                        if (emit)
+                            emit = axis_lower_bound_d(SA, SB, W.fr[SA.frame - 100], world,
+                                                      mk(SB.cx - ca.x, SB.cy - ca.y, SB.cz - ca.z)) <= safety;
+                    } else {
+                        const V3 d = mk(W.pc[ib - hoff][0] - ca.x, W.pc[ib - hoff][1] - ca.y, W.pc[ib - hoff][2] - ca.z);
+                        emit = sqrtf(dot(d, d)) - SA.radius - SB.radius - SA.margin - SB.margin <= safety;
+                        if (emit) emit = axis_lower_bound_d(SA, SB, W.fr[SA.frame - 100], W.fr[SB.frame - 100], d) <= safety;
+                    }
+                }
+                const unsigned em = __ballot_sync(FULL, emit);
+                if (em) {
+                    const int total = __popc(em);
+                    int b0 = 0;
+                    if (lane == 0) b0 = atomicAdd(A.item_count, total);
+                    b0 = __shfl_sync(FULL, b0, 0);
+                    if (b0 + total <= A.capacity) {
+                        if (emit) {
+                            const DevShape& SB = sm.shapes[ib];
+                            write_item(A.items + b0 + __popc(em & ((1u << lane) - 1u)), env, ia, ib, GJK_BRAKE, p + 1, safety,
+                                       W.fr[sm.shapes[ia].frame - 100], SB.frame == 0 ? world : W.fr[SB.frame - 100]);
+                        }
+                    } else if (lane == 0) {
+                        atomicAdd(A.overflow, total);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// adapt_action (ctlp.py:3055-3153) + get_braking_acceleration (:3000-3024), then the 24 setpoints and the tracked pose of
+// the human (Human.prepare_sim_step ctlp.py:4850-4860; robot_scene_base.py:789-837): thread = (env, joint)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) human_advance_kernel(HumanArgs A) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int env_raw = t >> 3, j = t & 7;
+    const bool valid = env_raw < A.n;
+    const size_t env = valid ? (size_t)env_raw : (size_t)(A.n - 1);
+    double* kin = A.buf.hkin + env * SM_KIN_STRIDE;
+    double* hs = A.buf.hstate + env * SM_HSTATE_STRIDE;
+    double* hb = A.buf.hbrake + env * SM_HBRAKE_STEPS * 8;
+    const int* bi = A.binfo + env * 4;
+    double a1 = A.range[(env * 8 + j) * 4 + 2];
+    const int count = (int)hs[SM_HS_BRAKE_COUNT];
+    int braked = 0, new_count = count;
+    if (c_sc.hu.check_braking) {
+        const bool execute = A.res[env * SM_RES_STRIDE + GJK_BRAKE] != SM_RES_NO_CONTACT || bi[2] != 0;
+        if (execute) {   // the stored braking trajectory is executed instead of the action
+            braked = 1;
+            if (count > 0) {
+                a1 = hb[j];
+#pragma unroll 1
+                for (int i = 0; i + 1 < count; ++i) hb[i * 8 + j] = hb[(i + 1) * 8 + j];
+                new_count = count - 1;
+            } else {
+                a1 = 0.0;
+            }
+        } else {         // the checked trajectory becomes the valid one (ctlp.py:3096-3119)
+            int k = bi[0];
+            if (k > SM_HBRAKE_STEPS) k = SM_HBRAKE_STEPS;
+            const double* src = A.bacc + env * SM_HBRAKE_STEPS * 8;
+#pragma unroll 1
+            for (int i = 0; i < k; ++i) hb[i * 8 + j] = src[i * 8 + j];
+            new_count = k;
+        }
+    }
+    const double q = kin[j], v = kin[8 + j], a = kin[16 + j], qa = kin[24 + j];
+    const double steps = hs[SM_HS_STEPS];
+    __syncwarp();   // every lane of the env has read the record before lane 0 rewrites it
+    if (valid) {
+        joint_advance_a1(kin, A.hscratch + env * SM_SCRATCH_FLOATS, j, q, v, a, qa, a1, 0.87, true, c_sc.hu.lim.jerk_max[j]);
+        if (j == 0) {
+            hs[SM_HS_BRAKE_COUNT] = (double)new_count;
+            hs[SM_HS_BRAKED] = (double)braked;
+            hs[SM_HS_STEPS] = steps + 1.0;
+        }
+    }
+}
+
+// observation of the nested env (observations.py:313-351 with two arms and alternating target points): entries spread over
+// `stride` lanes
+__device__ __forceinline__ void write_human_observation(float* hobs, const double* hk, const double* hs, int lane, int stride) {
+    const JointLim& L = c_sc.hu.lim;
+#pragma unroll 1
+    for (int i = lane; i < SM_HOBS_STRIDE; i += stride) {
+        double val = 0.0;
+        if (i < 24) {
+            const int grp = i >> 3, j = i & 7;
+            const double x = hk[grp * 8 + j];
+            val = grp == 0 ? normalize_mm(x, L.pos_lo[j], L.pos_hi[j]) : xdiv(x, grp == 1 ? L.vel_max[j] : L.acc_max[j]);
+        } else if (i < 30) {
+            const int r = (i - 24) / 3, c = (i - 24) % 3;
+            const double* tp = hs + 12 * r;
+            if (tp[SM_TP_ACTIVE] != 0.0) val = normalize_mm(tp[SM_TP_POS + c], c_sc.hu.tp_box_min[c], c_sc.hu.tp_box_max[c]);
+        } else if (i < 36) {
+            const int r = (i - 30) / 3, c = (i - 30) % 3;
+            const double* tp = hs + 12 * r;
+            if (tp[SM_TP_ACTIVE] != 0.0)
+                val = normalize_mm(xsub(tp[SM_TP_POS + c], tp[SM_TP_LINK_POS + c]), c_sc.hu.tp_rel_min[c], c_sc.hu.tp_rel_max[c]);
+        } else if (i < 38) {
+            val = hs[12 * (i - 36) + SM_TP_ACTIVE] != 0.0 ? 1.0 : 0.0;
+        }
+        hobs[i] = clip1(val);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// outcome of the nested env's step: 8 lanes per env.  Lane i checks sub-steps i, i + 8, i + 16 of the active arm against
+// its target point (ctlp.py:2787-2821; target link point of the sub-step's setpoint pose), lanes 0 / 1 take the link
+// points of the two arms at the new knot; then get_target_point_observation (ctlp.py:2210-2271) and the observation.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) human_outcome_kernel(HumanArgs A) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, sl = lane & 7;
+    const unsigned gmask = 0xffu << (lane & 24);
+    const int env_raw = t >> 3;
+    const bool valid = env_raw < A.n;
+    const size_t env = valid ? (size_t)env_raw : (size_t)(A.n - 1);
+    const int S = c_sc.substeps;
+    double* hs = A.buf.hstate + env * SM_HSTATE_STRIDE;
+    const double* hk = A.buf.hkin + env * SM_KIN_STRIDE;
+    const float* qs = A.hscratch + env * SM_SCRATCH_FLOATS + SM_QSET_OFF;
+    int active = -1;
+    if (hs[SM_TP_ACTIVE] != 0.0) active = 0;
+    else if (hs[12 + SM_TP_ACTIVE] != 0.0) active = 1;
+    bool hit = false;
+    if (active >= 0) {
+        const double* tp = hs + 12 * active;
+        const V3 T = mk((float)tp[SM_TP_POS], (float)tp[SM_TP_POS + 1], (float)tp[SM_TP_POS + 2]);
+        Xf B;
+        human_base(B);
+#pragma unroll 1
+        for (int k = sl; k < S; k += 8) {
+            Xf F = B;
+#pragma unroll 1
+            for (int i = 0; i < 4; ++i) human_chain_step(F, 4 * active + i, qs[k * SM_MAX_JOINTS + 4 * active + i]);
+            const V3 e = xf_apply(F, c_sc.hu.tp_local[active][0], c_sc.hu.tp_local[active][1], c_sc.hu.tp_local[active][2]) - T;
+            if (sqrtf(dot(e, e)) < (float)c_sc.hu.tp_radius) hit = true;
+        }
+    }
+    const bool reached = (__ballot_sync(FULL, hit) & gmask) != 0u;
+    // link points of both arms at the new knot (the setpoint pose of the last sub-step)
+    V3 lp = mk(0.f, 0.f, 0.f);
+    if (sl < 2) {
+        Xf F;
+        human_base(F);
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) human_chain_step(F, 4 * sl + i, (float)hk[4 * sl + i]);
+        lp = xf_apply(F, c_sc.hu.tp_local[sl][0], c_sc.hu.tp_local[sl][1], c_sc.hu.tp_local[sl][2]);
+    }
+    const double draws = hs[SM_HS_DRAWS];
+    __syncwarp();
+    if (valid && sl < 2) {   // lane r owns the record of arm r
+        double* tp = hs + 12 * sl;
+        tp[SM_TP_LINK_POS] = (double)lp.x; tp[SM_TP_LINK_POS + 1] = (double)lp.y; tp[SM_TP_LINK_POS + 2] = (double)lp.z;
+        bool act = tp[SM_TP_ACTIVE] != 0.0;
+        tp[SM_HTP_REACHED] = 0.0;
+        if (reached && sl == active) {         // ctlp.py:2806-2811
+            act = false;
+            tp[SM_TP_REACHED_N] += 1.0;
+        }
+        const bool sample_new = reached && sl == (active + 1) % 2;   // alternating target points (ctlp.py:2815-2817)
+        if (sample_new && A.target_pool_n > 0) {                      // _add_target_point from the device pool
+            const uint4 r = philox((uint32_t)(env + A.env_base), (uint32_t)draws, 0x7A28u, 3u, A.k0, A.k1);
+            const double* e = A.target_pool + ((size_t)sl * A.target_pool_n + (r.x % (uint32_t)A.target_pool_n)) * 4;
+            tp[SM_TP_POS] = e[0]; tp[SM_TP_POS + 1] = e[1]; tp[SM_TP_POS + 2] = e[2];
+            act = true;
+            tp[SM_TP_INIT_DIST] = nan("");
+        } else if (sample_new) {
+            tp[SM_HTP_SAMPLE_NEW] = 1.0;   // no pool: the caller injects the next target point (parity protocol)
+        }
+        tp[SM_TP_ACTIVE] = act ? 1.0 : 0.0;
+        if (act) {
+            const double dx = tp[SM_TP_POS] - tp[SM_TP_LINK_POS], dy = tp[SM_TP_POS + 1] - tp[SM_TP_LINK_POS + 1],
+                         dz = tp[SM_TP_POS + 2] - tp[SM_TP_LINK_POS + 2];
+            tp[SM_TP_LAST_DIST] = sqrt(dx * dx + dy * dy + dz * dz);
+            if (isnan(tp[SM_TP_INIT_DIST])) tp[SM_TP_INIT_DIST] = tp[SM_TP_LAST_DIST];
+        }
+        if (sample_new && A.target_pool_n > 0) hs[SM_HS_DRAWS] = draws + 1.0;
+        __threadfence_block();
+    }
+    __syncwarp();
+    if (valid) write_human_observation(A.buf.hobs + env * SM_HOBS_STRIDE, hk, hs, sl, 8);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// contacts robot <-> human in the simulation client (Human.check_if_object_is_colliding, ctlp.py:4888-4898): both bodies
+// at their motor-tracked poses of the 24 sub-steps.  Coarse phase as for planets / balls (smenv_plan.cuh): 8 threads per
+// env, each clears a span of 3 sub-steps with one forward kinematics of both bodies; link spheres are inflated by what
+// the joints move inside the span.  Spans that cannot be cleared go to the fine planning (one lane per sub-step).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hcontact_coarse_kernel(HumanArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SceneSmem* smp = reinterpret_cast<SceneSmem*>(smem_raw);
+    for (int i = threadIdx.x; i < (int)(sizeof(SceneSmem) / 16); i += blockDim.x)
+        reinterpret_cast<uint4*>(smp)[i] = __ldg(c_sc.scene_img + i);
+    __syncthreads();
+    const SceneSmem& sm = *smp;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int t = blockIdx.x * blockDim.x + tid;
+    const int env = t / SM_COARSE_LANES, c = t % SM_COARSE_LANES;
+    const int S = c_sc.substeps;
+    const int span = (S + SM_COARSE_LANES - 1) / SM_COARSE_LANES;
+    bool flag = false;
+    if (env < A.n && c_sc.contact_stride > 0 && c * span < S &&
+        A.buf.obst[(size_t)env * SM_OBST_STRIDE + SM_OB_LATCH] == 0.0) {
+        const int k0 = c * span, k1 = k0 + span < S ? k0 + span : S;
+        const int kc = (k0 + k1 - 1) >> 1;
+        const float* scr = A.scratch + (size_t)env * SM_SCRATCH_FLOATS;
+        const float* hscr = A.hscratch + (size_t)env * SM_SCRATCH_FLOATS;
+        float dq[SM_MAX_JOINTS], dh[SM_HUMAN_JOINTS], hq[SM_HUMAN_JOINTS];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { dq[j] = 0.f; dh[j] = 0.f; hq[j] = hscr[kc * SM_MAX_JOINTS + j]; }
+#pragma unroll 1
+        for (int k = k0; k < k1; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                dq[j] = fmaxf(dq[j], fabsf(scr[k * SM_MAX_JOINTS + j] - scr[kc * SM_MAX_JOINTS + j]));
+                dh[j] = fmaxf(dh[j], fabsf(hscr[k * SM_MAX_JOINTS + j] - hq[j]));
+            }
+        // human group spheres at the middle pose, inflated by the motion of the human inside the span
+        V3 gc[SM_HGROUPS];
+        float gr[SM_HGROUPS];
+        {
+            Xf hfr[SM_MAX_OBST_FRAMES];
+            human_fk_serial(hq, hfr);
+#pragma unroll
+            for (int g = 0; g < SM_HGROUPS; ++g) {
+                gc[g] = xf_apply(hfr[c_sc.hu.grp_frame[g]], c_sc.hu.grp_c[g][0], c_sc.hu.grp_c[g][1], c_sc.hu.grp_c[g][2]);
+                float infl = 1e-5f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) infl = fmaf(dh[j], c_sc.hu.grp_rho[g][j], infl);
+                gr[g] = c_sc.hu.grp_r[g] + infl + c_sc.hu.contact_thresh_max;
+            }
+        }
+        Xf F;
+        xf_identity(F);
+#pragma unroll 1
+        for (int f = 0; f <= c_sc.n_joints && !flag; ++f) {
+            if (f > 0) fk_chain_step(sm, F, f - 1, scr[kc * SM_MAX_JOINTS + f - 1]);
+#pragma unroll 1
+            for (int slot = c_sc.contact_frame_start[f]; slot < c_sc.contact_frame_start[f + 1]; ++slot) {
+                const DevShape& sh = sm.shapes[sm.mov_contact[slot]];
+                const V3 ctr = xf_apply(F, sh.cx, sh.cy, sh.cz);
+                float infl = 1e-5f;
+#pragma unroll
+                for (int j = 0; j < SM_MAX_JOINTS; ++j) infl = fmaf(dq[j], c_sc.contact_rho[slot][j], infl);
+                const float rr = sh.radius + sh.margin + infl;
+#pragma unroll
+                for (int g = 0; g < SM_HGROUPS; ++g) {
+                    const V3 e = ctr - gc[g];
+                    const float lim = rr + gr[g];
+                    if (dot(e, e) <= lim * lim) flag = true;
+                }
+            }
+        }
+    }
+    const unsigned fm = __ballot_sync(FULL, flag);
+    if (fm) {
+        int base = 0;
+        if (lane == __ffs(fm) - 1) base = atomicAdd(A.cwork, __popc(fm));
+        base = __shfl_sync(FULL, base, __ffs(fm) - 1);
+        if (flag) A.cwork[1 + base + __popc(fm & ((1u << lane) - 1u))] = t;
+        if (A.counters && lane == __ffs(fm) - 1) atomicAdd(&A.counters[5], (unsigned long long)__popc(fm));
+    }
+}
+
+// fine contact planning over the listed spans: one lane per sub-step; robot link spheres against the human's link groups,
+// then against every part's sphere and box, then the separating-axis bound; survivors become contact items
+__global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) hcontact_plan_kernel(HumanArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n_units = A.cwork[0];
+    const int span = (c_sc.substeps + SM_COARSE_LANES - 1) / SM_COARSE_LANES;
+    const int upw = 32 / span;
+    if (blockIdx.x * SM_WARPS_PER_BLOCK * upw >= n_units) return;
+    SceneSmem* smp = reinterpret_cast<SceneSmem*>(smem_raw);
+    for (int i = threadIdx.x; i < (int)(sizeof(SceneSmem) / 16); i += blockDim.x)
+        reinterpret_cast<uint4*>(smp)[i] = __ldg(c_sc.scene_img + i);
+    __syncthreads();
+    const SceneSmem& sm = *smp;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = c_sc.substeps, stride = c_sc.contact_stride;
+    const int lu = lane / span, i = lane - lu * span;
+    unsigned n_flag = 0;
+#pragma unroll 1
+    for (int ub = (blockIdx.x * SM_WARPS_PER_BLOCK + warp) * upw; ub < n_units; ub += gridDim.x * SM_WARPS_PER_BLOCK * upw) {
+        const int u = ub + lu;
+        if (u >= n_units || lu >= upw) continue;
+        const int unit = A.cwork[1 + u];
+        const int env = unit / SM_COARSE_LANES, k = (unit % SM_COARSE_LANES) * span + i;   // 0-based sub-step
+        if (k >= S || ((k + 1) % stride) != 0) continue;
+        const float* qrow = A.scratch + (size_t)env * SM_SCRATCH_FLOATS + k * SM_MAX_JOINTS;
+        const float* hrow = A.hscratch + (size_t)env * SM_SCRATCH_FLOATS + k * SM_MAX_JOINTS;
+        Xf hfr[SM_MAX_OBST_FRAMES];
+        {
+            float hq[SM_HUMAN_JOINTS];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hq[j] = hrow[j];
+            human_fk_serial(hq, hfr);
+        }
+        Xf F;
+        xf_identity(F);
+#pragma unroll 1
+        for (int f = 0; f <= c_sc.n_joints; ++f) {
+            if (f > 0) fk_chain_step(sm, F, f - 1, qrow[f - 1]);
+#pragma unroll 1
+            for (int slot = c_sc.contact_frame_start[f]; slot < c_sc.contact_frame_start[f + 1]; ++slot) {
+                const int ia = sm.mov_contact[slot];
+                const DevShape& sh = sm.shapes[ia];
+                const V3 cw = xf_apply(F, sh.cx, sh.cy, sh.cz);
+                const float rr = sh.radius + sh.margin;
+#pragma unroll 1
+                for (int g = 0; g < SM_HGROUPS; ++g) {
+                    const Xf& TB = hfr[c_sc.hu.grp_frame[g]];
+                    const V3 gcw = xf_apply(TB, c_sc.hu.grp_c[g][0], c_sc.hu.grp_c[g][1], c_sc.hu.grp_c[g][2]);
+                    const V3 dd = cw - gcw;
+                    const float lim = rr + c_sc.hu.grp_r[g] + c_sc.hu.contact_thresh_max;
+                    if (dot(dd, dd) > lim * lim) continue;
+                    const V3 cl = xf_rot_t(TB, mk(cw.x - TB.t[0], cw.y - TB.t[1], cw.z - TB.t[2]));   // in the group's frame
+#pragma unroll 1
+                    for (int s = c_sc.hu.grp_off[g]; s < c_sc.hu.grp_off[g] + c_sc.hu.grp_cnt[g]; ++s) {
+                        const DevShape& ps = sm.shapes[c_sc.hu.shape_off + s];
+                        const float th = __ldg(c_sc.hu.contact_thresh + c_sc.hu.shape_link[s] * SM_MAX_MOV_ROBOT + slot);
+                        const V3 e = mk(cl.x - ps.cx, cl.y - ps.cy, cl.z - ps.cz);
+                        const float l2 = rr + ps.radius + ps.margin + th;
+                        const float l3 = (rr + ps.margin + th) * (1.0f + 1e-6f) + 1e-6f;
+                        if (dot(e, e) <= l2 * l2 && box_dist2(cl, ps.bmin, ps.bmax) <= l3 * l3 &&
+                            axis_lower_bound(sh, ps, F, TB) <= th) {
+                            const int idx = atomicAdd(A.item_count, 1);
+                            if (idx < A.capacity) write_item(A.items + idx, env, ia, c_sc.hu.shape_off + s, GJK_CONTACT, k + 1, th, F, TB);
+                            else atomicAdd(A.overflow, 1);
+                            ++n_flag;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (A.counters && n_flag) atomicAdd(&A.counters[6], (unsigned long long)n_flag);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// start of an episode of the nested env: from the pool (reset / auto reset: envs with `done` set, or masked) or injected
+// (parity protocol).  One thread per env.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void human_episode_start(double* hk, double* hs, double* hb, float* hobs, const double* q,
+                                                    const double* v, const double* a, const double* first_target,
+                                                    int active_arm, double draws) {
+    const double dt = xdiv(c_sc.ts, (double)c_sc.substeps), tvdt = xmul(0.87, dt);
+    float qf[SM_HUMAN_JOINTS];
+    for (int j = 0; j < 8; ++j) {
+        hk[j] = q[j]; hk[8 + j] = v[j]; hk[16 + j] = a[j];
+        hk[24 + j] = xadd(q[j], xmul(tvdt, v[j]));   // as the robot: one stepSimulation with the start state as target
+        qf[j] = (float)q[j];
+    }
+    for (int i = 0; i < SM_HSTATE_STRIDE; ++i) hs[i] = 0.0;
+    Xf fr[SM_MAX_OBST_FRAMES];
+    human_fk_serial(qf, fr);
+    for (int r = 0; r < 2; ++r) {
+        const V3 p = human_link_point(fr, r);
+        hs[12 * r + SM_TP_LINK_POS] = (double)p.x; hs[12 * r + SM_TP_LINK_POS + 1] = (double)p.y; hs[12 * r + SM_TP_LINK_POS + 2] = (double)p.z;
+    }
+    double* tp = hs + 12 * active_arm;
+    tp[SM_TP_POS] = first_target[0]; tp[SM_TP_POS + 1] = first_target[1]; tp[SM_TP_POS + 2] = first_target[2];
+    tp[SM_TP_ACTIVE] = 1.0;
+    const double dx = tp[SM_TP_POS] - tp[SM_TP_LINK_POS], dy = tp[SM_TP_POS + 1] - tp[SM_TP_LINK_POS + 1],
+                 dz = tp[SM_TP_POS + 2] - tp[SM_TP_LINK_POS + 2];
+    tp[SM_TP_LAST_DIST] = tp[SM_TP_INIT_DIST] = sqrt(dx * dx + dy * dy + dz * dz);
+    hs[SM_HS_DRAWS] = draws;
+    (void)hb;   // the stored braking trajectory is empty (count 0): nothing to clear
+    write_human_observation(hobs, hk, hs, 0, 1);
+}
+
+// the human part of the main env's observation: Human.kinematic_observation (observations.py:100-110, :294-307)
+__device__ __forceinline__ void copy_human_kinematic_obs(float* obs, const float* hobs) {
+    const int off = c_sc.obs_size - 3 * SM_HUMAN_JOINTS;
+    for (int i = 0; i < 3 * SM_HUMAN_JOINTS; ++i) obs[off + i] = hobs[i];
+}
+
+__global__ void human_set_state_kernel(HumanArgs A, const double* hq, const double* hv, const double* ha,
+                                       const double* first_target, const int32_t* active_arm) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= A.n || (A.mask && !A.mask[env])) return;
+    human_episode_start(A.buf.hkin + (size_t)env * SM_KIN_STRIDE, A.buf.hstate + (size_t)env * SM_HSTATE_STRIDE,
+                        A.buf.hbrake + (size_t)env * SM_HBRAKE_STEPS * 8, A.buf.hobs + (size_t)env * SM_HOBS_STRIDE,
+                        hq + (size_t)env * 8, hv + (size_t)env * 8, ha + (size_t)env * 8, first_target + (size_t)env * 3,
+                        active_arm ? active_arm[env] : 0, 1.0);
+    if (A.buf.obs) copy_human_kinematic_obs(A.buf.obs + (size_t)env * c_sc.obs_size, A.buf.hobs + (size_t)env * SM_HOBS_STRIDE);
+}
+
+// reset of the nested env from the pools.  by_done != 0: the envs whose `done` flag the finish kernel just set (auto
+// reset; the robot's record was re-initialised there with pool entry `reset_count - 1`, the human takes the same entry:
+// the robot's start pose was sampled clear of that human pose); else the masked envs (smenv_reset, after reset_kernel).
+__global__ void human_reset_kernel(HumanArgs A, int by_done) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= A.n) return;
+    if (by_done ? !A.buf.done[env] : (A.mask && !A.mask[env])) return;
+    if (A.start_pool_n <= 0) return;
+    const int4 ep = *reinterpret_cast<const int4*>(A.buf.episode + 4 * (size_t)env);
+    const uint4 r = philox((uint32_t)(env + A.env_base), (uint32_t)(ep.y - 1), 0x5E7u, 1u, A.k0, A.k1);   // the robot's draw
+    const double* e = A.start_pool + (size_t)(r.x % (uint32_t)A.start_pool_n) * SM_HPOOL_STRIDE;
+    const uint4 r2 = philox((uint32_t)(env + A.env_base), (uint32_t)(ep.y - 1), 0x5E8u, 4u, A.k0, A.k1);
+    const int arm = (int)(r2.x & 1u);                          // np.random.randint(0, num_robots) (ctlp.py:1037-1038)
+    double ft[3] = {0.3, 0.0, 0.4};
+    if (A.target_pool_n > 0) {
+        const double* tp = A.target_pool + ((size_t)arm * A.target_pool_n + (r2.y % (uint32_t)A.target_pool_n)) * 4;
+        ft[0] = tp[0]; ft[1] = tp[1]; ft[2] = tp[2];
+    }
+    human_episode_start(A.buf.hkin + (size_t)env * SM_KIN_STRIDE, A.buf.hstate + (size_t)env * SM_HSTATE_STRIDE,
+                        A.buf.hbrake + (size_t)env * SM_HBRAKE_STEPS * 8, A.buf.hobs + (size_t)env * SM_HOBS_STRIDE, e, e + 8,
+                        e + 16, ft, arm, 1.0);
+    if (A.buf.obs) copy_human_kinematic_obs(A.buf.obs + (size_t)env * c_sc.obs_size, A.buf.hobs + (size_t)env * SM_HOBS_STRIDE);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// pools of the nested env (device-side rejection sampling with Philox streams, one warp per entry):
+//   start states   get_starting_point_joint_pos_vel_acc with always_use_collision_avoidance_starting_point_sampling
+//                  (ctlp.py:1461-1656; Human.__init__ ctlp.py:4723-4729): a random pose with both hands inside the box
+//                  and the clearances of the nested env, then with probability p a random feasible (v, a) per joint,
+//                  else a random walk with random actions that stops with probability 0.3 per step
+//   target points  _add_target_point(robot = r) (ctlp.py:1658-1676): the link point of a random pose of arm r
+// Not reproduced: the torque check of the pose sampler (Bullet dynamics) and the braking-trajectory check along the random
+// walk; a target point is sampled with the other arm hanging down instead of at its current pose.
+// ------------------------------------------------------------------------------------------------------------------
+// clearance of the human pose whose frames are in W.obx: pairs of the braking-trajectory check; arm_only >= 0 restricts
+// them to shapes of arm `arm_only` (frames 101 + 4 r .. 104 + 4 r), the trunk and the table
+__device__ __noinline__ bool human_pose_is_free(const float4* verts, const SceneSmem& sm, WarpScratch& W, float thr_static,
+                                                float thr_self, int arm_only, int lane) {
+    const int np = c_sc.hu.n_brake_pairs;
+#pragma unroll 1
+    for (int base = 0; base < np; base += 32) {
+        const int i = base + lane;
+        bool cand = false;
+        int ia = 0, ib = 0;
+        float thr = 0.f;
+        if (i < np) {
+            ia = c_sc.hu.brake_pairs[2 * i]; ib = c_sc.hu.brake_pairs[2 * i + 1];
+            const int fa = sm.shapes[ia].frame - 100, fb = sm.shapes[ib].frame;
+            thr = fb == 0 ? thr_static : thr_self;
+            bool use = true;
+            if (arm_only >= 0) {
+                const bool a_ok = fa >= 1 + 4 * arm_only && fa <= 4 + 4 * arm_only;
+                const bool b_ok = fb == 0 || fb == 100 || (fb - 100 >= 1 + 4 * arm_only && fb - 100 <= 4 + 4 * arm_only);
+                use = a_ok && b_ok;
+            }
+            cand = use && pair_lower_bound(sm, ia, ib, W.fr, W.obx) < thr;
+        }
+        unsigned mask = __ballot_sync(FULL, cand);
+#pragma unroll 1
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int qa = __shfl_sync(FULL, ia, src), qb = __shfl_sync(FULL, ib, src);
+            const float t = __shfl_sync(FULL, thr, src);
+            const float d = pair_distance(verts, sm, qa, qb, W.fr, W.obx, t + 0.005f, -1.f, lane, nullptr);
+            if (d < t) return false;
+        }
+    }
+    return true;
+}
+
+struct HumanPoolArgs {
+    double* start_pool;
+    int start_pool_n;
+    double* target_pool;   // [2][target_pool_n][4]
+    int target_pool_n;
+    uint32_t k0, k1;
+};
+
+__global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) fill_human_pool_kernel(HumanPoolArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemLayout Lm = block_prologue(smem_raw, true);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    WarpScratch& W = Lm.scratch[warp];
+    const SceneSmem& sm = Lm.bs->scene;
+    const float4* verts = Lm.verts;
+    const JointLim& L = c_sc.hu.lim;
+    const int j = lane & 7;
+    const bool jl = lane < SM_HUMAN_JOINTS;
+    if (lane == 0) xf_identity(W.fr[0]);
+    __syncwarp();
+    const int total = A.start_pool_n + 2 * A.target_pool_n;
+#pragma unroll 1
+    for (int e = blockIdx.x * SM_WARPS_PER_BLOCK + warp; e < total; e += gridDim.x * SM_WARPS_PER_BLOCK) {
+        Rng rng(key64(A.k0, A.k1), (uint32_t)e, 0x4A11u);
+        if (e >= A.start_pool_n) {   // ---------------- a target point of arm r
+            const int r = (e - A.start_pool_n) / A.target_pool_n, slot = (e - A.start_pool_n) % A.target_pool_n;
+            V3 p = mk(0.f, 0.f, 0.f);
+#pragma unroll 1
+            for (int attempt = 0; attempt < 25000; ++attempt) {
+                double ql = 0.0;
+#pragma unroll 1
+                for (int jj = 0; jj < 4; ++jj) {
+                    const double u = rng.uniform(L.pos_lo[4 * r + jj], L.pos_hi[4 * r + jj]);
+                    if (j == 4 * r + jj) ql = u;
+                }
+                human_fk_scan((float)ql, W.obx, lane);
+                p = human_link_point(W.obx, r);
+                bool ok = p.x >= c_sc.hu.tp_box_min[0] && p.x <= c_sc.hu.tp_box_max[0] && p.y >= c_sc.hu.tp_box_min[1] &&
+                          p.y <= c_sc.hu.tp_box_max[1] && p.z >= c_sc.hu.tp_box_min[2] && p.z <= c_sc.hu.tp_box_max[2];
+                if (ok) ok = human_pose_is_free(verts, sm, W, (float)c_sc.hu.tp_min_static, (float)c_sc.hu.tp_min_self, r, lane);
+                __syncwarp();
+                if (ok) break;
+            }
+            if (lane == 0) {
+                double* o = A.target_pool + ((size_t)r * A.target_pool_n + slot) * 4;
+                o[0] = (double)p.x; o[1] = (double)p.y; o[2] = (double)p.z; o[3] = 0.0;
+            }
+            __syncwarp();
+            continue;
+        }
+        // ---------------- a start state
+        double q = 0.0, v = 0.0, a = 0.0;
+        uint32_t lane_ctr = 0;
+#pragma unroll 1
+        for (int outer = 0; outer < 1000; ++outer) {
+#pragma unroll 1
+            for (int attempt = 0; attempt < 100000; ++attempt) {
+#pragma unroll 1
+                for (int jj = 0; jj < SM_HUMAN_JOINTS; ++jj) {
+                    const double u = rng.uniform(L.pos_lo[jj], L.pos_hi[jj]);
+                    if (j == jj) q = u;
+                }
+                human_fk_scan((float)q, W.obx, lane);
+                bool ok = true;
+#pragma unroll 1
+                for (int r = 0; r < 2; ++r) {
+                    const V3 p = human_link_point(W.obx, r);
+                    ok = ok && p.x >= c_sc.hu.start_box_min[0] && p.x <= c_sc.hu.start_box_max[0] && p.y >= c_sc.hu.start_box_min[1] &&
+                         p.y <= c_sc.hu.start_box_max[1] && p.z >= c_sc.hu.start_box_min[2] && p.z <= c_sc.hu.start_box_max[2];
+                }
+                if (ok) ok = human_pose_is_free(verts, sm, W, (float)c_sc.hu.min_start_static, (float)c_sc.hu.min_start_self, -1, lane);
+                __syncwarp();
+                if (ok) break;
+            }
+            v = 0.0; a = 0.0;
+            if (rng.uniform() < c_sc.hu.kinematic_sampling_probability) {   // ctlp.py:1494-1556
+                bool found = false;
+                if (jl) {
+#pragma unroll 1
+                    for (int iv = 0; iv < 5 && !found; ++iv) {
+                        const uint4 r = philox((uint32_t)e, 0x7000u + lane_ctr++, (uint32_t)lane, 0x4A12u, A.k0, A.k1);
+                        const double vj = L.vel_max[j] * (2.0 * u01d(r.x, r.y) - 1.0);
+#pragma unroll 1
+                        for (int ia = 0; ia < 10 && !found; ++ia) {
+                            const uint4 r2 = philox((uint32_t)e, 0x7000u + lane_ctr++, (uint32_t)lane, 0x4A13u, A.k0, A.k1);
+                            const double aj = L.acc_max[j] * (2.0 * u01d(r2.x, r2.y) - 1.0);
+                            double lo, hi;
+                            int code;
+                            safe_range_joint(L, j, q, vj, aj, lo, hi, code);
+                            if (code == 0) { found = true; v = vj; a = aj; }
+                        }
+                    }
+                }
+                if (__all_sync(FULL, !jl || found)) break;
+                continue;
+            }
+            // random walk from rest with random actions (ctlp.py:1558-1654), without the geometric checks
+#pragma unroll 1
+            for (int step = 0; step < 64; ++step) {
+                if (rng.uniform() < c_sc.hu.stay_in_state_probability) break;
+                const uint4 r = philox((uint32_t)e, 0x7000u + lane_ctr++, (uint32_t)lane, 0x4A14u, A.k0, A.k1);
+                if (jl) {
+                    double lo, hi, qe, ve, as_;
+                    int code;
+                    safe_range_joint(L, j, q, v, a, lo, hi, code);
+                    const double un = 2.0 * u01d(r.x, r.y) - 1.0;
+                    const double a1 = lo + 0.5 * (un + 1.0) * (hi - lo);
+                    interpolate(q, v, a, a1, c_sc.ts, qe, ve, as_);
+                    q = qe; v = ve; a = a1;
+                }
+            }
+            break;
+        }
+        if (jl) {
+            double* o = A.start_pool + (size_t)e * SM_HPOOL_STRIDE;
+            o[j] = q; o[8 + j] = v; o[16 + j] = a; o[24 + j] = 0.0;
+        }
+        __syncwarp();
+    }
+}

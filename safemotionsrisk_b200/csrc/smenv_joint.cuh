@@ -37,6 +37,14 @@ struct JointArgs {
     double* hpar;    // [8 n][SM_HPAR] hand-over records of the deferred instances
     int* heavy;      // [0] = number of (env, joint) instances whose position bound needs the iterative solve,
                      // [1..] = env * 8 + joint (filled by joint_kernel, consumed by joint_heavy_kernel)
+    int set;            // 0: the robot's joints; 1: the human's (limits c_sc.hu.lim, kin = buf.hkin, actions = buf.hactions)
+    int nj;             // joints of the set
+    int defer;          // human: do not advance, write (lo, hi, mapped acceleration, code) of every joint to range_out; the
+                        // braking-trajectory check decides the end acceleration first (actions.py:343-376)
+    double* range_out;  // [n][8][4]
+    double track_vel;   // 0.87 with use_controller_target_velocities, else 0 (robot_scene_base.py:792-805)
+    int store_qset;     // also store the setpoint pose of every sub-step (target points)
+    int keep_overflow;  // do not clear the overflow count of the item list (the human's braking-trajectory items came first)
     const float* exec;  // [n][n_joints] actions to execute when the risk gate is on (the backup policy's where the
                         // proposed action was rated risky), else NULL: buf.actions are executed.  The action punishment
                         // always rates the proposed action (safe_motions_base.py:1066, actions.py:328-331)
@@ -44,24 +52,27 @@ struct JointArgs {
 
 // the action the motors execute: the gated one if the risk gate is on
 __device__ __forceinline__ float joint_exec_action(const JointArgs& A, int env, int j, float proposed) {
-    return A.exec ? A.exec[(size_t)env * c_sc.n_joints + j] : proposed;
+    return A.exec ? A.exec[(size_t)env * A.nj + j] : proposed;
+}
+__device__ __forceinline__ const JointLim& joint_limits(const JointArgs& A) { return A.set ? c_sc.hu.lim : c_sc.lim; }
+__device__ __forceinline__ double* joint_kin(const JointArgs& A, size_t env) {
+    return (A.set ? A.buf.hkin : A.buf.kin) + env * SM_KIN_STRIDE;
 }
 __device__ __forceinline__ float joint_action(const JointArgs& A, int env, int j) {
     if (A.random_actions) {  // get_random_action (safe_motions_base.py:1327-1328)
         uint4 r = philox((uint32_t)(env + A.env_base), A.step_counter, (uint32_t)j, 0xAC71u, A.k0, A.k1);
         return 2.0f * u01f(r.x) - 1.0f;
     }
-    return A.buf.actions[(size_t)env * c_sc.n_joints + j];
+    return (A.set ? A.buf.hactions : A.buf.actions)[(size_t)env * A.nj + j];
 }
 
 // Action mapping, the S interpolated setpoints with the motor-tracked pose, the new knot (actions.py:268-280,
 // :412-443; safe_motions_base.py:1179-1185, :1233-1277).  Returns the relative jerk of the step (rewards.py:181-186).
-__device__ __forceinline__ float joint_advance(double* kin, float* scr, int j, double q, double v, double a, double qa,
-                                               double lo, double hi, float uf) {
+__device__ __forceinline__ float joint_advance_a1(double* kin, float* scr, int j, double q, double v, double a, double qa,
+                                                  double a1, double track_vel, bool store_qset, double jerk_max) {
     const int S = c_sc.substeps;
-    const double a1 = map_action((double)uf, lo, hi);
     const double dt = xdiv(c_sc.ts, (double)S);
-    const double tvdt = xmul(c_sc.track_vel, dt);
+    const double tvdt = xmul(track_vel, dt);
     const double jerk = xdiv(xsub(a1, a), c_sc.ts);      // actions.py:468-487, hoisted out of the sub-step loop
     const double hj = xmul(0.5, jerk), ha = xmul(0.5, a), sj = xmul(1.0 / 6.0, jerk);
     double q1 = q, v1 = v;
@@ -70,12 +81,22 @@ __device__ __forceinline__ float joint_advance(double* kin, float* scr, int j, d
         double vs = xadd(xadd(v, xmul(a, tk)), xmul(xmul(hj, tk), tk));
         double qs = xadd(xadd(xadd(q, xmul(v, tk)), xmul(xmul(ha, tk), tk)), xmul(xmul(xmul(sj, tk), tk), tk));
         scr[(k - 1) * SM_MAX_JOINTS + j] = (float)qa;    // pose seen by the collision detection of sub-step k
-        if (c_sc.use_target_points) scr[SM_QSET_OFF + (k - 1) * SM_MAX_JOINTS + j] = (float)qs;  // ctlp.py:2787-2791
+        if (store_qset) scr[SM_QSET_OFF + (k - 1) * SM_MAX_JOINTS + j] = (float)qs;  // ctlp.py:2787-2791
         qa = xadd(xadd(qa, xmul(c_sc.track_kp, xsub(qs, qa))), xmul(tvdt, vs));
         q1 = qs; v1 = vs;                                // k == S: the new knot
     }
     kin[j] = q1; kin[8 + j] = v1; kin[16 + j] = a1; kin[24 + j] = qa;
-    return (float)(fabs(jerk) / c_sc.jerk_max[j]);
+    return (float)(fabs(jerk) / jerk_max);
+}
+__device__ __forceinline__ float joint_advance(const JointArgs& A, double* kin, float* scr, int j, double q, double v,
+                                               double a, double qa, double lo, double hi, float uf) {
+    const double a1 = map_action((double)uf, lo, hi);
+    if (A.defer) {   // human: the braking-trajectory check comes first
+        double* ro = A.range_out + ((size_t)(kin - (A.set ? A.buf.hkin : A.buf.kin)) / SM_KIN_STRIDE * 8 + j) * 4;
+        ro[0] = lo; ro[1] = hi; ro[2] = a1;
+        return 0.0f;
+    }
+    return joint_advance_a1(kin, scr, j, q, v, a, qa, a1, A.track_vel, A.store_qset != 0, joint_limits(A).jerk_max[j]);
 }
 
 // First pass: every (env, joint) whose position bounds are certainly inactive (the common case) is finished here;
@@ -85,11 +106,12 @@ __global__ void __launch_bounds__(256) joint_kernel(JointArgs A) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int env = t >> 3, j = t & 7;
-    const int nj = c_sc.n_joints;
+    const int nj = A.nj;
     const bool valid = env < A.n;
     const bool jl = valid && j < nj;
     const size_t e = valid ? (size_t)env : 0;
-    double* kin = A.buf.kin + e * SM_KIN_STRIDE;
+    double* kin = joint_kin(A, e);
+    const JointLim& L = joint_limits(A);
     float* scr = A.scratch + e * SM_SCRATCH_FLOATS;
     float uf = 0.0f, jerk_rel = 0.0f;
     int code = 0;
@@ -98,8 +120,8 @@ __global__ void __launch_bounds__(256) joint_kernel(JointArgs A) {
         const double q = kin[j], v = kin[8 + j], a = kin[16 + j], qa = kin[24 + j];
         uf = joint_action(A, env, j);
         double lo, hi;
-        safe_range_light(j, q, v, a, lo, hi, code, defer);
-        if (!defer) jerk_rel = joint_advance(kin, scr, j, q, v, a, qa, lo, hi, joint_exec_action(A, env, j, uf));
+        safe_range_light(L, j, q, v, a, lo, hi, code, defer);
+        if (!defer) jerk_rel = joint_advance(A, kin, scr, j, q, v, a, qa, lo, hi, joint_exec_action(A, env, j, uf));
         else code = 0;  // reported by joint_heavy_kernel
     } else if (valid) {
         for (int k = 0; k < c_sc.substeps; ++k) scr[k * SM_MAX_JOINTS + j] = 0.0f;
@@ -125,7 +147,7 @@ __global__ void __launch_bounds__(256) joint_kernel(JointArgs A) {
         float val = j == SM_MISC_RCODE ? __int_as_float((int)rc) : j == SM_MISC_JERK ? jerk_rel : j == SM_MISC_UMAX ? um : 0.0f;
         scr[SM_MISC_OFF + j] = val;
     }
-    if (t == 0 && A.worklist) { A.worklist[0] = 0; A.worklist[1] = 0; }
+    if (t == 0 && A.worklist) { A.worklist[0] = 0; if (!A.keep_overflow) A.worklist[1] = 0; }
     if (t == 0 && A.cwork) A.cwork[0] = 0;
     if (t == 0 && A.tasks) A.tasks[0] = 0;
 }
@@ -152,15 +174,16 @@ __global__ void __launch_bounds__(SM_HEAVY_THREADS) joint_first_kernel(JointArgs
         if (i < n_heavy) {
             const int t = A.heavy[1 + i];
             const int env = t >> 3, j = t & 7;
-            const double* kin = A.buf.kin + (size_t)env * SM_KIN_STRIDE;
+            const double* kin = joint_kin(A, (size_t)env);
+            const JointLim& L = joint_limits(A);
             const double q = kin[j], v = kin[8 + j], a = kin[16 + j];
             double lo, hi;
             int code;
             bool need_pos;
-            safe_range_light(j, q, v, a, lo, hi, code, need_pos);
-            const double J = c_sc.jerk_max[j], Am = c_sc.acc_max[j];
-            const double fr_hi = pos_upper_first(q, v, a, c_sc.pos_hi[j], hi, J, Am, ts);
-            const double fr_lo = pos_upper_first(-q, -v, -a, -c_sc.pos_lo[j], -lo, J, Am, ts);
+            safe_range_light(L, j, q, v, a, lo, hi, code, need_pos);
+            const double J = L.jerk_max[j], Am = L.acc_max[j];
+            const double fr_hi = pos_upper_first(q, v, a, L.pos_hi[j], hi, J, Am, ts);
+            const double fr_lo = pos_upper_first(-q, -v, -a, -L.pos_lo[j], -lo, J, Am, ts);
             double* hp = A.hpar + (size_t)i * SM_HPAR;
             hp[0] = lo; hp[1] = hi; hp[2] = (double)code; hp[3] = fr_hi; hp[4] = fr_lo; hp[5] = SM_BIG; hp[6] = SM_BIG;
             t_hi = fr_hi > 0.0;
@@ -207,6 +230,7 @@ __global__ void __launch_bounds__(SM_HEAVY_THREADS) joint_solve_kernel(JointArgs
     double p = 0, v = 0, a = 0, an = 0, best = 0;                      // braking profile under evaluation
     double dp = 0, dv = 0, da = 0, dan = 1, dbest = 0;                 // its derivative with respect to the iterate
     int pit = 0;
+    unsigned n_intervals = 0;   // braking-profile intervals this lane evaluated (counting mode: algorithmic flops of the solve)
 #pragma unroll 1
     while (true) {
         const unsigned idle = __ballot_sync(FULL, !busy);
@@ -217,15 +241,16 @@ __global__ void __launch_bounds__(SM_HEAVY_THREADS) joint_solve_kernel(JointArgs
                 const int task = A.tasks[1 + my], i = task >> 1, sd = task & 1;
                 const int t = A.heavy[1 + i];
                 const int env = t >> 3, j = t & 7;
-                const double* kin = A.buf.kin + (size_t)env * SM_KIN_STRIDE;
+                const double* kin = joint_kin(A, (size_t)env);
+                const JointLim& L = joint_limits(A);
                 double* hp = A.hpar + (size_t)i * SM_HPAR;
                 const double sg = sd == 0 ? 1.0 : -1.0;
                 P0 = sg * kin[j]; V0 = sg * kin[8 + j]; A0 = sg * kin[16 + j];
-                pmax = sd == 0 ? c_sc.pos_hi[j] : -c_sc.pos_lo[j];
+                pmax = sd == 0 ? L.pos_hi[j] : -L.pos_lo[j];
                 lo = sd == 0 ? hp[0] : -hp[1];
                 xr = sd == 0 ? hp[1] : -hp[0];        // hi
                 fr = hp[3 + sd];
-                J = c_sc.jerk_max[j]; Am = c_sc.acc_max[j];
+                J = L.jerk_max[j]; Am = L.acc_max[j];
                 out = hp + 5 + sd;
                 phase = 0; x = lo;
                 p = P0; v = V0; a = A0; an = x; best = P0; pit = 0;
@@ -237,6 +262,7 @@ __global__ void __launch_bounds__(SM_HEAVY_THREADS) joint_solve_kernel(JointArgs
         if (!busy) continue;
         // ---------------- one interval of the braking profile (body of pos_peak_impl<true>)
         bool eval_done = false;
+        ++n_intervals;
         {
             const double j = xdiv(xsub(an, a), ts);
             const double dj = xdiv(xsub(dan, da), ts);
@@ -317,6 +343,11 @@ __global__ void __launch_bounds__(SM_HEAVY_THREADS) joint_solve_kernel(JointArgs
         }
     }
     if (A.counters && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&A.counters[9], (unsigned long long)n_task);
+    if (A.counters) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n_intervals += __shfl_xor_sync(FULL, n_intervals, o);
+        if (lane == 0 && n_intervals) atomicAdd(&A.counters[7], (unsigned long long)n_intervals);
+    }
 }
 
 __global__ void __launch_bounds__(SM_HEAVY_THREADS) joint_final_kernel(JointArgs A) {
@@ -325,7 +356,7 @@ __global__ void __launch_bounds__(SM_HEAVY_THREADS) joint_final_kernel(JointArgs
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_heavy; i += gridDim.x * blockDim.x) {
         const int t = A.heavy[1 + i];
         const int env = t >> 3, j = t & 7;
-        double* kin = A.buf.kin + (size_t)env * SM_KIN_STRIDE;
+        double* kin = joint_kin(A, (size_t)env);
         float* scr = A.scratch + (size_t)env * SM_SCRATCH_FLOATS;
         const double q = kin[j], v = kin[8 + j], a = kin[16 + j], qa = kin[24 + j];
         const double* hp = A.hpar + (size_t)i * SM_HPAR;
@@ -333,7 +364,7 @@ __global__ void __launch_bounds__(SM_HEAVY_THREADS) joint_final_kernel(JointArgs
         int code = (int)hp[2];
         if (c_sc.limit_position) clamp_range(lo, hi, -hp[6], hp[5], CODE_POS_HI, CODE_POS_LO, code);
         const float uf = joint_exec_action(A, env, j, joint_action(A, env, j));
-        const float jerk_rel = joint_advance(kin, scr, j, q, v, a, qa, lo, hi, uf);
+        const float jerk_rel = joint_advance(A, kin, scr, j, q, v, a, qa, lo, hi, uf);
         // non-negative floats order like their bit patterns
         atomicMax(reinterpret_cast<int*>(scr + SM_MISC_OFF + SM_MISC_JERK), __float_as_int(jerk_rel));
         if (code) atomicOr(reinterpret_cast<int*>(scr + SM_MISC_OFF + SM_MISC_RCODE), code);

@@ -12,8 +12,8 @@ struct WarpScratch {
     double ob[SM_OBST_STRIDE];              // the env's obstacle record (broadcast reads instead of shuffles)
     Xf fr[1 + SM_MAX_JOINTS];               // robot frames at the end-of-step setpoint pose
     Xf fr2[1 + SM_MAX_JOINTS];              // robot frames of one sub-step (narrow phase)
-    Xf obx[SM_MAX_OBSTACLES];               // obstacle poses at the end of the step
-    Xf obx2[SM_MAX_OBSTACLES];              // obstacle poses of one sub-step
+    Xf obx[SM_MAX_OBST_FRAMES];             // obstacle frames at the end of the step (human: base + 8 joint frames)
+    Xf obx2[SM_MAX_OBST_FRAMES];            // obstacle frames of one sub-step
     float pc[SM_MAX_SHAPES][3];             // world position of every shape's bounding-sphere centre (distance planning)
     float pg[SM_MAX_SHAPES][3];             // world position of every shape's centroid
 };
@@ -190,8 +190,10 @@ __device__ __forceinline__ double normalize_mm(double x, double lo, double hi) {
 // kin: the env's kinematic record in global memory (q[8] v[8] a[8] ...); ob: obstacle record (16 doubles)
 // tp: the env's target-point record (NULL unless the scene uses target points)
 // The entries are spread over `stride` lanes, `lane` = 0 .. stride - 1 (a warp per env, or 8 lanes per env).
+// hobs: the nested env's observation (Human scene): its kinematic part is the human's share of this observation
+// (Human.kinematic_observation, observations.py:100-110, :294-307)
 __device__ __noinline__ void write_observation(float* obs, const double* kin, const double* ob, const double* tp,
-                                               int lane, int stride = 32) {
+                                               int lane, int stride = 32, const float* hobs = nullptr) {
     const int nj = c_sc.n_joints;
     const int n_tp = (c_sc.use_target_points && tp) ? 3 * c_sc.obs_add_tp_pos + 3 * c_sc.obs_add_tp_rel : 0;
 #pragma unroll 1
@@ -212,6 +214,10 @@ __device__ __noinline__ void write_observation(float* obs, const double* kin, co
             }
         } else {
             int r = i - 3 * nj - n_tp;
+            if (c_sc.hu.enabled) {
+                if (hobs) obs[i] = hobs[r];
+                continue;
+            }
             if (c_sc.n_obstacles > 0 && c_sc.obst_kind[0] == SM_OBST_BALL) {
                 double t = ob[SM_OB_BALL_T];
                 if (r < 3) {
@@ -299,3 +305,80 @@ __device__ __forceinline__ void frames_from_q32(const SceneSmem& sm, const float
     sincosf(qrow[lane & 7], &s, &c);
     fk_scan(sm, c, s, out, lane);
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// forward kinematics of the human: frame 0 = base, 1 + j = child link of joint j; two serial arms of four joints
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void human_base(Xf& B) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) B.r[i] = c_sc.hu.baseR[i];
+    B.t[0] = c_sc.hu.baset[0]; B.t[1] = c_sc.hu.baset[1]; B.t[2] = c_sc.hu.baset[2];
+}
+// one joint of an arm: F <- F o [R_fix Rot(axis_j, q) | t_fix]; j is uniform over the calling lanes' loop
+__device__ __forceinline__ void human_chain_step(Xf& F, int j, float q) {
+    float s, c;
+    sincosf(q, &s, &c);
+    Xf L, C;
+    float Rj[9];
+    axis_angle(c_sc.hu.jaxis[j][0], c_sc.hu.jaxis[j][1], c_sc.hu.jaxis[j][2], c, s, Rj);
+    const float* A = c_sc.hu.jR[j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            L.r[3 * i + k] = fmaf(A[3 * i], Rj[k], fmaf(A[3 * i + 1], Rj[3 + k], A[3 * i + 2] * Rj[6 + k]));
+    L.t[0] = c_sc.hu.jt[j][0]; L.t[1] = c_sc.hu.jt[j][1]; L.t[2] = c_sc.hu.jt[j][2];
+    xf_compose(F, L, C);
+    F = C;
+}
+// all nine frames by one thread (q: 8 joint angles)
+__device__ __forceinline__ void human_fk_serial(const float* q, Xf* fr) {
+    human_base(fr[0]);
+#pragma unroll 1
+    for (int r = 0; r < 2; ++r) {
+        Xf F = fr[0];
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+            human_chain_step(F, 4 * r + i, q[4 * r + i]);
+            fr[1 + 4 * r + i] = F;
+        }
+    }
+}
+// warp version: lanes 0..7 each hold their joint's angle; the two arms are scanned as segments of four lanes
+__device__ __noinline__ void human_fk_scan(float q, Xf* out, int lane) {
+    const int j = lane & 7;
+    float s, c;
+    sincosf(q, &s, &c);
+    Xf X;
+    {
+        float Rj[9];
+        axis_angle(c_sc.hu.jaxis[j][0], c_sc.hu.jaxis[j][1], c_sc.hu.jaxis[j][2], c, s, Rj);
+        const float* A = c_sc.hu.jR[j];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                X.r[3 * i + k] = fmaf(A[3 * i], Rj[k], fmaf(A[3 * i + 1], Rj[3 + k], A[3 * i + 2] * Rj[6 + k]));
+        X.t[0] = c_sc.hu.jt[j][0]; X.t[1] = c_sc.hu.jt[j][1]; X.t[2] = c_sc.hu.jt[j][2];
+    }
+#pragma unroll
+    for (int d = 1; d < 4; d <<= 1) {
+        Xf P, C;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) P.r[i] = __shfl_up_sync(FULL, X.r[i], d, 4);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) P.t[i] = __shfl_up_sync(FULL, X.t[i], d, 4);
+        xf_compose(P, X, C);
+        if ((j & 3) >= d) X = C;
+    }
+    Xf B, W;
+    human_base(B);
+    xf_compose(B, X, W);
+    if (lane == 0) out[0] = B;
+    if (lane < SM_HUMAN_JOINTS) out[1 + lane] = W;
+    __syncwarp();
+}
+__device__ __forceinline__ V3 human_link_point(const Xf* fr, int r) {
+    return xf_apply(fr[4 * (r + 1)], c_sc.hu.tp_local[r][0], c_sc.hu.tp_local[r][1], c_sc.hu.tp_local[r][2]);
+}
+

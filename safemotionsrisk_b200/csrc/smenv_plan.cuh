@@ -27,6 +27,7 @@ struct PlanArgs {
     int advance;             // 1: obstacle poses at the end of the step about to be finished; 0: poses as recorded
     int* cwork;              // [0] = count, [1..] = spans (env * 8 + span) whose contacts need the fine planning
     double* target;          // [n][SM_TP_STRIDE] target-point records (the step only), or NULL
+    const double* hkin;      // Human scene: [n][SM_KIN_STRIDE] joint state of the human (its knot pose is the obstacle pose)
     unsigned long long* counters;
 };
 
@@ -417,11 +418,14 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) distance_plan_kernel(
             }
             if (!active) moving = false;  // not in the list of observed obstacles (ctlp.py:3239-3245)
             if (lane == 0) ball_pose(W.ob, ball_t, W.obx[0]);
+        } else if (kind == SM_OBST_HUMAN) {
+            // the human at its setpoint pose (set_position_in_obstacle_client_to_setpoints, ctlp.py:3246-3251)
+            human_fk_scan(A.hkin ? (float)A.hkin[(size_t)env * SM_KIN_STRIDE + (lane & 7)] : 0.0f, W.obx, lane);
         } else {
             moving = false;
         }
         frames_from_q32f(sm, (float)q1, W.fr, lane);
-        if (lane < SM_RES_STRIDE)
+        if (lane < 4)   // slots 4.. belong to the human's braking-trajectory check
             A.res[(size_t)env * SM_RES_STRIDE + lane] = lane == 3 ? SM_RES_NO_CONTACT
                                                                    : fkey(lane == GJK_MOVING ? query + 0.002f : cap);
         __syncwarp();

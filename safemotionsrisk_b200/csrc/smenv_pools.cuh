@@ -17,7 +17,9 @@ struct PoolArgs {
     double* ball_pool;
     int ball_pool_n;
     uint32_t k0, k1;
+    const double* hstart_pool;   // Human scene: start states of the nested env, entry e pairs with start-pool entry e
 };
+#define SM_HPOOL_STRIDE 32     /* doubles per entry of the human start pool: q[8] v[8] a[8] spare[8] */
 
 __device__ __forceinline__ uint64_t key64(uint32_t k0, uint32_t k1) { return ((uint64_t)k1 << 32) | k0; }
 
@@ -199,6 +201,11 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) fill_start_pool_kerne
         Rng rng(key64(A.k0, A.k1), (uint32_t)e, 0x51A7u);
         double q = 0.0, v = 0.0, a = 0.0;
         uint32_t lane_ctr = 0;
+        if (kind == SM_OBST_HUMAN && A.hstart_pool) {   // the human of this pool entry, at its start pose
+            human_fk_scan((float)A.hstart_pool[(size_t)e * SM_HPOOL_STRIDE + (lane & 7)], W.obx, lane);
+        }
+#pragma unroll 1
+        for (int hretry = 0; hretry < 200; ++hretry) {
 #pragma unroll 1
         for (int outer = 0; outer < 1000; ++outer) {
             V3 tgt;
@@ -265,6 +272,16 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) fill_start_pool_kerne
         }
         // ---------------- obstacles at reset
         frames_from_q64(sm, q, W.fr, lane);
+        if (kind != SM_OBST_HUMAN || !A.hstart_pool) break;
+        {   // "Collision with human." (ctlp.py:2113-2121): the start pose keeps the minimum distance to the human
+            const float thr = (float)c_sc.min_start_distance;
+            const float d = min_pairs(verts, sm, 1, nullptr, sm.mov_reward, c_sc.n_mov_reward * c_sc.obst_shape_cnt[0],
+                                      c_sc.obst_shape_cnt[0], c_sc.obst_shape_off[0], thr + 0.005f, thr + 0.005f, W.fr, W.obx,
+                                      lane, nullptr);
+            __syncwarp();
+            if (!(d < thr)) break;
+        }
+        }
         double ob = 0.0;
         if (kind == SM_OBST_PLANET) {  // Planet.reset: random phase without contact (ctlp.py:4470-4501)
             int idx = 0;
@@ -383,7 +400,8 @@ __global__ void __launch_bounds__(256) reset_kernel(ResetArgs A) {
         if (lane == 0) target_episode_start(tp, e, nullptr, A.target_pool, A.target_pool_n, env, A.k0, A.k1);
         __syncwarp();
     }
-    write_observation(A.buf.obs + (size_t)env * c_sc.obs_size, e, e + SM_KIN_STRIDE, tp, lane);
+    write_observation(A.buf.obs + (size_t)env * c_sc.obs_size, e, e + SM_KIN_STRIDE, tp, lane, 32,
+                      A.buf.hobs ? A.buf.hobs + (size_t)env * SM_HOBS_STRIDE : nullptr);
 }
 
 // observation only (after smenv_set_state)
@@ -393,7 +411,8 @@ __global__ void __launch_bounds__(256) observation_kernel(SmBuffers buf, int n) 
     if (env >= n) return;
     write_observation(buf.obs + (size_t)env * c_sc.obs_size, buf.kin + (size_t)env * SM_KIN_STRIDE,
                       buf.obst + (size_t)env * SM_OBST_STRIDE,
-                      (c_sc.use_target_points && buf.target) ? buf.target + (size_t)env * SM_TP_STRIDE : nullptr, lane);
+                      (c_sc.use_target_points && buf.target) ? buf.target + (size_t)env * SM_TP_STRIDE : nullptr, lane, 32,
+                      buf.hobs ? buf.hobs + (size_t)env * SM_HOBS_STRIDE : nullptr);
 }
 
 // ---------------- parity hooks: pieces of the step on caller-supplied states

@@ -80,7 +80,9 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
             const int idx0 = (int)ob[SM_OB_INDEX];
             int idx_new = idx0;
             double ball_t = ob[SM_OB_BALL_T];
-            if (kind == SM_OBST_PLANET) {
+            if (kind == SM_OBST_HUMAN) {
+                if (kc > 0) latch = 1.0;                   // Human._collision_detected (ctlp.py:4888-4898)
+            } else if (kind == SM_OBST_PLANET) {
                 if (kc > 0) latch = 1.0;                   // ctlp.py:2631-2637
                 idx_new = (idx0 + S) % c_sc.planet_steps;  // S x Planet.update (ctlp.py:4503-4505)
             } else if (kind == SM_OBST_BALL && ball_active != 0.0) {
@@ -294,7 +296,9 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
         }
         __syncwarp();
         // ---------------- observation of the state the next action acts on (observations.py:313-351)
-        if (valid) write_observation(A.buf.obs + (size_t)env * c_sc.obs_size, kin_obs, ob, tp, sl, 8);
+        if (valid)
+            write_observation(A.buf.obs + (size_t)env * c_sc.obs_size, kin_obs, ob, tp, sl, 8,
+                              A.buf.hobs ? A.buf.hobs + (size_t)env * SM_HOBS_STRIDE : nullptr);
     }
     __syncthreads();
     if (A.buf.stats && tid < 16 && s_stats[tid] != 0.0) atomicAdd(&A.buf.stats[tid], s_stats[tid]);

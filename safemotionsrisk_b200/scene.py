@@ -116,6 +116,44 @@ def ball_target_height_time(initial_height, initial_z_speed, target_height):
     return np.nan
 
 
+def merge_chain(body):
+    """Merges the fixed joints of a compiled URDF into the frame of the nearest revolute ancestor.  Returns the revolute
+    joints (parent frame, fixed transform in front of the rotation, axis, limits), per link the frame that moves it
+    (0 = the body's root, 1 + j = child link of revolute joint j) and its fixed pose in that frame."""
+    n_links = len(body.link_names)
+    link_frame = np.zeros(n_links, dtype=np.int32)
+    link_X = [(np.eye(3), np.zeros(3)) for _ in range(n_links)]
+    joints = []
+    for i in range(1, n_links):
+        p = body.parent[i]
+        r_loc, t_loc = rpy_to_matrix(body.joint_rpy[i]), body.joint_xyz[i]
+        rp, tp = link_X[p]
+        r_abs, t_abs = rp @ r_loc, rp @ t_loc + tp
+        if body.joint_type[i] == 0:
+            link_frame[i] = link_frame[p]
+            link_X[i] = (r_abs, t_abs)
+        elif body.joint_type[i] == 1:
+            joints.append(dict(link=i, parent_frame=int(link_frame[p]), R=r_abs, t=t_abs,
+                               axis=body.joint_axis[i] / np.linalg.norm(body.joint_axis[i]),
+                               limit=body.joint_limit[i]))
+            link_frame[i] = len(joints)
+        else:
+            raise NotImplementedError("joint type of link " + body.link_names[i])
+    return joints, link_frame, link_X
+
+
+# human_network/params.json (the nested env's env_config; the keys that shape the path) and robot_scene_base.py:24-25
+HUMAN_ENV = dict(closest_point_safety_distance=0.01, collision_check_time=0.033, check_braking_trajectory_collisions=True,
+                 obstacle_scene=1, target_point_radius=0.065, target_point_sequence=1, target_link_offset=[0.0, 0.0, -0.185],
+                 trajectory_time_step=0.1, pos_limit_factor=1.0, vel_limit_factor=1.0, acc_limit_factor=1.0,
+                 jerk_limit_factor=1.0, log_std_range=[-1.375, 0.0])
+MAX_ACCELERATION_HUMAN_ARM = [15.0, 15.0, 15.0, 15.0]     # robot_scene_base.py:24
+MAX_JERK_HUMAN_ARM = [7500, 7500, 7500, 7500]             # robot_scene_base.py:25
+HUMAN_BASE_POSITION = [0.7, 0, -0.94]                     # robot_scene_base.py:177
+HUMAN_BASE_EULER = [0, 0, np.pi]                          # robot_scene_base.py:178
+BRAKING_TIMEOUT = 2.0                                     # ctlp.py:3467-3468
+
+
 class Scene:
     """Holds the ctypes ``SmScene`` plus the NumPy arrays it points into."""
 
@@ -131,24 +169,7 @@ class Scene:
 
         # ---------------- kinematic chain: merge fixed joints into the frame of the nearest revolute ancestor
         n_links = len(robot.link_names)
-        link_frame = np.zeros(n_links, dtype=np.int32)
-        link_X = [(np.eye(3), np.zeros(3)) for _ in range(n_links)]  # link frame expressed in its movable frame
-        joints = []
-        for i in range(1, n_links):
-            p = robot.parent[i]
-            r_loc, t_loc = rpy_to_matrix(robot.joint_rpy[i]), robot.joint_xyz[i]
-            rp, tp = link_X[p]
-            r_abs, t_abs = rp @ r_loc, rp @ t_loc + tp
-            if robot.joint_type[i] == 0:
-                link_frame[i] = link_frame[p]
-                link_X[i] = (r_abs, t_abs)
-            elif robot.joint_type[i] == 1:
-                joints.append(dict(link=i, parent_frame=int(link_frame[p]), R=r_abs, t=t_abs,
-                                   axis=robot.joint_axis[i] / np.linalg.norm(robot.joint_axis[i]),
-                                   limit=robot.joint_limit[i]))
-                link_frame[i] = len(joints)
-            else:
-                raise NotImplementedError("joint type of link " + robot.link_names[i])
+        joints, link_frame, link_X = merge_chain(robot)
         nj = len(joints)
         assert nj <= abi.SM_MAX_JOINTS
         self.n_joints = nj
@@ -244,9 +265,17 @@ class Scene:
         # ---------------- moving obstacles
         obstacles = []
         upd = ts / sc.substeps  # ctlp.py:97
+        human = None
         if cfg.human_network_checkpoint is not None:
-            raise NotImplementedError("the Human scene (nested env + human policy, ctlp.py:4647-4959) is not "
-                                      "implemented yet; see DESIGN.md")
+            if cfg.planet_mode or cfg.use_moving_objects:
+                raise NotImplementedError("a human together with planets or balls is not implemented")
+            if os.path.basename(os.path.dirname(os.path.dirname(str(cfg.human_network_checkpoint)))) != "human_network":
+                raise NotImplementedError("human_network_checkpoint: only the shipped human_network/checkpoint/checkpoint "
+                                          "(its weights are packaged in assets/networks_human.npz) is supported")
+            human = _Body(assets, "human")
+            observed = ["iiwa_link_2", "iiwa_link_3", "iiwa_link_4", "iiwa_link_5", "iiwa_link_6"] + \
+                ([target_link] if cfg.ball_machine_mode else ["iiwa_link_7"])     # ctlp.py:788-794
+            obstacles.append(dict(kind=abi.SM_OBST_HUMAN, body=human, observed=observed))
         if cfg.planet_mode:
             iss = _Body(assets, "obstacle_ISS", scale=0.6)       # ctlp.py:736-737
             ast = _Body(assets, "obstacle_asteroid", scale=1.0)  # ctlp.py:762-763
@@ -305,6 +334,11 @@ class Scene:
         sc.n_obstacles = len(obstacles)
         for o, ob in enumerate(obstacles):
             body = ob["body"]
+            if ob["kind"] == abi.SM_OBST_HUMAN:
+                self._add_human(sc, cfg, body, add_shape, shapes, robot, link_disc, mov_contact,
+                                table_sid if cfg.obstacle_scene == 5 else None, assets)
+                mov_reward = [sid for n in ob["observed"] for sid in link_shapes[n]]
+                continue
             sids = [add_shape(v, 100 + o, -1) for v in body.parts]
             sc.obst_kind[o] = ob["kind"]
             sc.obst_shape_off[o], sc.obst_shape_cnt[o] = sids[0], len(sids)
@@ -394,6 +428,8 @@ class Scene:
             obs_size += 6
         if cfg.planet_mode:
             obs_size += sc.obs_planet_size  # planet two is phase-coupled (observations.py:94-98)
+        if human is not None:
+            obs_size += 3 * sc.human.n_joints   # Human.kinematic_observation (observations.py:100-110, :294-307)
         # ---------------- target points of the reaching task (observations.py:56-77; ctlp.py:184-235)
         sc.use_target_points = int(bool(cfg.use_target_points))
         self.obs_target_size = 0
@@ -446,6 +482,129 @@ class Scene:
         sc.plane_z = -0.94   # robot_scene_base.py:172
 
     # ------------------------------------------------------------------------------------------------------
+    def _add_human(self, sc, cfg, body, add_shape, shapes, robot, link_disc, mov_contact, table_sid, assets):
+        """The human obstacle: kinematic tree, limits, shapes, contact thresholds, the pair list of the nested env's
+        braking-trajectory check, target points, sampling constants (ctlp.py:4647-4959, human_network/params.json)."""
+        h = sc.human
+        he = HUMAN_ENV
+        joints, link_frame, link_X = merge_chain(body)
+        assert len(joints) == abi.SM_HUMAN_JOINTS
+        h.enabled, h.n_joints = 1, len(joints)
+        self.human_joints, self.human_link_frame, self.human_link_X, self.human_body = joints, link_frame, link_X, body
+        base_r = rpy_to_matrix(HUMAN_BASE_EULER)
+        h.base_R[:] = list(base_r.reshape(-1))
+        h.base_t[:] = list(np.asarray(HUMAN_BASE_POSITION, dtype=np.float64))
+        ts = float(cfg.trajectory_time_step)
+        if abs(ts - he["trajectory_time_step"]) > 1e-12:
+            raise NotImplementedError("the human's nested env runs at trajectory_time_step 0.1 (human_network/params.json)")
+        for j, jt in enumerate(joints):
+            h.joint_parent[j] = jt["parent_frame"]
+            h.joint_R[j][:] = list(jt["R"].reshape(-1))
+            h.joint_t[j][:] = list(jt["t"])
+            h.joint_axis[j][:] = list(jt["axis"])
+            h.pos_lo[j] = jt["limit"][0] * he["pos_limit_factor"]      # no safety buffer (robot_scene_base.py:351-352)
+            h.pos_hi[j] = jt["limit"][1] * he["pos_limit_factor"]
+            h.vel_max[j] = jt["limit"][3] * he["vel_limit_factor"]
+            acc = MAX_ACCELERATION_HUMAN_ARM[j % 4] * he["acc_limit_factor"]
+            h.acc_max[j] = acc
+            h.jerk_max[j] = min(2 * acc / ts, MAX_JERK_HUMAN_ARM[j % 4]) * he["jerk_limit_factor"]
+        self.human_pos_lo = np.array([h.pos_lo[j] for j in range(8)])
+        self.human_pos_hi = np.array([h.pos_hi[j] for j in range(8)])
+        self.human_vel_max = np.array([h.vel_max[j] for j in range(8)])
+        self.human_acc_max = np.array([h.acc_max[j] for j in range(8)])
+        # ---- shapes: the arms (obstacle links, ctlp.py:4772-4774) first, then the rest of the body
+        arm_links = ["upper_arm_r0", "forearm_r0", "hand_r0", "upper_arm_r1", "forearm_r1", "hand_r1"]
+        body_links = ["shoes", "lower_legs", "upper_legs", "body", "head"]
+        hshapes = {}   # link name -> shape ids
+        link_ids = {}
+        h.shape_off = len(shapes)
+        for name in arm_links + body_links:
+            li = body.link_index(name)
+            link_ids[name] = len(link_ids)
+            r_x, t_x = link_X[li]
+            for pi, v in enumerate(body.parts):
+                if int(body.part_link[pi]) != li or body.part_kind[pi] == "point":
+                    continue   # the 1e-5 m spheres of the dummy links are left out
+                sid = add_shape(v @ r_x.T + t_x, 100 + int(link_frame[li]), -1)
+                h.shape_link[sid - h.shape_off] = link_ids[name]
+                hshapes.setdefault(name, []).append(sid)
+            if name == arm_links[-1]:
+                h.n_arm_shapes = len(shapes) - h.shape_off
+        h.n_shapes = len(shapes) - h.shape_off
+        assert h.n_shapes <= 64 and len(link_ids) <= abi.SM_MAX_HLINKS
+        self.human_shapes = hshapes
+        sc.obst_kind[0] = abi.SM_OBST_HUMAN
+        sc.obst_shape_off[0], sc.obst_shape_cnt[0] = h.shape_off, h.n_arm_shapes
+        # bounding sphere of the whole human about its base for the coarse tests: arms stretched out reach ~0.9 m
+        # from the shoulders; computed from the link frames at every joint-limit corner would be tighter, a sphere
+        # about the trunk centre with the arm length is enough here
+        allv = np.concatenate([shapes[s]["verts"] for n in body_links for s in hshapes[n]])
+        centre = 0.5 * (allv.min(0) + allv.max(0))
+        sc.obst_center[0][:] = list(centre)
+        sc.obst_radius[0] = float(np.linalg.norm(allv - centre, axis=1).max()) + 1.0
+        # ---- contact thresholds per (human link, robot contact slot) (SURVEY Appendix B.5)
+        for name, lid in link_ids.items():
+            li = body.link_index(name)
+            disc_h = self._angular_motion_disc([body.parts[pi] for pi in range(len(body.parts))
+                                                if int(body.part_link[pi]) == li and body.part_kind[pi] != "point"],
+                                               body.inertial_xyz[li])
+            for slot, sid in enumerate(mov_contact):
+                rname = robot.link_names[shapes[sid]["link"]]
+                h.contact_thresh[lid][slot] = CONTACT_BREAKING_FACTOR * min(disc_h, link_disc[rname])
+        # ---- braking-trajectory check of the nested env: table x {forearm, hand} (ctlp.py:2503-2518), self-collision
+        # link pairs in which forearm or hand takes part (ctlp.py:1409-1437, :3347-3374)
+        if table_sid is None:   # the nested env has its own table (obstacle_scene = 1 > 0) even if the main scene has none
+            table = _Body(assets, "obstacle_table")
+            corners = table.parts[0]
+            centre_t = corners.mean(0)
+            half = np.abs(corners - centre_t).max(0)
+            table_sid = add_shape(centre_t + np.sign(corners - centre_t) * (half - URDF_MARGIN), 0, -1)
+        active = {"forearm_r0", "hand_r0", "forearm_r1", "hand_r1"}
+        pairs = []
+        for name in ("forearm_r0", "hand_r0", "forearm_r1", "hand_r1"):
+            pairs += [(a, table_sid) for a in hshapes[name]]
+        self_links = {n: [] for n in arm_links}
+        for n in arm_links[:3]:
+            self_links[n] += arm_links[3:]                      # arm r0 against arm r1
+        for n in arm_links:
+            self_links[n] += ["body", "head"]
+        for a_name in arm_links:
+            for b_name in self_links[a_name]:
+                if a_name in active or b_name in active:
+                    pairs += [(a, b) for a in hshapes[a_name] for b in hshapes[b_name]]
+        assert len(pairs) <= abi.SM_MAX_HPAIRS, len(pairs)
+        h.n_brake_pairs = len(pairs)
+        for i, (a, b) in enumerate(pairs):
+            h.brake_pairs[i][0], h.brake_pairs[i][1] = a, b
+        self.human_brake_pairs = pairs
+        h.check_braking = int(bool(he["check_braking_trajectory_collisions"]))
+        h.brake_checks = int(round(max(1, ts / he["collision_check_time"])))   # ctlp.py:99-103
+        h.brake_safety = he["closest_point_safety_distance"]
+        h.brake_timeout = BRAKING_TIMEOUT
+        # ---- target points (target_point_cartesian_range_scene 9, ctlp.py:186-189, :221-223)
+        for r, name in enumerate(("hand_r0", "hand_r1")):
+            li = body.link_index(name)
+            assert link_frame[li] == 4 * (r + 1), "the hand is expected to hang off the arm's last joint"
+            r_x, t_x = link_X[li]
+            h.tp_local[r][:] = list(r_x @ np.asarray(he["target_link_offset"]) + t_x)
+        box = [[0.0, 0.6], [-0.8, 0.8], [0.075, 0.75]]
+        rel = [[-1.4, -1.6, -1.5], [1.4, 1.6, 1.5]]
+        for i in range(3):
+            h.tp_box_min[i], h.tp_box_max[i] = box[i][0], box[i][1]
+            h.tp_rel_min[i], h.tp_rel_max[i] = rel[0][i], rel[1][i]
+            h.start_box_min[i], h.start_box_max[i] = box[i][0], box[i][1]     # ctlp.py:186-188
+        h.tp_radius = he["target_point_radius"]
+        h.tp_min_static = he["closest_point_safety_distance"] + 0.09         # ctlp.py:1661-1662
+        h.tp_min_self = he["closest_point_safety_distance"]                  # ctlp.py:2220
+        h.log_std_lo, h.log_std_hi = he["log_std_range"]
+        sampling = bool(cfg.human_network_use_collision_avoidance_starting_point_sampling)
+        h.kinematic_sampling_probability = \
+            cfg.human_network_collision_avoidance_kinematic_state_sampling_probability if sampling else 0.0
+        h.stay_in_state_probability = cfg.human_network_collision_avoidance_stay_in_state_probability if sampling else 1.0
+        h.min_start_static = he["closest_point_safety_distance"] + 0.09      # ctlp.py:1475-1477
+        h.min_start_self = he["closest_point_safety_distance"] + 0.04
+        h.obs_size = 3 * 8 + 2 * 3 + 2 * 3 + 2                               # observations.py:54-77
+
     @staticmethod
     def _angular_motion_disc(parts, inertial_xyz):
         """btCollisionShape::getAngularMotionDisc of a link's collision object (SURVEY Appendix B.5): the shape is

@@ -92,12 +92,23 @@ class SafeMotionsVecEnv:
         # target-point records of the reaching task (use_target_points), else absent
         self.target = torch.zeros((n, abi.SM_TP_STRIDE), dtype=torch.float64, device=dev) \
             if self.scene.struct.use_target_points else None
+        # Human scene: state of the nested env that moves the human's arms (ctlp.py:4647-4959)
+        self.has_human = bool(self.scene.struct.human.enabled)
+        self.hkin = self.hstate = self.hbrake = self.hobs = self.hactions = None
+        if self.has_human:
+            self.hkin = torch.zeros((n, abi.SM_KIN_STRIDE), dtype=torch.float64, device=dev)
+            self.hstate = torch.zeros((n, abi.SM_HSTATE_STRIDE), dtype=torch.float64, device=dev)
+            self.hbrake = torch.zeros((n, abi.SM_HBRAKE_STEPS * abi.SM_HUMAN_JOINTS), dtype=torch.float64, device=dev)
+            self.hobs = torch.zeros((n, abi.SM_HOBS_STRIDE), dtype=torch.float32, device=dev)
+            self.hactions = torch.zeros((n, abi.SM_HUMAN_JOINTS), dtype=torch.float32, device=dev)
+        opt = lambda t: t.data_ptr() if t is not None else None
         self._buf = abi.SmBuffers(
             kin=self.kin.data_ptr(), obst=self.obst.data_ptr(), episode=self.episode.data_ptr(),
             ep_return=self.ep_return.data_ptr(), actions=self.actions.data_ptr(), obs=self.obs.data_ptr(),
             reward=self.reward.data_ptr(), done=self.done.data_ptr(), term_reason=self.term_reason.data_ptr(),
-            info=self.info.data_ptr(), stats=self.stats.data_ptr(),
-            target=self.target.data_ptr() if self.target is not None else None)
+            info=self.info.data_ptr(), stats=self.stats.data_ptr(), target=opt(self.target),
+            hkin=opt(self.hkin), hstate=opt(self.hstate), hbrake=opt(self.hbrake), hobs=opt(self.hobs),
+            hactions=opt(self.hactions))
         # pinned host staging for the host-buffer API (step_host)
         self._h_actions = torch.zeros((n, nj), dtype=torch.float32).pin_memory()
         self.host_actions = self._h_actions.numpy()   # pinned input buffer of step_host
@@ -112,6 +123,8 @@ class SafeMotionsVecEnv:
         self._networks = False
         self._gate_threshold = None
         self._auto_reset_done = None   # envs the last step re-initialised on the device (see reset_at)
+        if self.has_human:
+            self.load_human_policy()
         if fill_pools:
             self.fill_pools(self._seed)
         # risk gate as the reference wires it (safe_motions_base.py:527-579, actions.py:303-340): risk_config_dir names
@@ -194,6 +207,52 @@ class SafeMotionsVecEnv:
     def fill_pools(self, seed=0):
         cabi.check(self._lib.smenv_fill_pools(self._handle, int(seed), self._stream()), "smenv_fill_pools")
         self._pools_filled = True
+
+    def human_pools(self):
+        """(start states of the nested env [P, 32] = q, v, a, spare; target points [2, T, 4] per arm), host copies."""
+        ps, pt = C.c_int(), C.c_int()
+        cabi.check(self._lib.smenv_human_pool_sizes(self._handle, C.byref(ps), C.byref(pt)), "smenv_human_pool_sizes")
+        start, target = np.zeros((ps.value, 32)), np.zeros((2, pt.value, 4))
+        cabi.check(self._lib.smenv_copy_human_pools(self._handle, start.ctypes.data, target.ctypes.data),
+                   "smenv_copy_human_pools")
+        return start, target
+
+    def set_human_state(self, hq, hv, ha, first_target, active_arm, mask=None):
+        """Injects the start state of the nested env (parity protocol): joint state [N, 8], the first target point
+        [N, 3] and the arm [N] it belongs to; call after set_state."""
+        def prep(x, cols, dtype=torch.float64):
+            t = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x, dtype=dtype)
+            return t.reshape(self.num_envs, cols).to(self.device).contiguous() if cols else \
+                t.reshape(self.num_envs).to(self.device).contiguous()
+        tq, tv, ta, tt = prep(hq, 8), prep(hv, 8), prep(ha, 8), prep(first_target, 3)
+        tarm = prep(active_arm, 0, torch.int32)
+        tm = None if mask is None else torch.as_tensor(mask, dtype=torch.uint8, device=self.device).contiguous()
+        cabi.check(self._lib.smenv_set_human_state(self._handle, C.byref(self._buf), tq.data_ptr(), tv.data_ptr(),
+                                                   ta.data_ptr(), tt.data_ptr(), tarm.data_ptr(),
+                                                   C.c_void_p(tm.data_ptr()) if tm is not None else None,
+                                                   self._stream()), "smenv_set_human_state")
+        return self.obs
+
+    def set_human_actions_external(self, external=True):
+        """With external=True the step reads the human's actions from ``self.hactions`` instead of evaluating the
+        human's policy (parity tests: the reference samples them from a stochastic policy, ctlp.py:4701, :4827)."""
+        cabi.check(self._lib.smenv_set_human_actions_external(self._handle, int(bool(external))),
+                   "smenv_set_human_actions_external")
+
+    def load_human_policy(self, source=None):
+        """The policy that moves the human's arms (trained_networks/human_network, exported by
+        tools/export_networks.py): 38 -> 256 -> 128 -> 16 (means and log-std outputs), swish / tanh."""
+        if source is None:
+            source = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets", "networks_human.npz")
+        w = np.load(source)
+        layers = [(w["human/{}/kernel".format(k)], w["human/{}/bias".format(k)]) for k in ("fc_1", "fc_2", "fc_out")]
+        if layers[0][0].shape[0] != self.scene.struct.human.obs_size or layers[-1][0].shape[1] != 16:
+            raise ValueError("unexpected shape of the human policy")
+        dims = np.array([layers[0][0].shape[0]] + [k.shape[1] for k, _ in layers], dtype=np.int32)
+        flat = np.concatenate([np.concatenate([k.astype(np.float32).ravel(), b.astype(np.float32).ravel()])
+                               for k, b in layers])
+        cabi.check(self._lib.smenv_mlp_load(self._handle, abi.SM_NET_HUMAN, len(layers) - 1, dims.ctypes.data, 1, 1,
+                                            flat.ctypes.data), "smenv_mlp_load")
 
     def pools(self):
         """(start_pool [P, 48], ball_pool [B, 12] or None) copied to the host, for inspection and tests."""
@@ -424,13 +483,18 @@ class SafeMotionsVecEnv:
         nj = self.scene.n_joints
         return lo[:, :nj], hi[:, :nj], code[:, :nj]
 
-    def distances(self, kin=None, obst=None):
+    def distances(self, kin=None, obst=None, hkin=None):
         kin = self.kin if kin is None else torch.as_tensor(kin, dtype=torch.float64, device=self.device).contiguous()
         obst = self.obst if obst is None else torch.as_tensor(obst, dtype=torch.float64,
                                                               device=self.device).contiguous()
         n = kin.shape[0]
         out = [torch.zeros(n, dtype=torch.float32, device=self.device) for _ in range(3)]
-        cabi.check(self._lib.smenv_distances(self._handle, kin.data_ptr(), obst.data_ptr(), out[0].data_ptr(),
+        hp = None
+        if self.scene.struct.human.enabled:
+            hkin = self.hkin if hkin is None else torch.as_tensor(hkin, dtype=torch.float64,
+                                                                   device=self.device).contiguous()
+            hp = C.c_void_p(hkin.data_ptr())
+        cabi.check(self._lib.smenv_distances(self._handle, kin.data_ptr(), obst.data_ptr(), hp, out[0].data_ptr(),
                                              out[1].data_ptr(), out[2].data_ptr(), n, self._stream()),
                    "smenv_distances")
         return out
@@ -451,7 +515,7 @@ class SafeMotionsVecEnv:
         """Loads the risk network and the backup policy (weights exported from the reference's checkpoints by
         tools/export_networks.py).  source: path of an .npz, or None for the packaged weights of the env's scene."""
         if source is None:
-            scene = "ball" if self.config.use_moving_objects else "space"
+            scene = "human" if self.has_human else "ball" if self.config.use_moving_objects else "space"
             source = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets",
                                   "networks_{}.npz".format(scene))
         w = np.load(source)
@@ -508,12 +572,13 @@ class SafeMotionsVecEnv:
             self.set_risk_gate(prev)
 
     # ------------------------------------------------------------------ backup-client look-ahead (risk ground truth)
-    _STATE = ("kin", "obst", "episode", "ep_return", "target", "stats", "obs", "reward", "done", "term_reason", "info")
+    _STATE = ("kin", "obst", "episode", "ep_return", "target", "stats", "obs", "reward", "done", "term_reason", "info",
+              "hkin", "hstate", "hbrake", "hobs", "hactions")
 
     def snapshot(self):
         """Copy of the whole env state (the reference clones its Bullet state into a "backup client" with
         saveBullet / restoreState plus attribute copies, safe_motions_base.py:1801-1891; here it is a tensor copy)."""
-        return {k: getattr(self, k).clone() for k in self._STATE if getattr(self, k) is not None}
+        return {k: getattr(self, k).clone() for k in self._STATE if getattr(self, k, None) is not None}
 
     def restore(self, snap):
         for k, v in snap.items():
@@ -565,8 +630,9 @@ class SafeMotionsVecEnv:
             self.set_risk_gate(gate)
         return state, act, risky.float()
 
-    KERNELS = ("joint_kernel", "joint_heavy_kernel", "contact_plan_kernel", "distance_plan_kernel", "gjk_kernel",
-               "finish_kernel")
+    KERNELS = ("human_policy", "human_joint_kernels", "human_brake_traj_kernel", "human_brake_plan_kernel",
+               "human_brake_gjk", "human_advance_outcome", "joint_kernel", "joint_heavy_kernel", "contact_plan_kernel",
+               "distance_plan_kernel", "gjk_kernel", "finish_kernel")
 
     def kernel_timing(self, enable=True):
         """Measurement mode: every step brackets each of its kernels with CUDA events and synchronises."""
