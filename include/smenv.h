@@ -141,7 +141,10 @@ typedef struct SmHuman {
     /* start-state sampling of the nested env (ctlp.py:1461-1656 with the human_network_* keys) */
     double start_box_min[3], start_box_max[3];
     double kinematic_sampling_probability, stay_in_state_probability, min_start_static, min_start_self;
-    int32_t obs_size, reserved;                /* 38 */
+    int32_t obs_size;                          /* 38 */
+    int32_t initial_braking_trajectory;        /* the reset seeds the stored braking trajectory from the start state
+                                                  (always_use_collision_avoidance_starting_point_sampling,
+                                                  safe_motions_base.py:961-967, ctlp.py:1120-1139) */
 } SmHuman;
 
 typedef struct SmShape {
@@ -271,6 +274,32 @@ enum SmTargetSlot {
     SM_TP_REACHED = 11    /* 1 if the target point was reached in the step just finished */
 };
 
+/* Per-episode aggregation of the step info (what train.py:59-117 computes from the per-step info dicts of the reference:
+ * custom_metrics[key + "_average" / "_max" / "_min"]).  SM_EP_SCALARS step scalars are accumulated on the device in
+ * SmBuffers.epacc (sum, max, min); when an episode ends the record is copied to SmBuffers.epinfo (which survives the
+ * auto reset) and the accumulators restart. */
+#define SM_EP_SCALARS 16
+#define SM_EP_STRIDE 64   /* floats: sum[16] max[16] min[16], then the episode counters below, spare */
+enum SmEpisodeScalar {
+    SM_EP_COLL_SELF = 0, SM_EP_COLL_STATIC = 1, SM_EP_COLL_MOVING = 2,   /* collision_rate_* (safe_motions_base.py:1350-1355) */
+    SM_EP_ACTION_PUNISH = 3, SM_EP_R_SELF = 4, SM_EP_R_STATIC = 5, SM_EP_R_MOVING = 6, /* rewards.py:490-498 */
+    SM_EP_REWARD = 7,              /* reward (rewards.py:177-178) */
+    SM_EP_TP_REWARD = 8,           /* target_point_reward (rewards.py:380-389) */
+    SM_EP_RISKY_ACTION = 9,        /* risky_action_rate (actions.py:339-340) */
+    SM_EP_JOINT_VEL_NORM = 10,     /* joint_vel_norm (observations.py:405) */
+    SM_EP_POS_VIOLATION = 11, SM_EP_VEL_VIOLATION = 12, SM_EP_ACC_VIOLATION = 13, /* joint_*_violation (observations.py:406-408) */
+    SM_EP_JERK_VIOLATION = 14,     /* joint_jerk_violation (rewards.py:195-203) */
+    SM_EP_OBS_CLIPPING = 15        /* observation_clipping_rate (observations.py:410-413), kinematic entries */
+};
+enum SmEpisodeCounter {
+    SM_EPC_BALLS_HIT_ROBOT = 48,   /* moving_object_hit_robot_total (ctlp.py:1186-1206) */
+    SM_EPC_BALLS_MISSED = 49,      /* moving_object_missed_robot_total + moving_object_hit_obstacle_total */
+    SM_EPC_TARGETS_REACHED = 50,   /* obstacles_num_target_points_reached (ctlp.py:1158-1163) */
+    SM_EPC_FIRST_RISKY_STEP = 51,  /* risk_network_first_risky_action_step, -1 = none (safe_motions_base.py:1378) */
+    SM_EPC_LENGTH = 52, SM_EPC_RETURN = 53, SM_EPC_REASON = 54,
+    SM_EPC_HUMAN_BRAKED = 55       /* steps in which the human's nested env executed its braking trajectory */
+};
+
 /* Device buffers of one call (all caller-owned, N = num_envs). */
 typedef struct SmBuffers {
     double* kin;          /* [N][SM_KIN_STRIDE]  q, v, a, q_act */
@@ -290,6 +319,8 @@ typedef struct SmBuffers {
     double* hstate;       /* [N][SM_HSTATE_STRIDE] target points of both arms, braking-trajectory bookkeeping */
     double* hbrake;       /* [N][SM_HBRAKE_STEPS][SM_HUMAN_JOINTS] accelerations of the stored braking trajectory */
     float* hobs;          /* [N][SM_HOBS_STRIDE] observation of the nested env (input of the human's policy) */
+    float* epacc;         /* [N][SM_EP_STRIDE] running aggregates of the current episode; may be NULL (no aggregation) */
+    float* epinfo;        /* [N][SM_EP_STRIDE] aggregates of the last finished episode of every env; NULL iff epacc is */
     float* hactions;      /* [N][SM_HUMAN_JOINTS] actions of the human's policy: written by the step (policy network +
                              Philox noise), or read from here when smenv_set_human_actions_external(1) (parity tests) */
 } SmBuffers;

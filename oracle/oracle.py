@@ -129,6 +129,8 @@ class OracleEnvs:
             lib().smo_human_init(self.scene.pointer(), _p(self.hkin[e], C.c_double), _p(self.hstate[e], C.c_double),
                                  _p(hq[e], C.c_double), _p(hv[e], C.c_double), _p(ha[e], C.c_double),
                                  _p(ft[e], C.c_double), int(arm[e]), _p(self.hobs[e], C.c_float))
+            lib().smo_human_initial_braking(self.scene.pointer(), _p(self.hkin[e], C.c_double),
+                                            _p(self.hstate[e], C.c_double), _p(self.hbrake[e], C.c_double))
         nh = 3 * abi.SM_HUMAN_JOINTS
         self.obs[:, self.scene.obs_size - nh:] = self.hobs[:, :nh]
 

@@ -789,15 +789,28 @@ static int human_braking_acceleration(const SmScene* sc, const double* q, const 
         return 1;
     }
     for (int j = 0; j < h->n_joints; ++j) {
+        /* np.clip(end_acceleration, next_acc_min, next_acc_max) with the full safe range (_acc_range_function,
+         * ctlp.py:3496-3499), evaluated lazily: clip to the jerk / acceleration / velocity part of the range first; if the
+         * braking profile that follows the clipped value keeps both position limits, the position bounds cannot cut it
+         * (they are the largest / smallest accelerations with that property) and the iterative solve is not needed */
+        double J = h->jerk_max[j], A = h->acc_max[j], ts = sc->ts;
         double lo, hi;
         int32_t code;
-        safe_range_limits(sc->ts, h->jerk_max[j], h->acc_max[j], h->vel_max[j], h->pos_lo[j], h->pos_hi[j], 1, 1, q[j],
-                          v[j], a[j], &lo, &hi, &code);
-        double e = brake_target(v[j], a[j], h->jerk_max[j], h->acc_max[j], sc->ts);
+        safe_range_limits(ts, J, A, h->vel_max[j], h->pos_lo[j], h->pos_hi[j], 1, 0, q[j], v[j], a[j], &lo, &hi, &code);
+        double e = brake_target(v[j], a[j], J, A, ts);
         if (fabs(v[j]) < 0.01 && fabs(a[j]) < 0.01) e = 0.0;
-        if (e < lo) e = lo; /* np.clip(end_acceleration, next_acc_min, next_acc_max) */
-        if (e > hi) e = hi;
-        a_end[j] = e;
+        double ec = e;
+        if (ec < lo) ec = lo;
+        if (ec > hi) ec = hi;
+        int ok_hi = pos_peak(q[j], v[j], a[j], ec, J, A, ts) - h->pos_hi[j] <= 0.0;
+        int ok_lo = pos_peak(-q[j], -v[j], -a[j], -ec, J, A, ts) - (-h->pos_lo[j]) <= 0.0;
+        if (!(ok_hi && ok_lo)) {
+            safe_range_limits(ts, J, A, h->vel_max[j], h->pos_lo[j], h->pos_hi[j], 1, 1, q[j], v[j], a[j], &lo, &hi, &code);
+            ec = e;
+            if (ec < lo) ec = lo;
+            if (ec > hi) ec = hi;
+        }
+        a_end[j] = ec;
     }
     return 0;
 }
@@ -984,6 +997,29 @@ void smo_human_init(const SmScene* sc, double* hkin, double* hstate, const doubl
     tp[SM_TP_LAST_DIST] = tp[SM_TP_INIT_DIST] = sqrt(dx * dx + dy * dy + dz * dz);
     hstate[SM_HS_DRAWS] = 1.0;
     if (hobs) smo_human_observation(sc, hkin, hstate, hobs);
+}
+
+/* ObstacleWrapperBase.reset with compute_initial_braking_trajectory (ctlp.py:1120-1139): the stored braking trajectory
+ * starts as the accelerations that brake from the start state.  As in the reference the position handed to the range
+ * computation is not advanced along this trajectory (start_position = position[-1] is the previous step's start). */
+void smo_human_initial_braking(const SmScene* sc, const double* hkin, double* hstate, double* hbrake) {
+    const SmHuman* h = &sc->human;
+    if (!h->check_braking || !h->initial_braking_trajectory) return;
+    double q[SM_HUMAN_JOINTS], v[SM_HUMAN_JOINTS], a[SM_HUMAN_JOINTS], e[SM_HUMAN_JOINTS];
+    memcpy(q, hkin, sizeof(q)); memcpy(v, hkin + 8, sizeof(v)); memcpy(a, hkin + 16, sizeof(a));
+    int k = 0;
+    for (;;) {
+        if ((double)(k - 1) * sc->ts > h->brake_timeout || k >= SM_HBRAKE_STEPS) break;
+        if (human_braking_acceleration(sc, q, v, a, e)) break;
+        memcpy(hbrake + (size_t)k * SM_HUMAN_JOINTS, e, sizeof(e));
+        ++k;
+        for (int j = 0; j < h->n_joints; ++j) {
+            double qq, vv, aa;
+            interpolate(sc, q[j], v[j], a[j], e[j], sc->ts, &qq, &vv, &aa);
+            v[j] = vv; a[j] = e[j];
+        }
+    }
+    hstate[SM_HS_BRAKE_COUNT] = (double)k;
 }
 
 /* getContactPoints(bodyA = human, bodyB = robot) in the simulation client (ctlp.py:4888-4898): both at their

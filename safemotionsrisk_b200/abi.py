@@ -14,6 +14,15 @@ SM_KIN_STRIDE = 32
 SM_OBST_STRIDE = 16
 SM_INFO_STRIDE = 32
 SM_TP_STRIDE = 12
+SM_EP_SCALARS, SM_EP_STRIDE = 16, 64
+# per-step scalars aggregated per episode (include/smenv.h SmEpisodeScalar), with the reference's info key names
+EP_SCALARS = ["collision_rate_self", "collision_rate_static_obstacles", "collision_rate_moving_obstacles",
+              "action_punishment", "self_collision_reward", "static_obstacles_collision_reward",
+              "moving_obstacles_collision_reward", "reward", "target_point_reward", "risky_action_rate", "joint_vel_norm",
+              "joint_pos_violation", "joint_vel_violation", "joint_acc_violation", "joint_jerk_violation",
+              "observation_clipping_rate"]
+EPC = dict(balls_hit_robot=48, balls_missed=49, targets_reached=50, first_risky_step=51, length=52, ret=53, reason=54,
+           human_braked=55)
 TP_POS, TP_LAST_DIST, TP_INIT_DIST, TP_ACTIVE, TP_REACHED_N, TP_LINK_POS, TP_DRAWS, TP_REACHED = 0, 3, 4, 5, 6, 7, 10, 11
 
 SM_OBST_NONE, SM_OBST_PLANET, SM_OBST_BALL, SM_OBST_HUMAN = 0, 1, 2, 3
@@ -70,7 +79,7 @@ class SmHuman(C.Structure):
         ("start_box_min", d * 3), ("start_box_max", d * 3),
         ("kinematic_sampling_probability", d), ("stay_in_state_probability", d),
         ("min_start_static", d), ("min_start_self", d),
-        ("obs_size", i32), ("reserved", i32),
+        ("obs_size", i32), ("initial_braking_trajectory", i32),
     ]
 
 
@@ -150,6 +159,7 @@ class SmBuffers(C.Structure):
         ("actions", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p),
         ("term_reason", C.c_void_p), ("info", C.c_void_p), ("stats", C.c_void_p), ("target", C.c_void_p),
         ("hkin", C.c_void_p), ("hstate", C.c_void_p), ("hbrake", C.c_void_p), ("hobs", C.c_void_p),
+        ("epacc", C.c_void_p), ("epinfo", C.c_void_p),
         ("hactions", C.c_void_p),
     ]
 

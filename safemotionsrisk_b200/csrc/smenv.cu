@@ -4,6 +4,7 @@
 #include <cstring>
 #include <string>
 #include <algorithm>
+#include <array>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -177,6 +178,7 @@ struct SmEnv {
     double* d_hbacc = nullptr;     // [n][SM_HBRAKE_STEPS][8]
     float* d_hposes = nullptr;     // [n][SM_HBRAKE_POSES][8]
     int* d_hbinfo = nullptr;       // [n][4]
+    int* d_hunits = nullptr;       // [0] = count, [1..] = (env << 7 | pose) units of the braking-trajectory pose checks
     float* d_hscratch = nullptr;   // [n][SM_SCRATCH_FLOATS]
     float* d_hpolicy = nullptr;    // [n][16]
     double* d_hstart_pool = nullptr;   // [start_pool_n][SM_HPOOL_STRIDE]
@@ -457,6 +459,7 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     for (int i = 0; i < 9; ++i) d.target_R[i] = (float)sc->target_R[i];
     d.ball_active_xy = sc->ball_active_xy;
     d.static_cap = sc->static_cap; d.moving_query = sc->moving_query; d.collision_dist = sc->collision_dist;
+    d.self_query = std::min(sc->static_cap, std::max(sc->collision_dist, sc->w_self != 0.0 ? sc->d_self : 0.0));
     d.w_self = sc->w_self; d.w_static = sc->w_static; d.w_moving = sc->w_moving;
     d.d_self = sc->d_self; d.d_static = sc->d_static; d.d_moving = sc->d_moving;
     d.w_low_acc = sc->w_low_acc; d.thr_low_acc = sc->thr_low_acc; d.w_low_vel = sc->w_low_vel; d.thr_low_vel = sc->thr_low_vel;
@@ -490,6 +493,7 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
             if (h.joint_parent[j] != ((j & 3) == 0 ? 0 : j)) return fail(SM_ERR_SCENE, "the human is expected as two serial arms of four joints");
         env->human = true;
         u.enabled = 1; u.n_joints = h.n_joints; u.check_braking = h.check_braking; u.brake_checks = h.brake_checks;
+        u.initial_braking_trajectory = h.initial_braking_trajectory;
         u.n_brake_pairs = h.n_brake_pairs; u.shape_off = h.shape_off; u.n_arm_shapes = h.n_arm_shapes; u.n_shapes = h.n_shapes;
         for (int i = 0; i < 9; ++i) u.baseR[i] = (float)h.base_R[i];
         for (int i = 0; i < 3; ++i) u.baset[i] = (float)h.base_t[i];
@@ -530,7 +534,51 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
                 tmax = fmaxf(tmax, (float)h.contact_thresh[l][r]);
             }
         u.contact_thresh_max = tmax;
-        for (int i = 0; i < h.n_brake_pairs; ++i) { hpairs.push_back((short)h.brake_pairs[i][0]); hpairs.push_back((short)h.brake_pairs[i][1]); }
+        {   // pair list sorted by (frame of A, frame of B, A, B); link-group pairs with the bounding volumes of both sides
+            std::vector<std::array<int, 4>> ps;
+            for (int i = 0; i < h.n_brake_pairs; ++i) {
+                const int a = h.brake_pairs[i][0], b = h.brake_pairs[i][1];
+                ps.push_back({sc->shapes[a].frame, sc->shapes[b].frame, a, b});
+            }
+            std::sort(ps.begin(), ps.end());
+            auto bound = [&](const std::vector<int>& ids, float* c, float* r, float* bmin, float* bmax) {
+                float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+                float mrg = 0.f;
+                for (int id : ids) {
+                    const SmShape& sh = sc->shapes[id];
+                    mrg = fmaxf(mrg, (float)sh.margin);
+                    for (int i = sh.vert_off; i < sh.vert_off + sh.vert_cnt; ++i)
+                        for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], (float)sc->verts[3 * i + k]); hi[k] = fmaxf(hi[k], (float)sc->verts[3 * i + k]); }
+                }
+                float rad = 0.f;
+                for (int k = 0; k < 3; ++k) { c[k] = 0.5f * (lo[k] + hi[k]); bmin[k] = lo[k] - mrg - 1e-6f; bmax[k] = hi[k] + mrg + 1e-6f; }
+                for (int id : ids) {
+                    const SmShape& sh = sc->shapes[id];
+                    for (int i = sh.vert_off; i < sh.vert_off + sh.vert_cnt; ++i) {
+                        const float dx = (float)sc->verts[3 * i] - c[0], dy = (float)sc->verts[3 * i + 1] - c[1], dz = (float)sc->verts[3 * i + 2] - c[2];
+                        rad = fmaxf(rad, sqrtf(dx * dx + dy * dy + dz * dz));
+                    }
+                }
+                *r = rad * (1.0f + 1e-6f) + mrg + 1e-6f;
+            };
+            int ngp = 0;
+            for (size_t i = 0; i < ps.size();) {
+                size_t e = i;
+                while (e < ps.size() && ps[e][0] == ps[i][0] && ps[e][1] == ps[i][1]) ++e;
+                if (ngp >= 8) return fail(SM_ERR_SCENE, "the human's braking-trajectory check has more than 8 link-group pairs");
+                std::vector<int> ia, ib;
+                for (size_t q = i; q < e; ++q) { ia.push_back(ps[q][2]); ib.push_back(ps[q][3]); }
+                u.gp_fa[ngp] = ps[i][0] - 100; u.gp_fb[ngp] = ps[i][1] >= 100 ? ps[i][1] - 100 : -1;   // -1: world frame
+                u.gp_off[ngp] = (int)i; u.gp_cnt[ngp] = (int)(e - i);
+                float dmin[3], dmax[3];
+                bound(ia, u.gp_ca[ngp], &u.gp_ra[ngp], dmin, dmax);
+                bound(ib, u.gp_cb[ngp], &u.gp_rb[ngp], u.gp_bmin[ngp], u.gp_bmax[ngp]);
+                ++ngp;
+                i = e;
+            }
+            u.n_gp = ngp;
+            for (auto& q : ps) { hpairs.push_back((short)q[2]); hpairs.push_back((short)q[3]); }
+        }
         // link groups: runs of consecutive human shapes in the same frame, with a bounding sphere in frame coordinates
         int ng = 0;
         for (int s = 0; s < h.n_shapes;) {
@@ -571,7 +619,19 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
             ++ng;
             s = e;
         }
-        for (int g = ng; g < SM_HGROUPS; ++g) { u.grp_frame[g] = 0; u.grp_off[g] = 0; u.grp_cnt[g] = 0; u.grp_r[g] = -1e9f; }
+        for (int g = ng; g < SM_HGROUPS; ++g) { u.grp_frame[g] = 0; u.grp_off[g] = 0; u.grp_cnt[g] = 0; u.grp_r[g] = 0.f; }
+        for (int k = 0; k < 3; ++k) { u.trunk_wmin[k] = FLT_MAX; u.trunk_wmax[k] = -FLT_MAX; }
+        for (int s = 0; s < h.n_shapes; ++s) {
+            const SmShape& sh = sc->shapes[h.shape_off + s];
+            if (sh.frame != 100) continue;
+            for (int i = sh.vert_off; i < sh.vert_off + sh.vert_cnt; ++i)
+                for (int k = 0; k < 3; ++k) {
+                    const float w = (float)(h.base_R[3 * k] * sc->verts[3 * i] + h.base_R[3 * k + 1] * sc->verts[3 * i + 1] +
+                                            h.base_R[3 * k + 2] * sc->verts[3 * i + 2] + h.base_t[k]);
+                    u.trunk_wmin[k] = fminf(u.trunk_wmin[k], w - (float)sh.margin - 1e-5f);
+                    u.trunk_wmax[k] = fmaxf(u.trunk_wmax[k], w + (float)sh.margin + 1e-5f);
+                }
+        }
     }
 
     int rc = upload(&env->d_verts, verts);
@@ -594,6 +654,8 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
         CU(cudaMalloc((void**)&env->d_hposes, N * SM_HBRAKE_POSES * 8 * sizeof(float)));
         CU(cudaMalloc((void**)&env->d_hbinfo, N * 4 * sizeof(int)));
         CU(cudaMemset(env->d_hbinfo, 0, N * 4 * sizeof(int)));
+        CU(cudaMalloc((void**)&env->d_hunits, (N * SM_HBRAKE_POSES + 16) * sizeof(int)));
+        CU(cudaMemset(env->d_hunits, 0, (N * SM_HBRAKE_POSES + 16) * sizeof(int)));
         CU(cudaMalloc((void**)&env->d_hscratch, N * SM_SCRATCH_FLOATS * sizeof(float)));
         CU(cudaMemset(env->d_hscratch, 0, N * SM_SCRATCH_FLOATS * sizeof(float)));
         CU(cudaMalloc((void**)&env->d_hpolicy, N * 16 * sizeof(float)));
@@ -743,7 +805,7 @@ extern "C" int smenv_destroy(SmEnv* env) {
     for (void* q : env->net_allocs) cudaFree(q);
     cudaFree(env->d_risk); cudaFree(env->d_backup); cudaFree(env->d_exec); cudaFree(env->d_risky);
     cudaFree(env->d_hpairs); cudaFree(env->d_hthresh); cudaFree(env->d_hrange); cudaFree(env->d_hbacc); cudaFree(env->d_hposes);
-    cudaFree(env->d_hbinfo); cudaFree(env->d_hscratch); cudaFree(env->d_hpolicy); cudaFree(env->d_hstart_pool); cudaFree(env->d_htarget_pool);
+    cudaFree(env->d_hbinfo); cudaFree(env->d_hunits); cudaFree(env->d_hscratch); cudaFree(env->d_hpolicy); cudaFree(env->d_hstart_pool); cudaFree(env->d_htarget_pool);
     for (int i = 0; i <= SM_K_COUNT; ++i) if (env->ev[i]) cudaEventDestroy(env->ev[i]);
     for (int c = 0; c < 8; ++c) {
         if (env->chunk_streams[c]) cudaStreamDestroy(env->chunk_streams[c]);
@@ -961,7 +1023,7 @@ extern "C" int smenv_reset(SmEnv* env, const SmBuffers* buf, const uint8_t* mask
         H.buf = *buf; H.n = env->n; H.env_base = 0; H.k0 = (uint32_t)env->seed; H.k1 = (uint32_t)(env->seed >> 32);
         H.mask = mask; H.start_pool = env->d_hstart_pool; H.start_pool_n = env->start_pool_n;
         H.target_pool = env->d_htarget_pool; H.target_pool_n = env->htarget_pool_n;
-        human_reset_kernel<<<(env->n + 255) / 256, 256, 0, stream>>>(H, 0);
+        human_reset_kernel<<<(env->n * 8 + 255) / 256, 256, 0, stream>>>(H, 0);
         env->launches++;
     }
     CU(cudaGetLastError());
@@ -1022,7 +1084,7 @@ extern "C" int smenv_set_human_state(SmEnv* env, const SmBuffers* buf, const dou
     HumanArgs H;
     memset(&H, 0, sizeof(H));
     H.buf = *buf; H.n = n; H.mask = (const uint8_t*)dm;
-    human_set_state_kernel<<<(n + 255) / 256, 256, 0, stream>>>(H, (const double*)dq, (const double*)dv, (const double*)da,
+    human_set_state_kernel<<<(n * 8 + 255) / 256, 256, 0, stream>>>(H, (const double*)dq, (const double*)dv, (const double*)da,
                                                                (const double*)dt, (const int32_t*)dar);
     env->launches++;
     CU(cudaGetLastError());
@@ -1054,6 +1116,8 @@ static SmBuffers buffers_at(const SmBuffers& b, int e0, int nj, int obs_size) {
     if (b.hbrake) o.hbrake = b.hbrake + (size_t)e0 * SM_HBRAKE_STEPS * SM_HUMAN_JOINTS;
     if (b.hobs) o.hobs = b.hobs + (size_t)e0 * SM_HOBS_STRIDE;
     if (b.hactions) o.hactions = b.hactions + (size_t)e0 * SM_HUMAN_JOINTS;
+    if (b.epacc) o.epacc = b.epacc + (size_t)e0 * SM_EP_STRIDE;
+    if (b.epinfo) o.epinfo = b.epinfo + (size_t)e0 * SM_EP_STRIDE;
     return o;
 }
 
@@ -1127,6 +1191,7 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
     JA.set = 0; JA.nj = env->host_scene.n_joints; JA.defer = 0; JA.range_out = nullptr;
     JA.track_vel = env->host_scene.track_vel; JA.store_qset = env->host_scene.use_target_points;
     JA.keep_overflow = env->human ? 1 : 0;
+    JA.clear_extra = nullptr;
     const bool gate = env->gate_threshold >= 0.0f;
     if (gate) {   // actions.py:303-340: rate the proposed action, execute the backup policy's where it is risky
         if (!buf->obs) return fail(SM_ERR_ARG, "smenv_step: the risk gate needs the observation buffer");
@@ -1170,6 +1235,7 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
         HA.bacc = env->d_hbacc + (size_t)e0 * SM_HBRAKE_STEPS * 8;
         HA.poses = env->d_hposes + (size_t)e0 * SM_HBRAKE_POSES * 8;
         HA.binfo = env->d_hbinfo + (size_t)e0 * 4;
+        HA.units = env->d_hunits + (size_t)e0 * SM_HBRAKE_POSES + chunk;
         HA.hscratch = env->d_hscratch + (size_t)e0 * SM_SCRATCH_FLOATS;
         HA.scratch = scratch;
         HA.items = items; HA.item_count = worklist; HA.capacity = capacity; HA.overflow = worklist + 1;
@@ -1195,6 +1261,7 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
         JH.set = 1; JH.nj = SM_HUMAN_JOINTS; JH.defer = 1; JH.range_out = HA.range; JH.random_actions = 0; JH.exec = nullptr;
         JH.track_vel = 0.87; JH.store_qset = 1; JH.keep_overflow = 0;
         JH.scratch = HA.hscratch;
+        JH.clear_extra = HA.units;
         const int hb = std::min((m * 8 + SM_HEAVY_THREADS - 1) / SM_HEAVY_THREADS, 8 * env->sms);
         SM_MARK(SM_K_HUMAN_JOINT);
         joint_kernel<<<(m * 8 + 255) / 256, 256, 0, stream>>>(JH);
@@ -1207,8 +1274,7 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
         env->launches += 5;
         SM_MARK(SM_K_HUMAN_BRAKE_PLAN);
         if (env->host_scene.hu.check_braking) {
-            const int blocks_h = (m + SM_WARPS_PER_BLOCK - 1) / SM_WARPS_PER_BLOCK;
-            human_brake_plan_kernel<<<std::min(blocks_h, 4 * env->sms), SM_WARPS_PER_BLOCK * 32, env->smem_bytes_hplan, stream>>>(HA);
+            human_brake_plan_kernel<<<8 * env->sms, 256, sizeof(SceneSmem), stream>>>(HA);
             SM_MARK(SM_K_HUMAN_BRAKE_GJK);
             GjkArgs GB;
             GB.items = items; GB.n_items = worklist; GB.capacity = capacity; GB.res = res; GB.counters = env->d_counters;
@@ -1307,7 +1373,7 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
     if (env->count) finish_kernel<true><<<grid_f, 256, 0, stream>>>(A);
     else finish_kernel<false><<<grid_f, 256, 0, stream>>>(A);
     if (env->human && auto_reset && env->pools_filled) {   // the nested env restarts with the main env
-        human_reset_kernel<<<(m + 255) / 256, 256, 0, stream>>>(HA, 1);
+        human_reset_kernel<<<(m * 8 + 255) / 256, 256, 0, stream>>>(HA, 1);
         env->launches++;
     }
     SM_MARK(SM_K_COUNT);

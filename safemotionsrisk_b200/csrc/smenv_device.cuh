@@ -66,6 +66,7 @@ struct JointLim {
 #define SM_HGROUPS 5 /* human link groups of the coarse tests: trunk, upper arm / forearm + hand of each arm */
 struct DevHuman {
     int enabled, n_joints, check_braking, brake_checks, n_brake_pairs, shape_off, n_arm_shapes, n_shapes;
+    int initial_braking_trajectory;
     int joint_parent[SM_HUMAN_JOINTS];
     float baseR[9], baset[3];
     float jR[SM_HUMAN_JOINTS][9], jt[SM_HUMAN_JOINTS][3], jaxis[SM_HUMAN_JOINTS][3];
@@ -83,6 +84,13 @@ struct DevHuman {
     float grp_c[SM_HGROUPS][3], grp_r[SM_HGROUPS];
     float grp_rho[SM_HGROUPS][SM_HUMAN_JOINTS];   // bound on |d group centre / d q_j|
     float contact_thresh_max;
+    float trunk_wmin[3], trunk_wmax[3];   // world box of the shapes in the base frame (the trunk does not move), margins included
+    // braking-trajectory check: the pair list is sorted by (frame of A, frame of B); one entry per such link-group pair
+    // with the bounding spheres of its two sides (frame coordinates; B in the world frame 0 is the table: its box is used)
+    int n_gp;
+    int gp_fa[8], gp_fb[8], gp_off[8], gp_cnt[8];
+    float gp_ca[8][3], gp_ra[8], gp_cb[8][3], gp_rb[8];
+    float gp_bmin[8][3], gp_bmax[8][3];   // B in frame 0: axis-aligned box of its core vertices (+ margin)
     double start_box_min[3], start_box_max[3], kinematic_sampling_probability, stay_in_state_probability,
         min_start_static, min_start_self, tp_min_static, tp_min_self;
 };
@@ -123,6 +131,8 @@ struct DevScene {
     double ball_obs_pos_min[3], ball_obs_pos_max[3], ball_obs_vel_min[3], ball_obs_vel_max[3];
     double ball_active_xy;
     double static_cap, moving_query, collision_dist;
+    double self_query;   // self-collision distances above it cannot change reward or termination: such pairs are pruned and
+                         // the class reports the cap (min(static_cap, reward distance of the self-collision term))
     double w_self, w_static, w_moving, d_self, d_static, d_moving, w_low_acc, thr_low_acc, w_low_vel, thr_low_vel;
     int punish_action, terminate_self, terminate_static, terminate_moving;
     double action_thresh, action_max_punishment, termination_bonus, early_termination_punishment, reward_scale;

@@ -30,6 +30,7 @@ struct HumanArgs {
     double* bacc;              // [n][SM_HBRAKE_STEPS][8] braking accelerations of the trajectory under check
     float* poses;              // [n][SM_HBRAKE_POSES][8] poses the check visits
     int* binfo;                // [n][4] braking steps k, poses, timeout, reserved
+    int* units;                // [0] = count, [1..] = env << 7 | pose: the poses the braking-trajectory check has to test
     float* hscratch;           // [n][SM_SCRATCH_FLOATS] sub-step poses of the human (tracked, setpoints)
     const float* scratch;      // [n][SM_SCRATCH_FLOATS] sub-step poses of the robot
     GjkItem* items;
@@ -89,6 +90,35 @@ __device__ __forceinline__ double brake_target(double v, double a, double J, dou
     return a1;
 }
 
+// _compute_braking_acceleration for one joint (ctlp.py:3495-3507): brake_target clipped to the full safe range, which is
+// evaluated lazily like the oracle's human_braking_acceleration (the iterative position bounds only if the braking profile
+// that follows the clipped value would leave a position limit)
+__device__ __forceinline__ double human_braking_acceleration(const JointLim& L, int j, double p, double v, double a, bool small_j) {
+    const double ts = c_sc.ts, J = L.jerk_max[j], Am = L.acc_max[j];
+    double lo, hi;
+    int code;
+    bool need_pos;
+    safe_range_light(L, j, p, v, a, lo, hi, code, need_pos);
+    const double e0 = small_j ? 0.0 : brake_target(v, a, J, Am, ts);
+    double e = e0;
+    if (e < lo) e = lo;
+    if (e > hi) e = hi;
+    if (need_pos) {
+        const double V = L.vel_max[j];
+        const bool ok_hi = pos_bound_inactive(p, v, a, e, L.pos_hi[j], J, Am, V, ts, false) ||
+                           xsub(pos_peak(p, v, a, e, J, Am, ts), L.pos_hi[j]) <= 0.0;
+        const bool ok_lo = pos_bound_inactive(-p, -v, -a, -e, -L.pos_lo[j], J, Am, V, ts, false) ||
+                           xsub(pos_peak(-p, -v, -a, -e, J, Am, ts), -L.pos_lo[j]) <= 0.0;
+        if (!(ok_hi && ok_lo)) {
+            safe_range_joint(L, j, p, v, a, lo, hi, code);
+            e = e0;
+            if (e < lo) e = lo;
+            if (e > hi) e = hi;
+        }
+    }
+    return e;
+}
+
 __global__ void __launch_bounds__(128) human_brake_traj_kernel(HumanArgs A) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -131,13 +161,7 @@ __global__ void __launch_bounds__(128) human_brake_traj_kernel(HumanArgs A) {
         if (!done) {
             if (stopped) done = true;
             else {
-                double lo, hi;
-                int code;
-                safe_range_joint(L, j, pend, vend, ae, lo, hi, code);   // _acc_range_function (ctlp.py:3496-3499)
-                double e = brake_target(vend, ae, J, Am, ts);
-                if (small_j) e = 0.0;
-                if (e < lo) e = lo;                                      // np.clip(end_acceleration, next_acc_min, next_acc_max)
-                if (e > hi) e = hi;
+                const double e = human_braking_acceleration(L, j, pend, vend, ae, small_j);
                 if (k < SM_HBRAKE_STEPS) bacc[k * 8 + j] = e;
                 ++k;
                 q = pend; v = vend; as = ae; ae = e;
@@ -147,95 +171,100 @@ __global__ void __launch_bounds__(128) human_brake_traj_kernel(HumanArgs A) {
     }
     if (valid && j == 0) {
         int* bi = A.binfo + env * 4;
-        bi[0] = k; bi[1] = np < SM_HBRAKE_POSES ? np : SM_HBRAKE_POSES; bi[2] = timeout; bi[3] = 0;
+        const int npc = np < SM_HBRAKE_POSES ? np : SM_HBRAKE_POSES;
+        bi[0] = k; bi[1] = npc; bi[2] = timeout; bi[3] = 0;
         A.res[env * SM_RES_STRIDE + GJK_BRAKE] = SM_RES_NO_CONTACT;
+        if (npc > 0) {   // one unit per pose for the geometry pass
+            const int base = atomicAdd(A.units, npc);
+            for (int p = 0; p < npc; ++p) A.units[1 + base + p] = ((int)env << 7) | p;
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// geometry of the braking-trajectory check: one warp per env, poses one after the other; per pose the frames (warp scan),
-// the world centres of the shapes, then lanes = the pairs of get_minimum_distance (ctlp.py:3282-3374) with the sphere and
-// separating-axis bounds of the distance planning.  A pair that may be closer than the safety distance becomes a
-// GJK_BRAKE item carrying the pose number.
+// geometry of the braking-trajectory check: ONE THREAD PER POSE (the joint-space kernel lists them).  Serial forward
+// kinematics of the two arms, then the link-group pairs of get_minimum_distance (ctlp.py:3282-3374: table x forearm /
+// hand, forearm / hand x other arm, forearm / hand x body / head) with bounding spheres; inside a surviving group pair
+// every convex pair goes through the sphere and separating-axis bounds of the distance planning.  A pair that may be
+// closer than the safety distance becomes a GJK_BRAKE item carrying the pose number.
 // ------------------------------------------------------------------------------------------------------------------
-struct HumanWarpScratch {
-    Xf fr[SM_MAX_OBST_FRAMES];
-    float pc[64 + 4][3];   // world centres of the human shapes, then of the static shape(s) of the pair list
-};
-struct HumanBlockShared {
+struct HumanBlockShared {   // kept for the size bookkeeping of smenv_create
     SceneSmem scene;
-    short pairs[SM_MAX_HPAIRS][2];
-    HumanWarpScratch w[SM_WARPS_PER_BLOCK];
 };
 
-__global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) human_brake_plan_kernel(HumanArgs A) {
+__global__ void __launch_bounds__(256) human_brake_plan_kernel(HumanArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    HumanBlockShared* bs = reinterpret_cast<HumanBlockShared*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < (int)(sizeof(SceneSmem) / 16); i += blockDim.x)
-        reinterpret_cast<uint4*>(&bs->scene)[i] = __ldg(c_sc.scene_img + i);
-    const int npairs = c_sc.hu.n_brake_pairs;
-    for (int i = tid; i < npairs * 2; i += blockDim.x) (&bs->pairs[0][0])[i] = c_sc.hu.brake_pairs[i];
+    const int n_units = A.units[0];
+    if (blockIdx.x * blockDim.x >= n_units) return;
+    SceneSmem* smp = reinterpret_cast<SceneSmem*>(smem_raw);
+    for (int i = threadIdx.x; i < (int)(sizeof(SceneSmem) / 16); i += blockDim.x)
+        reinterpret_cast<uint4*>(smp)[i] = __ldg(c_sc.scene_img + i);
     __syncthreads();
-    const SceneSmem& sm = bs->scene;
-    HumanWarpScratch& W = bs->w[warp];
-    const int hoff = c_sc.hu.shape_off, hn = c_sc.hu.n_shapes;
+    const SceneSmem& sm = *smp;
     const float safety = (float)c_sc.hu.brake_safety;
-    Xf world;
+    Xf world, B;
     xf_identity(world);
+    human_base(B);
 #pragma unroll 1
-    for (int env = blockIdx.x * SM_WARPS_PER_BLOCK + warp; env < A.n; env += gridDim.x * SM_WARPS_PER_BLOCK) {
-        const int np = A.binfo[(size_t)env * 4 + 1];
-        const float* poses = A.poses + (size_t)env * SM_HBRAKE_POSES * 8;
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += gridDim.x * blockDim.x) {
+        const int unit = A.units[1 + u];
+        const int env = unit >> 7, p = unit & 127;
+        const float4* row = reinterpret_cast<const float4*>(A.poses + ((size_t)env * SM_HBRAKE_POSES + p) * 8);
+        const float4 r0 = row[0], r1 = row[1];
+        // frames that carry shapes of the check: upper arm (3 / 7) and forearm + hand (4 / 8) of both arms
+        Xf F3, F4, F7, F8;
+        {
+            Xf F = B;
+            human_chain_step(F, 0, r0.x); human_chain_step(F, 1, r0.y); human_chain_step(F, 2, r0.z);
+            F3 = F;
+            human_chain_step(F, 3, r0.w);
+            F4 = F;
+            F = B;
+            human_chain_step(F, 4, r1.x); human_chain_step(F, 5, r1.y); human_chain_step(F, 6, r1.z);
+            F7 = F;
+            human_chain_step(F, 7, r1.w);
+            F8 = F;
+        }
 #pragma unroll 1
-        for (int p = 0; p < np; ++p) {
-            human_fk_scan(poses[p * 8 + (lane & 7)], W.fr, lane);
-#pragma unroll 1
-            for (int s = lane; s < hn; s += 32) {
-                const DevShape& sh = sm.shapes[hoff + s];
-                const V3 c = xf_apply(W.fr[sh.frame - 100], sh.cx, sh.cy, sh.cz);
-                W.pc[s][0] = c.x; W.pc[s][1] = c.y; W.pc[s][2] = c.z;
+        for (int g = 0; g < c_sc.hu.n_gp; ++g) {
+            const int fa = c_sc.hu.gp_fa[g], fb = c_sc.hu.gp_fb[g];
+            const Xf& TA = fa == 3 ? F3 : fa == 4 ? F4 : fa == 7 ? F7 : F8;
+            const Xf& TB = fb < 0 ? world : fb == 0 ? B : fb == 3 ? F3 : fb == 4 ? F4 : fb == 7 ? F7 : F8;
+            const V3 ga = xf_apply(TA, c_sc.hu.gp_ca[g][0], c_sc.hu.gp_ca[g][1], c_sc.hu.gp_ca[g][2]);
+            bool near_g;
+            if (fb < 0) {
+                const float l = c_sc.hu.gp_ra[g] + safety;
+                near_g = box_dist2(ga, c_sc.hu.gp_bmin[g], c_sc.hu.gp_bmax[g]) <= l * l;
+            } else {
+                const V3 d = xf_apply(TB, c_sc.hu.gp_cb[g][0], c_sc.hu.gp_cb[g][1], c_sc.hu.gp_cb[g][2]) - ga;
+                const float l = c_sc.hu.gp_ra[g] + c_sc.hu.gp_rb[g] + safety;
+                near_g = dot(d, d) <= l * l;
             }
-            __syncwarp();
+            if (!near_g) continue;
+            int last_a = -1;
+            V3 ca = mk(0.f, 0.f, 0.f);
 #pragma unroll 1
-            for (int base = 0; base < npairs; base += 32) {
-                const int i = base + lane;
-                bool emit = false;
-                int ia = 0, ib = 0;
-                if (i < npairs) {
-                    ia = bs->pairs[i][0]; ib = bs->pairs[i][1];
-                    const DevShape& SA = sm.shapes[ia];
-                    const DevShape& SB = sm.shapes[ib];
-                    const V3 ca = mk(W.pc[ia - hoff][0], W.pc[ia - hoff][1], W.pc[ia - hoff][2]);
-                    if (SB.frame == 0) {   // the table: sphere against its axis-aligned box
-                        emit = sqrtf(box_dist2(ca, SB.bmin, SB.bmax)) - SA.radius - SA.margin - SB.margin <= safety;
-                        if (emit)
-                            emit = axis_lower_bound_d(SA, SB, W.fr[SA.frame - 100], world,
-                                                      mk(SB.cx - ca.x, SB.cy - ca.y, SB.cz - ca.z)) <= safety;
-                    } else {
-                        const V3 d = mk(W.pc[ib - hoff][0] - ca.x, W.pc[ib - hoff][1] - ca.y, W.pc[ib - hoff][2] - ca.z);
-                        emit = sqrtf(dot(d, d)) - SA.radius - SB.radius - SA.margin - SB.margin <= safety;
-                        if (emit) emit = axis_lower_bound_d(SA, SB, W.fr[SA.frame - 100], W.fr[SB.frame - 100], d) <= safety;
-                    }
+            for (int i = c_sc.hu.gp_off[g]; i < c_sc.hu.gp_off[g] + c_sc.hu.gp_cnt[g]; ++i) {
+                const int ia = __ldg(c_sc.hu.brake_pairs + 2 * i), ib = __ldg(c_sc.hu.brake_pairs + 2 * i + 1);
+                const DevShape& SA = sm.shapes[ia];
+                const DevShape& SB = sm.shapes[ib];
+                if (ia != last_a) { ca = xf_apply(TA, SA.cx, SA.cy, SA.cz); last_a = ia; }
+                bool emit;
+                V3 d;
+                if (fb < 0) {   // the table: sphere against its axis-aligned box
+                    d = mk(SB.cx - ca.x, SB.cy - ca.y, SB.cz - ca.z);
+                    emit = sqrtf(box_dist2(ca, SB.bmin, SB.bmax)) - SA.radius - SA.margin - SB.margin <= safety;
+                } else {
+                    d = xf_apply(TB, SB.cx, SB.cy, SB.cz) - ca;
+                    emit = sqrtf(dot(d, d)) - SA.radius - SB.radius - SA.margin - SB.margin <= safety;
                 }
-                const unsigned em = __ballot_sync(FULL, emit);
-                if (em) {
-                    const int total = __popc(em);
-                    int b0 = 0;
-                    if (lane == 0) b0 = atomicAdd(A.item_count, total);
-                    b0 = __shfl_sync(FULL, b0, 0);
-                    if (b0 + total <= A.capacity) {
-                        if (emit) {
-                            const DevShape& SB = sm.shapes[ib];
-                            write_item(A.items + b0 + __popc(em & ((1u << lane) - 1u)), env, ia, ib, GJK_BRAKE, p + 1, safety,
-                                       W.fr[sm.shapes[ia].frame - 100], SB.frame == 0 ? world : W.fr[SB.frame - 100]);
-                        }
-                    } else if (lane == 0) {
-                        atomicAdd(A.overflow, total);
-                    }
+                if (emit) emit = axis_lower_bound_d(SA, SB, TA, TB, d) <= safety;
+                if (emit) {
+                    const int idx = atomicAdd(A.item_count, 1);
+                    if (idx < A.capacity) write_item(A.items + idx, env, ia, ib, GJK_BRAKE, p + 1, safety, TA, TB);
+                    else atomicAdd(A.overflow, 1);
                 }
             }
-            __syncwarp();
         }
     }
 }
@@ -461,6 +490,12 @@ __global__ void __launch_bounds__(256) hcontact_coarse_kernel(HumanArgs A) {
                 const float rr = sh.radius + sh.margin + infl;
 #pragma unroll
                 for (int g = 0; g < SM_HGROUPS; ++g) {
+                    if (c_sc.hu.grp_cnt[g] == 0) continue;
+                    if (c_sc.hu.grp_frame[g] == 0) {   // the trunk stands still: its world box instead of a sphere
+                        const float lim = rr + c_sc.hu.contact_thresh_max;
+                        if (box_dist2(ctr, c_sc.hu.trunk_wmin, c_sc.hu.trunk_wmax) <= lim * lim) flag = true;
+                        continue;
+                    }
                     const V3 e = ctr - gc[g];
                     const float lim = rr + gr[g];
                     if (dot(e, e) <= lim * lim) flag = true;
@@ -528,7 +563,11 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) hcontact_plan_kernel(
                     const V3 gcw = xf_apply(TB, c_sc.hu.grp_c[g][0], c_sc.hu.grp_c[g][1], c_sc.hu.grp_c[g][2]);
                     const V3 dd = cw - gcw;
                     const float lim = rr + c_sc.hu.grp_r[g] + c_sc.hu.contact_thresh_max;
-                    if (dot(dd, dd) > lim * lim) continue;
+                    if (c_sc.hu.grp_cnt[g] == 0) continue;
+                    if (c_sc.hu.grp_frame[g] == 0) {
+                        const float lb = rr + c_sc.hu.contact_thresh_max;
+                        if (box_dist2(cw, c_sc.hu.trunk_wmin, c_sc.hu.trunk_wmax) > lb * lb) continue;
+                    } else if (dot(dd, dd) > lim * lim) continue;
                     const V3 cl = xf_rot_t(TB, mk(cw.x - TB.t[0], cw.y - TB.t[1], cw.z - TB.t[2]));   // in the group's frame
 #pragma unroll 1
                     for (int s = c_sc.hu.grp_off[g]; s < c_sc.hu.grp_off[g] + c_sc.hu.grp_cnt[g]; ++s) {
@@ -590,39 +629,84 @@ __device__ __forceinline__ void copy_human_kinematic_obs(float* obs, const float
     for (int i = 0; i < 3 * SM_HUMAN_JOINTS; ++i) obs[off + i] = hobs[i];
 }
 
-__global__ void human_set_state_kernel(HumanArgs A, const double* hq, const double* hv, const double* ha,
-                                       const double* first_target, const int32_t* active_arm) {
-    const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env >= A.n || (A.mask && !A.mask[env])) return;
-    human_episode_start(A.buf.hkin + (size_t)env * SM_KIN_STRIDE, A.buf.hstate + (size_t)env * SM_HSTATE_STRIDE,
-                        A.buf.hbrake + (size_t)env * SM_HBRAKE_STEPS * 8, A.buf.hobs + (size_t)env * SM_HOBS_STRIDE,
-                        hq + (size_t)env * 8, hv + (size_t)env * 8, ha + (size_t)env * 8, first_target + (size_t)env * 3,
-                        active_arm ? active_arm[env] : 0, 1.0);
-    if (A.buf.obs) copy_human_kinematic_obs(A.buf.obs + (size_t)env * c_sc.obs_size, A.buf.hobs + (size_t)env * SM_HOBS_STRIDE);
+// ObstacleWrapperBase.reset with compute_initial_braking_trajectory (ctlp.py:1120-1139): the stored braking trajectory
+// starts as the accelerations that brake from the start state; the position handed to the range computation is not
+// advanced along it (as in the reference).  The eight lanes of an env, lane j = joint j, all lanes of the warp call.
+__device__ __forceinline__ void human_initial_braking(double* hs, double* hb, double q, double v, double a, bool active,
+                                                      int lane) {
+    const JointLim& L = c_sc.hu.lim;
+    const int j = lane & 7, gsh = lane & 24;
+    const double ts = c_sc.ts;
+    int k = 0;
+    bool done = !active || !c_sc.hu.check_braking || !c_sc.hu.initial_braking_trajectory;
+#pragma unroll 1
+    while (true) {
+        if (!done && ((double)(k - 1) * ts > c_sc.hu.brake_timeout || k >= SM_HBRAKE_STEPS)) done = true;
+        const bool small_j = fabs(v) < 0.01 && fabs(a) < 0.01;
+        const unsigned sm_all = __ballot_sync(FULL, done || small_j);
+        if (!done && ((sm_all >> gsh) & 0xffu) == 0xffu) done = true;
+        if (!done) {
+            const double e = human_braking_acceleration(L, j, q, v, a, small_j);
+            hb[k * 8 + j] = e;
+            ++k;
+            double qq, vv, aa;
+            interpolate(q, v, a, e, ts, qq, vv, aa);
+            v = vv; a = e;
+        }
+        if (__all_sync(FULL, done)) break;
+    }
+    if (active && j == 0) hs[SM_HS_BRAKE_COUNT] = (double)k;
+}
+
+__global__ void __launch_bounds__(256) human_set_state_kernel(HumanArgs A, const double* hq, const double* hv,
+                                                              const double* ha, const double* first_target,
+                                                              const int32_t* active_arm) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, j = t & 7;
+    const int env_raw = t >> 3;
+    const bool active = env_raw < A.n && !(A.mask && !A.mask[env_raw]);
+    const size_t env = env_raw < A.n ? (size_t)env_raw : (size_t)(A.n - 1);
+    if (active && j == 0) {
+        human_episode_start(A.buf.hkin + env * SM_KIN_STRIDE, A.buf.hstate + env * SM_HSTATE_STRIDE,
+                            A.buf.hbrake + env * SM_HBRAKE_STEPS * 8, A.buf.hobs + env * SM_HOBS_STRIDE, hq + env * 8,
+                            hv + env * 8, ha + env * 8, first_target + env * 3, active_arm ? active_arm[env] : 0, 1.0);
+        if (A.buf.obs) copy_human_kinematic_obs(A.buf.obs + env * c_sc.obs_size, A.buf.hobs + env * SM_HOBS_STRIDE);
+    }
+    __syncwarp();
+    human_initial_braking(A.buf.hstate + env * SM_HSTATE_STRIDE, A.buf.hbrake + env * SM_HBRAKE_STEPS * 8, hq[env * 8 + j],
+                          hv[env * 8 + j], ha[env * 8 + j], active, lane);
 }
 
 // reset of the nested env from the pools.  by_done != 0: the envs whose `done` flag the finish kernel just set (auto
 // reset; the robot's record was re-initialised there with pool entry `reset_count - 1`, the human takes the same entry:
 // the robot's start pose was sampled clear of that human pose); else the masked envs (smenv_reset, after reset_kernel).
-__global__ void human_reset_kernel(HumanArgs A, int by_done) {
-    const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env >= A.n) return;
-    if (by_done ? !A.buf.done[env] : (A.mask && !A.mask[env])) return;
-    if (A.start_pool_n <= 0) return;
-    const int4 ep = *reinterpret_cast<const int4*>(A.buf.episode + 4 * (size_t)env);
+// Eight lanes per env.
+__global__ void __launch_bounds__(256) human_reset_kernel(HumanArgs A, int by_done) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, j = t & 7;
+    const int env_raw = t >> 3;
+    bool active = env_raw < A.n && A.start_pool_n > 0;
+    const size_t env = env_raw < A.n ? (size_t)env_raw : (size_t)(A.n - 1);
+    if (active) active = by_done ? A.buf.done[env] != 0 : !(A.mask && !A.mask[env]);
+    const int4 ep = *reinterpret_cast<const int4*>(A.buf.episode + 4 * env);
     const uint4 r = philox((uint32_t)(env + A.env_base), (uint32_t)(ep.y - 1), 0x5E7u, 1u, A.k0, A.k1);   // the robot's draw
-    const double* e = A.start_pool + (size_t)(r.x % (uint32_t)A.start_pool_n) * SM_HPOOL_STRIDE;
-    const uint4 r2 = philox((uint32_t)(env + A.env_base), (uint32_t)(ep.y - 1), 0x5E8u, 4u, A.k0, A.k1);
-    const int arm = (int)(r2.x & 1u);                          // np.random.randint(0, num_robots) (ctlp.py:1037-1038)
-    double ft[3] = {0.3, 0.0, 0.4};
-    if (A.target_pool_n > 0) {
-        const double* tp = A.target_pool + ((size_t)arm * A.target_pool_n + (r2.y % (uint32_t)A.target_pool_n)) * 4;
-        ft[0] = tp[0]; ft[1] = tp[1]; ft[2] = tp[2];
+    const double* e = A.start_pool + (size_t)(r.x % (uint32_t)(A.start_pool_n > 0 ? A.start_pool_n : 1)) * SM_HPOOL_STRIDE;
+    if (active && j == 0) {
+        const uint4 r2 = philox((uint32_t)(env + A.env_base), (uint32_t)(ep.y - 1), 0x5E8u, 4u, A.k0, A.k1);
+        const int arm = (int)(r2.x & 1u);                          // np.random.randint(0, num_robots) (ctlp.py:1037-1038)
+        double ft[3] = {0.3, 0.0, 0.4};
+        if (A.target_pool_n > 0) {
+            const double* tp = A.target_pool + ((size_t)arm * A.target_pool_n + (r2.y % (uint32_t)A.target_pool_n)) * 4;
+            ft[0] = tp[0]; ft[1] = tp[1]; ft[2] = tp[2];
+        }
+        human_episode_start(A.buf.hkin + env * SM_KIN_STRIDE, A.buf.hstate + env * SM_HSTATE_STRIDE,
+                            A.buf.hbrake + env * SM_HBRAKE_STEPS * 8, A.buf.hobs + env * SM_HOBS_STRIDE, e, e + 8, e + 16, ft,
+                            arm, 1.0);
+        if (A.buf.obs) copy_human_kinematic_obs(A.buf.obs + env * c_sc.obs_size, A.buf.hobs + env * SM_HOBS_STRIDE);
     }
-    human_episode_start(A.buf.hkin + (size_t)env * SM_KIN_STRIDE, A.buf.hstate + (size_t)env * SM_HSTATE_STRIDE,
-                        A.buf.hbrake + (size_t)env * SM_HBRAKE_STEPS * 8, A.buf.hobs + (size_t)env * SM_HOBS_STRIDE, e, e + 8,
-                        e + 16, ft, arm, 1.0);
-    if (A.buf.obs) copy_human_kinematic_obs(A.buf.obs + (size_t)env * c_sc.obs_size, A.buf.hobs + (size_t)env * SM_HOBS_STRIDE);
+    __syncwarp();
+    human_initial_braking(A.buf.hstate + env * SM_HSTATE_STRIDE, A.buf.hbrake + env * SM_HBRAKE_STEPS * 8,
+                          active ? e[j] : 0.0, active ? e[8 + j] : 0.0, active ? e[16 + j] : 0.0, active, lane);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -670,6 +754,55 @@ __device__ __noinline__ bool human_pose_is_free(const float4* verts, const Scene
         }
     }
     return true;
+}
+
+// check_braking_trajectory_method for a candidate start state (ctlp.py:1527-1544): brake from (q, v, a) and check every
+// visited pose; lanes 0..7 hold the joints.  true = the braking trajectory is free of collisions and ends at rest.
+__device__ __noinline__ bool human_start_state_can_brake(double q, double v, double a, const float4* verts,
+                                                         const SceneSmem& sm, WarpScratch& W, int lane) {
+    const JointLim& L = c_sc.hu.lim;
+    const int j = lane & 7;
+    const bool jl = lane < SM_HUMAN_JOINTS;
+    const double ts = c_sc.ts, J = L.jerk_max[j], Am = L.acc_max[j];
+    const float safety = (float)c_sc.hu.brake_safety;
+    double as = a, ae = a;
+    {   // _compute_braking_acceleration at the start state
+        const bool small0 = fabs(v) < 0.01 && fabs(a) < 0.01;
+        if (__all_sync(FULL, !jl || small0)) return true;
+        double lo = 0.0, hi = 0.0;
+        int code = 0;
+        if (jl) safe_range_joint(L, j, q, v, a, lo, hi, code);
+        double e = brake_target(v, a, J, Am, ts);
+        if (small0) e = 0.0;
+        ae = fmin(fmax(e, lo), hi);
+    }
+#pragma unroll 1
+    for (int k = 0; k < 24; ++k) {
+        double pend = q;
+#pragma unroll 1
+        for (int m = 1; m <= c_sc.hu.brake_checks; ++m) {
+            double pm, vv, aa;
+            interpolate(q, v, as, ae, c_sc.hu.brake_t[m], pm, vv, aa);
+            human_fk_scan((float)pm, W.obx, lane);
+            const bool free_pose = human_pose_is_free(verts, sm, W, safety, safety, -1, lane);
+            __syncwarp();
+            if (!free_pose) return false;
+            pend = pm;
+        }
+        if ((double)k * ts > c_sc.hu.brake_timeout) return false;
+        double qq, vend, aa;
+        interpolate(q, v, as, ae, ts, qq, vend, aa);
+        const bool small_j = fabs(vend) < 0.01 && fabs(ae) < 0.01;
+        if (__all_sync(FULL, !jl || small_j)) return true;
+        double lo = 0.0, hi = 0.0;
+        int code = 0;
+        if (jl) safe_range_joint(L, j, pend, vend, ae, lo, hi, code);
+        double e = brake_target(vend, ae, J, Am, ts);
+        if (small_j) e = 0.0;
+        e = fmin(fmax(e, lo), hi);
+        q = pend; v = vend; as = ae; ae = e;
+    }
+    return false;
 }
 
 struct HumanPoolArgs {
@@ -765,10 +898,13 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) fill_human_pool_kerne
                         }
                     }
                 }
-                if (__all_sync(FULL, !jl || found)) break;
+                if (!__all_sync(FULL, !jl || found)) continue;
+                // the state must be able to brake without a collision (ctlp.py:1527-1544)
+                if (!c_sc.hu.check_braking || human_start_state_can_brake(q, v, a, verts, sm, W, lane)) break;
                 continue;
             }
-            // random walk from rest with random actions (ctlp.py:1558-1654), without the geometric checks
+            // random walk from rest with random actions (ctlp.py:1558-1654); the braking-trajectory method is applied to
+            // the state the walk ends in instead of to every step
 #pragma unroll 1
             for (int step = 0; step < 64; ++step) {
                 if (rng.uniform() < c_sc.hu.stay_in_state_probability) break;
@@ -783,7 +919,7 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) fill_human_pool_kerne
                     q = qe; v = ve; a = a1;
                 }
             }
-            break;
+            if (!c_sc.hu.check_braking || human_start_state_can_brake(q, v, a, verts, sm, W, lane)) break;
         }
         if (jl) {
             double* o = A.start_pool + (size_t)e * SM_HPOOL_STRIDE;

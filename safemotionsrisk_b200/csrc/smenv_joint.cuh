@@ -44,6 +44,7 @@ struct JointArgs {
     double* range_out;  // [n][8][4]
     double track_vel;   // 0.87 with use_controller_target_velocities, else 0 (robot_scene_base.py:792-805)
     int store_qset;     // also store the setpoint pose of every sub-step (target points)
+    int* clear_extra;   // a further list counter cleared by joint_kernel (human: the pose units of the braking check)
     int keep_overflow;  // do not clear the overflow count of the item list (the human's braking-trajectory items came first)
     const float* exec;  // [n][n_joints] actions to execute when the risk gate is on (the backup policy's where the
                         // proposed action was rated risky), else NULL: buf.actions are executed.  The action punishment
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(256) joint_kernel(JointArgs A) {
     if (t == 0 && A.worklist) { A.worklist[0] = 0; if (!A.keep_overflow) A.worklist[1] = 0; }
     if (t == 0 && A.cwork) A.cwork[0] = 0;
     if (t == 0 && A.tasks) A.tasks[0] = 0;
+    if (t == 0 && A.clear_extra) A.clear_extra[0] = 0;
 }
 
 // Second pass over the deferred (env, joint) instances, as three small kernels so that each runs with densely

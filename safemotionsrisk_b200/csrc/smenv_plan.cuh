@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) distance_plan_kernel(
         __syncwarp();
         // ---------------- pass 1 (lanes = pairs): the best upper bound of each class (distance of the hull centroids)
         const int np = moving ? n_pairs : n_fixed;
-        float ub_s = cap, ub_e = cap, ub_m = query;
+        float ub_s = cap, ub_e = (float)c_sc.self_query, ub_m = query;
         unsigned best_m = 0xffffffffu;  // the lane's moving pair with the smallest centroid distance
 #pragma unroll 1
         for (int p = lane; p < np; p += 32) {

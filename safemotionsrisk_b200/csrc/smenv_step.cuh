@@ -213,6 +213,78 @@ __global__ void __launch_bounds__(256) finish_kernel(StepArgs A) {
             }
             if (valid) A.buf.info[(size_t)env * SM_INFO_STRIDE + slot] = val;
         }
+        // ---------------- per-episode aggregation of the step info (train.py:59-117: average / max / min over the episode)
+        if (A.buf.epacc) {
+            // kinematic part of the observation before clipping (observations.py:365-413)
+            float prel = 0.f, vrel = 0.f, arel = 0.f;
+            if (sl < nj) {
+                prel = (float)normalize_mm(kin[sl], c_sc.pos_lo[sl], c_sc.pos_hi[sl]);
+                vrel = (float)(kin[8 + sl] / c_sc.vel_max[sl]);
+                arel = (float)(kin[16 + sl] / c_sc.acc_max[sl]);
+            }
+            float vn2 = vrel * vrel;
+            float pm = fabsf(prel), vm = fabsf(vrel), am = fabsf(arel);
+#pragma unroll
+            for (int m = 1; m < 8; m <<= 1) {
+                vn2 += __shfl_xor_sync(FULL, vn2, m);
+                pm = fmaxf(pm, __shfl_xor_sync(FULL, pm, m));
+                vm = fmaxf(vm, __shfl_xor_sync(FULL, vm, m));
+                am = fmaxf(am, __shfl_xor_sync(FULL, am, m));
+            }
+            float* acc = A.buf.epacc + (size_t)env * SM_EP_STRIDE;
+            const bool first_step = ep_len == 1;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = sl + 8 * h;
+                float x = 0.f;
+                switch (k) {
+                    case SM_EP_COLL_SELF: x = (float)c_self; break;
+                    case SM_EP_COLL_STATIC: x = (float)c_static; break;
+                    case SM_EP_COLL_MOVING: x = (float)c_moving; break;
+                    case SM_EP_ACTION_PUNISH: x = c_sc.punish_action || !tp ? (float)action_punishment : 0.f; break;
+                    case SM_EP_R_SELF: x = (float)r_self; break;
+                    case SM_EP_R_STATIC: x = (float)r_static; break;
+                    case SM_EP_R_MOVING: x = (float)r_moving; break;
+                    case SM_EP_REWARD: x = (float)reward; break;
+                    case SM_EP_TP_REWARD: x = (float)tp_reward; break;
+                    case SM_EP_RISKY_ACTION: x = (float)risky_now; break;
+                    case SM_EP_JOINT_VEL_NORM: x = sqrtf(vn2); break;
+                    case SM_EP_POS_VIOLATION: x = pm > 1.001f ? 1.f : 0.f; break;
+                    case SM_EP_VEL_VIOLATION: x = vm > 1.001f ? 1.f : 0.f; break;
+                    case SM_EP_ACC_VIOLATION: x = am > 1.001f ? 1.f : 0.f; break;
+                    case SM_EP_JERK_VIOLATION: x = jerk_rel > 1.002f ? 1.f : 0.f; break;
+                    case SM_EP_OBS_CLIPPING: x = (pm > 1.f || vm > 1.f || am > 1.f) ? 1.f : 0.f; break;
+                    default: break;
+                }
+                float s0 = first_step ? 0.f : acc[k], mx = first_step ? -FLT_MAX : acc[16 + k], mn = first_step ? FLT_MAX : acc[32 + k];
+                s0 += x; mx = fmaxf(mx, x); mn = fminf(mn, x);
+                float* dst = (done && valid) ? A.buf.epinfo + (size_t)env * SM_EP_STRIDE : acc;
+                if (valid) { dst[k] = s0; dst[16 + k] = mx; dst[32 + k] = mn; }
+            }
+            // episode counters: one lane each
+            if (valid && sl < 8) {
+                const int slot = 48 + sl;
+                float cprev = first_step ? 0.f : acc[slot], cnew = cprev;
+                switch (slot) {
+                    case SM_EPC_BALLS_HIT_ROBOT: cnew = cprev + ((kind == SM_OBST_BALL && kc > 0) ? 1.f : 0.f); break;
+                    case SM_EPC_BALLS_MISSED:
+                        cnew = cprev + ((kind == SM_OBST_BALL && kc == 0 && ob[SM_OB_BALL_ACTIVE] == 0.0 && ball_active == 0.0 &&
+                                         A.buf.obst[(size_t)env * SM_OBST_STRIDE + SM_OB_BALL_ACTIVE] != 0.0) ? 1.f : 0.f);
+                        break;
+                    case SM_EPC_TARGETS_REACHED: cnew = cprev + (tp_reached ? 1.f : 0.f); break;
+                    case SM_EPC_FIRST_RISKY_STEP: cnew = (float)(first_risky - 1); break;
+                    case SM_EPC_LENGTH: cnew = (float)ep_len; break;
+                    case SM_EPC_RETURN: cnew = (float)ep_return; break;
+                    case SM_EPC_REASON: cnew = (float)reason; break;
+                    case SM_EPC_HUMAN_BRAKED:
+                        cnew = cprev + ((A.buf.hstate && A.buf.hstate[(size_t)env * SM_HSTATE_STRIDE + SM_HS_BRAKED] != 0.0) ? 1.f : 0.f);
+                        break;
+                    default: break;
+                }
+                float* dst = done ? A.buf.epinfo + (size_t)env * SM_EP_STRIDE : acc;
+                dst[slot] = cnew;
+            }
+        }
         if (sl == 0 && done && valid) {  // episode statistics (train.py:59-117), aggregated per block first
             atomicAdd(&s_stats[0], 1.0);
             atomicAdd(&s_stats[1], ep_return);

@@ -604,6 +604,7 @@ class Scene:
         h.min_start_static = he["closest_point_safety_distance"] + 0.09      # ctlp.py:1475-1477
         h.min_start_self = he["closest_point_safety_distance"] + 0.04
         h.obs_size = 3 * 8 + 2 * 3 + 2 * 3 + 2                               # observations.py:54-77
+        h.initial_braking_trajectory = int(sampling)                         # safe_motions_base.py:961-967
 
     @staticmethod
     def _angular_motion_disc(parts, inertial_xyz):

@@ -101,6 +101,9 @@ class SafeMotionsVecEnv:
             self.hbrake = torch.zeros((n, abi.SM_HBRAKE_STEPS * abi.SM_HUMAN_JOINTS), dtype=torch.float64, device=dev)
             self.hobs = torch.zeros((n, abi.SM_HOBS_STRIDE), dtype=torch.float32, device=dev)
             self.hactions = torch.zeros((n, abi.SM_HUMAN_JOINTS), dtype=torch.float32, device=dev)
+        # per-episode aggregates of the step info (include/smenv.h SM_EP_*): running record and last finished episode
+        self.epacc = torch.zeros((n, abi.SM_EP_STRIDE), dtype=torch.float32, device=dev)
+        self.epinfo = torch.zeros((n, abi.SM_EP_STRIDE), dtype=torch.float32, device=dev)
         opt = lambda t: t.data_ptr() if t is not None else None
         self._buf = abi.SmBuffers(
             kin=self.kin.data_ptr(), obst=self.obst.data_ptr(), episode=self.episode.data_ptr(),
@@ -108,7 +111,7 @@ class SafeMotionsVecEnv:
             reward=self.reward.data_ptr(), done=self.done.data_ptr(), term_reason=self.term_reason.data_ptr(),
             info=self.info.data_ptr(), stats=self.stats.data_ptr(), target=opt(self.target),
             hkin=opt(self.hkin), hstate=opt(self.hstate), hbrake=opt(self.hbrake), hobs=opt(self.hobs),
-            hactions=opt(self.hactions))
+            epacc=self.epacc.data_ptr(), epinfo=self.epinfo.data_ptr(), hactions=opt(self.hactions))
         # pinned host staging for the host-buffer API (step_host)
         self._h_actions = torch.zeros((n, nj), dtype=torch.float32).pin_memory()
         self.host_actions = self._h_actions.numpy()   # pinned input buffer of step_host
@@ -410,33 +413,94 @@ class SafeMotionsVecEnv:
         return self.obs, self.reward, self.done, self.info
 
     # ------------------------------------------------------------------ info dicts (materialised on demand)
-    def infos(self, only_done=False):
-        """Per-env info dicts with the reference's key names (safe_motions_base.py:1350-1396, rewards.py:490-498)."""
-        info = self.info.cpu().numpy()
-        done = self.done.cpu().numpy()
-        reason = self.term_reason.cpu().numpy()
-        out = []
-        for e in range(self.num_envs):
-            if only_done and not done[e]:
-                out.append({})
+    def _step_info(self, row):
+        """The step's info of one env as the reference nests it ('average' / 'max' / 'min' hold the step's values,
+        safe_motions_base.py:1350-1365, rewards.py:490-498, actions.py:339-340)."""
+        step = dict(collision_rate_self=float(row[abi.INFO["coll_self"]]),
+                    collision_rate_static_obstacles=float(row[abi.INFO["coll_static"]]),
+                    collision_rate_moving_obstacles=float(row[abi.INFO["coll_moving"]]),
+                    action_punishment=float(row[abi.INFO["action_punishment"]]),
+                    self_collision_reward=float(row[abi.INFO["r_self"]]),
+                    static_obstacles_collision_reward=float(row[abi.INFO["r_static"]]),
+                    moving_obstacles_collision_reward=float(row[abi.INFO["r_moving"]]))
+        if self.scene.struct.use_target_points:
+            step["target_point_reward"] = float(row[abi.INFO["tp_reward"]])
+        if self._gate_threshold is not None:
+            step["risky_action_rate"] = float(row[abi.INFO["risky_action"]])
+        mx = dict(step, joint_jerk_violation=float(row[abi.INFO["max_jerk_rel"]] > 1.002))
+        return {"average": step, "max": mx, "min": dict(step)}
+
+    def _episode_info(self, rec, row, reason):
+        """End-of-episode keys (safe_motions_base.py:1367-1396, ctlp.py:1141-1309) plus, under 'episode', what
+        train.py:59-117 derives from the per-step info dicts of the reference: <key>_average / _max / _min over the
+        episode, aggregated on the device (SmBuffers.epinfo)."""
+        n = max(1.0, float(rec[abi.EPC["length"]]))
+        agg = {}
+        for k, name in enumerate(abi.EP_SCALARS):
+            if name == "target_point_reward" and not self.scene.struct.use_target_points:
                 continue
-            row = info[e]
-            step = dict(collision_rate_self=float(row[abi.INFO["coll_self"]]),
-                        collision_rate_static_obstacles=float(row[abi.INFO["coll_static"]]),
-                        collision_rate_moving_obstacles=float(row[abi.INFO["coll_moving"]]),
-                        action_punishment=float(row[abi.INFO["action_punishment"]]),
-                        self_collision_reward=float(row[abi.INFO["r_self"]]),
-                        static_obstacles_collision_reward=float(row[abi.INFO["r_static"]]),
-                        moving_obstacles_collision_reward=float(row[abi.INFO["r_moving"]]),
-                        joint_jerk_violation=float(row[abi.INFO["max_jerk_rel"]] > 1.002))
-            d = {"average": dict(step), "max": dict(step), "min": {}}
+            if name == "risky_action_rate" and self._gate_threshold is None:
+                continue
+            if name.endswith("_violation"):
+                agg[name + "_max"] = float(rec[16 + k])
+                continue
+            agg[name + "_average"] = float(rec[k]) / n
+            if not name.startswith("joint_vel_norm") and name != "observation_clipping_rate":
+                agg[name + "_max"] = float(rec[16 + k])
+                agg[name + "_min"] = float(rec[32 + k])
+        d = {"episode": agg,
+             "episode_length": int(rec[abi.EPC["length"]]),
+             "trajectory_length": self.scene.struct.episode_steps + 1,
+             "termination_reason": int(reason),
+             "trajectory_successful": 0.0 if int(reason) == self.TERMINATION_JOINT_LIMITS else 1.0,
+             "episode_return": float(rec[abi.EPC["ret"]]),
+             # the braking-trajectory method is off for the robot: the reference logs 1.0 per step for both lists
+             # (SURVEY Appendix A, Q4)
+             "obstacles_time_influenced_by_braking_trajectory": 2.0,
+             "obstacles_time_influenced_by_braking_trajectory_collision": 1.0,
+             "obstacles_time_influenced_by_braking_trajectory_torque": 1.0,
+             "obstacles_num_target_points_reached": float(rec[abi.EPC["targets_reached"]])}
+        if self._gate_threshold is not None:
+            first = float(rec[abi.EPC["first_risky_step"]])
+            d["risk_network_first_risky_action_step"] = first if first >= 0 else float("nan")
+        if self.config.use_moving_objects:
+            hit, missed = float(rec[abi.EPC["balls_hit_robot"]]), float(rec[abi.EPC["balls_missed"]])
+            d["moving_object_hit_robot_total"] = hit
+            d["moving_object_missed_robot_total"] = missed     # includes balls that ended on the table or the floor
+            if hit + missed > 0:
+                d["moving_object_hit_robot_fraction"] = hit / (hit + missed)
+                d["moving_object_missed_robot_fraction"] = missed / (hit + missed)
+        if self.has_human:
+            d["human_braking_trajectory_steps"] = float(rec[abi.EPC["human_braked"]])
+        return d
+
+    def infos(self, only_done=False):
+        """Per-env info dicts with the reference's key names.  only_done: dicts only for the envs whose episode ended in
+        the last step (what RLlib's callbacks need), the others get {}: host work proportional to the number of finished
+        episodes, not to the number of envs."""
+        done = self.done.cpu().numpy()
+        idx = np.nonzero(done)[0]
+        out = [{} for _ in range(self.num_envs)]
+        if only_done and idx.size == 0:
+            return out
+        if only_done:
+            sel = torch.as_tensor(idx, device=self.device)
+            info = self.info.index_select(0, sel).cpu().numpy()
+            rec = self.epinfo.index_select(0, sel).cpu().numpy()
+            reason = self.term_reason.index_select(0, sel).cpu().numpy()
+            for i, e in enumerate(idx):
+                d = self._step_info(info[i])
+                d.update(self._episode_info(rec[i], info[i], reason[i]))
+                out[e] = d
+            return out
+        info = self.info.cpu().numpy()
+        rec = self.epinfo.cpu().numpy()
+        reason = self.term_reason.cpu().numpy()
+        for e in range(self.num_envs):
+            d = self._step_info(info[e])
             if done[e]:
-                d["episode_length"] = int(row[abi.INFO["episode_length"]])
-                d["trajectory_length"] = self.scene.struct.episode_steps + 1
-                d["termination_reason"] = int(reason[e])
-                d["trajectory_successful"] = 1.0
-                d["episode_return"] = float(row[abi.INFO["episode_return"]])
-            out.append(d)
+                d.update(self._episode_info(rec[e], info[e], reason[e]))
+            out[e] = d
         return out
 
     def episode_statistics(self, reset=False):
@@ -573,7 +637,7 @@ class SafeMotionsVecEnv:
 
     # ------------------------------------------------------------------ backup-client look-ahead (risk ground truth)
     _STATE = ("kin", "obst", "episode", "ep_return", "target", "stats", "obs", "reward", "done", "term_reason", "info",
-              "hkin", "hstate", "hbrake", "hobs", "hactions")
+              "hkin", "hstate", "hbrake", "hobs", "hactions", "epacc", "epinfo")
 
     def snapshot(self):
         """Copy of the whole env state (the reference clones its Bullet state into a "backup client" with

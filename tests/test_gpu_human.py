@@ -97,7 +97,8 @@ def test_human_rollout_matches_oracle():
         # ---- main env
         ok = alive & same_h
         assert np.array_equal(env.kin.cpu().numpy()[alive], orc.kin[alive]), "robot joint trajectory"
-        d_dev, d_ref = info.cpu().numpy()[:, :3], o_info[:, :3]
+        d_dev, d_ref = info.cpu().numpy()[:, :3], o_info[:, :3].copy()
+        d_ref[(d_ref[:, 1] > 0.05) & (d_ref[:, 1] <= 0.102), 1] = 0.102   # reporting rule of the self class (test_gpu_parity.reported)
         edge = np.zeros(n, dtype=bool)
         for col, caps in ((0, (1e-3, 0.102)), (1, (1e-3, 0.102)), (2, (1e-3, 0.6))):
             for th in caps:

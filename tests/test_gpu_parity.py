@@ -32,6 +32,15 @@ def make_env(name, n, **kw):
     return SafeMotionsVecEnv(num_envs=n, config=CONFIGS[name](**cfg_kw), **opts)
 
 
+def reported(d):
+    """Distances as the device reports them: a self-collision distance above the reward's relevant distance (0.05 m in
+    every shipped config) cannot change reward or termination, such pairs are pruned and the class reports the cap."""
+    d = np.array(d, dtype=np.float64, copy=True)
+    col = d[..., 1]
+    col[(col > 0.05) & (col <= 0.102)] = 0.102
+    return d
+
+
 def knife_edge(d_raw_oracle, caps):
     """True where an oracle distance sits within 1e-5 m of a decision threshold (flags may legitimately differ)."""
     edge = np.zeros(d_raw_oracle.shape[0], dtype=bool)
@@ -100,7 +109,7 @@ def test_distances_match_oracle(name):
     kin = np.zeros((n, 32))
     kin[:, 0:7] = q
     ds, dse, dm = (x.cpu().numpy() for x in env.distances(kin, ob))
-    ref = np.array([oracle.distances(sc, q[e], ob[e]) for e in range(n)])
+    ref = reported(np.array([oracle.distances(sc, q[e], ob[e]) for e in range(n)]))
     clamp = lambda d: np.where(d < THRESH, 0.0, d)    # below 1 mm everything counts as collision (rewards.py:115)
     for dev, col in ((ds, 0), (dse, 1), (dm, 2)):
         assert np.abs(clamp(dev) - clamp(ref[:, col])).max() < 1e-4, (name, col)
@@ -137,7 +146,7 @@ def test_golden_rollout(name):
         o_info = g["out_info"][s]
         ok = alive.copy()
         assert np.array_equal(kin[ok], g["out_kin"][s][ok]), "joint trajectory must be bit-exact"
-        d_dev, d_ref = info.cpu().numpy()[:, :3], o_info[:, :3]
+        d_dev, d_ref = info.cpu().numpy()[:, :3], reported(o_info[:, :3])
         assert np.abs(d_dev - d_ref)[ok].max() < 1e-4
         flags_equal = (info.cpu().numpy()[:, 3:6] == o_info[:, 3:6]).all(1) & (done.cpu().numpy() == g["out_done"][s])
         edge = knife_edge(d_ref, caps) | (np.abs(d_dev - d_ref).max(1) > 0)  # flag flips need a distance on an edge
@@ -172,7 +181,7 @@ def test_rollout_from_device_pools_matches_oracle(name):
         nb = np.concatenate([dev_ob[:, 2:12], dev_ob[:, 14:16]], axis=1)   # the launch the device drew from its pool
         o_obs, o_rew, o_done, o_term, o_info = orc.step(act, nb)
         assert np.array_equal(env.kin.cpu().numpy()[alive], orc.kin[alive])
-        assert np.abs(info.cpu().numpy()[:, :3] - o_info[:, :3])[alive].max() < 1e-4
+        assert np.abs(info.cpu().numpy()[:, :3] - reported(o_info[:, :3]))[alive].max() < 1e-4
         same = (done.cpu().numpy() == o_done) & (info.cpu().numpy()[:, 3:6] == o_info[:, 3:6]).all(1)
         mism += int((~same & alive).sum())
         alive &= same
@@ -794,3 +803,39 @@ def test_behavioural_pin_shipped_backup_policy_avoids_collisions(name):
         rates["policy"], rates["random"]))
     assert rates["policy"] < 0.5 * rates["random"]
     assert rates["policy"] < 0.25
+
+
+def test_episode_aggregates_match_host_accumulation():
+    """SmBuffers.epinfo: sum / max / min of the step scalars over each finished episode, accumulated on the device,
+    against the same aggregation done on the host from the per-step outputs (what train.py:59-117 does with the
+    reference's per-step info dicts)."""
+    n = 512
+    env = make_env("ball", n, auto_reset=True)
+    env.reset()
+    keys = [("coll_self", 0), ("coll_static", 1), ("coll_moving", 2), ("action_punishment", 3), ("r_self", 4),
+            ("r_static", 5), ("r_moving", 6)]
+    s = np.zeros((n, 8)); mx = np.full((n, 8), -np.inf); mn = np.full((n, 8), np.inf)
+    checked = 0
+    rng = np.random.default_rng(0)
+    for _ in range(45):
+        act = rng.uniform(-1, 1, (n, 7)).astype(np.float32)
+        _, rew, done, info = env.step(act)
+        info, rew, done = info.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy().astype(bool)
+        vals = np.stack([info[:, I[k]] for k, _ in keys] + [rew], 1)
+        s += vals; mx = np.maximum(mx, vals); mn = np.minimum(mn, vals)
+        if done.any():
+            rec = env.epinfo.cpu().numpy()[done]
+            for c in range(8):
+                assert np.allclose(rec[:, c], s[done, c], rtol=1e-5, atol=1e-4)
+                assert np.allclose(rec[:, 16 + c], mx[done, c], atol=1e-6) and np.allclose(rec[:, 32 + c], mn[done, c], atol=1e-6)
+            assert np.array_equal(rec[:, abi.EPC["length"]], info[done, I["episode_length"]])
+            assert np.allclose(rec[:, abi.EPC["ret"]], info[done, I["episode_return"]], rtol=1e-6)
+            assert np.array_equal(rec[:, abi.EPC["reason"]], env.term_reason.cpu().numpy()[done])
+            checked += int(done.sum())
+            s[done] = 0; mx[done] = -np.inf; mn[done] = np.inf
+    assert checked >= 2 * n
+    d = [x for x in env.infos(only_done=True) if x]
+    for x in d[:3]:
+        assert x["episode_length"] <= 20 and "collision_rate_moving_obstacles_average" in x["episode"]
+        assert x["trajectory_successful"] == 1.0 and "moving_object_hit_robot_total" in x
+    env.close()
