@@ -136,14 +136,28 @@ def cpu_reference_run(scene_name, envs_per_thread, steps, warmup, threads, targe
         tgt = np.tile([0.3, 0.3, 0.5], (envs_per_thread, 1)) if scene.struct.use_target_points else None
         env.set_state(q, np.zeros_like(q), np.zeros_like(q), ob, tgt)
         env._q0, env._ob0, env._tgt = q, ob, tgt
+        if scene.struct.human.enabled:   # the human starts with its arms lowered, at rest, first target in front of it
+            hq = np.tile([0.3, -0.3, 0.2, -0.8, -0.3, -0.3, -0.2, -0.8], (envs_per_thread, 1)) + \
+                rng.uniform(-0.1, 0.1, (envs_per_thread, 8))
+            env._h0 = (hq, np.zeros_like(hq), np.zeros_like(hq), np.tile([0.4, -0.3, 0.3], (envs_per_thread, 1)),
+                       np.zeros(envs_per_thread, dtype=np.int32))
+            env.set_human_state(*env._h0)
         shards.append(env)
     acts = rng.uniform(-1, 1, (envs_per_thread, scene.n_joints)).astype(np.float32)
     nb = np.tile(np.array([2.4, 0.3, 1.0, -5.5, -0.6, 1.5, 0.3, 0.1, 0.0, 1.0, 200, 150.0]), (envs_per_thread, 1))
 
+    hacts = rng.uniform(-1, 1, (envs_per_thread, 8)).astype(np.float32)
+    htgt = np.tile([0.35, 0.3, 0.35], (envs_per_thread, 1))
+
     def one_step(env):
-        _, _, done, _, _ = env.step(acts, nb, env._tgt)
+        if scene.struct.human.enabled:
+            _, _, done, _, _ = env.step_human(acts, hacts, htgt)
+        else:
+            _, _, done, _, _ = env.step(acts, nb, env._tgt)
         if done.any():  # episodes restart from the same pool of start states
             env.set_state(env._q0, np.zeros_like(env._q0), np.zeros_like(env._q0), env._ob0, env._tgt)
+            if scene.struct.human.enabled:
+                env.set_human_state(*env._h0)
     with ThreadPoolExecutor(threads) as pool:
         tw = time.perf_counter()
         for _ in range(max(1, warmup)):
@@ -183,7 +197,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--scene", default="ball")
+    ap.add_argument("--scene", default="human",
+                    help="headline workload: human = BASELINE.json configs[2] (the config the 1/2/4/8 sweep is quoted on); the "
+                         "scenes of --scenes are measured after it and reported in the same line")
     ap.add_argument("--envs", type=int, default=65536, help="environments per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -193,7 +209,7 @@ def main():
     ap.add_argument("--risk-gate", action="store_true",
                     help="risk network + backup policy (tensor cores) in front of every step (BASELINE.json configs[3])")
     ap.add_argument("--risk-threshold", type=float, default=None)
-    ap.add_argument("--scenes", default="space,space_bm,ball",
+    ap.add_argument("--scenes", default="space,space_bm,ball,human",
                     help="further scenes measured (device-timed, shorter) after the main one and reported under 'scenes'")
     ap.add_argument("--no-scenes", action="store_true")
     args = ap.parse_args()
@@ -245,6 +261,7 @@ def main():
                               full=False, with_cpu=False)
             if rank == 0:
                 extra[name] = {k: r[k] for k in ("value", "ms_per_step", "workload", "gpu_launches", "roofline")}
+                extra[name]["launch"] = r["config"]["launch"]
                 extra[name]["e2e"] = r["e2e"]
     if rank == 0:
         out = {"impl": "b200", "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world,
@@ -281,6 +298,7 @@ def measure_scene(scene_name, args, dev, rank, world, local_rank, fma_peaks, ste
               "l2": "flushed between timed steps (256 MiB write)"}
     cfg = scene_config(scene_name)
     env = SafeMotionsVecEnv(num_envs=args.envs, device=dev, seed=1000 * rank, auto_reset=True, config=cfg)
+    config["launch"] = env.launch_config()
     gate_thr = None
     if args.risk_gate and full:
         env.load_networks()

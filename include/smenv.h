@@ -420,6 +420,9 @@ int smenv_copy_human_pools(SmEnv* env, double* host_start /* [P][64] */, double*
 int smenv_counters(SmEnv* env, SmCounters* out, int reset);
 int smenv_enable_counters(SmEnv* env, int enable);
 int smenv_launch_count(SmEnv* env, unsigned long long* out);
+/* out[8]: GJK grid, GJK threads per CTA, GJK dynamic shared memory bytes, direction-table words, planning grid, planning
+ * shared memory bytes, SM count, env ranges of the device step */
+int smenv_launch_config(SmEnv* env, int32_t* out);
 /* Measurement mode: with enable != 0 every smenv_step brackets each of its kernels with CUDA events on the caller's
  * stream and synchronises at the end of the step (so it is for measurement passes, not for the timed rollout).
  * smenv_kernel_times returns the accumulated milliseconds per SmKernel and the number of steps accumulated. */
@@ -449,6 +452,15 @@ int smenv_risk_gate(SmEnv* env, const SmBuffers* buf, float threshold, float* ri
  * computed from it, safe_motions_base.py:1066); info slots SM_INFO_RISKY_ACTION / RISK / FIRST_RISKY_STEP report the
  * gate.  Needs both networks (smenv_mlp_load).  threshold < 0 switches the gate off (default). */
 int smenv_set_risk_gate(SmEnv* env, float threshold);
+/* Exact gate (default on): the tensor-core risk (fp16 operands) of the rows within `band` of the threshold is re-computed
+ * in float32 on the CUDA cores before the decision, and the backup policy's action of the risky rows is computed in
+ * float32 too, so that decisions and executed actions are those of a float32 evaluation of the shipped networks
+ * (safe_motions_base.py:1597-1603, actions.py:328-333).  exact = 0: both networks on the tensor cores only.
+ * band <= 0 keeps the current band (default 0.01; the fp16 error around the reference's thresholds is < 4e-3). */
+int smenv_set_gate_exact(SmEnv* env, int exact, float band);
+/* The loaded network `which` in float32 on the CUDA cores for n rows (parity hook of the exact gate). */
+int smenv_mlp_forward_exact(SmEnv* env, int which, const float* in0, int in0_w, const float* in1, int in1_w, float* out,
+                            int out_stride, int n_out, int n, SmStream stream);
 /* Writes the U(-1,1) actions smenv_step_random would use for the next step into buf->actions (so that the gate can be
  * applied to them; follow with smenv_step). */
 int smenv_random_actions(SmEnv* env, const SmBuffers* buf, SmStream stream);

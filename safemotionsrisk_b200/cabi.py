@@ -49,6 +49,9 @@ def load():
     lib.smenv_human_pool_sizes.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
     lib.smenv_copy_human_pools.argtypes = [vp, vp, vp]
     lib.smenv_measure_fma_peaks.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.smenv_launch_config.argtypes = [vp, C.POINTER(i32)]
+    lib.smenv_set_gate_exact.argtypes = [vp, i32, C.c_float]
+    lib.smenv_mlp_forward_exact.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, vp]
     lib.smenv_set_seed.argtypes = [vp, u64]
     lib.smenv_set_risk_gate.argtypes = [vp, C.c_float]
     lib.smenv_random_actions.argtypes = [vp, C.POINTER(abi.SmBuffers), vp]

@@ -32,25 +32,25 @@ static int fail(int code, const std::string& msg) {
 // diam * (distance to the nearest sample) of the maximum -- then it is listed for every direction of the cell it
 // could win.  Float rounding of lut_cell on the device at a cell border is covered by the same slack.
 // ------------------------------------------------------------------------------------------------------------------
-static void build_lut_uncached(const float4* v, int n, std::vector<uint32_t>& out);
+static void build_lut_uncached(const float4* v, int n, int R, std::vector<uint32_t>& out);
 
 // tables are cached per process (keyed by the vertex bytes): every env of a scene shares the same hulls
-static void build_lut(const float4* v, int n, std::vector<uint32_t>& out) {
+static void build_lut(const float4* v, int n, int R, std::vector<uint32_t>& out) {
     static std::mutex mu;
     static std::map<std::string, std::vector<uint32_t>> cache;
-    const std::string key(reinterpret_cast<const char*>(v), (size_t)n * sizeof(float4));
+    const std::string key = std::string(reinterpret_cast<const char*>(v), (size_t)n * sizeof(float4)) + (char)R;
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);
     if (it == cache.end()) {
         std::vector<uint32_t> t;
-        build_lut_uncached(v, n, t);
+        build_lut_uncached(v, n, R, t);
         it = cache.emplace(key, std::move(t)).first;
     }
     out.insert(out.end(), it->second.begin(), it->second.end());
 }
 
-static void build_lut_uncached(const float4* v, int n, std::vector<uint32_t>& out) {
-    const int R = SM_LUT_RES, SUB = 17, cells = 6 * R * R;
+static void build_lut_uncached(const float4* v, int n, int R, std::vector<uint32_t>& out) {
+    const int SUB = R >= 8 ? 17 : 33, cells = 6 * R * R;   // the same sample density on the sphere for coarse cells
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     for (int i = 0; i < n; ++i) {
         const float p[3] = {v[i].x, v[i].y, v[i].z};
@@ -161,6 +161,7 @@ struct SmEnv {
     int* d_flag = nullptr;       // its device alias
     size_t smem_bytes_gjk = 0;
     int grid_gjk = 0;
+    int gjk_threads = GJK_THREADS;   // 512 when only one CTA of the GJK kernel fits on an SM
     MlpNet nets[SM_NET_COUNT];   // risk network, backup policy, human policy (smenv_mlp_load)
     bool net_loaded[SM_NET_COUNT] = {};
     std::vector<void*> net_allocs;
@@ -169,6 +170,9 @@ struct SmEnv {
     float* d_exec = nullptr;     // [n][n_joints] actions executed when the gate is on (smenv_set_risk_gate)
     uint8_t* d_risky = nullptr;  // [n] 1 where the gate replaced the action
     float gate_threshold = -1.0f;  // < 0: gate off
+    int* d_gate_list = nullptr;    // [0..15] counters (two per env range), then [n] near-threshold rows, [n] risky rows
+    int gate_exact = 1;            // re-rate near-threshold rows and compute the backup actions in float32 (smenv_set_gate_exact)
+    float gate_band = 0.01f;       // |risk - threshold| below which the tensor-core risk is re-rated
     // Human scene (smenv_human.cuh)
     bool human = false;
     int human_external = 0;        // the human's actions come from buf->hactions (parity protocol)
@@ -342,17 +346,27 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     // support-direction tables for the hulls that profit most (many vertices), as long as the GJK kernel's shared-memory
     // image (vertices + tables + shapes) fits into an SM: the threshold doubles until it does (Human scene: 50 shapes,
     // 4000 vertices -> tables only for the robot links)
-    for (int min_verts = SM_LUT_MIN_VERTS;; min_verts = 2 * min_verts - 1) {
+    // Which hulls get a table, and how fine: every hull of at least 33 vertices with 8 x 8 cells per cube face if that
+    // fits into 200 KB of shared memory next to the vertices; else coarse 4 x 4 tables for the hulls of up to 64 vertices
+    // (Human scene: 40 human parts); else only the big hulls.  SMENV_LUT_CONFIG=<k> forces configuration k (experiments).
+    static const int lut_configs[5][2] = {{33, 8}, {33, 4}, {65, 8}, {129, 8}, {256, 8}};   // min vertices, cells of small hulls
+    const int forced_cfg = getenv("SMENV_LUT_CONFIG") ? atoi(getenv("SMENV_LUT_CONFIG")) : -1;
+    for (int ci = forced_cfg >= 0 && forced_cfg < 5 ? forced_cfg : 0; ci < 5; ++ci) {
+        const int min_verts = lut_configs[ci][0], small_res = lut_configs[ci][1];
         lut.clear();
         for (int s = 0; s < sc->n_shapes; ++s) {
             const SmShape& h = sc->shapes[s];
             d.shapes[s].lut = -1;
             if (h.vert_cnt >= min_verts && h.vert_cnt <= 255) {
-                d.shapes[s].lut = (int)lut.size();
-                build_lut(verts.data() + h.vert_off, h.vert_cnt, lut);
+                const int R = h.vert_cnt <= 64 ? small_res : SM_LUT_RES;
+                d.shapes[s].lut = (int)lut.size() | (R == SM_LUT_RES ? 0 : SM_LUT_COARSE);
+                build_lut(verts.data() + h.vert_off, h.vert_cnt, R, lut);
             }
         }
-        if (gjk_smem_bytes(sc->n_verts, (int)lut.size() + 4, sc->n_shapes) <= 200 * 1024 || min_verts > 255) break;
+        // measured (profiles/r02_gjk_config_sweep.txt, space_bm): a support query through a table (~15 candidates) instead of
+        // a scan of all 64 vertices is worth more than a second resident CTA -- the kernel runs as two 256-thread CTAs per
+        // SM up to 112 KB, else as one 512-thread CTA (sixteen warps per SM either way)
+        if (gjk_smem_bytes(sc->n_verts, (int)lut.size() + 4, sc->n_shapes) <= 200 * 1024 || ci == 4) break;
     }
     d.n_static_pairs = sc->n_static_pairs; d.n_self_pairs = sc->n_self_pairs;
     d.n_mov_reward = sc->n_mov_reward; d.n_mov_contact = sc->n_mov_contact;
@@ -757,6 +771,8 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
         if (env->smem_bytes_gjk > lim_gjk) {
             CU(cudaFuncSetAttribute(gjk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_gjk));
             CU(cudaFuncSetAttribute(gjk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_gjk));
+            CU(cudaFuncSetAttribute(gjk_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_gjk));
+            CU(cudaFuncSetAttribute(gjk_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_gjk));
             lim_gjk = env->smem_bytes_gjk;
         }
         if (env->smem_bytes > lim_geom) {
@@ -781,6 +797,11 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     env->grid_broad = sms * per_sm;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk_kernel<false>, GJK_THREADS, env->smem_bytes_gjk));
     if (per_sm < 1) { return fail(SM_ERR_CUDA, "gjk kernel does not fit on an SM"); }
+    if (per_sm == 1 && !getenv("SMENV_GJK_256")) {   // one big CTA instead of a half-empty SM
+        int per_sm_512 = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_512, gjk_kernel<false, 512>, 512, env->smem_bytes_gjk));
+        if (per_sm_512 >= 1) { env->gjk_threads = 512; per_sm = per_sm_512; }
+    }
     env->grid_gjk = sms * per_sm;
     // big batches step as two env ranges side by side: the latency-bound tails of one range's kernels (the longest
     // position-bound solve, the last GJK pairs) hide behind the other's (Space, 65 536 envs: 799 -> 748 us per step)
@@ -803,7 +824,7 @@ extern "C" int smenv_destroy(SmEnv* env) {
     cudaFree(env->d_counters); cudaFree(env->d_scratch); cudaFree(env->d_worklist); cudaFree(env->d_heavy); cudaFree(env->d_cwork); cudaFree(env->d_tasks); cudaFree(env->d_hpar); cudaFree(env->d_items); cudaFree(env->d_res);
     if (env->h_flag) cudaFreeHost(env->h_flag);
     for (void* q : env->net_allocs) cudaFree(q);
-    cudaFree(env->d_risk); cudaFree(env->d_backup); cudaFree(env->d_exec); cudaFree(env->d_risky);
+    cudaFree(env->d_risk); cudaFree(env->d_backup); cudaFree(env->d_exec); cudaFree(env->d_risky); cudaFree(env->d_gate_list);
     cudaFree(env->d_hpairs); cudaFree(env->d_hthresh); cudaFree(env->d_hrange); cudaFree(env->d_hbacc); cudaFree(env->d_hposes);
     cudaFree(env->d_hbinfo); cudaFree(env->d_hunits); cudaFree(env->d_hscratch); cudaFree(env->d_hpolicy); cudaFree(env->d_hstart_pool); cudaFree(env->d_htarget_pool);
     for (int i = 0; i <= SM_K_COUNT; ++i) if (env->ev[i]) cudaEventDestroy(env->ev[i]);
@@ -1142,21 +1163,68 @@ static int mlp_launch(SmEnv* env, int which, MlpSeg s0, MlpSeg s1, MlpSeg s2, fl
 
 // The risk gate over the envs of `bv` (a view of m envs): risk network on (risk observation, proposed action), backup
 // policy on the risk observation, then the executed actions into `exec` (== bv.actions: in place).
-static int gate_launch(SmEnv* env, const SmBuffers& bv, int m, float threshold, float* risk, uint8_t* risky, float* backup,
-                       float* exec, cudaStream_t stream) {
+static int mlp_exact_launch(SmEnv* env, int which, MlpSeg s0, MlpSeg s1, MlpSeg s2, const int* rows, const int* n_rows,
+                            int max_rows, float* out, int out_stride, int n_write, cudaStream_t stream) {
+    if (!env->net_loaded[which]) return fail(SM_ERR_STATE, "network not loaded (smenv_mlp_load)");
+    MlpExactArgs X;
+    memset(&X, 0, sizeof(X));
+    X.net = env->nets[which]; X.rows = rows; X.n_rows = n_rows; X.n_rows_host = max_rows;
+    const MlpSeg segs[3] = {s0, s1, s2};
+    for (int i = 0; i < 3; ++i) { X.in[i] = segs[i].p; X.in_stride[i] = segs[i].stride; X.in_w[i] = segs[i].w; }
+    X.out = out; X.out_stride = out_stride; X.n_write = n_write;
+    int blocks = (max_rows + MLP_EXACT_ROWS - 1) / MLP_EXACT_ROWS;
+    if (blocks > 4 * env->sms) blocks = 4 * env->sms;   // grid-stride over the list; blocks beyond its length exit at once
+    if (blocks < 1) blocks = 1;
+    mlp_exact_kernel<<<blocks, 256, 0, stream>>>(X);
+    env->launches++;
+    CU(cudaGetLastError());
+    return SM_OK;
+}
+
+// The risk gate over the envs of `bv` (a view of m envs starting at env e0 of the whole vector env): risk network on
+// (risk observation, proposed action) on the tensor cores; in exact mode the rows within gate_band of the threshold are
+// re-rated in float32 and the backup policy's action of the risky rows is computed in float32 on that subset; else the
+// backup policy runs on the tensor cores for every row.  Executed actions go to `exec` (== bv.actions: in place).
+static int gate_launch(SmEnv* env, const SmBuffers& bv, int e0, int m, int chunk, float threshold, float* risk, uint8_t* risky,
+                       float* backup, float* exec, cudaStream_t stream) {
     const DevScene& hs = env->host_scene;
     const int nj = hs.n_joints, ow = hs.obs_size;
     // the risk observation is the observation without the target-point entries (observations.py:419-431): joint
     // position / velocity / acceleration, then the obstacle entries
     const int n_tp = hs.use_target_points ? 3 * hs.obs_add_tp_pos + 3 * hs.obs_add_tp_rel : 0;
     const MlpSeg kinem{bv.obs, ow, 3 * nj}, rest{bv.obs + 3 * nj + n_tp, ow, ow - 3 * nj - n_tp};
+    const MlpSeg act{bv.actions, nj, nj}, none{nullptr, 0, 0};
     int rc;
-    if ((rc = mlp_launch(env, SM_NET_RISK, kinem, rest, MlpSeg{bv.actions, nj, nj}, risk, 1, m, stream))) return rc;
-    if ((rc = mlp_launch(env, SM_NET_BACKUP, kinem, rest, MlpSeg{nullptr, 0, 0}, backup, MLP_MAX_OUT, m, stream))) return rc;
-    risk_gate_kernel<<<(m + 255) / 256, 256, 0, stream>>>(bv.actions, exec, risk, backup, MLP_MAX_OUT, nj, m, threshold, risky);
+    if ((rc = mlp_launch(env, SM_NET_RISK, kinem, rest, act, risk, 1, m, stream))) return rc;
+    if (!env->gate_exact) {
+        if ((rc = mlp_launch(env, SM_NET_BACKUP, kinem, rest, none, backup, MLP_MAX_OUT, m, stream))) return rc;
+        risk_gate_kernel<<<(m + 255) / 256, 256, 0, stream>>>(bv.actions, exec, risk, backup, MLP_MAX_OUT, nj, m, threshold, risky);
+        env->launches++;
+        CU(cudaGetLastError());
+        return SM_OK;
+    }
+    int* counts = env->d_gate_list + 2 * chunk;
+    int* near_list = env->d_gate_list + 32 + e0;
+    int* risky_list = env->d_gate_list + 32 + env->n + e0;
+    CU(cudaMemsetAsync(counts, 0, 2 * sizeof(int), stream));
+    gate_band_kernel<<<(m + 255) / 256, 256, 0, stream>>>(risk, m, threshold, env->gate_band, near_list, counts);
     env->launches++;
+    if ((rc = mlp_exact_launch(env, SM_NET_RISK, kinem, rest, act, near_list, counts, m, risk, 1, 1, stream))) return rc;
+    risk_decide_kernel<<<(m + 255) / 256, 256, 0, stream>>>(bv.actions, exec, risk, nj, m, threshold, risky, risky_list, counts + 1);
+    env->launches++;
+    if ((rc = mlp_exact_launch(env, SM_NET_BACKUP, kinem, rest, none, risky_list, counts + 1, m, exec, nj, nj, stream))) return rc;
     CU(cudaGetLastError());
     return SM_OK;
+}
+
+static void launch_gjk(SmEnv* env, const GjkArgs& G, cudaStream_t stream) {
+    if (env->gjk_threads == 512) {
+        if (env->count) gjk_kernel<true, 512><<<env->grid_gjk, 512, env->smem_bytes_gjk, stream>>>(G);
+        else gjk_kernel<false, 512><<<env->grid_gjk, 512, env->smem_bytes_gjk, stream>>>(G);
+    } else {
+        if (env->count) gjk_kernel<true><<<env->grid_gjk, GJK_THREADS, env->smem_bytes_gjk, stream>>>(G);
+        else gjk_kernel<false><<<env->grid_gjk, GJK_THREADS, env->smem_bytes_gjk, stream>>>(G);
+    }
 }
 
 // The kernels of one env step over the envs [e0, e0 + m) on `stream`, with the work lists of slot `chunk`: every list
@@ -1204,7 +1272,7 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
             JA.random_actions = 0;
         }
         float* exec = env->d_exec + (size_t)e0 * env->host_scene.n_joints;
-        int rc = gate_launch(env, buf_v, m, env->gate_threshold, env->d_risk + e0, env->d_risky + e0,
+        int rc = gate_launch(env, buf_v, e0, m, chunk, env->gate_threshold, env->d_risk + e0, env->d_risky + e0,
                              env->d_backup + (size_t)e0 * MLP_MAX_OUT, exec, stream);
         if (rc) return rc;
         JA.exec = exec;
@@ -1278,8 +1346,7 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
             SM_MARK(SM_K_HUMAN_BRAKE_GJK);
             GjkArgs GB;
             GB.items = items; GB.n_items = worklist; GB.capacity = capacity; GB.res = res; GB.counters = env->d_counters;
-            if (env->count) gjk_kernel<true><<<env->grid_gjk, GJK_THREADS, env->smem_bytes_gjk, stream>>>(GB);
-            else gjk_kernel<false><<<env->grid_gjk, GJK_THREADS, env->smem_bytes_gjk, stream>>>(GB);
+            launch_gjk(env, GB, stream);
             env->launches += 2;
         }
         else SM_MARK(SM_K_HUMAN_BRAKE_GJK);
@@ -1367,8 +1434,7 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
         CU(cudaStreamWaitEvent(stream, env->side_join[chunk], 0));
     }
     SM_MARK(SM_K_GJK);
-    if (env->count) gjk_kernel<true><<<env->grid_gjk, GJK_THREADS, env->smem_bytes_gjk, stream>>>(G);
-    else gjk_kernel<false><<<env->grid_gjk, GJK_THREADS, env->smem_bytes_gjk, stream>>>(G);
+    launch_gjk(env, G, stream);
     SM_MARK(SM_K_FINISH);
     if (env->count) finish_kernel<true><<<grid_f, 256, 0, stream>>>(A);
     else finish_kernel<false><<<grid_f, 256, 0, stream>>>(A);
@@ -1606,7 +1672,7 @@ extern "C" int smenv_distances(SmEnv* env, const double* kin, const double* obst
     const int blocks = (n + SM_WARPS_PER_BLOCK - 1) / SM_WARPS_PER_BLOCK;
     const int grid_p = blocks < env->grid_broad ? blocks : env->grid_broad;
     distance_plan_kernel<false><<<grid_p, T, env->smem_bytes_broad, stream>>>(P);
-    gjk_kernel<false><<<env->grid_gjk, GJK_THREADS, env->smem_bytes_gjk, stream>>>(G);
+    launch_gjk(env, G, stream);
     distances_out_kernel<<<(n + 255) / 256, 256, 0, stream>>>(env->d_res, obst, d_static, d_self, d_moving, n);
     env->launches += 3;
     CU(cudaGetLastError());
@@ -1668,6 +1734,13 @@ extern "C" int smenv_mlp_load(SmEnv* env, int which, int n_tc, const int32_t* di
                                    (size_t)(n % 8) * 16 + (size_t)(kl % 8) * 2;
                 packed[off / 2] = __float2half_rn(k < K_real ? wp[(size_t)k * N + n] : 0.0f);
             }
+        {   // float32 copy of the kernel for the exact evaluation of single rows
+            float* dw32 = nullptr;
+            CU(cudaMalloc((void**)&dw32, (size_t)K_real * N * sizeof(float)));
+            env->net_allocs.push_back(dw32);
+            CU(cudaMemcpy(dw32, wp, (size_t)K_real * N * sizeof(float), cudaMemcpyHostToDevice));
+            net.w32[l] = dw32;
+        }
         wp += (size_t)K_real * N;
         __half* dw = nullptr;
         float* db = nullptr;
@@ -1704,6 +1777,8 @@ extern "C" int smenv_mlp_load(SmEnv* env, int which, int n_tc, const int32_t* di
         CU(cudaMalloc((void**)&env->d_exec, (size_t)env->n * SM_MAX_JOINTS * sizeof(float)));
         CU(cudaMalloc((void**)&env->d_risky, (size_t)env->n));
         CU(cudaMemset(env->d_risky, 0, (size_t)env->n));
+        CU(cudaMalloc((void**)&env->d_gate_list, ((size_t)env->n * 2 + 32) * sizeof(int)));
+        CU(cudaMemset(env->d_gate_list, 0, ((size_t)env->n * 2 + 32) * sizeof(int)));
     }
     CU(cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SM_BYTES));
     return SM_OK;
@@ -1726,8 +1801,8 @@ extern "C" int smenv_risk_gate(SmEnv* env, const SmBuffers* buf, float threshold
     cudaStream_t stream = (cudaStream_t)s;
     DevLock dev_lock_(env); int rc = activate(env, stream);
     if (rc) return rc;
-    return gate_launch(env, *buf, env->n, threshold, risk_out ? risk_out : env->d_risk, risky_out, env->d_backup,
-                       const_cast<float*>(buf->actions), stream);
+    return gate_launch(env, *buf, 0, env->n, 0, threshold, risk_out ? risk_out : env->d_risk, risky_out ? risky_out : env->d_risky,
+                       env->d_backup, const_cast<float*>(buf->actions), stream);
 }
 
 extern "C" int smenv_set_risk_gate(SmEnv* env, float threshold) {
@@ -1736,6 +1811,25 @@ extern "C" int smenv_set_risk_gate(SmEnv* env, float threshold) {
         return fail(SM_ERR_STATE, "smenv_set_risk_gate: load the risk network and the backup policy first (smenv_mlp_load)");
     env->gate_threshold = threshold >= 0.0f ? threshold : -1.0f;
     return SM_OK;
+}
+
+extern "C" int smenv_set_gate_exact(SmEnv* env, int exact, float band) {
+    if (!env) return fail(SM_ERR_ARG, "smenv_set_gate_exact: null env");
+    env->gate_exact = exact != 0;
+    if (band > 0.0f) env->gate_band = band;
+    if (env->host_graph) { cudaGraphExecDestroy(env->host_graph); env->host_graph = nullptr; }
+    return SM_OK;
+}
+
+extern "C" int smenv_mlp_forward_exact(SmEnv* env, int which, const float* in0, int in0_w, const float* in1, int in1_w,
+                                       float* out, int out_stride, int n_out, int n, SmStream s) {
+    if (!env || !in0 || !out || which < 0 || which >= SM_NET_COUNT || n <= 0) return fail(SM_ERR_ARG, "smenv_mlp_forward_exact: bad argument");
+    cudaStream_t stream = (cudaStream_t)s;
+    DevLock dev_lock_(env); int rc = activate(env, stream);
+    if (rc) return rc;
+    if (in0_w + (in1 ? in1_w : 0) != env->nets[which].n_in) return fail(SM_ERR_ARG, "network input width does not match the loaded weights");
+    return mlp_exact_launch(env, which, MlpSeg{in0, in0_w, in0_w}, MlpSeg{in1, in1 ? in1_w : 0, in1 ? in1_w : 0},
+                            MlpSeg{nullptr, 0, 0}, nullptr, nullptr, n, out, out_stride, n_out, stream);
 }
 
 extern "C" int smenv_set_seed(SmEnv* env, uint64_t seed) {
@@ -1776,6 +1870,12 @@ extern "C" int smenv_kernel_times(SmEnv* env, double* ms_out, int* steps_out, in
         for (int i = 0; i < SM_K_COUNT; ++i) env->kernel_ms[i] = 0.0;
         env->timed_steps = 0;
     }
+    return SM_OK;
+}
+extern "C" int smenv_launch_config(SmEnv* env, int32_t* out) {
+    if (!env || !out) return fail(SM_ERR_ARG, "null argument");
+    out[0] = env->grid_gjk; out[1] = env->gjk_threads; out[2] = (int32_t)env->smem_bytes_gjk; out[3] = env->host_scene.n_lut_words;
+    out[4] = env->grid_broad; out[5] = (int32_t)env->smem_bytes_broad; out[6] = env->sms; out[7] = env->step_ranges;
     return SM_OK;
 }
 extern "C" int smenv_launch_count(SmEnv* env, unsigned long long* out) {

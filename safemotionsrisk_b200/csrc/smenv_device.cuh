@@ -42,19 +42,26 @@ struct DevShape {
 #endif
 #define SM_LUT_MIN_VERTS 33 /* smaller hulls are scanned directly */
 
-__host__ __device__ __forceinline__ int lut_cell(float dx, float dy, float dz) {
+// cell of direction d on a cube map with res x res cells per face
+__host__ __device__ __forceinline__ int lut_cell_res(float dx, float dy, float dz, int res) {
     const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
     int face;
     float m, u, w;
     if (ax >= ay && ax >= az) { face = dx > 0.0f ? 0 : 1; m = ax; u = dy; w = dz; }
     else if (ay >= az) { face = dy > 0.0f ? 2 : 3; m = ay; u = dz; w = dx; }
     else { face = dz > 0.0f ? 4 : 5; m = az; u = dx; w = dy; }
-    const float s = (0.5f * SM_LUT_RES) / m;
-    int iu = (int)(u * s + 0.5f * SM_LUT_RES), iw = (int)(w * s + 0.5f * SM_LUT_RES);
-    iu = iu < 0 ? 0 : (iu > SM_LUT_RES - 1 ? SM_LUT_RES - 1 : iu);
-    iw = iw < 0 ? 0 : (iw > SM_LUT_RES - 1 ? SM_LUT_RES - 1 : iw);
-    return (face * SM_LUT_RES + iu) * SM_LUT_RES + iw;
+    const float half = 0.5f * (float)res;
+    const float s = half / m;
+    int iu = (int)(u * s + half), iw = (int)(w * s + half);
+    iu = iu < 0 ? 0 : (iu > res - 1 ? res - 1 : iu);
+    iw = iw < 0 ? 0 : (iw > res - 1 ? res - 1 : iw);
+    return (face * res + iu) * res + iw;
 }
+__host__ __device__ __forceinline__ int lut_cell(float dx, float dy, float dz) { return lut_cell_res(dx, dy, dz, SM_LUT_RES); }
+// DevShape.lut: word offset of the table | SM_LUT_COARSE if the table has SM_LUT_RES_COARSE^2 cells per face (small
+// hulls of scenes whose tables would not fit into shared memory otherwise)
+#define SM_LUT_COARSE 0x40000000
+#define SM_LUT_RES_COARSE 4
 
 // limits of one set of joints: the robot's, or the human's (nested env, ctlp.py:4647-4959)
 struct JointLim {

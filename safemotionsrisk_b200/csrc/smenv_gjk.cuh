@@ -79,8 +79,8 @@ __device__ __forceinline__ int support_thread(const float4* __restrict__ v, int 
     float best = -FLT_MAX;
     int bi = 0;
     if (lut_off >= 0) {
-        const uint32_t* L = lut + lut_off;
-        const uint32_t e = L[lut_cell(d.x, d.y, d.z)];
+        const uint32_t* L = lut + (lut_off & (SM_LUT_COARSE - 1));
+        const uint32_t e = L[lut_cell_res(d.x, d.y, d.z, (lut_off & SM_LUT_COARSE) ? SM_LUT_RES_COARSE : SM_LUT_RES)];
         const uint32_t* w = L + (e >> 8);
         const int cnt = (int)(e & 255u);
         ndots += (unsigned)cnt;
@@ -117,8 +117,10 @@ __device__ __forceinline__ int support_thread(const float4* __restrict__ v, int 
 #define GJK_THREADS 256  /* threads per CTA */
 #endif
 
-template <bool COUNT>
-__global__ void __launch_bounds__(GJK_THREADS, GJK_MIN_BLOCKS) gjk_kernel(GjkArgs A) {
+// THREADS: 256 with two CTAs per SM when the scene's shared-memory image (vertices + direction tables + shapes) allows
+// it, else 512 with one CTA per SM (Human scene: 4000 vertices) -- sixteen warps per SM either way
+template <bool COUNT, int THREADS = GJK_THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS <= 256 ? GJK_MIN_BLOCKS : 1) gjk_kernel(GjkArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int n_items = *A.n_items;
     if (n_items > A.capacity) n_items = A.capacity;

@@ -54,6 +54,7 @@ struct MlpNet {
     const float* b[MLP_MAX_TC];
     const float* w_out;       // [dims[n_tc-1]][out_pad]
     const float* b_out;       // [out_pad]
+    const float* w32[MLP_MAX_TC];  // float32 kernels [in][out] row-major of the hidden layers (exact evaluation of a few rows)
 };
 
 struct MlpArgs {
@@ -382,4 +383,121 @@ __global__ void random_actions_kernel(float* actions, int nj, int n, int env_bas
     if (env >= n) return;
     uint4 r = philox((uint32_t)(env + env_base), step_counter, (uint32_t)j, 0xAC71u, k0, k1);
     actions[t] = 2.0f * u01f(r.x) - 1.0f;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Exact (float32, CUDA cores) evaluation of a network on a LIST of rows: the tensor-core pass rates every env with fp16
+// operands; rows whose risk lies within a band around the threshold are re-rated here so that the gate decision equals the
+// float32 decision of the reference's TensorFlow model (safe_motions_base.py:1597-1603), and the backup policy's action
+// of the risky envs is computed here in float32 as well (actions.py:328-333).  One CTA = eight rows; a thread owns output
+// columns, the weights stream through L2 once per eight rows.
+// ------------------------------------------------------------------------------------------------------------------
+#define MLP_EXACT_ROWS 8
+struct MlpExactArgs {
+    MlpNet net;
+    const int* rows;      // [*n_rows] row indices, or NULL: rows 0 .. *n_rows - 1
+    const int* n_rows;    // device counter
+    int n_rows_host;      // used when n_rows == NULL
+    const float* in[3];
+    int in_stride[3], in_w[3];
+    float* out;
+    int out_stride, n_write;   // the first n_write outputs of every listed row are written
+};
+
+__device__ __forceinline__ float mlp_hidden_act_exact(float x, int act) {
+    if (act == MLP_ACT_SELU) return 1.0507009873554805f * (x > 0.0f ? x : 1.6732632423543772f * (expf(x) - 1.0f));
+    return x / (1.0f + expf(-x));
+}
+
+__global__ void __launch_bounds__(256) mlp_exact_kernel(MlpExactArgs A) {
+    __shared__ float xa[MLP_EXACT_ROWS][MLP_MAX_WIDTH], xb[MLP_EXACT_ROWS][MLP_MAX_WIDTH];
+    __shared__ int row_id[MLP_EXACT_ROWS];
+    const int n_rows = A.n_rows ? *A.n_rows : A.n_rows_host;
+    const MlpNet& net = A.net;
+    const int tid = threadIdx.x;
+#pragma unroll 1
+    for (int base = blockIdx.x * MLP_EXACT_ROWS; base < n_rows; base += gridDim.x * MLP_EXACT_ROWS) {
+        __syncthreads();
+        if (tid < MLP_EXACT_ROWS) row_id[tid] = base + tid < n_rows ? (A.rows ? A.rows[base + tid] : base + tid) : -1;
+        __syncthreads();
+        for (int i = tid; i < MLP_EXACT_ROWS * net.n_in; i += blockDim.x) {
+            const int r = i / net.n_in, k = i - r * net.n_in, row = row_id[r];
+            float x = 0.0f;
+            if (row >= 0) {
+                if (k < A.in_w[0]) x = A.in[0][(size_t)row * A.in_stride[0] + k];
+                else if (k < A.in_w[0] + A.in_w[1]) x = A.in[1][(size_t)row * A.in_stride[1] + (k - A.in_w[0])];
+                else x = A.in[2][(size_t)row * A.in_stride[2] + (k - A.in_w[0] - A.in_w[1])];
+            }
+            xa[r][k] = x;
+        }
+        __syncthreads();
+        float (*src)[MLP_MAX_WIDTH] = xa;
+        float (*dst)[MLP_MAX_WIDTH] = xb;
+        int K = net.n_in;
+#pragma unroll 1
+        for (int l = 0; l < net.n_tc; ++l) {
+            const int N = net.dims[l];
+            const float* W = net.w32[l];
+#pragma unroll 1
+            for (int n = tid; n < N; n += blockDim.x) {
+                float acc[MLP_EXACT_ROWS];
+                const float b = __ldg(net.b[l] + n);
+#pragma unroll
+                for (int r = 0; r < MLP_EXACT_ROWS; ++r) acc[r] = b;
+#pragma unroll 4
+                for (int k = 0; k < K; ++k) {
+                    const float w = __ldg(W + (size_t)k * N + n);
+#pragma unroll
+                    for (int r = 0; r < MLP_EXACT_ROWS; ++r) acc[r] = fmaf(src[r][k], w, acc[r]);
+                }
+#pragma unroll
+                for (int r = 0; r < MLP_EXACT_ROWS; ++r) dst[r][n] = mlp_hidden_act_exact(acc[r], net.hidden_act);
+            }
+            __syncthreads();
+            float (*t)[MLP_MAX_WIDTH] = src; src = dst; dst = t;
+            K = N;
+        }
+        if (tid < MLP_EXACT_ROWS * A.n_write) {
+            const int r = tid / A.n_write, o = tid - r * A.n_write, row = row_id[r];
+            if (row >= 0) {
+                float acc = __ldg(net.b_out + o);
+                for (int k = 0; k < K; ++k) acc = fmaf(src[r][k], __ldg(net.w_out + (size_t)k * net.out_pad + o), acc);
+                A.out[(size_t)row * A.out_stride + o] = net.out_act == MLP_OUT_SIGMOID ? 1.0f / (1.0f + expf(-acc)) : tanhf(acc);
+            }
+        }
+    }
+}
+
+// rows whose tensor-core risk lies within `band` of the threshold -> list (re-rated exactly before the gate decides)
+__global__ void gate_band_kernel(const float* risk, int n, float threshold, float band, int* list, int* count) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool near = env < n && fabsf(risk[env] - threshold) < band;
+    const unsigned m = __ballot_sync(FULL, near);
+    if (m) {
+        int b0 = 0;
+        if (lane == __ffs(m) - 1) b0 = atomicAdd(count, __popc(m));
+        b0 = __shfl_sync(FULL, b0, __ffs(m) - 1);
+        if (near) list[b0 + __popc(m & ((1u << lane) - 1u))] = env;
+    }
+}
+
+// the gate decision; risky envs are listed so that their backup action can be computed (exact mode)
+__global__ void risk_decide_kernel(const float* actions, float* exec, const float* risk, int nj, int n, float threshold,
+                                   uint8_t* risky, int* list, int* count) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool r = env < n && risk[env] >= threshold;
+    if (env < n) {
+        if (risky) risky[env] = r ? 1 : 0;
+        if (exec != actions)
+            for (int j = 0; j < nj; ++j) exec[(size_t)env * nj + j] = actions[(size_t)env * nj + j];
+    }
+    const unsigned m = __ballot_sync(FULL, r);
+    if (m) {
+        int b0 = 0;
+        if (lane == __ffs(m) - 1) b0 = atomicAdd(count, __popc(m));
+        b0 = __shfl_sync(FULL, b0, __ffs(m) - 1);
+        if (r) list[b0 + __popc(m & ((1u << lane) - 1u))] = env;
+    }
 }

@@ -615,6 +615,25 @@ class SafeMotionsVecEnv:
                                                out.data_ptr(), n_out, n, self._stream()), "smenv_mlp_forward")
         return out
 
+    def set_gate_exact(self, exact=True, band=0.0):
+        """Exact gate (default on): rows whose tensor-core risk lies within `band` (default 0.01) of the threshold are
+        re-rated in float32 and the backup action of the risky rows is computed in float32 (smenv_set_gate_exact)."""
+        cabi.check(self._lib.smenv_set_gate_exact(self._handle, int(bool(exact)), float(band)), "smenv_set_gate_exact")
+
+    def mlp_forward_exact(self, which, in0, in1=None, n_out=1):
+        """Parity hook: the loaded network `which` in float32 on the CUDA cores (the exact path of the gate)."""
+        in0 = torch.as_tensor(in0, dtype=torch.float32, device=self.device).contiguous()
+        n = in0.shape[0]
+        out = torch.zeros((n, n_out), dtype=torch.float32, device=self.device)
+        p1, w1 = None, 0
+        if in1 is not None:
+            in1 = torch.as_tensor(in1, dtype=torch.float32, device=self.device).contiguous()
+            p1, w1 = C.c_void_p(in1.data_ptr()), in1.shape[1]
+        cabi.check(self._lib.smenv_mlp_forward_exact(self._handle, which, in0.data_ptr(), in0.shape[1], p1, w1,
+                                                     out.data_ptr(), n_out, n_out, n, self._stream()),
+                   "smenv_mlp_forward_exact")
+        return out
+
     def risk_gate(self, threshold=None):
         """Replaces, in self.actions, every action the risk network rates >= threshold by the backup policy's action
         for the current observation (actions.py:303-340).  Returns (risk [N], risky [N])."""
@@ -709,6 +728,13 @@ class SafeMotionsVecEnv:
         cabi.check(self._lib.smenv_kernel_times(self._handle, ms, C.byref(steps), int(reset)), "smenv_kernel_times")
         n = max(1, steps.value)
         return {k: ms[i] / n for i, k in enumerate(self.KERNELS)}, steps.value
+
+    def launch_config(self):
+        """Launch geometry the library chose for this scene (GJK CTAs / threads / shared memory, planning grid ...)."""
+        out = (C.c_int32 * 8)()
+        cabi.check(self._lib.smenv_launch_config(self._handle, out), "smenv_launch_config")
+        keys = ("gjk_grid", "gjk_threads", "gjk_smem_bytes", "lut_words", "plan_grid", "plan_smem_bytes", "sms", "step_ranges")
+        return dict(zip(keys, [int(x) for x in out]))
 
     def launch_count(self):
         n = C.c_ulonglong()

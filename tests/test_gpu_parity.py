@@ -21,6 +21,12 @@ CONFIGS = {"space_task": lambda **k: space_task_config(**k),
            "space_bm": lambda **k: space_backup_config(ball_machine_mode=True, **k),
            "ball_bm": lambda **k: ball_backup_config(ball_machine_mode=True, **k)}
 I = abi.INFO
+
+
+def _assets(name):
+    return os.path.join(os.path.dirname(GOLDEN), "..", "safemotionsrisk_b200", "assets", "networks_{}.npz".format(name))
+
+
 THRESH = 1e-3   # collision threshold of the reward (rewards.py:115-155)
 
 
@@ -423,7 +429,27 @@ def test_networks_match_the_float32_reference(name):
     env.close()
 
 
+def test_exact_network_path_matches_the_float32_reference():
+    """The float32 CUDA-core path of the gate (mlp_exact_kernel) against the NumPy float32 forward pass: only the
+    summation order differs (1e-5 absolute on outputs in [0, 1] / [-1, 1])."""
+    from oracle import mlp
+    env = make_env("space_bm", 777)
+    env.load_networks()
+    w = np.load(_assets("space"))
+    rng = np.random.default_rng(6)
+    obs = rng.uniform(-1, 1, (777, env.scene.obs_size)).astype(np.float32)
+    act = rng.uniform(-1, 1, (777, 7)).astype(np.float32)
+    risk = env.mlp_forward_exact(0, obs, act, n_out=1).cpu().numpy()[:, 0]
+    pol = env.mlp_forward_exact(1, obs, None, n_out=7).cpu().numpy()
+    assert np.abs(risk - mlp.risk_forward(w, obs, act)).max() < 1e-5
+    assert np.abs(pol - mlp.backup_forward(w, obs)).max() < 1e-5
+    env.close()
+
+
 def test_risk_gate_replaces_exactly_the_risky_actions():
+    """Gate decisions are those of a float32 evaluation of the shipped networks (exact gate: the tensor-core risk of
+    the rows within 0.01 of the threshold is re-rated in float32, the backup action of the risky rows is computed in
+    float32): decisions may differ only where the float32 risk itself lies within 1e-5 of the threshold."""
     from oracle import mlp
     n, thr = 4096, 0.065    # README.md:223 risk_threshold of the Space task
     env = make_env("space_bm", n, auto_reset=True)
@@ -431,7 +457,7 @@ def test_risk_gate_replaces_exactly_the_risky_actions():
     env.reset()
     for _ in range(5):
         env.step_random()
-    w = np.load(os.path.join(os.path.dirname(GOLDEN), "..", "safemotionsrisk_b200", "assets", "networks_space.npz"))
+    w = np.load(_assets("space"))
     obs = env.obs.cpu().numpy().copy()
     act = np.random.default_rng(9).uniform(-1, 1, (n, 7)).astype(np.float32)
     env.actions.copy_(torch.from_numpy(act))
@@ -439,13 +465,24 @@ def test_risk_gate_replaces_exactly_the_risky_actions():
     torch.cuda.synchronize()
     o_act, o_risk, o_risky = mlp.gate(w, obs, act, thr)
     risk, risky, gated = risk.cpu().numpy(), risky.cpu().numpy().astype(bool), env.actions.cpu().numpy()
-    assert np.abs(risk - o_risk).max() < 3e-2
-    clear = np.abs(o_risk - thr) > 4e-3          # decisions may differ only on the knife edge
+    assert np.abs(risk - o_risk).max() < 3e-2                       # far from the threshold: tensor-core value
+    near = np.abs(o_risk - thr) < 5e-3
+    assert np.abs(risk - o_risk)[near].max() < 1e-5                 # in the band: float32 value
+    clear = np.abs(o_risk - thr) > 1e-5
     assert np.array_equal(risky[clear], o_risky[clear])
-    assert 0 < risky.sum() < n                   # the gate fires on some envs, not on all
+    assert 0 < risky.sum() < n                                      # the gate fires on some envs, not on all
     same = risky == o_risky
-    assert np.abs(gated[same] - o_act[same]).max() < 3e-2
-    assert np.array_equal(gated[~risky], act[~risky])   # safe actions pass through untouched
+    assert np.abs(gated[same] - o_act[same]).max() < 1e-5           # backup actions in float32
+    assert np.array_equal(gated[~risky], act[~risky])               # safe actions pass through untouched
+    # tensor cores only (smenv_set_gate_exact(0)): decisions may differ on the fp16 knife edge
+    env.set_gate_exact(False)
+    env.actions.copy_(torch.from_numpy(act))
+    risk2, risky2 = env.risk_gate(thr)
+    torch.cuda.synchronize()
+    risky2 = risky2.cpu().numpy().astype(bool)
+    assert np.array_equal(risky2[np.abs(o_risk - thr) > 4e-3], o_risky[np.abs(o_risk - thr) > 4e-3])
+    assert np.abs(env.actions.cpu().numpy()[risky2 & o_risky] - o_act[risky2 & o_risky]).max() < 3e-2
+    env.set_gate_exact(True)
     # and the gated step runs end to end
     env.step_gated(threshold=thr)
     torch.cuda.synchronize()
@@ -621,9 +658,6 @@ def test_host_step_in_ranges_equals_the_device_step(scene):
 
 
 # ---------------------------------------------------------------------------------------------- round 2: gate wiring
-def _assets(name):
-    return os.path.join(os.path.dirname(GOLDEN), "..", "safemotionsrisk_b200", "assets", "networks_{}.npz".format(name))
-
 
 def test_gate_inside_step_keeps_the_proposed_action_for_the_reward():
     """actions.py:303-340 / safe_motions_base.py:1066: the gate replaces the executed action only; the action
