@@ -76,24 +76,55 @@ class ClockSampler:
 
     def __init__(self, index):
         self.rows, self.proc = [], None
+        self.nvml_rows, self.nvml_stop, self.nvml_thread = [], threading.Event(), None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
+        try:   # the same counters straight from NVML every 5 ms: one nvidia-smi query takes longer than a short timed region
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml_thread = threading.Thread(target=self._read_nvml, daemon=True)
+            self.nvml_thread.start()
+        except Exception:
+            self.nvml_thread = None
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
+    def _read_nvml(self):
+        n = self.nvml
+        bits = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
+        try:
+            mx = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        while not self.nvml_stop.is_set():
+            try:
+                clk = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.nvml_rows.append((time.time(), clk, mx, [k for k, b in bits.items() if mask & b]))
+            except Exception:
+                break
+            time.sleep(0.005)
+
     def stop(self, t0, t1):
-        if self.proc is None:
+        if self.proc is None and self.nvml_thread is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        time.sleep(0.05)
+        self.nvml_stop.set()
+        if self.proc is not None:
+            self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ts, line in self.rows:
@@ -104,13 +135,20 @@ class ClockSampler:
                 clk, mx = float(parts[0]), float(parts[1])
             except ValueError:
                 continue
-            if t0 - 0.05 <= ts <= t1 + 0.15:
+            if t0 - 0.01 <= ts <= t1 + 0.03:
                 sm.append(clk)
                 for name, val in zip(names, parts[3:7]):
                     if val.lower().startswith("active"):
                         reasons.add(name)
+        n_smi = len(sm)
+        nv = [r for r in self.nvml_rows if t0 <= r[0] <= t1]
+        for _, clk, nmx, rs in nv:
+            sm.append(clk)
+            mx = mx if mx is not None else nmx
+            reasons.update(rs)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "samples_nvidia_smi": n_smi, "samples_nvml": len(nv),
+                "source": "nvidia-smi -lms 20 and NVML every 5 ms, samples inside the timed region"}
 
 
 def cpu_reference_run(scene_name, envs_per_thread, steps, warmup, threads, target_seconds=None):
@@ -191,6 +229,26 @@ def _emit(line):
     os.write(_STDOUT_FD if _STDOUT_FD is not None else 1, (line + "\n").encode())
 
 
+def bind_to_gpu_cpus(local_rank):
+    """Pins this rank to the CPUs nearest to its GPU (NVML's ideal affinity) before any pinned host buffer exists, so
+    that the staging buffers of the host-buffer step are first touched on the GPU's own NUMA node.  Returns what was
+    done for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w in range(words) for b in range(64) if (mask[w] >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return {"bound": False, "why": "no overlap between the GPU's CPU set and this process' affinity"}
+        os.sched_setaffinity(0, allowed)
+        return {"bound": True, "cpus": "{}-{} ({})".format(allowed[0], allowed[-1], len(allowed))}
+    except Exception as e:  # the bench runs unbound
+        return {"bound": False, "why": repr(e)[:120]}
+
+
 def main():
     _quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -243,6 +301,8 @@ def main():
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
 
+    args.all_cpus = sorted(os.sched_getaffinity(0))   # the CPU baseline leg runs on every host core again
+    args.host_affinity = bind_to_gpu_cpus(local_rank)
     import torch
     import torch.distributed as dist
     if world > 1:
@@ -299,6 +359,7 @@ def measure_scene(scene_name, args, dev, rank, world, local_rank, fma_peaks, ste
     cfg = scene_config(scene_name)
     env = SafeMotionsVecEnv(num_envs=args.envs, device=dev, seed=1000 * rank, auto_reset=True, config=cfg)
     config["launch"] = env.launch_config()
+    config["host_affinity"] = args.host_affinity
     gate_thr = None
     if args.risk_gate and full:
         env.load_networks()
@@ -311,6 +372,7 @@ def measure_scene(scene_name, args, dev, rank, world, local_rank, fma_peaks, ste
 
     def one_step():
         env.step_random()
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # started early: nvidia-smi needs ~0.1 s to its first sample
     env.reset()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     for _ in range(max(3, args.warmup)):
@@ -321,7 +383,6 @@ def measure_scene(scene_name, args, dev, rank, world, local_rank, fma_peaks, ste
     launches0 = env.launch_count()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     t_wall0 = time.time()
     for i in range(steps):
         flush.fill_(i & 0xff)  # evict the env state from L2 (outside the timed region of the step)
@@ -446,13 +507,23 @@ def measure_scene(scene_name, args, dev, rank, world, local_rank, fma_peaks, ste
         torch.cuda.synchronize(dev)
         gate_ms = g0.elapsed_time(g1) / 10
         ow = sc.obs_size
-        gflop = 2.0 * args.envs * ((ow + sc_nj) * 512 + 512 * 256 + 256 * 128 + 128 + ow * 256 + 256 * 128 + 128 * sc_nj)
+        n_tp = 3 * (sc.obs_add_tp_pos + sc.obs_add_tp_rel) if sc.use_target_points else 0
+        risk_mac = (ow - n_tp + sc_nj) * 512 + 512 * 256 + 256 * 128 + 128
+        backup_mac = (ow - n_tp) * 256 + 256 * 128 + 128 * sc_nj
+        risky_frac = float(env.info[:, 16].mean().item())
+        # tensor cores: the risk network on every row; float32 CUDA cores: the risk network on the rows within the band
+        # of the threshold and the backup policy on the risky rows (smenv_set_gate_exact, the default)
+        gflop = 2.0 * args.envs * risk_mac
         tpeak = peaks.get("bf16_tflops", 2250.0)
-        roofline["risk_gate"] = {"bound": "tensor", "kernel": "mlp_kernel x2 + risk_gate_kernel", "ms": gate_ms,
+        roofline["risk_gate"] = {"bound": "tensor", "kernel": "mlp_kernel (risk network, all rows) + gate_band_kernel + "
+                                 "mlp_exact_kernel (near-threshold rows) + risk_decide_kernel + mlp_exact_kernel (backup "
+                                 "policy, risky rows)", "ms": gate_ms,
                                  "achieved": gflop / (gate_ms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
                                  "frac": gflop / (gate_ms * 1e-3) / 1e12 / tpeak,
+                                 "flops_counted": "risk network on all rows only (2 x {} MAC per row); the float32 subset "
+                                                  "passes add 2 x {} MAC per risky row".format(risk_mac, backup_mac),
                                  "peak_source": "MEASURED_PEAKS.json bf16_tflops" if peaks else "nominal",
-                                 "risky_fraction": float(env.info[:, 16].mean().item())}
+                                 "risky_fraction": risky_frac}
 
     # ---------------- end to end through the host-buffer API
     e2e = None
@@ -483,6 +554,7 @@ def measure_scene(scene_name, args, dev, rank, world, local_rank, fma_peaks, ste
     # ---------------- CPU baseline beside it (rank 0, N = 1 only, bounded sample)
     cpu = None
     if with_cpu:
+        os.sched_setaffinity(0, args.all_cpus)
         per_thread = 1024 if scene_name.startswith("ball") else 8 if scene_name.startswith("human") else 64
         val, dt, total, csteps = cpu_reference_run(scene_name, per_thread, 20, 1, threads, target_seconds=15.0)
         cpu = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",

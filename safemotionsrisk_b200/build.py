@@ -7,7 +7,7 @@ CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.environ.get("SMENV_LIB") or os.path.join(CSRC, "libsmenv.so")  # SMENV_LIB: experiment builds
 SOURCES = ["smenv.cu", "smenv_device.cuh", "smenv_geom.cuh", "smenv_kernels.cuh", "smenv_joint.cuh", "smenv_step.cuh",
            "smenv_gjk.cuh", "smenv_plan.cuh", "smenv_mlp.cuh",
-           "smenv_pools.cuh"]
+           "smenv_pools.cuh", "smenv_human.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared"]
 
@@ -24,7 +24,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "smenv.cu")]
+    extra = os.environ.get("SMENV_NVCC_EXTRA", "").split()   # experiment builds: e.g. -DSM_CONTACT_MIN_BLOCKS=3 with SMENV_LIB set
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "smenv.cu")]
     subprocess.check_call(cmd, cwd=CSRC)
     return LIB
 

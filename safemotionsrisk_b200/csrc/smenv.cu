@@ -189,6 +189,7 @@ struct SmEnv {
     double* d_htarget_pool = nullptr;  // [2][htarget_pool_n][4]
     int htarget_pool_n = 0;
     size_t smem_bytes_hplan = 0;
+    int grid_hplan = 0;              // resident CTAs of human_brake_plan_kernel on the device
     bool time_kernels = false;   // measurement mode (smenv_kernel_timing)
     cudaEvent_t ev[SM_K_COUNT + 1] = {};
     double kernel_ms[SM_K_COUNT] = {};
@@ -430,7 +431,14 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     {   // pair list of the distance planning
         int np = 0;
         auto push = [&](int a, int b, int cls) {
-            if (np < SM_MAX_PLAN_PAIRS) d.pair_tab[np] = (uint32_t)a | ((uint32_t)b << 12) | ((uint32_t)cls << 24);
+            if (np < SM_MAX_PLAN_PAIRS) {
+                const DevShape& SA = d.shapes[a];
+                const DevShape& SB = d.shapes[b];
+                const bool box = SB.frame == 0;
+                d.pair_tab[np] = (uint32_t)a | ((uint32_t)b << 12) | ((uint32_t)cls << 24) | (box ? 0x80000000u : 0u);
+                const float m = SA.margin + SB.margin;
+                d.pair_rm[np] = make_float2(m * (1.0f - 1e-6f), (SA.radius + (box ? 0.f : SB.radius) + m) * (1.0f + 1e-6f));
+            }
             ++np;
         };
         for (int i = 0; i < sc->n_static_pairs; ++i) push(sc->static_pairs[i][0], sc->static_pairs[i][1], 0);
@@ -575,6 +583,55 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
                 }
                 *r = rad * (1.0f + 1e-6f) + mrg + 1e-6f;
             };
+            // capsule around a set of shapes: segment along the principal axis of the vertices, radius = largest distance of a
+            // vertex to the segment (+ margin)
+            auto capsule = [&](const std::vector<int>& ids, float* seg, float* r) {
+                std::vector<std::array<double, 3>> pts;
+                double mrg = 0.0;
+                for (int id : ids) {
+                    const SmShape& sh = sc->shapes[id];
+                    mrg = std::max(mrg, sh.margin);
+                    for (int i = sh.vert_off; i < sh.vert_off + sh.vert_cnt; ++i)
+                        pts.push_back({sc->verts[3 * i], sc->verts[3 * i + 1], sc->verts[3 * i + 2]});
+                }
+                double m[3] = {0, 0, 0}, C[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+                for (auto& q : pts) for (int k = 0; k < 3; ++k) m[k] += q[k] / (double)pts.size();
+                for (auto& q : pts)
+                    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) C[a][b] += (q[a] - m[a]) * (q[b] - m[b]);
+                double u[3] = {1.0, 0.7, 0.3};
+                for (int it = 0; it < 64; ++it) {   // power iteration: dominant eigenvector of the covariance
+                    double w[3];
+                    for (int a = 0; a < 3; ++a) w[a] = C[a][0] * u[0] + C[a][1] * u[1] + C[a][2] * u[2];
+                    const double nrm = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+                    if (nrm < 1e-30) break;
+                    for (int a = 0; a < 3; ++a) u[a] = w[a] / nrm;
+                }
+                double tmin = 1e300, tmax = -1e300;
+                for (auto& q : pts) {
+                    const double t = (q[0] - m[0]) * u[0] + (q[1] - m[1]) * u[1] + (q[2] - m[2]) * u[2];
+                    tmin = std::min(tmin, t); tmax = std::max(tmax, t);
+                }
+                // pull the end points in by the cross-section radius (a capsule's caps cover the ends)
+                double rad_line = 0.0;
+                for (auto& q : pts) {
+                    const double t = (q[0] - m[0]) * u[0] + (q[1] - m[1]) * u[1] + (q[2] - m[2]) * u[2];
+                    double d2 = 0.0;
+                    for (int a = 0; a < 3; ++a) { const double e = q[a] - m[a] - t * u[a]; d2 += e * e; }
+                    rad_line = std::max(rad_line, sqrt(d2));
+                }
+                double t0 = tmin + rad_line, t1 = tmax - rad_line;
+                if (t0 > t1) t0 = t1 = 0.5 * (tmin + tmax);
+                double rad = 0.0;
+                for (auto& q : pts) {
+                    double t = (q[0] - m[0]) * u[0] + (q[1] - m[1]) * u[1] + (q[2] - m[2]) * u[2];
+                    t = std::min(std::max(t, t0), t1);
+                    double d2 = 0.0;
+                    for (int a = 0; a < 3; ++a) { const double e = q[a] - m[a] - t * u[a]; d2 += e * e; }
+                    rad = std::max(rad, sqrt(d2));
+                }
+                for (int a = 0; a < 3; ++a) { seg[a] = (float)(m[a] + t0 * u[a]); seg[3 + a] = (float)(m[a] + t1 * u[a]); }
+                *r = (float)(rad * (1.0 + 1e-5) + mrg + 1e-5);
+            };
             int ngp = 0;
             for (size_t i = 0; i < ps.size();) {
                 size_t e = i;
@@ -584,13 +641,50 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
                 for (size_t q = i; q < e; ++q) { ia.push_back(ps[q][2]); ib.push_back(ps[q][3]); }
                 u.gp_fa[ngp] = ps[i][0] - 100; u.gp_fb[ngp] = ps[i][1] >= 100 ? ps[i][1] - 100 : -1;   // -1: world frame
                 u.gp_off[ngp] = (int)i; u.gp_cnt[ngp] = (int)(e - i);
+                {   // the device code walks a group pair as two nested shape ranges
+                    std::vector<int> ua(ia), ub(ib);
+                    std::sort(ua.begin(), ua.end()); ua.erase(std::unique(ua.begin(), ua.end()), ua.end());
+                    std::sort(ub.begin(), ub.end()); ub.erase(std::unique(ub.begin(), ub.end()), ub.end());
+                    const bool dense = ua.size() * ub.size() == e - i && ua.back() - ua.front() + 1 == (int)ua.size() &&
+                                       ub.back() - ub.front() + 1 == (int)ub.size();
+                    if (!dense)
+                        return fail(SM_ERR_SCENE, "the pairs of the human's braking check between two frames must be the cross "
+                                                  "product of two contiguous shape ranges");
+                    if (ub.size() > 32) return fail(SM_ERR_SCENE, "braking check: more than 32 shapes on side B of a link-group pair");
+                    u.gp_a0[ngp] = ua.front(); u.gp_na[ngp] = (int)ua.size();
+                    u.gp_b0[ngp] = ub.front(); u.gp_nb[ngp] = (int)ub.size();
+                }
                 float dmin[3], dmax[3];
                 bound(ia, u.gp_ca[ngp], &u.gp_ra[ngp], dmin, dmax);
                 bound(ib, u.gp_cb[ngp], &u.gp_rb[ngp], u.gp_bmin[ngp], u.gp_bmax[ngp]);
+                capsule(ia, u.gp_sa[ngp], &u.gp_sra[ngp]);
+                capsule(ib, u.gp_sb[ngp], &u.gp_srb[ngp]);
                 ++ngp;
                 i = e;
             }
             u.n_gp = ngp;
+            // arm frames 3, 4, 7, 8: shape range and capsule (side A of every group pair is one of them)
+            const int arm_frames[4] = {103, 104, 107, 108};
+            for (int fi = 0; fi < 4; ++fi) {
+                std::vector<int> ids;
+                for (int q = 0; q < h.n_arm_shapes; ++q)
+                    if (sc->shapes[h.shape_off + q].frame == arm_frames[fi]) ids.push_back(h.shape_off + q);
+                u.hf_s0[fi] = ids.empty() ? h.shape_off : ids.front(); u.hf_sn[fi] = (int)ids.size();
+                if (!ids.empty() && ids.back() - ids.front() + 1 != (int)ids.size())
+                    return fail(SM_ERR_SCENE, "the shapes of a human arm frame must be contiguous");
+                for (int k = 0; k < 6; ++k) u.hf_seg[fi][k] = 0.f;
+                u.hf_rad[fi] = 0.f;
+                if (!ids.empty()) capsule(ids, u.hf_seg[fi], &u.hf_rad[fi]);
+            }
+            for (int g = 0; g < ngp; ++g) {
+                const int fa = u.gp_fa[g], fb = u.gp_fb[g];
+                const bool arm_a = fa == 3 || fa == 4 || fa == 7 || fa == 8, arm_b = fb == 3 || fb == 4 || fb == 7 || fb == 8;
+                if (!arm_a || !(arm_b || fb == 0 || fb == -1))
+                    return fail(SM_ERR_SCENE, "braking check: side A must be an arm frame, side B an arm frame, the trunk or the world");
+                if (h.n_arm_shapes > 32) return fail(SM_ERR_SCENE, "braking check: more than 32 arm shapes");
+                if (fb == 0 && (u.gp_b0[g] < h.shape_off + h.n_arm_shapes || h.n_shapes - h.n_arm_shapes > 32))
+                    return fail(SM_ERR_SCENE, "braking check: trunk shapes must follow the arm shapes (at most 32)");
+            }
             for (auto& q : ps) { hpairs.push_back((short)q[2]); hpairs.push_back((short)q[3]); }
         }
         // link groups: runs of consecutive human shapes in the same frame, with a bounding sphere in frame coordinates
@@ -674,7 +768,7 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
         CU(cudaMemset(env->d_hscratch, 0, N * SM_SCRATCH_FLOATS * sizeof(float)));
         CU(cudaMalloc((void**)&env->d_hpolicy, N * 16 * sizeof(float)));
         CU(cudaMemset(env->d_hpolicy, 0, N * 16 * sizeof(float)));
-        env->smem_bytes_hplan = sizeof(HumanBlockShared);
+        env->smem_bytes_hplan = human_plan_smem_bytes(sc->human.n_arm_shapes);
     }
     for (int o = 0; o < sc->n_obstacles; ++o) {
         if (sc->obst_kind[o] != SM_OBST_PLANET) continue;
@@ -706,6 +800,7 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
         memcpy(si.mov_contact, d.mov_contact, sizeof(si.mov_contact));
         memcpy(si.contact_thresh, d.contact_thresh, sizeof(si.contact_thresh));
         memcpy(img[0].pair_tab, d.pair_tab, sizeof(img[0].pair_tab));
+        memcpy(img[0].pair_rm, d.pair_rm, sizeof(img[0].pair_rm));
         if ((rc = upload(&env->d_scene_img, img))) { return rc; }
         d.scene_img = reinterpret_cast<const uint4*>(env->d_scene_img);
     }
@@ -763,6 +858,19 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
 
     env->smem_bytes = smem_bytes_for(sc->n_verts, SM_WARPS_PER_BLOCK);
     env->smem_bytes_broad = smem_bytes_for(0, SM_WARPS_PER_BLOCK);
+    {   // the planning kernels' shared memory (scene image + per-warp scratch, a compile-time size) is above the 48 KB default
+        static bool raised[SM_MAX_DEVICES] = {};
+        if (!raised[device % SM_MAX_DEVICES]) {
+            const int b = (int)env->smem_bytes_broad;
+            CU(cudaFuncSetAttribute(contact_coarse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            CU(cudaFuncSetAttribute(contact_coarse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            CU(cudaFuncSetAttribute(contact_plan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            CU(cudaFuncSetAttribute(contact_plan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            CU(cudaFuncSetAttribute(distance_plan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            CU(cudaFuncSetAttribute(distance_plan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            raised[device % SM_MAX_DEVICES] = true;
+        }
+    }
     env->smem_bytes_gjk = gjk_smem_bytes(sc->n_verts, d.n_lut_words, sc->n_shapes);
     {   // opt-in shared-memory limits are per function and process wide: only ever raised, so that an env created
         // earlier with bigger tables keeps launching
@@ -773,6 +881,10 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
             CU(cudaFuncSetAttribute(gjk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_gjk));
             CU(cudaFuncSetAttribute(gjk_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_gjk));
             CU(cudaFuncSetAttribute(gjk_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_gjk));
+            CU(cudaFuncSetAttribute(gjk_kernel<false, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_gjk));
+            CU(cudaFuncSetAttribute(gjk_kernel<true, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_gjk));
+            CU(cudaFuncSetAttribute(gjk_kernel<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_gjk));
+            CU(cudaFuncSetAttribute(gjk_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_gjk));
             lim_gjk = env->smem_bytes_gjk;
         }
         if (env->smem_bytes > lim_geom) {
@@ -801,8 +913,32 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
         int per_sm_512 = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_512, gjk_kernel<false, 512>, 512, env->smem_bytes_gjk));
         if (per_sm_512 >= 1) { env->gjk_threads = 512; per_sm = per_sm_512; }
+        // 24 warps under an 80-register cap (8 bytes of spill) hide more of the dependent-issue latency than 16 warps at
+        // 107 registers: space_bm GJK 221 -> 211 us, Human 170 -> 166 us; 32 warps at 64 registers spill and lose
+        int per_sm_768 = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_768, gjk_kernel<false, 768>, 768, env->smem_bytes_gjk));
+        if (per_sm_768 >= 1 && !getenv("SMENV_GJK_512")) { env->gjk_threads = 768; per_sm = per_sm_768; }
+    }
+    if (const char* e = getenv("SMENV_GJK_THREADS")) {   // experiments: 24 / 32 warps under an 85 / 64-register cap
+        const int t = atoi(e);
+        int fit = 0;
+        if (t == 768) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, gjk_kernel<false, 768>, 768, env->smem_bytes_gjk));
+        if (t == 1024) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, gjk_kernel<false, 1024>, 1024, env->smem_bytes_gjk));
+        if (fit >= 1) { env->gjk_threads = t; per_sm = fit; }
     }
     env->grid_gjk = sms * per_sm;
+    if (sc->human.enabled) {
+        static size_t g_smem_hplan[SM_MAX_DEVICES] = {};   // under the create lock; only ever raised, like the limits above
+        size_t& lim = g_smem_hplan[device % SM_MAX_DEVICES];
+        if (env->smem_bytes_hplan > lim) {
+            CU(cudaFuncSetAttribute(human_brake_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_hplan));
+            lim = env->smem_bytes_hplan;
+        }
+        int per = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, human_brake_plan_kernel, HBP_THREADS, env->smem_bytes_hplan));
+        if (per < 1) { return fail(SM_ERR_CUDA, "the human's braking-check planning kernel does not fit on an SM"); }
+        env->grid_hplan = sms * per;
+    }
     // big batches step as two env ranges side by side: the latency-bound tails of one range's kernels (the longest
     // position-bound solve, the last GJK pairs) hide behind the other's (Space, 65 536 envs: 799 -> 748 us per step)
     if (const char* e = getenv("SMENV_STEP_RANGES")) env->step_ranges = atoi(e) < 1 ? 1 : (atoi(e) > 8 ? 8 : atoi(e));
@@ -1175,7 +1311,7 @@ static int mlp_exact_launch(SmEnv* env, int which, MlpSeg s0, MlpSeg s1, MlpSeg 
     int blocks = (max_rows + MLP_EXACT_ROWS - 1) / MLP_EXACT_ROWS;
     if (blocks > 4 * env->sms) blocks = 4 * env->sms;   // grid-stride over the list; blocks beyond its length exit at once
     if (blocks < 1) blocks = 1;
-    mlp_exact_kernel<<<blocks, 256, 0, stream>>>(X);
+    mlp_exact_kernel<<<blocks, 256, MLP_EXACT_SMEM, stream>>>(X);
     env->launches++;
     CU(cudaGetLastError());
     return SM_OK;
@@ -1218,7 +1354,13 @@ static int gate_launch(SmEnv* env, const SmBuffers& bv, int e0, int m, int chunk
 }
 
 static void launch_gjk(SmEnv* env, const GjkArgs& G, cudaStream_t stream) {
-    if (env->gjk_threads == 512) {
+    if (env->gjk_threads == 1024) {
+        if (env->count) gjk_kernel<true, 1024><<<env->grid_gjk, 1024, env->smem_bytes_gjk, stream>>>(G);
+        else gjk_kernel<false, 1024><<<env->grid_gjk, 1024, env->smem_bytes_gjk, stream>>>(G);
+    } else if (env->gjk_threads == 768) {
+        if (env->count) gjk_kernel<true, 768><<<env->grid_gjk, 768, env->smem_bytes_gjk, stream>>>(G);
+        else gjk_kernel<false, 768><<<env->grid_gjk, 768, env->smem_bytes_gjk, stream>>>(G);
+    } else if (env->gjk_threads == 512) {
         if (env->count) gjk_kernel<true, 512><<<env->grid_gjk, 512, env->smem_bytes_gjk, stream>>>(G);
         else gjk_kernel<false, 512><<<env->grid_gjk, 512, env->smem_bytes_gjk, stream>>>(G);
     } else {
@@ -1342,7 +1484,7 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
         env->launches += 5;
         SM_MARK(SM_K_HUMAN_BRAKE_PLAN);
         if (env->host_scene.hu.check_braking) {
-            human_brake_plan_kernel<<<8 * env->sms, 256, sizeof(SceneSmem), stream>>>(HA);
+            human_brake_plan_kernel<<<env->grid_hplan, HBP_THREADS, env->smem_bytes_hplan, stream>>>(HA);
             SM_MARK(SM_K_HUMAN_BRAKE_GJK);
             GjkArgs GB;
             GB.items = items; GB.n_items = worklist; GB.capacity = capacity; GB.res = res; GB.counters = env->d_counters;
@@ -1781,6 +1923,7 @@ extern "C" int smenv_mlp_load(SmEnv* env, int which, int n_tc, const int32_t* di
         CU(cudaMemset(env->d_gate_list, 0, ((size_t)env->n * 2 + 32) * sizeof(int)));
     }
     CU(cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_SM_BYTES));
+    CU(cudaFuncSetAttribute(mlp_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_EXACT_SMEM));
     return SM_OK;
 }
 

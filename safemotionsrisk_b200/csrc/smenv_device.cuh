@@ -98,6 +98,14 @@ struct DevHuman {
     int gp_fa[8], gp_fb[8], gp_off[8], gp_cnt[8];
     float gp_ca[8][3], gp_ra[8], gp_cb[8][3], gp_rb[8];
     float gp_bmin[8][3], gp_bmax[8][3];   // B in frame 0: axis-aligned box of its core vertices (+ margin)
+    // capsules (segment + radius, frame coordinates, margins included) around the two sides: the arm groups are long and
+    // thin, a capsule is several times tighter than their bounding sphere
+    float gp_sa[8][6], gp_sra[8], gp_sb[8][6], gp_srb[8];
+    // the pairs of a link-group pair are the cross product of two contiguous shape ranges (checked by smenv_create)
+    int gp_a0[8], gp_na[8], gp_b0[8], gp_nb[8];
+    // arm frames 3, 4, 7, 8 (index 0..3): their contiguous shape range and a capsule around all of it (frame coordinates)
+    int hf_s0[4], hf_sn[4];
+    float hf_seg[4][6], hf_rad[4];
     double start_box_min[3], start_box_max[3], kinematic_sampling_probability, stay_in_state_probability,
         min_start_static, min_start_self, tp_min_static, tp_min_self;
 };
@@ -159,6 +167,7 @@ struct DevScene {
     // moving obstacle; entry = shape A | shape B << 12 | class << 24
     int n_pairs_fixed, n_pairs;
     uint32_t pair_tab[SM_MAX_PLAN_PAIRS];
+    float2 pair_rm[SM_MAX_PLAN_PAIRS];   // host copies for the SceneImage (layout: smenv_geom.cuh)
     // support-width tables: per shape and cube-map cell an upper bound of h(d) = max_v (v - centre) . d over the unit
     // directions d of the cell.  centre distance - h_A(d) - h_B(-d) along the line of centres is a lower bound of the
     // pair distance that is far tighter than bounding spheres for elongated hulls (planning kernels).

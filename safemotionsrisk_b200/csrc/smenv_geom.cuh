@@ -81,7 +81,9 @@ struct SceneSmem {
 // smenv_create): 16-byte vector copies instead of divergent (serialised) constant-memory reads.
 struct SceneImage {
     SceneSmem scene;
-    uint32_t pair_tab[SM_MAX_PLAN_PAIRS];
+    uint32_t pair_tab[SM_MAX_PLAN_PAIRS];   // shape A | shape B << 12 | class << 24 | (B is a static box in the world frame) << 31
+    float2 pair_rm[SM_MAX_PLAN_PAIRS];      // x: sum of the margins (rounded down), y: what the sphere bound subtracts
+                                            // (radii + margins; static box: radius of A + margins), rounded up
 };
 static_assert(sizeof(SceneImage) % 16 == 0, "SceneImage is copied in 16-byte vectors");
 
@@ -138,6 +140,9 @@ __device__ __forceinline__ unsigned fkey(float f) {
 __device__ __forceinline__ int warp_support(const float4* __restrict__ v, int n, V3 d, int lane) {
     float best = -FLT_MAX;
     int bi = 0;
+    // hulls have at most 255 vertices: eight independent loads per lane, issued together (the vertices of the planning
+    // kernels come from global memory / L2: one latency instead of eight)
+#pragma unroll 8
     for (int i = lane; i < n; i += 32) {
         float4 p = v[i];
         float s = fmaf(p.x, d.x, fmaf(p.y, d.y, p.z * d.z));

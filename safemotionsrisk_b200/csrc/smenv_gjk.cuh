@@ -110,6 +110,9 @@ __device__ __forceinline__ int support_thread(const float4* __restrict__ v, int 
 #ifndef GJK_REFILL_MIN
 #define GJK_REFILL_MIN 8 /* idle lanes of a warp before it fetches new items */
 #endif
+#ifndef GJK_CTA_CURSOR
+#define GJK_CTA_CURSOR 1 /* warps draw items from their CTA's chunk (0: a fixed chunk per warp) */
+#endif
 #ifndef GJK_MIN_BLOCKS
 #define GJK_MIN_BLOCKS 2 /* resident CTAs per SM the register allocation aims for */
 #endif
@@ -118,18 +121,28 @@ __device__ __forceinline__ int support_thread(const float4* __restrict__ v, int 
 #endif
 
 // THREADS: 256 with two CTAs per SM when the scene's shared-memory image (vertices + direction tables + shapes) allows
-// it, else 512 with one CTA per SM (Human scene: 4000 vertices) -- sixteen warps per SM either way
+// it (sixteen warps per SM at up to 128 registers), else one CTA per SM of 768 threads (24 warps, 80 registers; Human
+// scene: 4000 vertices; 512 and 1024 threads are kept for the sweep of tools/gjk_config_sweep.py)
 template <bool COUNT, int THREADS = GJK_THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS <= 256 ? GJK_MIN_BLOCKS : 1) gjk_kernel(GjkArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int n_items = *A.n_items;
     if (n_items > A.capacity) n_items = A.capacity;
-    // static partition of the list: every warp of the grid owns one contiguous chunk (no global cursor to contend on;
-    // the items of an env stay together, so that lanes of a warp hold pairs that can prune each other)
+    // static partition of the list over the CTAs; inside a CTA the warps draw from the CTA's chunk through a cursor in
+    // shared memory (no global cursor to contend on; the items of an env stay together, so that lanes of a warp hold
+    // pairs that can prune each other; the warps of a CTA finish together instead of each draining its own tail)
     const int tid = threadIdx.x, lane = tid & 31;
+#if GJK_CTA_CURSOR
+    const int chunk = (n_items + (int)gridDim.x - 1) / (int)gridDim.x;
+    if ((long long)blockIdx.x * chunk >= n_items) return;  // nothing for this block: no staging
+    __shared__ int cta_cursor;
+    if (tid == 0) cta_cursor = blockIdx.x * chunk;
+    const int end = (blockIdx.x + 1) * chunk < n_items ? (blockIdx.x + 1) * chunk : n_items;
+#else
     const int n_warps = gridDim.x * (blockDim.x >> 5);
     const int chunk = (n_items + n_warps - 1) / n_warps;
     if ((long long)blockIdx.x * (blockDim.x >> 5) * chunk >= n_items) return;  // nothing for this block: no staging
+#endif
     GjkSmem G = gjk_carve(smem_raw);
     // hulls, direction tables and shapes -> shared memory: three bulk TMA copies issued by one thread
     __shared__ __align__(8) uint64_t stage_bar;
@@ -145,8 +158,12 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 256 ? GJK_MIN_BLOCKS : 1) 
     }
     __syncthreads();                 // the barrier init is visible to everyone
     mbar_wait(&stage_bar, 0);
+#if GJK_CTA_CURSOR
+    bool more = true;   // warp-uniform: the CTA's chunk still held items at the warp's last draw
+#else
     int cursor = (blockIdx.x * (blockDim.x >> 5) + (tid >> 5)) * chunk;
     const int end = cursor + chunk < n_items ? cursor + chunk : n_items;
+#endif
     unsigned c_iters = 0, c_dots = 0, c_calls = 0;
 
     // ---------------- per-lane state of the pair in flight
@@ -166,9 +183,21 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 256 ? GJK_MIN_BLOCKS : 1) 
     while (true) {
         // ---------------- refill: idle lanes take the next items of the warp's chunk
         const unsigned idle = __ballot_sync(FULL, !busy);
+#if GJK_CTA_CURSOR
+        int my = end;
+        if (more && (idle == FULL || __popc(idle) >= GJK_REFILL_MIN)) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&cta_cursor, __popc(idle));
+            base = __shfl_sync(FULL, base, 0);
+            more = base + __popc(idle) < end;
+            my = base + __popc(idle & ((1u << lane) - 1u));
+        }
+        {
+#else
         if (cursor < end && (idle == FULL || __popc(idle) >= GJK_REFILL_MIN)) {
             const int my = cursor + __popc(idle & ((1u << lane) - 1u));
             cursor += __popc(idle);
+#endif
             if (!busy && my < end) {
                 const float4* ip = reinterpret_cast<const float4*>(A.items + my);
                 const float4 h0 = __ldg(ip), h1 = __ldg(ip + 1), h2 = __ldg(ip + 2), h3 = __ldg(ip + 3);

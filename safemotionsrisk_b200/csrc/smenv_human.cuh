@@ -183,31 +183,98 @@ __global__ void __launch_bounds__(128) human_brake_traj_kernel(HumanArgs A) {
 
 // ------------------------------------------------------------------------------------------------------------------
 // geometry of the braking-trajectory check: ONE THREAD PER POSE (the joint-space kernel lists them).  Serial forward
-// kinematics of the two arms, then the link-group pairs of get_minimum_distance (ctlp.py:3282-3374: table x forearm /
-// hand, forearm / hand x other arm, forearm / hand x body / head) with bounding spheres; inside a surviving group pair
-// every convex pair goes through the sphere and separating-axis bounds of the distance planning.  A pair that may be
-// closer than the safety distance becomes a GJK_BRAKE item carrying the pose number.
+// kinematics of the two arms; as soon as a frame is known, the bounding-sphere centres of its shapes and the end points
+// of its bounding capsule go to the thread's column of a shared-memory table -- every later test reads points by
+// (uniform) index from there, no transform is applied twice.  Then the link-group pairs of get_minimum_distance
+// (ctlp.py:3282-3374: table x forearm / hand, forearm / hand x other arm, forearm / hand x body / head): a capsule test
+// per group pair, and inside a surviving group pair the sphere bound of every convex pair (the pairs of a group pair
+// are the cross product of two shape ranges, smenv_create checks it) and the separating-axis bound of the distance
+// planning for what is left.  A pair that may be closer than the safety distance becomes a GJK_BRAKE item carrying
+// the pose number.  The trunk does not move: its shapes' world centres are computed once per CTA.
 // ------------------------------------------------------------------------------------------------------------------
-struct HumanBlockShared {   // kept for the size bookkeeping of smenv_create
-    SceneSmem scene;
-};
+// squared distance between the segments [p1, q1] and [p2, q2] (Ericson, Real-Time Collision Detection, 5.1.9)
+__device__ __forceinline__ float segment_dist2(V3 p1, V3 q1, V3 p2, V3 q2) {
+    const V3 d1 = q1 - p1, d2 = q2 - p2, r = p1 - p2;
+    const float a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r);
+    float s, t;
+    if (a <= 1e-12f && e <= 1e-12f) return dot(r, r);
+    if (a <= 1e-12f) { s = 0.f; t = fminf(fmaxf(f / e, 0.f), 1.f); }
+    else {
+        const float c = dot(d1, r);
+        if (e <= 1e-12f) { t = 0.f; s = fminf(fmaxf(-c / a, 0.f), 1.f); }
+        else {
+            const float b = dot(d1, d2), den = a * e - b * b;
+            s = den > 1e-12f ? fminf(fmaxf((b * f - c * e) / den, 0.f), 1.f) : 0.f;
+            t = (b * s + f) / e;
+            if (t < 0.f) { t = 0.f; s = fminf(fmaxf(-c / a, 0.f), 1.f); }
+            else if (t > 1.f) { t = 1.f; s = fminf(fmaxf((b - c) / a, 0.f), 1.f); }
+        }
+    }
+    const V3 c1 = p1 + s * d1, c2 = p2 + t * d2, dd = c1 - c2;
+    return dot(dd, dd);
+}
 
-__global__ void __launch_bounds__(256) human_brake_plan_kernel(HumanArgs A) {
+#define HBP_THREADS 128
+#define HBP_MAX_TRUNK 32
+// dynamic shared memory: point table [n_arm_shapes + 8][3][HBP_THREADS] | trunk spheres [HBP_MAX_TRUNK] float4 |
+// world capsules of the trunk sides of the group pairs [8][8] | radius + margin of the arm shapes [32]
+static size_t human_plan_smem_bytes(int n_arm_shapes) {
+    return (size_t)(n_arm_shapes + 8) * 3 * HBP_THREADS * sizeof(float) + HBP_MAX_TRUNK * sizeof(float4) + (64 + 32) * sizeof(float);
+}
+__device__ __forceinline__ int hbp_frame_index(int f) { return f == 3 ? 0 : f == 4 ? 1 : f == 7 ? 2 : 3; }
+__device__ __forceinline__ void hbp_pick(int f, const Xf& F3, const Xf& F4, const Xf& F7, const Xf& F8, const Xf& B,
+                                         const Xf& world, Xf& out) {
+    out = f < 0 ? world : f == 0 ? B : f == 3 ? F3 : f == 4 ? F4 : f == 7 ? F7 : F8;
+}
+
+__global__ void __launch_bounds__(HBP_THREADS) human_brake_plan_kernel(HumanArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n_units = A.units[0];
-    if (blockIdx.x * blockDim.x >= n_units) return;
-    SceneSmem* smp = reinterpret_cast<SceneSmem*>(smem_raw);
-    for (int i = threadIdx.x; i < (int)(sizeof(SceneSmem) / 16); i += blockDim.x)
-        reinterpret_cast<uint4*>(smp)[i] = __ldg(c_sc.scene_img + i);
-    __syncthreads();
-    const SceneSmem& sm = *smp;
+    if (blockIdx.x * HBP_THREADS >= n_units) return;
+    const int tid = threadIdx.x;
+    const int nas = c_sc.hu.n_arm_shapes, soff = c_sc.hu.shape_off;
+    float* P = reinterpret_cast<float*>(smem_raw) + tid;                    // this thread's column: P[(slot * 3 + k) * HBP_THREADS]
+    float4* TC = reinterpret_cast<float4*>(smem_raw + (size_t)(nas + 8) * 3 * HBP_THREADS * sizeof(float));
+    float* GC = reinterpret_cast<float*>(TC + HBP_MAX_TRUNK);
+    float* RM = GC + 64;
     const float safety = (float)c_sc.hu.brake_safety;
     Xf world, B;
     xf_identity(world);
     human_base(B);
+    const int n_trunk = c_sc.hu.n_shapes - nas;
+    if (tid < n_trunk) {
+        const DevShape& sh = c_sc.shapes[soff + nas + tid];
+        const V3 c = xf_apply(B, sh.cx, sh.cy, sh.cz);
+        TC[tid] = make_float4(c.x, c.y, c.z, sh.radius + sh.margin);
+    }
+    if (tid < nas && tid < 32) RM[tid] = c_sc.shapes[soff + tid].radius + c_sc.shapes[soff + tid].margin;
+    if (tid < c_sc.hu.n_gp && c_sc.hu.gp_fb[tid] == 0) {
+        const float* sb = c_sc.hu.gp_sb[tid];
+        const V3 b0 = xf_apply(B, sb[0], sb[1], sb[2]), b1 = xf_apply(B, sb[3], sb[4], sb[5]);
+        GC[8 * tid] = b0.x; GC[8 * tid + 1] = b0.y; GC[8 * tid + 2] = b0.z;
+        GC[8 * tid + 3] = b1.x; GC[8 * tid + 4] = b1.y; GC[8 * tid + 5] = b1.z;
+    }
+    __syncthreads();
+    auto put = [&](int slot, V3 v) {
+        P[(slot * 3 + 0) * HBP_THREADS] = v.x; P[(slot * 3 + 1) * HBP_THREADS] = v.y; P[(slot * 3 + 2) * HBP_THREADS] = v.z;
+    };
+    auto get = [&](int slot) {
+        return mk(P[(slot * 3 + 0) * HBP_THREADS], P[(slot * 3 + 1) * HBP_THREADS], P[(slot * 3 + 2) * HBP_THREADS]);
+    };
+    auto frame_points = [&](const Xf& F, int fi) {   // shapes and capsule of arm frame fi (uniform loop bounds)
+        const int s0 = c_sc.hu.hf_s0[fi], s1 = s0 + c_sc.hu.hf_sn[fi];
 #pragma unroll 1
-    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += gridDim.x * blockDim.x) {
-        const int unit = A.units[1 + u];
+        for (int sI = s0; sI < s1; ++sI) put(sI - soff, xf_apply(F, c_sc.shapes[sI].cx, c_sc.shapes[sI].cy, c_sc.shapes[sI].cz));
+        const float* sg = c_sc.hu.hf_seg[fi];
+        put(nas + 2 * fi, xf_apply(F, sg[0], sg[1], sg[2]));
+        put(nas + 2 * fi + 1, xf_apply(F, sg[3], sg[4], sg[5]));
+    };
+#pragma unroll 1
+    for (int u0 = blockIdx.x * HBP_THREADS; u0 < n_units; u0 += gridDim.x * HBP_THREADS) {
+        __syncwarp();   // lanes leave the pair loops of the previous pose at different times
+        const int u = u0 + tid;
+        const bool valid = u < n_units;   // the loops below are uniform over the warp: idle lanes run them on the last pose
+        const int unit = A.units[1 + (valid ? u : n_units - 1)];
         const int env = unit >> 7, p = unit & 127;
         const float4* row = reinterpret_cast<const float4*>(A.poses + ((size_t)env * SM_HBRAKE_POSES + p) * 8);
         const float4 r0 = row[0], r1 = row[1];
@@ -217,52 +284,93 @@ __global__ void __launch_bounds__(256) human_brake_plan_kernel(HumanArgs A) {
             Xf F = B;
             human_chain_step(F, 0, r0.x); human_chain_step(F, 1, r0.y); human_chain_step(F, 2, r0.z);
             F3 = F;
+            frame_points(F3, 0);
             human_chain_step(F, 3, r0.w);
             F4 = F;
+            frame_points(F4, 1);
             F = B;
             human_chain_step(F, 4, r1.x); human_chain_step(F, 5, r1.y); human_chain_step(F, 6, r1.z);
             F7 = F;
+            frame_points(F7, 2);
             human_chain_step(F, 7, r1.w);
             F8 = F;
+            frame_points(F8, 3);
         }
 #pragma unroll 1
         for (int g = 0; g < c_sc.hu.n_gp; ++g) {
+            __syncwarp();
             const int fa = c_sc.hu.gp_fa[g], fb = c_sc.hu.gp_fb[g];
-            const Xf& TA = fa == 3 ? F3 : fa == 4 ? F4 : fa == 7 ? F7 : F8;
-            const Xf& TB = fb < 0 ? world : fb == 0 ? B : fb == 3 ? F3 : fb == 4 ? F4 : fb == 7 ? F7 : F8;
-            const V3 ga = xf_apply(TA, c_sc.hu.gp_ca[g][0], c_sc.hu.gp_ca[g][1], c_sc.hu.gp_ca[g][2]);
+            const int fia = hbp_frame_index(fa);
+            const V3 a0 = get(nas + 2 * fia), a1 = get(nas + 2 * fia + 1);
+            const float ra = c_sc.hu.hf_rad[fia];
             bool near_g;
-            if (fb < 0) {
-                const float l = c_sc.hu.gp_ra[g] + safety;
-                near_g = box_dist2(ga, c_sc.hu.gp_bmin[g], c_sc.hu.gp_bmax[g]) <= l * l;
-            } else {
-                const V3 d = xf_apply(TB, c_sc.hu.gp_cb[g][0], c_sc.hu.gp_cb[g][1], c_sc.hu.gp_cb[g][2]) - ga;
-                const float l = c_sc.hu.gp_ra[g] + c_sc.hu.gp_rb[g] + safety;
-                near_g = dot(d, d) <= l * l;
-            }
-            if (!near_g) continue;
-            int last_a = -1;
-            V3 ca = mk(0.f, 0.f, 0.f);
-#pragma unroll 1
-            for (int i = c_sc.hu.gp_off[g]; i < c_sc.hu.gp_off[g] + c_sc.hu.gp_cnt[g]; ++i) {
-                const int ia = __ldg(c_sc.hu.brake_pairs + 2 * i), ib = __ldg(c_sc.hu.brake_pairs + 2 * i + 1);
-                const DevShape& SA = sm.shapes[ia];
-                const DevShape& SB = sm.shapes[ib];
-                if (ia != last_a) { ca = xf_apply(TA, SA.cx, SA.cy, SA.cz); last_a = ia; }
-                bool emit;
-                V3 d;
-                if (fb < 0) {   // the table: sphere against its axis-aligned box
-                    d = mk(SB.cx - ca.x, SB.cy - ca.y, SB.cz - ca.z);
-                    emit = sqrtf(box_dist2(ca, SB.bmin, SB.bmax)) - SA.radius - SA.margin - SB.margin <= safety;
+            if (fb < 0) {    // the table's box against two spheres that cover the capsule of side A
+                const V3 dl = a1 - a0;
+                const float quarter = 0.25f * sqrtf(dot(dl, dl));
+                const float l = sqrtf(ra * ra + quarter * quarter) * (1.0f + 1e-5f) + safety + 1e-5f;
+                near_g = box_dist2(a0 + 0.25f * dl, c_sc.hu.gp_bmin[g], c_sc.hu.gp_bmax[g]) <= l * l ||
+                         box_dist2(a0 + 0.75f * dl, c_sc.hu.gp_bmin[g], c_sc.hu.gp_bmax[g]) <= l * l;
+            } else {         // capsules of both sides: the arm groups are long and thin
+                V3 b0, b1;
+                float rb;
+                if (fb == 0) {
+                    b0 = mk(GC[8 * g], GC[8 * g + 1], GC[8 * g + 2]); b1 = mk(GC[8 * g + 3], GC[8 * g + 4], GC[8 * g + 5]);
+                    rb = c_sc.hu.gp_srb[g];
                 } else {
-                    d = xf_apply(TB, SB.cx, SB.cy, SB.cz) - ca;
-                    emit = sqrtf(dot(d, d)) - SA.radius - SB.radius - SA.margin - SB.margin <= safety;
+                    const int fib = hbp_frame_index(fb);
+                    b0 = get(nas + 2 * fib); b1 = get(nas + 2 * fib + 1);
+                    rb = c_sc.hu.hf_rad[fib];
                 }
-                if (emit) emit = axis_lower_bound_d(SA, SB, TA, TB, d) <= safety;
-                if (emit) {
-                    const int idx = atomicAdd(A.item_count, 1);
-                    if (idx < A.capacity) write_item(A.items + idx, env, ia, ib, GJK_BRAKE, p + 1, safety, TA, TB);
-                    else atomicAdd(A.overflow, 1);
+                const float l = ra + rb + safety * (1.0f + 1e-5f) + 1e-5f;
+                near_g = segment_dist2(a0, a1, b0, b1) <= l * l;
+            }
+            if (!(near_g && valid)) continue;
+            const int sa0 = c_sc.hu.gp_a0[g], sa1 = sa0 + c_sc.hu.gp_na[g];
+            const int sb0 = c_sc.hu.gp_b0[g], nb = c_sc.hu.gp_nb[g];
+#pragma unroll 1
+            for (int ia = sa0; ia < sa1; ++ia) {
+                const V3 ca = get(ia - soff);
+                const float la = RM[ia - soff] + safety;
+                // sphere bound of the nb pairs (ia, sb0 + k): bit k of `hits` = the pair goes on to the axis bound
+                unsigned hits = 0u;
+                if (fb < 0) {              // the table: sphere against its axis-aligned box
+#pragma unroll 1
+                    for (int k = 0; k < nb; ++k) {
+                        const DevShape& SB = c_sc.shapes[sb0 + k];
+                        const float l = la + SB.margin;
+                        hits |= (box_dist2(ca, SB.bmin, SB.bmax) <= l * l * (1.0f + 1e-5f) ? 1u : 0u) << k;
+                    }
+                } else if (fb == 0) {      // the trunk: constant spheres
+                    const float4* tc = TC + (sb0 - soff - nas);
+#pragma unroll 4
+                    for (int k = 0; k < nb; ++k) {
+                        const float4 t = tc[k];
+                        const float dx = t.x - ca.x, dy = t.y - ca.y, dz = t.z - ca.z, l = la + t.w;
+                        hits |= (fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= l * l * (1.0f + 1e-5f) ? 1u : 0u) << k;
+                    }
+                } else {                   // the other arm
+                    const int slot0 = sb0 - soff;
+#pragma unroll 4
+                    for (int k = 0; k < nb; ++k) {
+                        const V3 d = get(slot0 + k) - ca;
+                        const float l = la + RM[slot0 + k];
+                        hits |= (dot(d, d) <= l * l * (1.0f + 1e-5f) ? 1u : 0u) << k;
+                    }
+                }
+                while (hits) {             // rare: the frames are picked out of the registers only here
+                    const int ib = sb0 + __ffs(hits) - 1;
+                    hits &= hits - 1u;
+                    Xf TA, TB;
+                    hbp_pick(fa, F3, F4, F7, F8, B, world, TA);
+                    hbp_pick(fb, F3, F4, F7, F8, B, world, TB);
+                    const DevShape& SA = c_sc.shapes[ia];
+                    const DevShape& SB = c_sc.shapes[ib];
+                    const V3 d = xf_apply(TB, SB.cx, SB.cy, SB.cz) - ca;
+                    if (axis_lower_bound_d(SA, SB, TA, TB, d) <= safety) {
+                        const int idx = atomicAdd(A.item_count, 1);
+                        if (idx < A.capacity) write_item(A.items + idx, env, ia, ib, GJK_BRAKE, p + 1, safety, TA, TB);
+                        else atomicAdd(A.overflow, 1);
+                    }
                 }
             }
         }

@@ -14,13 +14,14 @@ struct WarpScratch {
     Xf fr2[1 + SM_MAX_JOINTS];              // robot frames of one sub-step (narrow phase)
     Xf obx[SM_MAX_OBST_FRAMES];             // obstacle frames at the end of the step (human: base + 8 joint frames)
     Xf obx2[SM_MAX_OBST_FRAMES];            // obstacle frames of one sub-step
-    float pc[SM_MAX_SHAPES][3];             // world position of every shape's bounding-sphere centre (distance planning)
-    float pg[SM_MAX_SHAPES][3];             // world position of every shape's centroid
+    float4 pc[SM_MAX_SHAPES];               // world position of every shape's bounding-sphere centre (distance planning)
+    float4 pg[SM_MAX_SHAPES];               // world position of every shape's centroid
 };
 
 struct BlockShared {
-    SceneSmem scene;                        // \ the first two members mirror SceneImage
-    uint32_t pair_tab[SM_MAX_PLAN_PAIRS];   // /
+    SceneSmem scene;                        // \ the first three members mirror SceneImage
+    uint32_t pair_tab[SM_MAX_PLAN_PAIRS];   // |
+    float2 pair_rm[SM_MAX_PLAN_PAIRS];      // /
     double stats[16];
     unsigned long long counters[16];
 };

@@ -389,10 +389,11 @@ __global__ void random_actions_kernel(float* actions, int nj, int n, int env_bas
 // Exact (float32, CUDA cores) evaluation of a network on a LIST of rows: the tensor-core pass rates every env with fp16
 // operands; rows whose risk lies within a band around the threshold are re-rated here so that the gate decision equals the
 // float32 decision of the reference's TensorFlow model (safe_motions_base.py:1597-1603), and the backup policy's action
-// of the risky envs is computed here in float32 as well (actions.py:328-333).  One CTA = eight rows; a thread owns output
-// columns, the weights stream through L2 once per eight rows.
+// of the risky envs is computed here in float32 as well (actions.py:328-333).  One CTA = sixteen rows; a thread owns output
+// columns, the weights stream through L2 once per sixteen rows.
 // ------------------------------------------------------------------------------------------------------------------
-#define MLP_EXACT_ROWS 8
+#define MLP_EXACT_ROWS 16
+#define MLP_EXACT_SMEM (2 * MLP_EXACT_ROWS * MLP_MAX_WIDTH * 4)
 struct MlpExactArgs {
     MlpNet net;
     const int* rows;      // [*n_rows] row indices, or NULL: rows 0 .. *n_rows - 1
@@ -410,7 +411,9 @@ __device__ __forceinline__ float mlp_hidden_act_exact(float x, int act) {
 }
 
 __global__ void __launch_bounds__(256) mlp_exact_kernel(MlpExactArgs A) {
-    __shared__ float xa[MLP_EXACT_ROWS][MLP_MAX_WIDTH], xb[MLP_EXACT_ROWS][MLP_MAX_WIDTH];
+    extern __shared__ __align__(16) unsigned char exact_smem[];
+    float (*xa)[MLP_MAX_WIDTH] = reinterpret_cast<float (*)[MLP_MAX_WIDTH]>(exact_smem);
+    float (*xb)[MLP_MAX_WIDTH] = xa + MLP_EXACT_ROWS;
     __shared__ int row_id[MLP_EXACT_ROWS];
     const int n_rows = A.n_rows ? *A.n_rows : A.n_rows_host;
     const MlpNet& net = A.net;
@@ -457,8 +460,9 @@ __global__ void __launch_bounds__(256) mlp_exact_kernel(MlpExactArgs A) {
             float (*t)[MLP_MAX_WIDTH] = src; src = dst; dst = t;
             K = N;
         }
-        if (tid < MLP_EXACT_ROWS * A.n_write) {
-            const int r = tid / A.n_write, o = tid - r * A.n_write, row = row_id[r];
+        for (int idx = tid; idx < MLP_EXACT_ROWS * A.n_write; idx += blockDim.x) {
+            const int tid2 = idx;
+            const int r = tid2 / A.n_write, o = tid2 - r * A.n_write, row = row_id[r];
             if (row >= 0) {
                 float acc = __ldg(net.b_out + o);
                 for (int k = 0; k < K; ++k) acc = fmaf(src[r][k], __ldg(net.w_out + (size_t)k * net.out_pad + o), acc);

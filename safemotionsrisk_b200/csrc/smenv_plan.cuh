@@ -321,8 +321,11 @@ __device__ __forceinline__ int contact_scan(const SceneSmem& sm, const float* __
 
 // Fine contact planning over the spans the coarse phase listed: one lane per sub-step of a span, 32 / span spans per
 // warp (ten at 24 sub-steps).
+#ifndef SM_CONTACT_MIN_BLOCKS
+#define SM_CONTACT_MIN_BLOCKS 1   /* resident CTAs per SM the register allocation aims for (experiments: -DSM_CONTACT_MIN_BLOCKS=3) */
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) contact_plan_kernel(PlanArgs A) {
+__global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32, SM_CONTACT_MIN_BLOCKS) contact_plan_kernel(PlanArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n_units = A.cwork[0];
     const int span = (c_sc.substeps + SM_COARSE_LANES - 1) / SM_COARSE_LANES;
@@ -394,6 +397,7 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) distance_plan_kernel(
     const float cap = (float)c_sc.static_cap, query = (float)c_sc.moving_query;
     const int n_fixed = c_sc.n_pairs_fixed, n_pairs = c_sc.n_pairs;
     const uint32_t* pair_tab = L.bs->pair_tab;
+    const float2* pair_rm = L.bs->pair_rm;
     unsigned n_emit = 0;
 #pragma unroll 1
     for (int env = blockIdx.x * SM_WARPS_PER_BLOCK + warp; env < A.n; env += gridDim.x * SM_WARPS_PER_BLOCK) {
@@ -475,8 +479,8 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) distance_plan_kernel(
             const DevShape& sh = sm.shapes[sI];
             const Xf& T = *frame_ptr(sh, W.fr, W.obx);
             const V3 c = xf_apply(T, sh.cx, sh.cy, sh.cz), g = xf_apply(T, sh.gx, sh.gy, sh.gz);
-            W.pc[sI][0] = c.x; W.pc[sI][1] = c.y; W.pc[sI][2] = c.z;
-            W.pg[sI][0] = g.x; W.pg[sI][1] = g.y; W.pg[sI][2] = g.z;
+            W.pc[sI] = make_float4(c.x, c.y, c.z, 0.f);
+            W.pg[sI] = make_float4(g.x, g.y, g.z, 0.f);
         }
         __syncwarp();
         // ---------------- pass 1 (lanes = pairs): the best upper bound of each class (distance of the hull centroids)
@@ -486,11 +490,10 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) distance_plan_kernel(
 #pragma unroll 1
         for (int p = lane; p < np; p += 32) {
             const uint32_t e = pair_tab[p];
-            const int ia = (int)(e & 0xfffu), ib = (int)((e >> 12) & 0xfffu), cls = (int)(e >> 24);
-            const DevShape& SA = sm.shapes[ia];
-            const DevShape& SB = sm.shapes[ib];
-            const V3 g = mk(W.pg[ia][0] - W.pg[ib][0], W.pg[ia][1] - W.pg[ib][1], W.pg[ia][2] - W.pg[ib][2]);
-            const float ub = sqrtf(dot(g, g)) * (1.0f + 1e-6f) + 1e-7f - SA.margin - SB.margin;
+            const int ia = (int)(e & 0xfffu), ib = (int)((e >> 12) & 0xfffu), cls = (int)((e >> 24) & 3u);
+            const float4 ga = W.pg[ia], gb = W.pg[ib];
+            const V3 g = mk(ga.x - gb.x, ga.y - gb.y, ga.z - gb.z);
+            const float ub = sqrtf(dot(g, g)) * (1.0f + 1e-6f) + 1e-7f - pair_rm[p].x;
             if (cls == GJK_STATIC) ub_s = fminf(ub_s, ub);
             else if (cls == GJK_SELF) ub_e = fminf(ub_e, ub);
             else if (ub < ub_m) { ub_m = ub; best_m = (unsigned)ia | ((unsigned)ib << 16); }
@@ -517,31 +520,23 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) distance_plan_kernel(
                 ub_m = fminf(ub_m, sqrtf(dot(e, e)) * (1.0f + 1e-6f) + 1e-7f - SA.margin - SB.margin);
             }
         }
-        // ---------------- pass 2: one item per pair whose sphere lower bound is below its class' upper bound
-#pragma unroll 1
-        for (int base = 0; base < np; base += 32) {
-            const int p = base + lane;
+        // ---------------- pass 2: one item per pair whose lower bounds are below its class' upper bound.  The sphere
+        // bound runs over all pairs (lanes = pairs); its survivors (a few per 32 pairs) are queued and the support-width
+        // bound and the item write run on full batches of 32 survivors instead of on the few lanes of every batch
+        unsigned short* Q = reinterpret_cast<unsigned short*>(W.fr2);   // [64]; fr2 is not used by this kernel
+        int qn = 0;
+        auto drain = [&](int cnt) {   // the first cnt (<= 32) queued pairs
             bool emit = false;
             float thr = 0.0f;
             int ia = 0, ib = 0, cls = 0;
-            if (p < np) {
-                const uint32_t e = pair_tab[p];
-                ia = (int)(e & 0xfffu); ib = (int)((e >> 12) & 0xfffu); cls = (int)(e >> 24);
+            if (lane < cnt) {
+                const uint32_t e = pair_tab[Q[lane]];
+                ia = (int)(e & 0xfffu); ib = (int)((e >> 12) & 0xfffu); cls = (int)((e >> 24) & 3u);
                 thr = cls == GJK_STATIC ? ub_s : cls == GJK_SELF ? ub_e : ub_m;
                 const DevShape& SA = sm.shapes[ia];
                 const DevShape& SB = sm.shapes[ib];
-                const V3 ca = mk(W.pc[ia][0], W.pc[ia][1], W.pc[ia][2]);
-                if (SB.frame == 0) {  // static shape in the world frame: sphere against its axis-aligned box
-                    const float dx = fmaxf(fmaxf(SB.bmin[0] - ca.x, ca.x - SB.bmax[0]), 0.f);
-                    const float dy = fmaxf(fmaxf(SB.bmin[1] - ca.y, ca.y - SB.bmax[1]), 0.f);
-                    const float dz = fmaxf(fmaxf(SB.bmin[2] - ca.z, ca.z - SB.bmax[2]), 0.f);
-                    emit = sqrtf(dx * dx + dy * dy + dz * dz) - SA.radius - SA.margin - SB.margin <= thr;
-                } else {
-                    const V3 d = mk(W.pc[ib][0] - ca.x, W.pc[ib][1] - ca.y, W.pc[ib][2] - ca.z);
-                    emit = sqrtf(dot(d, d)) - SA.radius - SB.radius - SA.margin - SB.margin <= thr;
-                }
-                if (emit) emit = axis_lower_bound_d(SA, SB, *frame_ptr(SA, W.fr, W.obx), *frame_ptr(SB, W.fr, W.obx),
-                                                    mk(W.pc[ib][0] - ca.x, W.pc[ib][1] - ca.y, W.pc[ib][2] - ca.z)) <= thr;
+                emit = axis_lower_bound_d(SA, SB, *frame_ptr(SA, W.fr, W.obx), *frame_ptr(SB, W.fr, W.obx),
+                                          mk(W.pc[ib].x - W.pc[ia].x, W.pc[ib].y - W.pc[ia].y, W.pc[ib].z - W.pc[ia].z)) <= thr;
             }
             const unsigned em = __ballot_sync(FULL, emit);
             if (em) {
@@ -558,7 +553,44 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) distance_plan_kernel(
                 }
                 if (COUNT) n_emit += (unsigned)total;
             }
+        };
+#pragma unroll 1
+        for (int base = 0; base < np; base += 32) {
+            const int p = base + lane;
+            bool pass = false;
+            if (p < np) {
+                const uint32_t e = pair_tab[p];
+                const int ia = (int)(e & 0xfffu), ib = (int)((e >> 12) & 0xfffu), cls = (int)((e >> 24) & 3u);
+                const float thr = cls == GJK_STATIC ? ub_s : cls == GJK_SELF ? ub_e : ub_m;
+                const float4 ca = W.pc[ia];
+                if (e >> 31) {  // static shape in the world frame: sphere against its axis-aligned box
+                    const DevShape& SB = sm.shapes[ib];
+                    const float dx = fmaxf(fmaxf(SB.bmin[0] - ca.x, ca.x - SB.bmax[0]), 0.f);
+                    const float dy = fmaxf(fmaxf(SB.bmin[1] - ca.y, ca.y - SB.bmax[1]), 0.f);
+                    const float dz = fmaxf(fmaxf(SB.bmin[2] - ca.z, ca.z - SB.bmax[2]), 0.f);
+                    pass = sqrtf(dx * dx + dy * dy + dz * dz) - pair_rm[p].y <= thr;
+                } else {
+                    const float4 cb = W.pc[ib];
+                    const V3 d = mk(cb.x - ca.x, cb.y - ca.y, cb.z - ca.z);
+                    pass = sqrtf(dot(d, d)) - pair_rm[p].y <= thr;
+                }
+            }
+            const unsigned pm = __ballot_sync(FULL, pass);
+            if (pm) {
+                if (pass) Q[qn + __popc(pm & ((1u << lane) - 1u))] = (unsigned short)p;
+                qn += __popc(pm);
+                __syncwarp();
+                if (qn >= 32) {
+                    drain(32);
+                    const unsigned short keep = Q[32 + lane];
+                    __syncwarp();
+                    Q[lane] = keep;
+                    qn -= 32;
+                    __syncwarp();
+                }
+            }
         }
+        if (qn) drain(qn);
         __syncwarp();
     }
     if (COUNT && A.counters && lane == 0 && n_emit) atomicAdd(&A.counters[3], (unsigned long long)n_emit);

@@ -32,9 +32,11 @@ kt, _ = env.kernel_times()
 print(json.dumps(dict(scene=sys.argv[1], us_per_step=1e3 * ms, gjk_us=1e3 * kt["gjk_kernel"], launch=env.launch_config())))
 ''' % ROOT
 
+# SMENV_SWEEP: JSON list of env-var overrides, one process each (default: CTA geometry of the GJK kernel)
+CONFIGS = json.loads(os.environ.get("SMENV_SWEEP", "null")) or [
+    {}, {"SMENV_GJK_THREADS": "768"}, {"SMENV_GJK_THREADS": "1024"}, {"SMENV_GJK_256": "1"}]
 for scene in sys.argv[1:] or ["space_bm"]:
-    for env_over in ({}, {"SMENV_LUT_MIN_VERTS": "33"}, {"SMENV_LUT_MIN_VERTS": "65"}, {"SMENV_LUT_MIN_VERTS": "129"},
-                     {"SMENV_LUT_MIN_VERTS": "33", "SMENV_GJK_256": "1"}):
+    for env_over in CONFIGS:
         out = subprocess.run([sys.executable, "-c", CHILD, scene], env=dict(os.environ, **env_over), capture_output=True, text=True)
         line = out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-300:]
         print(env_over, line, flush=True)
