@@ -186,6 +186,8 @@ struct SmEnv {
     float* d_hscratch = nullptr;   // [n][SM_SCRATCH_FLOATS]
     float* d_hpolicy = nullptr;    // [n][16]
     double* d_hstart_pool = nullptr;   // [start_pool_n][SM_HPOOL_STRIDE]
+    double* d_hpool_brake = nullptr;   // [start_pool_n][SM_HBRAKE_STEPS][8] initial braking trajectory of every start state
+    int* d_hpool_bcount = nullptr;     // [start_pool_n]
     double* d_htarget_pool = nullptr;  // [2][htarget_pool_n][4]
     int htarget_pool_n = 0;
     size_t smem_bytes_hplan = 0;
@@ -534,6 +536,16 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
             u.start_box_min[i] = h.start_box_min[i]; u.start_box_max[i] = h.start_box_max[i];
             for (int r = 0; r < 2; ++r) u.tp_local[r][i] = (float)h.tp_local[r][i];
         }
+        for (int r = 0; r < 2; ++r)   // a change of joint 4 r + i by dq moves the target link point of arm r by at most dq * tp_rho[r][i]
+            for (int i = 0; i < 4; ++i) {
+                float rho = sqrtf(u.tp_local[r][0] * u.tp_local[r][0] + u.tp_local[r][1] * u.tp_local[r][1] +
+                                  u.tp_local[r][2] * u.tp_local[r][2]);
+                for (int m = i + 1; m < 4; ++m) {
+                    const float* t = u.jt[4 * r + m];
+                    rho += sqrtf(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+                }
+                u.tp_rho[r][i] = rho * (1.0f + 1e-5f);
+            }
         u.kinematic_sampling_probability = h.kinematic_sampling_probability;
         u.stay_in_state_probability = h.stay_in_state_probability;
         u.min_start_static = h.min_start_static; u.min_start_self = h.min_start_self;
@@ -814,6 +826,10 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
         env->htarget_pool_n = 2 * env->start_pool_n;
         CU(cudaMalloc((void**)&env->d_hstart_pool, (size_t)env->start_pool_n * SM_HPOOL_STRIDE * sizeof(double)));
         CU(cudaMemset(env->d_hstart_pool, 0, (size_t)env->start_pool_n * SM_HPOOL_STRIDE * sizeof(double)));
+        CU(cudaMalloc((void**)&env->d_hpool_brake, (size_t)env->start_pool_n * SM_HBRAKE_STEPS * 8 * sizeof(double)));
+        CU(cudaMemset(env->d_hpool_brake, 0, (size_t)env->start_pool_n * SM_HBRAKE_STEPS * 8 * sizeof(double)));
+        CU(cudaMalloc((void**)&env->d_hpool_bcount, (size_t)env->start_pool_n * sizeof(int)));
+        CU(cudaMemset(env->d_hpool_bcount, 0, (size_t)env->start_pool_n * sizeof(int)));
         CU(cudaMalloc((void**)&env->d_htarget_pool, (size_t)2 * env->htarget_pool_n * 4 * sizeof(double)));
         CU(cudaMemset(env->d_htarget_pool, 0, (size_t)2 * env->htarget_pool_n * 4 * sizeof(double)));
     }
@@ -962,7 +978,7 @@ extern "C" int smenv_destroy(SmEnv* env) {
     for (void* q : env->net_allocs) cudaFree(q);
     cudaFree(env->d_risk); cudaFree(env->d_backup); cudaFree(env->d_exec); cudaFree(env->d_risky); cudaFree(env->d_gate_list);
     cudaFree(env->d_hpairs); cudaFree(env->d_hthresh); cudaFree(env->d_hrange); cudaFree(env->d_hbacc); cudaFree(env->d_hposes);
-    cudaFree(env->d_hbinfo); cudaFree(env->d_hunits); cudaFree(env->d_hscratch); cudaFree(env->d_hpolicy); cudaFree(env->d_hstart_pool); cudaFree(env->d_htarget_pool);
+    cudaFree(env->d_hbinfo); cudaFree(env->d_hunits); cudaFree(env->d_hscratch); cudaFree(env->d_hpolicy); cudaFree(env->d_hstart_pool); cudaFree(env->d_hpool_brake); cudaFree(env->d_hpool_bcount); cudaFree(env->d_htarget_pool);
     for (int i = 0; i <= SM_K_COUNT; ++i) if (env->ev[i]) cudaEventDestroy(env->ev[i]);
     for (int c = 0; c < 8; ++c) {
         if (env->chunk_streams[c]) cudaStreamDestroy(env->chunk_streams[c]);
@@ -1025,7 +1041,9 @@ extern "C" int smenv_fill_pools(SmEnv* env, uint64_t seed, SmStream s) {
                         (uint32_t)(seed >> 32)};
         fill_human_pool_kernel<<<grid_for(env, env->start_pool_n + 2 * env->htarget_pool_n), SM_WARPS_PER_BLOCK * 32,
                                  env->smem_bytes, stream>>>(H);
-        env->launches++;
+        human_pool_braking_kernel<<<(env->start_pool_n * 8 + 255) / 256, 256, 0, stream>>>(env->d_hstart_pool, env->start_pool_n,
+                                                                                         env->d_hpool_brake, env->d_hpool_bcount);
+        env->launches += 2;
     }
     if (env->ball_pool_n) {
         fill_ball_pool_kernel<<<grid_for(env, env->ball_pool_n), SM_WARPS_PER_BLOCK * 32, env->smem_bytes, stream>>>(A);
@@ -1179,6 +1197,7 @@ extern "C" int smenv_reset(SmEnv* env, const SmBuffers* buf, const uint8_t* mask
         memset(&H, 0, sizeof(H));
         H.buf = *buf; H.n = env->n; H.env_base = 0; H.k0 = (uint32_t)env->seed; H.k1 = (uint32_t)(env->seed >> 32);
         H.mask = mask; H.start_pool = env->d_hstart_pool; H.start_pool_n = env->start_pool_n;
+        H.pool_brake = env->d_hpool_brake; H.pool_bcount = env->d_hpool_bcount;
         H.target_pool = env->d_htarget_pool; H.target_pool_n = env->htarget_pool_n;
         human_reset_kernel<<<(env->n * 8 + 255) / 256, 256, 0, stream>>>(H, 0);
         env->launches++;
@@ -1453,6 +1472,7 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
         HA.target_pool = env->pools_filled ? env->d_htarget_pool : nullptr;
         HA.target_pool_n = env->pools_filled ? env->htarget_pool_n : 0;
         HA.start_pool = env->pools_filled ? env->d_hstart_pool : nullptr;
+        HA.pool_brake = env->pools_filled ? env->d_hpool_brake : nullptr; HA.pool_bcount = env->d_hpool_bcount;
         HA.start_pool_n = env->pools_filled ? env->start_pool_n : 0;
         HA.cwork = cwork;
         HA.counters = env->count ? env->d_counters : nullptr;
@@ -1494,8 +1514,7 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
         else SM_MARK(SM_K_HUMAN_BRAKE_GJK);
         SM_MARK(SM_K_HUMAN_ADVANCE);
         human_advance_kernel<<<(m * 8 + 255) / 256, 256, 0, stream>>>(HA);
-        human_outcome_kernel<<<(m * 8 + 255) / 256, 256, 0, stream>>>(HA);
-        env->launches += 2;
+        env->launches++;
         CU(cudaGetLastError());
     }
     SM_MARK(SM_K_JOINT);

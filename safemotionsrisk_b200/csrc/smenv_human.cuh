@@ -42,6 +42,8 @@ struct HumanArgs {
     int target_pool_n;
     const double* start_pool;  // [start_pool_n][SM_HPOOL_STRIDE] start states of the nested env
     int start_pool_n;
+    const double* pool_brake;  // [start_pool_n][SM_HBRAKE_STEPS][8] initial braking trajectory of every start state, NULL: computed
+    const int* pool_bcount;    // [start_pool_n] its number of steps
     int* cwork;                // contact planning: [0] = count, [1..] = env * 8 + span
     const uint8_t* mask;       // reset: envs to reset (NULL = by done flag / all)
     unsigned long long* counters;
@@ -377,11 +379,138 @@ __global__ void __launch_bounds__(HBP_THREADS) human_brake_plan_kernel(HumanArgs
     }
 }
 
+// observation of the nested env (observations.py:313-351 with two arms and alternating target points): entries spread over
+// `stride` lanes
+__device__ __forceinline__ void write_human_observation(float* hobs, const double* hk, const double* hs, int lane, int stride) {
+    const JointLim& L = c_sc.hu.lim;
+#pragma unroll 1
+    for (int i = lane; i < SM_HOBS_STRIDE; i += stride) {
+        double val = 0.0;
+        if (i < 24) {
+            const int grp = i >> 3, j = i & 7;
+            const double x = hk[grp * 8 + j];
+            val = grp == 0 ? normalize_mm(x, L.pos_lo[j], L.pos_hi[j]) : xdiv(x, grp == 1 ? L.vel_max[j] : L.acc_max[j]);
+        } else if (i < 30) {
+            const int r = (i - 24) / 3, c = (i - 24) % 3;
+            const double* tp = hs + 12 * r;
+            if (tp[SM_TP_ACTIVE] != 0.0) val = normalize_mm(tp[SM_TP_POS + c], c_sc.hu.tp_box_min[c], c_sc.hu.tp_box_max[c]);
+        } else if (i < 36) {
+            const int r = (i - 30) / 3, c = (i - 30) % 3;
+            const double* tp = hs + 12 * r;
+            if (tp[SM_TP_ACTIVE] != 0.0)
+                val = normalize_mm(xsub(tp[SM_TP_POS + c], tp[SM_TP_LINK_POS + c]), c_sc.hu.tp_rel_min[c], c_sc.hu.tp_rel_max[c]);
+        } else if (i < 38) {
+            val = hs[12 * (i - 36) + SM_TP_ACTIVE] != 0.0 ? 1.0 : 0.0;
+        }
+        hobs[i] = clip1(val);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// outcome of the nested env's step: 8 lanes per env (the second half of human_advance_kernel).  Lanes 0 / 1 take the link
+// points of the two arms at the new knot; if the active arm's point is close enough to its target for a sub-step to have
+// reached it (how far every joint strays from the knot inside the step comes from the lanes that just integrated it), lane
+// i checks sub-steps i, i + 8, i + 16 (ctlp.py:2787-2821; target link point of the sub-step's setpoint pose); then
+// get_target_point_observation (ctlp.py:2210-2271) and the observation.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void human_outcome(const HumanArgs& A, size_t env, bool valid, int lane,
+                                              float dq_lane /* how far joint (lane & 7) strays from the new knot in the step */,
+                                              double q0, double v0, double a0, double a1 /* the step of joint (lane & 7) */) {
+    const int sl = lane & 7;
+    const unsigned gmask = 0xffu << (lane & 24);
+    const int S = c_sc.substeps;
+    double* hs = A.buf.hstate + env * SM_HSTATE_STRIDE;
+    const double* hk = A.buf.hkin + env * SM_KIN_STRIDE;
+    int active = -1;
+    if (hs[SM_TP_ACTIVE] != 0.0) active = 0;
+    else if (hs[12 + SM_TP_ACTIVE] != 0.0) active = 1;
+    // link points of both arms at the new knot (the setpoint pose of the last sub-step)
+    V3 lp = mk(0.f, 0.f, 0.f);
+    if (sl < 2) {
+        Xf F;
+        human_base(F);
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) human_chain_step(F, 4 * sl + i, (float)hk[4 * sl + i]);
+        lp = xf_apply(F, c_sc.hu.tp_local[sl][0], c_sc.hu.tp_local[sl][1], c_sc.hu.tp_local[sl][2]);
+    }
+    bool hit = false;
+    {
+        // every sub-step's link point lies within infl of the new knot's: sum_i max_k |q_i(k) - q_i(S)| rho_i; only an
+        // env whose knot point is that close to the target runs the forward kinematics of the sub-steps
+        const int arm = active >= 0 ? active : 0, src = (lane & 24) | arm;
+        const V3 lpa = mk(__shfl_sync(FULL, lp.x, src), __shfl_sync(FULL, lp.y, src), __shfl_sync(FULL, lp.z, src));
+        float infl = 1e-5f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            infl = fmaf(__shfl_sync(FULL, dq_lane, (lane & 24) | (4 * arm + i)), c_sc.hu.tp_rho[arm][i], infl);
+        if (active >= 0) {
+            const double* tp = hs + 12 * active;
+            const V3 T = mk((float)tp[SM_TP_POS], (float)tp[SM_TP_POS + 1], (float)tp[SM_TP_POS + 2]);
+            const V3 e1 = lpa - T;
+            if (sqrtf(dot(e1, e1)) - infl < (float)c_sc.hu.tp_radius) {   // uniform over the eight lanes of the env
+                // the step of the four joints of the active arm, from the lanes that own them (the setpoints are not stored)
+                double jq[4], jv[4], ja[4], ja1[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int from = (lane & 24) | (4 * arm + i);
+                    jq[i] = __shfl_sync(gmask, q0, from); jv[i] = __shfl_sync(gmask, v0, from);
+                    ja[i] = __shfl_sync(gmask, a0, from); ja1[i] = __shfl_sync(gmask, a1, from);
+                }
+                Xf B;
+                human_base(B);
+#pragma unroll 1
+                for (int k = sl; k < S; k += 8) {
+                    Xf F = B;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        human_chain_step(F, 4 * active + i, (float)joint_setpoint_at(jq[i], jv[i], ja[i], ja1[i], k + 1));
+                    const V3 e = xf_apply(F, c_sc.hu.tp_local[active][0], c_sc.hu.tp_local[active][1], c_sc.hu.tp_local[active][2]) - T;
+                    if (sqrtf(dot(e, e)) < (float)c_sc.hu.tp_radius) hit = true;
+                }
+            }
+        }
+    }
+    const bool reached = (__ballot_sync(FULL, hit) & gmask) != 0u;
+    const double draws = hs[SM_HS_DRAWS];
+    __syncwarp();
+    if (valid && sl < 2) {   // lane r owns the record of arm r
+        double* tp = hs + 12 * sl;
+        tp[SM_TP_LINK_POS] = (double)lp.x; tp[SM_TP_LINK_POS + 1] = (double)lp.y; tp[SM_TP_LINK_POS + 2] = (double)lp.z;
+        bool act = tp[SM_TP_ACTIVE] != 0.0;
+        tp[SM_HTP_REACHED] = 0.0;
+        if (reached && sl == active) {         // ctlp.py:2806-2811
+            act = false;
+            tp[SM_TP_REACHED_N] += 1.0;
+        }
+        const bool sample_new = reached && sl == (active + 1) % 2;   // alternating target points (ctlp.py:2815-2817)
+        if (sample_new && A.target_pool_n > 0) {                      // _add_target_point from the device pool
+            const uint4 r = philox((uint32_t)(env + A.env_base), (uint32_t)draws, 0x7A28u, 3u, A.k0, A.k1);
+            const double* e = A.target_pool + ((size_t)sl * A.target_pool_n + (r.x % (uint32_t)A.target_pool_n)) * 4;
+            tp[SM_TP_POS] = e[0]; tp[SM_TP_POS + 1] = e[1]; tp[SM_TP_POS + 2] = e[2];
+            act = true;
+            tp[SM_TP_INIT_DIST] = nan("");
+        } else if (sample_new) {
+            tp[SM_HTP_SAMPLE_NEW] = 1.0;   // no pool: the caller injects the next target point (parity protocol)
+        }
+        tp[SM_TP_ACTIVE] = act ? 1.0 : 0.0;
+        if (act) {
+            const double dx = tp[SM_TP_POS] - tp[SM_TP_LINK_POS], dy = tp[SM_TP_POS + 1] - tp[SM_TP_LINK_POS + 1],
+                         dz = tp[SM_TP_POS + 2] - tp[SM_TP_LINK_POS + 2];
+            tp[SM_TP_LAST_DIST] = sqrt(dx * dx + dy * dy + dz * dz);
+            if (isnan(tp[SM_TP_INIT_DIST])) tp[SM_TP_INIT_DIST] = tp[SM_TP_LAST_DIST];
+        }
+        if (sample_new && A.target_pool_n > 0) hs[SM_HS_DRAWS] = draws + 1.0;
+        __threadfence_block();
+    }
+    __syncwarp();
+    if (valid) write_human_observation(A.buf.hobs + env * SM_HOBS_STRIDE, hk, hs, sl, 8);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // adapt_action (ctlp.py:3055-3153) + get_braking_acceleration (:3000-3024), then the 24 setpoints and the tracked pose of
-// the human (Human.prepare_sim_step ctlp.py:4850-4860; robot_scene_base.py:789-837): thread = (env, joint)
+// the human (Human.prepare_sim_step ctlp.py:4850-4860; robot_scene_base.py:789-837): thread = (env, joint); then the outcome
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) human_advance_kernel(HumanArgs A) {
+__global__ void __launch_bounds__(256, 4) human_advance_kernel(HumanArgs A) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int env_raw = t >> 3, j = t & 7;
     const bool valid = env_raw < A.n;
@@ -417,120 +546,17 @@ __global__ void __launch_bounds__(256) human_advance_kernel(HumanArgs A) {
     const double q = kin[j], v = kin[8 + j], a = kin[16 + j], qa = kin[24 + j];
     const double steps = hs[SM_HS_STEPS];
     __syncwarp();   // every lane of the env has read the record before lane 0 rewrites it
+    float dq = 0.f;
     if (valid) {
-        joint_advance_a1(kin, A.hscratch + env * SM_SCRATCH_FLOATS, j, q, v, a, qa, a1, 0.87, true, c_sc.hu.lim.jerk_max[j]);
+        joint_advance_a1(kin, A.hscratch + env * SM_SCRATCH_FLOATS, j, q, v, a, qa, a1, 0.87, false, c_sc.hu.lim.jerk_max[j], &dq);
         if (j == 0) {
             hs[SM_HS_BRAKE_COUNT] = (double)new_count;
             hs[SM_HS_BRAKED] = (double)braked;
             hs[SM_HS_STEPS] = steps + 1.0;
         }
     }
-}
-
-// observation of the nested env (observations.py:313-351 with two arms and alternating target points): entries spread over
-// `stride` lanes
-__device__ __forceinline__ void write_human_observation(float* hobs, const double* hk, const double* hs, int lane, int stride) {
-    const JointLim& L = c_sc.hu.lim;
-#pragma unroll 1
-    for (int i = lane; i < SM_HOBS_STRIDE; i += stride) {
-        double val = 0.0;
-        if (i < 24) {
-            const int grp = i >> 3, j = i & 7;
-            const double x = hk[grp * 8 + j];
-            val = grp == 0 ? normalize_mm(x, L.pos_lo[j], L.pos_hi[j]) : xdiv(x, grp == 1 ? L.vel_max[j] : L.acc_max[j]);
-        } else if (i < 30) {
-            const int r = (i - 24) / 3, c = (i - 24) % 3;
-            const double* tp = hs + 12 * r;
-            if (tp[SM_TP_ACTIVE] != 0.0) val = normalize_mm(tp[SM_TP_POS + c], c_sc.hu.tp_box_min[c], c_sc.hu.tp_box_max[c]);
-        } else if (i < 36) {
-            const int r = (i - 30) / 3, c = (i - 30) % 3;
-            const double* tp = hs + 12 * r;
-            if (tp[SM_TP_ACTIVE] != 0.0)
-                val = normalize_mm(xsub(tp[SM_TP_POS + c], tp[SM_TP_LINK_POS + c]), c_sc.hu.tp_rel_min[c], c_sc.hu.tp_rel_max[c]);
-        } else if (i < 38) {
-            val = hs[12 * (i - 36) + SM_TP_ACTIVE] != 0.0 ? 1.0 : 0.0;
-        }
-        hobs[i] = clip1(val);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// outcome of the nested env's step: 8 lanes per env.  Lane i checks sub-steps i, i + 8, i + 16 of the active arm against
-// its target point (ctlp.py:2787-2821; target link point of the sub-step's setpoint pose), lanes 0 / 1 take the link
-// points of the two arms at the new knot; then get_target_point_observation (ctlp.py:2210-2271) and the observation.
-// ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) human_outcome_kernel(HumanArgs A) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31, sl = lane & 7;
-    const unsigned gmask = 0xffu << (lane & 24);
-    const int env_raw = t >> 3;
-    const bool valid = env_raw < A.n;
-    const size_t env = valid ? (size_t)env_raw : (size_t)(A.n - 1);
-    const int S = c_sc.substeps;
-    double* hs = A.buf.hstate + env * SM_HSTATE_STRIDE;
-    const double* hk = A.buf.hkin + env * SM_KIN_STRIDE;
-    const float* qs = A.hscratch + env * SM_SCRATCH_FLOATS + SM_QSET_OFF;
-    int active = -1;
-    if (hs[SM_TP_ACTIVE] != 0.0) active = 0;
-    else if (hs[12 + SM_TP_ACTIVE] != 0.0) active = 1;
-    bool hit = false;
-    if (active >= 0) {
-        const double* tp = hs + 12 * active;
-        const V3 T = mk((float)tp[SM_TP_POS], (float)tp[SM_TP_POS + 1], (float)tp[SM_TP_POS + 2]);
-        Xf B;
-        human_base(B);
-#pragma unroll 1
-        for (int k = sl; k < S; k += 8) {
-            Xf F = B;
-#pragma unroll 1
-            for (int i = 0; i < 4; ++i) human_chain_step(F, 4 * active + i, qs[k * SM_MAX_JOINTS + 4 * active + i]);
-            const V3 e = xf_apply(F, c_sc.hu.tp_local[active][0], c_sc.hu.tp_local[active][1], c_sc.hu.tp_local[active][2]) - T;
-            if (sqrtf(dot(e, e)) < (float)c_sc.hu.tp_radius) hit = true;
-        }
-    }
-    const bool reached = (__ballot_sync(FULL, hit) & gmask) != 0u;
-    // link points of both arms at the new knot (the setpoint pose of the last sub-step)
-    V3 lp = mk(0.f, 0.f, 0.f);
-    if (sl < 2) {
-        Xf F;
-        human_base(F);
-#pragma unroll 1
-        for (int i = 0; i < 4; ++i) human_chain_step(F, 4 * sl + i, (float)hk[4 * sl + i]);
-        lp = xf_apply(F, c_sc.hu.tp_local[sl][0], c_sc.hu.tp_local[sl][1], c_sc.hu.tp_local[sl][2]);
-    }
-    const double draws = hs[SM_HS_DRAWS];
-    __syncwarp();
-    if (valid && sl < 2) {   // lane r owns the record of arm r
-        double* tp = hs + 12 * sl;
-        tp[SM_TP_LINK_POS] = (double)lp.x; tp[SM_TP_LINK_POS + 1] = (double)lp.y; tp[SM_TP_LINK_POS + 2] = (double)lp.z;
-        bool act = tp[SM_TP_ACTIVE] != 0.0;
-        tp[SM_HTP_REACHED] = 0.0;
-        if (reached && sl == active) {         // ctlp.py:2806-2811
-            act = false;
-            tp[SM_TP_REACHED_N] += 1.0;
-        }
-        const bool sample_new = reached && sl == (active + 1) % 2;   // alternating target points (ctlp.py:2815-2817)
-        if (sample_new && A.target_pool_n > 0) {                      // _add_target_point from the device pool
-            const uint4 r = philox((uint32_t)(env + A.env_base), (uint32_t)draws, 0x7A28u, 3u, A.k0, A.k1);
-            const double* e = A.target_pool + ((size_t)sl * A.target_pool_n + (r.x % (uint32_t)A.target_pool_n)) * 4;
-            tp[SM_TP_POS] = e[0]; tp[SM_TP_POS + 1] = e[1]; tp[SM_TP_POS + 2] = e[2];
-            act = true;
-            tp[SM_TP_INIT_DIST] = nan("");
-        } else if (sample_new) {
-            tp[SM_HTP_SAMPLE_NEW] = 1.0;   // no pool: the caller injects the next target point (parity protocol)
-        }
-        tp[SM_TP_ACTIVE] = act ? 1.0 : 0.0;
-        if (act) {
-            const double dx = tp[SM_TP_POS] - tp[SM_TP_LINK_POS], dy = tp[SM_TP_POS + 1] - tp[SM_TP_LINK_POS + 1],
-                         dz = tp[SM_TP_POS + 2] - tp[SM_TP_LINK_POS + 2];
-            tp[SM_TP_LAST_DIST] = sqrt(dx * dx + dy * dy + dz * dz);
-            if (isnan(tp[SM_TP_INIT_DIST])) tp[SM_TP_INIT_DIST] = tp[SM_TP_LAST_DIST];
-        }
-        if (sample_new && A.target_pool_n > 0) hs[SM_HS_DRAWS] = draws + 1.0;
-        __threadfence_block();
-    }
-    __syncwarp();
-    if (valid) write_human_observation(A.buf.hobs + env * SM_HOBS_STRIDE, hk, hs, sl, 8);
+    __syncwarp();   // the new knot and the sub-step setpoints of the env are visible to its eight lanes
+    human_outcome(A, env, valid, threadIdx.x & 31, dq, q, v, a, a1);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -740,8 +766,7 @@ __device__ __forceinline__ void copy_human_kinematic_obs(float* obs, const float
 // ObstacleWrapperBase.reset with compute_initial_braking_trajectory (ctlp.py:1120-1139): the stored braking trajectory
 // starts as the accelerations that brake from the start state; the position handed to the range computation is not
 // advanced along it (as in the reference).  The eight lanes of an env, lane j = joint j, all lanes of the warp call.
-__device__ __forceinline__ void human_initial_braking(double* hs, double* hb, double q, double v, double a, bool active,
-                                                      int lane) {
+__device__ __forceinline__ int human_initial_braking_steps(double* hb, double q, double v, double a, bool active, int lane) {
     const JointLim& L = c_sc.hu.lim;
     const int j = lane & 7, gsh = lane & 24;
     const double ts = c_sc.ts;
@@ -763,7 +788,23 @@ __device__ __forceinline__ void human_initial_braking(double* hs, double* hb, do
         }
         if (__all_sync(FULL, done)) break;
     }
-    if (active && j == 0) hs[SM_HS_BRAKE_COUNT] = (double)k;
+    return k;
+}
+__device__ __forceinline__ void human_initial_braking(double* hs, double* hb, double q, double v, double a, bool active,
+                                                      int lane) {
+    const int k = human_initial_braking_steps(hb, q, v, a, active, lane);
+    if (active && (lane & 7) == 0) hs[SM_HS_BRAKE_COUNT] = (double)k;
+}
+// the same for every entry of the start pool, once per pool fill: a reset then copies the stored trajectory
+__global__ void __launch_bounds__(256) human_pool_braking_kernel(const double* pool, int n, double* pool_brake, int* pool_bcount) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, j = t & 7;
+    const int e_raw = t >> 3;
+    const bool active = e_raw < n;
+    const size_t e = active ? (size_t)e_raw : (size_t)(n - 1);
+    const double* st = pool + e * SM_HPOOL_STRIDE;
+    const int k = human_initial_braking_steps(pool_brake + e * SM_HBRAKE_STEPS * 8, st[j], st[8 + j], st[16 + j], active, lane);
+    if (active && j == 0) pool_bcount[e] = k;
 }
 
 __global__ void __launch_bounds__(256) human_set_state_kernel(HumanArgs A, const double* hq, const double* hv,
@@ -813,6 +854,18 @@ __global__ void __launch_bounds__(256) human_reset_kernel(HumanArgs A, int by_do
         if (A.buf.obs) copy_human_kinematic_obs(A.buf.obs + env * c_sc.obs_size, A.buf.hobs + env * SM_HOBS_STRIDE);
     }
     __syncwarp();
+    if (A.pool_brake) {   // the braking trajectory of a pool entry does not depend on the env: stored with the pool
+        if (active) {
+            const size_t entry = (size_t)(r.x % (uint32_t)A.start_pool_n);
+            const int k = c_sc.hu.check_braking && c_sc.hu.initial_braking_trajectory ? A.pool_bcount[entry] : 0;
+            const double* src = A.pool_brake + entry * SM_HBRAKE_STEPS * 8;
+            double* hb = A.buf.hbrake + env * SM_HBRAKE_STEPS * 8;
+#pragma unroll 1
+            for (int i = 0; i < k; ++i) hb[i * 8 + j] = src[i * 8 + j];
+            if (j == 0) A.buf.hstate[env * SM_HSTATE_STRIDE + SM_HS_BRAKE_COUNT] = (double)k;
+        }
+        return;
+    }
     human_initial_braking(A.buf.hstate + env * SM_HSTATE_STRIDE, A.buf.hbrake + env * SM_HBRAKE_STEPS * 8,
                           active ? e[j] : 0.0, active ? e[8 + j] : 0.0, active ? e[16 + j] : 0.0, active, lane);
 }

@@ -69,14 +69,24 @@ __device__ __forceinline__ float joint_action(const JointArgs& A, int env, int j
 
 // Action mapping, the S interpolated setpoints with the motor-tracked pose, the new knot (actions.py:268-280,
 // :412-443; safe_motions_base.py:1179-1185, :1233-1277).  Returns the relative jerk of the step (rewards.py:181-186).
+// setpoint of sub-step k (1-based) of a step from (q, v, a) to the end acceleration a1: the arithmetic of the loop in
+// joint_advance_a1, operation by operation (the human's target-point check recomputes setpoints instead of storing them)
+__device__ __forceinline__ double joint_setpoint_at(double q, double v, double a, double a1, int k) {
+    const double jerk = xdiv(xsub(a1, a), c_sc.ts);
+    const double ha = xmul(0.5, a), sj = xmul(1.0 / 6.0, jerk);
+    const double tk = c_sc.sub_t[k];
+    return xadd(xadd(xadd(q, xmul(v, tk)), xmul(xmul(ha, tk), tk)), xmul(xmul(xmul(sj, tk), tk), tk));
+}
 __device__ __forceinline__ float joint_advance_a1(double* kin, float* scr, int j, double q, double v, double a, double qa,
-                                                  double a1, double track_vel, bool store_qset, double jerk_max) {
+                                                  double a1, double track_vel, bool store_qset, double jerk_max,
+                                                  float* dq_out = nullptr /* max_k |setpoint(k) - setpoint(S)| */) {
     const int S = c_sc.substeps;
     const double dt = xdiv(c_sc.ts, (double)S);
     const double tvdt = xmul(track_vel, dt);
     const double jerk = xdiv(xsub(a1, a), c_sc.ts);      // actions.py:468-487, hoisted out of the sub-step loop
     const double hj = xmul(0.5, jerk), ha = xmul(0.5, a), sj = xmul(1.0 / 6.0, jerk);
     double q1 = q, v1 = v;
+    float qmin = FLT_MAX, qmax = -FLT_MAX;
     for (int k = 1; k <= S; ++k) {
         const double tk = c_sc.sub_t[k];
         double vs = xadd(xadd(v, xmul(a, tk)), xmul(xmul(hj, tk), tk));
@@ -85,8 +95,10 @@ __device__ __forceinline__ float joint_advance_a1(double* kin, float* scr, int j
         if (store_qset) scr[SM_QSET_OFF + (k - 1) * SM_MAX_JOINTS + j] = (float)qs;  // ctlp.py:2787-2791
         qa = xadd(xadd(qa, xmul(c_sc.track_kp, xsub(qs, qa))), xmul(tvdt, vs));
         q1 = qs; v1 = vs;                                // k == S: the new knot
+        qmin = fminf(qmin, (float)qs); qmax = fmaxf(qmax, (float)qs);
     }
     kin[j] = q1; kin[8 + j] = v1; kin[16 + j] = a1; kin[24 + j] = qa;
+    if (dq_out) *dq_out = fmaxf(qmax - (float)q1, (float)q1 - qmin);
     return (float)(fabs(jerk) / jerk_max);
 }
 __device__ __forceinline__ float joint_advance(const JointArgs& A, double* kin, float* scr, int j, double q, double v,
