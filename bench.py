@@ -437,14 +437,17 @@ def measure_scene(scene_name, args, dev, rank, world, local_rank, fma_peaks, ste
     # the device)
     hj, hs = c["heavy_joints"] / steps_counted, c["heavy_solves"] / steps_counted
     intervals = c["reserved"] / steps_counted      # braking-profile intervals evaluated by joint_solve_kernel
+    brake_poses, brake_bounds = c["brake_poses"] / steps_counted, c["brake_pair_bounds"] / steps_counted
     kflops = {"joint_kernel": (sc_nj - hj) * 360.0, "joint_heavy_kernel": hj * 360.0 + intervals * 60.0,
               "contact_plan_kernel": 8 * 600.0, "distance_plan_kernel": 600.0,
               "gjk_kernel": 5.0 * n_dot + 100.0 * n_iter, "finish_kernel": 200.0,
-              # Human scene: policy 2 x 44 544 MAC on the tensor cores; range + braking steps of 8 joints; ~11 poses x
-              # (FK 600 + 203 pair bounds x 30); GJK counted with the main GJK launch
+              # Human scene: policy 2 x 44 544 MAC on the tensor cores; range + braking steps of 8 joints; the pose
+              # checks from the device counters: per pose the FK of 8 joints (axis-angle matrix + two 3x3 products + the
+              # translation: 140 flops each), 30 table points (18 flops) and 7 capsule tests (70), per evaluated convex
+              # pair a sphere bound of 14 flops; culled group pairs are NOT counted.  GJK counted with the main GJK launch
               "human_policy": 2.0 * 44544.0, "human_joint_kernels": 8 * 360.0, "human_brake_traj_kernel": 8 * 3 * 360.0,
-              "human_brake_plan_kernel": 11 * (600.0 + 203 * 30.0), "human_brake_gjk": 0.0,
-              "human_advance_outcome": 8 * 60.0 + 24 * 300.0}
+              "human_brake_plan_kernel": brake_poses * (8 * 140.0 + 30 * 18.0 + 7 * 70.0) + brake_bounds * 14.0,
+              "human_brake_gjk": 0.0, "human_advance_outcome": 8 * 60.0 + 24 * 300.0}
     ktimes = {k: v for k, v in ktimes.items() if v > 0.0 or not k.startswith("human")}
     kbound = {"joint_kernel": "fp64", "joint_heavy_kernel": "fp64", "human_joint_kernels": "fp64",
               "human_brake_traj_kernel": "fp64"}
@@ -488,6 +491,7 @@ def measure_scene(scene_name, args, dev, rank, world, local_rank, fma_peaks, ste
                 "kernels_ms": ktimes, "flops_per_env_step": f_step, "support_dots_per_env_step": n_dot,
                 "gjk_iters_per_env_step": n_iter, "gjk_pairs_per_env_step": c["gjk_calls"] / steps_counted,
                 "position_solve_intervals_per_env_step": intervals,
+                "brake_poses_per_env_step": brake_poses, "brake_pair_bounds_per_env_step": brake_bounds,
                 "whole_step": {"achieved": per_gpu_steps_s * f_step / 1e12,
                                "frac": per_gpu_steps_s * f_step / 1e12 / fma_peaks["fp32"],
                                "unculled_reference_flops_per_env_step": uncull},

@@ -337,6 +337,8 @@ typedef struct SmCounters {
     unsigned long long heavy_joints;   /* (env, joint) instances that went through joint_heavy_kernel */
     unsigned long long heavy_solves;   /* position bounds that needed the iterative solve */
     unsigned long long aux[6];         /* GJK pairs by iteration count: <= 4, <= 8, <= 12, <= 16, <= 24, more */
+    unsigned long long brake_poses;        /* Human: poses the braking-trajectory check visited */
+    unsigned long long brake_pair_bounds;  /* Human: sphere bounds of convex pairs evaluated for those poses */
 } SmCounters;
 
 /* Kernels of one step, in launch order (smenv_kernel_times). */

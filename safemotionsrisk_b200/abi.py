@@ -167,7 +167,8 @@ class SmBuffers(C.Structure):
 class SmCounters(C.Structure):
     _fields_ = [("gjk_calls", C.c_ulonglong), ("gjk_iters", C.c_ulonglong), ("support_dots", C.c_ulonglong),
                 ("distance_items", C.c_ulonglong), ("env_steps", C.c_ulonglong), ("contact_envs", C.c_ulonglong),
-                ("contact_items", C.c_ulonglong), ("reserved", C.c_ulonglong), ("heavy_joints", C.c_ulonglong), ("heavy_solves", C.c_ulonglong), ("aux", C.c_ulonglong * 6)]
+                ("contact_items", C.c_ulonglong), ("reserved", C.c_ulonglong), ("heavy_joints", C.c_ulonglong), ("heavy_solves", C.c_ulonglong), ("aux", C.c_ulonglong * 6),
+                ("brake_poses", C.c_ulonglong), ("brake_pair_bounds", C.c_ulonglong)]
 
 
 # every extern "C" symbol include/smenv.h declares

@@ -869,8 +869,8 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     }
     CU(cudaMalloc((void**)&env->d_heavy, ((size_t)num_envs * 8 + 8) * sizeof(int)));
     CU(cudaMemset(env->d_heavy, 0, ((size_t)num_envs * 8 + 8) * sizeof(int)));
-    CU(cudaMalloc((void**)&env->d_counters, 16 * sizeof(unsigned long long)));
-    CU(cudaMemset(env->d_counters, 0, 16 * sizeof(unsigned long long)));
+    CU(cudaMalloc((void**)&env->d_counters, 24 * sizeof(unsigned long long)));
+    CU(cudaMemset(env->d_counters, 0, 24 * sizeof(unsigned long long)));
 
     env->smem_bytes = smem_bytes_for(sc->n_verts, SM_WARPS_PER_BLOCK);
     env->smem_bytes_broad = smem_bytes_for(0, SM_WARPS_PER_BLOCK);
@@ -1848,12 +1848,13 @@ extern "C" int smenv_enable_counters(SmEnv* env, int enable) {
 extern "C" int smenv_counters(SmEnv* env, SmCounters* out, int reset) {
     if (!env || !out) return fail(SM_ERR_ARG, "null argument");
     CU(cudaSetDevice(env->device));
-    unsigned long long h[16];
+    unsigned long long h[24];
     CU(cudaMemcpy(h, env->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
     out->gjk_calls = h[0]; out->gjk_iters = h[1]; out->support_dots = h[2]; out->distance_items = h[3];
     out->env_steps = h[4]; out->contact_envs = h[5]; out->contact_items = h[6]; out->reserved = h[7];
     out->heavy_joints = h[8]; out->heavy_solves = h[9];
     for (int i = 0; i < 6; ++i) out->aux[i] = h[10 + i];
+    out->brake_poses = h[16]; out->brake_pair_bounds = h[17];
     if (reset) CU(cudaMemset(env->d_counters, 0, sizeof(h)));
     return SM_OK;
 }

@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(128) human_brake_traj_kernel(HumanArgs A) {
         const int npc = np < SM_HBRAKE_POSES ? np : SM_HBRAKE_POSES;
         bi[0] = k; bi[1] = npc; bi[2] = timeout; bi[3] = 0;
         A.res[env * SM_RES_STRIDE + GJK_BRAKE] = SM_RES_NO_CONTACT;
+        if (A.counters && npc > 0) atomicAdd(&A.counters[16], (unsigned long long)npc);
         if (npc > 0) {   // one unit per pose for the geometry pass
             const int base = atomicAdd(A.units, npc);
             for (int p = 0; p < npc; ++p) A.units[1 + base + p] = ((int)env << 7) | p;
@@ -217,6 +218,12 @@ __device__ __forceinline__ float segment_dist2(V3 p1, V3 q1, V3 p2, V3 q2) {
 }
 
 #define HBP_THREADS 128
+#ifndef HBP_INTERLEAVE
+#define HBP_INTERLEAVE 0   /* the FK chains of the two arms written side by side (experiment) */
+#endif
+#ifndef HBP_UNROLL_NEAR
+#define HBP_UNROLL_NEAR 0  /* capsule tests of the link-group pairs unrolled (experiment) */
+#endif
 #define HBP_MAX_TRUNK 32
 // dynamic shared memory: point table [n_arm_shapes + 8][3][HBP_THREADS] | trunk spheres [HBP_MAX_TRUNK] float4 |
 // world capsules of the trunk sides of the group pairs [8][8] | radius + margin of the arm shapes [32]
@@ -271,6 +278,7 @@ __global__ void __launch_bounds__(HBP_THREADS) human_brake_plan_kernel(HumanArgs
         put(nas + 2 * fi, xf_apply(F, sg[0], sg[1], sg[2]));
         put(nas + 2 * fi + 1, xf_apply(F, sg[3], sg[4], sg[5]));
     };
+    unsigned n_bounds = 0;   // sphere bounds of convex pairs evaluated by this thread (counted in the measurement mode)
 #pragma unroll 1
     for (int u0 = blockIdx.x * HBP_THREADS; u0 < n_units; u0 += gridDim.x * HBP_THREADS) {
         __syncwarp();   // lanes leave the pair loops of the previous pose at different times
@@ -282,6 +290,18 @@ __global__ void __launch_bounds__(HBP_THREADS) human_brake_plan_kernel(HumanArgs
         const float4 r0 = row[0], r1 = row[1];
         // frames that carry shapes of the check: upper arm (3 / 7) and forearm + hand (4 / 8) of both arms
         Xf F3, F4, F7, F8;
+#if HBP_INTERLEAVE
+        {   // the two arms are independent chains: written side by side so that their latencies overlap
+            Xf Fa = B, Fb = B;
+            human_chain_step(Fa, 0, r0.x); human_chain_step(Fb, 4, r1.x);
+            human_chain_step(Fa, 1, r0.y); human_chain_step(Fb, 5, r1.y);
+            human_chain_step(Fa, 2, r0.z); human_chain_step(Fb, 6, r1.z);
+            F3 = Fa; F7 = Fb;
+            human_chain_step(Fa, 3, r0.w); human_chain_step(Fb, 7, r1.w);
+            F4 = Fa; F8 = Fb;
+            frame_points(F3, 0); frame_points(F7, 2); frame_points(F4, 1); frame_points(F8, 3);
+        }
+#else
         {
             Xf F = B;
             human_chain_step(F, 0, r0.x); human_chain_step(F, 1, r0.y); human_chain_step(F, 2, r0.z);
@@ -298,9 +318,16 @@ __global__ void __launch_bounds__(HBP_THREADS) human_brake_plan_kernel(HumanArgs
             F8 = F;
             frame_points(F8, 3);
         }
+#endif
+        // capsule tests of all link-group pairs first (independent of each other: unrolled, no branches between them)
+        unsigned near = 0u;
+#if HBP_UNROLL_NEAR
+#pragma unroll
+#else
 #pragma unroll 1
-        for (int g = 0; g < c_sc.hu.n_gp; ++g) {
-            __syncwarp();
+#endif
+        for (int g = 0; g < 8; ++g) {
+            if (g >= c_sc.hu.n_gp) continue;
             const int fa = c_sc.hu.gp_fa[g], fb = c_sc.hu.gp_fb[g];
             const int fia = hbp_frame_index(fa);
             const V3 a0 = get(nas + 2 * fia), a1 = get(nas + 2 * fia + 1);
@@ -326,9 +353,17 @@ __global__ void __launch_bounds__(HBP_THREADS) human_brake_plan_kernel(HumanArgs
                 const float l = ra + rb + safety * (1.0f + 1e-5f) + 1e-5f;
                 near_g = segment_dist2(a0, a1, b0, b1) <= l * l;
             }
-            if (!(near_g && valid)) continue;
+            near |= (near_g ? 1u : 0u) << g;
+        }
+        if (!valid) near = 0u;
+#pragma unroll 1
+        for (int g = 0; g < c_sc.hu.n_gp; ++g) {
+            __syncwarp();
+            if (!((near >> g) & 1u)) continue;
+            const int fa = c_sc.hu.gp_fa[g], fb = c_sc.hu.gp_fb[g];
             const int sa0 = c_sc.hu.gp_a0[g], sa1 = sa0 + c_sc.hu.gp_na[g];
             const int sb0 = c_sc.hu.gp_b0[g], nb = c_sc.hu.gp_nb[g];
+            n_bounds += (unsigned)((sa1 - sa0) * nb);
 #pragma unroll 1
             for (int ia = sa0; ia < sa1; ++ia) {
                 const V3 ca = get(ia - soff);
@@ -377,6 +412,7 @@ __global__ void __launch_bounds__(HBP_THREADS) human_brake_plan_kernel(HumanArgs
             }
         }
     }
+    if (A.counters && n_bounds) atomicAdd(&A.counters[17], (unsigned long long)n_bounds);
 }
 
 // observation of the nested env (observations.py:313-351 with two arms and alternating target points): entries spread over
