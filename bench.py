@@ -323,6 +323,9 @@ def main():
                 extra[name] = {k: r[k] for k in ("value", "ms_per_step", "workload", "gpu_launches", "roofline")}
                 extra[name]["launch"] = r["config"]["launch"]
                 extra[name]["e2e"] = r["e2e"]
+    pin = None
+    if rank == 0 and world == 1 and not args.no_scenes:
+        pin = behavioural_pin(dev)
     if rank == 0:
         out = {"impl": "b200", "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world,
                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": main["ms_per_step"],
@@ -330,11 +333,37 @@ def main():
                "dtype": "f64 joint space / f32 geometry", "data": "synthetic", "config": main["config"],
                "clocks": main["clocks"], "e2e": main["e2e"], "gpu_launches": main["gpu_launches"],
                "roofline": main["roofline"], "cpu_baseline": main["cpu_baseline"], "episode_stats": main["episode_stats"],
-               "scenes": extra}
+               "scenes": extra, "behavioural_pin": pin}
         _emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def behavioural_pin(dev, envs=16384, steps=60):
+    """The only reference-held artefacts that can pin the restated env are the shipped network weights:
+    the backup policy, trained in the real PyBullet env, must keep far more 20-step episodes collision free in THIS env
+    than random actions do.  Collision-termination rate per finished episode, scenes with the robot of the checkpoints."""
+    from safemotionsrisk_b200.vec_env import SafeMotionsVecEnv
+    out = {"what": "collision terminations per finished episode over {} steps of {} envs from pool starts: shipped backup "
+                   "policy (deterministic mean action, tensor cores) vs uniform random actions".format(steps, envs)}
+    for name in ("space_bm", "ball_bm"):
+        rates = {}
+        for mode in ("backup_policy", "random_actions"):
+            env = SafeMotionsVecEnv(num_envs=envs, device=dev, seed=11, auto_reset=True, config=scene_config(name))
+            env.load_networks()
+            env.reset()
+            env.stats.zero_()
+            for _ in range(steps):
+                if mode == "backup_policy":
+                    env.step(env.backup_policy_actions())
+                else:
+                    env.step_random()
+            st = env.episode_statistics().cpu().numpy()
+            rates[mode] = float((st[3 + 3] + st[3 + 4] + st[3 + 5]) / max(st[0], 1))
+            env.close()
+        out[name] = rates
+    return out
 
 
 def measure_fma_peaks(device_index):

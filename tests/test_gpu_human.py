@@ -159,3 +159,59 @@ def test_human_policy_head_and_auto_reset():
     s = env.episode_statistics().cpu().numpy()
     assert s[0] >= n
     env.close()
+
+
+def test_human_golden_rollout():
+    """Committed oracle vectors of the Human scene (tests/golden/human.npz): same start states, robot actions and human
+    actions through the CUDA step.  Joint space bit-exact; an env whose braking decision or collision flag sits on a
+    float32 knife edge leaves the comparison (counted)."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "human.npz"))
+    n = g["q"].shape[0]
+    env = make_env(n)
+    env.set_human_actions_external(True)
+    env.set_state(g["q"], g["v"], g["a"], np.zeros((n, 16)))
+    env.set_human_state(g["hq"], g["hv"], g["ha"], g["first_target"], g["arm"])
+    torch.cuda.synchronize()
+    assert np.array_equal(env.kin.cpu().numpy(), g["kin0"]) and np.array_equal(env.hkin.cpu().numpy(), g["hkin0"])
+    assert np.abs(env.obs.cpu().numpy() - g["obs0"]).max() < 1e-6 and np.abs(env.hobs.cpu().numpy() - g["hobs0"]).max() < 1e-6
+    k0 = env.hstate.cpu().numpy()[:, abi.HS_BRAKE_COUNT].astype(int)
+    assert np.array_equal(k0, g["hstate0"][:, abi.HS_BRAKE_COUNT].astype(int))
+    for e in range(n):
+        assert np.array_equal(env.hbrake.cpu().numpy().reshape(n, -1, 8)[e, :k0[e]], g["hbrake0"].reshape(n, -1, 8)[e, :k0[e]])
+    alive = np.ones(n, dtype=bool)
+    same_h = np.ones(n, dtype=bool)
+    dropped = 0
+    for s in range(g["actions"].shape[0]):
+        env.hactions.copy_(torch.from_numpy(g["hactions"][s]))
+        obs, rew, done, info = env.step(g["actions"][s])
+        torch.cuda.synchronize()
+        hs, hk = env.hstate.cpu().numpy(), env.hkin.cpu().numpy()
+        flip = same_h & ((hs[:, abi.HS_BRAKED] != 0) != (g["out_hinfo"][s][:, 0] != 0))
+        flip |= same_h & (hs[:, [abi.TP_ACTIVE, 12 + abi.TP_ACTIVE]] != g["out_hstate"][s][:, [abi.TP_ACTIVE, 12 + abi.TP_ACTIVE]]).any(1)
+        dropped += int(flip.sum())
+        same_h &= ~flip
+        assert np.array_equal(hk[same_h], g["out_hkin"][s][same_h]), "human joint trajectory, step {}".format(s)
+        assert np.array_equal(hs[same_h, abi.HS_BRAKE_COUNT], g["out_hstate"][s][same_h, abi.HS_BRAKE_COUNT])
+        hb, hb_ref = env.hbrake.cpu().numpy().reshape(n, -1, 8), g["out_hbrake"][s].reshape(n, -1, 8)
+        for e in np.where(same_h)[0]:    # only the first `count` rows of the stored braking trajectory are defined
+            k = int(hs[e, abi.HS_BRAKE_COUNT])
+            assert np.array_equal(hb[e, :k], hb_ref[e, :k]), "stored braking trajectory, env {} step {}".format(e, s)
+        assert np.abs(env.hobs.cpu().numpy()[same_h] - g["out_hobs"][s][same_h]).max() < 1e-5
+        assert np.array_equal(env.kin.cpu().numpy()[alive], g["out_kin"][s][alive]), "robot joint trajectory"
+        ok = alive & same_h
+        o_info = g["out_info"][s]
+        d_dev, d_ref = info.cpu().numpy()[:, :3], o_info[:, :3].copy()
+        d_ref[(d_ref[:, 1] > 0.05) & (d_ref[:, 1] <= 0.102), 1] = 0.102   # reporting rule of the self class
+        flags_equal = (info.cpu().numpy()[:, 3:6] == o_info[:, 3:6]).all(1) & (done.cpu().numpy() == g["out_done"][s])
+        dropped += int((ok & ~flags_equal).sum())
+        alive &= flags_equal | ~ok
+        ok = alive & same_h
+        if ok.any():
+            assert np.abs(d_dev - d_ref)[ok].max() < 1e-4, "distances"
+            assert np.allclose(rew.cpu().numpy()[ok], g["out_reward"][s][ok], rtol=1e-4, atol=1e-4), "reward"
+            assert np.abs(obs.cpu().numpy()[ok] - g["out_obs"][s][ok]).max() < 1e-5, "observation"
+            assert np.array_equal(env.term_reason.cpu().numpy()[ok], g["out_term"][s][ok])
+        alive &= g["out_done"][s] == 0
+        same_h &= g["out_done"][s] == 0
+    assert dropped <= 2, "knife-edge drops: {}".format(dropped)
+    env.close()

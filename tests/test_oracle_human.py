@@ -141,3 +141,23 @@ def test_human_contact_terminates_the_episode(scene):
     ds, dse, dm = None, None, None
     env.step_human(np.zeros((1, 7), dtype=np.float32), np.zeros((1, 8), dtype=np.float32), None)
     assert env.info[0, abi.INFO["d_moving"]] < 0.2
+
+
+def test_oracle_reproduces_human_golden_vectors(scene):
+    """tests/golden/human.npz (make_golden.py record_human): regression vectors of the oracle for BASELINE.json configs[2]."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "human.npz"))
+    n = g["q"].shape[0]
+    env = oracle.OracleEnvs(scene, n)
+    env.set_state(g["q"], g["v"], g["a"], np.zeros((n, 16)))
+    env.set_human_state(g["hq"], g["hv"], g["ha"], g["first_target"], g["arm"])
+    assert np.array_equal(env.kin, g["kin0"]) and np.array_equal(env.hkin, g["hkin0"])
+    assert np.array_equal(env.obs, g["obs0"]) and np.array_equal(env.hobs, g["hobs0"])
+    assert np.array_equal(env.hstate, g["hstate0"], equal_nan=True) and np.array_equal(env.hbrake, g["hbrake0"])
+    for s in range(g["actions"].shape[0]):
+        env.step_human(g["actions"][s], g["hactions"][s], g["next_targets"][s])
+        for key, arr in (("kin", env.kin), ("hkin", env.hkin), ("hbrake", env.hbrake), ("obs", env.obs), ("hobs", env.hobs),
+                         ("reward", env.reward), ("done", env.done), ("term", env.term), ("hinfo", env.hinfo)):
+            assert np.array_equal(arr, g["out_" + key][s]), (key, s)
+        assert np.array_equal(env.hstate, g["out_hstate"][s], equal_nan=True)
+    assert (g["out_hinfo"][:, :, 0] != 0).any() and (g["out_done"] != 0).any()   # the vectors hold braking steps and terminations
