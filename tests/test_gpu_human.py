@@ -215,3 +215,41 @@ def test_human_golden_rollout():
         same_h &= g["out_done"][s] == 0
     assert dropped <= 2, "knife-edge drops: {}".format(dropped)
     env.close()
+
+
+def test_human_full_size_invariants():
+    """BASELINE.json configs[2] at its full size (65 536 envs): size-independent properties of the nested env and of the
+    main env over auto-reset steps with the human's policy in the loop."""
+    n = 65536
+    env = make_env(n, seed=1, auto_reset=True)
+    sc = env.scene
+    env.reset()
+    hlo, hhi, hV, hA = (torch.tensor(x, device=env.device) for x in (sc.human_pos_lo, sc.human_pos_hi, sc.human_vel_max,
+                                                                     sc.human_acc_max))
+    lo, hi, V = (torch.tensor(x, device=env.device) for x in (sc.pos_lo, sc.pos_hi, sc.vel_max))
+    total_done, braked = 0, 0
+    for s in range(35):
+        obs, rew, done, info = env.step_random()
+        hq, hv, ha = env.hkin[:, 0:8], env.hkin[:, 8:16], env.hkin[:, 16:24]
+        # position limits: kept by the safe range, except while an env executes the INITIAL braking trajectory of its
+        # reset -- the reference computes that one without advancing the position along it (ctlp.py:1120-1139, restated
+        # as is), so a start state close to a limit overshoots it by a few mrad (measured: 2 - 4 of 65 536 envs, <= 7 mrad)
+        over = (torch.clamp(hq - hhi, min=0) + torch.clamp(hlo - hq, min=0)).max(1).values
+        assert int((over > 1e-6).sum()) <= n // 4096 and float(over.max()) < 0.02, "human joint positions inside their limits"
+        assert bool((hv.abs() <= hV * (1 + 1e-9)).all()) and bool((ha.abs() <= hA * (1 + 1e-12)).all())
+        q, v = env.kin[:, 0:7], env.kin[:, 8:15]
+        assert bool(((q >= lo - 1e-6) & (q <= hi + 1e-6)).all()) and bool((v.abs() <= V * (1 + 1e-9)).all())
+        assert bool((obs.abs() <= 1).all()) and bool((env.hobs.abs() <= 1).all()) and bool(torch.isfinite(rew).all())
+        assert bool((env.hactions.abs() <= 1).all())
+        hs = env.hstate
+        assert bool(((hs[:, abi.TP_ACTIVE] != 0).int() + (hs[:, 12 + abi.TP_ACTIVE] != 0).int() == 1).all())   # one active target
+        assert bool((hs[:, abi.HS_BRAKE_COUNT] >= 0).all()) and bool((hs[:, abi.HS_BRAKE_COUNT] <= abi.SM_HBRAKE_STEPS).all())
+        assert bool(torch.equal(obs[:, 21:], env.hobs[:, :24]))       # the human's kinematic observation inside the main obs
+        assert bool((info[:, I["episode_length"]] <= 30).all())
+        braked += int((hs[:, abi.HS_BRAKED] != 0).sum())
+        total_done += int((done > 0).sum())
+    assert total_done > n                         # 30-step episodes: every env finished at least once
+    assert 0 < braked < 35 * n // 2               # the braking-trajectory method intervenes, but not most of the time
+    stats = env.episode_statistics().cpu().numpy()
+    assert stats[0] == total_done
+    env.close()

@@ -873,3 +873,41 @@ def test_episode_aggregates_match_host_accumulation():
         assert x["episode_length"] <= 20 and "collision_rate_moving_obstacles_average" in x["episode"]
         assert x["trajectory_successful"] == 1.0 and "moving_object_hit_robot_total" in x
     env.close()
+
+
+@pytest.mark.parametrize("variant", ["no_table", "planet_obs_1"])
+def test_scene_variants_match_oracle(variant):
+    """Config switches outside the two shipped scenes: obstacle_scene = 0 (no table, ctlp.py:2426-2434) and one
+    observation entry per planet (observations.py:258-292).  (A single planet / independent planets raise in scene.py.)"""
+    cfg = {"no_table": dict(obstacle_scene=0), "planet_obs_1": dict(obs_planet_size_per_planet=1)}[variant]
+    n = 96
+    env = make_env("space", n, seed=5, cfg=cfg)
+    sc = env.scene.struct
+    if variant == "no_table":
+        assert sc.has_table == 0
+    if variant == "planet_obs_1":
+        assert sc.obs_planet_size == 1 and sc.obs_size == 22
+    start, _ = env.pools()
+    q, v, a, ob = start[:n, 0:7], start[:n, 8:15], start[:n, 16:23], start[:n, 32:48]
+    env.set_state(q, v, a, ob)
+    orc = oracle.OracleEnvs(env.scene, n)
+    orc.set_state(q, v, a, ob)
+    assert np.array_equal(env.obs.cpu().numpy(), orc.obs)
+    rng = np.random.default_rng(9)
+    alive = np.ones(n, dtype=bool)
+    mism = 0
+    for s in range(8):
+        act = rng.uniform(-1, 1, (n, 7)).astype(np.float32)
+        obs, rew, done, info = env.step(act)
+        torch.cuda.synchronize()
+        o_obs, o_rew, o_done, o_term, o_info = orc.step(act)
+        assert np.array_equal(env.kin.cpu().numpy()[alive], orc.kin[alive])
+        assert np.abs(info.cpu().numpy()[:, :3] - reported(o_info[:, :3]))[alive].max() < 1e-4
+        same = (done.cpu().numpy() == o_done) & (info.cpu().numpy()[:, 3:6] == o_info[:, 3:6]).all(1)
+        mism += int((~same & alive).sum())
+        alive &= same
+        assert np.allclose(rew.cpu().numpy()[alive], o_rew[alive], rtol=1e-4, atol=1e-4)
+        assert np.array_equal(obs.cpu().numpy()[alive], o_obs[alive])
+        alive &= o_done == 0
+    assert mism <= 1
+    env.close()
