@@ -201,6 +201,7 @@ struct SmEnv {
     cudaEvent_t chunk_fork = nullptr;
     cudaStream_t side_streams[8] = {};   // contact planning next to the distance planning, per env range
     cudaEvent_t side_fork[8] = {}, side_join[8] = {};
+    cudaEvent_t joint_fork[8] = {}, joint_join[8] = {};   // Human scene: the robot's joint kernels next to the nested env
     cudaStream_t host_stream = nullptr;  // origin stream of the host-step graph
     cudaEvent_t host_order = nullptr;
     cudaGraphExec_t host_graph = nullptr;
@@ -212,6 +213,9 @@ struct SmEnv {
     int* d_cwork = nullptr;      // [0] = count, [1..8n] = spans (env * 8 + span) the coarse contact phase could not clear
     int* d_tasks = nullptr;      // [0] = count, [1..16n] = position bounds to solve (joint_solve_kernel)
     double* d_hpar = nullptr;    // [8n][SM_HPAR] hand-over records of the deferred joints
+    int* d_hheavy = nullptr;     // Human scene: the same three lists for the human's joints (its joint kernels run next to
+    int* d_htasks = nullptr;     // the robot's)
+    double* d_hhpar = nullptr;
     bool count = false;
     size_t smem_bytes = 0;        // kernels that stage the hull vertices
     size_t smem_bytes_broad = 0;  // contact_broad_kernel: scene tables only
@@ -866,9 +870,18 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
         CU(cudaStreamCreateWithFlags(&env->side_streams[c], cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&env->side_fork[c], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&env->side_join[c], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&env->joint_fork[c], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&env->joint_join[c], cudaEventDisableTiming));
     }
     CU(cudaMalloc((void**)&env->d_heavy, ((size_t)num_envs * 8 + 8) * sizeof(int)));
     CU(cudaMemset(env->d_heavy, 0, ((size_t)num_envs * 8 + 8) * sizeof(int)));
+    if (sc->human.enabled) {
+        CU(cudaMalloc((void**)&env->d_hheavy, ((size_t)num_envs * 8 + 8) * sizeof(int)));
+        CU(cudaMemset(env->d_hheavy, 0, ((size_t)num_envs * 8 + 8) * sizeof(int)));
+        CU(cudaMalloc((void**)&env->d_htasks, ((size_t)num_envs * 16 + 8) * sizeof(int)));
+        CU(cudaMemset(env->d_htasks, 0, ((size_t)num_envs * 16 + 8) * sizeof(int)));
+        CU(cudaMalloc((void**)&env->d_hhpar, (size_t)num_envs * 8 * SM_HPAR * sizeof(double)));
+    }
     CU(cudaMalloc((void**)&env->d_counters, 24 * sizeof(unsigned long long)));
     CU(cudaMemset(env->d_counters, 0, 24 * sizeof(unsigned long long)));
 
@@ -973,7 +986,7 @@ extern "C" int smenv_destroy(SmEnv* env) {
         if (active == env) { cudaDeviceSynchronize(); active = nullptr; }
     }
     cudaFree(env->d_verts); cudaFree(env->d_lut); cudaFree(env->d_hwidth); cudaFree(env->d_scene_img); cudaFree(env->d_plocal); cudaFree(env->d_start_pool); cudaFree(env->d_ball_pool); cudaFree(env->d_target_pool);
-    cudaFree(env->d_counters); cudaFree(env->d_scratch); cudaFree(env->d_worklist); cudaFree(env->d_heavy); cudaFree(env->d_cwork); cudaFree(env->d_tasks); cudaFree(env->d_hpar); cudaFree(env->d_items); cudaFree(env->d_res);
+    cudaFree(env->d_counters); cudaFree(env->d_scratch); cudaFree(env->d_worklist); cudaFree(env->d_heavy); cudaFree(env->d_cwork); cudaFree(env->d_tasks); cudaFree(env->d_hpar); cudaFree(env->d_hheavy); cudaFree(env->d_htasks); cudaFree(env->d_hhpar); cudaFree(env->d_items); cudaFree(env->d_res);
     if (env->h_flag) cudaFreeHost(env->h_flag);
     for (void* q : env->net_allocs) cudaFree(q);
     cudaFree(env->d_risk); cudaFree(env->d_backup); cudaFree(env->d_exec); cudaFree(env->d_risky); cudaFree(env->d_gate_list);
@@ -989,6 +1002,8 @@ extern "C" int smenv_destroy(SmEnv* env) {
         if (env->side_streams[c]) cudaStreamDestroy(env->side_streams[c]);
         if (env->side_fork[c]) cudaEventDestroy(env->side_fork[c]);
         if (env->side_join[c]) cudaEventDestroy(env->side_join[c]);
+        if (env->joint_fork[c]) cudaEventDestroy(env->joint_fork[c]);
+        if (env->joint_join[c]) cudaEventDestroy(env->joint_join[c]);
     }
     if (env->host_graph) cudaGraphExecDestroy(env->host_graph);
     if (env->host_order) cudaEventDestroy(env->host_order);
@@ -1421,6 +1436,7 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
     JA.track_vel = env->host_scene.track_vel; JA.store_qset = env->host_scene.use_target_points;
     JA.keep_overflow = env->human ? 1 : 0;
     JA.clear_extra = nullptr;
+    if (env->human) JA.worklist = nullptr;   // the nested env's kernels clear the counters (its braking check emits items first)
     const bool gate = env->gate_threshold >= 0.0f;
     if (gate) {   // actions.py:303-340: rate the proposed action, execute the backup policy's where it is risky
         if (!buf->obs) return fail(SM_ERR_ARG, "smenv_step: the risk gate needs the observation buffer");
@@ -1449,6 +1465,25 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
                                              cudaGetErrorString(e_));                                        \
         }                                                                                                    \
     } while (0)
+    auto robot_joint_heavy = [&](cudaStream_t st) {   // the lists are at most 8 m / 16 m long; blocks beyond their length exit at once
+        int hb = (m * 8 + SM_HEAVY_THREADS - 1) / SM_HEAVY_THREADS;
+        if (hb > 8 * env->sms) hb = 8 * env->sms;
+        joint_first_kernel<<<hb, SM_HEAVY_THREADS, 0, st>>>(JA);
+        joint_solve_kernel<<<16 * env->sms, SM_HEAVY_THREADS, 0, st>>>(JA);  // warps take chunks of the task list
+        joint_final_kernel<<<hb, SM_HEAVY_THREADS, 0, st>>>(JA);
+    };
+    // Human scene: the robot's joint kernels do not depend on the nested env; outside the measurement modes they run on
+    // the range's side stream next to the human's policy / range / braking check (latency-bound kernels that leave most
+    // of the SMs' issue slots free) and join before the planning kernels
+    static const bool no_joint_fork = getenv("SMENV_NO_JOINT_FORK") != nullptr;
+    const bool joints_aside = env->human && !tk && !dbg_sync && !no_joint_fork;
+    cudaStream_t jstream = env->side_streams[chunk];
+    if (joints_aside) {
+        CU(cudaEventRecord(env->joint_fork[chunk], stream));
+        CU(cudaStreamWaitEvent(jstream, env->joint_fork[chunk], 0));
+        joint_kernel<<<(m * 8 + 255) / 256, 256, 0, jstream>>>(JA);
+        robot_joint_heavy(jstream);
+    }
     HumanArgs HA;
     memset(&HA, 0, sizeof(HA));
     if (!env->human && tk)
@@ -1492,13 +1527,18 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
         JH.track_vel = 0.87; JH.store_qset = 1; JH.keep_overflow = 0;
         JH.scratch = HA.hscratch;
         JH.clear_extra = HA.units;
+        JH.worklist = worklist;
+        JH.heavy = env->d_hheavy + (size_t)e0 * 8 + chunk;
+        JH.tasks = env->d_htasks + (size_t)e0 * 16 + chunk;
+        JH.hpar = env->d_hhpar + (size_t)e0 * 8 * SM_HPAR;
+        JH.cwork = nullptr;
         const int hb = std::min((m * 8 + SM_HEAVY_THREADS - 1) / SM_HEAVY_THREADS, 8 * env->sms);
         SM_MARK(SM_K_HUMAN_JOINT);
         joint_kernel<<<(m * 8 + 255) / 256, 256, 0, stream>>>(JH);
         joint_first_kernel<<<hb, SM_HEAVY_THREADS, 0, stream>>>(JH);
         joint_solve_kernel<<<16 * env->sms, SM_HEAVY_THREADS, 0, stream>>>(JH);
         joint_final_kernel<<<hb, SM_HEAVY_THREADS, 0, stream>>>(JH);
-        CU(cudaMemsetAsync(heavy, 0, sizeof(int), stream));   // the robot's pass reuses the deferred-joint list
+        CU(cudaMemsetAsync(JH.heavy, 0, sizeof(int), stream));   // the human's deferred-joint list is empty for the next step
         SM_MARK(SM_K_HUMAN_BRAKE_TRAJ);
         human_brake_traj_kernel<<<(m * 8 + 127) / 128, 128, 0, stream>>>(HA);
         env->launches += 5;
@@ -1512,20 +1552,20 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
             env->launches += 2;
         }
         else SM_MARK(SM_K_HUMAN_BRAKE_GJK);
+        CU(cudaMemsetAsync(worklist, 0, sizeof(int), stream));   // the items of the braking check are consumed
         SM_MARK(SM_K_HUMAN_ADVANCE);
         human_advance_kernel<<<(m * 8 + 255) / 256, 256, 0, stream>>>(HA);
         env->launches++;
         CU(cudaGetLastError());
     }
-    SM_MARK(SM_K_JOINT);
-    joint_kernel<<<(m * 8 + 255) / 256, 256, 0, stream>>>(JA);
-    SM_MARK(SM_K_JOINT_HEAVY);
-    {   // the lists are at most 8 m / 16 m long; blocks beyond their length exit at once
-        int hb = (m * 8 + SM_HEAVY_THREADS - 1) / SM_HEAVY_THREADS;
-        if (hb > 8 * env->sms) hb = 8 * env->sms;
-        joint_first_kernel<<<hb, SM_HEAVY_THREADS, 0, stream>>>(JA);
-        joint_solve_kernel<<<16 * env->sms, SM_HEAVY_THREADS, 0, stream>>>(JA);  // warps take chunks of the task list
-        joint_final_kernel<<<hb, SM_HEAVY_THREADS, 0, stream>>>(JA);
+    if (joints_aside) {   // the robot's joints are done before the planning kernels read its sub-step poses
+        CU(cudaEventRecord(env->joint_join[chunk], jstream));
+        CU(cudaStreamWaitEvent(stream, env->joint_join[chunk], 0));
+    } else {
+        SM_MARK(SM_K_JOINT);
+        joint_kernel<<<(m * 8 + 255) / 256, 256, 0, stream>>>(JA);
+        SM_MARK(SM_K_JOINT_HEAVY);
+        robot_joint_heavy(stream);
     }
     env->launches += 4;
     PlanArgs P;
@@ -1617,6 +1657,9 @@ static int set_list_layout(SmEnv* env, int chunks, cudaStream_t stream) {
     const int per = (env->n + chunks - 1) / chunks;
     for (int c = 0; c < chunks && c * per < env->n; ++c)
         CU(cudaMemsetAsync(env->d_heavy + (size_t)c * per * 8 + c, 0, sizeof(int), stream));
+    if (env->d_hheavy)
+        for (int c = 0; c < chunks && c * per < env->n; ++c)
+            CU(cudaMemsetAsync(env->d_hheavy + (size_t)c * per * 8 + c, 0, sizeof(int), stream));
     env->list_layout = chunks;
     return SM_OK;
 }
