@@ -171,17 +171,17 @@ __global__ void __launch_bounds__(128) human_brake_traj_kernel(HumanArgs A) {
         }
         if (__all_sync(FULL, done)) break;
     }
+    const int npc = valid ? (np < SM_HBRAKE_POSES ? np : SM_HBRAKE_POSES) : 0;   // the same in the eight lanes of the env
+    int base = 0;
     if (valid && j == 0) {
         int* bi = A.binfo + env * 4;
-        const int npc = np < SM_HBRAKE_POSES ? np : SM_HBRAKE_POSES;
         bi[0] = k; bi[1] = npc; bi[2] = timeout; bi[3] = 0;
         A.res[env * SM_RES_STRIDE + GJK_BRAKE] = SM_RES_NO_CONTACT;
         if (A.counters && npc > 0) atomicAdd(&A.counters[16], (unsigned long long)npc);
-        if (npc > 0) {   // one unit per pose for the geometry pass
-            const int base = atomicAdd(A.units, npc);
-            for (int p = 0; p < npc; ++p) A.units[1 + base + p] = ((int)env << 7) | p;
-        }
+        if (npc > 0) base = atomicAdd(A.units, npc);
     }
+    base = __shfl_sync(FULL, base, lane & 24);
+    for (int p = j; p < npc; p += 8) A.units[1 + base + p] = ((int)env << 7) | p;   // one unit per pose for the geometry pass
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -765,38 +765,46 @@ __global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) hcontact_plan_kernel(
 // start of an episode of the nested env: from the pool (reset / auto reset: envs with `done` set, or masked) or injected
 // (parity protocol).  One thread per env.
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void human_episode_start(double* hk, double* hs, double* hb, float* hobs, const double* q,
-                                                    const double* v, const double* a, const double* first_target,
-                                                    int active_arm, double draws) {
-    const double dt = xdiv(c_sc.ts, (double)c_sc.substeps), tvdt = xmul(0.87, dt);
-    float qf[SM_HUMAN_JOINTS];
-    for (int j = 0; j < 8; ++j) {
-        hk[j] = q[j]; hk[8 + j] = v[j]; hk[16 + j] = a[j];
-        hk[24 + j] = xadd(q[j], xmul(tvdt, v[j]));   // as the robot: one stepSimulation with the start state as target
-        qf[j] = (float)q[j];
+// The eight lanes of an env (sl = lane & 7) start its nested episode together: lane j copies joint j, lanes 0 / 1 take the
+// link point of arm 0 / 1, lane `active_arm` sets up the first target point, then every lane writes its share of the
+// observation.  All eight lanes call (inactive groups skip the stores).
+__device__ __forceinline__ void human_episode_start(bool active, int sl, unsigned gmask, double* hk, double* hs, double* hb,
+                                                    float* hobs, const double* q, const double* v, const double* a,
+                                                    const double* first_target, int active_arm, double draws) {
+    (void)hb;   // the stored braking trajectory is empty (count 0) or set by the caller: nothing to clear
+    if (active) {
+        const double dt = xdiv(c_sc.ts, (double)c_sc.substeps), tvdt = xmul(0.87, dt);
+        hk[sl] = q[sl]; hk[8 + sl] = v[sl]; hk[16 + sl] = a[sl];
+        hk[24 + sl] = xadd(q[sl], xmul(tvdt, v[sl]));   // as the robot: one stepSimulation with the start state as target
+#pragma unroll
+        for (int i = sl; i < SM_HSTATE_STRIDE; i += 8) hs[i] = 0.0;
     }
-    for (int i = 0; i < SM_HSTATE_STRIDE; ++i) hs[i] = 0.0;
-    Xf fr[SM_MAX_OBST_FRAMES];
-    human_fk_serial(qf, fr);
-    for (int r = 0; r < 2; ++r) {
-        const V3 p = human_link_point(fr, r);
-        hs[12 * r + SM_TP_LINK_POS] = (double)p.x; hs[12 * r + SM_TP_LINK_POS + 1] = (double)p.y; hs[12 * r + SM_TP_LINK_POS + 2] = (double)p.z;
+    __syncwarp(gmask);
+    if (active && sl < 2) {   // link point of arm sl
+        Xf F;
+        human_base(F);
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) human_chain_step(F, 4 * sl + i, (float)q[4 * sl + i]);
+        const V3 p = xf_apply(F, c_sc.hu.tp_local[sl][0], c_sc.hu.tp_local[sl][1], c_sc.hu.tp_local[sl][2]);
+        double* tp = hs + 12 * sl;
+        tp[SM_TP_LINK_POS] = (double)p.x; tp[SM_TP_LINK_POS + 1] = (double)p.y; tp[SM_TP_LINK_POS + 2] = (double)p.z;
+        if (sl == active_arm) {
+            tp[SM_TP_POS] = first_target[0]; tp[SM_TP_POS + 1] = first_target[1]; tp[SM_TP_POS + 2] = first_target[2];
+            tp[SM_TP_ACTIVE] = 1.0;
+            const double dx = tp[SM_TP_POS] - tp[SM_TP_LINK_POS], dy = tp[SM_TP_POS + 1] - tp[SM_TP_LINK_POS + 1],
+                         dz = tp[SM_TP_POS + 2] - tp[SM_TP_LINK_POS + 2];
+            tp[SM_TP_LAST_DIST] = tp[SM_TP_INIT_DIST] = sqrt(dx * dx + dy * dy + dz * dz);
+        }
     }
-    double* tp = hs + 12 * active_arm;
-    tp[SM_TP_POS] = first_target[0]; tp[SM_TP_POS + 1] = first_target[1]; tp[SM_TP_POS + 2] = first_target[2];
-    tp[SM_TP_ACTIVE] = 1.0;
-    const double dx = tp[SM_TP_POS] - tp[SM_TP_LINK_POS], dy = tp[SM_TP_POS + 1] - tp[SM_TP_LINK_POS + 1],
-                 dz = tp[SM_TP_POS + 2] - tp[SM_TP_LINK_POS + 2];
-    tp[SM_TP_LAST_DIST] = tp[SM_TP_INIT_DIST] = sqrt(dx * dx + dy * dy + dz * dz);
-    hs[SM_HS_DRAWS] = draws;
-    (void)hb;   // the stored braking trajectory is empty (count 0): nothing to clear
-    write_human_observation(hobs, hk, hs, 0, 1);
+    if (active && sl == 2) hs[SM_HS_DRAWS] = draws;
+    __syncwarp(gmask);
+    if (active) write_human_observation(hobs, hk, hs, sl, 8);
 }
 
 // the human part of the main env's observation: Human.kinematic_observation (observations.py:100-110, :294-307)
-__device__ __forceinline__ void copy_human_kinematic_obs(float* obs, const float* hobs) {
+__device__ __forceinline__ void copy_human_kinematic_obs(float* obs, const float* hobs, int sl = 0, int stride = 1) {
     const int off = c_sc.obs_size - 3 * SM_HUMAN_JOINTS;
-    for (int i = 0; i < 3 * SM_HUMAN_JOINTS; ++i) obs[off + i] = hobs[i];
+    for (int i = sl; i < 3 * SM_HUMAN_JOINTS; i += stride) obs[off + i] = hobs[i];
 }
 
 // ObstacleWrapperBase.reset with compute_initial_braking_trajectory (ctlp.py:1120-1139): the stored braking trajectory
@@ -851,12 +859,12 @@ __global__ void __launch_bounds__(256) human_set_state_kernel(HumanArgs A, const
     const int env_raw = t >> 3;
     const bool active = env_raw < A.n && !(A.mask && !A.mask[env_raw]);
     const size_t env = env_raw < A.n ? (size_t)env_raw : (size_t)(A.n - 1);
-    if (active && j == 0) {
-        human_episode_start(A.buf.hkin + env * SM_KIN_STRIDE, A.buf.hstate + env * SM_HSTATE_STRIDE,
-                            A.buf.hbrake + env * SM_HBRAKE_STEPS * 8, A.buf.hobs + env * SM_HOBS_STRIDE, hq + env * 8,
-                            hv + env * 8, ha + env * 8, first_target + env * 3, active_arm ? active_arm[env] : 0, 1.0);
-        if (A.buf.obs) copy_human_kinematic_obs(A.buf.obs + env * c_sc.obs_size, A.buf.hobs + env * SM_HOBS_STRIDE);
-    }
+    const unsigned gmask = 0xffu << (lane & 24);
+    human_episode_start(active, j, gmask, A.buf.hkin + env * SM_KIN_STRIDE, A.buf.hstate + env * SM_HSTATE_STRIDE,
+                        A.buf.hbrake + env * SM_HBRAKE_STEPS * 8, A.buf.hobs + env * SM_HOBS_STRIDE, hq + env * 8,
+                        hv + env * 8, ha + env * 8, first_target + env * 3, active_arm ? active_arm[env] : 0, 1.0);
+    __syncwarp(gmask);
+    if (active && A.buf.obs) copy_human_kinematic_obs(A.buf.obs + env * c_sc.obs_size, A.buf.hobs + env * SM_HOBS_STRIDE, j, 8);
     __syncwarp();
     human_initial_braking(A.buf.hstate + env * SM_HSTATE_STRIDE, A.buf.hbrake + env * SM_HBRAKE_STEPS * 8, hq[env * 8 + j],
                           hv[env * 8 + j], ha[env * 8 + j], active, lane);
@@ -876,18 +884,21 @@ __global__ void __launch_bounds__(256) human_reset_kernel(HumanArgs A, int by_do
     const int4 ep = *reinterpret_cast<const int4*>(A.buf.episode + 4 * env);
     const uint4 r = philox((uint32_t)(env + A.env_base), (uint32_t)(ep.y - 1), 0x5E7u, 1u, A.k0, A.k1);   // the robot's draw
     const double* e = A.start_pool + (size_t)(r.x % (uint32_t)(A.start_pool_n > 0 ? A.start_pool_n : 1)) * SM_HPOOL_STRIDE;
-    if (active && j == 0) {
+    {
+        const unsigned gmask = 0xffu << (lane & 24);
         const uint4 r2 = philox((uint32_t)(env + A.env_base), (uint32_t)(ep.y - 1), 0x5E8u, 4u, A.k0, A.k1);
         const int arm = (int)(r2.x & 1u);                          // np.random.randint(0, num_robots) (ctlp.py:1037-1038)
         double ft[3] = {0.3, 0.0, 0.4};
-        if (A.target_pool_n > 0) {
+        if (active && A.target_pool_n > 0) {
             const double* tp = A.target_pool + ((size_t)arm * A.target_pool_n + (r2.y % (uint32_t)A.target_pool_n)) * 4;
             ft[0] = tp[0]; ft[1] = tp[1]; ft[2] = tp[2];
         }
-        human_episode_start(A.buf.hkin + env * SM_KIN_STRIDE, A.buf.hstate + env * SM_HSTATE_STRIDE,
+        human_episode_start(active, j, gmask, A.buf.hkin + env * SM_KIN_STRIDE, A.buf.hstate + env * SM_HSTATE_STRIDE,
                             A.buf.hbrake + env * SM_HBRAKE_STEPS * 8, A.buf.hobs + env * SM_HOBS_STRIDE, e, e + 8, e + 16, ft,
                             arm, 1.0);
-        if (A.buf.obs) copy_human_kinematic_obs(A.buf.obs + env * c_sc.obs_size, A.buf.hobs + env * SM_HOBS_STRIDE);
+        __syncwarp(gmask);
+        if (active && A.buf.obs)
+            copy_human_kinematic_obs(A.buf.obs + env * c_sc.obs_size, A.buf.hobs + env * SM_HOBS_STRIDE, j, 8);
     }
     __syncwarp();
     if (A.pool_brake) {   // the braking trajectory of a pool entry does not depend on the env: stored with the pool
