@@ -159,6 +159,8 @@ struct SmEnv {
     unsigned* d_res = nullptr;   // [n][SM_RES_STRIDE] distance keys / first contact sub-step
     int* h_flag = nullptr;       // mapped pinned host word set by finish_kernel when the item buffer overflowed
     int* d_flag = nullptr;       // its device alias
+    uint32_t* h_step = nullptr;  // pinned: the step counter of the host-buffer step; a captured copy node reads it at every
+    uint32_t* d_step = nullptr;  // replay of the graph (a kernel argument would be frozen at capture time)
     size_t smem_bytes_gjk = 0;
     int grid_gjk = 0;
     int gjk_threads = GJK_THREADS;   // 512 when only one CTA of the GJK kernel fits on an SM
@@ -860,6 +862,10 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
         CU(cudaHostAlloc((void**)&env->h_flag, sizeof(int), cudaHostAllocMapped));
         *env->h_flag = 0;
         CU(cudaHostGetDevicePointer((void**)&env->d_flag, env->h_flag, 0));
+        CU(cudaHostAlloc((void**)&env->h_step, sizeof(uint32_t), cudaHostAllocDefault));
+        *env->h_step = 0;
+        CU(cudaMalloc((void**)&env->d_step, sizeof(uint32_t)));
+        CU(cudaMemset(env->d_step, 0, sizeof(uint32_t)));
     }
     CU(cudaMalloc((void**)&env->d_tasks, ((size_t)num_envs * 16 + 8) * sizeof(int)));
     CU(cudaMemset(env->d_tasks, 0, ((size_t)num_envs * 16 + 8) * sizeof(int)));
@@ -988,6 +994,8 @@ extern "C" int smenv_destroy(SmEnv* env) {
     cudaFree(env->d_verts); cudaFree(env->d_lut); cudaFree(env->d_hwidth); cudaFree(env->d_scene_img); cudaFree(env->d_plocal); cudaFree(env->d_start_pool); cudaFree(env->d_ball_pool); cudaFree(env->d_target_pool);
     cudaFree(env->d_counters); cudaFree(env->d_scratch); cudaFree(env->d_worklist); cudaFree(env->d_heavy); cudaFree(env->d_cwork); cudaFree(env->d_tasks); cudaFree(env->d_hpar); cudaFree(env->d_hheavy); cudaFree(env->d_htasks); cudaFree(env->d_hhpar); cudaFree(env->d_items); cudaFree(env->d_res);
     if (env->h_flag) cudaFreeHost(env->h_flag);
+    if (env->h_step) cudaFreeHost(env->h_step);
+    cudaFree(env->d_step);
     for (void* q : env->net_allocs) cudaFree(q);
     cudaFree(env->d_risk); cudaFree(env->d_backup); cudaFree(env->d_exec); cudaFree(env->d_risky); cudaFree(env->d_gate_list);
     cudaFree(env->d_hpairs); cudaFree(env->d_hthresh); cudaFree(env->d_hrange); cudaFree(env->d_hbacc); cudaFree(env->d_hposes);
@@ -1407,7 +1415,7 @@ static void launch_gjk(SmEnv* env, const GjkArgs& G, cudaStream_t stream) {
 // of the whole env ([0] = count, [1..k n] = entries) holds the sub-lists of the ranges back to back, the range's
 // sub-list starting at entry k * e0 + chunk (its own count first).  Ranges in flight at once need distinct slots.
 static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chunk, int auto_reset, int random_actions,
-                      uint32_t step_counter, bool tk, cudaStream_t stream) {
+                      uint32_t step_counter, bool tk, cudaStream_t stream, const uint32_t* step_ptr = nullptr) {
     const SmBuffers buf_v = buffers_at(*full, e0, env->host_scene.n_joints, env->host_scene.obs_size);
     const SmBuffers* buf = &buf_v;
     const int per_env_items = env->item_capacity / env->n;
@@ -1494,6 +1502,7 @@ static int step_range(SmEnv* env, const SmBuffers* full, int e0, int m, int chun
             return fail(SM_ERR_ARG, "smenv_step: the Human scene needs the hkin / hstate / hbrake / hobs / hactions buffers");
         HA.buf = *buf; HA.n = m; HA.env_base = e0;
         HA.k0 = (uint32_t)env->seed; HA.k1 = (uint32_t)(env->seed >> 32); HA.step_counter = step_counter;
+        HA.step_ptr = step_ptr;   // host-buffer step: the counter lives in device memory (graph replays)
         HA.policy_out = env->d_hpolicy + (size_t)e0 * 16;
         HA.range = env->d_hrange + (size_t)e0 * 32;
         HA.bacc = env->d_hbacc + (size_t)e0 * SM_HBRAKE_STEPS * 8;
@@ -1750,6 +1759,8 @@ struct HostStepKey {
 static int host_step_enqueue(SmEnv* env, const SmBuffers* buf, const float* h_actions, float* h_obs, float* h_reward,
                              uint8_t* h_done, int auto_reset, int chunks, uint32_t counter, cudaStream_t origin) {
     const int nj = env->host_scene.n_joints, od = env->host_scene.obs_size;
+    // the step counter (Philox stream of the human's policy noise): copied from the pinned word the caller just set
+    CU(cudaMemcpyAsync(env->d_step, env->h_step, sizeof(uint32_t), cudaMemcpyHostToDevice, origin));
     CU(cudaEventRecord(env->chunk_fork, origin));
     const int per = (env->n + chunks - 1) / chunks;
     for (int c = 0; c < chunks; ++c) {
@@ -1757,9 +1768,18 @@ static int host_step_enqueue(SmEnv* env, const SmBuffers* buf, const float* h_ac
         if (m <= 0) break;
         cudaStream_t cs = env->chunk_streams[c];
         CU(cudaStreamWaitEvent(cs, env->chunk_fork, 0));
+        // Human scene without the gate: only the robot's joint kernels read the actions, and they run on the range's side
+        // stream (step_range): the copy goes there too, the nested env's chain starts without waiting for it
+        static const bool no_joint_fork = getenv("SMENV_NO_JOINT_FORK") != nullptr || getenv("SMENV_DEBUG_SYNC") != nullptr;
+        const bool copy_aside = env->human && env->gate_threshold < 0.0f && !no_joint_fork;
+        cudaStream_t hs = cs;
+        if (copy_aside) {
+            hs = env->side_streams[c];
+            CU(cudaStreamWaitEvent(hs, env->chunk_fork, 0));
+        }
         CU(cudaMemcpyAsync((float*)buf->actions + (size_t)e0 * nj, h_actions + (size_t)e0 * nj,
-                           (size_t)m * nj * sizeof(float), cudaMemcpyHostToDevice, cs));
-        int rc = step_range(env, buf, e0, m, c, auto_reset, 0, counter, false, cs);
+                           (size_t)m * nj * sizeof(float), cudaMemcpyHostToDevice, hs));
+        int rc = step_range(env, buf, e0, m, c, auto_reset, 0, counter, false, cs, env->d_step);
         if (rc) return rc;
         CU(cudaMemcpyAsync(h_obs + (size_t)e0 * od, buf->obs + (size_t)e0 * od, (size_t)m * od * sizeof(float),
                            cudaMemcpyDeviceToHost, cs));
@@ -1786,6 +1806,8 @@ extern "C" int smenv_step_host(SmEnv* env, const SmBuffers* buf, const float* h_
     rc = ensure_chunk_streams(env);
     if (rc) return rc;
     const uint32_t counter = env->step_counter++;
+    CU(cudaStreamSynchronize(env->host_stream));   // the previous host step has read the pinned counter word (it returned
+    *env->h_step = counter;                         // synchronised; a no-op in practice)
     rc = set_list_layout(env, chunks, stream);
     if (rc) return rc;
     // the internal origin stream comes after the work already queued on the caller's stream

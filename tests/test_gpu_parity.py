@@ -13,10 +13,10 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 from oracle import oracle  # noqa: E402
-from safemotionsrisk_b200 import abi, ball_backup_config, cabi, space_backup_config, space_task_config  # noqa: E402
+from safemotionsrisk_b200 import abi, ball_backup_config, cabi, human_backup_config, space_backup_config, space_task_config  # noqa: E402
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CONFIGS = {"space_task": lambda **k: space_task_config(**k),
+CONFIGS = {"space_task": lambda **k: space_task_config(**k), "human": lambda **k: human_backup_config(**k),
            "space": lambda **k: space_backup_config(**k), "ball": lambda **k: ball_backup_config(**k),
            "space_bm": lambda **k: space_backup_config(ball_machine_mode=True, **k),
            "ball_bm": lambda **k: ball_backup_config(ball_machine_mode=True, **k)}
@@ -621,7 +621,7 @@ def test_backup_look_ahead_labels_and_restores_the_state():
     env.close()
 
 
-@pytest.mark.parametrize("scene", ["ball", "space_bm", "space_task"])
+@pytest.mark.parametrize("scene", ["ball", "space_bm", "space_task", "human"])
 def test_host_step_in_ranges_equals_the_device_step(scene):
     """smenv_step_host cuts the envs into ranges on separate streams (copies overlap kernels); every range count gives
     bit-identical states, observations and rewards to the one-launch device step, including auto-resets and ball /
@@ -652,6 +652,8 @@ def test_host_step_in_ranges_equals_the_device_step(scene):
             for w, g in zip(want, got):
                 assert np.array_equal(w, g), (scene, c, step)
             assert torch.equal(e.kin, ref.kin) and torch.equal(e.obst, ref.obst) and torch.equal(e.episode, ref.episode)
+            if scene == "human":   # the nested env (its policy's Philox noise included) is independent of the ranges too
+                assert torch.equal(e.hkin, ref.hkin) and torch.equal(e.hactions, ref.hactions)
     assert ref.stats[0].item() > 0   # episodes ended and were reset on the way
     for e in list(envs.values()) + [mixed, ref]:
         e.close()
