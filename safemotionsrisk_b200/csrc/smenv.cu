@@ -207,7 +207,7 @@ struct SmEnv {
     cudaStream_t host_stream = nullptr;  // origin stream of the host-step graph
     cudaEvent_t host_order = nullptr;
     cudaGraphExec_t host_graph = nullptr;
-    unsigned char host_graph_key[sizeof(SmBuffers) + 4 * sizeof(void*) + 4 * sizeof(int) + 16] = {};
+    unsigned char host_graph_key[sizeof(SmBuffers) + 4 * sizeof(void*) + 8 * sizeof(int) + 32] = {};
     int host_graph_kernels = 0;
     int step_ranges = 1;         // env ranges the device step runs side by side (smenv_set_step_ranges)
     int list_layout = 1;         // number of env ranges of the last step (where the counts of the work lists sit)
@@ -1752,8 +1752,8 @@ static int step_impl(SmEnv* env, const SmBuffers* buf, int auto_reset, int rando
 struct HostStepKey {
     SmBuffers buf;
     const void* h[4];
-    int auto_reset, chunks, count, pools;
-    float gate;
+    int auto_reset, chunks, count, pools, human_external, gate_exact;
+    float gate, gate_band;
 };
 
 static int host_step_enqueue(SmEnv* env, const SmBuffers* buf, const float* h_actions, float* h_obs, float* h_reward,
@@ -1826,6 +1826,7 @@ extern "C" int smenv_step_host(SmEnv* env, const SmBuffers* buf, const float* h_
     key.buf = *buf;
     key.h[0] = h_actions; key.h[1] = h_obs; key.h[2] = h_reward; key.h[3] = h_done;
     key.auto_reset = auto_reset; key.chunks = chunks; key.count = env->count ? 1 : 0; key.pools = env->pools_filled ? 1 : 0; key.gate = env->gate_threshold;
+    key.human_external = env->human_external ? 1 : 0; key.gate_exact = env->gate_exact ? 1 : 0; key.gate_band = env->gate_band;
     if (!env->host_graph || memcmp(&key, env->host_graph_key, sizeof(key)) != 0) {
         if (env->host_graph) { cudaGraphExecDestroy(env->host_graph); env->host_graph = nullptr; }
         const unsigned long long launches0 = env->launches;
