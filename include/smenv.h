@@ -433,7 +433,7 @@ int smenv_kernel_times(SmEnv* env, double* ms_out /* SM_K_COUNT */, int* steps_o
 /*
  * Networks in the step loop (safe_motions_base.py:1498-1603, actions.py:303-340): batched inference on the tensor
  * cores.  which: SM_NET_RISK = risk(obs, action) -> [0, 1]; SM_NET_BACKUP = backup policy, obs -> action mean.
- * dims = { n_in, N_1 .. N_n_tc, n_out }: n_tc hidden Dense layers (widths multiples of 16, at most 256, or 512) and
+ * dims = { n_in, N_1 .. N_n_tc, n_out }: n_tc hidden Dense layers (widths 16, 32, 48, 64, 128, 192, 256 or 512) and
  * one output Dense layer (n_out <= 16; SM_NET_HUMAN: the human's stochastic policy, means and log-std outputs,
  * ctlp.py:4647-4762).  weights (host, float32, Keras layout): per layer kernel [in][out] row-major
  * followed by its bias.  hidden_act: 0 selu, 1 swish; out_act: 0 sigmoid, 1 tanh.

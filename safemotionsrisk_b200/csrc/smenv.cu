@@ -1940,8 +1940,9 @@ extern "C" int smenv_mlp_load(SmEnv* env, int which, int n_tc, const int32_t* di
         return fail(SM_ERR_ARG, "smenv_mlp_load: last hidden width x padded output width exceeds 2048");
     for (int l = 0; l < n_tc; ++l) {
         const int N = dims[1 + l];
-        if (N % 16 != 0 || N < 16 || (N > 256 && N != 512))
-            return fail(SM_ERR_ARG, "smenv_mlp_load: hidden widths must be multiples of 16, at most 256, or 512");
+        // a layer's width is the K of the next one, streamed in chunks of 64 columns: 16, 32, 48 or a multiple of 64
+        if (N % 16 != 0 || N < 16 || (N > 64 && N % 64 != 0) || (N > 256 && N != 512))
+            return fail(SM_ERR_ARG, "smenv_mlp_load: hidden widths must be 16, 32, 48, 64, 128, 192, 256 or 512");
     }
     if (dims[n_tc] > MLP_MAX_LAST) return fail(SM_ERR_ARG, "smenv_mlp_load: the last hidden layer may be at most 256 wide");
     CU(cudaSetDevice(env->device));

@@ -283,7 +283,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(MlpArgs A) {
             // the tensor memory hides behind the arithmetic)
             {
                 const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16);
-                const int cbeg = half * (N / MLP_PARTS), cend = (half + 1) * (N / MLP_PARTS);
+                // blocks of 16 columns; this thread takes blocks half, half + MLP_PARTS, ... (any width that is a multiple of
+                // 16: narrow layers leave some of the four column groups idle)
+                const int nblk = N / 16;
                 const int hidden_act = net.hidden_act, n_out = net.n_out;
                 auto process16 = [&](const uint32_t* u, int c) {
                     float r[16];
@@ -322,16 +324,21 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(MlpArgs A) {
                     }
                 };
                 uint32_t ua[16], ub[16];
-                tmem_ld16_issue(tbase + (uint32_t)cbeg, ua);
-                tmem_wait16(ua);
+                if (half < nblk) {
+                    tmem_ld16_issue(tbase + (uint32_t)(half * 16), ua);
+                    tmem_wait16(ua);
+                }
 #pragma unroll 1
-                for (int c0 = cbeg; c0 < cend; c0 += 32) {
-                    tmem_ld16_issue(tbase + (uint32_t)(c0 + 16), ub);
-                    process16(ua, c0);
-                    tmem_wait16(ub);
-                    if (c0 + 32 < cend) tmem_ld16_issue(tbase + (uint32_t)(c0 + 32), ua);
-                    process16(ub, c0 + 16);
-                    if (c0 + 32 < cend) tmem_wait16(ua);
+                for (int bi = half; bi < nblk; bi += 2 * MLP_PARTS) {
+                    const bool second = bi + MLP_PARTS < nblk, third = bi + 2 * MLP_PARTS < nblk;
+                    if (second) tmem_ld16_issue(tbase + (uint32_t)((bi + MLP_PARTS) * 16), ub);
+                    process16(ua, bi * 16);
+                    if (second) {
+                        tmem_wait16(ub);
+                        if (third) tmem_ld16_issue(tbase + (uint32_t)((bi + 2 * MLP_PARTS) * 16), ua);
+                        process16(ub, (bi + MLP_PARTS) * 16);
+                        if (third) tmem_wait16(ua);
+                    }
                 }
             }
             tc_fence_before();

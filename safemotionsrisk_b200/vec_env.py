@@ -178,6 +178,9 @@ class SafeMotionsVecEnv:
         state_action/<scene>, README.md:223-235) -> the packaged export of that scene's networks, or an .npz path."""
         if str(path).endswith(".npz") and os.path.isfile(path):
             return path
+        trained = os.path.join(str(path), "risk_network.npz")   # a directory written by safemotionsrisk_b200.risk_train
+        if os.path.isfile(trained):
+            return trained
         name = os.path.basename(os.path.normpath(str(path)))
         packaged = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets", "networks_{}.npz".format(name))
         if name in ("space", "ball", "human") and os.path.isfile(packaged):
@@ -584,14 +587,30 @@ class SafeMotionsVecEnv:
                                   "networks_{}.npz".format(scene))
         w = np.load(source)
         nj = self.scene.n_joints
-        risk = [(w["risk/dense_{}/kernel".format(i)], w["risk/dense_{}/bias".format(i)]) for i in range(4)]
-        pol = [(w["backup/{}/kernel".format(n)], w["backup/{}/bias".format(n)]) for n in ("fc_1", "fc_2", "fc_out")]
+        n_risk = len([k for k in w.files if k.startswith("risk/") and k.endswith("/kernel")])
+        if not 2 <= n_risk <= 4:
+            raise ValueError("{}: the risk network needs 1 to 3 hidden layers and an output layer".format(source))
+        risk = [(w["risk/dense_{}/kernel".format(i)], w["risk/dense_{}/bias".format(i)]) for i in range(n_risk)]
+        if "backup/fc_1/kernel" not in w.files:   # a risk network trained here (risk_train.py): the backup policy is the
+            packaged = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets", "networks_{}.npz".format(   # scene's
+                "human" if self.has_human else "ball" if self.config.use_moving_objects else "space"))
+            wp = np.load(packaged)
+        else:
+            wp = w
+        pol = [(wp["backup/{}/kernel".format(n)], wp["backup/{}/bias".format(n)]) for n in ("fc_1", "fc_2", "fc_out")]
         pol[-1] = (pol[-1][0][:, :nj], pol[-1][1][:nj])  # deterministic action = the mean head
         risk_obs = self.scene.obs_size - self.scene.obs_target_size   # without the target-point entries
         if risk[0][0].shape[0] != risk_obs + nj or pol[0][0].shape[0] != risk_obs:
             raise ValueError("networks expect a risk observation of size {}, the env produces {}".format(
                 pol[0][0].shape[0], risk_obs))
-        for which, layers, hidden, out_act in ((0, risk, 0, 0), (1, pol, 1, 1)):
+        risk_hidden = 0
+        if "risk/hidden_layer_activation" in w.files:   # written by risk_train.export_weights
+            act, last = str(w["risk/hidden_layer_activation"]), str(w["risk/last_layer_activation"])
+            if act not in ("selu", "swish") or last != "sigmoid":
+                raise ValueError("{}: the step loop runs selu or swish hidden layers and a sigmoid output, not {} / {}".format(
+                    source, act, last))
+            risk_hidden = 0 if act == "selu" else 1
+        for which, layers, hidden, out_act in ((0, risk, risk_hidden, 0), (1, pol, 1, 1)):
             dims = np.array([layers[0][0].shape[0]] + [k.shape[1] for k, _ in layers], dtype=np.int32)
             flat = np.concatenate([np.concatenate([k.astype(np.float32).ravel(), b.astype(np.float32).ravel()])
                                    for k, b in layers])

@@ -913,3 +913,29 @@ def test_scene_variants_match_oracle(variant):
         alive &= o_done == 0
     assert mism <= 1
     env.close()
+
+
+@pytest.mark.parametrize("hidden", [[512, 256, 128], [256, 128], [128, 64], [64, 64], [128, 64, 32], [32, 16], [192, 48]])
+def test_tensor_core_mlp_layer_widths(hidden):
+    """mlp_kernel for every supported layer shape (a network trained by risk_train.py need not have the shipped 512 /
+    256 / 128 widths) against a NumPy float32 forward pass; unsupported widths are refused, not mis-computed."""
+    from oracle import mlp
+    env = make_env("space_bm", 1024, fill_pools=False)
+    rng = np.random.default_rng(len(hidden) * 1000 + hidden[0])
+    x = rng.uniform(-1, 1, (1024, 30)).astype(np.float32)
+    dims = [30] + hidden + [1]
+    layers = [(rng.normal(0, 1.0 / np.sqrt(dims[i]), (dims[i], dims[i + 1])).astype(np.float32),
+               rng.normal(0, 0.1, dims[i + 1]).astype(np.float32)) for i in range(len(dims) - 1)]
+    flat = np.concatenate([np.concatenate([k.ravel(), b.ravel()]) for k, b in layers])
+    d = np.array(dims, dtype=np.int32)
+    cabi.check(env._lib.smenv_mlp_load(env._handle, 0, len(hidden), d.ctypes.data, 0, 0, flat.ctypes.data), "smenv_mlp_load")
+    h = x
+    for k, b in layers[:-1]:
+        h = mlp.selu(h @ k + b)
+    want = (1 / (1 + np.exp(-(h @ layers[-1][0] + layers[-1][1]))))[:, 0]
+    got = env.mlp_forward(0, x[:, :23], x[:, 23:])[:, 0].cpu().numpy()
+    exact = env.mlp_forward_exact(0, x[:, :23], x[:, 23:])[:, 0].cpu().numpy()
+    assert np.abs(got - want).max() < 2e-3 and np.abs(exact - want).max() < 2e-6
+    bad = np.array([30, 96, 64, 1], dtype=np.int32)
+    assert env._lib.smenv_mlp_load(env._handle, 0, 2, bad.ctypes.data, 0, 0, flat.ctypes.data) != 0
+    env.close()
