@@ -659,6 +659,38 @@ def test_host_step_in_ranges_equals_the_device_step(scene):
         e.close()
 
 
+@pytest.mark.parametrize("scene,threshold", [("space_bm", 0.065), ("human", 0.06)])
+def test_gated_host_step_equals_the_gated_device_step(scene, threshold):
+    """The risk gate inside the host-buffer step (CUDA graph replay, ranges on separate streams) decides and acts exactly
+    like the gate inside the device step: same risky flags, executed actions, states and outputs."""
+    n = 1000
+    envs = [make_env(scene, n, auto_reset=True) for _ in range(3)]
+    for e in envs:
+        e.load_networks()
+        e.set_risk_gate(threshold)
+        e.reset()
+    ref, host2, host3 = envs
+    ref.set_step_ranges(1)
+    rng = np.random.default_rng(17)
+    risky_total = 0
+    for step in range(25):
+        act = rng.uniform(-1, 1, (n, 7)).astype(np.float32)
+        ref.step(torch.from_numpy(act).cuda())
+        torch.cuda.synchronize()
+        want = (ref.obs.cpu().numpy(), ref.reward.cpu().numpy(), ref.done.cpu().numpy())
+        for e, c in ((host2, 2), (host3, 3)):
+            got = e.step_host(act, chunks=c)
+            for w, g in zip(want, got):
+                assert np.array_equal(w, g), (scene, c, step)
+            assert torch.equal(e.kin, ref.kin) and torch.equal(e.info[:, 16], ref.info[:, 16]), (scene, c, step)
+            if scene == "human":
+                assert torch.equal(e.hkin, ref.hkin)
+        risky_total += int(ref.info[:, 16].sum())
+    assert 0 < risky_total < 25 * n
+    for e in envs:
+        e.close()
+
+
 # ---------------------------------------------------------------------------------------------- round 2: gate wiring
 
 def test_gate_inside_step_keeps_the_proposed_action_for_the_reward():
