@@ -253,3 +253,26 @@ def test_human_full_size_invariants():
     stats = env.episode_statistics().cpu().numpy()
     assert stats[0] == total_done
     env.close()
+
+
+def test_human_backup_look_ahead_restores_the_nested_env():
+    """risk_ground_truth in the Human scene: the look-ahead (robot under its backup policy, human under its own policy)
+    runs on a copy; afterwards both envs are bit for bit where they were, and the labels separate risky from safe rows."""
+    n = 2048
+    env = make_env(n, auto_reset=True)
+    env.load_networks()
+    env.reset()
+    for _ in range(3):
+        env.step_random()
+    before = {k: v.clone() for k, v in env.snapshot().items()}
+    assert {"hkin", "hstate", "hbrake", "hobs"} <= set(before)
+    act = np.random.default_rng(4).uniform(-1, 1, (n, 7)).astype(np.float32)
+    state, a, risk = env.risk_ground_truth(act, 20)
+    after = env.snapshot()
+    for k in before:
+        assert torch.equal(before[k], after[k]) or (before[k].isnan() == after[k].isnan()).all(), k
+    assert state.shape == (n, 45) and 0.02 < float(risk.mean()) < 0.98
+    shipped = env.mlp_forward_exact(0, state, a)[:, 0].cpu().numpy()
+    r = risk.cpu().numpy() > 0.5
+    assert shipped[r].mean() > shipped[~r].mean()      # the shipped risk network rates the risky rows higher on average
+    env.close()
