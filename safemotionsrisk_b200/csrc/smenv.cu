@@ -308,6 +308,8 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
         for (int i = 0; i < 3; ++i) { d.jt[j][i] = (float)sc->joint_t[j][i]; d.jaxis[j][i] = (float)sc->joint_axis[j][i]; }
         d.pos_lo[j] = sc->pos_lo[j]; d.pos_hi[j] = sc->pos_hi[j]; d.vel_max[j] = sc->vel_max[j];
         d.acc_max[j] = sc->acc_max[j]; d.jerk_max[j] = sc->jerk_max[j];
+        d.lim.inv_jts[j] = sc->jerk_max[j] * sc->ts > 0.0 ? (1.0 / (sc->jerk_max[j] * sc->ts)) * (1.0 + 1e-12) : 0.0;
+        d.lim.inv_2a[j] = sc->acc_max[j] > 0.0 ? (1.0 / (2.0 * sc->acc_max[j])) * (1.0 + 1e-12) : 0.0;
     }
     d.ts = sc->ts; d.action_mapping_factor = sc->action_mapping_factor; d.track_kp = sc->track_kp;
     d.track_vel = sc->track_vel;
@@ -533,6 +535,8 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
             for (int i = 0; i < 3; ++i) { u.jt[j][i] = (float)h.joint_t[j][i]; u.jaxis[j][i] = (float)h.joint_axis[j][i]; }
             u.lim.pos_lo[j] = h.pos_lo[j]; u.lim.pos_hi[j] = h.pos_hi[j]; u.lim.vel_max[j] = h.vel_max[j];
             u.lim.acc_max[j] = h.acc_max[j]; u.lim.jerk_max[j] = h.jerk_max[j];
+            u.lim.inv_jts[j] = (1.0 / (h.jerk_max[j] * sc->ts)) * (1.0 + 1e-12);
+            u.lim.inv_2a[j] = (1.0 / (2.0 * h.acc_max[j])) * (1.0 + 1e-12);
         }
         u.brake_safety = h.brake_safety; u.brake_timeout = h.brake_timeout; u.tp_radius = h.tp_radius;
         u.log_std_lo = h.log_std_lo; u.log_std_hi = h.log_std_hi;

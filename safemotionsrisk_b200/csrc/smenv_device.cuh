@@ -67,6 +67,9 @@ __host__ __device__ __forceinline__ int lut_cell(float dx, float dy, float dz) {
 struct JointLim {
     double pos_lo[SM_MAX_JOINTS], pos_hi[SM_MAX_JOINTS], vel_max[SM_MAX_JOINTS], acc_max[SM_MAX_JOINTS],
         jerk_max[SM_MAX_JOINTS];
+    // 1 / (jerk_max ts) and 1 / (2 acc_max), rounded up: the conservative position-bound filter multiplies instead of
+    // dividing (pos_bound_inactive; a filter, not part of any result)
+    double inv_jts[SM_MAX_JOINTS], inv_2a[SM_MAX_JOINTS];
 };
 
 // the human obstacle (include/smenv.h SmHuman) as the kernels use it
@@ -385,14 +388,14 @@ __device__ __forceinline__ void clamp_range(double& lo, double& hi, double blo, 
 //                                                                              to hi guarantees the second term)
 //   then constant -A: stopping distance <= vp^2 / (2A)
 // Everything is rounded up by a 1e-6 rad slack; plain double arithmetic (this is a filter, not part of the result).
-__device__ __forceinline__ bool pos_bound_inactive(double p, double v, double a, double a1, double pmax, double J,
-                                                   double A, double V, double ts, bool vel_guaranteed) {
+__device__ __forceinline__ bool pos_bound_inactive(double p, double v, double a, double a1, double pmax, double inv_jts,
+                                                   double inv_2a, double A, double V, double ts, bool vel_guaranteed) {
     const double m0 = fmax(fmax(a, a1), 0.0), a1p = fmax(a1, 0.0), vp0 = fmax(v, 0.0);
-    const double n = ceil((a1p + A) / (J * ts)) + 1.0;
+    const double n = ceil((a1p + A) * inv_jts) + 1.0;    // inv_jts >= 1 / (J ts): n is not below the exact count
     double w = fmax(v + m0 * ts, 0.0) + a1p * n * ts;
     if (vel_guaranteed) w = fmin(w, 1.001 * V + 1e-6);
     w = fmax(w, vp0);
-    const double bound = p + vp0 * ts + 0.5 * m0 * ts * ts + w * n * ts + w * w / (2.0 * A);
+    const double bound = p + vp0 * ts + 0.5 * m0 * ts * ts + w * n * ts + w * w * inv_2a;
     return bound + 1e-6 < pmax;
 }
 
@@ -417,8 +420,8 @@ __device__ __forceinline__ void safe_range_light(const JointLim& L, int j, doubl
     need_pos = false;
     if (c_sc.limit_position) {
         const bool vg = c_sc.limit_velocity && code == 0 && fabs(v) <= V;
-        need_pos = !(pos_bound_inactive(p, v, a, hi, L.pos_hi[j], J, A, V, ts, vg) &&
-                     pos_bound_inactive(-p, -v, -a, -lo, -L.pos_lo[j], J, A, V, ts, vg));
+        need_pos = !(pos_bound_inactive(p, v, a, hi, L.pos_hi[j], L.inv_jts[j], L.inv_2a[j], A, V, ts, vg) &&
+                     pos_bound_inactive(-p, -v, -a, -lo, -L.pos_lo[j], L.inv_jts[j], L.inv_2a[j], A, V, ts, vg));
     }
 }
 __device__ __forceinline__ void safe_range_light(int j, double p, double v, double a, double& lo, double& hi, int& code,

@@ -109,9 +109,9 @@ __device__ __forceinline__ double human_braking_acceleration(const JointLim& L, 
     if (e > hi) e = hi;
     if (need_pos) {
         const double V = L.vel_max[j];
-        const bool ok_hi = pos_bound_inactive(p, v, a, e, L.pos_hi[j], J, Am, V, ts, false) ||
+        const bool ok_hi = pos_bound_inactive(p, v, a, e, L.pos_hi[j], L.inv_jts[j], L.inv_2a[j], Am, V, ts, false) ||
                            xsub(pos_peak(p, v, a, e, J, Am, ts), L.pos_hi[j]) <= 0.0;
-        const bool ok_lo = pos_bound_inactive(-p, -v, -a, -e, -L.pos_lo[j], J, Am, V, ts, false) ||
+        const bool ok_lo = pos_bound_inactive(-p, -v, -a, -e, -L.pos_lo[j], L.inv_jts[j], L.inv_2a[j], Am, V, ts, false) ||
                            xsub(pos_peak(-p, -v, -a, -e, J, Am, ts), -L.pos_lo[j]) <= 0.0;
         if (!(ok_hi && ok_lo)) {
             safe_range_joint(L, j, p, v, a, lo, hi, code);
@@ -560,7 +560,8 @@ __global__ void __launch_bounds__(256, 4) human_advance_kernel(HumanArgs A) {
     double a1 = A.range[(env * 8 + j) * 4 + 2];
     const int count = (int)hs[SM_HS_BRAKE_COUNT];
     int braked = 0, new_count = count;
-    if (c_sc.hu.check_braking) {
+    // `valid`: the lanes past the last env alias its record and must not shift its stored trajectory a second time
+    if (valid && c_sc.hu.check_braking) {
         const bool execute = A.res[env * SM_RES_STRIDE + GJK_BRAKE] != SM_RES_NO_CONTACT || bi[2] != 0;
         if (execute) {   // the stored braking trajectory is executed instead of the action
             braked = 1;
