@@ -471,6 +471,14 @@ int smenv_random_actions(SmEnv* env, const SmBuffers* buf, SmStream stream);
  * on all SMs): the denominators of bench.py's roofline for the vector-pipe-bound kernels. */
 int smenv_measure_fma_peaks(int device, double* tflops_fp32, double* tflops_fp64);
 
+/* Host-only (no GPU needed): the support-direction table the GJK kernel would use for a convex hull of n <= 255
+ * vertices (xyz, float32) at `res` cells per cube-map face edge (4, 8, 12 or 16).  Layout: cells[6 res res] = (word offset
+ * of the list << 8 | candidates), then the lists (vertex indices, one byte each).  Returns the number of words, or a
+ * negative status; out may be NULL to query the size.  smenv_debug_lut_cell is the cell of a direction.  Tests check
+ * that the true support vertex of every direction is among the candidates of its cell. */
+int smenv_debug_build_lut(const float* xyz, int n, int res, uint32_t* out, int capacity);
+int smenv_debug_lut_cell(float dx, float dy, float dz, int res);
+
 /* Debug: trace of one GJK call between shapes ia and ib for one env state given on the host (trace: 32 x 8 floats per
  * iteration = simplex size, |v|^2, v.w, support ids, v; result: distance, iterations, then the 9 robot frames). */
 int smenv_debug_gjk(SmEnv* env, const double* kin_host, const double* obst_host, int ia, int ib, float upper,

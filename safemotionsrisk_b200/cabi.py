@@ -53,6 +53,8 @@ def load():
     lib.smenv_set_gate_exact.argtypes = [vp, i32, C.c_float]
     lib.smenv_mlp_forward_exact.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, vp]
     lib.smenv_set_seed.argtypes = [vp, u64]
+    lib.smenv_debug_build_lut.argtypes = [vp, i32, i32, vp, i32]
+    lib.smenv_debug_lut_cell.argtypes = [C.c_float, C.c_float, C.c_float, i32]
     lib.smenv_set_risk_gate.argtypes = [vp, C.c_float]
     lib.smenv_random_actions.argtypes = [vp, C.POINTER(abi.SmBuffers), vp]
     lib.smenv_kernel_timing.argtypes = [vp, i32]

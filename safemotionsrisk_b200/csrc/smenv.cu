@@ -7,6 +7,7 @@
 #include <array>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "smenv_pools.cuh"
@@ -31,6 +32,11 @@ static int fail(int code, const std::string& msg) {
 // direction of the cell (a (SUB x SUB) grid that includes the cell border), its support value is within
 // diam * (distance to the nearest sample) of the maximum -- then it is listed for every direction of the cell it
 // could win.  Float rounding of lut_cell on the device at a cell border is covered by the same slack.
+// Two passes: a coarse grid (17 or 33 samples per cell edge) over all vertices gives a superset of the candidates; a
+// fine grid (1 / 512 of a face edge between samples, slack eight times smaller) over that superset alone thins it to nearly
+// the exact set.  The lists set the trip count of the support loop of a whole GJK warp (its longest list), so every
+// listed vertex that cannot win costs time in every step: 17 -> 9 candidates on average for an iiwa link.
+// SMENV_LUT_FINE=0 keeps the coarse pass only (experiments).
 // ------------------------------------------------------------------------------------------------------------------
 static void build_lut_uncached(const float4* v, int n, int R, std::vector<uint32_t>& out);
 
@@ -49,8 +55,37 @@ static void build_lut(const float4* v, int n, int R, std::vector<uint32_t>& out)
     out.insert(out.end(), it->second.begin(), it->second.end());
 }
 
+// marks in `take` the vertices of `cand` (all n vertices if cand is NULL) that come within `slack` of the maximum for some
+// sample direction of cell (face, iu, iw) on a SUB x SUB grid
+static void lut_cell_pass(const float4* v, int n, const unsigned char* cand, int n_cand, int R, int face, int iu, int iw,
+                          int SUB, double slack, std::vector<char>& take) {
+    const int ax = face / 2, a = (ax + 1) % 3, b = (ax + 2) % 3;
+    const double sgn = (face % 2 == 0) ? 1.0 : -1.0;
+    const int m = cand ? n_cand : n;
+    std::vector<double> dots(m);
+    for (int su = 0; su < SUB; ++su)
+        for (int sw = 0; sw < SUB; ++sw) {
+            double d[3];
+            d[ax] = sgn;
+            d[a] = -1.0 + 2.0 * (iu + (double)su / (SUB - 1)) / R;
+            d[b] = -1.0 + 2.0 * (iw + (double)sw / (SUB - 1)) / R;
+            const double inv = 1.0 / sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            const double dx = d[0] * inv, dy = d[1] * inv, dz = d[2] * inv;
+            double mx = -1e300;
+            for (int k = 0; k < m; ++k) {
+                const float4& p = v[cand ? cand[k] : k];
+                dots[k] = p.x * dx + p.y * dy + p.z * dz;
+                if (dots[k] > mx) mx = dots[k];
+            }
+            for (int k = 0; k < m; ++k)
+                if (mx - dots[k] <= slack) take[cand ? cand[k] : k] = 1;
+        }
+}
+
 static void build_lut_uncached(const float4* v, int n, int R, std::vector<uint32_t>& out) {
     const int SUB = R >= 8 ? 17 : 33, cells = 6 * R * R;   // the same sample density on the sphere for coarse cells
+    static const bool fine = !(getenv("SMENV_LUT_FINE") && atoi(getenv("SMENV_LUT_FINE")) == 0);
+    const int SUB_FINE = 1 + 1024 / R;
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     for (int i = 0; i < n; ++i) {
         const float p[3] = {v[i].x, v[i].y, v[i].z};
@@ -58,36 +93,36 @@ static void build_lut_uncached(const float4* v, int n, int R, std::vector<uint32
     }
     const double diam = sqrt((double)(hi[0] - lo[0]) * (hi[0] - lo[0]) + (double)(hi[1] - lo[1]) * (hi[1] - lo[1]) +
                              (double)(hi[2] - lo[2]) * (hi[2] - lo[2]));
-    const double spacing = 2.0 / R / (SUB - 1);            // on the cube face; the chord on the sphere is shorter
-    const double slack = diam * spacing * 0.7072 * 1.05 + 1e-7;
+    // spacing on the cube face; the chord on the sphere is shorter
+    auto slack_of = [&](int sub) { return diam * (2.0 / R / (sub - 1)) * 0.7072 * 1.05 + 1e-7; };
     std::vector<std::vector<unsigned char>> lists(cells);
-    std::vector<double> dots(n);
-    std::vector<char> take(n);
-    for (int face = 0; face < 6; ++face) {
-        const int ax = face / 2, a = (ax + 1) % 3, b = (ax + 2) % 3;
-        const double sgn = (face % 2 == 0) ? 1.0 : -1.0;
-        for (int iu = 0; iu < R; ++iu)
-            for (int iw = 0; iw < R; ++iw) {
-                std::fill(take.begin(), take.end(), 0);
-                for (int su = 0; su < SUB; ++su)
-                    for (int sw = 0; sw < SUB; ++sw) {
-                        double d[3];
-                        d[ax] = sgn;
-                        d[a] = -1.0 + 2.0 * (iu + (double)su / (SUB - 1)) / R;
-                        d[b] = -1.0 + 2.0 * (iw + (double)sw / (SUB - 1)) / R;
-                        const double nrm = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-                        double mx = -1e300;
-                        for (int i = 0; i < n; ++i) {
-                            dots[i] = (v[i].x * d[0] + v[i].y * d[1] + v[i].z * d[2]) / nrm;
-                            if (dots[i] > mx) mx = dots[i];
-                        }
-                        for (int i = 0; i < n; ++i)
-                            if (mx - dots[i] <= slack) take[i] = 1;
-                    }
-                std::vector<unsigned char>& L = lists[(face * R + iu) * R + iw];
+    auto do_cells = [&](int c0, int c1) {
+        std::vector<char> take(n), take2(n);
+        std::vector<unsigned char> sup;
+        for (int c = c0; c < c1; ++c) {
+            const int face = c / (R * R), iu = (c / R) % R, iw = c % R;
+            std::fill(take.begin(), take.end(), 0);
+            lut_cell_pass(v, n, nullptr, 0, R, face, iu, iw, SUB, slack_of(SUB), take);
+            if (fine) {
+                sup.clear();
                 for (int i = 0; i < n; ++i)
-                    if (take[i]) L.push_back((unsigned char)i);
+                    if (take[i]) sup.push_back((unsigned char)i);
+                std::fill(take2.begin(), take2.end(), 0);
+                lut_cell_pass(v, n, sup.data(), (int)sup.size(), R, face, iu, iw, SUB_FINE, slack_of(SUB_FINE), take2);
+                take.swap(take2);
             }
+            std::vector<unsigned char>& L = lists[c];
+            for (int i = 0; i < n; ++i)
+                if (take[i]) L.push_back((unsigned char)i);
+        }
+    };
+    {   // cells are independent: a few host threads (the tables of a scene are built once per process)
+        unsigned nt = std::thread::hardware_concurrency();
+        nt = nt < 1 ? 1 : nt > 16 ? 16 : nt;
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t)
+            th.emplace_back(do_cells, (int)((long long)cells * t / nt), (int)((long long)cells * (t + 1) / nt));
+        for (auto& x : th) x.join();
     }
     const size_t base = out.size();
     out.resize(base + cells);
@@ -354,30 +389,51 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
         }
         g.lut = -1;
     }
-    // support-direction tables for the hulls that profit most (many vertices), as long as the GJK kernel's shared-memory
-    // image (vertices + tables + shapes) fits into an SM: the threshold doubles until it does (Human scene: 50 shapes,
-    // 4000 vertices -> tables only for the robot links)
-    // Which hulls get a table, and how fine: every hull of at least 33 vertices with 8 x 8 cells per cube face if that
-    // fits into 200 KB of shared memory next to the vertices; else coarse 4 x 4 tables for the hulls of up to 64 vertices
-    // (Human scene: 40 human parts); else only the big hulls.  SMENV_LUT_CONFIG=<k> forces configuration k (experiments).
-    static const int lut_configs[5][2] = {{33, 8}, {33, 4}, {65, 8}, {129, 8}, {256, 8}};   // min vertices, cells of small hulls
-    const int forced_cfg = getenv("SMENV_LUT_CONFIG") ? atoi(getenv("SMENV_LUT_CONFIG")) : -1;
-    for (int ci = forced_cfg >= 0 && forced_cfg < 5 ? forced_cfg : 0; ci < 5; ++ci) {
-        const int min_verts = lut_configs[ci][0], small_res = lut_configs[ci][1];
+    // Support-direction tables.  The longest candidate list among the lanes of a GJK warp sets the trip count of its
+    // support loop, so every hull that can have a table gets one as long as the kernel's shared-memory image (vertices +
+    // tables + shapes) fits.  Candidates in order of quality, the first that fits the budget wins:
+    //   hulls from 33 vertices with 8 x 8 cells per cube face, smaller hulls (from 8 vertices) with 4 x 4 -- then every lane
+    //   takes the table branch instead of the warp running a table loop and a full-scan loop one after the other;
+    //   the same without tables for the hulls below 33 vertices;
+    //   4 x 4 cells for all hulls up to 64 vertices (Human scene: 40 human parts), with / without the small hulls;
+    //   tables only from 65 / 129 / 256 vertices.
+    // Budget: 113 KB if some candidate of the first four fits (two 256-thread CTAs per SM, and a planning CTA of the other
+    // env range still finds room next to them), else 220 KB (one 768-thread CTA).  Measured (r03e): finer cells for the
+    // big hulls (12 or 16 per edge) shorten the lists further but cost the second CTA or the co-resident planning CTA and
+    // lose: space_bm 661 us per step with 8 cells in 111 KB, 672 / 674 with 16 / 12 cells; Ball 388 (77 KB) against 402.
+    // SMENV_LUT_BUDGET_KB, SMENV_LUT_BIG_RES, SMENV_LUT_TINY_MIN, SMENV_LUT_CONFIG override (experiments).
+    auto build_tables = [&](int min_verts, int small_res, int tiny_min, int big_res) {
         lut.clear();
         for (int s = 0; s < sc->n_shapes; ++s) {
             const SmShape& h = sc->shapes[s];
             d.shapes[s].lut = -1;
-            if (h.vert_cnt >= min_verts && h.vert_cnt <= 255) {
-                const int R = h.vert_cnt <= 64 ? small_res : SM_LUT_RES;
-                d.shapes[s].lut = (int)lut.size() | (R == SM_LUT_RES ? 0 : SM_LUT_COARSE);
+            const bool tiny = h.vert_cnt < min_verts && h.vert_cnt >= tiny_min;
+            if ((h.vert_cnt >= min_verts || tiny) && h.vert_cnt <= 255) {
+                const int R = tiny ? SM_LUT_RES_COARSE : h.vert_cnt <= 64 ? small_res : big_res;
+                d.shapes[s].lut = (int)lut.size() | (lut_code_of(R) << SM_LUT_RES_SHIFT);
                 build_lut(verts.data() + h.vert_off, h.vert_cnt, R, lut);
             }
         }
-        // measured (profiles/r02_gjk_config_sweep.txt, space_bm): a support query through a table (~15 candidates) instead of
-        // a scan of all 64 vertices is worth more than a second resident CTA -- the kernel runs as two 256-thread CTAs per
-        // SM up to 112 KB, else as one 512-thread CTA (sixteen warps per SM either way)
-        if (gjk_smem_bytes(sc->n_verts, (int)lut.size() + 4, sc->n_shapes) <= 200 * 1024 || ci == 4) break;
+        return gjk_smem_bytes(sc->n_verts, (int)lut.size() + 4, sc->n_shapes);
+    };
+    {
+        const int forced_budget = getenv("SMENV_LUT_BUDGET_KB") ? atoi(getenv("SMENV_LUT_BUDGET_KB")) : 0;
+        const int forced_cfg = getenv("SMENV_LUT_CONFIG") ? atoi(getenv("SMENV_LUT_CONFIG")) : -1;
+        const int big = getenv("SMENV_LUT_BIG_RES") ? atoi(getenv("SMENV_LUT_BIG_RES")) : SM_LUT_RES;
+        const int tiny_min = getenv("SMENV_LUT_TINY_MIN") ? atoi(getenv("SMENV_LUT_TINY_MIN")) : 8;
+        const int none = 1 << 30, n_cand = 7;
+        // min vertices, cells of hulls up to 64 vertices, smallest hull with a coarse table
+        const int cand[n_cand][3] = {{33, 8, tiny_min}, {33, 8, none}, {33, 4, tiny_min}, {33, 4, none},
+                                     {65, 8, none}, {129, 8, none}, {256, 8, none}};
+        bool placed = false;
+        for (int pass = 0; pass < 2 && !placed; ++pass) {
+            const size_t budget = (size_t)(forced_budget ? forced_budget : pass == 0 ? 113 : 220) * 1024;
+            for (int ci = 0; ci < (pass == 0 ? 4 : n_cand) && !placed; ++ci) {
+                if (forced_cfg >= 0 && ci != forced_cfg) continue;
+                placed = build_tables(cand[ci][0], cand[ci][1], cand[ci][2], big) <= budget;
+            }
+        }
+        if (!placed) build_tables(cand[n_cand - 1][0], cand[n_cand - 1][1], cand[n_cand - 1][2], SM_LUT_RES);
     }
     d.n_static_pairs = sc->n_static_pairs; d.n_self_pairs = sc->n_self_pairs;
     d.n_mov_reward = sc->n_mov_reward; d.n_mov_contact = sc->n_mov_contact;
@@ -924,6 +980,8 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
             CU(cudaFuncSetAttribute(gjk_kernel<true, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_gjk));
             CU(cudaFuncSetAttribute(gjk_kernel<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_gjk));
             CU(cudaFuncSetAttribute(gjk_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_gjk));
+            CU(cudaFuncSetAttribute(gjk_kernel<false, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_gjk));
+            CU(cudaFuncSetAttribute(gjk_kernel<true, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_gjk));
             lim_gjk = env->smem_bytes_gjk;
         }
         if (env->smem_bytes > lim_geom) {
@@ -963,6 +1021,7 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
         int fit = 0;
         if (t == 768) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, gjk_kernel<false, 768>, 768, env->smem_bytes_gjk));
         if (t == 1024) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, gjk_kernel<false, 1024>, 1024, env->smem_bytes_gjk));
+        if (t == 384) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, gjk_kernel<false, 384>, 384, env->smem_bytes_gjk));
         if (fit >= 1) { env->gjk_threads = t; per_sm = fit; }
     }
     env->grid_gjk = sms * per_sm;
@@ -1409,6 +1468,9 @@ static void launch_gjk(SmEnv* env, const GjkArgs& G, cudaStream_t stream) {
     } else if (env->gjk_threads == 512) {
         if (env->count) gjk_kernel<true, 512><<<env->grid_gjk, 512, env->smem_bytes_gjk, stream>>>(G);
         else gjk_kernel<false, 512><<<env->grid_gjk, 512, env->smem_bytes_gjk, stream>>>(G);
+    } else if (env->gjk_threads == 384) {
+        if (env->count) gjk_kernel<true, 384><<<env->grid_gjk, 384, env->smem_bytes_gjk, stream>>>(G);
+        else gjk_kernel<false, 384><<<env->grid_gjk, 384, env->smem_bytes_gjk, stream>>>(G);
     } else {
         if (env->count) gjk_kernel<true><<<env->grid_gjk, GJK_THREADS, env->smem_bytes_gjk, stream>>>(G);
         else gjk_kernel<false><<<env->grid_gjk, GJK_THREADS, env->smem_bytes_gjk, stream>>>(G);
@@ -2119,6 +2181,21 @@ extern "C" int smenv_launch_count(SmEnv* env, unsigned long long* out) {
 }
 
 // debug: trace one GJK call on the device (not part of the product path; used by tools/ and tests to explain parity)
+extern "C" int smenv_debug_build_lut(const float* xyz, int n, int res, uint32_t* out, int capacity) {
+    if (!xyz || n < 1 || n > 255) return fail(SM_ERR_ARG, "smenv_debug_build_lut: 1 .. 255 vertices");
+    if (res != 4 && res != 8 && res != 12 && res != 16) return fail(SM_ERR_ARG, "smenv_debug_build_lut: res is 4, 8, 12 or 16");
+    std::vector<float4> v(n);
+    for (int i = 0; i < n; ++i) v[i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.f);
+    std::vector<uint32_t> t;
+    build_lut(v.data(), n, res, t);
+    if (out) {
+        if ((int)t.size() > capacity) return fail(SM_ERR_ARG, "smenv_debug_build_lut: buffer too small");
+        memcpy(out, t.data(), t.size() * sizeof(uint32_t));
+    }
+    return (int)t.size();
+}
+extern "C" int smenv_debug_lut_cell(float dx, float dy, float dz, int res) { return lut_cell_res(dx, dy, dz, res); }
+
 extern "C" int smenv_debug_gjk(SmEnv* env, const double* kin_host, const double* obst_host, int ia, int ib, float upper,
                                float* trace_host /* 32 x 8 */, float* result_host /* 4 + 12 * 9 */) {
     if (!env || !kin_host || !obst_host || !trace_host || !result_host) return fail(SM_ERR_ARG, "null argument");

@@ -58,10 +58,17 @@ __host__ __device__ __forceinline__ int lut_cell_res(float dx, float dy, float d
     return (face * res + iu) * res + iw;
 }
 __host__ __device__ __forceinline__ int lut_cell(float dx, float dy, float dz) { return lut_cell_res(dx, dy, dz, SM_LUT_RES); }
-// DevShape.lut: word offset of the table | SM_LUT_COARSE if the table has SM_LUT_RES_COARSE^2 cells per face (small
-// hulls of scenes whose tables would not fit into shared memory otherwise)
-#define SM_LUT_COARSE 0x40000000
+// DevShape.lut: word offset of the table | resolution code << 29: the cells per cube-map face edge are 8 (code 0), 4 (1:
+// small hulls), 12 (2) or 16 (3: big hulls of scenes whose tables fit into shared memory at that resolution)
+#define SM_LUT_RES_SHIFT 29
+#define SM_LUT_OFF_MASK 0x1fffffff
+#define SM_LUT_COARSE (1 << SM_LUT_RES_SHIFT)
 #define SM_LUT_RES_COARSE 4
+__host__ __device__ __forceinline__ int lut_res_of(int lut) {
+    const int code = (lut >> SM_LUT_RES_SHIFT) & 3;
+    return code == 0 ? SM_LUT_RES : code == 1 ? SM_LUT_RES_COARSE : code == 2 ? 12 : 16;
+}
+__host__ __device__ __forceinline__ int lut_code_of(int res) { return res == SM_LUT_RES ? 0 : res == SM_LUT_RES_COARSE ? 1 : res == 12 ? 2 : 3; }
 
 // limits of one set of joints: the robot's, or the human's (nested env, ctlp.py:4647-4959)
 struct JointLim {

@@ -79,8 +79,8 @@ __device__ __forceinline__ int support_thread(const float4* __restrict__ v, int 
     float best = -FLT_MAX;
     int bi = 0;
     if (lut_off >= 0) {
-        const uint32_t* L = lut + (lut_off & (SM_LUT_COARSE - 1));
-        const uint32_t e = L[lut_cell_res(d.x, d.y, d.z, (lut_off & SM_LUT_COARSE) ? SM_LUT_RES_COARSE : SM_LUT_RES)];
+        const uint32_t* L = lut + (lut_off & SM_LUT_OFF_MASK);
+        const uint32_t e = L[lut_cell_res(d.x, d.y, d.z, lut_res_of(lut_off))];
         const uint32_t* w = L + (e >> 8);
         const int cnt = (int)(e & 255u);
         ndots += (unsigned)cnt;
@@ -119,12 +119,15 @@ __device__ __forceinline__ int support_thread(const float4* __restrict__ v, int 
 #ifndef GJK_THREADS
 #define GJK_THREADS 256  /* threads per CTA */
 #endif
+#ifndef GJK_FIRST_PRUNE
+#define GJK_FIRST_PRUNE 1 /* the separating-plane bound is tested on the first direction (the line of centres) as well */
+#endif
 
 // THREADS: 256 with two CTAs per SM when the scene's shared-memory image (vertices + direction tables + shapes) allows
 // it (sixteen warps per SM at up to 128 registers), else one CTA per SM of 768 threads (24 warps, 80 registers; Human
 // scene: 4000 vertices; 512 and 1024 threads are kept for the sweep of tools/gjk_config_sweep.py)
 template <bool COUNT, int THREADS = GJK_THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS <= 256 ? GJK_MIN_BLOCKS : 1) gjk_kernel(GjkArgs A) {
+__global__ void __launch_bounds__(THREADS, THREADS <= 384 ? GJK_MIN_BLOCKS : 1) gjk_kernel(GjkArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int n_items = *A.n_items;
     if (n_items > A.capacity) n_items = A.capacity;
@@ -252,12 +255,23 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 256 ? GJK_MIN_BLOCKS : 1) 
                             pa.y - fmaf(r3, pb.x, fmaf(r4, pb.y, fmaf(r5, pb.z, ty))),
                             pa.z - fmaf(r6, pb.x, fmaf(r7, pb.y, fmaf(r8, pb.z, tz))));
             const int id = (sa << 16) | sb;
-            if (!have_point) {  // the first iteration only seeds the simplex with a real point of A - B
-                S.p0 = w; S.i0 = id; S.n = 1;
-                v = w; vv = dot(v, v);
-                have_point = true;
-                if (touch >= 0.0f && vv <= touch * touch) done = true;
-                if (vv <= 1e-20f) { vv = 0.0f; done = true; }
+            if (!have_point) {  // the first iteration seeds the simplex with a real point of A - B
+#if GJK_FIRST_PRUNE
+                // w minimises v . x over A - B for ANY direction v, so the separating-plane bound already holds for the
+                // line of centres: most pairs the planning could not decide with its table-based widths end here, after
+                // one support query instead of two (the lane reports nothing: its upper bound is above the limit too)
+                const float vw0 = dot(v, w);
+                if (vw0 > 0.0f && vw0 * vw0 >= lim * lim * vv * (1.0f + 4e-6f)) {
+                    done = true;
+                } else
+#endif
+                {
+                    S.p0 = w; S.i0 = id; S.n = 1;
+                    v = w; vv = dot(v, v);
+                    have_point = true;
+                    if (touch >= 0.0f && vv <= touch * touch) done = true;
+                    if (vv <= 1e-20f) { vv = 0.0f; done = true; }
+                }
             } else {
                 const float vw = dot(v, w);
                 const float nv = sqrtf(vv);
