@@ -11,7 +11,7 @@ python tools/step_time.py space space_bm ball human > $out/${tag}_step_time.txt 
 # launch list of the bench command itself (cold-cache, serialised per-launch times: shares, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $out/${tag}_launches_human.csv \
     python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --no-scenes > $out/${tag}_ncu_launches.log 2>&1
-for scene in human space_bm space ball; do
+for scene in ${SCENES:-human space_bm space ball}; do
   # one env range per step: every kernel appears once in the report
   SMENV_STEP_RANGES=1 ncu --profile-from-start off --set full --import-source on --clock-control none -f \
       -o /tmp/${tag}_step_${scene} python tools/profile_step.py $scene > $out/${tag}_ncu_${scene}.log 2>&1
