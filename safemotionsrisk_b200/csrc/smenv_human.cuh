@@ -123,7 +123,11 @@ __device__ __forceinline__ double human_braking_acceleration(const JointLim& L, 
     return e;
 }
 
-__global__ void __launch_bounds__(128) human_brake_traj_kernel(HumanArgs A) {
+#ifndef HBT_MIN_BLOCKS
+#define HBT_MIN_BLOCKS 8   /* resident CTAs per SM the register allocation aims for: 64 registers and 220 B of spill, but 32
+                              warps instead of 16 hide the FP64 latency chains (Human step 1547 -> 1483 us; 5, 6: no gain, 10, 12: worse) */
+#endif
+__global__ void __launch_bounds__(128, HBT_MIN_BLOCKS) human_brake_traj_kernel(HumanArgs A) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int env_raw = t >> 3, j = t & 7;
@@ -604,7 +608,11 @@ __global__ void __launch_bounds__(256, 4) human_advance_kernel(HumanArgs A) {
 // env, each clears a span of 3 sub-steps with one forward kinematics of both bodies; link spheres are inflated by what
 // the joints move inside the span.  Spans that cannot be cleared go to the fine planning (one lane per sub-step).
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) hcontact_coarse_kernel(HumanArgs A) {
+#ifndef HCC_MIN_BLOCKS
+#define HCC_MIN_BLOCKS 4   /* resident CTAs per SM the register allocation aims for: 64 registers instead of 75 (Human step
+                              1485 -> 1469 us) */
+#endif
+__global__ void __launch_bounds__(256, HCC_MIN_BLOCKS) hcontact_coarse_kernel(HumanArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SceneSmem* smp = reinterpret_cast<SceneSmem*>(smem_raw);
     for (int i = threadIdx.x; i < (int)(sizeof(SceneSmem) / 16); i += blockDim.x)
@@ -688,7 +696,10 @@ __global__ void __launch_bounds__(256) hcontact_coarse_kernel(HumanArgs A) {
 
 // fine contact planning over the listed spans: one lane per sub-step; robot link spheres against the human's link groups,
 // then against every part's sphere and box, then the separating-axis bound; survivors become contact items
-__global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32) hcontact_plan_kernel(HumanArgs A) {
+#ifndef HCP_MIN_BLOCKS
+#define HCP_MIN_BLOCKS 1   /* resident CTAs per SM the register allocation aims for (4: 64 registers, 1486 -> 1498 us: worse) */
+#endif
+__global__ void __launch_bounds__(SM_WARPS_PER_BLOCK * 32, HCP_MIN_BLOCKS) hcontact_plan_kernel(HumanArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n_units = A.cwork[0];
     const int span = (c_sc.substeps + SM_COARSE_LANES - 1) / SM_COARSE_LANES;

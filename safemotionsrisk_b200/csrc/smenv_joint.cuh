@@ -115,7 +115,10 @@ __device__ __forceinline__ float joint_advance(const JointArgs& A, double* kin, 
 // First pass: every (env, joint) whose position bounds are certainly inactive (the common case) is finished here;
 // the others are compacted into the `heavy` list so that the iterative solve runs with full warps afterwards
 // instead of stalling 31 idle lanes (the single-pass kernel averaged 5.6 active lanes per instruction).
-__global__ void __launch_bounds__(256) joint_kernel(JointArgs A) {
+#ifndef JK_MIN_BLOCKS
+#define JK_MIN_BLOCKS 1   /* resident CTAs per SM the register allocation aims for (4: 64 registers, no change: FP64-pipe bound) */
+#endif
+__global__ void __launch_bounds__(256, JK_MIN_BLOCKS) joint_kernel(JointArgs A) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int env = t >> 3, j = t & 7;

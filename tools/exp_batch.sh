@@ -1,8 +1,6 @@
 #!/bin/bash
 out=gpurun_out; tag=${1:-exp}
-run() { echo "== $*"; env "$@" python tools/step_time.py $scene; }
 {
-scene=space_bm; run SMENV_LUT_TINY_MIN=4; run SMENV_STEP_RANGES=3; run SMENV_STEP_RANGES=4
-scene=human; run SMENV_LUT_TINY_MIN=4; run SMENV_STEP_RANGES=3; run SMENV_LUT_CONFIG=2
-scene=space; run SMENV_LUT_TINY_MIN=4
+python tools/lib_compare.py human build/exp/base.so build/exp/hcp4.so build/exp/fin5.so build/exp/fin6.so build/exp/hcc4.so
+python tools/lib_compare.py space_bm build/exp/base.so build/exp/fin5.so build/exp/fin6.so
 } 2>&1 | tee $out/${tag}_cmp.txt
