@@ -501,7 +501,7 @@ def measure_scene(scene_name, args, dev, rank, world, local_rank, fma_peaks, ste
     uncull = {"space": 1.51e6, "space_bm": 1.71e6, "ball": 0.15e6, "ball_bm": 0.35e6, "space_task": 1.51e6,
               "space_task_bm": 1.71e6, "human": 3.6e6, "human_bm": 3.8e6}[scene_name]
     traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-    for tf in ("r02b_traffic.json", "r02_traffic.json", "r01_traffic.json"):
+    for tf in ("r02c_traffic.json", "r02b_traffic.json", "r02_traffic.json", "r01_traffic.json"):
         try:
             with open(os.path.join(ROOT, "profiles", tf)) as f:
                 traffic = json.load(f)["bytes_per_launch"].get(scene_name, {}).get(dom)
