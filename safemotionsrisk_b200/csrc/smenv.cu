@@ -85,7 +85,8 @@ static void lut_cell_pass(const float4* v, int n, const unsigned char* cand, int
 static void build_lut_uncached(const float4* v, int n, int R, std::vector<uint32_t>& out) {
     const int SUB = R >= 8 ? 17 : 33, cells = 6 * R * R;   // the same sample density on the sphere for coarse cells
     static const bool fine = !(getenv("SMENV_LUT_FINE") && atoi(getenv("SMENV_LUT_FINE")) == 0);
-    const int SUB_FINE = 1 + 1024 / R;
+    static const int fine_div = getenv("SMENV_LUT_FINE_DIV") ? atoi(getenv("SMENV_LUT_FINE_DIV")) : 1024;   // samples per face edge
+    const int SUB_FINE = 1 + fine_div / R;
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     for (int i = 0; i < n; ++i) {
         const float p[3] = {v[i].x, v[i].y, v[i].z};
