@@ -151,6 +151,26 @@ class ClockSampler:
                 "source": "nvidia-smi -lms 20 and NVML every 5 ms, samples inside the timed region"}
 
 
+def pcie_bandwidth(dev, nbytes, reps=10):
+    """GB/s of a pinned host <-> device copy of nbytes (the D2H block of one env range of the host-buffer step)."""
+    import torch
+    h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    out = {"bytes": int(nbytes)}
+    for name, src, dst in (("d2h", d, h), ("h2d", h, d)):
+        for _ in range(2):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            dst.copy_(src, non_blocking=True)
+        e.record()
+        torch.cuda.synchronize(dev)
+        out[name] = nbytes * reps / (s.elapsed_time(e) * 1e-3) / 1e9
+    return out
+
+
 def cpu_reference_run(scene_name, envs_per_thread, steps, warmup, threads, target_seconds=None):
     """Times the CPU oracle on `threads` host threads (ctypes releases the GIL); returns env-steps/s and a note.
     With target_seconds the number of timed steps is chosen from the duration of the warm-up steps so that the
@@ -584,6 +604,10 @@ def measure_scene(scene_name, args, dev, rank, world, local_rank, fma_peaks, ste
                "steps": k_e2e, "host_chunks": args.host_chunks,
                "api": "SafeMotionsVecEnv.step_host -> smenv_step_host (actions in the pinned host buffer, H2D, step, "
                       "D2H of obs / reward / done into pinned host buffers, all inside the timed region)"}
+        try:   # the pinned-copy bandwidth of this box at the size the step moves: what bounds the part of e2e the step cannot hide
+            e2e["pcie_gbs"] = pcie_bandwidth(dev, max(1 << 20, e2e["d2h_bytes_per_step"] // max(1, args.host_chunks)))
+        except Exception as ex:   # a measurement aid, never a reason to lose the line
+            e2e["pcie_gbs"] = {"error": str(ex)[:100]}
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only, bounded sample)
     cpu = None
