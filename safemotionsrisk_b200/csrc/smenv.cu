@@ -398,10 +398,10 @@ extern "C" int smenv_create(const SmScene* sc, int num_envs, int device, uint64_
     //   the same without tables for the hulls below 33 vertices;
     //   4 x 4 cells for all hulls up to 64 vertices (Human scene: 40 human parts), with / without the small hulls;
     //   tables only from 65 / 129 / 256 vertices.
-    // Budget: 113 KB if some candidate of the first four fits (two 256-thread CTAs per SM, and a planning CTA of the other
-    // env range still finds room next to them), else 220 KB (one 768-thread CTA).  Measured (r03e): finer cells for the
-    // big hulls (12 or 16 per edge) shorten the lists further but cost the second CTA or the co-resident planning CTA and
-    // lose: space_bm 661 us per step with 8 cells in 111 KB, 672 / 674 with 16 / 12 cells; Ball 388 (77 KB) against 402.
+    // Budget: 113 KB if some candidate of the first four fits (two 256-thread CTAs per SM), else 220 KB (one 768-thread
+    // CTA).  Measured (profiles/r02b_gjk_table_sweep.txt): finer cells for the big hulls (12 or 16 per edge) shorten the
+    // lists further but cost the second CTA, or the room a planning CTA of the other env range finds next to the pair,
+    // and lose: space_bm 661 us per step with 8 cells in 111 KB, 672 / 674 with 16 / 12 cells; Ball 388 (77 KB) against 402.
     // SMENV_LUT_BUDGET_KB, SMENV_LUT_BIG_RES, SMENV_LUT_TINY_MIN, SMENV_LUT_CONFIG override (experiments).
     auto build_tables = [&](int min_verts, int small_res, int tiny_min, int big_res) {
         lut.clear();
