@@ -552,7 +552,10 @@ __device__ __forceinline__ void human_outcome(const HumanArgs& A, size_t env, bo
 // adapt_action (ctlp.py:3055-3153) + get_braking_acceleration (:3000-3024), then the 24 setpoints and the tracked pose of
 // the human (Human.prepare_sim_step ctlp.py:4850-4860; robot_scene_base.py:789-837): thread = (env, joint); then the outcome
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 4) human_advance_kernel(HumanArgs A) {
+#ifndef HADV_MIN_BLOCKS
+#define HADV_MIN_BLOCKS 4   /* resident CTAs per SM the register allocation aims for (3, 5, 6: 1491 / 1482 / 1485 us against 1480) */
+#endif
+__global__ void __launch_bounds__(256, HADV_MIN_BLOCKS) human_advance_kernel(HumanArgs A) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int env_raw = t >> 3, j = t & 7;
     const bool valid = env_raw < A.n;
